@@ -1,0 +1,154 @@
+/*
+ * kofft_cuda.h -- C ABI of libkofft_cuda.so: the B200 (sm_100a) backend for the batched
+ * FFT / rfft / STFT hot path of okian/kofft.
+ *
+ * This is the boundary a `kofft-cuda` crate binds (`extern "C"`); its `CudaFftImpl`
+ * implements kofft's `FftImpl<f32>` trait on top of the host-pointer entry points and
+ * exposes the device-pointer batched entry points as inherent methods.  Every function
+ * cites the reference interface it replaces (paths relative to the kofft repository).
+ *
+ * Conventions
+ *  - Complex data is interleaved {re, im} f32 == `#[repr(C)] Complex<f32>` (src/num.rs:105-110).
+ *  - Return value: 0 = Ok; 1..6 = kofft's `FftError` variants in declaration order
+ *    (src/fft.rs:446-454); negative = -(cudaError_t) with text in kofft_cuda_last_error().
+ *  - Only power-of-two lengths run on the GPU.  Non-power-of-two lengths return
+ *    KOFFT_ERR_NON_POWER_OF_TWO_NO_STD (the reference's Bluestein path, src/fft.rs:1083-1132,
+ *    is outside this backend's scope).
+ *  - Host-pointer functions are synchronous and never retain the caller's pointers.
+ *    Device-pointer functions are stream-ordered on `stream` (NULL = the context's stream)
+ *    and return as soon as the work is enqueued.
+ *  - A context belongs to one device and is not thread-safe (the reference's
+ *    ScalarFftImpl is !Sync for the same reason, src/fft.rs:589-605).
+ *  - There is no CPU fallback: without a CUDA device kofft_cuda_create fails.
+ */
+#ifndef KOFFT_CUDA_H
+#define KOFFT_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* FftError, src/fft.rs:446-454 */
+#define KOFFT_OK 0
+#define KOFFT_ERR_EMPTY_INPUT 1
+#define KOFFT_ERR_NON_POWER_OF_TWO_NO_STD 2
+#define KOFFT_ERR_MISMATCHED_LENGTHS 3
+#define KOFFT_ERR_INVALID_STRIDE 4
+#define KOFFT_ERR_INVALID_HOP_SIZE 5
+#define KOFFT_ERR_INVALID_VALUE 6
+
+/* window kinds for kofft_cuda_window_host_f32 (src/window.rs:24-61) */
+#define KOFFT_WINDOW_HANN 0
+#define KOFFT_WINDOW_HAMMING 1
+#define KOFFT_WINDOW_BLACKMAN 2
+#define KOFFT_WINDOW_KAISER 3
+
+typedef struct kofft_cuda_ctx kofft_cuda_ctx;
+
+/* ---- context: the device twin of ScalarFftImpl + FftPlanner (src/fft.rs:332-445, 600-632) */
+int kofft_cuda_create(kofft_cuda_ctx **out, int device);
+void kofft_cuda_destroy(kofft_cuda_ctx *ctx);
+const char *kofft_cuda_last_error(void);
+int kofft_cuda_device(const kofft_cuda_ctx *ctx);
+void *kofft_cuda_stream(const kofft_cuda_ctx *ctx); /* cudaStream_t */
+int kofft_cuda_synchronize(kofft_cuda_ctx *ctx);
+/* exact != 0 (default): every product and sum rounded as in the reference -> bit-identical
+ * results.  exact == 0: packed FMUL2/FFMA2 butterflies (about 1e-7 relative difference). */
+int kofft_cuda_set_exact(kofft_cuda_ctx *ctx, int exact);
+int kofft_cuda_get_exact(const kofft_cuda_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+unsigned long long kofft_cuda_launch_count(const kofft_cuda_ctx *ctx);
+/* 0 = let the library size the grid (occupancy x SM count); otherwise cap the CTA count */
+int kofft_cuda_set_max_ctas(kofft_cuda_ctx *ctx, int max_ctas);
+
+/* ---- planner tables -------------------------------------------------------------------- */
+/* FftPlanner::get_twiddles (src/fft.rs:370-408): n/2 complex, f32 recurrence, bit-exact. */
+int kofft_cuda_twiddles_host_f32(size_t n, float *out);
+/* build_twiddle_table (src/rfft.rs:172-183): m complex; fma_mul selects the
+ * `target-feature=+fma` flavour of Complex::mul (src/num.rs:173-178). */
+int kofft_cuda_rfft_twiddles_host_f32(size_t m, float *out, int fma_mul);
+/* device-resident copies, created on first use, pointer-stable for the context's life
+ * (the reference's Arc<[Complex<T>]> cache, tests/rfft_twiddles.rs:13-15). */
+int kofft_cuda_get_twiddles(kofft_cuda_ctx *ctx, size_t n, const void **dev_ptr);
+int kofft_cuda_get_rfft_twiddles(kofft_cuda_ctx *ctx, size_t m, const void **dev_ptr);
+/* which Complex::mul flavour builds the rfft table (default 0 = default cargo build) */
+int kofft_cuda_set_rfft_table_fma(kofft_cuda_ctx *ctx, int fma_mul);
+/* hann / hamming / blackman / kaiser (src/window.rs:24-61); beta only for kaiser */
+int kofft_cuda_window_host_f32(int kind, size_t len, float beta, float *out);
+
+/* ---- device-pointer batched entry points ------------------------------------------------ */
+/* batch() / batch_inverse() over dense rows [batch][n] (src/fft.rs:2156-2175), each row one
+ * FftImpl::fft / ifft (src/fft.rs:1054-1174).  d_in == d_out is allowed. */
+int kofft_cuda_fft_c2c_f32(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch,
+                           int inverse, void *stream);
+/* fft_out_of_place_strided generalised to a batch (src/fft.rs:1260-1336): element e of row r
+ * is at d_in[r*in_dist + e*in_stride] (units: complex elements). */
+int kofft_cuda_fft_strided_f32(kofft_cuda_ctx *ctx, const void *d_in, size_t in_stride, size_t in_dist,
+                               void *d_out, size_t out_stride, size_t out_dist, size_t n, size_t batch,
+                               int inverse, void *stream);
+/* fft_split / ifft_split (src/fft.rs:1365-1439): SoA rows [batch][n]. */
+int kofft_cuda_fft_split_f32(kofft_cuda_ctx *ctx, const float *d_in_re, const float *d_in_im, float *d_out_re,
+                             float *d_out_im, size_t n, size_t batch, int inverse, void *stream);
+/* rfft_with_scratch per row (src/rfft.rs:425-465): in [batch][n] f32, out [batch][n/2+1] complex. */
+int kofft_cuda_rfft_f32(kofft_cuda_ctx *ctx, const float *d_in, void *d_out, size_t n, size_t batch,
+                        void *stream);
+/* irfft_with_scratch per row (src/rfft.rs:468-508): in [batch][n/2+1] complex, out [batch][n] f32. */
+int kofft_cuda_irfft_f32(kofft_cuda_ctx *ctx, const void *d_in, float *d_out, size_t n, size_t batch,
+                         void *stream);
+/* stft() per channel (src/stft.rs:76-105): signal [channels][len], window [win_len],
+ * frames [channels][nframes][win_len] complex; nframes >= ceil(len/hop). */
+int kofft_cuda_stft_f32(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, size_t channels,
+                        const float *d_window, size_t win_len, size_t hop, void *d_frames, size_t nframes,
+                        void *stream);
+/* istft() per channel (src/stft.rs:117-156): frames [channels][nframes][win_len] (left
+ * untouched), output [channels][out_len] is ACCUMULATED into as in the reference, d_norm
+ * (optional, [channels][out_len]) receives the reference's `scratch` (sum of window^2).
+ * zero_uncovered != 0 selects inverse_parallel's variant (src/stft.rs:335-341). */
+int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nframes, size_t channels,
+                         const float *d_window, size_t win_len, size_t hop, float *d_output, size_t out_len,
+                         float *d_norm, int zero_uncovered, void *stream);
+
+/* ---- host-pointer drop-ins: what `impl FftImpl<f32> for CudaFftImpl` calls ---------------- */
+/* FftImpl::fft / ifft (src/fft.rs:467-468): in place on n complex. */
+int kofft_cuda_fft_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, int inverse);
+/* batch() / batch_inverse() on dense rows (src/fft.rs:2156-2175). */
+int kofft_cuda_fft_batch_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, size_t batch, int inverse);
+/* FftImpl::fft_split / ifft_split (src/fft.rs:556-586, 1365-1439). */
+int kofft_cuda_fft_split_host_f32(kofft_cuda_ctx *ctx, float *re, size_t re_len, float *im, size_t im_len,
+                                  int inverse);
+/* FftImpl::fft_strided / ifft_strided (src/fft.rs:494-506, 1175-1199): input_len complex
+ * elements, n = scratch.len(). */
+int kofft_cuda_fft_strided_host_f32(kofft_cuda_ctx *ctx, float *input, size_t input_len, size_t stride,
+                                    size_t n, int inverse);
+/* FftImpl::fft_out_of_place_strided / ifft_... (src/fft.rs:508-522, 1260-1336). */
+int kofft_cuda_fft_out_of_place_strided_host_f32(kofft_cuda_ctx *ctx, const float *input, size_t input_len,
+                                                 size_t in_stride, float *output, size_t output_len,
+                                                 size_t out_stride, int inverse);
+/* RealFftImpl::rfft_with_scratch (src/rfft.rs:780-788): output_len must be n/2+1 and
+ * scratch_len >= n/2 (the scratch itself is not needed on the GPU; its length is checked
+ * so error behaviour matches). */
+int kofft_cuda_rfft_host_f32(kofft_cuda_ctx *ctx, const float *input, size_t n, float *output,
+                             size_t output_len, size_t scratch_len);
+int kofft_cuda_rfft_batch_host_f32(kofft_cuda_ctx *ctx, const float *input, size_t n, size_t batch,
+                                   float *output);
+/* RealFftImpl::irfft_with_scratch (src/rfft.rs:809-817). */
+int kofft_cuda_irfft_host_f32(kofft_cuda_ctx *ctx, const float *input, size_t input_len, float *output,
+                              size_t n, size_t scratch_len);
+int kofft_cuda_irfft_batch_host_f32(kofft_cuda_ctx *ctx, const float *input, size_t n, size_t batch,
+                                    float *output);
+/* stft() (src/stft.rs:76-105) with `output` flattened to [nframes][win_len] complex;
+ * channels > 1 processes [channels][len] -> [channels][nframes][win_len]. */
+int kofft_cuda_stft_host_f32(kofft_cuda_ctx *ctx, const float *signal, size_t len, size_t channels,
+                             const float *window, size_t win_len, size_t hop, float *frames, size_t nframes);
+/* istft() (src/stft.rs:117-156); scratch receives the window-power sums like the reference.
+ * zero_uncovered != 0: inverse_parallel semantics (scratch may then be NULL). */
+int kofft_cuda_istft_host_f32(kofft_cuda_ctx *ctx, const float *frames, size_t nframes, size_t channels,
+                              const float *window, size_t win_len, size_t hop, float *output, size_t out_len,
+                              float *scratch, size_t scratch_len, int zero_uncovered);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KOFFT_CUDA_H */

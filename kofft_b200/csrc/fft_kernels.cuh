@@ -1,0 +1,321 @@
+// fft_kernels.cuh -- the CTA body around fft_engine.cuh plus the I/O policies that fuse
+// kofft's per-call pre/post passes into the first load / last store of the transform:
+//   IoC2C      FftImpl::fft / ifft on contiguous rows        (src/fft.rs:1054-1174)
+//   IoGeneric  strided and split (SoA) entry points           (src/fft.rs:1175-1336, 1365-1439)
+//   IoStft     stft framing + windowing                        (src/stft.rs:91-102)
+//   IoIstft    istft: ifft + real*window                       (src/stft.rs:141-147)
+//   IoRfft     rfft pack + Hermitian twist                     (src/rfft.rs:444-463)
+//   IoIrfft    irfft untwist + unpack                          (src/rfft.rs:485-503)
+#pragma once
+#include "fft_engine.cuh"
+
+namespace kofft {
+
+#ifdef __CUDACC__
+#define KOFFT_LDG(p) __ldg(p)
+#define KOFFT_SYNC() __syncthreads()
+#else
+#define KOFFT_LDG(p) (*(p))
+#endif
+
+// ------------------------------------------------------------------------------------------
+// I/O policies.  load(row, i) returns element i of the length-N complex sequence fed to the
+// forward Stockham core for transform `row`; store(row, i, v) receives output bin i.
+// ------------------------------------------------------------------------------------------
+
+// ifft = conj -> fft -> conj, re*scale, im*scale  (src/fft.rs:1163-1172)
+template <bool INV>
+KHD float2 pre_conj(float2 v)
+{
+    if (INV) v.y = -v.y;
+    return v;
+}
+template <bool INV>
+KHD float2 post_conj_scale(float2 v, float scale)
+{
+    if (INV) {
+        v.y = -v.y;
+        v.x = mul_rn(v.x, scale);
+        v.y = mul_rn(v.y, scale);
+    }
+    return v;
+}
+
+template <bool INV>
+struct IoC2C {
+    static constexpr bool kEpilogueExchange = false;
+    const float2 *__restrict__ in;
+    float2 *__restrict__ out;
+    long n;
+    float scale; // 1/n, computed on the host as 1.0f / (float)n
+    KHD void init(int) {}
+    KHD float2 load(long row, int i) const { return pre_conj<INV>(KOFFT_LDG(in + row * n + i)); }
+    KHD void store(long row, int i, float2 v) const { out[row * n + i] = post_conj_scale<INV>(v, scale); }
+};
+
+// element e of row r lives at  re[r*row_stride + e*elem_stride]  (strides in floats);
+// interleaved data passes im = re + 1 and elem_stride = 2*stride.
+template <bool INV>
+struct IoGeneric {
+    static constexpr bool kEpilogueExchange = false;
+    const float *__restrict__ in_re;
+    const float *__restrict__ in_im;
+    float *__restrict__ out_re;
+    float *__restrict__ out_im;
+    long in_es, in_rs, out_es, out_rs;
+    float scale;
+    KHD void init(int) {}
+    KHD float2 load(long row, int i) const
+    {
+        long o = row * in_rs + (long)i * in_es;
+        return pre_conj<INV>(make_float2(KOFFT_LDG(in_re + o), KOFFT_LDG(in_im + o)));
+    }
+    KHD void store(long row, int i, float2 v) const
+    {
+        v = post_conj_scale<INV>(v, scale);
+        long o = row * out_rs + (long)i * out_es;
+        out_re[o] = v.x;
+        out_im[o] = v.y;
+    }
+};
+
+// stft: frame f of channel c, x[i] = signal[c][f*hop + i] * window[i], 0 past the end, imag 0
+struct IoStft {
+    static constexpr bool kEpilogueExchange = false;
+    const float *__restrict__ signal;
+    const float *__restrict__ window;
+    float2 *__restrict__ frames;
+    long len;     // samples per channel
+    long nframes; // frames per channel
+    long hop;
+    long n; // win_len
+    KHD void init(int) {}
+    KHD float2 load(long row, int i) const
+    {
+        long c = row / nframes, f = row - c * nframes;
+        long pos = f * hop + i;
+        float x = 0.0f;
+        if (pos < len) x = mul_rn(KOFFT_LDG(signal + c * len + pos), KOFFT_LDG(window + i));
+        return make_float2(x, 0.0f);
+    }
+    KHD void store(long row, int i, float2 v) const { frames[row * n + i] = v; }
+};
+
+// istft stage 1: time[row][i] = (ifft(frame).re) * window[i]; the overlap-add is a second,
+// order-preserving gather kernel (ola_kernel below).
+struct IoIstft {
+    static constexpr bool kEpilogueExchange = false;
+    const float2 *__restrict__ frames;
+    const float *__restrict__ window;
+    float *__restrict__ time; // [rows][n] f32
+    long n;
+    float scale;
+    KHD void init(int) {}
+    KHD float2 load(long row, int i) const { return pre_conj<true>(KOFFT_LDG(frames + row * n + i)); }
+    KHD void store(long row, int i, float2 v) const
+    {
+        float re = mul_rn(v.x, scale);
+        time[row * n + i] = mul_rn(re, KOFFT_LDG(window + i));
+    }
+};
+
+// rfft: input row = 2m reals viewed as m complex (pack is a reinterpretation); after the
+// length-m FFT the bins are exchanged once more through shared memory and twisted.
+template <bool EXACT>
+struct IoRfft {
+    static constexpr bool kEpilogueExchange = true;
+    const float2 *__restrict__ in;     // [rows][m]
+    float2 *__restrict__ out;          // [rows][m + 1]
+    const float2 *__restrict__ rtw;    // T'[k] = exp(-i pi k / m), m entries (src/rfft.rs:172-183)
+    long m;
+    KHD void init(int) {}
+    KHD float2 load(long row, int i) const { return KOFFT_LDG(in + row * m + i); }
+    KHD void store(long, int, float2) const {}
+    // Y: padded shared copy of the m FFT bins of this row
+    KHD void epilogue(long row, int k, const float2 *Y) const
+    {
+        float2 *o = out + row * (m + 1);
+        if (k == 0) {
+            float2 y0 = Y[0];
+            o[0] = make_float2(add_rn(y0.x, y0.y), 0.0f);
+            o[m] = make_float2(sub_rn(y0.x, y0.y), 0.0f);
+            return;
+        }
+        float2 a = Y[pad(k)];
+        float2 ym = Y[pad((int)m - k)];
+        float2 b = make_float2(ym.x, -ym.y);
+        float2 sum = add2(a, b), diff = sub2(a, b);
+        float2 t = cmul<EXACT>(KOFFT_LDG(rtw + k), diff);
+        float2 temp = make_float2(add_rn(sum.x, t.y), sub_rn(sum.y, t.x)); // sum + (t.im, -t.re)
+        o[k] = make_float2(mul_rn(temp.x, 0.5f), mul_rn(temp.y, 0.5f));
+    }
+};
+
+// irfft: the untwist (src/rfft.rs:485-498) is evaluated straight from global memory while
+// loading element i (it needs X[i] and X[m-i]), then ifft, then unpack to 2m reals.
+template <bool EXACT>
+struct IoIrfft {
+    static constexpr bool kEpilogueExchange = false;
+    const float2 *__restrict__ in;   // [rows][m + 1]
+    float2 *__restrict__ out;        // [rows][m] == 2m reals
+    const float2 *__restrict__ rtw;
+    long m;
+    float scale; // 1/m
+    KHD void init(int) {}
+    KHD float2 load(long row, int i) const
+    {
+        const float2 *X = in + row * (m + 1);
+        float2 v;
+        if (i == 0) {
+            float2 x0 = KOFFT_LDG(X), xm = KOFFT_LDG(X + m);
+            v = make_float2(mul_rn(add_rn(x0.x, xm.x), 0.5f), mul_rn(sub_rn(x0.x, xm.x), 0.5f));
+        } else {
+            float2 a = KOFFT_LDG(X + i);
+            float2 xm = KOFFT_LDG(X + (m - i));
+            float2 b = make_float2(xm.x, -xm.y);
+            float2 sum = add2(a, b), diff = sub2(a, b);
+            float2 tw = KOFFT_LDG(rtw + i);
+            float2 t = cmul<EXACT>(make_float2(tw.x, -tw.y), diff);
+            float2 temp = make_float2(sub_rn(sum.x, t.y), add_rn(sum.y, t.x)); // sum - (t.im, -t.re)
+            v = make_float2(mul_rn(temp.x, 0.5f), mul_rn(temp.y, 0.5f));
+        }
+        return pre_conj<true>(v);
+    }
+    KHD void store(long row, int i, float2 v) const { out[row * m + i] = post_conj_scale<true>(v, scale); }
+};
+
+// ------------------------------------------------------------------------------------------
+// The CTA body, written as per-thread phase functions so that tests/emu can run the very
+// same code on the CPU (phase by phase over all threads) -- see tests/emu/emu_engine.cpp.
+// ------------------------------------------------------------------------------------------
+template <class P, bool EXACT, class IO>
+struct CtaFft {
+    using P0 = Pass<P, 0, EXACT>;
+    using P1 = Pass<P, 1, EXACT>;
+    using P2 = Pass<P, (P::NP > 2 ? 2 : 1), EXACT>;
+    using P3 = Pass<P, (P::NP > 3 ? 3 : 1), EXACT>;
+
+    template <class PS>
+    static KHD void load_global(const IO &io, long row, int t, float2 *x)
+    {
+#pragma unroll
+        for (int u = 0; u < PS::U; u++)
+#pragma unroll
+            for (int q = 0; q < PS::R; q++) x[u * PS::R + q] = io.load(row, PS::src_index(t, u, q));
+    }
+    template <class PS>
+    static KHD void store_global(const IO &io, long row, int t, const float2 *x)
+    {
+#pragma unroll
+        for (int u = 0; u < PS::U; u++)
+#pragma unroll
+            for (int w = 0; w < PS::R; w++) io.store(row, PS::dst_index(t, u, w), x[u * PS::R + w]);
+    }
+    template <class PS>
+    static KHD void store_smem(float2 *buf, int t, const float2 *x)
+    {
+#pragma unroll
+        for (int u = 0; u < PS::U; u++)
+#pragma unroll
+            for (int w = 0; w < PS::R; w++) buf[PS::dst_pad(PS::dst_base(t, u), w)] = x[u * PS::R + w];
+    }
+    template <class PS>
+    static KHD void load_smem(const float2 *buf, int t, float2 *x)
+    {
+#pragma unroll
+        for (int u = 0; u < PS::U; u++)
+#pragma unroll
+            for (int q = 0; q < PS::R; q++) x[u * PS::R + q] = buf[PS::src_pad(PS::src_base(t, u), q)];
+    }
+    // rfft-style epilogue: thread t handles bins k = t + u*T
+    static KHD void epilogue(const IO &io, long row, int t, const float2 *buf)
+    {
+#pragma unroll
+        for (int u = 0; u < EPT; u++) io.epilogue(row, t + u * P::T, buf);
+    }
+
+#ifdef __CUDACC__
+    // rows: number of transforms; smem: 2 * TPC * PADN float2
+    static __device__ void run(IO io, const Tw0 &tw0, const float2 *__restrict__ table, long rows, float2 *smem)
+    {
+        const int tid = threadIdx.x;
+        const int slot = tid / P::T; // which of the CTA's TPC transforms
+        const int t = tid - slot * P::T;
+        float2 *buf0 = smem + slot * P::PADN;
+        float2 *buf1 = buf0 + P::TPC * P::PADN;
+        int par = 0;
+
+        io.init(t);
+        float2 tw1[P1::NTW], tw2[P2::NTW], tw3[P3::NTW];
+        if (P::TW_REGS) {
+            P1::load_tw(table, t, tw1);
+            if (P::NP > 2) P2::load_tw(table, t, tw2);
+        }
+
+        const long groups = (rows + P::TPC - 1) / P::TPC;
+        for (long g = blockIdx.x; g < groups; g += gridDim.x) {
+            const long row = g * P::TPC + slot;
+            const bool active = row < rows;
+            float2 x[EPT];
+            if (active) {
+                load_global<P0>(io, row, t, x);
+            } else {
+#pragma unroll
+                for (int e = 0; e < EPT; e++) x[e] = make_float2(0.f, 0.f);
+            }
+            P0::compute(x, tw0.v);
+
+            float2 *b = par ? buf1 : buf0;
+            par ^= 1;
+            store_smem<P0>(b, t, x);
+            __syncthreads();
+            load_smem<P1>(b, t, x);
+            if (!P::TW_REGS) P1::load_tw(table, t, tw1);
+            P1::compute(x, tw1);
+
+            if (P::NP > 2) {
+                b = par ? buf1 : buf0;
+                par ^= 1;
+                store_smem<P1>(b, t, x);
+                __syncthreads();
+                load_smem<P2>(b, t, x);
+                if (!P::TW_REGS) P2::load_tw(table, t, tw2);
+                P2::compute(x, tw2);
+            }
+            if (P::NP > 3) {
+                b = par ? buf1 : buf0;
+                par ^= 1;
+                store_smem<P2>(b, t, x);
+                __syncthreads();
+                load_smem<P3>(b, t, x);
+                P3::load_tw(table, t, tw3);
+                P3::compute(x, tw3);
+            }
+
+            using PL = Pass<P, P::NP - 1, EXACT>;
+            if constexpr (IO::kEpilogueExchange) {
+                b = par ? buf1 : buf0;
+                par ^= 1;
+                store_smem<PL>(b, t, x);
+                __syncthreads();
+                if (active) epilogue(io, row, t, b);
+            } else {
+                if (active) store_global<PL>(io, row, t, x);
+            }
+        }
+    }
+#endif
+};
+
+#ifdef __CUDACC__
+template <int L, bool EXACT, class IO>
+__global__ void __launch_bounds__(Plan<L>::CTA, (Plan<L>::CTA <= 256 ? 2 : 1))
+    fft_cta_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0 tw0,
+                   const float2 *__restrict__ table, long rows)
+{
+    extern __shared__ __align__(16) float2 smem[];
+    CtaFft<Plan<L>, EXACT, IO>::run(io, tw0, table, rows, smem);
+}
+#endif
+
+} // namespace kofft

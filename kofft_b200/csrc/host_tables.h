@@ -1,0 +1,9 @@
+// host_tables.h -- see host_tables.cpp
+#pragma once
+#include <cstddef>
+
+namespace kofft {
+void host_fft_twiddles(size_t n, float *out);                  // n/2 complex
+void host_rfft_twiddles(size_t m, float *out, bool fma_mul);   // m complex
+int host_window(int kind, size_t len, float beta, float *out); // 0 ok, -1 unknown kind
+} // namespace kofft

@@ -1,0 +1,123 @@
+// hostdev.h -- lets the FFT engine (fft_engine.cuh) compile both under nvcc (the product)
+// and under plain g++ (tests/emu: a CPU emulation of the CTA used to check index math and
+// bit-exactness before spending GPU time).  The g++ side is test scaffolding only.
+#pragma once
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define KHD __device__ __forceinline__
+#define KD __device__ __forceinline__
+#else
+#include <cmath>
+#define KHD inline
+#define KD inline
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#endif
+
+namespace kofft {
+
+// ---- exactly-rounded scalar ops (never contracted) ------------------------------------------
+#if defined(__CUDA_ARCH__)
+KD float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+KD float add_rn(float a, float b) { return __fadd_rn(a, b); }
+KD float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+KD float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+KD float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#else
+// host: translation units including this header are compiled with -ffp-contract=off
+KHD float mul_rn(float a, float b) { return a * b; }
+KHD float add_rn(float a, float b) { return a + b; }
+KHD float sub_rn(float a, float b) { return a - b; }
+KHD float div_rn(float a, float b) { return a / b; }
+KHD float fma_rn(float a, float b, float c) { return fmaf(a, b, c); }
+#endif
+
+// ---- packed f32x2 ops (sm_100a FADD2 / FMUL2 / FFMA2) -----------------------------------------
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with explicit .rn, so packed
+// multiplies are only used where contraction is allowed (the FAST path); packed adds of
+// non-product operands are safe everywhere.
+#if defined(__CUDA_ARCH__)
+KD float2 add2(float2 a, float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; "
+        "mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+KD float2 sub2(float2 a, float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; "
+        "mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+KD float2 mul2(float2 a, float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; "
+        "mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+KD float2 fma2(float2 a, float2 b, float2 c)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+#else
+KHD float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+KHD float2 sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+KHD float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+KHD float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+
+// ---- the radix-2 butterfly of kofft's Stockham stage (src/fft.rs:845-862 / 881-893) ---------
+//   t = v * w ;  u' = u + t ;  v' = u - t
+// EXACT: every product and sum individually rounded, in the reference's operand order
+//        -> bit-identical to the reference / oracle.
+// FAST : FMUL2 + FFMA2 + 2 FADD2 (one of the two products of each component stays unrounded).
+template <bool EXACT>
+KHD void butterfly(float2 &u, float2 &v, const float2 w)
+{
+    float2 t;
+    if (EXACT) {
+        t.x = sub_rn(mul_rn(v.x, w.x), mul_rn(v.y, w.y));
+        t.y = add_rn(mul_rn(v.x, w.y), mul_rn(v.y, w.x));
+    } else {
+        // (v.x*w.x - v.y*w.y, v.x*w.y + v.y*w.x) = v.x*(w.x,w.y) + v.y*(-w.y,w.x)
+        float2 p = mul2(make_float2(v.y, v.y), make_float2(-w.y, w.x));
+        t = fma2(make_float2(v.x, v.x), w, p);
+    }
+    float2 a = add2(u, t);
+    v = sub2(u, t);
+    u = a;
+}
+
+// twiddle == (1, 0) exactly (table entry 0): v*1 is the identity for finite v
+KHD void butterfly_unit(float2 &u, float2 &v)
+{
+    float2 a = add2(u, v);
+    v = sub2(u, v);
+    u = a;
+}
+
+// Complex::mul, unfused (src/num.rs:160-165), or contracted in FAST mode
+template <bool EXACT>
+KHD float2 cmul(const float2 a, const float2 b)
+{
+    if (EXACT)
+        return make_float2(sub_rn(mul_rn(a.x, b.x), mul_rn(a.y, b.y)), add_rn(mul_rn(a.x, b.y), mul_rn(a.y, b.x)));
+    return make_float2(fma_rn(a.x, b.x, -(a.y * b.y)), fma_rn(a.x, b.y, a.y * b.x));
+}
+
+} // namespace kofft

@@ -1,0 +1,679 @@
+// kofft_cuda.cu -- the C ABI (include/kofft_cuda.h): context, device-resident planner tables,
+// argument checks that mirror the reference's error behaviour, and kernel dispatch.
+#include "../../include/kofft_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "host_tables.h"
+#include "launch.h"
+
+using namespace kofft;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail_cuda(cudaError_t e, const char *where)
+{
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+    g_last_error = buf;
+    int code = -static_cast<int>(e);
+    return code == 0 ? -1 : code;
+}
+
+int fail_msg(int code, const char *msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CU(call)                                          \
+    do {                                                  \
+        cudaError_t e__ = (call);                         \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+bool is_pow2(size_t n) { return n != 0 && (n & (n - 1)) == 0; }
+int log2_of(size_t n)
+{
+    int l = 0;
+    while ((size_t(1) << l) < n) l++;
+    return l;
+}
+
+struct Table {
+    std::vector<float> host; // interleaved
+    float2 *dev = nullptr;
+};
+
+} // namespace
+
+struct kofft_cuda_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    bool exact = true;
+    bool rfft_fma = false;
+    int max_ctas = 0;
+    unsigned long long launches = 0;
+    std::map<size_t, Table> fft_tables;                  // key n
+    std::map<std::pair<size_t, int>, Table> rfft_tables; // key (m, fma)
+    // grow-only device workspaces: [0] host-API staging in, [1] staging out, [2] istft time frames,
+    // [3] small staging (windows)
+    void *ws[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t ws_bytes[4] = {0, 0, 0, 0};
+    size_t istft_ws_limit = size_t(1) << 30;
+};
+
+namespace {
+
+int ensure_ws(kofft_cuda_ctx *ctx, int which, size_t bytes, void **out)
+{
+    if (bytes == 0) bytes = 16;
+    if (ctx->ws_bytes[which] < bytes) {
+        if (ctx->ws[which]) {
+            CU(cudaStreamSynchronize(ctx->stream));
+            CU(cudaFree(ctx->ws[which]));
+            ctx->ws[which] = nullptr;
+            ctx->ws_bytes[which] = 0;
+        }
+        CU(cudaMalloc(&ctx->ws[which], bytes));
+        ctx->ws_bytes[which] = bytes;
+    }
+    *out = ctx->ws[which];
+    return 0;
+}
+
+int get_fft_table(kofft_cuda_ctx *ctx, size_t n, const Table **out)
+{
+    auto it = ctx->fft_tables.find(n);
+    if (it == ctx->fft_tables.end()) {
+        Table t;
+        size_t half = n / 2;
+        t.host.resize(2 * (half ? half : 1));
+        host_fft_twiddles(n, t.host.data());
+        CU(cudaMalloc(&t.dev, sizeof(float2) * (half ? half : 1)));
+        CU(cudaMemcpyAsync(t.dev, t.host.data(), sizeof(float2) * half, cudaMemcpyHostToDevice, ctx->stream));
+        // the host vector must outlive the async copy: it is owned by the map entry below
+        it = ctx->fft_tables.emplace(n, std::move(t)).first;
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    *out = &it->second;
+    return 0;
+}
+
+int get_rfft_table(kofft_cuda_ctx *ctx, size_t m, const Table **out)
+{
+    auto key = std::make_pair(m, ctx->rfft_fma ? 1 : 0);
+    auto it = ctx->rfft_tables.find(key);
+    if (it == ctx->rfft_tables.end()) {
+        Table t;
+        t.host.resize(2 * (m ? m : 1));
+        host_rfft_twiddles(m, t.host.data(), ctx->rfft_fma);
+        CU(cudaMalloc(&t.dev, sizeof(float2) * (m ? m : 1)));
+        CU(cudaMemcpyAsync(t.dev, t.host.data(), sizeof(float2) * m, cudaMemcpyHostToDevice, ctx->stream));
+        it = ctx->rfft_tables.emplace(key, std::move(t)).first;
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    *out = &it->second;
+    return 0;
+}
+
+// Common dispatch: the complex core has length n (power of two, >= 1), `rows` transforms.
+int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t rows, cudaStream_t stream)
+{
+    if (rows == 0) return KOFFT_OK;
+    LaunchArgs a;
+    a.kind = kind;
+    a.exact = ctx->exact;
+    a.io = io;
+    a.io.n = static_cast<long>(n);
+    a.rows = static_cast<long>(rows);
+    a.num_sms = ctx->num_sms;
+    a.max_ctas = ctx->max_ctas;
+    a.stream = stream;
+    memset(&a.tw0, 0, sizeof a.tw0);
+    cudaError_t e;
+    if (n <= 16) {
+        e = launch_small_fft(static_cast<int>(n), a);
+    } else {
+        const int L = log2_of(n);
+        if (L > 14)
+            return fail_msg(-static_cast<int>(cudaErrorNotSupported),
+                            "transform length above 16384 is not supported by the single-CTA engine yet");
+        const Table *t = nullptr;
+        int rc = get_fft_table(ctx, n, &t);
+        if (rc) return rc;
+        a.table = t->dev;
+        // pass-0 twiddles (group k = 0): v[(2^t - 1) + c] = T[c << (L-1-t)]
+        const int NP = L <= 8 ? 2 : (L <= 12 ? 3 : 4);
+        const int R0 = L - 4 * (NP - 1);
+        for (int tl = 0; tl < R0; tl++)
+            for (int c = 0; c < (1 << tl); c++) {
+                size_t idx = static_cast<size_t>(c) << (L - 1 - tl);
+                a.tw0.v[(1 << tl) - 1 + c] = make_float2(t->host[2 * idx], t->host[2 * idx + 1]);
+            }
+        e = launch_cta_fft(L, a);
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+    ctx->launches++;
+    return KOFFT_OK;
+}
+
+// length checks shared by every entry that ends in FftImpl::fft(n) (src/fft.rs:1054-1082)
+int check_fft_len(size_t n)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
+    if (!is_pow2(n)) return KOFFT_ERR_NON_POWER_OF_TWO_NO_STD;
+    return KOFFT_OK;
+}
+
+cudaStream_t pick_stream(kofft_cuda_ctx *ctx, void *stream)
+{
+    return stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+}
+
+} // namespace
+
+extern "C" {
+
+int kofft_cuda_create(kofft_cuda_ctx **out, int device)
+{
+    if (!out) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null out pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount (no CUDA device: there is no CPU fallback)");
+    if (device < 0 || device >= count) return fail_msg(-static_cast<int>(cudaErrorInvalidDevice), "invalid device index");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail_msg(-static_cast<int>(cudaErrorNoKernelImageForDevice),
+                        "libkofft_cuda is built for sm_100a (B200) only");
+    kofft_cuda_ctx *ctx = new kofft_cuda_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return fail_cuda(e, "cudaStreamCreate");
+    }
+    *out = ctx;
+    return KOFFT_OK;
+}
+
+void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->fft_tables) cudaFree(kv.second.dev);
+    for (auto &kv : ctx->rfft_tables) cudaFree(kv.second.dev);
+    for (int i = 0; i < 4; i++)
+        if (ctx->ws[i]) cudaFree(ctx->ws[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *kofft_cuda_last_error(void) { return g_last_error.c_str(); }
+int kofft_cuda_device(const kofft_cuda_ctx *ctx) { return ctx ? ctx->device : -1; }
+void *kofft_cuda_stream(const kofft_cuda_ctx *ctx) { return ctx ? ctx->stream : nullptr; }
+
+int kofft_cuda_synchronize(kofft_cuda_ctx *ctx)
+{
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_set_exact(kofft_cuda_ctx *ctx, int exact)
+{
+    ctx->exact = exact != 0;
+    return KOFFT_OK;
+}
+int kofft_cuda_get_exact(const kofft_cuda_ctx *ctx) { return ctx->exact ? 1 : 0; }
+unsigned long long kofft_cuda_launch_count(const kofft_cuda_ctx *ctx) { return ctx->launches; }
+int kofft_cuda_set_max_ctas(kofft_cuda_ctx *ctx, int max_ctas)
+{
+    ctx->max_ctas = max_ctas < 0 ? 0 : max_ctas;
+    return KOFFT_OK;
+}
+int kofft_cuda_set_rfft_table_fma(kofft_cuda_ctx *ctx, int fma_mul)
+{
+    ctx->rfft_fma = fma_mul != 0;
+    return KOFFT_OK;
+}
+
+// ---- planner tables ---------------------------------------------------------------------
+int kofft_cuda_twiddles_host_f32(size_t n, float *out)
+{
+    host_fft_twiddles(n, out);
+    return KOFFT_OK;
+}
+int kofft_cuda_rfft_twiddles_host_f32(size_t m, float *out, int fma_mul)
+{
+    host_rfft_twiddles(m, out, fma_mul != 0);
+    return KOFFT_OK;
+}
+int kofft_cuda_get_twiddles(kofft_cuda_ctx *ctx, size_t n, const void **dev_ptr)
+{
+    CU(cudaSetDevice(ctx->device));
+    const Table *t = nullptr;
+    int rc = get_fft_table(ctx, n, &t);
+    if (rc) return rc;
+    *dev_ptr = t->dev;
+    return KOFFT_OK;
+}
+int kofft_cuda_get_rfft_twiddles(kofft_cuda_ctx *ctx, size_t m, const void **dev_ptr)
+{
+    CU(cudaSetDevice(ctx->device));
+    const Table *t = nullptr;
+    int rc = get_rfft_table(ctx, m, &t);
+    if (rc) return rc;
+    *dev_ptr = t->dev;
+    return KOFFT_OK;
+}
+int kofft_cuda_window_host_f32(int kind, size_t len, float beta, float *out)
+{
+    if (host_window(kind, len, beta, out) != 0) return fail_msg(KOFFT_ERR_INVALID_VALUE, "unknown window kind");
+    return KOFFT_OK;
+}
+
+// ---- device-pointer entry points ----------------------------------------------------------
+int kofft_cuda_fft_c2c_f32(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch,
+                           int inverse, void *stream)
+{
+    int rc = check_fft_len(n);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    if (n == 1) { // fft of one point is the identity (src/fft.rs:1059-1061)
+        if (d_in != d_out && batch)
+            CU(cudaMemcpyAsync(d_out, d_in, batch * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+        return KOFFT_OK;
+    }
+    IoArgs io;
+    io.in = d_in;
+    io.out = d_out;
+    io.scale = 1.0f / static_cast<float>(n); // src/fft.rs:1163
+    return dispatch(ctx, inverse ? KIND_C2C_INV : KIND_C2C_FWD, io, n, batch, s);
+}
+
+int kofft_cuda_fft_strided_f32(kofft_cuda_ctx *ctx, const void *d_in, size_t in_stride, size_t in_dist,
+                               void *d_out, size_t out_stride, size_t out_dist, size_t n, size_t batch,
+                               int inverse, void *stream)
+{
+    if (in_stride == 0 || out_stride == 0) return KOFFT_ERR_INVALID_STRIDE;
+    int rc = check_fft_len(n);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    IoArgs io;
+    io.in = d_in;
+    io.in2 = static_cast<const float *>(d_in) + 1;
+    io.out = d_out;
+    io.out2 = static_cast<float *>(d_out) + 1;
+    io.p0 = 2 * static_cast<long>(in_stride);
+    io.p1 = 2 * static_cast<long>(in_dist);
+    io.p2 = 2 * static_cast<long>(out_stride);
+    io.p3 = 2 * static_cast<long>(out_dist);
+    io.scale = 1.0f / static_cast<float>(n);
+    return dispatch(ctx, inverse ? KIND_GEN_INV : KIND_GEN_FWD, io, n, batch, pick_stream(ctx, stream));
+}
+
+int kofft_cuda_fft_split_f32(kofft_cuda_ctx *ctx, const float *d_in_re, const float *d_in_im, float *d_out_re,
+                             float *d_out_im, size_t n, size_t batch, int inverse, void *stream)
+{
+    int rc = check_fft_len(n);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    IoArgs io;
+    io.in = d_in_re;
+    io.in2 = d_in_im;
+    io.out = d_out_re;
+    io.out2 = d_out_im;
+    io.p0 = 1;
+    io.p1 = static_cast<long>(n);
+    io.p2 = 1;
+    io.p3 = static_cast<long>(n);
+    io.scale = 1.0f / static_cast<float>(n); // src/fft.rs:1413
+    return dispatch(ctx, inverse ? KIND_GEN_INV : KIND_GEN_FWD, io, n, batch, pick_stream(ctx, stream));
+}
+
+int kofft_cuda_rfft_f32(kofft_cuda_ctx *ctx, const float *d_in, void *d_out, size_t n, size_t batch, void *stream)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;       // src/rfft.rs:434-436
+    if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE; // :437-439
+    const size_t m = n / 2;
+    int rc = check_fft_len(m);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const Table *t = nullptr;
+    rc = get_rfft_table(ctx, m, &t);
+    if (rc) return rc;
+    IoArgs io;
+    io.in = d_in;
+    io.out = d_out;
+    io.aux = t->dev;
+    return dispatch(ctx, KIND_RFFT, io, m, batch, pick_stream(ctx, stream));
+}
+
+int kofft_cuda_irfft_f32(kofft_cuda_ctx *ctx, const void *d_in, float *d_out, size_t n, size_t batch, void *stream)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;       // src/rfft.rs:477-479
+    if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE; // :480-482
+    const size_t m = n / 2;
+    int rc = check_fft_len(m);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const Table *t = nullptr;
+    rc = get_rfft_table(ctx, m, &t);
+    if (rc) return rc;
+    IoArgs io;
+    io.in = d_in;
+    io.out = d_out;
+    io.aux = t->dev;
+    io.scale = 1.0f / static_cast<float>(m);
+    return dispatch(ctx, KIND_IRFFT, io, m, batch, pick_stream(ctx, stream));
+}
+
+int kofft_cuda_stft_f32(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, size_t channels,
+                        const float *d_window, size_t win_len, size_t hop, void *d_frames, size_t nframes,
+                        void *stream)
+{
+    if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE;          // src/stft.rs:83-85
+    const size_t required = (len + hop - 1) / hop;            // :86
+    if (nframes < required) return KOFFT_ERR_MISMATCHED_LENGTHS; // :87-89
+    if (nframes == 0 || channels == 0) return KOFFT_OK;
+    int rc = check_fft_len(win_len);                          // first fft.fft(frame) :102
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    IoArgs io;
+    io.in = d_signal;
+    io.aux = d_window;
+    io.out = d_frames;
+    io.p0 = static_cast<long>(len);
+    io.p1 = static_cast<long>(nframes);
+    io.p2 = static_cast<long>(hop);
+    return dispatch(ctx, KIND_STFT, io, win_len, channels * nframes, pick_stream(ctx, stream));
+}
+
+int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nframes, size_t channels,
+                         const float *d_window, size_t win_len, size_t hop, float *d_output, size_t out_len,
+                         float *d_norm, int zero_uncovered, void *stream)
+{
+    if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE; // src/stft.rs:125-127
+    if (channels == 0) return KOFFT_OK;
+    if (nframes > 0) {
+        int rc = check_fft_len(win_len); // fft.ifft(frame) :141
+        if (rc) return rc;
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    // stage 1 writes windowed real frames into a bounded workspace, a few channels at a time
+    const size_t per_channel = nframes * win_len * sizeof(float);
+    size_t chunk = per_channel ? ctx->istft_ws_limit / per_channel : channels;
+    if (chunk < 1) chunk = 1;
+    if (chunk > channels) chunk = channels;
+    void *time = nullptr;
+    int rc = ensure_ws(ctx, 2, chunk * per_channel, &time);
+    if (rc) return rc;
+    for (size_t c0 = 0; c0 < channels; c0 += chunk) {
+        const size_t nc = (channels - c0 < chunk) ? channels - c0 : chunk;
+        if (nframes > 0) {
+            IoArgs io;
+            io.in = static_cast<const float2 *>(d_frames) + c0 * nframes * win_len;
+            io.aux = d_window;
+            io.out = time;
+            io.scale = 1.0f / static_cast<float>(win_len);
+            rc = dispatch(ctx, KIND_ISTFT, io, win_len, nc * nframes, s);
+            if (rc) return rc;
+        }
+        OlaArgs o;
+        o.time = static_cast<const float *>(time);
+        o.window = d_window;
+        o.output = d_output + c0 * out_len;
+        o.norm = d_norm ? d_norm + c0 * out_len : nullptr;
+        o.channels = static_cast<long>(nc);
+        o.nframes = static_cast<long>(nframes);
+        o.win_len = static_cast<long>(win_len);
+        o.hop = static_cast<long>(hop);
+        o.out_len = static_cast<long>(out_len);
+        o.zero_uncovered = zero_uncovered;
+        cudaError_t e = launch_ola(o, s);
+        if (e != cudaSuccess) return fail_cuda(e, "ola launch");
+        ctx->launches++;
+    }
+    return KOFFT_OK;
+}
+
+// ---- host-pointer drop-ins ------------------------------------------------------------------
+static int host_roundtrip_begin(kofft_cuda_ctx *ctx, const void *src, size_t bytes, int which, void **dev)
+{
+    int rc = ensure_ws(ctx, which, bytes, dev);
+    if (rc) return rc;
+    if (src && bytes) CU(cudaMemcpyAsync(*dev, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int kofft_cuda_fft_batch_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, size_t batch, int inverse)
+{
+    int rc = check_fft_len(n);
+    if (rc) return rc;
+    if (n == 1 || batch == 0) return KOFFT_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = n * batch * sizeof(float2);
+    void *d = nullptr;
+    rc = host_roundtrip_begin(ctx, data, bytes, 0, &d);
+    if (rc) return rc;
+    rc = kofft_cuda_fft_c2c_f32(ctx, d, d, n, batch, inverse, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_fft_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, int inverse)
+{
+    return kofft_cuda_fft_batch_host_f32(ctx, data, n, 1, inverse);
+}
+
+int kofft_cuda_fft_split_host_f32(kofft_cuda_ctx *ctx, float *re, size_t re_len, float *im, size_t im_len,
+                                  int inverse)
+{
+    if (re_len != im_len) return KOFFT_ERR_MISMATCHED_LENGTHS; // src/fft.rs:1366-1368
+    const size_t n = re_len;
+    int rc = check_fft_len(n);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    void *d = nullptr;
+    rc = ensure_ws(ctx, 0, 2 * n * sizeof(float), &d);
+    if (rc) return rc;
+    float *dre = static_cast<float *>(d), *dim = dre + n;
+    CU(cudaMemcpyAsync(dre, re, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dim, im, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 1) { // n == 1 is the identity for fft_split and (negate, negate, *1/1) for ifft_split
+        rc = kofft_cuda_fft_split_f32(ctx, dre, dim, dre, dim, n, 1, inverse, ctx->stream);
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(re, dre, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(im, dim, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_fft_strided_host_f32(kofft_cuda_ctx *ctx, float *input, size_t input_len, size_t stride, size_t n,
+                                    int inverse)
+{
+    if (stride == 0) return KOFFT_ERR_INVALID_STRIDE;                           // src/fft.rs:1181-1183
+    if (n == 0) return KOFFT_OK;                                                // :1185-1187
+    if (input_len < (n - 1) * stride + 1) return KOFFT_ERR_MISMATCHED_LENGTHS; // :1188-1190
+    int rc = check_fft_len(n);
+    if (rc) return rc;
+    if (n == 1) return KOFFT_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t span = (n - 1) * stride + 1;
+    void *d = nullptr;
+    rc = host_roundtrip_begin(ctx, input, span * sizeof(float2), 0, &d);
+    if (rc) return rc;
+    rc = kofft_cuda_fft_strided_f32(ctx, d, stride, span, d, stride, span, n, 1, inverse, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(input, d, span * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_fft_out_of_place_strided_host_f32(kofft_cuda_ctx *ctx, const float *input, size_t input_len,
+                                                 size_t in_stride, float *output, size_t output_len,
+                                                 size_t out_stride, int inverse)
+{
+    if (in_stride == 0 || out_stride == 0) return KOFFT_ERR_INVALID_STRIDE;   // src/fft.rs:1267-1269
+    if (input_len % in_stride != 0 || output_len % out_stride != 0) return KOFFT_ERR_INVALID_STRIDE; // :1270-1272
+    const size_t n = input_len / in_stride;
+    if (output_len / out_stride != n) return KOFFT_ERR_MISMATCHED_LENGTHS;    // :1274-1276
+    int rc = check_fft_len(n);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    void *din = nullptr, *dout = nullptr;
+    rc = host_roundtrip_begin(ctx, input, input_len * sizeof(float2), 0, &din);
+    if (rc) return rc;
+    // the scatter only touches every out_stride-th element: stage the caller's buffer so the
+    // untouched elements survive the copy back
+    rc = host_roundtrip_begin(ctx, output, output_len * sizeof(float2), 1, &dout);
+    if (rc) return rc;
+    rc = kofft_cuda_fft_strided_f32(ctx, din, in_stride, input_len, dout, out_stride, output_len, n, 1, inverse,
+                                    ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(output, dout, output_len * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_rfft_batch_host_f32(kofft_cuda_ctx *ctx, const float *input, size_t n, size_t batch, float *output)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
+    if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE;
+    const size_t m = n / 2;
+    int rc = check_fft_len(m);
+    if (rc) return rc;
+    if (batch == 0) return KOFFT_OK;
+    CU(cudaSetDevice(ctx->device));
+    void *din = nullptr, *dout = nullptr;
+    rc = host_roundtrip_begin(ctx, input, n * batch * sizeof(float), 0, &din);
+    if (rc) return rc;
+    rc = ensure_ws(ctx, 1, (m + 1) * batch * sizeof(float2), &dout);
+    if (rc) return rc;
+    rc = kofft_cuda_rfft_f32(ctx, static_cast<const float *>(din), dout, n, batch, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(output, dout, (m + 1) * batch * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_rfft_host_f32(kofft_cuda_ctx *ctx, const float *input, size_t n, float *output, size_t output_len,
+                             size_t scratch_len)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
+    if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE;
+    if (output_len != n / 2 + 1 || scratch_len < n / 2) return KOFFT_ERR_MISMATCHED_LENGTHS; // src/rfft.rs:441-443
+    return kofft_cuda_rfft_batch_host_f32(ctx, input, n, 1, output);
+}
+
+int kofft_cuda_irfft_batch_host_f32(kofft_cuda_ctx *ctx, const float *input, size_t n, size_t batch, float *output)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
+    if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE;
+    const size_t m = n / 2;
+    int rc = check_fft_len(m);
+    if (rc) return rc;
+    if (batch == 0) return KOFFT_OK;
+    CU(cudaSetDevice(ctx->device));
+    void *din = nullptr, *dout = nullptr;
+    rc = host_roundtrip_begin(ctx, input, (m + 1) * batch * sizeof(float2), 0, &din);
+    if (rc) return rc;
+    rc = ensure_ws(ctx, 1, n * batch * sizeof(float), &dout);
+    if (rc) return rc;
+    rc = kofft_cuda_irfft_f32(ctx, din, static_cast<float *>(dout), n, batch, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(output, dout, n * batch * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_irfft_host_f32(kofft_cuda_ctx *ctx, const float *input, size_t input_len, float *output, size_t n,
+                              size_t scratch_len)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
+    if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE;
+    if (input_len != n / 2 + 1 || scratch_len < n / 2) return KOFFT_ERR_MISMATCHED_LENGTHS; // src/rfft.rs:484-486
+    return kofft_cuda_irfft_batch_host_f32(ctx, input, n, 1, output);
+}
+
+int kofft_cuda_stft_host_f32(kofft_cuda_ctx *ctx, const float *signal, size_t len, size_t channels,
+                             const float *window, size_t win_len, size_t hop, float *frames, size_t nframes)
+{
+    if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE;
+    if (nframes < (len + hop - 1) / hop) return KOFFT_ERR_MISMATCHED_LENGTHS;
+    if (nframes == 0 || channels == 0) return KOFFT_OK;
+    int rc = check_fft_len(win_len);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    void *dsig = nullptr, *dfr = nullptr, *dwin = nullptr;
+    rc = host_roundtrip_begin(ctx, signal, len * channels * sizeof(float), 0, &dsig);
+    if (rc) return rc;
+    rc = host_roundtrip_begin(ctx, window, win_len * sizeof(float), 3, &dwin);
+    if (rc) return rc;
+    const size_t fbytes = channels * nframes * win_len * sizeof(float2);
+    rc = ensure_ws(ctx, 1, fbytes, &dfr);
+    if (rc) return rc;
+    rc = kofft_cuda_stft_f32(ctx, static_cast<const float *>(dsig), len, channels, static_cast<const float *>(dwin),
+                             win_len, hop, dfr, nframes, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(frames, dfr, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_istft_host_f32(kofft_cuda_ctx *ctx, const float *frames, size_t nframes, size_t channels,
+                              const float *window, size_t win_len, size_t hop, float *output, size_t out_len,
+                              float *scratch, size_t scratch_len, int zero_uncovered)
+{
+    if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE;
+    if (!zero_uncovered && scratch_len != out_len * channels)
+        return KOFFT_ERR_MISMATCHED_LENGTHS; // src/stft.rs:128-130 (per channel)
+    if (channels == 0) return KOFFT_OK;
+    if (nframes > 0) {
+        int rc = check_fft_len(win_len);
+        if (rc) return rc;
+    }
+    CU(cudaSetDevice(ctx->device));
+    void *dfr = nullptr, *dwin = nullptr, *dout = nullptr;
+    int rc = host_roundtrip_begin(ctx, frames, channels * nframes * win_len * sizeof(float2), 0, &dfr);
+    if (rc) return rc;
+    rc = host_roundtrip_begin(ctx, window, win_len * sizeof(float), 3, &dwin);
+    if (rc) return rc;
+    // output (accumulated into) followed by norm in one staging buffer
+    const size_t obytes = channels * out_len * sizeof(float);
+    rc = ensure_ws(ctx, 1, 2 * obytes, &dout);
+    if (rc) return rc;
+    float *d_out = static_cast<float *>(dout);
+    float *d_norm = d_out + channels * out_len;
+    if (obytes) CU(cudaMemcpyAsync(d_out, output, obytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = kofft_cuda_istft_f32(ctx, dfr, nframes, channels, static_cast<const float *>(dwin), win_len, hop, d_out,
+                              out_len, d_norm, zero_uncovered, ctx->stream);
+    if (rc) return rc;
+    if (obytes) CU(cudaMemcpyAsync(output, d_out, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (scratch && obytes) CU(cudaMemcpyAsync(scratch, d_norm, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+} // extern "C"

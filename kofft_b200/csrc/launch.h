@@ -1,0 +1,70 @@
+// launch.h -- type-erased launch interface between the C ABI (kofft_cuda.cu) and the
+// per-size kernel translation units (fft_inst.cu is compiled once per L with -DKOFFT_L=<L>
+// so the ten sizes build in parallel).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fft_engine.cuh"
+
+namespace kofft {
+
+enum Kind : int {
+    KIND_C2C_FWD = 0,
+    KIND_C2C_INV = 1,
+    KIND_GEN_FWD = 2,
+    KIND_GEN_INV = 3,
+    KIND_STFT = 4,
+    KIND_ISTFT = 5,
+    KIND_RFFT = 6,
+    KIND_IRFFT = 7,
+    KIND_COUNT = 8
+};
+
+// Untyped operands; their meaning per kind is documented at the IO policy they feed
+// (fft_kernels.cuh).
+struct IoArgs {
+    const void *in = nullptr;   // c2c/rfft/irfft/istft: input rows; gen: re; stft: signal
+    const void *in2 = nullptr;  // gen: im
+    void *out = nullptr;        // output rows; gen: re
+    void *out2 = nullptr;       // gen: im
+    const void *aux = nullptr;  // stft/istft: window; rfft/irfft: T' table
+    long n = 0;                 // transform length of the complex core
+    long p0 = 0, p1 = 0, p2 = 0, p3 = 0; // gen: in_es,in_rs,out_es,out_rs; stft: len,nframes,hop
+    float scale = 1.0f;         // 1/n for inverse kinds
+};
+
+struct LaunchArgs {
+    int kind = 0;
+    bool exact = true;
+    IoArgs io;
+    Tw0 tw0;
+    const float2 *table = nullptr; // device-resident FftPlanner table for n
+    long rows = 0;
+    int num_sms = 148;
+    int max_ctas = 0; // 0 = occupancy * num_sms
+    cudaStream_t stream = nullptr;
+};
+
+// N = 32 .. 16384 (L = 5 .. 14)
+cudaError_t launch_cta_fft(int L, const LaunchArgs &a);
+// N = 1 .. 16
+cudaError_t launch_small_fft(int n, const LaunchArgs &a);
+
+// per-L entry points (one per fft_inst.cu build)
+#define KOFFT_DECL_L(L) cudaError_t launch_cta_fft_L##L(const LaunchArgs &a);
+KOFFT_DECL_L(5) KOFFT_DECL_L(6) KOFFT_DECL_L(7) KOFFT_DECL_L(8) KOFFT_DECL_L(9)
+KOFFT_DECL_L(10) KOFFT_DECL_L(11) KOFFT_DECL_L(12) KOFFT_DECL_L(13) KOFFT_DECL_L(14)
+#undef KOFFT_DECL_L
+
+// istft stage 2: ordered overlap-add gather + normalisation (src/stft.rs:142-154)
+struct OlaArgs {
+    const float *time;  // [channels][nframes][win_len] windowed real frames
+    const float *window;
+    float *output;      // [channels][out_len], accumulated into (reference semantics)
+    float *norm;        // optional [channels][out_len] (the reference's `scratch`), may be null
+    long channels, nframes, win_len, hop, out_len;
+    int zero_uncovered; // 0: istft (leave sample untouched), 1: inverse_parallel (write 0)
+};
+cudaError_t launch_ola(const OlaArgs &a, cudaStream_t stream);
+
+} // namespace kofft
