@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- measures BASELINE.json's headline metric on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input: the batched C2C f32
+FFT of BASELINE configs[1] (N = 4096 x batch 65536, 2 GiB in + 2 GiB out) through
+`kofft_cuda_fft_c2c_f32` (one kernel launch).  Each rank owns one GPU and processes its own
+65536 rows (rows are independent: no data-path collective; weak scaling).
+
+Printed JSON line (rank 0):
+  value      whole-job GFLOP/s (5 N log2 N per transform), inputs resident in HBM, CUDA-event timed
+  e2e        the same metric through the host-pointer C ABI call (`kofft_cuda_fft_batch_host_f32`,
+             what `CudaFftImpl::batch` binds) with pinned HOST buffers: H2D + kernel + D2H per step
+  roofline   algorithmic bytes (16 N B per launch) / measured launch time vs the
+             measured HBM copy peak in MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of kofft's CPU path timed on this box's host cores (bounded sample)
+  extra      STFT (configs[3] shape) frames/s and rfft numbers measured after the headline region
+
+`--impl reference` times the CPU restatement of the reference (oracle/, "port": the Rust crate
+cannot be built in this image) on the same config with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N = 4096
+ROWS_PER_GPU = 65536
+FLOPS_PER_TRANSFORM = 5 * N * int(math.log2(N))
+ALGO_BYTES_PER_TRANSFORM = 16 * N  # read 8N + write 8N
+METRIC = "batched_c2c_f32_fft_gflops"
+UNIT = "GFLOP/s"
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": f"batched C2C f32 FFT N={N} x batch {ROWS_PER_GPU} per GPU (BASELINE configs[1]), "
+                    "uniform[-1,1) synthetic rows, out-of-place",
+        "n": N,
+        "rows_per_gpu": ROWS_PER_GPU,
+        "global_batch": ROWS_PER_GPU * n_gpus,
+        "parallelism": f"batch-sharded x{n_gpus}, no collective",
+        "l2_policy": "inputs larger than L2 (2 GiB in + 2 GiB out per step vs 126 MB L2)",
+        "arithmetic": "exact (bit-identical to the reference's unfused f32 arithmetic)",
+    }
+
+
+def peaks() -> tuple[float, str]:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic() -> float | None:
+    """dram bytes per launch of the headline kernel from the committed ncu summary, if any."""
+    path = os.path.join(ROOT, "profiles", "headline_kernel_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples: list[int] = []
+        self.reasons: set[str] = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if bit and (mask & bit):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def stop(self) -> dict:
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_port_gflops(rows: int, reps: int, threads: int) -> tuple[float, float]:
+    """kofft's CPU path (oracle port) on `rows` transforms of length N, all `threads` cores:
+    rows split evenly over threads, one reused planner per thread.  Returns (GFLOP/s, seconds)."""
+    from oracle import kofft_oracle as ko
+
+    ko.build()
+    rng = np.random.default_rng(0)
+    x = (rng.uniform(-1, 1, (rows, N)) + 1j * rng.uniform(-1, 1, (rows, N))).astype(np.complex64)
+    ko.fft_batch_inplace(x[: max(threads, 1)].copy(), nthreads=threads)  # warm the threads / tables
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ko.fft_batch_inplace(x, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return FLOPS_PER_TRANSFORM * rows * reps / dt / 1e9, dt
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows = 4096
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_gflops(rows, 1, threads)
+    t0 = time.perf_counter()
+    vals = [cpu_port_gflops(rows, 1, threads)[0] for _ in range(args.steps)]
+    total = time.perf_counter() - t0
+    value = statistics.median(vals)
+    sample = f"{rows} of {ROWS_PER_GPU} rows per step (N={N}), {threads} threads, rows split evenly; scaled by flops"
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * FLOPS_PER_TRANSFORM * rows / (value * 1e9),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "kofft is a Rust crate and cannot be built in this image (no rustc/cargo); this arm times the "
+                "bit-faithful C restatement of its CPU path (oracle/kofft_oracle.c) on the host cores",
+        "wall_s": total,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import kofft_b200
+    from kofft_b200 import stft as S
+    from kofft_b200 import window as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: kofft_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    fft = kofft_b200.CudaFftImpl(device=local, exact=True)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.view_as_complex((torch.rand((ROWS_PER_GPU, N, 2), generator=g, device=dev) * 2 - 1)).contiguous()
+    y = torch.empty_like(x)
+
+    # ---- device-resident timing: K launches bracketed by events on the launching stream -------
+    for _ in range(max(args.warmup, 3)):
+        fft.fft_batch(x, out=y)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = fft.ctx.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        fft.fft_batch(x, out=y)
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop()
+    launches = fft.ctx.launch_count - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = FLOPS_PER_TRANSFORM * ROWS_PER_GPU * n_gpus / (ms_per_step * 1e-3) / 1e9
+
+    avg_launch_ms = sum(per_launch_ms) / len(per_launch_ms)
+    peak, peak_src = peaks()
+    achieved = ALGO_BYTES_PER_TRANSFORM * ROWS_PER_GPU / (avg_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "peak_source": peak_src,
+                "kernel": "fft_cta_kernel<12, exact, IoC2C<false>>",
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_TRANSFORM * ROWS_PER_GPU,
+                "launch_ms_avg": avg_launch_ms, "launch_ms_min": min(per_launch_ms),
+                "frac_of_8TBs_spec": achieved / 8000.0}
+
+    # ---- end to end through the host-pointer C ABI (pinned host buffers) -----------------------
+    e2e_steps = max(2, min(args.steps, 5))
+    host = torch.empty((ROWS_PER_GPU, N), dtype=torch.complex64, pin_memory=True)
+    host.copy_(x)
+    h = host.numpy()
+    fft.fft_batch(h)  # warm-up: allocates the staging workspace
+    host.copy_(x)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        fft.fft_batch(h)  # H2D 2 GiB -> kernel -> D2H 2 GiB, synchronous
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    nbytes = ROWS_PER_GPU * N * 8
+    e2e = {"value": FLOPS_PER_TRANSFORM * ROWS_PER_GPU * n_gpus / e2e_s / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_s * 1e3,
+           "steps": e2e_steps, "api": "kofft_cuda_fft_batch_host_f32 (CudaFftImpl.fft_batch on pinned host rows)"}
+    del host, h
+
+    # ---- extra: STFT (configs[3] shape) and FAST-mode C2C, after the headline region ------------
+    extra = {}
+    try:
+        fast = kofft_b200.CudaFftImpl(device=local, exact=False)
+        for _ in range(3):
+            fast.fft_batch(x, out=y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fast.fft_batch(x, out=y)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        extra["c2c_fast_mode"] = {"ms_per_step": ms, "gflops": FLOPS_PER_TRANSFORM * ROWS_PER_GPU / ms / 1e6,
+                                  "hbm_gbs": ALGO_BYTES_PER_TRANSFORM * ROWS_PER_GPU / ms / 1e6,
+                                  "frac_of_measured_peak": ALGO_BYTES_PER_TRANSFORM * ROWS_PER_GPU / ms / 1e6 / peak}
+        del x, y
+        torch.cuda.empty_cache()
+        free, _ = torch.cuda.mem_get_info()
+        ch, length, hop, win = 64, 28_800_000, 512, 2048
+        if free < 90e9:
+            ch = 8
+        nframes = -(-length // hop)
+        sig = (torch.rand((ch, length), generator=g, device=dev) * 2 - 1).contiguous()
+        w = torch.from_numpy(W.hann(win)).to(dev)
+        frames = torch.empty((ch, nframes, win), dtype=torch.complex64, device=dev)
+        S.stft_batch(fft, sig, w, hop, nframes, out=frames)
+        torch.cuda.synchronize()
+        reps = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            S.stft_batch(fft, sig, w, hop, nframes, out=frames)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        algo = 4 * ch * length + 8 * ch * nframes * win
+        extra["stft"] = {"workload": f"Hann {win}, hop {hop}, {ch} ch x {length} samples (BASELINE configs[3])",
+                         "frames_per_s": ch * nframes / (ms * 1e-3), "ms": ms, "hbm_gbs": algo / ms / 1e6,
+                         "frac_of_measured_peak": algo / ms / 1e6 / peak}
+        out = torch.zeros((ch, length), device=dev)
+        S.istft_batch(fft, frames, w, hop, out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        S.istft_batch(fft, frames, w, hop, out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        extra["istft"] = {"frames_per_s": ch * nframes / (ms * 1e-3), "ms": ms, "hbm_gbs": algo / ms / 1e6,
+                          "frac_of_measured_peak": algo / ms / 1e6 / peak,
+                          "note": "two-kernel path (ifft+window, ordered overlap-add gather)"}
+        del sig, frames, out
+    except Exception as e:  # extras never invalidate the headline line
+        extra["error"] = f"{type(e).__name__}: {e}"
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ------------------------
+    cpu = None
+    if rank == 0 and n_gpus == 1:
+        threads = os.cpu_count() or 1
+        rows = 8192
+        reps = 1
+        gf, dt = cpu_port_gflops(rows, reps, threads)
+        while dt < 10.0 and reps < 64:  # aim at >= 10 s of CPU work in the timed sample
+            reps *= 2
+            gf, dt = cpu_port_gflops(rows, reps, threads)
+        cpu = {"value": gf, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{rows} rows x {reps} reps of N={N} ({dt:.1f} s), {threads} threads over rows, one planner "
+                         "per thread; oracle/kofft_oracle.c (C restatement; the Rust crate cannot be built here)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(n_gpus),
+            "hbm_gbs": ALGO_BYTES_PER_TRANSFORM * ROWS_PER_GPU * n_gpus / (ms_per_step * 1e-3) / 1e9,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,9 @@
 // kofft_cuda.cu -- the C ABI (include/kofft_cuda.h): context, device-resident planner tables,
 // argument checks that mirror the reference's error behaviour, and kernel dispatch.
+// the library is built with -fvisibility=hidden; only the C ABI is exported
+#pragma GCC visibility push(default)
 #include "../../include/kofft_cuda.h"
+#pragma GCC visibility pop
 
 #include <cuda_runtime.h>
 

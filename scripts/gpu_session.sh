@@ -1,0 +1,27 @@
+#!/bin/bash
+# One GPU-box session: parity tests, smoke, bench, ncu launch list + full capture of the headline kernel.
+# Usage (from the repo root, under gpurun): bash scripts/gpu_session.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.csv 2>&1
+echo "== smoke" | tee $OUT/summary.txt
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke exit $?" | tee -a $OUT/summary.txt
+tail -3 $OUT/smoke.log | tee -a $OUT/summary.txt
+echo "== pytest -m gpu" | tee -a $OUT/summary.txt
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a $OUT/summary.txt
+tail -40 $OUT/pytest_gpu.log | tee -a $OUT/summary.txt
+echo "== bench" | tee -a $OUT/summary.txt
+timeout 900 python bench.py --steps 50 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?" | tee -a $OUT/summary.txt
+cat $OUT/bench.json | tee -a $OUT/summary.txt
+tail -5 $OUT/bench.err | tee -a $OUT/summary.txt
+echo "== bench reference arm" | tee -a $OUT/summary.txt
+timeout 600 python bench.py --impl reference --steps 10 --warmup 2 > $OUT/bench_ref.json 2>> $OUT/bench.err
+cat $OUT/bench_ref.json | tee -a $OUT/summary.txt
+echo "== ncu launch list" | tee -a $OUT/summary.txt
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 3 --warmup 3 > $OUT/ncu_launches.log 2>&1; echo "ncu list exit $?" | tee -a $OUT/summary.txt
+echo "== ncu full" | tee -a $OUT/summary.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_cta_kernel -s 3 -c 2 -o $OUT/prof_c2c \
+    python scripts/one_kernel.py c2c > $OUT/ncu_full.log 2>&1; echo "ncu full exit $?" | tee -a $OUT/summary.txt
+ls -la $OUT | tee -a $OUT/summary.txt

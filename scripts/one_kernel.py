@@ -1,0 +1,32 @@
+"""Launches one headline kernel a few times (target command for `ncu --set full`)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+import kofft_b200  # noqa: E402
+from kofft_b200 import stft as S  # noqa: E402
+from kofft_b200 import window as W  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "c2c"
+exact = not (len(sys.argv) > 2 and sys.argv[2] == "fast")
+fft = kofft_b200.CudaFftImpl(device=0, exact=exact)
+g = torch.Generator(device="cuda").manual_seed(0)
+if which == "c2c":
+    x = torch.view_as_complex(torch.rand((65536, 4096, 2), generator=g, device="cuda") * 2 - 1).contiguous()
+    y = torch.empty_like(x)
+    for _ in range(6):
+        fft.fft_batch(x, out=y)
+elif which == "stft":
+    ch, length, hop, win = 16, 28_800_000, 512, 2048
+    nframes = -(-length // hop)
+    sig = (torch.rand((ch, length), generator=g, device="cuda") * 2 - 1).contiguous()
+    w = torch.from_numpy(W.hann(win)).cuda()
+    frames = torch.empty((ch, nframes, win), dtype=torch.complex64, device="cuda")
+    for _ in range(6):
+        S.stft_batch(fft, sig, w, hop, nframes, out=frames)
+elif which == "rfft":
+    x = (torch.rand((4096, 32768), generator=g, device="cuda") * 2 - 1).contiguous()
+    for _ in range(6):
+        fft.rfft_batch(x)
+torch.cuda.synchronize()

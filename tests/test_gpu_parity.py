@@ -1,0 +1,548 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libkofft_cuda.so via the host-side mirror of the reference interface (kofft_b200), and is
+compared with the CPU oracle on the same seeded inputs:
+
+  * EXACT mode (default): bit-identical to the oracle.
+  * FAST mode: relative L2 <= 1e-5 (the north-star tolerance, BASELINE.json).
+
+The first block restates the reference's own tests against `CudaFftImpl` so they read like
+the originals (file:line cited per test)."""
+import numpy as np
+import pytest
+
+from tests.conftest import rel_l2, uniform_c64
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5  # BASELINE.json north_star tolerance: relative L2 vs kofft's f32 output
+
+
+def c32(*vals):
+    return np.array(vals, dtype=np.complex64)
+
+
+# ------------------------------------------------------------------------------------------
+# 1. the reference's tests, restated against the GPU backend
+# ------------------------------------------------------------------------------------------
+def test_fft_ifft_f32(cuda_fft):  # src/lib.rs:178-199
+    data = c32(1, 0, 0, 0)
+    cuda_fft.fft(data)
+    assert np.all(np.abs(data.real - 1) < 1e-6) and np.all(np.abs(data.imag) < 1e-6)
+    cuda_fft.ifft(data)
+    assert abs(data[0].real - 1) < 1e-6 and np.all(np.abs(data[1:]) < 1e-6)
+
+
+def test_fft_all_zeros_all_ones(cuda_fft):  # src/lib.rs:242-264
+    data = np.zeros(8, np.complex64)
+    cuda_fft.fft(data)
+    assert np.all(np.abs(data) < 1e-6)
+    data = np.ones(8, np.complex64)
+    cuda_fft.fft(data)
+    assert abs(data[0].real - 8) < 1e-6 and np.all(np.abs(data[1:]) < 1e-6)
+
+
+def test_fft_symmetries(cuda_fft):  # src/lib.rs:360-388
+    d = c32(1, 2, 3, 4)
+    cuda_fft.fft(d)
+    assert abs(d[1].real - d[3].real) < 1e-6 and abs(d[1].imag + d[3].imag) < 1e-6
+    d = c32(1j, 2j, 3j, 4j)
+    cuda_fft.fft(d)
+    assert abs(d[1].real + d[3].real) < 1e-6 and abs(d[1].imag - d[3].imag) < 1e-6
+
+
+def test_fft_empty_single_nonpow2(cuda_fft):  # src/lib.rs:313-318, 342-349
+    import kofft_b200 as k
+
+    with pytest.raises(k.EmptyInput):
+        cuda_fft.fft(np.zeros(0, np.complex64))
+    with pytest.raises(k.EmptyInput):
+        cuda_fft.ifft(np.zeros(0, np.complex64))
+    d = c32(1)
+    cuda_fft.fft(d)
+    assert d[0] == 1
+    with pytest.raises(k.NonPowerOfTwoNoStd):  # Bluestein is out of scope for this backend
+        cuda_fft.fft(c32(1, 2, 3))
+
+
+def test_fft_out_of_place(cuda_fft, oracle):  # src/lib.rs:281-311, 320-329
+    import kofft_b200 as k
+
+    inp = c32(1, 2, 3, 4)
+    out = np.zeros(4, np.complex64)
+    cuda_fft.fft_out_of_place(inp, out)
+    assert np.array_equal(inp, c32(1, 2, 3, 4)) and np.array_equal(out, oracle.fft(inp))
+    assert np.array_equal(cuda_fft.fft_vec(inp), oracle.fft(inp))
+    with pytest.raises(k.MismatchedLengths):
+        cuda_fft.fft_out_of_place(c32(1, 2), np.zeros(3, np.complex64))
+    cuda_fft.ifft_out_of_place(out.copy(), out)
+    assert np.all(np.abs(out - inp) < 1e-6)
+
+
+def test_roundtrip_repeated_and_large_values(cuda_fft):  # src/lib.rs:390-429
+    d = c32(1000, 2000, 3000, 4000)
+    orig = d.copy()
+    cuda_fft.fft(d)
+    cuda_fft.ifft(d)
+    assert np.all(np.abs(d - orig) < 1e-3)
+    d = c32(1, 2, 3, 4)
+    for _ in range(10):
+        cuda_fft.fft(d)
+        cuda_fft.ifft(d)
+    assert np.all(np.abs(d - c32(1, 2, 3, 4)) < 1e-4)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32])
+def test_fft_matches_dft_for_powers_of_two(cuda_fft, n):  # tests/pow2.rs:18-31
+    i = np.arange(n, dtype=np.float32)
+    data = (i - 0.5j * i).astype(np.complex64)
+    expected = np.fft.fft(data.astype(np.complex128))
+    cuda_fft.fft(data)
+    assert np.all(np.abs(data.real - expected.real) < 1e-2) and np.all(np.abs(data.imag - expected.imag) < 1e-2)
+
+
+@pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024])
+def test_stockham_matches_fft(cuda_fft, oracle, n):  # tests/stockham_parity.rs, stockham_large.rs
+    import kofft_b200 as k
+
+    i = np.arange(n, dtype=np.float32)
+    src = ((i - 0.25j * i) if n <= 256 else (np.sin(i) + 1j * np.cos(i))).astype(np.complex64)
+    data, expected = src.copy(), src.copy()
+    cuda_fft.fft(expected)
+    cuda_fft.fft_with_strategy(data, k.FftStrategy.SplitRadix)  # == stockham_fft (src/fft.rs:1360)
+    assert np.array_equal(data, expected) and np.array_equal(data, oracle.fft(src))
+
+
+def test_parallel_stockham_4096(cuda_fft, oracle):  # tests/parallel_stockham.rs:6-27
+    import kofft_b200 as k
+
+    i = np.arange(4096, dtype=np.float32)
+    a = (i + 2j * i).astype(np.complex64)
+    b = a.copy()
+    k.fft_parallel(a)
+    cuda_fft.fft(b)
+    assert np.all(np.abs(a - b) < 1e-4) and np.array_equal(b, oracle.fft((i + 2j * i).astype(np.complex64)))
+
+
+def test_split(cuda_fft):  # tests/split.rs:11-27, 48-78
+    import kofft_b200 as k
+
+    data = np.arange(16, dtype=np.float32).astype(np.complex64)
+    re, im = data.real.copy(), data.imag.copy()
+    aos = data.copy()
+    cuda_fft.fft(aos)
+    k.fft_split(re, im)
+    assert np.all(np.abs(aos.real - re) < 1e-6) and np.all(np.abs(aos.imag - im) < 1e-6)
+    i = np.arange(64, dtype=np.float32)
+    re, im = i.copy(), -i
+    cuda_fft.fft_split(re, im)
+    cuda_fft.ifft_split(re, im)
+    assert np.all(np.abs(re - i) < 1e-4) and np.all(np.abs(im + i) < 1e-4)
+    with pytest.raises(k.MismatchedLengths):
+        cuda_fft.fft_split(np.zeros(4, np.float32), np.zeros(3, np.float32))
+
+
+def test_planner_device_table(cuda_fft, oracle):  # tests/twiddle.rs:7-13 + "device-resident twiddle tables"
+    import torch
+
+    p = cuda_fft.planner
+    t = p.get_twiddles(8)
+    e = np.exp(-2j * np.pi / 8)
+    assert abs(t[1].real - e.real) < 1e-6 and abs(t[1].imag - e.imag) < 1e-6
+    ptr1, ptr2 = p.device_twiddles(4096), p.device_twiddles(4096)
+    assert ptr1 == ptr2 and ptr1 != 0  # pointer-stable like the reference's Arc
+    # read the device copy back and compare with the oracle's table
+    from cuda import cudart
+
+    host = np.empty(2048, np.complex64)
+    (err,) = cudart.cudaMemcpy(host.ctypes.data, ptr1, host.nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+    assert int(err) == 0
+    assert np.array_equal(host, oracle.twiddles(4096))
+
+
+def test_rfft_roundtrip_and_errors(cuda_fft, oracle):  # src/lib.rs:431-478, src/rfft.rs:892-906
+    import kofft_b200 as k
+
+    for vals in ([1, 2, 3, 4], [1, 2, 3, 4, 5, 6, 7, 8]):
+        inp = np.array(vals, np.float32)
+        freq = np.zeros(len(inp) // 2 + 1, np.complex64)
+        scratch = np.zeros(len(inp) // 2, np.complex64)
+        cuda_fft.rfft_with_scratch(inp, freq, scratch)
+        assert abs(freq[0].imag) < 1e-6 and abs(freq[-1].imag) < 1e-6
+        assert np.array_equal(freq, oracle.rfft(inp))
+        out = np.zeros(len(inp), np.float32)
+        cuda_fft.irfft_with_scratch(freq, out, scratch)
+        assert np.all(np.abs(out - inp) < 1e-5)
+    with pytest.raises(k.MismatchedLengths):
+        cuda_fft.rfft(np.array([1, 2, 3, 4], np.float32), np.zeros(4, np.complex64))
+    with pytest.raises(k.InvalidValue):
+        cuda_fft.rfft(np.array([1, 2, 3], np.float32), np.zeros(2, np.complex64))
+    with pytest.raises(k.EmptyInput):
+        cuda_fft.rfft(np.zeros(0, np.float32), np.zeros(1, np.complex64))
+    planner = k.RfftPlanner()  # tests/rfft_dispatch.rs:5-24
+    inp = np.array([1, 2, 3, 4], np.float32)
+    freq, scratch, out = np.zeros(3, np.complex64), np.zeros(2, np.complex64), np.zeros(4, np.float32)
+    planner.rfft_with_scratch(cuda_fft, inp, freq, scratch)
+    planner.irfft_with_scratch(cuda_fft, freq, out, scratch)
+    assert np.all(np.abs(out - inp) < 1e-5)
+
+
+def test_rfft_sin32(cuda_fft, oracle):  # tests/rfft_arch_parity.rs:11-46
+    x = np.sin(np.arange(32, dtype=np.float32))
+    f = np.zeros(17, np.complex64)
+    cuda_fft.rfft(x, f)
+    assert np.array_equal(f, oracle.rfft(x))
+
+
+def test_stft_errors(cuda_fft):  # tests/stft.rs:6-14, src/stft.rs:83-89
+    import kofft_b200 as k
+    from kofft_b200 import stft as S
+    from kofft_b200.window import hann
+
+    with pytest.raises(k.MismatchedLengths):
+        S.stft(np.zeros(10, np.float32), hann(4), 4, [None] * 2, cuda_fft)
+    with pytest.raises(k.InvalidHopSize):
+        S.stft(np.zeros(10, np.float32), hann(4), 0, [None] * 3, cuda_fft)
+    with pytest.raises(k.InvalidHopSize):
+        S.istft([], hann(4), 0, np.zeros(4, np.float32), np.zeros(4, np.float32), cuda_fft)
+    with pytest.raises(k.MismatchedLengths):
+        S.istft([np.zeros(4, np.complex64)], hann(4), 2, np.zeros(4, np.float32), np.zeros(5, np.float32), cuda_fft)
+    with pytest.raises(k.MismatchedLengths):
+        S.istft([np.zeros(3, np.complex64)], hann(4), 2, np.zeros(4, np.float32), np.zeros(4, np.float32), cuda_fft)
+
+
+def test_stft_istft_roundtrip(cuda_fft):  # src/stft.rs:527-630, 800-813
+    from kofft_b200 import stft as S
+
+    signal = np.arange(1, 9, dtype=np.float32)
+    window = np.ones(4, np.float32)
+    frames = [None] * 4
+    S.stft(signal, window, 2, frames, cuda_fft)
+    out, scratch = np.zeros(8, np.float32), np.zeros(8, np.float32)
+    S.istft(frames, window, 2, out, scratch, cuda_fft)
+    assert np.all(np.abs(out - signal) < 1e-4)
+
+
+def test_istft_stream_reconstructs_and_flushes(cuda_fft):  # tests/istft_stream.rs:5-49 (assert_eq!)
+    from kofft_b200 import stft as S
+
+    signal = np.arange(1, 9, dtype=np.float32)
+    win_len, hop = 4, 2
+    window = np.ones(win_len, np.float32)
+    st = S.StftStream(signal, window, hop, cuda_fft)
+    ist = S.IstftStream(win_len, hop, window.copy(), cuda_fft)
+    frame = np.zeros(win_len, np.complex64)
+    frames, stream_out = [], []
+    while st.next_frame(frame):
+        frames.append(frame.copy())
+        stream_out.extend(ist.push_frame(frame).tolist())
+    tail = ist.flush().copy()
+    stream_out.extend(tail.tolist())
+    offline = np.zeros(len(signal) + win_len - hop, np.float32)
+    S.istft([f.copy() for f in frames], window, hop, offline, np.zeros_like(offline), cuda_fft)
+    assert np.array_equal(np.array(stream_out[: len(signal)], np.float32), offline[: len(signal)])
+    assert len(tail) == win_len - hop and np.array_equal(tail, offline[len(signal):])
+
+
+def test_zero_window(cuda_fft):  # src/stft.rs:699-720
+    from kofft_b200 import stft as S
+
+    signal = np.arange(1, 9, dtype=np.float32)
+    window = np.zeros(4, np.float32)
+    frames = [None] * 4
+    S.stft(signal, window, 2, frames, cuda_fft)
+    assert not np.stack(frames).any()
+    out = np.zeros(8, np.float32)
+    S.istft(frames, window, 2, out, np.zeros(8, np.float32), cuda_fft)
+    assert not out.any()
+
+
+def test_parallel_equals_serial(cuda_fft):  # src/visual/spectrogram.rs:281-297 (bit-exact)
+    from kofft_b200 import stft as S
+    from kofft_b200.window import hann
+
+    signal = np.arange(16, dtype=np.float32)
+    a, b = [None] * 8, [None] * 8
+    S.stft(signal, hann(4), 2, a, cuda_fft)
+    S.parallel(signal, hann(4), 2, b, cuda_fft)
+    assert np.array_equal(np.stack(a), np.stack(b))
+
+
+# ------------------------------------------------------------------------------------------
+# 2. parity with the oracle on seeded inputs, every size
+# ------------------------------------------------------------------------------------------
+SIZES = [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("inverse", [False, True])
+def test_c2c_batch_bit_exact(cuda_fft, cuda_fft_fast, oracle, n, inverse):
+    rng = np.random.default_rng(n + 100 * inverse)
+    rows = 37 if n <= 4096 else 5  # ragged vs transforms-per-CTA and vs the grid
+    x = uniform_c64(rng, (rows, n))
+    ref = oracle.fft_batch(x, inverse=inverse, nthreads=4)
+    y = x.copy()
+    cuda_fft.fft_batch(y, inverse=inverse)
+    assert np.array_equal(y, ref), f"exact mode differs: rel {rel_l2(y, ref):.3e}"
+    z = x.copy()
+    cuda_fft_fast.fft_batch(z, inverse=inverse)
+    assert rel_l2(z, ref) <= TOL
+    worst = max(rel_l2(z[r], ref[r]) for r in range(rows))
+    assert worst <= TOL
+
+
+def test_config1_basic_usage(cuda_fft, oracle):
+    """BASELINE configs[0]: 1024-point FFT + IFFT of (sin(0.1 i), 0) (examples/basic_usage.rs:232-241)."""
+    i = np.arange(1024, dtype=np.float32)
+    x = np.sin(np.float32(0.1) * i).astype(np.float32).astype(np.complex64)
+    y = x.copy()
+    cuda_fft.fft(y)
+    assert np.array_equal(y, oracle.fft(x))
+    cuda_fft.ifft(y)
+    assert np.array_equal(y, oracle.ifft(oracle.fft(x)))
+    assert np.max(np.abs(y - x)) < 1e-4
+
+
+def test_reference_dynamic_range_inputs(cuda_fft, oracle):
+    # kofft-bench uses (i, 0) (bench_fft.rs:109); tests use (i, 2i): large dynamic range
+    for n in (1024, 4096):
+        i = np.arange(n, dtype=np.float32)
+        for x in ((i + 0j), (i + 2j * i)):
+            x = x.astype(np.complex64)
+            y = x.copy()
+            cuda_fft.fft(y)
+            assert np.array_equal(y, oracle.fft(x))
+
+
+def test_device_tensor_path(cuda_fft, oracle):
+    import torch
+
+    rng = np.random.default_rng(5)
+    x = uniform_c64(rng, (300, 2048))
+    d = torch.from_numpy(x).cuda()
+    out = torch.empty_like(d)
+    cuda_fft.fft_batch(d, out=out)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), oracle.fft_batch(x, nthreads=4))
+    assert np.array_equal(d.cpu().numpy(), x)  # out-of-place leaves the input alone
+    cuda_fft.fft_batch(d, inverse=True)  # in place
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy(), oracle.fft_batch(x, inverse=True, nthreads=4))
+
+
+@pytest.mark.parametrize("n", [1, 2, 16, 64, 1024])
+def test_strided_and_out_of_place_strided(cuda_fft, oracle, n):
+    import kofft_b200 as k
+
+    rng = np.random.default_rng(n)
+    stride = 3
+    buf = uniform_c64(rng, ((n - 1) * stride + 1 + 2,))
+    for inverse in (False, True):
+        a = buf.copy()
+        scratch = np.zeros(n, np.complex64)
+        (cuda_fft.ifft_strided if inverse else cuda_fft.fft_strided)(a, stride, scratch)
+        assert np.array_equal(a, oracle.fft_strided(buf, stride, n, inverse))
+    a = buf.copy()
+    cuda_fft.fft_strided_alloc(a[: n * stride], stride)
+    inp = uniform_c64(rng, (n * 2,))
+    out = np.full(n * 4, 9 - 9j, np.complex64)
+    cuda_fft.fft_out_of_place_strided(inp, 2, out, 4)
+    assert np.array_equal(out, oracle.fft_out_of_place_strided(inp, 2, np.full(n * 4, 9 - 9j, np.complex64), 4))
+    with pytest.raises(k.InvalidStride):
+        cuda_fft.fft_strided(buf.copy(), 0, np.zeros(n, np.complex64))
+    with pytest.raises(k.InvalidStride):
+        cuda_fft.fft_out_of_place_strided(inp, 0, out, 4)
+    if n > 2:
+        with pytest.raises(k.MismatchedLengths):
+            cuda_fft.fft_strided(buf[: n].copy(), stride, np.zeros(n, np.complex64))
+
+
+@pytest.mark.parametrize("m", [1, 2, 4, 16, 32, 256, 2048, 16384])
+def test_rfft_irfft_batch(cuda_fft, cuda_fft_fast, oracle, m):
+    rng = np.random.default_rng(m)
+    n, rows = 2 * m, (9 if m <= 2048 else 3)
+    x = rng.uniform(-1, 1, (rows, n)).astype(np.float32)
+    ref = oracle.rfft_batch(x, nthreads=4)
+    y = cuda_fft.rfft_batch(x)
+    assert np.array_equal(y, ref), rel_l2(y, ref)
+    assert rel_l2(cuda_fft_fast.rfft_batch(x), ref) <= TOL
+    back = oracle.irfft_batch(ref, n, nthreads=4)
+    assert np.array_equal(cuda_fft.irfft_batch(ref, n), back)
+    assert rel_l2(cuda_fft_fast.irfft_batch(ref, n), back) <= TOL
+
+
+def test_rfft_fma_table_flavour(oracle):
+    """xtask's `-C target-feature=+fma` build fuses Complex::mul in the rfft table recurrence."""
+    import kofft_b200 as k
+
+    fft = k.CudaFftImpl(device=0, exact=True)
+    planner = k.RfftPlanner(fma_mul=True)
+    x = np.random.default_rng(3).uniform(-1, 1, 4096).astype(np.float32)
+    f = np.zeros(2049, np.complex64)
+    planner.rfft(fft, x, f)
+    assert np.array_equal(f, oracle.rfft(x, fma_mul=True))
+    assert not np.array_equal(f, oracle.rfft(x, fma_mul=False))
+
+
+@pytest.mark.parametrize("win_len,hop,length,kind", [(4, 2, 8, "hann"), (16, 4, 50, "hamming"), (64, 16, 1000, "blackman"),
+                                                     (2048, 512, 40000, "hann"), (256, 300, 700, "kaiser"),
+                                                     (1024, 256, 9999, "hann")])
+def test_stft_istft_batch(cuda_fft, cuda_fft_fast, oracle, win_len, hop, length, kind):
+    from kofft_b200 import stft as S
+    from kofft_b200 import window as W
+
+    rng = np.random.default_rng(win_len + hop)
+    ch = 3
+    sig = rng.uniform(-1, 1, (ch, length)).astype(np.float32)
+    w = {"hann": W.hann, "hamming": W.hamming, "blackman": W.blackman,
+         "kaiser": lambda n: W.kaiser(n, 8.6)}[kind](win_len)
+    nframes = -(-length // hop) + 2  # more frames than required: the reference fills them all
+    ref = oracle.stft_batch(sig, w, hop, nframes, nthreads=4)
+    frames = S.stft_batch(cuda_fft, sig, w, hop, nframes)
+    assert np.array_equal(frames, ref)
+    assert rel_l2(S.stft_batch(cuda_fft_fast, sig, w, hop, nframes), ref) <= TOL
+    out_len = length + 5
+    base = rng.uniform(-1, 1, (ch, out_len)).astype(np.float32)  # istft ACCUMULATES into output
+    want = np.stack([oracle.istft(ref[c], w, hop, base[c]) for c in range(ch)])
+    got = base.copy()
+    norm = np.zeros_like(got)
+    S.istft_batch(cuda_fft, ref, w, hop, got, norm)
+    assert np.array_equal(got, want)
+    want0 = np.stack([oracle.istft_parallel(ref[c], w, hop, base[c]) for c in range(ch)])
+    got0 = base.copy()
+    S.istft_batch(cuda_fft, ref, w, hop, got0, None, zero_uncovered=True)
+    assert np.array_equal(got0, want0)
+    fast = base.copy()
+    S.istft_batch(cuda_fft_fast, ref, w, hop, fast, np.zeros_like(fast))
+    assert rel_l2(fast, want) <= TOL
+
+
+def test_stft_device_tensors(cuda_fft, oracle):
+    import torch
+    from kofft_b200 import stft as S
+    from kofft_b200 import window as W
+
+    rng = np.random.default_rng(11)
+    sig = rng.uniform(-1, 1, (4, 48000)).astype(np.float32)
+    w = W.hann(2048)
+    nframes = -(-48000 // 512)
+    d_sig, d_w = torch.from_numpy(sig).cuda(), torch.from_numpy(w).cuda()
+    frames = S.stft_batch(cuda_fft, d_sig, d_w, 512, nframes)
+    torch.cuda.synchronize()
+    ref = oracle.stft_batch(sig, w, 512, nframes, nthreads=4)
+    assert np.array_equal(frames.cpu().numpy(), ref)
+    out = torch.zeros((4, 48000), device="cuda")
+    norm = torch.zeros_like(out)
+    S.istft_batch(cuda_fft, frames, d_w, 512, out, norm)
+    torch.cuda.synchronize()
+    want = np.stack([oracle.istft(ref[c], w, 512, np.zeros(48000, np.float32)) for c in range(4)])
+    assert np.array_equal(out.cpu().numpy(), want)
+    # reconstruction away from the edges (sample 0 has w = 0; full overlap from win_len on)
+    assert np.max(np.abs(want[:, 2048:-2048] - sig[:, 2048:-2048])) < 2e-3
+
+
+def test_batch_free_functions_ragged(cuda_fft, oracle):  # src/fft.rs:2156-2191
+    import kofft_b200 as k
+
+    rng = np.random.default_rng(9)
+    rows = [uniform_c64(rng, (n,)) for n in (64, 64, 64, 8, 1024, 1024, 1)]
+    want = [oracle.fft(r) if len(r) > 1 else r.copy() for r in rows]
+    k.batch(cuda_fft, rows)
+    for a, b in zip(rows, want):
+        assert np.array_equal(a, b)
+    k.batch_inverse(cuda_fft, rows)
+    k.multi_channel(cuda_fft, rows)
+    for a, b in zip(rows, want):  # fft(ifft(fft(x))): kofft's own round-trip error is ~3e-5 at N=1024
+        assert rel_l2(a, b) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------
+# 3. BASELINE.json full sizes: sampled rows against the oracle + size-independent properties
+# ------------------------------------------------------------------------------------------
+def test_config2_full_size_c2c_4096x65536(cuda_fft, cuda_fft_fast, oracle):
+    import torch
+
+    n, batch = 4096, 65536
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = (torch.rand((batch, n, 2), generator=g, device="cuda") * 2 - 1)
+    x = torch.view_as_complex(x).contiguous()
+    y = torch.empty_like(x)
+    cuda_fft.fft_batch(x, out=y)
+    torch.cuda.synchronize()
+    rows = np.random.default_rng(0).choice(batch, 96, replace=False)
+    rows = np.concatenate([rows, [0, 1, batch - 1]])
+    xs = x[torch.from_numpy(rows).cuda()].cpu().numpy()
+    ys = y[torch.from_numpy(rows).cuda()].cpu().numpy()
+    ref = oracle.fft_batch(xs, nthreads=8)
+    assert np.array_equal(ys, ref)  # bit-exact on every sampled row
+    # no worse than the reference's own error against an f64 DFT (north star, second criterion)
+    f64 = np.fft.fft(xs[:16].astype(np.complex128), axis=1)
+    assert rel_l2(ys[:16], f64) <= rel_l2(ref[:16], f64) * (1 + 1e-6)
+    # FAST mode on the whole batch: rel-L2 vs EXACT over everything, and worst row
+    z = torch.empty_like(x)
+    cuda_fft_fast.fft_batch(x, out=z)
+    torch.cuda.synchronize()
+    num = torch.linalg.vector_norm((z - y).view(batch, -1), dim=1)
+    den = torch.linalg.vector_norm(y.view(batch, -1), dim=1)
+    assert float((num / den).max()) <= TOL
+    del z
+    # Parseval per row (size-independent): sum|Y|^2 = N sum|x|^2 up to kofft's table error
+    ex = torch.linalg.vector_norm(x, dim=1) ** 2
+    ey = torch.linalg.vector_norm(y, dim=1) ** 2
+    assert float(((ey / (n * ex)) - 1).abs().max()) < 2e-3
+    # linearity: F(a x1 + x2) = a F(x1) + F(x2) on the first 4096 rows (f32 round-off bound)
+    a = 0.5
+    lin_in = (a * x[:4096] + x[4096:8192]).contiguous()
+    lin = torch.empty_like(lin_in)
+    cuda_fft.fft_batch(lin_in, out=lin)
+    torch.cuda.synchronize()
+    comb = a * y[:4096] + y[4096:8192]
+    assert float(torch.linalg.vector_norm(lin - comb) / torch.linalg.vector_norm(comb)) < 1e-6
+    # round trip through the inverse, in place, whole batch
+    cuda_fft.fft_batch(y, inverse=True)
+    torch.cuda.synchronize()
+    err = torch.linalg.vector_norm((y - x).view(batch, -1), dim=1) / torch.linalg.vector_norm(x.view(batch, -1), dim=1)
+    assert float(err.max()) < 5e-4  # kofft's own fft->ifft round trip at N=4096 is ~1.7e-4
+    back = oracle.fft_batch(ref, inverse=True, nthreads=8)
+    assert np.array_equal(y[torch.from_numpy(rows).cuda()].cpu().numpy(), back)
+
+
+def test_config4_stft_full_shape_sampled(cuda_fft, oracle):
+    """BASELINE configs[3] shape (Hann 2048, hop 512, 48 kHz) on as many channels as fit
+    comfortably: sampled frames bit-exact vs the oracle, ISTFT round trip."""
+    import torch
+    from kofft_b200 import stft as S
+    from kofft_b200 import window as W
+
+    free, _ = torch.cuda.mem_get_info()
+    ch = 64 if free > 100e9 else 8
+    length = 28_800_000 if free > 100e9 else 2_880_000
+    hop, win_len = 512, 2048
+    nframes = -(-length // hop)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    t = torch.arange(length, device="cuda", dtype=torch.float32) / 48000.0
+    sig = (0.5 * torch.sin(2 * np.pi * 440.0 * t) + 0.3 * torch.sin(2 * np.pi * 1000.0 * t)
+           + 0.1 * torch.sin(2 * np.pi * 5000.0 * t))
+    sig = (sig.unsqueeze(0) + 0.1 * (torch.rand((ch, length), generator=g, device="cuda") * 2 - 1)).contiguous()
+    w = W.hann(win_len)
+    d_w = torch.from_numpy(w).cuda()
+    frames = S.stft_batch(cuda_fft, sig, d_w, hop, nframes)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(4)
+    for c in rng.choice(ch, 3, replace=False):
+        fs = np.concatenate([rng.choice(nframes, 24, replace=False), [0, 1, nframes - 4, nframes - 1]])
+        host_sig = sig[c].cpu().numpy()
+        for f in fs:
+            seg = np.zeros(win_len, np.float32)
+            part = host_sig[f * hop: f * hop + win_len]
+            seg[: len(part)] = part
+            want = oracle.fft((seg * w).astype(np.complex64))
+            assert np.array_equal(frames[c, f].cpu().numpy(), want), (c, f)
+    out = torch.zeros((ch, length), device="cuda")
+    S.istft_batch(cuda_fft, frames, d_w, hop, out)
+    torch.cuda.synchronize()
+    # fully overlapped interior reconstructs the input (Hann^2 / sum Hann^2 at 75 % overlap)
+    err = (out[:, win_len:-win_len] - sig[:, win_len:-win_len]).abs().max()
+    assert float(err) < 5e-3
+    c = int(rng.integers(ch))
+    n_chk = 20 * hop + win_len
+    want = oracle.istft(frames[c, : 20 + 4].cpu().numpy(), w, hop, np.zeros(n_chk, np.float32))
+    assert np.array_equal(out[c, : 20 * hop].cpu().numpy(), want[: 20 * hop])
