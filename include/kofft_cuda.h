@@ -15,8 +15,9 @@
  *    KOFFT_ERR_NON_POWER_OF_TWO_NO_STD (the reference's Bluestein path, src/fft.rs:1083-1132,
  *    is outside this backend's scope).
  *  - Host-pointer functions are synchronous and never retain the caller's pointers.
- *    Device-pointer functions are stream-ordered on `stream` (NULL = the context's stream)
- *    and return as soon as the work is enqueued.
+ *    Device-pointer functions are stream-ordered on `stream`, a cudaStream_t passed as
+ *    void* with CUDA's own meaning (NULL = the legacy default stream; kofft_cuda_stream()
+ *    returns the context's private stream), and return as soon as the work is enqueued.
  *  - A context belongs to one device and is not thread-safe (the reference's
  *    ScalarFftImpl is !Sync for the same reason, src/fft.rs:589-605).
  *  - There is no CPU fallback: without a CUDA device kofft_cuda_create fails.
@@ -60,6 +61,9 @@ int kofft_cuda_set_exact(kofft_cuda_ctx *ctx, int exact);
 int kofft_cuda_get_exact(const kofft_cuda_ctx *ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 unsigned long long kofft_cuda_launch_count(const kofft_cuda_ctx *ctx);
+/* enable (default) / disable the TMA-staged input prefetch (cp.async.bulk + mbarrier); the
+ * library falls back to plain loads by itself when a pointer is not 16-byte aligned */
+int kofft_cuda_set_tma_staging(kofft_cuda_ctx *ctx, int enable);
 /* 0 = let the library size the grid (occupancy x SM count); otherwise cap the CTA count */
 int kofft_cuda_set_max_ctas(kofft_cuda_ctx *ctx, int max_ctas);
 

@@ -47,7 +47,13 @@ struct Plan {
     static constexpr int CTA = T < 256 ? 256 : T;    // threads per CTA
     static constexpr int TPC = CTA / T;              // transforms per CTA
     static constexpr int PADN = N + (N >> 4);        // padded float2 per exchange buffer
-    static constexpr int SMEM_BYTES = 2 * TPC * PADN * 8;
+    // two exchange buffers (one __syncthreads per exchange) when they fit, else one
+    static constexpr int NBUF = (2 * TPC * PADN * 8 <= 160 * 1024) ? 2 : 1;
+    static constexpr int XCHG_BYTES = NBUF * TPC * PADN * 8;
+    static constexpr int STAGE_BYTES = TPC * N * 8;  // TMA landing zone for the next row group
+    static constexpr bool CAN_STAGE = XCHG_BYTES + STAGE_BYTES <= 226 * 1024;
+    static constexpr int SMEM_BYTES = XCHG_BYTES;
+    static constexpr int SMEM_BYTES_STAGED = XCHG_BYTES + STAGE_BYTES;
     static constexpr bool TW_REGS = L <= 12;         // later-pass twiddles live in registers
 
     static constexpr int r(int p) { return p == 0 ? R0 : 4; }

@@ -10,17 +10,18 @@ namespace kofft {
 
 namespace {
 
-template <int L, bool EXACT, class IO>
-cudaError_t launch_one(const IO &io, const LaunchArgs &a)
+template <int L, bool EXACT, class IO, bool STAGED>
+cudaError_t launch_variant(const IO &io, const LaunchArgs &a)
 {
     using P = Plan<L>;
-    auto kern = fft_cta_kernel<L, EXACT, IO>;
+    constexpr int smem = STAGED ? P::SMEM_BYTES_STAGED : P::SMEM_BYTES;
+    auto kern = fft_cta_kernel<L, EXACT, IO, STAGED>;
     static int occ = 0; // per instantiation
     if (occ == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, P::CTA, P::SMEM_BYTES);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, P::CTA, smem);
         if (e != cudaSuccess) return e;
         occ = o > 0 ? o : 1;
     }
@@ -28,8 +29,18 @@ cudaError_t launch_one(const IO &io, const LaunchArgs &a)
     long cap = a.max_ctas > 0 ? a.max_ctas : (long)occ * a.num_sms;
     int grid = (int)(groups < cap ? groups : cap);
     if (grid <= 0) return cudaSuccess;
-    kern<<<grid, P::CTA, P::SMEM_BYTES, a.stream>>>(io, a.tw0, a.table, a.rows);
+    kern<<<grid, P::CTA, smem, a.stream>>>(io, a.tw0, a.table, a.rows);
     return cudaGetLastError();
+}
+
+// a.staged: the host verified alignment / contiguity for the TMA-staged variant
+template <int L, bool EXACT, class IO>
+cudaError_t launch_one(const IO &io, const LaunchArgs &a)
+{
+    if constexpr (IO::kStageable && Plan<L>::CAN_STAGE) {
+        if (a.staged) return launch_variant<L, EXACT, IO, true>(io, a);
+    }
+    return launch_variant<L, EXACT, IO, false>(io, a);
 }
 
 template <int L, bool EXACT>

@@ -51,6 +51,20 @@ struct IoC2C {
     KHD void init(int) {}
     KHD float2 load(long row, int i) const { return pre_conj<INV>(KOFFT_LDG(in + row * n + i)); }
     KHD void store(long row, int i, float2 v) const { out[row * n + i] = post_conj_scale<INV>(v, scale); }
+    // staging: the TPC rows of group g are one contiguous byte range
+    static constexpr bool kStageable = true;
+    static constexpr bool kLoadAux = false;
+    KHD float load_aux(int) const { return 0.0f; }
+    KHD unsigned stage_bytes(long g, int tpc, long rows) const
+    {
+        long nr = rows - g * tpc;
+        return (unsigned)((nr < tpc ? nr : tpc) * n * 8);
+    }
+    KHD const void *stage_src(long g, int tpc) const { return in + g * tpc * n; }
+    KHD float2 load_staged(const unsigned char *stage, long, long, int slot, int i, float) const
+    {
+        return pre_conj<INV>(reinterpret_cast<const float2 *>(stage)[slot * n + i]);
+    }
 };
 
 // element e of row r lives at  re[r*row_stride + e*elem_stride]  (strides in floats);
@@ -64,6 +78,8 @@ struct IoGeneric {
     float *__restrict__ out_im;
     long in_es, in_rs, out_es, out_rs;
     float scale;
+    static constexpr bool kStageable = false;
+    static constexpr bool kLoadAux = false;
     KHD void init(int) {}
     KHD float2 load(long row, int i) const
     {
@@ -99,6 +115,35 @@ struct IoStft {
         return make_float2(x, 0.0f);
     }
     KHD void store(long row, int i, float2 v) const { frames[row * n + i] = v; }
+    // staging: the TPC consecutive frames of group g (same channel: the host only picks the
+    // staged kernel when nframes % TPC == 0) read one contiguous run of (TPC-1)*hop + n samples
+    static constexpr bool kStageable = true;
+    static constexpr bool kLoadAux = true;
+    KHD float load_aux(int i) const { return KOFFT_LDG(window + i); } // window value, kept in a register
+    KHD unsigned stage_bytes(long g, int tpc, long) const
+    {
+        long r0 = g * tpc;
+        long c = r0 / nframes, f0 = r0 - c * nframes;
+        long avail = len - f0 * hop;
+        long want = (long)(tpc - 1) * hop + n;
+        if (avail <= 0) return 0u;
+        return (unsigned)((avail < want ? avail : want) * 4);
+    }
+    KHD const void *stage_src(long g, int tpc) const
+    {
+        long r0 = g * tpc;
+        long c = r0 / nframes, f0 = r0 - c * nframes;
+        return signal + c * len + f0 * hop;
+    }
+    KHD float2 load_staged(const unsigned char *stage, long g, long row, int slot, int i, float w) const
+    {
+        long c = row / nframes, f = row - c * nframes;
+        long pos = f * hop + i;
+        float x = 0.0f;
+        if (pos < len) x = mul_rn(reinterpret_cast<const float *>(stage)[(long)slot * hop + i], w);
+        (void)g;
+        return make_float2(x, 0.0f);
+    }
 };
 
 // istft stage 1: time[row][i] = (ifft(frame).re) * window[i]; the overlap-add is a second,
@@ -117,6 +162,19 @@ struct IoIstft {
         float re = mul_rn(v.x, scale);
         time[row * n + i] = mul_rn(re, KOFFT_LDG(window + i));
     }
+    static constexpr bool kStageable = true;
+    static constexpr bool kLoadAux = false;
+    KHD float load_aux(int) const { return 0.0f; }
+    KHD unsigned stage_bytes(long g, int tpc, long rows) const
+    {
+        long nr = rows - g * tpc;
+        return (unsigned)((nr < tpc ? nr : tpc) * n * 8);
+    }
+    KHD const void *stage_src(long g, int tpc) const { return frames + g * tpc * n; }
+    KHD float2 load_staged(const unsigned char *stage, long, long, int slot, int i, float) const
+    {
+        return pre_conj<true>(reinterpret_cast<const float2 *>(stage)[slot * n + i]);
+    }
 };
 
 // rfft: input row = 2m reals viewed as m complex (pack is a reinterpretation); after the
@@ -131,6 +189,19 @@ struct IoRfft {
     KHD void init(int) {}
     KHD float2 load(long row, int i) const { return KOFFT_LDG(in + row * m + i); }
     KHD void store(long, int, float2) const {}
+    static constexpr bool kStageable = true;
+    static constexpr bool kLoadAux = false;
+    KHD float load_aux(int) const { return 0.0f; }
+    KHD unsigned stage_bytes(long g, int tpc, long rows) const
+    {
+        long nr = rows - g * tpc;
+        return (unsigned)((nr < tpc ? nr : tpc) * m * 8);
+    }
+    KHD const void *stage_src(long g, int tpc) const { return in + g * tpc * m; }
+    KHD float2 load_staged(const unsigned char *stage, long, long, int slot, int i, float) const
+    {
+        return reinterpret_cast<const float2 *>(stage)[slot * m + i];
+    }
     // Y: padded shared copy of the m FFT bins of this row
     KHD void epilogue(long row, int k, const float2 *Y) const
     {
@@ -161,6 +232,8 @@ struct IoIrfft {
     const float2 *__restrict__ rtw;
     long m;
     float scale; // 1/m
+    static constexpr bool kStageable = false;
+    static constexpr bool kLoadAux = false;
     KHD void init(int) {}
     KHD float2 load(long row, int i) const
     {
@@ -235,15 +308,35 @@ struct CtaFft {
     }
 
 #ifdef __CUDACC__
-    // rows: number of transforms; smem: 2 * TPC * PADN float2
+    // rows: number of transforms.  smem: [stage (STAGED only)] [NBUF exchange buffers].
+    //
+    // STAGED: the next row group's raw input (one contiguous byte range) is fetched by a single
+    // TMA bulk copy (cp.async.bulk, completion on an mbarrier) into the stage while the CTA is
+    // still computing passes 1.. of the current group, so the HBM read latency of group g+1
+    // overlaps the butterflies of group g.  Pass 0 then reads the stage instead of HBM.
+    template <bool STAGED>
     static __device__ void run(IO io, const Tw0 &tw0, const float2 *__restrict__ table, long rows, float2 *smem)
     {
         const int tid = threadIdx.x;
         const int slot = tid / P::T; // which of the CTA's TPC transforms
         const int t = tid - slot * P::T;
-        float2 *buf0 = smem + slot * P::PADN;
-        float2 *buf1 = buf0 + P::TPC * P::PADN;
+        unsigned char *stage = reinterpret_cast<unsigned char *>(smem);
+        float2 *xch = STAGED ? smem + P::STAGE_BYTES / 8 : smem;
+        float2 *buf0 = xch + slot * P::PADN;
+        float2 *buf1 = P::NBUF == 2 ? buf0 + P::TPC * P::PADN : buf0;
         int par = 0;
+        __shared__ __align__(8) unsigned long long mbar;
+        unsigned phase = 0;
+        const long groups = (rows + P::TPC - 1) / P::TPC;
+
+        if constexpr (STAGED) {
+            if (tid == 0) {
+                mbar_init(&mbar, 1);
+                fence_mbar_init();
+            }
+            __syncthreads();
+            if (tid == 0 && (long)blockIdx.x < groups) stage_issue(io, stage, &mbar, blockIdx.x, rows);
+        }
 
         io.init(t);
         float2 tw1[P1::NTW], tw2[P2::NTW], tw3[P3::NTW];
@@ -251,17 +344,36 @@ struct CtaFft {
             P1::load_tw(table, t, tw1);
             if (P::NP > 2) P2::load_tw(table, t, tw2);
         }
+        float aux[EPT]; // per-element constants of pass-0 loads (the STFT window), hoisted out of the row loop
+        if constexpr (STAGED && IO::kLoadAux) {
+#pragma unroll
+            for (int u = 0; u < P0::U; u++)
+#pragma unroll
+                for (int q = 0; q < P0::R; q++) aux[u * P0::R + q] = io.load_aux(P0::src_index(t, u, q));
+        }
 
-        const long groups = (rows + P::TPC - 1) / P::TPC;
         for (long g = blockIdx.x; g < groups; g += gridDim.x) {
             const long row = g * P::TPC + slot;
             const bool active = row < rows;
             float2 x[EPT];
-            if (active) {
-                load_global<P0>(io, row, t, x);
-            } else {
+            if constexpr (STAGED) {
+                if (io.stage_bytes(g, P::TPC, rows) != 0) {
+                    mbar_wait(&mbar, phase);
+                    phase ^= 1;
+                }
 #pragma unroll
-                for (int e = 0; e < EPT; e++) x[e] = make_float2(0.f, 0.f);
+                for (int u = 0; u < P0::U; u++)
+#pragma unroll
+                    for (int q = 0; q < P0::R; q++)
+                        x[u * P0::R + q] = io.load_staged(stage, g, row, slot, P0::src_index(t, u, q),
+                                                          IO::kLoadAux ? aux[u * P0::R + q] : 0.0f);
+            } else {
+                if (active) {
+                    load_global<P0>(io, row, t, x);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < EPT; e++) x[e] = make_float2(0.f, 0.f);
+                }
             }
             P0::compute(x, tw0.v);
 
@@ -269,7 +381,11 @@ struct CtaFft {
             par ^= 1;
             store_smem<P0>(b, t, x);
             __syncthreads();
+            if constexpr (STAGED) { // every thread has consumed the stage: refill it for this CTA's next group
+                if (tid == 0 && g + gridDim.x < groups) stage_issue(io, stage, &mbar, g + gridDim.x, rows);
+            }
             load_smem<P1>(b, t, x);
+            if (P::NBUF == 1) __syncthreads();
             if (!P::TW_REGS) P1::load_tw(table, t, tw1);
             P1::compute(x, tw1);
 
@@ -279,6 +395,7 @@ struct CtaFft {
                 store_smem<P1>(b, t, x);
                 __syncthreads();
                 load_smem<P2>(b, t, x);
+                if (P::NBUF == 1) __syncthreads();
                 if (!P::TW_REGS) P2::load_tw(table, t, tw2);
                 P2::compute(x, tw2);
             }
@@ -288,6 +405,7 @@ struct CtaFft {
                 store_smem<P2>(b, t, x);
                 __syncthreads();
                 load_smem<P3>(b, t, x);
+                if (P::NBUF == 1) __syncthreads();
                 P3::load_tw(table, t, tw3);
                 P3::compute(x, tw3);
             }
@@ -299,22 +417,67 @@ struct CtaFft {
                 store_smem<PL>(b, t, x);
                 __syncthreads();
                 if (active) epilogue(io, row, t, b);
+                if (P::NBUF == 1) __syncthreads();
             } else {
                 if (active) store_global<PL>(io, row, t, x);
             }
         }
     }
+
+    // ---- mbarrier / TMA bulk-copy helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) -------------------
+    static __device__ __forceinline__ unsigned smem_u32(const void *p)
+    {
+        return static_cast<unsigned>(__cvta_generic_to_shared(p));
+    }
+    static __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    }
+    static __device__ __forceinline__ void fence_mbar_init()
+    {
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    static __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+    {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE_%=;\n"
+            "bra WAIT_%=;\n"
+            "DONE_%=:\n"
+            "}\n" ::"r"(smem_u32(bar)),
+            "r"(parity)
+            : "memory");
+    }
+    // one thread: arm the barrier with the byte count and start the bulk copy of group g
+    static __device__ __forceinline__ void stage_issue(const IO &io, unsigned char *stage, unsigned long long *bar,
+                                                       long g, long rows)
+    {
+        const unsigned bytes = io.stage_bytes(g, P::TPC, rows);
+        if (bytes == 0) return;
+        const void *src = io.stage_src(g, P::TPC);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(stage)),
+            "l"(src), "r"(bytes), "r"(smem_u32(bar))
+            : "memory");
+    }
 #endif
 };
 
 #ifdef __CUDACC__
-template <int L, bool EXACT, class IO>
+template <int L, bool EXACT, class IO, bool STAGED>
 __global__ void __launch_bounds__(Plan<L>::CTA, (Plan<L>::CTA <= 256 ? 2 : 1))
     fft_cta_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0 tw0,
                    const float2 *__restrict__ table, long rows)
 {
-    extern __shared__ __align__(16) float2 smem[];
-    CtaFft<Plan<L>, EXACT, IO>::run(io, tw0, table, rows, smem);
+    extern __shared__ __align__(128) float2 smem[];
+    CtaFft<Plan<L>, EXACT, IO>::template run<STAGED>(io, tw0, table, rows, smem);
 }
 #endif
 

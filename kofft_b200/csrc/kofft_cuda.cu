@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -25,6 +26,7 @@ thread_local std::string g_last_error;
 
 int fail_cuda(cudaError_t e, const char *where)
 {
+    (void)cudaGetLastError(); // do not let a reported error leak into the next call's launch check
     char buf[256];
     snprintf(buf, sizeof buf, "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
     g_last_error = buf;
@@ -74,6 +76,7 @@ struct kofft_cuda_ctx {
     void *ws[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t ws_bytes[4] = {0, 0, 0, 0};
     size_t istft_ws_limit = size_t(1) << 30;
+    bool use_tma = true; // TMA-staged input prefetch where alignment allows
 };
 
 namespace {
@@ -83,7 +86,7 @@ int ensure_ws(kofft_cuda_ctx *ctx, int which, size_t bytes, void **out)
     if (bytes == 0) bytes = 16;
     if (ctx->ws_bytes[which] < bytes) {
         if (ctx->ws[which]) {
-            CU(cudaStreamSynchronize(ctx->stream));
+            CU(cudaDeviceSynchronize()); // the old block may be in use on a caller's stream
             CU(cudaFree(ctx->ws[which]));
             ctx->ws[which] = nullptr;
             ctx->ws_bytes[which] = 0;
@@ -131,10 +134,12 @@ int get_rfft_table(kofft_cuda_ctx *ctx, size_t m, const Table **out)
 }
 
 // Common dispatch: the complex core has length n (power of two, >= 1), `rows` transforms.
-int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t rows, cudaStream_t stream)
+int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t rows, cudaStream_t stream,
+             bool staged = false)
 {
     if (rows == 0) return KOFFT_OK;
     LaunchArgs a;
+    a.staged = staged && ctx->use_tma;
     a.kind = kind;
     a.exact = ctx->exact;
     a.io = io;
@@ -144,6 +149,7 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
     a.max_ctas = ctx->max_ctas;
     a.stream = stream;
     memset(&a.tw0, 0, sizeof a.tw0);
+    (void)cudaGetLastError();
     cudaError_t e;
     if (n <= 16) {
         e = launch_small_fft(static_cast<int>(n), a);
@@ -179,10 +185,17 @@ int check_fft_len(size_t n)
     return KOFFT_OK;
 }
 
-cudaStream_t pick_stream(kofft_cuda_ctx *ctx, void *stream)
+// `stream` is a cudaStream_t exactly as the caller passed it (NULL = CUDA's legacy default
+// stream, which is what frameworks hand out as "the current stream" most of the time)
+cudaStream_t pick_stream(kofft_cuda_ctx *, void *stream)
 {
-    return stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return static_cast<cudaStream_t>(stream);
 }
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// transforms per CTA of the single-CTA engine (Plan<L>::TPC)
+long tpc_of(size_t n) { return n >= 4096 ? 1 : static_cast<long>(4096 / n); }
 
 } // namespace
 
@@ -250,6 +263,11 @@ int kofft_cuda_set_max_ctas(kofft_cuda_ctx *ctx, int max_ctas)
     ctx->max_ctas = max_ctas < 0 ? 0 : max_ctas;
     return KOFFT_OK;
 }
+int kofft_cuda_set_tma_staging(kofft_cuda_ctx *ctx, int enable)
+{
+    ctx->use_tma = enable != 0;
+    return KOFFT_OK;
+}
 int kofft_cuda_set_rfft_table_fma(kofft_cuda_ctx *ctx, int fma_mul)
 {
     ctx->rfft_fma = fma_mul != 0;
@@ -308,7 +326,7 @@ int kofft_cuda_fft_c2c_f32(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, s
     io.in = d_in;
     io.out = d_out;
     io.scale = 1.0f / static_cast<float>(n); // src/fft.rs:1163
-    return dispatch(ctx, inverse ? KIND_C2C_INV : KIND_C2C_FWD, io, n, batch, s);
+    return dispatch(ctx, inverse ? KIND_C2C_INV : KIND_C2C_FWD, io, n, batch, s, aligned16(d_in) && n >= 2);
 }
 
 int kofft_cuda_fft_strided_f32(kofft_cuda_ctx *ctx, const void *d_in, size_t in_stride, size_t in_dist,
@@ -366,7 +384,7 @@ int kofft_cuda_rfft_f32(kofft_cuda_ctx *ctx, const float *d_in, void *d_out, siz
     io.in = d_in;
     io.out = d_out;
     io.aux = t->dev;
-    return dispatch(ctx, KIND_RFFT, io, m, batch, pick_stream(ctx, stream));
+    return dispatch(ctx, KIND_RFFT, io, m, batch, pick_stream(ctx, stream), aligned16(d_in) && m >= 2);
 }
 
 int kofft_cuda_irfft_f32(kofft_cuda_ctx *ctx, const void *d_in, float *d_out, size_t n, size_t batch, void *stream)
@@ -406,7 +424,11 @@ int kofft_cuda_stft_f32(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, 
     io.p0 = static_cast<long>(len);
     io.p1 = static_cast<long>(nframes);
     io.p2 = static_cast<long>(hop);
-    return dispatch(ctx, KIND_STFT, io, win_len, channels * nframes, pick_stream(ctx, stream));
+    // TMA staging needs 16-byte aligned, whole-float4 segments that never straddle a channel
+    const long tpc = tpc_of(win_len);
+    const bool staged = aligned16(d_signal) && len % 4 == 0 && hop % 4 == 0 && nframes % tpc == 0 &&
+                        ((tpc - 1) * static_cast<long>(hop) + static_cast<long>(win_len)) * 4 <= tpc * static_cast<long>(win_len) * 8;
+    return dispatch(ctx, KIND_STFT, io, win_len, channels * nframes, pick_stream(ctx, stream), staged);
 }
 
 int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nframes, size_t channels,
@@ -437,7 +459,7 @@ int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nfram
             io.aux = d_window;
             io.out = time;
             io.scale = 1.0f / static_cast<float>(win_len);
-            rc = dispatch(ctx, KIND_ISTFT, io, win_len, nc * nframes, s);
+            rc = dispatch(ctx, KIND_ISTFT, io, win_len, nc * nframes, s, aligned16(io.in) && win_len >= 2);
             if (rc) return rc;
         }
         OlaArgs o;

@@ -42,6 +42,7 @@ struct LaunchArgs {
     long rows = 0;
     int num_sms = 148;
     int max_ctas = 0; // 0 = occupancy * num_sms
+    bool staged = false; // input rows may be fetched with TMA bulk copies (16-byte aligned, contiguous)
     cudaStream_t stream = nullptr;
 };
 

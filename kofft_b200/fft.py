@@ -92,6 +92,9 @@ class Context:
     def set_max_ctas(self, n: int) -> None:
         check(_lib.lib().kofft_cuda_set_max_ctas(self.handle, int(n)))
 
+    def set_tma_staging(self, enable: bool) -> None:
+        check(_lib.lib().kofft_cuda_set_tma_staging(self.handle, int(bool(enable))))
+
     def set_rfft_table_fma(self, fma: bool) -> None:
         check(_lib.lib().kofft_cuda_set_rfft_table_fma(self.handle, int(bool(fma))))
 

@@ -34,7 +34,8 @@ class Emu:
         lib.kofft_emu_bank_audit.argtypes = [C.c_int, C.POINTER(C.c_int)]
 
     def run(self, kind, exact, n, rows, table, inp=None, in2=None, out=None, out2=None, aux=None,
-            p=(0, 0, 0, 0), scale=1.0):
+            p=(0, 0, 0, 0), scale=1.0, staged=False):
+        self.lib.kofft_emu_set_staged(int(staged))
         def ptr(a):
             return a.ctypes.data if a is not None else None
 

@@ -26,7 +26,7 @@ struct EmuArgs {
 };
 
 template <class P, bool EXACT, class IO>
-void emu_cta(const IO &io_in, const Tw0 &tw0, const float2 *table, long rows)
+void emu_cta(const IO &io_in, const Tw0 &tw0, const float2 *table, long rows, bool staged)
 {
     using C = CtaFft<P, EXACT, IO>;
     using P0 = typename C::P0;
@@ -52,10 +52,34 @@ void emu_cta(const IO &io_in, const Tw0 &tw0, const float2 *table, long rows)
     for (long g = 0; g < groups; g++) {
         auto row_of = [&](int tid) { return g * P::TPC + slot_of(tid); };
         int b = par; par ^= 1;
+        std::vector<unsigned char> stage(P::STAGE_BYTES, 0xCD);
+        if constexpr (IO::kStageable) {
+            if (staged) {
+                unsigned nb = io.stage_bytes(g, P::TPC, rows);
+                if (nb > (unsigned)P::STAGE_BYTES || (nb % 16) != 0 || ((size_t)io.stage_src(g, P::TPC) % 16) != 0)
+                    throw 1; // what the TMA bulk copy would reject
+                if (nb) memcpy(stage.data(), io.stage_src(g, P::TPC), nb);
+            }
+        }
         for (int tid = 0; tid < NT; tid++) {
             float2 *x = &X[tid * EPT];
-            if (row_of(tid) < rows) C::template load_global<P0>(io, row_of(tid), t_of(tid), x);
-            else for (int e = 0; e < EPT; e++) x[e] = make_float2(0.f, 0.f);
+            bool done = false;
+            if constexpr (IO::kStageable) {
+                if (staged) {
+                    int t = t_of(tid);
+                    for (int u = 0; u < P0::U; u++)
+                        for (int q = 0; q < P0::R; q++) {
+                            int idx = P0::src_index(t, u, q);
+                            x[u * P0::R + q] = io.load_staged(stage.data(), g, row_of(tid), slot_of(tid), idx,
+                                                              IO::kLoadAux ? io.load_aux(idx) : 0.0f);
+                        }
+                    done = true;
+                }
+            }
+            if (!done) {
+                if (row_of(tid) < rows) C::template load_global<P0>(io, row_of(tid), t_of(tid), x);
+                else for (int e = 0; e < EPT; e++) x[e] = make_float2(0.f, 0.f);
+            }
             P0::compute(x, tw0.v);
             C::template store_smem<P0>(buf_of(tid, b), t_of(tid), x);
         }
@@ -101,6 +125,8 @@ void emu_small(const IO &io, long rows)
     for (long r = 0; r < rows; r++) small_transform<N, EXACT, IO>(io, r);
 }
 
+static bool g_staged = false;
+
 template <bool EXACT, class IO>
 int run_sized(int n, const IO &io, const Tw0 &tw0, const float2 *table, long rows)
 {
@@ -110,7 +136,7 @@ int run_sized(int n, const IO &io, const Tw0 &tw0, const float2 *table, long row
     case 4: emu_small<4, EXACT>(io, rows); return 0;
     case 8: emu_small<8, EXACT>(io, rows); return 0;
     case 16: emu_small<16, EXACT>(io, rows); return 0;
-#define CASE_L(L) case (1 << L): emu_cta<Plan<L>, EXACT>(io, tw0, table, rows); return 0;
+#define CASE_L(L) case (1 << L): emu_cta<Plan<L>, EXACT>(io, tw0, table, rows, g_staged && Plan<L>::CAN_STAGE); return 0;
     CASE_L(5) CASE_L(6) CASE_L(7) CASE_L(8) CASE_L(9) CASE_L(10) CASE_L(11) CASE_L(12) CASE_L(13) CASE_L(14)
 #undef CASE_L
     default: return -1;
@@ -136,6 +162,8 @@ int run_kind(int kind, int n, const EmuArgs &q, const Tw0 &tw0, const float2 *ta
 } // namespace
 
 // kind: kofft::Kind numbering (launch.h).  table: the n/2-entry FftPlanner table (host).
+extern "C" __attribute__((visibility("default"))) void kofft_emu_set_staged(int staged) { g_staged = staged != 0; }
+
 extern "C" __attribute__((visibility("default"))) int
 kofft_emu_run(int kind, int exact, long n, long rows, const void *in, const void *in2, void *out, void *out2,
               const void *aux, long p0, long p1, long p2, long p3, float scale, const float *table)
@@ -154,8 +182,12 @@ kofft_emu_run(int kind, int exact, long n, long rows, const void *in, const void
                 tw0.v[(1 << tl) - 1 + c] = make_float2(table[2 * idx], table[2 * idx + 1]);
             }
     }
-    return exact ? run_kind<true>(kind, (int)n, q, tw0, (const float2 *)table, rows)
-                 : run_kind<false>(kind, (int)n, q, tw0, (const float2 *)table, rows);
+    try {
+        return exact ? run_kind<true>(kind, (int)n, q, tw0, (const float2 *)table, rows)
+                     : run_kind<false>(kind, (int)n, q, tw0, (const float2 *)table, rows);
+    } catch (int) {
+        return -7; // staged copy would violate TMA alignment / size rules
+    }
 }
 
 // shared-memory conflict audit: for every (L, exchange, access) return the worst number of

@@ -24,12 +24,14 @@ def test_c2c(emu, oracle, n, inverse):
     ref = oracle.fft_batch(x, inverse=inverse) if n > 1 else x.copy()
     scale = float(np.float32(1.0) / np.float32(n))
     for exact in (True, False):
-        y = np.zeros_like(x)
-        emu.run("c2c_inv" if inverse else "c2c_fwd", exact, n, rows, table_for(oracle, n), inp=x, out=y, scale=scale)
-        if exact:
-            assert np.array_equal(y, ref)
-        else:
-            assert rel_l2(y, ref) <= TOL
+        for staged in (False, True):  # staged = the TMA bulk-copy input path
+            y = np.zeros_like(x)
+            emu.run("c2c_inv" if inverse else "c2c_fwd", exact, n, rows, table_for(oracle, n), inp=x, out=y,
+                    scale=scale, staged=staged)
+            if exact:
+                assert np.array_equal(y, ref)
+            else:
+                assert rel_l2(y, ref) <= TOL
 
 
 @pytest.mark.parametrize("n", [4, 32, 256, 2048])
@@ -76,9 +78,10 @@ def test_rfft_irfft(emu, oracle, m):
     ref = oracle.rfft_batch(x)
     rtw = oracle.rfft_twiddles(m)
     for exact in (True, False):
-        y = np.zeros((rows, m + 1), np.complex64)
-        emu.run("rfft", exact, m, rows, table_for(oracle, m), inp=x, out=y, aux=rtw)
-        assert np.array_equal(y, ref) if exact else rel_l2(y, ref) <= TOL
+        for staged in (False, True):
+            y = np.zeros((rows, m + 1), np.complex64)
+            emu.run("rfft", exact, m, rows, table_for(oracle, m), inp=x, out=y, aux=rtw, staged=staged)
+            assert np.array_equal(y, ref) if exact else rel_l2(y, ref) <= TOL
     back_ref = oracle.irfft_batch(ref, n)
     for exact in (True, False):
         z = np.zeros((rows, n), np.float32)
@@ -87,22 +90,28 @@ def test_rfft_irfft(emu, oracle, m):
         assert np.array_equal(z, back_ref) if exact else rel_l2(z, back_ref) <= TOL
 
 
-@pytest.mark.parametrize("win_len,hop,length", [(4, 2, 8), (16, 4, 50), (64, 16, 1000), (2048, 512, 5000), (256, 300, 700)])
-def test_stft_and_istft_stage1(emu, oracle, win_len, hop, length):
+@pytest.mark.parametrize("win_len,hop,length,staged", [
+    (4, 2, 8, False), (16, 4, 50, False), (64, 16, 1000, False), (2048, 512, 5000, False), (256, 300, 700, False),
+    (2048, 512, 5120, True), (1024, 256, 6144, True), (64, 16, 1024, True), (256, 64, 4096, True), (4096, 1024, 20480, True)])
+def test_stft_and_istft_stage1(emu, oracle, win_len, hop, length, staged):
     rng = np.random.default_rng(win_len + hop)
     ch = 2
     sig = rng.uniform(-1, 1, (ch, length)).astype(np.float32)
     w = oracle.hann(win_len)
     nframes = -(-length // hop) + 1  # one frame more than required: the reference fills it too
+    if staged:  # what the host requires before it picks the TMA-staged kernel (kofft_cuda_stft_f32)
+        tpc = max(1, 4096 // win_len)
+        nframes = -(-nframes // tpc) * tpc + tpc  # multiple of TPC, incl. frames wholly past the end
+        assert length % 4 == 0 and hop % 4 == 0 and sig.ctypes.data % 16 == 0
     ref = oracle.stft_batch(sig, w, hop, nframes)
     frames = np.zeros((ch, nframes, win_len), np.complex64)
     emu.run("stft", True, win_len, ch * nframes, table_for(oracle, win_len), inp=sig, out=frames, aux=w,
-            p=(length, nframes, hop, 0))
+            p=(length, nframes, hop, 0), staged=staged)
     assert np.array_equal(frames, ref)
     # istft stage 1: (ifft(frame).re) * window
     time = np.zeros((ch, nframes, win_len), np.float32)
     emu.run("istft", True, win_len, ch * nframes, table_for(oracle, win_len), inp=ref, out=time, aux=w,
-            scale=float(np.float32(1.0) / np.float32(win_len)))
+            scale=float(np.float32(1.0) / np.float32(win_len)), staged=staged)
     exp = np.stack([oracle.fft_batch(ref[c], inverse=True).real * w for c in range(ch)])
     assert np.array_equal(time, exp.astype(np.float32))
     # ordered overlap-add of those frames == the oracle's istft (pure numpy restatement of ola.cu)

@@ -546,3 +546,57 @@ def test_config4_stft_full_shape_sampled(cuda_fft, oracle):
     n_chk = 20 * hop + win_len
     want = oracle.istft(frames[c, : 20 + 4].cpu().numpy(), w, hop, np.zeros(n_chk, np.float32))
     assert np.array_equal(out[c, : 20 * hop].cpu().numpy(), want[: 20 * hop])
+
+
+# ------------------------------------------------------------------------------------------
+# 4. kernel variants: TMA-staged input prefetch vs plain loads, unaligned fallbacks
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [32, 256, 2048, 4096, 8192])
+def test_tma_staged_and_plain_variants_agree(cuda_fft, oracle, n):
+    import torch
+
+    rng = np.random.default_rng(n)
+    rows = 1000 if n <= 4096 else 77
+    x = uniform_c64(rng, (rows + 1, n))
+    ref = oracle.fft_batch(x[:rows], nthreads=8)
+    d = torch.from_numpy(x).cuda()
+    try:
+        for tma in (True, False):
+            cuda_fft.ctx.set_tma_staging(tma)
+            out = torch.zeros((rows, n), dtype=torch.complex64, device="cuda")
+            cuda_fft.fft_batch(d[:rows], out=out)
+            torch.cuda.synchronize()
+            assert np.array_equal(out.cpu().numpy(), ref), f"tma={tma}"
+        # an input that is only 8-byte aligned must silently take the plain-load kernel
+        cuda_fft.ctx.set_tma_staging(True)
+        flat = d.view(-1)
+        shifted = flat[1: 1 + rows * n].view(rows, n)
+        assert shifted.data_ptr() % 16 == 8
+        out = torch.zeros((rows, n), dtype=torch.complex64, device="cuda")
+        cuda_fft.fft_batch(shifted, out=out)
+        torch.cuda.synchronize()
+        want = oracle.fft_batch(x.reshape(-1)[1: 1 + rows * n].reshape(rows, n), nthreads=8)
+        assert np.array_equal(out.cpu().numpy(), want)
+    finally:
+        cuda_fft.ctx.set_tma_staging(True)
+
+
+def test_stream_ordering_on_a_side_stream(cuda_fft, oracle):
+    """Device entry points are ordered on the caller's stream (here a non-default torch stream)."""
+    import torch
+
+    rng = np.random.default_rng(1)
+    x = uniform_c64(rng, (512, 1024))
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        d = torch.from_numpy(x).cuda(non_blocking=True)
+        out = torch.empty_like(d)
+        for _ in range(3):
+            cuda_fft.fft_batch(d, out=out)
+            cuda_fft.fft_batch(out, inverse=True, out=d)
+        cuda_fft.fft_batch(d, out=out)
+    side.synchronize()
+    want = x
+    for _ in range(3):
+        want = oracle.fft_batch(oracle.fft_batch(want, nthreads=8), inverse=True, nthreads=8)
+    assert np.array_equal(out.cpu().numpy(), oracle.fft_batch(want, nthreads=8))
