@@ -287,6 +287,27 @@ def run_gpu(args) -> None:
                                   "frac_of_measured_peak": ALGO_BYTES_PER_TRANSFORM * ROWS_PER_GPU / ms / 1e6 / peak}
         del x, y
         torch.cuda.empty_cache()
+        # rfft N = 2^16 x batch 16384 (BASELINE configs[2]): two-pass path with the fused twist
+        rn, rb = 65536, 16384
+        xr = (torch.rand((rb, rn), generator=g, device=dev) * 2 - 1).contiguous()
+        yr = torch.empty((rb, rn // 2 + 1), dtype=torch.complex64, device=dev)
+        for _ in range(2):
+            fft.rfft_batch(xr, out=yr)
+        torch.cuda.synchronize()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fft.rfft_batch(xr, out=yr)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        algo = (4 * rn + 8 * (rn // 2 + 1)) * rb
+        extra["rfft_65536x16384"] = {"ms": ms, "gflops_nominal": 2.5 * rn * 16 * rb / ms / 1e6, "hbm_gbs": algo / ms / 1e6,
+                                     "frac_of_measured_peak": algo / ms / 1e6 / peak,
+                                     "note": "two kernels per 48 MB chunk (column pass, row pass + twist), L2-resident intermediate"}
+        del xr, yr
+        torch.cuda.empty_cache()
         free, _ = torch.cuda.mem_get_info()
         ch, length, hop, win = 64, 28_800_000, 512, 2048
         if free < 90e9:
@@ -332,7 +353,7 @@ def run_gpu(args) -> None:
         rows = 8192
         reps = 1
         gf, dt = cpu_port_gflops(rows, reps, threads)
-        while dt < 10.0 and reps < 64:  # aim at >= 10 s of CPU work in the timed sample
+        while dt < 10.0 and reps < 4096:  # aim at >= 10 s of CPU work in the timed sample
             reps *= 2
             gf, dt = cpu_port_gflops(rows, reps, threads)
         cpu = {"value": gf, "unit": UNIT, "cores": threads, "kind": "port",

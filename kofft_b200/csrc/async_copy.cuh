@@ -1,0 +1,85 @@
+// async_copy.cuh -- mbarrier + TMA bulk-copy (cp.async.bulk) helpers shared by the kernels.
+// SASS on sm_100a: SYNCS.* for the mbarrier ops, UBLKCP for the bulk copy.
+// Under KOFFT_EMU (tests/emu, CPU-only CI) the same names are host stand-ins that perform the
+// copy synchronously and enforce the hardware's 16-byte alignment / size rules.
+#pragma once
+#include "hostdev.h"
+
+namespace kofft {
+
+#if defined(__CUDACC__)
+
+KD unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+
+KD void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+KD void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// spin until the phase with the given parity has completed
+KD void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// one arrival + the number of bytes the bulk copies of this phase will deliver
+KD void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy; dst, src and bytes must be multiples of 16
+KD void bulk_copy_g2s(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+#elif defined(KOFFT_EMU)
+
+// *bar counts completed phases; a phase completes when the bytes announced by expect_tx have
+// all been delivered (copies are synchronous here).
+struct EmuMbar {
+    unsigned completed;
+    int pending;
+};
+static_assert(sizeof(EmuMbar) == 8, "fits the kernels' 8-byte mbarrier word");
+inline EmuMbar &emu_mbar(unsigned long long *bar) { return *reinterpret_cast<EmuMbar *>(bar); }
+inline void mbar_init(unsigned long long *bar, unsigned) { emu_mbar(bar) = EmuMbar{0u, 0}; }
+inline void fence_mbar_init() {}
+inline void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    while ((emu_mbar(bar).completed & 1u) == parity) cuda_emu::yield_to_scheduler();
+}
+inline void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    emu_mbar(bar).pending += static_cast<int>(bytes);
+    if (bytes == 0) emu_mbar(bar).completed++;
+}
+inline void bulk_copy_g2s(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    if ((reinterpret_cast<uintptr_t>(dst_smem) & 15) || (reinterpret_cast<uintptr_t>(src) & 15) || (bytes & 15) || !bytes)
+        abort(); // the hardware would fault / hang on these
+    memcpy(dst_smem, src, bytes);
+    EmuMbar &m = emu_mbar(bar);
+    m.pending -= static_cast<int>(bytes);
+    if (m.pending == 0) m.completed++;
+}
+
+#endif
+
+} // namespace kofft

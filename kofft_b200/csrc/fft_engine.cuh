@@ -69,17 +69,28 @@ struct Tw0 {
     float2 v[16];
 };
 
-// index into the N/2-entry table for pass p, layer t, group k, produced bits c_low
+// Where a sub-transform sits inside a larger transform of length 2^Lbig (large-N two-pass
+// path, fft_large.cuh).  The engine's stage s of the sub-transform is stage s + sh1 of the big
+// one, k0 holds the sh1 output bits produced before this sub-transform started, and sh2 is the
+// number of stages that follow it:  index = (k0 + ((k + c_low*2^s) << sh1)) << (L-1-s-t + sh2).
+// A stand-alone transform has {0, 0, 0}.
+struct TwMap {
+    int k0 = 0, sh1 = 0, sh2 = 0;
+};
+
+// index into the table for pass p, layer t, group k, produced bits c_low
 template <class P>
-KHD int tw_index(int p, int t, int k, int c_low)
+KHD int tw_index(int p, int t, int k, int c_low, const TwMap &m = TwMap())
 {
-    return (k + (c_low << P::s(p))) << (P::L - 1 - P::s(p) - t);
+    return (m.k0 + ((k + (c_low << P::s(p))) << m.sh1)) << (P::L - 1 - P::s(p) - t + m.sh2);
 }
 
 // ------------------------------------------------------------------------------------------
 // One thread's share of pass p: U = 16 >> r butterflies of radix 2^r on x[u*R + w].
 // ------------------------------------------------------------------------------------------
-template <class P, int p, bool EXACT>
+// UNIT0: the sub-transform starts at stage 0 of the whole transform, so the group-0 twiddle of
+// pass 0 is table entry 0 == (1, 0) and its other pass-0 twiddles are thread-independent (Tw0).
+template <class P, int p, bool EXACT, bool UNIT0 = true>
 struct Pass {
     static constexpr int r = P::r(p);
     static constexpr int R = 1 << r;
@@ -128,8 +139,8 @@ struct Pass {
     static KHD int src_index(int t, int u, int q) { return src_base(t, u) + src_off(q); }
     static KHD int dst_index(int t, int u, int w) { return dst_base(t, u) + dst_off(w); }
 
-    // gather this thread's twiddles for pass p >= 1 from the device-resident table
-    static KHD void load_tw(const float2 *__restrict__ table, int t, float2 *tw /*[NTW]*/)
+    // gather this thread's twiddles for the pass from the device-resident table
+    static KHD void load_tw(const float2 *__restrict__ table, int t, float2 *tw /*[NTW]*/, const TwMap &m = TwMap())
     {
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -138,7 +149,7 @@ struct Pass {
             for (int tl = 0; tl < r; tl++)
 #pragma unroll
                 for (int c = 0; c < (1 << tl); c++)
-                    tw[u * (R - 1) + (1 << tl) - 1 + c] = table[tw_index<P>(p, tl, k, c)];
+                    tw[u * (R - 1) + (1 << tl) - 1 + c] = table[tw_index<P>(p, tl, k, c, m)];
         }
     }
 
@@ -157,7 +168,7 @@ struct Pass {
                     const int c_low = bitrev(w0 >> (r - tl), tl);
                     float2 &a = x[u * R + w0];
                     float2 &b = x[u * R + (w0 | bit)];
-                    if (p == 0) {
+                    if (p == 0 && UNIT0) {
                         if (c_low == 0)
                             butterfly_unit(a, b); // T[0] == (1, 0) exactly
                         else

@@ -7,6 +7,7 @@
 //   IoRfft     rfft pack + Hermitian twist                     (src/rfft.rs:444-463)
 //   IoIrfft    irfft untwist + unpack                          (src/rfft.rs:485-503)
 #pragma once
+#include "async_copy.cuh"
 #include "fft_engine.cuh"
 
 namespace kofft {
@@ -202,23 +203,25 @@ struct IoRfft {
     {
         return reinterpret_cast<const float2 *>(stage)[slot * m + i];
     }
-    // Y: padded shared copy of the m FFT bins of this row
-    KHD void epilogue(long row, int k, const float2 *Y) const
+    // Hermitian twist of bin k (src/rfft.rs:450-463): a = Y[k], ym = Y[m-k] (for k = 0: a = Y[0])
+    KHD void twist_store(long row, long k, float2 a, float2 ym) const
     {
         float2 *o = out + row * (m + 1);
         if (k == 0) {
-            float2 y0 = Y[0];
-            o[0] = make_float2(add_rn(y0.x, y0.y), 0.0f);
-            o[m] = make_float2(sub_rn(y0.x, y0.y), 0.0f);
+            o[0] = make_float2(add_rn(a.x, a.y), 0.0f);
+            o[m] = make_float2(sub_rn(a.x, a.y), 0.0f);
             return;
         }
-        float2 a = Y[pad(k)];
-        float2 ym = Y[pad((int)m - k)];
         float2 b = make_float2(ym.x, -ym.y);
         float2 sum = add2(a, b), diff = sub2(a, b);
         float2 t = cmul<EXACT>(KOFFT_LDG(rtw + k), diff);
         float2 temp = make_float2(add_rn(sum.x, t.y), sub_rn(sum.y, t.x)); // sum + (t.im, -t.re)
         o[k] = make_float2(mul_rn(temp.x, 0.5f), mul_rn(temp.y, 0.5f));
+    }
+    // Y: padded shared copy of the m FFT bins of this row
+    KHD void epilogue(long row, int k, const float2 *Y) const
+    {
+        twist_store(row, k, Y[pad(k)], k == 0 ? Y[0] : Y[pad((int)m - k)]);
     }
 };
 
@@ -307,7 +310,7 @@ struct CtaFft {
         for (int u = 0; u < EPT; u++) io.epilogue(row, t + u * P::T, buf);
     }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(KOFFT_EMU)
     // rows: number of transforms.  smem: [stage (STAGED only)] [NBUF exchange buffers].
     //
     // STAGED: the next row group's raw input (one contiguous byte range) is fetched by a single
@@ -315,7 +318,7 @@ struct CtaFft {
     // still computing passes 1.. of the current group, so the HBM read latency of group g+1
     // overlaps the butterflies of group g.  Pass 0 then reads the stage instead of HBM.
     template <bool STAGED>
-    static __device__ void run(IO io, const Tw0 &tw0, const float2 *__restrict__ table, long rows, float2 *smem)
+    static KD void run(IO io, const Tw0 &tw0, const float2 *__restrict__ table, long rows, float2 *smem)
     {
         const int tid = threadIdx.x;
         const int slot = tid / P::T; // which of the CTA's TPC transforms
@@ -424,48 +427,13 @@ struct CtaFft {
         }
     }
 
-    // ---- mbarrier / TMA bulk-copy helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) -------------------
-    static __device__ __forceinline__ unsigned smem_u32(const void *p)
-    {
-        return static_cast<unsigned>(__cvta_generic_to_shared(p));
-    }
-    static __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-    {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    }
-    static __device__ __forceinline__ void fence_mbar_init()
-    {
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    static __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-    {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "WAIT_%=:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-            "@p bra DONE_%=;\n"
-            "bra WAIT_%=;\n"
-            "DONE_%=:\n"
-            "}\n" ::"r"(smem_u32(bar)),
-            "r"(parity)
-            : "memory");
-    }
     // one thread: arm the barrier with the byte count and start the bulk copy of group g
-    static __device__ __forceinline__ void stage_issue(const IO &io, unsigned char *stage, unsigned long long *bar,
-                                                       long g, long rows)
+    static KD void stage_issue(const IO &io, unsigned char *stage, unsigned long long *bar, long g, long rows)
     {
         const unsigned bytes = io.stage_bytes(g, P::TPC, rows);
         if (bytes == 0) return;
-        const void *src = io.stage_src(g, P::TPC);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                     : "memory");
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                smem_u32(stage)),
-            "l"(src), "r"(bytes), "r"(smem_u32(bar))
-            : "memory");
+        mbar_expect_tx(bar, bytes);
+        bulk_copy_g2s(stage, io.stage_src(g, P::TPC), bytes, bar);
     }
 #endif
 };

@@ -3,10 +3,15 @@
 // bit-exactness before spending GPU time).  The g++ side is test scaffolding only.
 #pragma once
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__)
 #include <cuda_runtime.h>
 #define KHD __device__ __forceinline__
 #define KD __device__ __forceinline__
+#elif defined(KOFFT_EMU)
+// whole-kernel CPU emulation (tests/emu/cuda_emu.h): CUDA threads are coroutines
+#include "cuda_emu.h"
+#define KHD inline
+#define KD inline
 #else
 #include <cmath>
 #define KHD inline

@@ -72,9 +72,10 @@ struct kofft_cuda_ctx {
     std::map<size_t, Table> fft_tables;                  // key n
     std::map<std::pair<size_t, int>, Table> rfft_tables; // key (m, fma)
     // grow-only device workspaces: [0] host-API staging in, [1] staging out, [2] istft time frames,
-    // [3] small staging (windows)
-    void *ws[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t ws_bytes[4] = {0, 0, 0, 0};
+    // [3] small staging (windows), [4] two-pass (N > 16384) intermediate
+    void *ws[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t ws_bytes[5] = {0, 0, 0, 0, 0};
+    size_t large_scratch_bytes = size_t(48) << 20; // two-pass intermediate per chunk: stays in the 126 MB L2
     size_t istft_ws_limit = size_t(1) << 30;
     bool use_tma = true; // TMA-staged input prefetch where alignment allows
 };
@@ -155,13 +156,42 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
         e = launch_small_fft(static_cast<int>(n), a);
     } else {
         const int L = log2_of(n);
-        if (L > 14)
+        if (L > 16)
             return fail_msg(-static_cast<int>(cudaErrorNotSupported),
-                            "transform length above 16384 is not supported by the single-CTA engine yet");
+                            "transform lengths above 65536 (rfft above 131072) are not supported yet");
         const Table *t = nullptr;
         int rc = get_fft_table(ctx, n, &t);
         if (rc) return rc;
         a.table = t->dev;
+        if (L > 14) {
+            // two-pass path: pass A's pass-0 twiddles are those of stage 0..3 of the big transform
+            if (kind == KIND_STFT || kind == KIND_ISTFT)
+                return fail_msg(-static_cast<int>(cudaErrorNotSupported), "STFT windows above 16384 are not supported");
+            for (int tl = 0; tl < 4; tl++)
+                for (int c = 0; c < (1 << tl); c++) {
+                    size_t idx = static_cast<size_t>(c) << (L - 1 - tl);
+                    a.tw0.v[(1 << tl) - 1 + c] = make_float2(t->host[2 * idx], t->host[2 * idx + 1]);
+                }
+            // chunk the batch so the intermediate stays L2-resident
+            const size_t row_bytes = n * sizeof(float2);
+            size_t chunk = ctx->large_scratch_bytes / row_bytes;
+            if (chunk < 1) chunk = 1;
+            if (chunk > rows) chunk = rows;
+            void *scratch = nullptr;
+            rc = ensure_ws(ctx, 4, chunk * row_bytes, &scratch);
+            if (rc) return rc;
+            for (size_t r0 = 0; r0 < rows; r0 += chunk) {
+                LargeArgs g;
+                g.lsub = L - 8;
+                g.row0 = static_cast<long>(r0);
+                g.chunk_rows = static_cast<long>(rows - r0 < chunk ? rows - r0 : chunk);
+                g.scratch = static_cast<float2 *>(scratch);
+                e = launch_large_fft(L, a, g);
+                if (e != cudaSuccess) return fail_cuda(e, "large-N kernel launch");
+                ctx->launches += 2;
+            }
+            return KOFFT_OK;
+        }
         // pass-0 twiddles (group k = 0): v[(2^t - 1) + c] = T[c << (L-1-t)]
         const int NP = L <= 8 ? 2 : (L <= 12 ? 3 : 4);
         const int R0 = L - 4 * (NP - 1);
@@ -234,7 +264,7 @@ void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->fft_tables) cudaFree(kv.second.dev);
     for (auto &kv : ctx->rfft_tables) cudaFree(kv.second.dev);
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 5; i++)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -50,6 +50,14 @@ struct LaunchArgs {
 cudaError_t launch_cta_fft(int L, const LaunchArgs &a);
 // N = 1 .. 16
 cudaError_t launch_small_fft(int n, const LaunchArgs &a);
+// N = 2^15, 2^16: two kernels (column pass, row pass) over one chunk of the batch
+struct LargeArgs {
+    int lsub = 0;             // L - 8
+    long row0 = 0;            // first transform of the chunk
+    long chunk_rows = 0;      // transforms in the chunk
+    float2 *scratch = nullptr; // chunk_rows * 2^L complex, reused by every chunk (L2-resident)
+};
+cudaError_t launch_large_fft(int L, const LaunchArgs &a, const LargeArgs &g);
 
 // per-L entry points (one per fft_inst.cu build)
 #define KOFFT_DECL_L(L) cudaError_t launch_cta_fft_L##L(const LaunchArgs &a);

@@ -33,6 +33,14 @@ def emu():
 
 
 @pytest.fixture(scope="session")
+def emuk():
+    """The real kernel bodies run by the cooperative block emulator (tests/emu/cuda_emu.h)."""
+    from tests.emu import emu_binding
+
+    return emu_binding.load_kernels()
+
+
+@pytest.fixture(scope="session")
 def cuda_fft():
     """The product: CudaFftImpl over libkofft_cuda.so on cuda:0 (exact mode)."""
     import torch

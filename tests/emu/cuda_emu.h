@@ -1,0 +1,135 @@
+// cuda_emu.h -- a tiny cooperative CUDA-block emulator for CPU-only CI (test scaffolding).
+//
+// Lets a __global__ kernel body written for nvcc be compiled by g++ and executed on the host:
+// every CUDA thread of a block is a ucontext coroutine, __syncthreads() is a counting barrier
+// that yields to the scheduler, threadIdx/blockIdx/blockDim/gridDim are globals the scheduler
+// sets before resuming a thread, and `__shared__` variables become statics (one block runs at
+// a time).  The mbarrier / TMA-bulk-copy helpers used by the kernels have host stand-ins here.
+//
+// Only tests/emu/*.cpp includes this; it is never part of the product build.
+#pragma once
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+inline emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __grid_constant__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+#define __ldg(p) (*(p))
+
+namespace cuda_emu {
+
+struct Thread {
+    ucontext_t ctx;
+    std::vector<char> stack;
+    bool done = false;
+    emu_dim3 tid;
+};
+
+struct Scheduler {
+    ucontext_t main_ctx;
+    std::vector<Thread> threads;
+    int current = -1;
+    unsigned long long barrier_generation = 0;
+    int barrier_arrived = 0;
+    int alive = 0;
+    std::function<void()> body;
+};
+
+inline Scheduler *g_sched = nullptr;
+
+inline void yield_to_scheduler()
+{
+    Scheduler *s = g_sched;
+    Thread &t = s->threads[s->current];
+    swapcontext(&t.ctx, &s->main_ctx);
+}
+
+inline void syncthreads()
+{
+    Scheduler *s = g_sched;
+    const unsigned long long gen = s->barrier_generation;
+    if (++s->barrier_arrived == s->alive) {
+        s->barrier_arrived = 0;
+        s->barrier_generation++;
+        return;
+    }
+    while (s->barrier_generation == gen) yield_to_scheduler();
+}
+
+inline void trampoline()
+{
+    Scheduler *s = g_sched;
+    s->body();
+    Thread &t = s->threads[s->current];
+    t.done = true;
+    s->alive--;
+    // a thread that exits counts as arrived for any barrier the others wait on (CUDA semantics
+    // for exited threads)
+    if (s->alive > 0 && s->barrier_arrived == s->alive) {
+        s->barrier_arrived = 0;
+        s->barrier_generation++;
+    }
+    swapcontext(&t.ctx, &s->main_ctx);
+}
+
+// run `body` once per thread of one block
+inline void run_block(unsigned block_x, unsigned grid_x, unsigned threads_x, const std::function<void()> &body)
+{
+    Scheduler s;
+    s.body = body;
+    s.threads.resize(threads_x);
+    s.alive = static_cast<int>(threads_x);
+    g_sched = &s;
+    blockIdx.x = block_x;
+    gridDim.x = grid_x;
+    blockDim.x = threads_x;
+    const size_t stack_bytes = 256 * 1024;
+    for (unsigned i = 0; i < threads_x; i++) {
+        Thread &t = s.threads[i];
+        t.stack.resize(stack_bytes);
+        t.tid.x = i;
+        getcontext(&t.ctx);
+        t.ctx.uc_stack.ss_sp = t.stack.data();
+        t.ctx.uc_stack.ss_size = stack_bytes;
+        t.ctx.uc_link = &s.main_ctx;
+        makecontext(&t.ctx, reinterpret_cast<void (*)()>(trampoline), 0);
+    }
+    while (s.alive > 0) {
+        for (unsigned i = 0; i < threads_x; i++) {
+            Thread &t = s.threads[i];
+            if (t.done) continue;
+            s.current = static_cast<int>(i);
+            threadIdx = t.tid;
+            swapcontext(&s.main_ctx, &t.ctx);
+        }
+    }
+    g_sched = nullptr;
+}
+
+// launch a whole grid, block after block
+inline void launch(unsigned grid_x, unsigned threads_x, const std::function<void()> &body)
+{
+    for (unsigned b = 0; b < grid_x; b++) run_block(b, grid_x, threads_x, body);
+}
+
+} // namespace cuda_emu
+
+#define __syncthreads() cuda_emu::syncthreads()

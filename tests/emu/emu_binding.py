@@ -54,3 +54,54 @@ def load() -> Emu:
         subprocess.run(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-shared", "-fPIC",
                         "-fvisibility=hidden", "-o", _SO, _SRC], check=True)
     return Emu(C.CDLL(_SO))
+
+
+# ---- whole-kernel emulation (cuda_emu.h coroutines running the real kernel bodies) ---------------
+_SOK = os.path.join(_HERE, "libkofft_emuk.so")
+_SRCK = os.path.join(_HERE, "emu_kernels.cpp")
+
+
+def _stale_k() -> bool:
+    if not os.path.exists(_SOK):
+        return True
+    t = os.path.getmtime(_SOK)
+    deps = [_SRCK, os.path.join(_HERE, "cuda_emu.h")] + [
+        os.path.join(_CSRC, f) for f in ("hostdev.h", "async_copy.cuh", "fft_engine.cuh", "fft_kernels.cuh",
+                                         "fft_large.cuh", "small_kernels.cuh")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+class EmuKernels:
+    def __init__(self, lib):
+        self.lib = lib
+        for f in (lib.kofft_emuk_cta, lib.kofft_emuk_large):
+            f.restype = C.c_int
+            f.argtypes = ([C.c_int, C.c_int, C.c_int, C.c_long] + [C.c_void_p] * 5 + [C.c_long] * 4
+                          + [C.c_float, C.c_void_p, C.c_int, C.c_int])
+
+    @staticmethod
+    def _ptr(a):
+        return a.ctypes.data if a is not None else None
+
+    def cta(self, kind, exact, L, rows, table, inp=None, in2=None, out=None, out2=None, aux=None,
+            p=(0, 0, 0, 0), scale=1.0, staged=False, grid=2):
+        """CtaFft::run<STAGED> on `grid` persistent CTAs."""
+        rc = self.lib.kofft_emuk_cta(KIND[kind], int(exact), L, rows, self._ptr(inp), self._ptr(in2), self._ptr(out),
+                                     self._ptr(out2), self._ptr(aux), *[int(v) for v in p], C.c_float(scale),
+                                     self._ptr(table), int(staged), grid)
+        assert rc == 0, rc
+
+    def large(self, kind, exact, L, rows, table, inp=None, in2=None, out=None, out2=None, aux=None,
+              p=(0, 0, 0, 0), scale=1.0, grid_col=5, grid_row=16):
+        """ColPass::run + RowPass::run (two chunks) for a complex core of length 2^L."""
+        rc = self.lib.kofft_emuk_large(KIND[kind], int(exact), L, rows, self._ptr(inp), self._ptr(in2),
+                                       self._ptr(out), self._ptr(out2), self._ptr(aux), *[int(v) for v in p],
+                                       C.c_float(scale), self._ptr(table), grid_col, grid_row)
+        assert rc == 0, rc
+
+
+def load_kernels() -> EmuKernels:
+    if _stale_k():
+        subprocess.run(["g++", "-O1", "-DKOFFT_EMU", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-shared",
+                        "-fPIC", "-fvisibility=hidden", "-I", _HERE, "-o", _SOK, _SRCK], check=True)
+    return EmuKernels(C.CDLL(_SOK))

@@ -1,0 +1,154 @@
+// emu_kernels.cpp -- runs the *actual* kernel bodies (CtaFft::run, ColPass::run, RowPass::run)
+// on the CPU with the cooperative block emulator in cuda_emu.h (CUDA threads = coroutines,
+// __syncthreads = counting barrier, mbarrier / TMA bulk copy = host stand-ins).  Test
+// scaffolding for the GPU-less CI: never shipped, never imported by kofft_b200/.
+//
+// Build: g++ -O1 -DKOFFT_EMU -ffp-contract=off -std=c++17 -shared -fPIC -I tests/emu
+#include <cstring>
+#include <vector>
+
+#include "../../kofft_b200/csrc/fft_large.cuh"
+
+using namespace kofft;
+
+namespace {
+
+struct Args {
+    const void *in, *in2;
+    void *out, *out2;
+    const void *aux;
+    long n, p0, p1, p2, p3;
+    float scale;
+};
+
+Tw0 make_tw0(int L, int R0, const float *table)
+{
+    Tw0 tw0;
+    memset(&tw0, 0, sizeof tw0);
+    for (int tl = 0; tl < R0; tl++)
+        for (int c = 0; c < (1 << tl); c++) {
+            long idx = (long)c << (L - 1 - tl);
+            tw0.v[(1 << tl) - 1 + c] = make_float2(table[2 * idx], table[2 * idx + 1]);
+        }
+    return tw0;
+}
+
+// ---- single-CTA engine: the real CtaFft::run<STAGED> -------------------------------------------
+template <int L, bool EXACT, class IO>
+int run_cta(const IO &io, const float *table, long rows, bool staged, int grid)
+{
+    using P = Plan<L>;
+    Tw0 tw0 = make_tw0(L, P::R0, table);
+    const long groups = (rows + P::TPC - 1) / P::TPC;
+    if (grid > groups) grid = (int)groups;
+    if (grid < 1) grid = 1;
+    std::vector<float2> smem((P::SMEM_BYTES_STAGED + 256) / 8);
+    float2 *sm = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
+    const float2 *tab = reinterpret_cast<const float2 *>(table);
+    if constexpr (IO::kStageable && P::CAN_STAGE) {
+        if (staged) {
+            cuda_emu::launch(grid, P::CTA, [&] { CtaFft<P, EXACT, IO>::template run<true>(io, tw0, tab, rows, sm); });
+            return 0;
+        }
+    }
+    cuda_emu::launch(grid, P::CTA, [&] { CtaFft<P, EXACT, IO>::template run<false>(io, tw0, tab, rows, sm); });
+    return 0;
+}
+
+template <bool EXACT, class IO>
+int run_cta_sized(int L, const IO &io, const float *table, long rows, bool staged, int grid)
+{
+    switch (L) {
+#define CASE_L(L) case L: return run_cta<L, EXACT>(io, table, rows, staged, grid);
+    CASE_L(5) CASE_L(6) CASE_L(7) CASE_L(8) CASE_L(9) CASE_L(10) CASE_L(11) CASE_L(12) CASE_L(13) CASE_L(14)
+#undef CASE_L
+    default: return -1;
+    }
+}
+
+// ---- two-pass large-N path: the real ColPass::run + RowPass::run --------------------------------
+template <int LB, bool EXACT, class IO, int EPI>
+int run_large(const IO &io, const float *table, long rows, int grid_col, int grid_row)
+{
+    const int L = LB + LARGE_S1;
+    const long n = 1L << L;
+    Tw0 tw0 = make_tw0(L, 4, table);
+    const float2 *tab = reinterpret_cast<const float2 *>(table);
+    std::vector<float2> scratch((size_t)rows * n);
+    using C = ColPass<EXACT, IO>;
+    using R = RowPass<LB, EXACT, IO, EPI>;
+    std::vector<float2> smem((std::max(C::SMEM_BYTES, R::SMEM_BYTES) + 256) / 8);
+    float2 *sm = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
+    // process the batch in two chunks to exercise row0
+    const long half = rows > 1 ? rows / 2 : rows;
+    for (long r0 = 0; r0 < rows; r0 += half) {
+        const long nr = std::min(half, rows - r0);
+        const long tiles_c = nr << (LB - 4);
+        int gc = (int)std::min<long>(grid_col, tiles_c);
+        cuda_emu::launch(gc, 256, [&] { C::run(io, tw0, tab, LB, tiles_c, r0, scratch.data(), sm); });
+        const long tiles_r = nr * R::NKB;
+        long gr = std::min<long>(grid_row, tiles_r) / R::NKB * R::NKB;
+        if (gr < R::NKB) gr = R::NKB;
+        cuda_emu::launch((int)gr, 256, [&] { R::run(io, tab, tiles_r, r0, scratch.data(), sm); });
+    }
+    return 0;
+}
+
+template <int LB, bool EXACT>
+int run_large_kind(int kind, const Args &q, const float *table, long rows, int gc, int gr)
+{
+    switch (kind) {
+    case 0: { IoC2C<false> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale}; return run_large<LB, EXACT, IoC2C<false>, ROW_STORE>(io, table, rows, gc, gr); }
+    case 1: { IoC2C<true> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale}; return run_large<LB, EXACT, IoC2C<true>, ROW_STORE>(io, table, rows, gc, gr); }
+    case 2: { IoGeneric<false> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_large<LB, EXACT, IoGeneric<false>, ROW_STORE>(io, table, rows, gc, gr); }
+    case 3: { IoGeneric<true> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_large<LB, EXACT, IoGeneric<true>, ROW_STORE>(io, table, rows, gc, gr); }
+    case 6: { IoRfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n}; return run_large<LB, EXACT, IoRfft<EXACT>, ROW_TWIST>(io, table, rows, gc, gr); }
+    case 7: { IoIrfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n, q.scale}; return run_large<LB, EXACT, IoIrfft<EXACT>, ROW_STORE>(io, table, rows, gc, gr); }
+    default: return -2;
+    }
+}
+
+template <bool EXACT>
+int run_cta_kind(int kind, int L, const Args &q, const float *table, long rows, bool staged, int grid)
+{
+    switch (kind) {
+    case 0: { IoC2C<false> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
+    case 1: { IoC2C<true> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
+    case 2: { IoGeneric<false> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
+    case 3: { IoGeneric<true> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
+    case 4: { IoStft io{(const float *)q.in, (const float *)q.aux, (float2 *)q.out, q.p0, q.p1, q.p2, q.n}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
+    case 5: { IoIstft io{(const float2 *)q.in, (const float *)q.aux, (float *)q.out, q.n, q.scale}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
+    case 6: { IoRfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
+    case 7: { IoIrfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n, q.scale}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
+    default: return -2;
+    }
+}
+
+} // namespace
+
+#define API extern "C" __attribute__((visibility("default")))
+
+// the real single-CTA kernel body; grid = number of (persistent) CTAs to emulate
+API int kofft_emuk_cta(int kind, int exact, int L, long rows, const void *in, const void *in2, void *out, void *out2,
+                       const void *aux, long p0, long p1, long p2, long p3, float scale, const float *table,
+                       int staged, int grid)
+{
+    Args q{in, in2, out, out2, aux, 1L << L, p0, p1, p2, p3, scale};
+    return exact ? run_cta_kind<true>(kind, L, q, table, rows, staged != 0, grid)
+                 : run_cta_kind<false>(kind, L, q, table, rows, staged != 0, grid);
+}
+
+// the real two-pass kernel bodies; L = 15 or 16 is the length of the complex core
+API int kofft_emuk_large(int kind, int exact, int L, long rows, const void *in, const void *in2, void *out,
+                         void *out2, const void *aux, long p0, long p1, long p2, long p3, float scale,
+                         const float *table, int grid_col, int grid_row)
+{
+    Args q{in, in2, out, out2, aux, 1L << L, p0, p1, p2, p3, scale};
+    if (L == 15)
+        return exact ? run_large_kind<7, true>(kind, q, table, rows, grid_col, grid_row)
+                     : run_large_kind<7, false>(kind, q, table, rows, grid_col, grid_row);
+    if (L == 16)
+        return exact ? run_large_kind<8, true>(kind, q, table, rows, grid_col, grid_row)
+                     : run_large_kind<8, false>(kind, q, table, rows, grid_col, grid_row);
+    return -1;
+}

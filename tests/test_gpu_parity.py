@@ -600,3 +600,72 @@ def test_stream_ordering_on_a_side_stream(cuda_fft, oracle):
     for _ in range(3):
         want = oracle.fft_batch(oracle.fft_batch(want, nthreads=8), inverse=True, nthreads=8)
     assert np.array_equal(out.cpu().numpy(), oracle.fft_batch(want, nthreads=8))
+
+
+# ------------------------------------------------------------------------------------------
+# 5. large-N two-pass path (N = 2^15, 2^16; rfft N = 2^16, 2^17)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [32768, 65536])
+def test_large_c2c(cuda_fft, cuda_fft_fast, oracle, n):
+    rng = np.random.default_rng(n)
+    rows = 7
+    x = uniform_c64(rng, (rows, n))
+    for inverse in (False, True):
+        ref = oracle.fft_batch(x, inverse=inverse, nthreads=8)
+        y = x.copy()
+        cuda_fft.fft_batch(y, inverse=inverse)
+        assert np.array_equal(y, ref), rel_l2(y, ref)
+        z = x.copy()
+        cuda_fft_fast.fft_batch(z, inverse=inverse)
+        assert rel_l2(z, ref) <= TOL
+    one = x[0].copy()
+    cuda_fft.fft(one)  # trait-level single transform
+    assert np.array_equal(one, oracle.fft(x[0]))
+    re, im = np.ascontiguousarray(x[1].real), np.ascontiguousarray(x[1].imag)
+    cuda_fft.fft_split(re, im)
+    ref1 = oracle.fft(x[1])
+    assert np.array_equal(re, ref1.real) and np.array_equal(im, ref1.imag)
+
+
+@pytest.mark.parametrize("n", [65536, 131072])
+def test_large_rfft_irfft(cuda_fft, cuda_fft_fast, oracle, n):
+    rng = np.random.default_rng(n)
+    rows = 5
+    x = rng.uniform(-1, 1, (rows, n)).astype(np.float32)
+    ref = oracle.rfft_batch(x, nthreads=8)
+    y = cuda_fft.rfft_batch(x)
+    assert np.array_equal(y, ref), rel_l2(y, ref)
+    assert rel_l2(cuda_fft_fast.rfft_batch(x), ref) <= TOL
+    back = oracle.irfft_batch(ref, n, nthreads=8)
+    assert np.array_equal(cuda_fft.irfft_batch(ref, n), back)
+    # the reference's bench input x_i = i (kofft-bench/benches/bench_fft.rs:300)
+    ramp = np.arange(n, dtype=np.float32).reshape(1, n)
+    assert np.array_equal(cuda_fft.rfft_batch(ramp), oracle.rfft_batch(ramp))
+
+
+def test_config3_full_size_rfft_65536x16384(cuda_fft, oracle):
+    """BASELINE configs[2]: rfft N = 2^16 x batch 16384 (4 GiB in, 4 GiB out)."""
+    import torch
+
+    n, batch = 65536, 16384
+    m = n // 2
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = (torch.rand((batch, n), generator=g, device="cuda") * 2 - 1).contiguous()
+    y = cuda_fft.rfft_batch(x)
+    torch.cuda.synchronize()
+    rows = np.concatenate([np.random.default_rng(1).choice(batch, 24, replace=False), [0, batch - 1]])
+    idx = torch.from_numpy(rows).cuda()
+    xs, ys = x[idx].cpu().numpy(), y[idx].cpu().numpy()
+    ref = oracle.rfft_batch(xs, nthreads=8)
+    assert np.array_equal(ys, ref)
+    # no worse than the reference's own error against an f64 transform
+    f64 = np.fft.rfft(xs[:8].astype(np.float64), axis=1)
+    assert rel_l2(ys[:8], f64) <= rel_l2(ref[:8], f64) * (1 + 1e-6)
+    # DC / Nyquist bins are purely real for every row (src/rfft.rs:450-452)
+    assert float(y[:, 0].imag.abs().max()) == 0.0 and float(y[:, m].imag.abs().max()) == 0.0
+    # round trip through irfft, whole batch (kofft's own rfft->irfft error at this size is ~5e-3)
+    z = cuda_fft.irfft_batch(y, n)
+    torch.cuda.synchronize()
+    err = torch.linalg.vector_norm(z - x, dim=1) / torch.linalg.vector_norm(x, dim=1)
+    assert float(err.max()) < 1e-2
+    assert np.array_equal(z[idx].cpu().numpy(), oracle.irfft_batch(ref, n, nthreads=8))

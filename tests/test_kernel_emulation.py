@@ -1,0 +1,101 @@
+"""The real kernel bodies (CtaFft::run incl. the TMA/mbarrier staging protocol, and the large-N
+ColPass::run / RowPass::run) executed on the CPU by the cooperative block emulator
+(tests/emu/cuda_emu.h: CUDA threads are coroutines, __syncthreads a counting barrier) and
+compared bit-for-bit with the oracle.  Persistent grids smaller than the work exercise the
+row-group loops, buffer alternation and barrier phases exactly as on the GPU."""
+import numpy as np
+import pytest
+
+from tests.conftest import rel_l2, uniform_c64
+
+TOL = 1e-5
+
+
+@pytest.mark.parametrize("L", [5, 7, 8, 9, 11, 12, 13, 14])
+@pytest.mark.parametrize("staged", [False, True])
+def test_cta_kernel_body(emuk, oracle, L, staged):
+    n = 1 << L
+    rng = np.random.default_rng(L)
+    rows = 11 if L < 13 else 3
+    x = uniform_c64(rng, (rows, n))
+    tab = oracle.twiddles(n)
+    for inverse in (False, True):
+        ref = oracle.fft_batch(x, inverse=inverse)
+        for grid in (1, 3):
+            y = np.zeros_like(x)
+            emuk.cta("c2c_inv" if inverse else "c2c_fwd", True, L, rows, tab, inp=x, out=y,
+                     scale=float(np.float32(1) / np.float32(n)), staged=staged, grid=grid)
+            assert np.array_equal(y, ref), (L, staged, inverse, grid)
+    y = np.zeros_like(x)
+    emuk.cta("c2c_fwd", False, L, rows, tab, inp=x, out=y, staged=staged, grid=2)
+    assert rel_l2(y, oracle.fft_batch(x)) <= TOL
+
+
+@pytest.mark.parametrize("staged", [False, True])
+def test_cta_kernel_body_stft_rfft(emuk, oracle, staged):
+    rng = np.random.default_rng(3)
+    win_len, hop, length, ch = 2048, 512, 8192, 2
+    sig = rng.uniform(-1, 1, (ch, length)).astype(np.float32)
+    w = oracle.hann(win_len)
+    nframes = length // hop + 2  # even (TPC = 2), includes frames that run past the end
+    ref = oracle.stft_batch(sig, w, hop, nframes)
+    frames = np.zeros_like(ref)
+    emuk.cta("stft", True, 11, ch * nframes, oracle.twiddles(win_len), inp=sig, out=frames, aux=w,
+             p=(length, nframes, hop, 0), staged=staged, grid=3)
+    assert np.array_equal(frames, ref)
+    time = np.zeros((ch, nframes, win_len), np.float32)
+    emuk.cta("istft", True, 11, ch * nframes, oracle.twiddles(win_len), inp=ref, out=time, aux=w,
+             scale=float(np.float32(1) / np.float32(win_len)), staged=staged, grid=3)
+    want = np.stack([oracle.fft_batch(ref[c], inverse=True).real * w for c in range(ch)]).astype(np.float32)
+    assert np.array_equal(time, want)
+    m = 4096
+    x = rng.uniform(-1, 1, (5, 2 * m)).astype(np.float32)
+    y = np.zeros((5, m + 1), np.complex64)
+    emuk.cta("rfft", True, 12, 5, oracle.twiddles(m), inp=x, out=y, aux=oracle.rfft_twiddles(m), staged=staged, grid=2)
+    assert np.array_equal(y, oracle.rfft_batch(x))
+
+
+@pytest.mark.parametrize("L", [15, 16])
+def test_large_two_pass_c2c(emuk, oracle, L):
+    n = 1 << L
+    rng = np.random.default_rng(L)
+    rows = 3
+    x = uniform_c64(rng, (rows, n))
+    tab = oracle.twiddles(n)
+    ref = oracle.fft_batch(x)
+    y = np.zeros_like(x)
+    emuk.large("c2c_fwd", True, L, rows, tab, inp=x, out=y, grid_col=5, grid_row=16)
+    assert np.array_equal(y, ref)
+    y[...] = 0
+    emuk.large("c2c_inv", True, L, rows, tab, inp=x, out=y, scale=float(np.float32(1) / np.float32(n)),
+               grid_col=7, grid_row=32)
+    assert np.array_equal(y, oracle.fft_batch(x, inverse=True))
+    y[...] = 0
+    emuk.large("c2c_fwd", False, L, rows, tab, inp=x, out=y)
+    assert rel_l2(y, ref) <= TOL
+    # SoA through the generic policy
+    re, im = np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag)
+    ore, oim = np.zeros_like(re), np.zeros_like(im)
+    emuk.large("gen_fwd", True, L, rows, tab, inp=re, in2=im, out=ore, out2=oim, p=(1, n, 1, n))
+    assert np.array_equal(ore, ref.real) and np.array_equal(oim, ref.imag)
+
+
+@pytest.mark.parametrize("L", [15, 16])
+def test_large_two_pass_rfft_irfft(emuk, oracle, L):
+    """BASELINE configs[2] is rfft N = 2^16, i.e. a half-length core m = 2^15 with the Hermitian
+    twist fused behind the row pass (mirrored k-blocks)."""
+    m = 1 << L
+    rng = np.random.default_rng(100 + L)
+    rows = 2
+    x = rng.uniform(-1, 1, (rows, 2 * m)).astype(np.float32)
+    tab, rtw = oracle.twiddles(m), oracle.rfft_twiddles(m)
+    ref = oracle.rfft_batch(x)
+    y = np.zeros((rows, m + 1), np.complex64)
+    emuk.large("rfft", True, L, rows, tab, inp=x, out=y, aux=rtw)
+    assert np.array_equal(y, ref)
+    z = np.zeros((rows, 2 * m), np.float32)
+    emuk.large("irfft", True, L, rows, tab, inp=ref, out=z, aux=rtw, scale=float(np.float32(1) / np.float32(m)))
+    assert np.array_equal(z, oracle.irfft_batch(ref, 2 * m))
+    y[...] = 0
+    emuk.large("rfft", False, L, rows, tab, inp=x, out=y, aux=rtw)
+    assert rel_l2(y, ref) <= TOL
