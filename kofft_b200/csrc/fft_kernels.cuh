@@ -44,6 +44,7 @@ KHD float2 post_conj_scale(float2 v, float scale)
 
 template <bool INV>
 struct IoC2C {
+    static constexpr bool kStoreAux = false;
     static constexpr bool kEpilogueExchange = false;
     const float2 *__restrict__ in;
     float2 *__restrict__ out;
@@ -62,7 +63,10 @@ struct IoC2C {
         return (unsigned)((nr < tpc ? nr : tpc) * n * 8);
     }
     KHD const void *stage_src(long g, int tpc) const { return in + g * tpc * n; }
-    KHD float2 load_staged(const unsigned char *stage, long, long, int slot, int i, float) const
+    KHD void group_init(long, int) {}
+    KHD void group_next(long, int) {}
+    KHD int row_begin(int) const { return 0; }
+    KHD float2 load_staged(const unsigned char *stage, int, int slot, int i, float) const
     {
         return pre_conj<INV>(reinterpret_cast<const float2 *>(stage)[slot * n + i]);
     }
@@ -72,6 +76,7 @@ struct IoC2C {
 // interleaved data passes im = re + 1 and elem_stride = 2*stride.
 template <bool INV>
 struct IoGeneric {
+    static constexpr bool kStoreAux = false;
     static constexpr bool kEpilogueExchange = false;
     const float *__restrict__ in_re;
     const float *__restrict__ in_im;
@@ -98,6 +103,7 @@ struct IoGeneric {
 
 // stft: frame f of channel c, x[i] = signal[c][f*hop + i] * window[i], 0 past the end, imag 0
 struct IoStft {
+    static constexpr bool kStoreAux = false;
     static constexpr bool kEpilogueExchange = false;
     const float *__restrict__ signal;
     const float *__restrict__ window;
@@ -136,13 +142,25 @@ struct IoStft {
         long c = r0 / nframes, f0 = r0 - c * nframes;
         return signal + c * len + f0 * hop;
     }
-    KHD float2 load_staged(const unsigned char *stage, long g, long row, int slot, int i, float w) const
+    // frame index (within its channel) of the current group's first row, advanced without
+    // divisions as the persistent CTA strides over the groups
+    long cur_f0 = 0;
+    KHD void group_init(long g0, int tpc) { cur_f0 = (g0 * tpc) % nframes; }
+    KHD void group_next(long step, int tpc)
     {
-        long c = row / nframes, f = row - c * nframes;
-        long pos = f * hop + i;
+        cur_f0 += step * tpc;
+        while (cur_f0 >= nframes) cur_f0 -= nframes;
+    }
+    // samples of this slot's frame that lie inside the signal, clamped to [0, n]
+    KHD int row_begin(int slot) const
+    {
+        long rem = len - (cur_f0 + slot) * hop;
+        return rem <= 0 ? 0 : (rem >= n ? (int)n : (int)rem);
+    }
+    KHD float2 load_staged(const unsigned char *stage, int rem, int slot, int i, float w) const
+    {
         float x = 0.0f;
-        if (pos < len) x = mul_rn(reinterpret_cast<const float *>(stage)[(long)slot * hop + i], w);
-        (void)g;
+        if (i < rem) x = mul_rn(reinterpret_cast<const float *>(stage)[(long)slot * hop + i], w);
         return make_float2(x, 0.0f);
     }
 };
@@ -163,6 +181,13 @@ struct IoIstft {
         float re = mul_rn(v.x, scale);
         time[row * n + i] = mul_rn(re, KOFFT_LDG(window + i));
     }
+    static constexpr bool kStoreAux = true;
+    KHD float store_aux_value(int i) const { return KOFFT_LDG(window + i); }
+    KHD void store_aux(long row, int i, float2 v, float w) const
+    {
+        float re = mul_rn(v.x, scale);
+        time[row * n + i] = mul_rn(re, w);
+    }
     static constexpr bool kStageable = true;
     static constexpr bool kLoadAux = false;
     KHD float load_aux(int) const { return 0.0f; }
@@ -172,7 +197,10 @@ struct IoIstft {
         return (unsigned)((nr < tpc ? nr : tpc) * n * 8);
     }
     KHD const void *stage_src(long g, int tpc) const { return frames + g * tpc * n; }
-    KHD float2 load_staged(const unsigned char *stage, long, long, int slot, int i, float) const
+    KHD void group_init(long, int) {}
+    KHD void group_next(long, int) {}
+    KHD int row_begin(int) const { return 0; }
+    KHD float2 load_staged(const unsigned char *stage, int, int slot, int i, float) const
     {
         return pre_conj<true>(reinterpret_cast<const float2 *>(stage)[slot * n + i]);
     }
@@ -182,6 +210,7 @@ struct IoIstft {
 // length-m FFT the bins are exchanged once more through shared memory and twisted.
 template <bool EXACT>
 struct IoRfft {
+    static constexpr bool kStoreAux = false;
     static constexpr bool kEpilogueExchange = true;
     const float2 *__restrict__ in;     // [rows][m]
     float2 *__restrict__ out;          // [rows][m + 1]
@@ -199,7 +228,10 @@ struct IoRfft {
         return (unsigned)((nr < tpc ? nr : tpc) * m * 8);
     }
     KHD const void *stage_src(long g, int tpc) const { return in + g * tpc * m; }
-    KHD float2 load_staged(const unsigned char *stage, long, long, int slot, int i, float) const
+    KHD void group_init(long, int) {}
+    KHD void group_next(long, int) {}
+    KHD int row_begin(int) const { return 0; }
+    KHD float2 load_staged(const unsigned char *stage, int, int slot, int i, float) const
     {
         return reinterpret_cast<const float2 *>(stage)[slot * m + i];
     }
@@ -229,6 +261,7 @@ struct IoRfft {
 // loading element i (it needs X[i] and X[m-i]), then ifft, then unpack to 2m reals.
 template <bool EXACT>
 struct IoIrfft {
+    static constexpr bool kStoreAux = false;
     static constexpr bool kEpilogueExchange = false;
     const float2 *__restrict__ in;   // [rows][m + 1]
     float2 *__restrict__ out;        // [rows][m] == 2m reals
@@ -286,6 +319,16 @@ struct CtaFft {
         for (int u = 0; u < PS::U; u++)
 #pragma unroll
             for (int w = 0; w < PS::R; w++) io.store(row, PS::dst_index(t, u, w), x[u * PS::R + w]);
+    }
+    // same, with per-element constants (the ISTFT window) preloaded into registers
+    template <class PS>
+    static KHD void store_global_aux(const IO &io, long row, int t, const float2 *x, const float *aux)
+    {
+#pragma unroll
+        for (int u = 0; u < PS::U; u++)
+#pragma unroll
+            for (int w = 0; w < PS::R; w++)
+                io.store_aux(row, PS::dst_index(t, u, w), x[u * PS::R + w], aux[u * PS::R + w]);
     }
     template <class PS>
     static KHD void store_smem(float2 *buf, int t, const float2 *x)
@@ -355,6 +398,16 @@ struct CtaFft {
                 for (int q = 0; q < P0::R; q++) aux[u * P0::R + q] = io.load_aux(P0::src_index(t, u, q));
         }
 
+        using PLast = Pass<P, P::NP - 1, EXACT>;
+        float auxo[EPT]; // per-element constants of the final stores (the ISTFT window)
+        if constexpr (IO::kStoreAux) {
+#pragma unroll
+            for (int u = 0; u < PLast::U; u++)
+#pragma unroll
+                for (int w = 0; w < PLast::R; w++) auxo[u * PLast::R + w] = io.store_aux_value(PLast::dst_index(t, u, w));
+        }
+
+        if constexpr (STAGED) io.group_init(blockIdx.x, P::TPC);
         for (long g = blockIdx.x; g < groups; g += gridDim.x) {
             const long row = g * P::TPC + slot;
             const bool active = row < rows;
@@ -364,11 +417,12 @@ struct CtaFft {
                     mbar_wait(&mbar, phase);
                     phase ^= 1;
                 }
+                const int rctx = io.row_begin(slot);
 #pragma unroll
                 for (int u = 0; u < P0::U; u++)
 #pragma unroll
                     for (int q = 0; q < P0::R; q++)
-                        x[u * P0::R + q] = io.load_staged(stage, g, row, slot, P0::src_index(t, u, q),
+                        x[u * P0::R + q] = io.load_staged(stage, rctx, slot, P0::src_index(t, u, q),
                                                           IO::kLoadAux ? aux[u * P0::R + q] : 0.0f);
             } else {
                 if (active) {
@@ -421,9 +475,12 @@ struct CtaFft {
                 __syncthreads();
                 if (active) epilogue(io, row, t, b);
                 if (P::NBUF == 1) __syncthreads();
+            } else if constexpr (IO::kStoreAux) {
+                if (active) store_global_aux<PL>(io, row, t, x, auxo);
             } else {
                 if (active) store_global<PL>(io, row, t, x);
             }
+            if constexpr (STAGED) io.group_next(gridDim.x, P::TPC);
         }
     }
 

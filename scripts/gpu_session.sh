@@ -25,3 +25,8 @@ echo "== ncu full" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_cta_kernel -s 3 -c 2 -o $OUT/prof_c2c \
     python scripts/one_kernel.py c2c > $OUT/ncu_full.log 2>&1; echo "ncu full exit $?" | tee -a $OUT/summary.txt
 ls -la $OUT | tee -a $OUT/summary.txt
+echo "== ncu stft / rfft" | tee -a $OUT/summary.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_cta_kernel -s 3 -c 1 -o $OUT/prof_stft \
+    python scripts/one_kernel.py stft > $OUT/ncu_stft.log 2>&1; echo "ncu stft exit $?" | tee -a $OUT/summary.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:pass_kernel -s 4 -c 2 -o $OUT/prof_rfft \
+    python scripts/one_kernel.py rfft > $OUT/ncu_rfft.log 2>&1; echo "ncu rfft exit $?" | tee -a $OUT/summary.txt

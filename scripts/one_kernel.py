@@ -26,7 +26,7 @@ elif which == "stft":
     for _ in range(6):
         S.stft_batch(fft, sig, w, hop, nframes, out=frames)
 elif which == "rfft":
-    x = (torch.rand((4096, 32768), generator=g, device="cuda") * 2 - 1).contiguous()
+    x = (torch.rand((4096, 65536), generator=g, device="cuda") * 2 - 1).contiguous()
     for _ in range(6):
         fft.rfft_batch(x)
 torch.cuda.synchronize()

@@ -55,6 +55,7 @@ void emu_cta(const IO &io_in, const Tw0 &tw0, const float2 *table, long rows, bo
         std::vector<unsigned char> stage(P::STAGE_BYTES, 0xCD);
         if constexpr (IO::kStageable) {
             if (staged) {
+                io.group_init(g, P::TPC);
                 unsigned nb = io.stage_bytes(g, P::TPC, rows);
                 if (nb > (unsigned)P::STAGE_BYTES || (nb % 16) != 0 || ((size_t)io.stage_src(g, P::TPC) % 16) != 0)
                     throw 1; // what the TMA bulk copy would reject
@@ -67,10 +68,11 @@ void emu_cta(const IO &io_in, const Tw0 &tw0, const float2 *table, long rows, bo
             if constexpr (IO::kStageable) {
                 if (staged) {
                     int t = t_of(tid);
+                    const int rctx = io.row_begin(slot_of(tid));
                     for (int u = 0; u < P0::U; u++)
                         for (int q = 0; q < P0::R; q++) {
                             int idx = P0::src_index(t, u, q);
-                            x[u * P0::R + q] = io.load_staged(stage.data(), g, row_of(tid), slot_of(tid), idx,
+                            x[u * P0::R + q] = io.load_staged(stage.data(), rctx, slot_of(tid), idx,
                                                               IO::kLoadAux ? io.load_aux(idx) : 0.0f);
                         }
                     done = true;
