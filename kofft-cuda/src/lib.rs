@@ -1,0 +1,211 @@
+//! `CudaFftImpl`: kofft's `FftImpl<f32>` on an NVIDIA B200 (sm_100a).
+//!
+//! Drop-in for the reference's `ScalarFftImpl<f32>` on the batched FFT / rfft / STFT path:
+//! the trait methods keep their argument meaning and error behaviour and produce results
+//! bit-identical to kofft's scalar/SSE f32 path (the kernels reuse kofft's own twiddle tables
+//! and stage structure).  `rfft`/`irfft` arrive through kofft's blanket `RealFftImpl`; the
+//! fused batched variants (`fft_batch`, `rfft_batch`, `stft`, `istft`) are inherent methods
+//! because the blanket impl cannot be specialised.
+//!
+//! FFI: `include/kofft_cuda.h` (C ABI of libkofft_cuda).  Return codes 1..=6 are the
+//! `FftError` variants in declaration order; a negative code is a CUDA failure, for which kofft
+//! has no variant, so it panics with the backend's message.
+#![allow(clippy::missing_safety_doc)]
+
+use core::ffi::{c_char, c_int, c_void};
+use kofft::fft::{Complex32, FftError, FftImpl, FftStrategy};
+
+#[repr(C)]
+pub struct RawCtx {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    fn kofft_cuda_create(out: *mut *mut RawCtx, device: c_int) -> c_int;
+    fn kofft_cuda_destroy(ctx: *mut RawCtx);
+    fn kofft_cuda_last_error() -> *const c_char;
+    fn kofft_cuda_set_exact(ctx: *mut RawCtx, exact: c_int) -> c_int;
+    fn kofft_cuda_fft_host_f32(ctx: *mut RawCtx, data: *mut f32, n: usize, inverse: c_int) -> c_int;
+    fn kofft_cuda_fft_batch_host_f32(ctx: *mut RawCtx, data: *mut f32, n: usize, batch: usize, inverse: c_int) -> c_int;
+    fn kofft_cuda_fft_split_host_f32(ctx: *mut RawCtx, re: *mut f32, re_len: usize, im: *mut f32, im_len: usize,
+                                     inverse: c_int) -> c_int;
+    fn kofft_cuda_fft_strided_host_f32(ctx: *mut RawCtx, input: *mut f32, input_len: usize, stride: usize, n: usize,
+                                       inverse: c_int) -> c_int;
+    fn kofft_cuda_fft_out_of_place_strided_host_f32(ctx: *mut RawCtx, input: *const f32, input_len: usize,
+                                                    in_stride: usize, output: *mut f32, output_len: usize,
+                                                    out_stride: usize, inverse: c_int) -> c_int;
+    fn kofft_cuda_rfft_batch_host_f32(ctx: *mut RawCtx, input: *const f32, n: usize, batch: usize, output: *mut f32) -> c_int;
+    fn kofft_cuda_irfft_batch_host_f32(ctx: *mut RawCtx, input: *const f32, n: usize, batch: usize, output: *mut f32) -> c_int;
+    fn kofft_cuda_stft_host_f32(ctx: *mut RawCtx, signal: *const f32, len: usize, channels: usize, window: *const f32,
+                                win_len: usize, hop: usize, frames: *mut f32, nframes: usize) -> c_int;
+    fn kofft_cuda_istft_host_f32(ctx: *mut RawCtx, frames: *const f32, nframes: usize, channels: usize,
+                                 window: *const f32, win_len: usize, hop: usize, output: *mut f32, out_len: usize,
+                                 scratch: *mut f32, scratch_len: usize, zero_uncovered: c_int) -> c_int;
+    // device-pointer entry points (stream-ordered) for callers that keep data on the GPU
+    pub fn kofft_cuda_fft_c2c_f32(ctx: *mut RawCtx, d_in: *const c_void, d_out: *mut c_void, n: usize, batch: usize,
+                                  inverse: c_int, stream: *mut c_void) -> c_int;
+    pub fn kofft_cuda_rfft_f32(ctx: *mut RawCtx, d_in: *const f32, d_out: *mut c_void, n: usize, batch: usize,
+                               stream: *mut c_void) -> c_int;
+    pub fn kofft_cuda_stft_f32(ctx: *mut RawCtx, d_signal: *const f32, len: usize, channels: usize,
+                               d_window: *const f32, win_len: usize, hop: usize, d_frames: *mut c_void,
+                               nframes: usize, stream: *mut c_void) -> c_int;
+}
+
+fn check(rc: c_int) -> Result<(), FftError> {
+    match rc {
+        0 => Ok(()),
+        1 => Err(FftError::EmptyInput),
+        2 => Err(FftError::NonPowerOfTwoNoStd),
+        3 => Err(FftError::MismatchedLengths),
+        4 => Err(FftError::InvalidStride),
+        5 => Err(FftError::InvalidHopSize),
+        6 => Err(FftError::InvalidValue),
+        _ => {
+            // kofft's FftError has no variant for a backend failure
+            let msg = unsafe { std::ffi::CStr::from_ptr(kofft_cuda_last_error()) };
+            panic!("kofft-cuda: CUDA backend error {rc}: {}", msg.to_string_lossy());
+        }
+    }
+}
+
+/// Owns one device context (stream, device-resident twiddle tables, workspaces).
+/// `!Sync` like the reference's `ScalarFftImpl` (src/fft.rs:589-605); `Send`.
+pub struct CudaFftImpl {
+    ctx: *mut RawCtx,
+}
+
+unsafe impl Send for CudaFftImpl {}
+
+impl CudaFftImpl {
+    /// Fails (no CPU fallback) if `device` is not a CUDA device of compute capability 10.x.
+    pub fn new(device: i32) -> Result<Self, String> {
+        let mut ctx = core::ptr::null_mut();
+        let rc = unsafe { kofft_cuda_create(&mut ctx, device) };
+        if rc != 0 {
+            let msg = unsafe { std::ffi::CStr::from_ptr(kofft_cuda_last_error()) };
+            return Err(msg.to_string_lossy().into_owned());
+        }
+        Ok(Self { ctx })
+    }
+    /// `false` selects the FMA-contracted butterflies (~1e-7 relative difference).
+    pub fn set_exact(&self, exact: bool) {
+        unsafe { kofft_cuda_set_exact(self.ctx, exact as c_int) };
+    }
+    pub fn raw(&self) -> *mut RawCtx {
+        self.ctx
+    }
+
+    /// `batch()` (src/fft.rs:2156-2164) over dense rows `[batch][n]` in one launch.
+    pub fn fft_batch(&self, rows: &mut [Complex32], n: usize, inverse: bool) -> Result<(), FftError> {
+        if n == 0 {
+            return Err(FftError::EmptyInput);
+        }
+        if rows.len() % n != 0 {
+            return Err(FftError::MismatchedLengths);
+        }
+        check(unsafe {
+            kofft_cuda_fft_batch_host_f32(self.ctx, rows.as_mut_ptr() as *mut f32, n, rows.len() / n, inverse as c_int)
+        })
+    }
+    /// Fused pack + FFT + twist per row: `[batch][n]` reals -> `[batch][n/2+1]` bins.
+    pub fn rfft_batch(&self, input: &[f32], n: usize, output: &mut [Complex32]) -> Result<(), FftError> {
+        if n == 0 {
+            return Err(FftError::EmptyInput);
+        }
+        let batch = input.len() / n;
+        if input.len() % n != 0 || output.len() != batch * (n / 2 + 1) {
+            return Err(FftError::MismatchedLengths);
+        }
+        check(unsafe { kofft_cuda_rfft_batch_host_f32(self.ctx, input.as_ptr(), n, batch, output.as_mut_ptr() as *mut f32) })
+    }
+    pub fn irfft_batch(&self, input: &[Complex32], n: usize, output: &mut [f32]) -> Result<(), FftError> {
+        if n == 0 {
+            return Err(FftError::EmptyInput);
+        }
+        let batch = output.len() / n;
+        if output.len() % n != 0 || input.len() != batch * (n / 2 + 1) {
+            return Err(FftError::MismatchedLengths);
+        }
+        check(unsafe { kofft_cuda_irfft_batch_host_f32(self.ctx, input.as_ptr() as *const f32, n, batch, output.as_mut_ptr()) })
+    }
+    /// `stft()` (src/stft.rs:76-105) for `channels` signals of `len` samples; `frames` is dense
+    /// `[channels][nframes][window.len()]`.
+    pub fn stft(&self, signal: &[f32], channels: usize, window: &[f32], hop: usize, frames: &mut [Complex32],
+                nframes: usize) -> Result<(), FftError> {
+        if channels == 0 || signal.len() % channels != 0 || frames.len() != channels * nframes * window.len() {
+            return Err(FftError::MismatchedLengths);
+        }
+        check(unsafe {
+            kofft_cuda_stft_host_f32(self.ctx, signal.as_ptr(), signal.len() / channels, channels, window.as_ptr(),
+                                     window.len(), hop, frames.as_mut_ptr() as *mut f32, nframes)
+        })
+    }
+    /// `istft()` (src/stft.rs:117-156): accumulates into `output`, fills `scratch` with the
+    /// window-power sums, normalises where the sum exceeds 1e-8.
+    pub fn istft(&self, frames: &[Complex32], channels: usize, window: &[f32], hop: usize, output: &mut [f32],
+                 scratch: &mut [f32]) -> Result<(), FftError> {
+        if scratch.len() != output.len() || channels == 0 || window.is_empty() {
+            return Err(FftError::MismatchedLengths);
+        }
+        let nframes = frames.len() / (channels * window.len());
+        check(unsafe {
+            kofft_cuda_istft_host_f32(self.ctx, frames.as_ptr() as *const f32, nframes, channels, window.as_ptr(),
+                                      window.len(), hop, output.as_mut_ptr(), output.len() / channels,
+                                      scratch.as_mut_ptr(), scratch.len(), 0)
+        })
+    }
+}
+
+impl Drop for CudaFftImpl {
+    fn drop(&mut self) {
+        unsafe { kofft_cuda_destroy(self.ctx) }
+    }
+}
+
+impl FftImpl<f32> for CudaFftImpl {
+    fn fft(&self, input: &mut [Complex32]) -> Result<(), FftError> {
+        check(unsafe { kofft_cuda_fft_host_f32(self.ctx, input.as_mut_ptr() as *mut f32, input.len(), 0) })
+    }
+    fn ifft(&self, input: &mut [Complex32]) -> Result<(), FftError> {
+        check(unsafe { kofft_cuda_fft_host_f32(self.ctx, input.as_mut_ptr() as *mut f32, input.len(), 1) })
+    }
+    fn fft_strided(&self, input: &mut [Complex32], stride: usize, scratch: &mut [Complex32]) -> Result<(), FftError> {
+        check(unsafe {
+            kofft_cuda_fft_strided_host_f32(self.ctx, input.as_mut_ptr() as *mut f32, input.len(), stride, scratch.len(), 0)
+        })
+    }
+    fn ifft_strided(&self, input: &mut [Complex32], stride: usize, scratch: &mut [Complex32]) -> Result<(), FftError> {
+        check(unsafe {
+            kofft_cuda_fft_strided_host_f32(self.ctx, input.as_mut_ptr() as *mut f32, input.len(), stride, scratch.len(), 1)
+        })
+    }
+    fn fft_out_of_place_strided(&self, input: &[Complex32], in_stride: usize, output: &mut [Complex32],
+                                out_stride: usize) -> Result<(), FftError> {
+        check(unsafe {
+            kofft_cuda_fft_out_of_place_strided_host_f32(self.ctx, input.as_ptr() as *const f32, input.len(), in_stride,
+                                                         output.as_mut_ptr() as *mut f32, output.len(), out_stride, 0)
+        })
+    }
+    fn ifft_out_of_place_strided(&self, input: &[Complex32], in_stride: usize, output: &mut [Complex32],
+                                 out_stride: usize) -> Result<(), FftError> {
+        check(unsafe {
+            kofft_cuda_fft_out_of_place_strided_host_f32(self.ctx, input.as_ptr() as *const f32, input.len(), in_stride,
+                                                         output.as_mut_ptr() as *mut f32, output.len(), out_stride, 1)
+        })
+    }
+    fn fft_with_strategy(&self, input: &mut [Complex32], _strategy: FftStrategy) -> Result<(), FftError> {
+        // every strategy runs the faithful Stockham kernels (Radix2/SplitRadix/Auto already do in the reference)
+        self.fft(input)
+    }
+    fn fft_split(&self, re: &mut [f32], im: &mut [f32]) -> Result<(), FftError> {
+        check(unsafe { kofft_cuda_fft_split_host_f32(self.ctx, re.as_mut_ptr(), re.len(), im.as_mut_ptr(), im.len(), 0) })
+    }
+    fn ifft_split(&self, re: &mut [f32], im: &mut [f32]) -> Result<(), FftError> {
+        check(unsafe { kofft_cuda_fft_split_host_f32(self.ctx, re.as_mut_ptr(), re.len(), im.as_mut_ptr(), im.len(), 1) })
+    }
+}
+
+/// What `kofft::fft::new_fft_impl()` (src/fft.rs:1954-1985) would return with the `cuda` feature.
+pub fn new_cuda_fft_impl(device: i32) -> Result<Box<dyn FftImpl<f32>>, String> {
+    Ok(Box::new(CudaFftImpl::new(device)?))
+}
