@@ -305,7 +305,20 @@ def run_gpu(args) -> None:
         algo = (4 * rn + 8 * (rn // 2 + 1)) * rb
         extra["rfft_65536x16384"] = {"ms": ms, "gflops_nominal": 2.5 * rn * 16 * rb / ms / 1e6, "hbm_gbs": algo / ms / 1e6,
                                      "frac_of_measured_peak": algo / ms / 1e6 / peak,
-                                     "note": "two kernels per 48 MB chunk (column pass, row pass + twist), L2-resident intermediate"}
+                                     "note": "one persistent thread-block-cluster kernel (column pass, cluster barrier, "
+                                             "row pass + twist), L2-resident intermediate"}
+        fft.ctx.set_cluster_fusion(False)
+        fft.rfft_batch(xr, out=yr)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fft.rfft_batch(xr, out=yr)
+        e1.record()
+        torch.cuda.synchronize()
+        fft.ctx.set_cluster_fusion(True)
+        ms2 = e0.elapsed_time(e1) / reps
+        extra["rfft_65536x16384_two_kernel_path"] = {"ms": ms2, "hbm_gbs": algo / ms2 / 1e6,
+                                                     "frac_of_measured_peak": algo / ms2 / 1e6 / peak}
         del xr, yr
         torch.cuda.empty_cache()
         free, _ = torch.cuda.mem_get_info()
@@ -330,6 +343,16 @@ def run_gpu(args) -> None:
         extra["stft"] = {"workload": f"Hann {win}, hop {hop}, {ch} ch x {length} samples (BASELINE configs[3])",
                          "frames_per_s": ch * nframes / (ms * 1e-3), "ms": ms, "hbm_gbs": algo / ms / 1e6,
                          "frac_of_measured_peak": algo / ms / 1e6 / peak}
+        S.stft_batch(fast, sig, w, hop, nframes, out=frames)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            S.stft_batch(fast, sig, w, hop, nframes, out=frames)
+        e1.record()
+        torch.cuda.synchronize()
+        msf = e0.elapsed_time(e1) / reps
+        extra["stft_fast_mode"] = {"frames_per_s": ch * nframes / (msf * 1e-3), "ms": msf, "hbm_gbs": algo / msf / 1e6,
+                                   "frac_of_measured_peak": algo / msf / 1e6 / peak}
         out = torch.zeros((ch, length), device=dev)
         S.istft_batch(fft, frames, w, hop, out)
         torch.cuda.synchronize()

@@ -64,6 +64,9 @@ unsigned long long kofft_cuda_launch_count(const kofft_cuda_ctx *ctx);
 /* enable (default) / disable the TMA-staged input prefetch (cp.async.bulk + mbarrier); the
  * library falls back to plain loads by itself when a pointer is not 16-byte aligned */
 int kofft_cuda_set_tma_staging(kofft_cuda_ctx *ctx, int enable);
+/* N > 16384: enable (default) / disable the single persistent thread-block-cluster kernel;
+ * when disabled (or unavailable) two kernels per L2-sized batch chunk are used instead */
+int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable);
 /* 0 = let the library size the grid (occupancy x SM count); otherwise cap the CTA count */
 int kofft_cuda_set_max_ctas(kofft_cuda_ctx *ctx, int max_ctas);
 

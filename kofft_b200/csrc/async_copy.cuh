@@ -49,7 +49,23 @@ KD void bulk_copy_g2s(void *dst_smem, const void *src, unsigned bytes, unsigned 
                  : "memory");
 }
 
+// thread-block cluster barrier with release/acquire semantics (all threads of all CTAs)
+KD void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+KD unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
 #elif defined(KOFFT_EMU)
+
+inline void cluster_sync() { cuda_emu::cluster_sync(); }
+inline unsigned cluster_ctarank() { return cuda_emu::cluster_rank(); }
 
 // *bar counts completed phases; a phase completes when the bytes announced by expect_tx have
 // all been delivered (copies are synchronous here).

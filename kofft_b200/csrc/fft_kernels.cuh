@@ -14,9 +14,10 @@ namespace kofft {
 
 #ifdef __CUDACC__
 #define KOFFT_LDG(p) __ldg(p)
-#define KOFFT_SYNC() __syncthreads()
+#define KOFFT_LDCG(p) __ldcg(p) // L2 only: data written by other CTAs of the same launch
 #else
 #define KOFFT_LDG(p) (*(p))
+#define KOFFT_LDCG(p) (*(p))
 #endif
 
 // ------------------------------------------------------------------------------------------

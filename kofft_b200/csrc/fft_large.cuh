@@ -40,6 +40,27 @@ struct ColPass {
     static constexpr int SMEM_BYTES = 2 * COLS * RS * 8;
     static_assert(P::T == 16 && P::CTA == 256 && P::TPC == COLS, "tile shape");
 
+    // one tile: 16 adjacent columns starting at j0 of transform `row` (io) -> scratch_row.
+    // bf: this thread's exchange region (column-fastest layout), tw1: pass-1 twiddles.
+    static KD void tile(const IO &io, const Tw0 &tw0, const float2 *tw1, int lsub, long row, long j0,
+                        float2 *__restrict__ scratch_row, float2 *bf, int t, int slot)
+    {
+        const long j = j0 + slot;
+        float2 x[EPT];
+#pragma unroll
+        for (int q = 0; q < P0::R; q++) x[q] = io.load(row, (int)(((long)P0::src_index(t, 0, q) << lsub) + j));
+        P0::compute(x, tw0.v);
+#pragma unroll
+        for (int w = 0; w < P0::R; w++) bf[P0::dst_pad(P0::dst_base(t, 0), w)] = x[w];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < P1::R; q++) x[q] = bf[P1::src_pad(P1::src_base(t, 0), q)];
+        P1::compute(x, tw1);
+        float2 *o = scratch_row + j;
+#pragma unroll
+        for (int w = 0; w < P1::R; w++) o[(long)P1::dst_index(t, 0, w) << lsub] = x[w];
+    }
+
     // n = 2^L elements per transform, lsub = L - 8, tiles = batch * (2^lsub / 16)
     // row0: index of the chunk's first transform in the caller's batch (scratch is chunk-local)
     static KD void run(const IO &io, const Tw0 &tw0, const float2 *__restrict__ table, int lsub, long tiles,
@@ -57,24 +78,11 @@ struct ColPass {
         P1::load_tw(table, t, tw1, map);
         const int ltiles = lsub - 4; // log2 tiles per transform
         const long n = 1L << (LARGE_S1 + lsub);
-        for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const long b = tile >> ltiles;
-            const long j = ((tile & ((1L << ltiles) - 1)) << 4) + slot;
-            float2 x[EPT];
-#pragma unroll
-            for (int q = 0; q < P0::R; q++) x[q] = io.load(row0 + b, (int)(((long)P0::src_index(t, 0, q) << lsub) + j));
-            P0::compute(x, tw0.v);
-            float2 *bf = par ? buf1 : buf0;
+        for (long tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+            const long b = tl >> ltiles;
+            const long j0 = (tl & ((1L << ltiles) - 1)) << 4;
+            tile(io, tw0, tw1, lsub, row0 + b, j0, scratch + b * n, par ? buf1 : buf0, t, slot);
             par ^= 1;
-#pragma unroll
-            for (int w = 0; w < P0::R; w++) bf[P0::dst_pad(P0::dst_base(t, 0), w)] = x[w];
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < P1::R; q++) x[q] = bf[P1::src_pad(P1::src_base(t, 0), q)];
-            P1::compute(x, tw1);
-            float2 *o = scratch + b * n + j;
-#pragma unroll
-            for (int w = 0; w < P1::R; w++) o[(long)P1::dst_index(t, 0, w) << lsub] = x[w];
         }
     }
 };
@@ -114,6 +122,52 @@ struct RowPass {
         return (kb == 0 && slot == HALF) ? HALF : slot - HALF;
     }
 
+    // one tile: the TPC sub-transforms of k-block kb of one transform, read from scratch_row
+    // (LDCG: the intermediate was written by other CTAs), stored / twisted through io as `row`.
+    // bfa/bfb: this thread's two exchange regions, alla/allb: the same buffers seen CTA-wide.
+    static KD void tile(const IO &io, const float2 *tw0, const float2 *tw1, long row, int kb, int k,
+                        const float2 *__restrict__ scratch_row, float2 *bfa, float2 *bfb, const float2 *allb, int t,
+                        int tid)
+    {
+        const float2 *in = scratch_row + (long)k * NB;
+        float2 x[EPT];
+#pragma unroll
+        for (int u = 0; u < P0::U; u++)
+#pragma unroll
+            for (int q = 0; q < P0::R; q++) x[u * P0::R + q] = KOFFT_LDCG(in + P0::src_index(t, u, q));
+        P0::compute(x, tw0);
+#pragma unroll
+        for (int u = 0; u < P0::U; u++)
+#pragma unroll
+            for (int w = 0; w < P0::R; w++) bfa[P0::dst_pad(P0::dst_base(t, u), w)] = x[u * P0::R + w];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < P1::R; q++) x[q] = bfa[P1::src_pad(P1::src_base(t, 0), q)];
+        P1::compute(x, tw1);
+        // transpose through shared memory: bins of all TPC sub-transforms, k fastest
+#pragma unroll
+        for (int w = 0; w < P1::R; w++) bfb[P1::dst_pad(P1::dst_base(t, 0), w)] = x[w];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const int flat = e * P::CTA + tid;
+            const int s2 = flat % TPC, c = flat / TPC;
+            const long K = kmap(kb, s2) + ((long)c << LARGE_S1);
+            const float2 a = allb[s2 * RS + pad(c)];
+            if constexpr (EPI == ROW_TWIST) {
+                const int kk = kmap(kb, s2);
+                float2 ym;
+                if (kk == 0)
+                    ym = c == 0 ? a : allb[s2 * RS + pad(NB - c)]; // m - K = 256 (NB - c)
+                else
+                    ym = allb[mirror_slot(kb, s2) * RS + pad(NB - 1 - c)];
+                io.twist_store(row, K, a, ym);
+            } else {
+                io.store(row, (int)K, a);
+            }
+        }
+    }
+
     // tiles = batch * NKB; the grid is a multiple of NKB so a CTA keeps its k-block (and with it
     // its twiddles, which live in registers) for every tile it processes.
     static KD void run(const IO &io, const float2 *__restrict__ table, long tiles, long row0,
@@ -126,9 +180,6 @@ struct RowPass {
         const int k = kmap(kb, slot);
         float2 *buf0 = smem + slot * RS;
         float2 *buf1 = buf0 + TPC * RS;
-        const float2 *all0 = smem;
-        const float2 *all1 = smem + TPC * RS;
-        int par = 0;
         TwMap map;
         map.k0 = k;
         map.sh1 = LARGE_S1;
@@ -136,50 +187,72 @@ struct RowPass {
         P0::load_tw(table, t, tw0, map);
         P1::load_tw(table, t, tw1, map);
         const long n = (long)NB << LARGE_S1;
-        for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const long b = tile / NKB;
-            const float2 *in = scratch + b * n + (long)k * NB;
-            float2 x[EPT];
-#pragma unroll
-            for (int u = 0; u < P0::U; u++)
-#pragma unroll
-                for (int q = 0; q < P0::R; q++) x[u * P0::R + q] = in[P0::src_index(t, u, q)];
-            P0::compute(x, tw0);
-            float2 *bf = par ? buf1 : buf0;
-            par ^= 1;
-#pragma unroll
-            for (int u = 0; u < P0::U; u++)
-#pragma unroll
-                for (int w = 0; w < P0::R; w++) bf[P0::dst_pad(P0::dst_base(t, u), w)] = x[u * P0::R + w];
+        for (long tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+            const long b = tl / NKB;
+            // buffer A of this tile was last read before the previous tile's second barrier and
+            // buffer B before this tile's first barrier, so two buffers suffice
+            tile(io, tw0, tw1, row0 + b, kb, k, scratch + b * n, buf0, buf1, smem + TPC * RS, t, tid);
             __syncthreads();
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Both passes in ONE persistent kernel: a thread-block cluster of NKB CTAs owns one transform at
+// a time.  Each CTA runs its share of the column tiles, the cluster synchronises
+// (barrier.cluster, release/acquire), then CTA `rank` runs k-block `rank` of the row pass.  The
+// intermediate goes through a small per-cluster global scratch (double-buffered, a few MB in
+// total, so it never leaves L2) and is read back with ld.global.cg.  One launch per batch, no
+// chunking, no launch gaps, and the row-pass twiddles stay in registers.
+// ---------------------------------------------------------------------------------------------
+template <int LB, bool EXACT, class IO, int EPI>
+struct LargeFused {
+    using C = ColPass<EXACT, IO>;
+    using R = RowPass<LB, EXACT, IO, EPI>;
+    static constexpr int CLUSTER = R::NKB;             // 8 (N = 2^15) or 16 (N = 2^16) CTAs
+    static constexpr int NTA = (1 << LB) / C::COLS;    // column tiles per transform (== CLUSTER)
+    static constexpr int TW_SMEM = 16 * 16;            // pass-A pass-1 twiddles: [t][15] float2
+    static constexpr int XCHG = (C::SMEM_BYTES > R::SMEM_BYTES ? C::SMEM_BYTES : R::SMEM_BYTES);
+    static constexpr int SMEM_BYTES = XCHG + TW_SMEM * 8;
+    static_assert(NTA == CLUSTER, "one column tile and one k-block per CTA");
+
+    // scratch: clusters * 2 * n complex.  rows: transforms in the batch.
+    static KD void run(const IO &io, const Tw0 &tw0, const float2 *__restrict__ table, long rows,
+                       float2 *__restrict__ scratch, float2 *smem, int rank, long cluster_id, long nclusters)
+    {
+        const int tid = threadIdx.x;
+        const long n = 1L << (LARGE_S1 + LB);
+        // pass A (column-fastest mapping)
+        const int slotA = tid & (C::COLS - 1), tA = tid >> 4;
+        float2 *twA = smem + XCHG / 8; // shared copy of the 16 x 15 pass-1 twiddles of the 256-point pass
+        if (tid < 16) {
+            TwMap map;
+            map.sh2 = LB;
+            float2 tmp[C::P1::NTW];
+            C::P1::load_tw(table, tid, tmp, map);
 #pragma unroll
-            for (int q = 0; q < P1::R; q++) x[q] = bf[P1::src_pad(P1::src_base(t, 0), q)];
-            P1::compute(x, tw1);
-            // transpose through shared memory: bins of all TPC sub-transforms, k fastest
-            bf = par ? buf1 : buf0;
-            const float2 *all = par ? all1 : all0;
-            par ^= 1;
-#pragma unroll
-            for (int w = 0; w < P1::R; w++) bf[P1::dst_pad(P1::dst_base(t, 0), w)] = x[w];
-            __syncthreads();
-#pragma unroll
-            for (int e = 0; e < EPT; e++) {
-                const int flat = e * P::CTA + tid;
-                const int s2 = flat % TPC, c = flat / TPC;
-                const long K = kmap(kb, s2) + ((long)c << LARGE_S1);
-                const float2 a = all[s2 * RS + pad(c)];
-                if constexpr (EPI == ROW_TWIST) {
-                    const int kk = kmap(kb, s2);
-                    float2 ym;
-                    if (kk == 0)
-                        ym = c == 0 ? a : all[s2 * RS + pad(NB - c)]; // m - K = 256 (NB - c)
-                    else
-                        ym = all[mirror_slot(kb, s2) * RS + pad(NB - 1 - c)];
-                    io.twist_store(row0 + b, K, a, ym);
-                } else {
-                    io.store(row0 + b, (int)K, a);
-                }
-            }
+            for (int i = 0; i < C::P1::NTW; i++) twA[tid * 16 + i] = tmp[i];
+        }
+        // pass B (sub-transform-major mapping); k-block == cluster rank, twiddles in registers
+        const int slotB = tid / R::P::T, tB = tid - slotB * R::P::T;
+        const int kb = rank, k = R::kmap(kb, slotB);
+        TwMap mapB;
+        mapB.k0 = k;
+        mapB.sh1 = LARGE_S1;
+        float2 twB0[R::P0::NTW], twB1[R::P1::NTW];
+        R::P0::load_tw(table, tB, twB0, mapB);
+        R::P1::load_tw(table, tB, twB1, mapB);
+        __syncthreads();
+
+        float2 *bufA0 = smem + slotA * C::RS;
+        float2 *bufB0 = smem + slotB * R::RS, *bufB1 = bufB0 + R::TPC * R::RS;
+        int it = 0;
+        for (long b = cluster_id; b < rows; b += nclusters, it ^= 1) {
+            float2 *sc = scratch + (cluster_id * 2 + it) * n;
+            C::tile(io, tw0, twA + tA * 16, LB, b, (long)rank * C::COLS, sc, bufA0, tA, slotA);
+            cluster_sync(); // every column tile of this transform is in `sc` (also a CTA barrier)
+            R::tile(io, twB0, twB1, b, kb, k, sc, bufB0, bufB1, smem + R::TPC * R::RS, tB, tid);
+            __syncthreads(); // smem is reused by the next transform's column tile
         }
     }
 };
@@ -201,6 +274,16 @@ __global__ void __launch_bounds__(256, 2)
 {
     extern __shared__ __align__(128) float2 smem[];
     RowPass<LB, EXACT, IO, EPI>::run(io, table, tiles, row0, scratch, smem);
+}
+template <int LB, bool EXACT, class IO, int EPI>
+__global__ void __launch_bounds__(256, 2)
+    large_fused_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0 tw0, const float2 *__restrict__ table,
+                       long rows, float2 *__restrict__ scratch)
+{
+    extern __shared__ __align__(128) float2 smem[];
+    using F = LargeFused<LB, EXACT, IO, EPI>;
+    const int rank = (int)cluster_ctarank();
+    F::run(io, tw0, table, rows, scratch, smem, rank, blockIdx.x / F::CLUSTER, gridDim.x / F::CLUSTER);
 }
 #endif
 

@@ -52,43 +52,84 @@ cudaError_t launch_row(const IO &io, const LaunchArgs &a, const LargeArgs &g)
     return cudaGetLastError();
 }
 
+// one persistent launch: clusters of NKB CTAs, one transform per cluster at a time
+template <int LB, bool EXACT, class IO, int EPI>
+cudaError_t launch_fused(const IO &io, const LaunchArgs &a, const LargeArgs &g)
+{
+    using F = LargeFused<LB, EXACT, IO, EPI>;
+    auto kern = large_fused_kernel<LB, EXACT, IO, EPI>;
+    static int max_clusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = F::CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = F::SMEM_BYTES;
+    cfg.stream = a.stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        if (F::CLUSTER > 8) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return e;
+        }
+        cfg.gridDim = dim3(F::CLUSTER * a.num_sms, 1, 1);
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e != cudaSuccess) return e;
+        if (n < 1) return cudaErrorLaunchOutOfResources;
+        max_clusters = n;
+    }
+    long nclusters = g.chunk_rows < max_clusters ? g.chunk_rows : max_clusters;
+    if (g.max_clusters > 0 && nclusters > g.max_clusters) nclusters = g.max_clusters;
+    if (nclusters < 1) return cudaSuccess;
+    cfg.gridDim = dim3((unsigned)(nclusters * F::CLUSTER), 1, 1);
+    return cudaLaunchKernelEx(&cfg, kern, io, a.tw0, a.table, g.chunk_rows, g.scratch);
+}
+
+template <int LB, bool EXACT, class IO, int EPI>
+cudaError_t launch_both(const IO &io, const LaunchArgs &a, const LargeArgs &g)
+{
+    if (g.fused) return launch_fused<LB, EXACT, IO, EPI>(io, a, g);
+    cudaError_t e = launch_col<EXACT>(io, a, g);
+    if (e != cudaSuccess) return e;
+    return launch_row<LB, EXACT, IO, EPI>(io, a, g);
+}
+
 template <int LB, bool EXACT>
 cudaError_t launch_pair(const LaunchArgs &a, const LargeArgs &g)
 {
     const IoArgs &q = a.io;
-    cudaError_t e;
     switch (a.kind) {
     case KIND_C2C_FWD: {
         IoC2C<false> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale};
-        if ((e = launch_col<EXACT>(io, a, g)) != cudaSuccess) return e;
-        return launch_row<LB, EXACT, IoC2C<false>, ROW_STORE>(io, a, g);
+        return launch_both<LB, EXACT, IoC2C<false>, ROW_STORE>(io, a, g);
     }
     case KIND_C2C_INV: {
         IoC2C<true> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale};
-        if ((e = launch_col<EXACT>(io, a, g)) != cudaSuccess) return e;
-        return launch_row<LB, EXACT, IoC2C<true>, ROW_STORE>(io, a, g);
+        return launch_both<LB, EXACT, IoC2C<true>, ROW_STORE>(io, a, g);
     }
     case KIND_GEN_FWD: {
         IoGeneric<false> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2,
                             q.p0, q.p1, q.p2, q.p3, q.scale};
-        if ((e = launch_col<EXACT>(io, a, g)) != cudaSuccess) return e;
-        return launch_row<LB, EXACT, IoGeneric<false>, ROW_STORE>(io, a, g);
+        return launch_both<LB, EXACT, IoGeneric<false>, ROW_STORE>(io, a, g);
     }
     case KIND_GEN_INV: {
         IoGeneric<true> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2,
                            q.p0, q.p1, q.p2, q.p3, q.scale};
-        if ((e = launch_col<EXACT>(io, a, g)) != cudaSuccess) return e;
-        return launch_row<LB, EXACT, IoGeneric<true>, ROW_STORE>(io, a, g);
+        return launch_both<LB, EXACT, IoGeneric<true>, ROW_STORE>(io, a, g);
     }
     case KIND_RFFT: {
         IoRfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n};
-        if ((e = launch_col<EXACT>(io, a, g)) != cudaSuccess) return e;
-        return launch_row<LB, EXACT, IoRfft<EXACT>, ROW_TWIST>(io, a, g);
+        return launch_both<LB, EXACT, IoRfft<EXACT>, ROW_TWIST>(io, a, g);
     }
     case KIND_IRFFT: {
         IoIrfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n, q.scale};
-        if ((e = launch_col<EXACT>(io, a, g)) != cudaSuccess) return e;
-        return launch_row<LB, EXACT, IoIrfft<EXACT>, ROW_STORE>(io, a, g);
+        return launch_both<LB, EXACT, IoIrfft<EXACT>, ROW_STORE>(io, a, g);
     }
     default:
         return cudaErrorNotSupported;

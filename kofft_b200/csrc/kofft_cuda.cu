@@ -78,6 +78,7 @@ struct kofft_cuda_ctx {
     size_t large_scratch_bytes = size_t(48) << 20; // two-pass intermediate per chunk: stays in the 126 MB L2
     size_t istft_ws_limit = size_t(1) << 30;
     bool use_tma = true; // TMA-staged input prefetch where alignment allows
+    bool large_fused = true; // N > 16384: one persistent thread-block-cluster kernel
 };
 
 namespace {
@@ -172,12 +173,30 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
                     size_t idx = static_cast<size_t>(c) << (L - 1 - tl);
                     a.tw0.v[(1 << tl) - 1 + c] = make_float2(t->host[2 * idx], t->host[2 * idx + 1]);
                 }
-            // chunk the batch so the intermediate stays L2-resident
             const size_t row_bytes = n * sizeof(float2);
+            void *scratch = nullptr;
+            if (ctx->large_fused) {
+                // one persistent launch; each cluster double-buffers one transform in scratch
+                rc = ensure_ws(ctx, 4, size_t(kMaxFusedClusters) * 2 * row_bytes, &scratch);
+                if (rc) return rc;
+                LargeArgs g;
+                g.lsub = L - 8;
+                g.row0 = 0;
+                g.chunk_rows = static_cast<long>(rows);
+                g.scratch = static_cast<float2 *>(scratch);
+                g.fused = true;
+                g.max_clusters = kMaxFusedClusters;
+                e = launch_large_fft(L, a, g);
+                if (e == cudaSuccess) {
+                    ctx->launches += 1;
+                    return KOFFT_OK;
+                }
+                (void)cudaGetLastError(); // cluster launch not possible: fall through to two kernels
+            }
+            // chunk the batch so the intermediate stays L2-resident
             size_t chunk = ctx->large_scratch_bytes / row_bytes;
             if (chunk < 1) chunk = 1;
             if (chunk > rows) chunk = rows;
-            void *scratch = nullptr;
             rc = ensure_ws(ctx, 4, chunk * row_bytes, &scratch);
             if (rc) return rc;
             for (size_t r0 = 0; r0 < rows; r0 += chunk) {
@@ -186,6 +205,7 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
                 g.row0 = static_cast<long>(r0);
                 g.chunk_rows = static_cast<long>(rows - r0 < chunk ? rows - r0 : chunk);
                 g.scratch = static_cast<float2 *>(scratch);
+                g.fused = false;
                 e = launch_large_fft(L, a, g);
                 if (e != cudaSuccess) return fail_cuda(e, "large-N kernel launch");
                 ctx->launches += 2;
@@ -296,6 +316,11 @@ int kofft_cuda_set_max_ctas(kofft_cuda_ctx *ctx, int max_ctas)
 int kofft_cuda_set_tma_staging(kofft_cuda_ctx *ctx, int enable)
 {
     ctx->use_tma = enable != 0;
+    return KOFFT_OK;
+}
+int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable)
+{
+    ctx->large_fused = enable != 0;
     return KOFFT_OK;
 }
 int kofft_cuda_set_rfft_table_fma(kofft_cuda_ctx *ctx, int fma_mul)

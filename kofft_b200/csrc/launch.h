@@ -55,8 +55,13 @@ struct LargeArgs {
     int lsub = 0;             // L - 8
     long row0 = 0;            // first transform of the chunk
     long chunk_rows = 0;      // transforms in the chunk
-    float2 *scratch = nullptr; // chunk_rows * 2^L complex, reused by every chunk (L2-resident)
+    float2 *scratch = nullptr; // two-kernel path: chunk_rows * 2^L complex, reused by every chunk
+                               // fused path: clusters * 2 * 2^L complex (L2-resident either way)
+    bool fused = true;         // one persistent cluster kernel instead of two kernels per chunk
+    int max_clusters = 0;      // fused path: 0 = as many clusters as fit on the device
 };
+// upper bound on the clusters the fused kernel runs with (sizes its scratch)
+constexpr int kMaxFusedClusters = 148;
 cudaError_t launch_large_fft(int L, const LaunchArgs &a, const LargeArgs &g);
 
 // per-L entry points (one per fft_inst.cu build)

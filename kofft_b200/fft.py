@@ -95,6 +95,9 @@ class Context:
     def set_tma_staging(self, enable: bool) -> None:
         check(_lib.lib().kofft_cuda_set_tma_staging(self.handle, int(bool(enable))))
 
+    def set_cluster_fusion(self, enable: bool) -> None:
+        check(_lib.lib().kofft_cuda_set_cluster_fusion(self.handle, int(bool(enable))))
+
     def set_rfft_table_fma(self, fma: bool) -> None:
         check(_lib.lib().kofft_cuda_set_rfft_table_fma(self.handle, int(bool(fma))))
 

@@ -41,14 +41,23 @@ struct Thread {
     std::vector<char> stack;
     bool done = false;
     emu_dim3 tid;
+    unsigned block = 0; // index of the thread's block inside the cluster
+};
+
+struct BlockState {
+    unsigned long long generation = 0;
+    int arrived = 0;
+    int alive = 0;
+    emu_dim3 bid;
 };
 
 struct Scheduler {
     ucontext_t main_ctx;
     std::vector<Thread> threads;
+    std::vector<BlockState> blocks; // the blocks of one cluster run concurrently
     int current = -1;
-    unsigned long long barrier_generation = 0;
-    int barrier_arrived = 0;
+    unsigned long long cluster_generation = 0;
+    int cluster_arrived = 0;
     int alive = 0;
     std::function<void()> body;
 };
@@ -65,69 +74,97 @@ inline void yield_to_scheduler()
 inline void syncthreads()
 {
     Scheduler *s = g_sched;
-    const unsigned long long gen = s->barrier_generation;
-    if (++s->barrier_arrived == s->alive) {
-        s->barrier_arrived = 0;
-        s->barrier_generation++;
+    BlockState &b = s->blocks[s->threads[s->current].block];
+    const unsigned long long gen = b.generation;
+    if (++b.arrived == b.alive) {
+        b.arrived = 0;
+        b.generation++;
         return;
     }
-    while (s->barrier_generation == gen) yield_to_scheduler();
+    while (b.generation == gen) yield_to_scheduler();
 }
+
+// barrier.cluster.arrive + wait: every thread of every block of the cluster
+inline void cluster_sync()
+{
+    Scheduler *s = g_sched;
+    const unsigned long long gen = s->cluster_generation;
+    if (++s->cluster_arrived == s->alive) {
+        s->cluster_arrived = 0;
+        s->cluster_generation++;
+        return;
+    }
+    while (s->cluster_generation == gen) yield_to_scheduler();
+}
+
+inline unsigned cluster_rank() { return g_sched->threads[g_sched->current].block; }
 
 inline void trampoline()
 {
     Scheduler *s = g_sched;
     s->body();
     Thread &t = s->threads[s->current];
+    BlockState &b = s->blocks[t.block];
     t.done = true;
     s->alive--;
-    // a thread that exits counts as arrived for any barrier the others wait on (CUDA semantics
-    // for exited threads)
-    if (s->alive > 0 && s->barrier_arrived == s->alive) {
-        s->barrier_arrived = 0;
-        s->barrier_generation++;
+    b.alive--;
+    // an exited thread no longer takes part in barriers
+    if (b.alive > 0 && b.arrived == b.alive) {
+        b.arrived = 0;
+        b.generation++;
+    }
+    if (s->alive > 0 && s->cluster_arrived == s->alive) {
+        s->cluster_arrived = 0;
+        s->cluster_generation++;
     }
     swapcontext(&t.ctx, &s->main_ctx);
 }
 
-// run `body` once per thread of one block
-inline void run_block(unsigned block_x, unsigned grid_x, unsigned threads_x, const std::function<void()> &body)
+// run `body` once per thread of `cluster` consecutive blocks starting at first_block
+inline void run_cluster(unsigned first_block, unsigned cluster, unsigned grid_x, unsigned threads_x,
+                        const std::function<void()> &body)
 {
     Scheduler s;
     s.body = body;
-    s.threads.resize(threads_x);
-    s.alive = static_cast<int>(threads_x);
+    s.threads.resize(static_cast<size_t>(threads_x) * cluster);
+    s.blocks.resize(cluster);
+    s.alive = static_cast<int>(threads_x * cluster);
     g_sched = &s;
-    blockIdx.x = block_x;
     gridDim.x = grid_x;
     blockDim.x = threads_x;
     const size_t stack_bytes = 256 * 1024;
-    for (unsigned i = 0; i < threads_x; i++) {
-        Thread &t = s.threads[i];
-        t.stack.resize(stack_bytes);
-        t.tid.x = i;
-        getcontext(&t.ctx);
-        t.ctx.uc_stack.ss_sp = t.stack.data();
-        t.ctx.uc_stack.ss_size = stack_bytes;
-        t.ctx.uc_link = &s.main_ctx;
-        makecontext(&t.ctx, reinterpret_cast<void (*)()>(trampoline), 0);
+    for (unsigned c = 0; c < cluster; c++) {
+        s.blocks[c].alive = static_cast<int>(threads_x);
+        s.blocks[c].bid.x = first_block + c;
+        for (unsigned i = 0; i < threads_x; i++) {
+            Thread &t = s.threads[c * threads_x + i];
+            t.stack.resize(stack_bytes);
+            t.tid.x = i;
+            t.block = c;
+            getcontext(&t.ctx);
+            t.ctx.uc_stack.ss_sp = t.stack.data();
+            t.ctx.uc_stack.ss_size = stack_bytes;
+            t.ctx.uc_link = &s.main_ctx;
+            makecontext(&t.ctx, reinterpret_cast<void (*)()>(trampoline), 0);
+        }
     }
     while (s.alive > 0) {
-        for (unsigned i = 0; i < threads_x; i++) {
+        for (size_t i = 0; i < s.threads.size(); i++) {
             Thread &t = s.threads[i];
             if (t.done) continue;
             s.current = static_cast<int>(i);
             threadIdx = t.tid;
+            blockIdx = s.blocks[t.block].bid;
             swapcontext(&s.main_ctx, &t.ctx);
         }
     }
     g_sched = nullptr;
 }
 
-// launch a whole grid, block after block
-inline void launch(unsigned grid_x, unsigned threads_x, const std::function<void()> &body)
+// launch a whole grid, block after block (or cluster after cluster)
+inline void launch(unsigned grid_x, unsigned threads_x, const std::function<void()> &body, unsigned cluster = 1)
 {
-    for (unsigned b = 0; b < grid_x; b++) run_block(b, grid_x, threads_x, body);
+    for (unsigned b = 0; b < grid_x; b += cluster) run_cluster(b, cluster, grid_x, threads_x, body);
 }
 
 } // namespace cuda_emu

@@ -94,16 +94,49 @@ int run_large(const IO &io, const float *table, long rows, int grid_col, int gri
     return 0;
 }
 
+// the fused cluster kernel body: grid_col is reused as the number of clusters
+template <int LB, bool EXACT, class IO, int EPI>
+int run_fused(const IO &io, const float *table, long rows, int nclusters)
+{
+    using F = LargeFused<LB, EXACT, IO, EPI>;
+    const int L = LB + LARGE_S1;
+    const long n = 1L << L;
+    Tw0 tw0 = make_tw0(L, 4, table);
+    const float2 *tab = reinterpret_cast<const float2 *>(table);
+    if (nclusters > rows) nclusters = (int)rows;
+    if (nclusters < 1) nclusters = 1;
+    std::vector<float2> scratch((size_t)nclusters * 2 * n);
+    // one shared-memory block per CTA of the cluster
+    const size_t per = (F::SMEM_BYTES + 255) / 8;
+    std::vector<float2> smem(per * F::CLUSTER + 32);
+    float2 *base = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
+    const unsigned grid = (unsigned)nclusters * F::CLUSTER;
+    cuda_emu::launch(grid, 256, [&] {
+        const unsigned rank = cuda_emu::cluster_rank();
+        float2 *sm = base + (size_t)rank * ((per + 15) / 16 * 16);
+        F::run(io, tw0, tab, rows, scratch.data(), sm, (int)rank, blockIdx.x / F::CLUSTER, gridDim.x / F::CLUSTER);
+    }, F::CLUSTER);
+    return 0;
+}
+
+static bool g_fused = false;
+
+template <int LB, bool EXACT, class IO, int EPI>
+int run_large_any(const IO &io, const float *table, long rows, int gc, int gr)
+{
+    return g_fused ? run_fused<LB, EXACT, IO, EPI>(io, table, rows, gc) : run_large<LB, EXACT, IO, EPI>(io, table, rows, gc, gr);
+}
+
 template <int LB, bool EXACT>
 int run_large_kind(int kind, const Args &q, const float *table, long rows, int gc, int gr)
 {
     switch (kind) {
-    case 0: { IoC2C<false> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale}; return run_large<LB, EXACT, IoC2C<false>, ROW_STORE>(io, table, rows, gc, gr); }
-    case 1: { IoC2C<true> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale}; return run_large<LB, EXACT, IoC2C<true>, ROW_STORE>(io, table, rows, gc, gr); }
-    case 2: { IoGeneric<false> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_large<LB, EXACT, IoGeneric<false>, ROW_STORE>(io, table, rows, gc, gr); }
-    case 3: { IoGeneric<true> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_large<LB, EXACT, IoGeneric<true>, ROW_STORE>(io, table, rows, gc, gr); }
-    case 6: { IoRfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n}; return run_large<LB, EXACT, IoRfft<EXACT>, ROW_TWIST>(io, table, rows, gc, gr); }
-    case 7: { IoIrfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n, q.scale}; return run_large<LB, EXACT, IoIrfft<EXACT>, ROW_STORE>(io, table, rows, gc, gr); }
+    case 0: { IoC2C<false> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale}; return run_large_any<LB, EXACT, IoC2C<false>, ROW_STORE>(io, table, rows, gc, gr); }
+    case 1: { IoC2C<true> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale}; return run_large_any<LB, EXACT, IoC2C<true>, ROW_STORE>(io, table, rows, gc, gr); }
+    case 2: { IoGeneric<false> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_large_any<LB, EXACT, IoGeneric<false>, ROW_STORE>(io, table, rows, gc, gr); }
+    case 3: { IoGeneric<true> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_large_any<LB, EXACT, IoGeneric<true>, ROW_STORE>(io, table, rows, gc, gr); }
+    case 6: { IoRfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n}; return run_large_any<LB, EXACT, IoRfft<EXACT>, ROW_TWIST>(io, table, rows, gc, gr); }
+    case 7: { IoIrfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n, q.scale}; return run_large_any<LB, EXACT, IoIrfft<EXACT>, ROW_STORE>(io, table, rows, gc, gr); }
     default: return -2;
     }
 }
@@ -137,6 +170,8 @@ API int kofft_emuk_cta(int kind, int exact, int L, long rows, const void *in, co
     return exact ? run_cta_kind<true>(kind, L, q, table, rows, staged != 0, grid)
                  : run_cta_kind<false>(kind, L, q, table, rows, staged != 0, grid);
 }
+
+API void kofft_emuk_set_fused(int fused) { g_fused = fused != 0; }
 
 // the real two-pass kernel bodies; L = 15 or 16 is the length of the complex core
 API int kofft_emuk_large(int kind, int exact, int L, long rows, const void *in, const void *in2, void *out,

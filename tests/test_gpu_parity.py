@@ -627,6 +627,28 @@ def test_large_c2c(cuda_fft, cuda_fft_fast, oracle, n):
     assert np.array_equal(re, ref1.real) and np.array_equal(im, ref1.imag)
 
 
+@pytest.mark.parametrize("n", [32768, 65536])
+def test_large_cluster_fused_and_two_kernel_paths_agree(cuda_fft, oracle, n):
+    """N > 16384 runs as one persistent thread-block-cluster kernel by default; the two-kernel
+    chunked path is the fallback.  Both must be bit-identical to the oracle (enough rows that
+    every cluster iterates several times)."""
+    rng = np.random.default_rng(n + 1)
+    rows = 150
+    x = uniform_c64(rng, (rows, n))
+    ref = oracle.fft_batch(x, nthreads=8)
+    xr = rng.uniform(-1, 1, (rows, 2 * n)).astype(np.float32)
+    rref = oracle.rfft_batch(xr, nthreads=8)
+    try:
+        for fused in (True, False):
+            cuda_fft.ctx.set_cluster_fusion(fused)
+            y = x.copy()
+            cuda_fft.fft_batch(y)
+            assert np.array_equal(y, ref), f"fused={fused}"
+            assert np.array_equal(cuda_fft.rfft_batch(xr), rref), f"fused={fused}"
+    finally:
+        cuda_fft.ctx.set_cluster_fusion(True)
+
+
 @pytest.mark.parametrize("n", [65536, 131072])
 def test_large_rfft_irfft(cuda_fft, cuda_fft_fast, oracle, n):
     rng = np.random.default_rng(n)
