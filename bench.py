@@ -364,7 +364,18 @@ def run_gpu(args) -> None:
         ms = e0.elapsed_time(e1)
         extra["istft"] = {"frames_per_s": ch * nframes / (ms * 1e-3), "ms": ms, "hbm_gbs": algo / ms / 1e6,
                           "frac_of_measured_peak": algo / ms / 1e6 / peak,
-                          "note": "two-kernel path (ifft+window, ordered overlap-add gather)"}
+                          "note": "one fused kernel (ifft + window + ordered overlap-add + normalisation)"}
+        fft.ctx.set_istft_fusion(False)
+        S.istft_batch(fft, frames, w, hop, out)
+        torch.cuda.synchronize()
+        e0.record()
+        S.istft_batch(fft, frames, w, hop, out)
+        e1.record()
+        torch.cuda.synchronize()
+        fft.ctx.set_istft_fusion(True)
+        ms2 = e0.elapsed_time(e1)
+        extra["istft_two_kernel_path"] = {"frames_per_s": ch * nframes / (ms2 * 1e-3), "ms": ms2,
+                                          "frac_of_measured_peak": algo / ms2 / 1e6 / peak}
         del sig, frames, out
     except Exception as e:  # extras never invalidate the headline line
         extra["error"] = f"{type(e).__name__}: {e}"

@@ -29,6 +29,7 @@ SIGNATURES = {
     "kofft_cuda_set_max_ctas": (_i, [_vp, _i]),
     "kofft_cuda_set_tma_staging": (_i, [_vp, _i]),
     "kofft_cuda_set_cluster_fusion": (_i, [_vp, _i]),
+    "kofft_cuda_set_istft_fusion": (_i, [_vp, _i, _i]),
     "kofft_cuda_twiddles_host_f32": (_i, [_sz, _vp]),
     "kofft_cuda_rfft_twiddles_host_f32": (_i, [_sz, _vp, _i]),
     "kofft_cuda_get_twiddles": (_i, [_vp, _sz, C.POINTER(_vp)]),

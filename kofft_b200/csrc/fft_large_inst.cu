@@ -1,4 +1,7 @@
 // fft_large_inst.cu -- instantiates the two-pass kernels (fft_large.cuh) for N = 2^15, 2^16.
+#include <cstdio>
+#include <cstdlib>
+
 #include "fft_large.cuh"
 #include "launch.h"
 
@@ -83,6 +86,9 @@ cudaError_t launch_fused(const IO &io, const LaunchArgs &a, const LargeArgs &g)
         if (e != cudaSuccess) return e;
         if (n < 1) return cudaErrorLaunchOutOfResources;
         max_clusters = n;
+        if (getenv("KOFFT_CUDA_VERBOSE"))
+            fprintf(stderr, "[kofft_cuda] large_fused LB=%d cluster=%d smem=%d: max active clusters %d\n", LB,
+                    F::CLUSTER, F::SMEM_BYTES, n);
     }
     long nclusters = g.chunk_rows < max_clusters ? g.chunk_rows : max_clusters;
     if (g.max_clusters > 0 && nclusters > g.max_clusters) nclusters = g.max_clusters;

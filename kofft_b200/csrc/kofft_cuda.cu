@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "host_tables.h"
+#include "istft_fused.cuh"
 #include "launch.h"
 
 using namespace kofft;
@@ -79,6 +80,8 @@ struct kofft_cuda_ctx {
     size_t istft_ws_limit = size_t(1) << 30;
     bool use_tma = true; // TMA-staged input prefetch where alignment allows
     bool large_fused = true; // N > 16384: one persistent thread-block-cluster kernel
+    bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
+    int istft_run_frames = 64;
 };
 
 namespace {
@@ -133,6 +136,19 @@ int get_rfft_table(kofft_cuda_ctx *ctx, size_t m, const Table **out)
     }
     *out = &it->second;
     return 0;
+}
+
+// pass-0 twiddles (group k = 0) of the single-CTA engine: v[(2^t - 1) + c] = T[c << (L-1-t)]
+void fill_tw0(const Table *t, int L, Tw0 *tw0)
+{
+    memset(tw0, 0, sizeof *tw0);
+    const int NP = L <= 8 ? 2 : (L <= 12 ? 3 : 4);
+    const int R0 = L - 4 * (NP - 1);
+    for (int tl = 0; tl < R0; tl++)
+        for (int c = 0; c < (1 << tl); c++) {
+            size_t idx = static_cast<size_t>(c) << (L - 1 - tl);
+            tw0->v[(1 << tl) - 1 + c] = make_float2(t->host[2 * idx], t->host[2 * idx + 1]);
+        }
 }
 
 // Common dispatch: the complex core has length n (power of two, >= 1), `rows` transforms.
@@ -318,6 +334,12 @@ int kofft_cuda_set_tma_staging(kofft_cuda_ctx *ctx, int enable)
     ctx->use_tma = enable != 0;
     return KOFFT_OK;
 }
+int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames)
+{
+    ctx->istft_fused = enable != 0;
+    if (run_frames > 0) ctx->istft_run_frames = run_frames;
+    return KOFFT_OK;
+}
 int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable)
 {
     ctx->large_fused = enable != 0;
@@ -498,6 +520,38 @@ int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nfram
     }
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
+    const int Lw = log2_of(win_len);
+    if (ctx->istft_fused && nframes > 0 && out_len > 0 && Lw >= 9 && Lw <= 12 && hop <= win_len &&
+        aligned16(d_frames)) {
+        // one kernel: ifft + window + ordered overlap-add + normalisation (istft_fused.cuh)
+        const Table *t = nullptr;
+        int rc = get_fft_table(ctx, win_len, &t);
+        if (rc) return rc;
+        LaunchArgs a;
+        a.exact = ctx->exact;
+        a.table = t->dev;
+        a.num_sms = ctx->num_sms;
+        a.max_ctas = ctx->max_ctas;
+        a.stream = s;
+        fill_tw0(t, Lw, &a.tw0);
+        IstftFusedArgs f;
+        f.frames = static_cast<const float2 *>(d_frames);
+        f.window = d_window;
+        f.output = d_output;
+        f.norm = d_norm;
+        f.channels = static_cast<long>(channels);
+        f.nframes = static_cast<long>(nframes);
+        f.hop = static_cast<long>(hop);
+        f.out_len = static_cast<long>(out_len);
+        f.run_frames = ctx->istft_run_frames;
+        f.zero_uncovered = zero_uncovered;
+        f.scale = 1.0f / static_cast<float>(win_len);
+        (void)cudaGetLastError();
+        cudaError_t e = launch_istft_fused(Lw, a, f);
+        if (e != cudaSuccess) return fail_cuda(e, "fused istft launch");
+        ctx->launches++;
+        return KOFFT_OK;
+    }
     // stage 1 writes windowed real frames into a bounded workspace, a few channels at a time
     const size_t per_channel = nframes * win_len * sizeof(float);
     size_t chunk = per_channel ? ctx->istft_ws_limit / per_channel : channels;

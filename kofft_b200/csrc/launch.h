@@ -81,4 +81,8 @@ struct OlaArgs {
 };
 cudaError_t launch_ola(const OlaArgs &a, cudaStream_t stream);
 
+// fused single-kernel istft (istft_fused.cuh), N = 512 .. 4096
+struct IstftFusedArgs;
+cudaError_t launch_istft_fused(int L, const LaunchArgs &a, const IstftFusedArgs &f);
+
 } // namespace kofft

@@ -95,6 +95,9 @@ class Context:
     def set_tma_staging(self, enable: bool) -> None:
         check(_lib.lib().kofft_cuda_set_tma_staging(self.handle, int(bool(enable))))
 
+    def set_istft_fusion(self, enable: bool, run_frames: int = 0) -> None:
+        check(_lib.lib().kofft_cuda_set_istft_fusion(self.handle, int(bool(enable)), int(run_frames)))
+
     def set_cluster_fusion(self, enable: bool) -> None:
         check(_lib.lib().kofft_cuda_set_cluster_fusion(self.handle, int(bool(enable))))
 

@@ -6,7 +6,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.csv 2>&1
 echo "== microbench" | tee $OUT/summary.txt
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/fp32x2 scripts/microbench/fp32x2.cu && /tmp/fp32x2 > $OUT/fp32x2.txt 2>&1
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/fp32x2 scripts/microbench/fp32x2.cu > $OUT/fp32x2.txt 2>&1 && /tmp/fp32x2 >> $OUT/fp32x2.txt 2>&1
 cat $OUT/fp32x2.txt | tee -a $OUT/summary.txt
 echo "== smoke" | tee -a $OUT/summary.txt
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke exit $?" | tee -a $OUT/summary.txt
@@ -15,7 +15,7 @@ echo "== pytest -m gpu" | tee -a $OUT/summary.txt
 timeout 1500 python -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a $OUT/summary.txt
 tail -40 $OUT/pytest_gpu.log | tee -a $OUT/summary.txt
 echo "== bench" | tee -a $OUT/summary.txt
-timeout 900 python bench.py --steps 50 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?" | tee -a $OUT/summary.txt
+KOFFT_CUDA_VERBOSE=1 timeout 900 python bench.py --steps 50 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?" | tee -a $OUT/summary.txt
 cat $OUT/bench.json | tee -a $OUT/summary.txt
 tail -5 $OUT/bench.err | tee -a $OUT/summary.txt
 echo "== bench reference arm" | tee -a $OUT/summary.txt
@@ -31,5 +31,7 @@ ls -la $OUT | tee -a $OUT/summary.txt
 echo "== ncu stft / rfft" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_cta_kernel -s 3 -c 1 -o $OUT/prof_stft \
     python scripts/one_kernel.py stft > $OUT/ncu_stft.log 2>&1; echo "ncu stft exit $?" | tee -a $OUT/summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:pass_kernel -s 4 -c 2 -o $OUT/prof_rfft \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:large_fused -s 2 -c 1 -o $OUT/prof_rfft \
     python scripts/one_kernel.py rfft > $OUT/ncu_rfft.log 2>&1; echo "ncu rfft exit $?" | tee -a $OUT/summary.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:istft_fused -s 2 -c 1 -o $OUT/prof_istft \
+    python scripts/one_kernel.py istft > $OUT/ncu_istft.log 2>&1; echo "ncu istft exit $?" | tee -a $OUT/summary.txt

@@ -25,6 +25,14 @@ elif which == "stft":
     frames = torch.empty((ch, nframes, win), dtype=torch.complex64, device="cuda")
     for _ in range(6):
         S.stft_batch(fft, sig, w, hop, nframes, out=frames)
+elif which == "istft":
+    ch, length, hop, win = 16, 28_800_000, 512, 2048
+    nframes = -(-length // hop)
+    w = torch.from_numpy(W.hann(win)).cuda()
+    frames = torch.view_as_complex(torch.rand((ch, nframes, win, 2), generator=g, device="cuda") * 2 - 1).contiguous()
+    out = torch.zeros((ch, length), device="cuda")
+    for _ in range(4):
+        S.istft_batch(fft, frames, w, hop, out)
 elif which == "rfft":
     x = (torch.rand((4096, 65536), generator=g, device="cuda") * 2 - 1).contiguous()
     for _ in range(6):

@@ -67,7 +67,7 @@ def _stale_k() -> bool:
     t = os.path.getmtime(_SOK)
     deps = [_SRCK, os.path.join(_HERE, "cuda_emu.h")] + [
         os.path.join(_CSRC, f) for f in ("hostdev.h", "async_copy.cuh", "fft_engine.cuh", "fft_kernels.cuh",
-                                         "fft_large.cuh", "small_kernels.cuh")]
+                                         "fft_large.cuh", "istft_fused.cuh", "small_kernels.cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -102,8 +102,29 @@ class EmuKernels:
         assert rc == 0, rc
 
 
+def _bind_istft(lib):
+    f = lib.kofft_emuk_istft_fused
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_long,
+                  C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_int]
+
+
+def _istft_fused(self, exact, L, frames, window, output, norm, hop, run_frames, zero_uncovered, table, grid=3):
+    """IstftFused::run: frames [ch, nframes, N] -> accumulates into output [ch, out_len] in place."""
+    ch, nframes, _ = frames.shape
+    rc = self.lib.kofft_emuk_istft_fused(int(exact), L, frames.ctypes.data, window.ctypes.data, output.ctypes.data,
+                                         norm.ctypes.data if norm is not None else None, ch, nframes, hop,
+                                         output.shape[1], run_frames, int(zero_uncovered), table.ctypes.data, grid)
+    assert rc == 0, rc
+
+
+EmuKernels.istft_fused = _istft_fused
+
+
 def load_kernels() -> EmuKernels:
     if _stale_k():
         subprocess.run(["g++", "-O1", "-DKOFFT_EMU", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-shared",
                         "-fPIC", "-fvisibility=hidden", "-I", _HERE, "-o", _SOK, _SRCK], check=True)
-    return EmuKernels(C.CDLL(_SOK))
+    lib = C.CDLL(_SOK)
+    _bind_istft(lib)
+    return EmuKernels(lib)

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../kofft_b200/csrc/fft_large.cuh"
+#include "../../kofft_b200/csrc/istft_fused.cuh"
 
 using namespace kofft;
 
@@ -186,4 +187,41 @@ API int kofft_emuk_large(int kind, int exact, int L, long rows, const void *in, 
         return exact ? run_large_kind<8, true>(kind, q, table, rows, grid_col, grid_row)
                      : run_large_kind<8, false>(kind, q, table, rows, grid_col, grid_row);
     return -1;
+}
+
+// the real fused istft kernel body (istft_fused.cuh)
+template <int L, bool EXACT>
+static int run_istft(const IstftFusedArgs &a, const float *table, int grid)
+{
+    using K = IstftFused<L, EXACT>;
+    Tw0 tw0 = make_tw0(L, Plan<L>::R0, table);
+    std::vector<float2> smem((K::SMEM_BYTES + 256) / 8);
+    float2 *sm = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
+    const float2 *tab = reinterpret_cast<const float2 *>(table);
+    cuda_emu::launch(grid, Plan<L>::CTA, [&] { K::run(a, tw0, tab, sm); });
+    return 0;
+}
+
+API int kofft_emuk_istft_fused(int exact, int L, const void *frames, const float *window, float *output, float *norm,
+                               long channels, long nframes, long hop, long out_len, int run_frames,
+                               int zero_uncovered, const float *table, int grid)
+{
+    IstftFusedArgs a;
+    a.frames = (const float2 *)frames;
+    a.window = window;
+    a.output = output;
+    a.norm = norm;
+    a.channels = channels;
+    a.nframes = nframes;
+    a.hop = hop;
+    a.out_len = out_len;
+    a.run_frames = run_frames;
+    a.zero_uncovered = zero_uncovered;
+    a.scale = 1.0f / (float)(1L << L);
+    switch (L) {
+#define CASE_L(L) case L: return exact ? run_istft<L, true>(a, table, grid) : run_istft<L, false>(a, table, grid);
+    CASE_L(9) CASE_L(10) CASE_L(11) CASE_L(12)
+#undef CASE_L
+    default: return -1;
+    }
 }

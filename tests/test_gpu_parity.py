@@ -415,6 +415,41 @@ def test_stft_istft_batch(cuda_fft, cuda_fft_fast, oracle, win_len, hop, length,
     assert rel_l2(fast, want) <= TOL
 
 
+@pytest.mark.parametrize("win_len,hop,length,run_frames", [(2048, 512, 60000, 8), (512, 128, 5000, 64), (4096, 1024, 50000, 3),
+                                                         (1024, 1024, 9000, 5), (512, 200, 4000, 4)])
+def test_istft_fused_and_two_kernel_paths_agree(cuda_fft, oracle, win_len, hop, length, run_frames):
+    """istft runs as ONE fused kernel for windows 512..4096; the two-kernel path is the fallback.
+    Both bit-identical to the oracle, incl. accumulate-into-output, norm, uncovered samples."""
+    from kofft_b200 import stft as S
+    from kofft_b200 import window as W
+
+    rng = np.random.default_rng(win_len + hop)
+    ch = 3
+    sig = rng.uniform(-1, 1, (ch, length)).astype(np.float32)
+    w = W.hann(win_len)
+    nframes = -(-length // hop) + 1
+    frames = oracle.stft_batch(sig, w, hop, nframes, nthreads=4)
+    out_len = length + 700
+    base = rng.uniform(-1, 1, (ch, out_len)).astype(np.float32)
+    want = np.stack([oracle.istft(frames[c], w, hop, base[c]) for c in range(ch)])
+    want0 = np.stack([oracle.istft_parallel(frames[c], w, hop, base[c]) for c in range(ch)])
+    try:
+        for fused in (True, False):
+            cuda_fft.ctx.set_istft_fusion(fused, run_frames)
+            got, norm = base.copy(), np.zeros_like(base)
+            S.istft_batch(cuda_fft, frames, w, hop, got, norm)
+            assert np.array_equal(got, want), f"fused={fused}"
+            got0 = base.copy()
+            S.istft_batch(cuda_fft, frames, w, hop, got0, None, zero_uncovered=True)
+            assert np.array_equal(got0, want0), f"fused={fused}"
+            if fused:
+                norm_fused = norm
+            else:
+                assert np.array_equal(norm, norm_fused)
+    finally:
+        cuda_fft.ctx.set_istft_fusion(True, 64)
+
+
 def test_stft_device_tensors(cuda_fft, oracle):
     import torch
     from kofft_b200 import stft as S

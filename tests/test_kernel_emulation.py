@@ -99,3 +99,68 @@ def test_large_two_pass_rfft_irfft(emuk, oracle, L):
     y[...] = 0
     emuk.large("rfft", False, L, rows, tab, inp=x, out=y, aux=rtw)
     assert rel_l2(y, ref) <= TOL
+
+
+@pytest.mark.parametrize("L,hop,length,extra_out,run_frames,grid", [
+    (9, 128, 3000, 7, 4, 3),       # several runs per channel, halo frames, tail beyond the last frame
+    (11, 512, 9000, 0, 3, 2),      # BASELINE window/hop, out_len == signal length (frames clipped)
+    (10, 1024, 5000, 3000, 2, 2),  # hop == N (no overlap), output longer than the covered range
+    (9, 200, 2600, 100, 64, 1),    # hop does not divide N; one run per channel
+    (12, 1024, 9000, 0, 2, 2),     # one frame per CTA group (TPC = 1)
+])
+def test_fused_istft_kernel_body(emuk, oracle, L, hop, length, extra_out, run_frames, grid):
+    """IstftFused::run (ifft + window + ordered overlap-add + normalisation in one kernel) is
+    bit-identical to the reference's sequential istft / inverse_parallel, including the
+    accumulate-into-output semantics and samples no frame reaches."""
+    N = 1 << L
+    rng = np.random.default_rng(L * hop)
+    ch = 2
+    sig = rng.uniform(-1, 1, (ch, length)).astype(np.float32)
+    w = oracle.hann(N)
+    nframes = -(-length // hop) + 1
+    frames = oracle.stft_batch(sig, w, hop, nframes)
+    out_len = length + extra_out
+    base = rng.uniform(-1, 1, (ch, out_len)).astype(np.float32)
+    tab = oracle.twiddles(N)
+    for zero_uncovered in (0, 1):
+        got = base.copy()
+        norm = np.full_like(got, -1.0)
+        emuk.istft_fused(True, L, frames, w, got, norm, hop, run_frames, zero_uncovered, tab, grid=grid)
+        if zero_uncovered:
+            want = np.stack([oracle.istft_parallel(frames[c], w, hop, base[c]) for c in range(ch)])
+        else:
+            want = np.stack([oracle.istft(frames[c], w, hop, base[c]) for c in range(ch)])
+        assert np.array_equal(got, want), (zero_uncovered, np.flatnonzero(got != want)[:10])
+        # the reference's `scratch`: summed window power per sample, in frame order
+        nrm = np.zeros(out_len, np.float32)
+        for f in range(nframes):
+            for i in range(N):
+                if f * hop + i < out_len:
+                    nrm[f * hop + i] = np.float32(nrm[f * hop + i] + np.float32(w[i] * w[i]))
+        assert np.array_equal(norm[0], nrm) and np.array_equal(norm[1], nrm)
+    got = base.copy()
+    emuk.istft_fused(False, L, frames, w, got, None, hop, run_frames, 0, tab, grid=grid)
+    want = np.stack([oracle.istft(frames[c], w, hop, base[c]) for c in range(ch)])
+    assert rel_l2(got, want) <= TOL
+
+
+@pytest.mark.parametrize("L", [15, 16])
+def test_large_fused_cluster_kernel_body(emuk, oracle, L):
+    """LargeFused::run: thread-block clusters, cluster barrier, double-buffered scratch."""
+    n = 1 << L
+    rng = np.random.default_rng(7 + L)
+    rows = 5
+    x = uniform_c64(rng, (rows, n))
+    tab = oracle.twiddles(n)
+    y = np.zeros_like(x)
+    emuk.large("c2c_fwd", True, L, rows, tab, inp=x, out=y, grid_col=2, fused=True)
+    assert np.array_equal(y, oracle.fft_batch(x))
+    xr = rng.uniform(-1, 1, (rows, 2 * n)).astype(np.float32)
+    rtw = oracle.rfft_twiddles(n)
+    yr = np.zeros((rows, n + 1), np.complex64)
+    emuk.large("rfft", True, L, rows, tab, inp=xr, out=yr, aux=rtw, grid_col=2, fused=True)
+    assert np.array_equal(yr, oracle.rfft_batch(xr))
+    zr = np.zeros((rows, 2 * n), np.float32)
+    emuk.large("irfft", True, L, rows, tab, inp=yr, out=zr, aux=rtw, scale=float(np.float32(1) / np.float32(n)),
+               grid_col=3, fused=True)
+    assert np.array_equal(zr, oracle.irfft_batch(yr, 2 * n))
