@@ -5,9 +5,6 @@ TAG=${1:-r01}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.csv 2>&1
-echo "== microbench" | tee $OUT/summary.txt
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/fp32x2 scripts/microbench/fp32x2.cu > $OUT/fp32x2.txt 2>&1 && /tmp/fp32x2 >> $OUT/fp32x2.txt 2>&1
-cat $OUT/fp32x2.txt | tee -a $OUT/summary.txt
 echo "== smoke" | tee -a $OUT/summary.txt
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke exit $?" | tee -a $OUT/summary.txt
 tail -3 $OUT/smoke.log | tee -a $OUT/summary.txt
