@@ -54,23 +54,27 @@ struct IoC2C {
     KHD void init(int) {}
     KHD float2 load(long row, int i) const { return pre_conj<INV>(KOFFT_LDG(in + row * n + i)); }
     KHD void store(long row, int i, float2 v) const { out[row * n + i] = post_conj_scale<INV>(v, scale); }
-    // staging: the TPC rows of group g are one contiguous byte range
     static constexpr bool kStageable = true;
     static constexpr bool kLoadAux = false;
     KHD float load_aux(int) const { return 0.0f; }
-    KHD unsigned stage_bytes(long g, int tpc, long rows) const
+    // staging: the TPC rows of a group are one contiguous byte range.  The group a CTA works on
+    // is part of the IO state (group_init / group_next) so the row loop needs no divisions.
+    long cur_g = 0, g_step = 0;
+    KHD void group_init(long g0, long step, int) { cur_g = g0; g_step = step; }
+    KHD void group_next(int) { cur_g += g_step; }
+    KHD unsigned stage_bytes(int tpc, long rows) const
     {
-        long nr = rows - g * tpc;
+        long nr = rows - cur_g * tpc;
         return (unsigned)((nr < tpc ? nr : tpc) * n * 8);
     }
-    KHD const void *stage_src(long g, int tpc) const { return in + g * tpc * n; }
-    KHD void group_init(long, int) {}
-    KHD void group_next(long, int) {}
+    KHD const void *stage_src(int tpc) const { return in + cur_g * tpc * n; }
     KHD int row_begin(int) const { return 0; }
+    template <bool FULL>
     KHD float2 load_staged(const unsigned char *stage, int, int slot, int i, float) const
     {
         return pre_conj<INV>(reinterpret_cast<const float2 *>(stage)[slot * n + i]);
     }
+    KHD bool row_full(int) const { return true; }
 };
 
 // element e of row r lives at  re[r*row_stride + e*elem_stride]  (strides in floats);
@@ -128,42 +132,50 @@ struct IoStft {
     static constexpr bool kStageable = true;
     static constexpr bool kLoadAux = true;
     KHD float load_aux(int i) const { return KOFFT_LDG(window + i); } // window value, kept in a register
-    KHD unsigned stage_bytes(long g, int tpc, long) const
+    // Group state: channel and first frame of the CTA's current group, advanced without
+    // divisions as the persistent CTA strides over the groups (two divisions per CTA lifetime).
+    long cur_c = 0, cur_f0 = 0, adv_c = 0, adv_f = 0;
+    KHD void group_init(long g0, long step, int tpc)
     {
-        long r0 = g * tpc;
-        long c = r0 / nframes, f0 = r0 - c * nframes;
-        long avail = len - f0 * hop;
+        long r0 = g0 * tpc;
+        cur_c = r0 / nframes;
+        cur_f0 = r0 - cur_c * nframes;
+        long a = step * tpc;
+        adv_c = a / nframes;
+        adv_f = a - adv_c * nframes;
+    }
+    KHD void group_next(int)
+    {
+        cur_c += adv_c;
+        cur_f0 += adv_f;
+        if (cur_f0 >= nframes) {
+            cur_f0 -= nframes;
+            cur_c++;
+        }
+    }
+    KHD unsigned stage_bytes(int tpc, long) const
+    {
+        long avail = len - cur_f0 * hop;
         long want = (long)(tpc - 1) * hop + n;
         if (avail <= 0) return 0u;
         return (unsigned)((avail < want ? avail : want) * 4);
     }
-    KHD const void *stage_src(long g, int tpc) const
-    {
-        long r0 = g * tpc;
-        long c = r0 / nframes, f0 = r0 - c * nframes;
-        return signal + c * len + f0 * hop;
-    }
-    // frame index (within its channel) of the current group's first row, advanced without
-    // divisions as the persistent CTA strides over the groups
-    long cur_f0 = 0;
-    KHD void group_init(long g0, int tpc) { cur_f0 = (g0 * tpc) % nframes; }
-    KHD void group_next(long step, int tpc)
-    {
-        cur_f0 += step * tpc;
-        while (cur_f0 >= nframes) cur_f0 -= nframes;
-    }
+    KHD const void *stage_src(int) const { return signal + cur_c * len + cur_f0 * hop; }
     // samples of this slot's frame that lie inside the signal, clamped to [0, n]
     KHD int row_begin(int slot) const
     {
         long rem = len - (cur_f0 + slot) * hop;
         return rem <= 0 ? 0 : (rem >= n ? (int)n : (int)rem);
     }
+    // FULL: the whole frame lies inside the signal (rem == n), no per-element bound check
+    template <bool FULL>
     KHD float2 load_staged(const unsigned char *stage, int rem, int slot, int i, float w) const
     {
         float x = 0.0f;
-        if (i < rem) x = mul_rn(reinterpret_cast<const float *>(stage)[(long)slot * hop + i], w);
+        if (FULL || i < rem) x = mul_rn(reinterpret_cast<const float *>(stage)[(long)slot * hop + i], w);
         return make_float2(x, 0.0f);
     }
+    KHD bool row_full(int rem) const { return rem >= (int)n; }
 };
 
 // istft stage 1: time[row][i] = (ifft(frame).re) * window[i]; the overlap-add is a second,
@@ -192,19 +204,24 @@ struct IoIstft {
     static constexpr bool kStageable = true;
     static constexpr bool kLoadAux = false;
     KHD float load_aux(int) const { return 0.0f; }
-    KHD unsigned stage_bytes(long g, int tpc, long rows) const
+    // staging: the TPC rows of a group are one contiguous byte range.  The group a CTA works on
+    // is part of the IO state (group_init / group_next) so the row loop needs no divisions.
+    long cur_g = 0, g_step = 0;
+    KHD void group_init(long g0, long step, int) { cur_g = g0; g_step = step; }
+    KHD void group_next(int) { cur_g += g_step; }
+    KHD unsigned stage_bytes(int tpc, long rows) const
     {
-        long nr = rows - g * tpc;
+        long nr = rows - cur_g * tpc;
         return (unsigned)((nr < tpc ? nr : tpc) * n * 8);
     }
-    KHD const void *stage_src(long g, int tpc) const { return frames + g * tpc * n; }
-    KHD void group_init(long, int) {}
-    KHD void group_next(long, int) {}
+    KHD const void *stage_src(int tpc) const { return frames + cur_g * tpc * n; }
     KHD int row_begin(int) const { return 0; }
+    template <bool FULL>
     KHD float2 load_staged(const unsigned char *stage, int, int slot, int i, float) const
     {
         return pre_conj<true>(reinterpret_cast<const float2 *>(stage)[slot * n + i]);
     }
+    KHD bool row_full(int) const { return true; }
 };
 
 // rfft: input row = 2m reals viewed as m complex (pack is a reinterpretation); after the
@@ -223,19 +240,24 @@ struct IoRfft {
     static constexpr bool kStageable = true;
     static constexpr bool kLoadAux = false;
     KHD float load_aux(int) const { return 0.0f; }
-    KHD unsigned stage_bytes(long g, int tpc, long rows) const
+    // staging: the TPC rows of a group are one contiguous byte range.  The group a CTA works on
+    // is part of the IO state (group_init / group_next) so the row loop needs no divisions.
+    long cur_g = 0, g_step = 0;
+    KHD void group_init(long g0, long step, int) { cur_g = g0; g_step = step; }
+    KHD void group_next(int) { cur_g += g_step; }
+    KHD unsigned stage_bytes(int tpc, long rows) const
     {
-        long nr = rows - g * tpc;
+        long nr = rows - cur_g * tpc;
         return (unsigned)((nr < tpc ? nr : tpc) * m * 8);
     }
-    KHD const void *stage_src(long g, int tpc) const { return in + g * tpc * m; }
-    KHD void group_init(long, int) {}
-    KHD void group_next(long, int) {}
+    KHD const void *stage_src(int tpc) const { return in + cur_g * tpc * m; }
     KHD int row_begin(int) const { return 0; }
+    template <bool FULL>
     KHD float2 load_staged(const unsigned char *stage, int, int slot, int i, float) const
     {
         return reinterpret_cast<const float2 *>(stage)[slot * m + i];
     }
+    KHD bool row_full(int) const { return true; }
     // Hermitian twist of bin k (src/rfft.rs:450-463): a = Y[k], ym = Y[m-k] (for k = 0: a = Y[0])
     KHD void twist_store(long row, long k, float2 a, float2 ym) const
     {
@@ -382,7 +404,6 @@ struct CtaFft {
                 fence_mbar_init();
             }
             __syncthreads();
-            if (tid == 0 && (long)blockIdx.x < groups) stage_issue(io, stage, &mbar, blockIdx.x, rows);
         }
 
         io.init(t);
@@ -408,23 +429,35 @@ struct CtaFft {
                 for (int w = 0; w < PLast::R; w++) auxo[u * PLast::R + w] = io.store_aux_value(PLast::dst_index(t, u, w));
         }
 
-        if constexpr (STAGED) io.group_init(blockIdx.x, P::TPC);
+        if constexpr (STAGED) {
+            io.group_init(blockIdx.x, gridDim.x, P::TPC);
+            if (tid == 0 && (long)blockIdx.x < groups) stage_issue(io, stage, &mbar, rows);
+        }
         for (long g = blockIdx.x; g < groups; g += gridDim.x) {
             const long row = g * P::TPC + slot;
             const bool active = row < rows;
             float2 x[EPT];
             if constexpr (STAGED) {
-                if (io.stage_bytes(g, P::TPC, rows) != 0) {
+                if (io.stage_bytes(P::TPC, rows) != 0) {
                     mbar_wait(&mbar, phase);
                     phase ^= 1;
                 }
                 const int rctx = io.row_begin(slot);
+                if (io.row_full(rctx)) { // warp-uniform: a slot's threads share the frame
 #pragma unroll
-                for (int u = 0; u < P0::U; u++)
+                    for (int u = 0; u < P0::U; u++)
 #pragma unroll
-                    for (int q = 0; q < P0::R; q++)
-                        x[u * P0::R + q] = io.load_staged(stage, rctx, slot, P0::src_index(t, u, q),
-                                                          IO::kLoadAux ? aux[u * P0::R + q] : 0.0f);
+                        for (int q = 0; q < P0::R; q++)
+                            x[u * P0::R + q] = io.template load_staged<true>(stage, rctx, slot, P0::src_index(t, u, q),
+                                                                             IO::kLoadAux ? aux[u * P0::R + q] : 0.0f);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < P0::U; u++)
+#pragma unroll
+                        for (int q = 0; q < P0::R; q++)
+                            x[u * P0::R + q] = io.template load_staged<false>(stage, rctx, slot, P0::src_index(t, u, q),
+                                                                              IO::kLoadAux ? aux[u * P0::R + q] : 0.0f);
+                }
             } else {
                 if (active) {
                     load_global<P0>(io, row, t, x);
@@ -440,7 +473,8 @@ struct CtaFft {
             store_smem<P0>(b, t, x);
             __syncthreads();
             if constexpr (STAGED) { // every thread has consumed the stage: refill it for this CTA's next group
-                if (tid == 0 && g + gridDim.x < groups) stage_issue(io, stage, &mbar, g + gridDim.x, rows);
+                io.group_next(P::TPC);
+                if (tid == 0 && g + gridDim.x < groups) stage_issue(io, stage, &mbar, rows);
             }
             load_smem<P1>(b, t, x);
             if (P::NBUF == 1) __syncthreads();
@@ -481,17 +515,16 @@ struct CtaFft {
             } else {
                 if (active) store_global<PL>(io, row, t, x);
             }
-            if constexpr (STAGED) io.group_next(gridDim.x, P::TPC);
         }
     }
 
-    // one thread: arm the barrier with the byte count and start the bulk copy of group g
-    static KD void stage_issue(const IO &io, unsigned char *stage, unsigned long long *bar, long g, long rows)
+    // one thread: arm the barrier with the byte count and start the bulk copy of io's current group
+    static KD void stage_issue(const IO &io, unsigned char *stage, unsigned long long *bar, long rows)
     {
-        const unsigned bytes = io.stage_bytes(g, P::TPC, rows);
+        const unsigned bytes = io.stage_bytes(P::TPC, rows);
         if (bytes == 0) return;
         mbar_expect_tx(bar, bytes);
-        bulk_copy_g2s(stage, io.stage_src(g, P::TPC), bytes, bar);
+        bulk_copy_g2s(stage, io.stage_src(P::TPC), bytes, bar);
     }
 #endif
 };

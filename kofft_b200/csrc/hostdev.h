@@ -39,9 +39,9 @@ KHD float fma_rn(float a, float b, float c) { return fmaf(a, b, c); }
 #endif
 
 // ---- packed f32x2 ops (sm_100a FADD2 / FMUL2 / FFMA2) -----------------------------------------
-// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with explicit .rn, so packed
-// multiplies are only used where contraction is allowed (the FAST path); packed adds of
-// non-product operands are safe everywhere.
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with explicit .rn, so in EXACT
+// code a packed product is never fed to a packed add (scalar adds of FMUL2 halves are left
+// alone); packed adds of non-product operands are safe everywhere.
 #if defined(__CUDA_ARCH__)
 KD float2 add2(float2 a, float2 b)
 {
@@ -88,26 +88,33 @@ KHD float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x
 
 // ---- the radix-2 butterfly of kofft's Stockham stage (src/fft.rs:845-862 / 881-893) ---------
 //   t = v * w ;  u' = u + t ;  v' = u - t
+// Measured on B200 (scripts/microbench/fp32x2.cu, profiles/r01e_fp32x2.txt): a packed f32x2
+// instruction occupies the FMA pipe for two cycles, i.e. packing saves issue slots, not pipe
+// cycles.  What counts is lane-operations per butterfly:
 // EXACT: every product and sum individually rounded, in the reference's operand order
-//        -> bit-identical to the reference / oracle.
-// FAST : FMUL2 + 2 FFMA + 2 FADD2 (one of the two products of each component stays unrounded).
+//        -> bit-identical to the reference / oracle.  10 lane-ops: 2 FMUL2 (v.x*(w.x,w.y),
+//        v.y*(w.y,w.x)) + 2 FADD + 2 FADD2 = 6 issue slots.  The products are combined with
+//        SCALAR adds: ptxas contracts mul.f32x2 -> add.f32x2 into FFMA2 even with .rn, but it
+//        leaves FMUL2 -> FADD alone (checked in SASS, and by the bit-exact GPU tests).
+// FAST : 6 lane-ops: a = u + v*w as FFMA2 + 2 FFMA, then b = 2u - a as one FFMA2 (immediate 2,
+//        negated addend) = 4 issue slots.  ~2e-7 rel-L2 from EXACT.
 template <bool EXACT>
 KHD void butterfly(float2 &u, float2 &v, const float2 w)
 {
-    float2 t;
     if (EXACT) {
-        t.x = sub_rn(mul_rn(v.x, w.x), mul_rn(v.y, w.y));
-        t.y = add_rn(mul_rn(v.x, w.y), mul_rn(v.y, w.x));
+        float2 p = mul2(make_float2(v.x, v.x), w);
+        float2 q = mul2(make_float2(v.y, v.y), make_float2(w.y, w.x));
+        float2 t = make_float2(sub_rn(p.x, q.x), add_rn(p.y, q.y));
+        float2 a = add2(u, t);
+        v = sub2(u, t);
+        u = a;
     } else {
-        // p = v.y * (w.y, w.x) as one FMUL2 (the half swap is a free operand modifier), then one
-        // scalar FFMA per component: 5 issue slots and 8 lane-ops instead of 8 and 10.
-        float2 p = mul2(make_float2(v.y, v.y), make_float2(w.y, w.x));
-        t.x = fma_rn(v.x, w.x, -p.x);
-        t.y = fma_rn(v.x, w.y, p.y);
+        float2 a = fma2(make_float2(v.x, v.x), w, u);
+        a.x = fma_rn(-v.y, w.y, a.x);
+        a.y = fma_rn(v.y, w.x, a.y);
+        v = fma2(u, make_float2(2.0f, 2.0f), make_float2(-a.x, -a.y));
+        u = a;
     }
-    float2 a = add2(u, t);
-    v = sub2(u, t);
-    u = a;
 }
 
 // twiddle == (1, 0) exactly (table entry 0): v*1 is the identity for finite v

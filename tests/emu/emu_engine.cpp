@@ -39,6 +39,7 @@ void emu_cta(const IO &io_in, const Tw0 &tw0, const float2 *table, long rows, bo
     std::vector<float2> X(static_cast<size_t>(NT) * EPT);
     std::vector<float2> TW1(static_cast<size_t>(NT) * 16), TW2(static_cast<size_t>(NT) * 16), TW3(static_cast<size_t>(NT) * 16);
     IO io = io_in;
+    IO io_prev[3] = {io_in, io_in, io_in};
     auto slot_of = [](int tid) { return tid / P::T; };
     auto t_of = [](int tid) { return tid % P::T; };
     auto buf_of = [&](int tid, int par) { return smem.data() + slot_of(tid) * P::PADN + (par ? P::TPC * P::PADN : 0); };
@@ -55,11 +56,14 @@ void emu_cta(const IO &io_in, const Tw0 &tw0, const float2 *table, long rows, bo
         std::vector<unsigned char> stage(P::STAGE_BYTES, 0xCD);
         if constexpr (IO::kStageable) {
             if (staged) {
-                io.group_init(g, P::TPC);
-                unsigned nb = io.stage_bytes(g, P::TPC, rows);
-                if (nb > (unsigned)P::STAGE_BYTES || (nb % 16) != 0 || ((size_t)io.stage_src(g, P::TPC) % 16) != 0)
+                // grid of 3 CTAs: exercises group_next (adv_c / adv_f) as well as group_init
+                if (g < 3) io.group_init(g, 3, P::TPC);
+                else { io = io_prev[g % 3]; io.group_next(P::TPC); }
+                io_prev[g % 3] = io;
+                unsigned nb = io.stage_bytes(P::TPC, rows);
+                if (nb > (unsigned)P::STAGE_BYTES || (nb % 16) != 0 || ((size_t)io.stage_src(P::TPC) % 16) != 0)
                     throw 1; // what the TMA bulk copy would reject
-                if (nb) memcpy(stage.data(), io.stage_src(g, P::TPC), nb);
+                if (nb) memcpy(stage.data(), io.stage_src(P::TPC), nb);
             }
         }
         for (int tid = 0; tid < NT; tid++) {
@@ -72,8 +76,10 @@ void emu_cta(const IO &io_in, const Tw0 &tw0, const float2 *table, long rows, bo
                     for (int u = 0; u < P0::U; u++)
                         for (int q = 0; q < P0::R; q++) {
                             int idx = P0::src_index(t, u, q);
-                            x[u * P0::R + q] = io.load_staged(stage.data(), rctx, slot_of(tid), idx,
-                                                              IO::kLoadAux ? io.load_aux(idx) : 0.0f);
+                            const float w = IO::kLoadAux ? io.load_aux(idx) : 0.0f;
+                            x[u * P0::R + q] = io.row_full(rctx)
+                                                   ? io.template load_staged<true>(stage.data(), rctx, slot_of(tid), idx, w)
+                                                   : io.template load_staged<false>(stage.data(), rctx, slot_of(tid), idx, w);
                         }
                     done = true;
                 }
