@@ -71,6 +71,12 @@ int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames)
 /* N > 16384: enable (default) / disable the single persistent thread-block-cluster kernel;
  * when disabled (or unavailable) two kernels per L2-sized batch chunk are used instead */
 int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable);
+/* Host-pointer batch entry points (fft_batch_host, rfft_batch_host, irfft_batch_host): batches
+ * larger than chunk_bytes are cut into chunks of about chunk_bytes that flow through three
+ * streams (H2D copy engine, kernels, D2H copy engine), so both PCIe directions and the SMs work
+ * at the same time.  Default 32 MiB; 0 = one copy in, one launch, one copy out.  Pin the host
+ * buffers (cudaHostRegister) for full PCIe rate; pageable buffers work but copy synchronously. */
+int kofft_cuda_set_host_pipeline(kofft_cuda_ctx *ctx, size_t chunk_bytes);
 /* 0 = let the library size the grid (occupancy x SM count); otherwise cap the CTA count */
 int kofft_cuda_set_max_ctas(kofft_cuda_ctx *ctx, int max_ctas);
 

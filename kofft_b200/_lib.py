@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libkofft_cuda.so")
+# KOFFT_CUDA_LIB: load another build of the same ABI (tuning variants, scripts/build_variants.sh)
+LIB_PATH = os.environ.get("KOFFT_CUDA_LIB") or os.path.join(_HERE, "lib", "libkofft_cuda.so")
 
 _sz, _vp, _i, _f = C.c_size_t, C.c_void_p, C.c_int, C.c_float
 
@@ -28,6 +29,7 @@ SIGNATURES = {
     "kofft_cuda_launch_count": (C.c_ulonglong, [_vp]),
     "kofft_cuda_set_max_ctas": (_i, [_vp, _i]),
     "kofft_cuda_set_tma_staging": (_i, [_vp, _i]),
+    "kofft_cuda_set_host_pipeline": (_i, [_vp, _sz]),
     "kofft_cuda_set_cluster_fusion": (_i, [_vp, _i]),
     "kofft_cuda_set_istft_fusion": (_i, [_vp, _i, _i]),
     "kofft_cuda_twiddles_host_f32": (_i, [_sz, _vp]),

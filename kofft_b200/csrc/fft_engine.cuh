@@ -36,15 +36,18 @@ constexpr int bitrev(int w, int bits)
 
 constexpr int EPT = 16; // elements per thread
 
-template <int L_>
+// MINCTA_: smallest CTA.  Transforms needing fewer threads share a CTA (TPC > 1).  256 keeps two
+// 8-warp CTAs per SM; 128 gives four 4-warp CTAs per SM (finer-grained barriers).
+template <int L_, int MINCTA_ = 256>
 struct Plan {
     static constexpr int L = L_;
+    static constexpr int MINCTA = MINCTA_;
     static constexpr int N = 1 << L;
     static_assert(L >= 5 && L <= 14, "single-CTA engine covers N = 32 .. 16384");
     static constexpr int NP = L <= 8 ? 2 : (L <= 12 ? 3 : 4);
     static constexpr int R0 = L - 4 * (NP - 1);      // log2 radix of pass 0 (1..4)
     static constexpr int T = N / EPT;                // threads per transform
-    static constexpr int CTA = T < 256 ? 256 : T;    // threads per CTA
+    static constexpr int CTA = T < MINCTA ? MINCTA : T; // threads per CTA
     static constexpr int TPC = CTA / T;              // transforms per CTA
     static constexpr int PADN = N + (N >> 4);        // padded float2 per exchange buffer
     // two exchange buffers (one __syncthreads per exchange) when they fit, else one
@@ -90,7 +93,9 @@ KHD int tw_index(int p, int t, int k, int c_low, const TwMap &m = TwMap())
 // ------------------------------------------------------------------------------------------
 // UNIT0: the sub-transform starts at stage 0 of the whole transform, so the group-0 twiddle of
 // pass 0 is table entry 0 == (1, 0) and its other pass-0 twiddles are thread-independent (Tw0).
-template <class P, int p, bool EXACT, bool UNIT0 = true>
+// REAL0 (pass 0 only, with UNIT0): the inputs are real (imag == +0): butterflies on elements that
+// have met only unit twiddles so far take the real-input shortcuts of hostdev.h.
+template <class P, int p, bool EXACT, bool UNIT0 = true, bool REAL0 = false>
 struct Pass {
     static constexpr int r = P::r(p);
     static constexpr int R = 1 << r;
@@ -169,10 +174,18 @@ struct Pass {
                     float2 &a = x[u * R + w0];
                     float2 &b = x[u * R + (w0 | bit)];
                     if (p == 0 && UNIT0) {
-                        if (c_low == 0)
-                            butterfly_unit(a, b); // T[0] == (1, 0) exactly
-                        else
+                        // still real: every earlier layer used the unit twiddle (its c_low was 0)
+                        const bool real_in = REAL0 && (tl == 0 || (w0 >> (r - tl + 1)) == 0);
+                        if (c_low == 0) {
+                            if (real_in)
+                                butterfly_unit_real(a, b);
+                            else
+                                butterfly_unit(a, b); // T[0] == (1, 0) exactly
+                        } else if (real_in) {
+                            butterfly_real<EXACT>(a, b, tw[(1 << tl) - 1 + c_low]);
+                        } else {
                             butterfly<EXACT>(a, b, tw[(1 << tl) - 1 + c_low]);
+                        }
                     } else {
                         butterfly<EXACT>(a, b, tw[u * (R - 1) + (1 << tl) - 1 + c_low]);
                     }

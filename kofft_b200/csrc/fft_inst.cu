@@ -13,7 +13,7 @@ namespace {
 template <int L, bool EXACT, class IO, bool STAGED>
 cudaError_t launch_variant(const IO &io, const LaunchArgs &a)
 {
-    using P = Plan<L>;
+    using P = Plan<L, IoTraits<IO>::kMinCta>;
     constexpr int smem = STAGED ? P::SMEM_BYTES_STAGED : P::SMEM_BYTES;
     auto kern = fft_cta_kernel<L, EXACT, IO, STAGED>;
     static int occ = 0; // per instantiation
@@ -37,7 +37,7 @@ cudaError_t launch_variant(const IO &io, const LaunchArgs &a)
 template <int L, bool EXACT, class IO>
 cudaError_t launch_one(const IO &io, const LaunchArgs &a)
 {
-    if constexpr (IO::kStageable && Plan<L>::CAN_STAGE) {
+    if constexpr (IO::kStageable && Plan<L, IoTraits<IO>::kMinCta>::CAN_STAGE) {
         if (a.staged) return launch_variant<L, EXACT, IO, true>(io, a);
     }
     return launch_variant<L, EXACT, IO, false>(io, a);

@@ -316,13 +316,33 @@ struct IoIrfft {
     KHD void store(long row, int i, float2 v) const { out[row * m + i] = post_conj_scale<true>(v, scale); }
 };
 
+// Compile-time properties of an IO policy that shape the kernel around it.
+//   kRealInput: load() returns imag == +0 -> pass 0 takes the real-input butterfly shortcuts
+//   kMinCta   : Plan<L, kMinCta> (see fft_engine.cuh)
+#ifndef KOFFT_STFT_MIN_CTA
+#define KOFFT_STFT_MIN_CTA 128
+#endif
+#ifndef KOFFT_STFT_REAL
+#define KOFFT_STFT_REAL 1
+#endif
+template <class IO>
+struct IoTraits {
+    static constexpr bool kRealInput = false;
+    static constexpr int kMinCta = 256;
+};
+template <>
+struct IoTraits<IoStft> {
+    static constexpr bool kRealInput = KOFFT_STFT_REAL != 0;
+    static constexpr int kMinCta = KOFFT_STFT_MIN_CTA;
+};
+
 // ------------------------------------------------------------------------------------------
 // The CTA body, written as per-thread phase functions so that tests/emu can run the very
 // same code on the CPU (phase by phase over all threads) -- see tests/emu/emu_engine.cpp.
 // ------------------------------------------------------------------------------------------
 template <class P, bool EXACT, class IO>
 struct CtaFft {
-    using P0 = Pass<P, 0, EXACT>;
+    using P0 = Pass<P, 0, EXACT, true, IoTraits<IO>::kRealInput>;
     using P1 = Pass<P, 1, EXACT>;
     using P2 = Pass<P, (P::NP > 2 ? 2 : 1), EXACT>;
     using P3 = Pass<P, (P::NP > 3 ? 3 : 1), EXACT>;
@@ -531,12 +551,13 @@ struct CtaFft {
 
 #ifdef __CUDACC__
 template <int L, bool EXACT, class IO, bool STAGED>
-__global__ void __launch_bounds__(Plan<L>::CTA, (Plan<L>::CTA <= 256 ? 2 : 1))
+__global__ void __launch_bounds__((Plan<L, IoTraits<IO>::kMinCta>::CTA),
+                                  (Plan<L, IoTraits<IO>::kMinCta>::CTA <= 512 ? 512 / Plan<L, IoTraits<IO>::kMinCta>::CTA : 1))
     fft_cta_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0 tw0,
                    const float2 *__restrict__ table, long rows)
 {
     extern __shared__ __align__(128) float2 smem[];
-    CtaFft<Plan<L>, EXACT, IO>::template run<STAGED>(io, tw0, table, rows, smem);
+    CtaFft<Plan<L, IoTraits<IO>::kMinCta>, EXACT, IO>::template run<STAGED>(io, tw0, table, rows, smem);
 }
 #endif
 

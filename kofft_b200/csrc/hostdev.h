@@ -125,6 +125,34 @@ KHD void butterfly_unit(float2 &u, float2 &v)
     u = a;
 }
 
+// Real-input shortcuts (stft frames have imag == +0 exactly, src/stft.rs:97-100).  While an element
+// has only met unit twiddles it stays real, and the reference's operations on its zero imaginary
+// part reduce to identities: v.y*w = +-0 drops out of v*w, and 0 +- t.y = +-t.y.  The results are
+// the same f32 values (only the sign of an exact zero can differ, which no later operation of
+// the transform can turn into a different value).
+KHD void butterfly_unit_real(float2 &u, float2 &v)
+{
+    float a = add_rn(u.x, v.x);
+    v.x = sub_rn(u.x, v.x);
+    u.x = a;
+}
+template <bool EXACT>
+KHD void butterfly_real(float2 &u, float2 &v, const float2 w)
+{
+    if (EXACT) {
+        float2 t = mul2(make_float2(v.x, v.x), w);
+        float ax = add_rn(u.x, t.x), bx = sub_rn(u.x, t.x);
+        u = make_float2(ax, t.y);
+        v = make_float2(bx, -t.y);
+    } else {
+        float ax = fma_rn(v.x, w.x, u.x);
+        float ty = mul_rn(v.x, w.y);
+        float bx = fma_rn(u.x, 2.0f, -ax);
+        u = make_float2(ax, ty);
+        v = make_float2(bx, -ty);
+    }
+}
+
 // Complex::mul, unfused (src/num.rs:160-165), or contracted in FAST mode
 template <bool EXACT>
 KHD float2 cmul(const float2 a, const float2 b)

@@ -82,6 +82,13 @@ struct kofft_cuda_ctx {
     bool large_fused = true; // N > 16384: one persistent thread-block-cluster kernel
     bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
     int istft_run_frames = 64;
+    // host-pointer batch entry points: the batch is cut into chunks that flow through three
+    // streams (H2D copy engine, SMs, D2H copy engine) so both PCIe directions and the kernels overlap
+    size_t host_chunk_bytes = size_t(32) << 20; // 0 = one copy in, one launch, one copy out
+    static constexpr int kPipeSlots = 4;
+    cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr}; // [0] H2D, [1] compute, [2] D2H
+    cudaEvent_t pipe_event[3][kPipeSlots] = {};                // [0] H2D done, [1] kernel done, [2] D2H done
+    bool pipe_ready = false;
 };
 
 namespace {
@@ -260,8 +267,12 @@ cudaStream_t pick_stream(kofft_cuda_ctx *, void *stream)
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// transforms per CTA of the single-CTA engine (Plan<L>::TPC)
-long tpc_of(size_t n) { return n >= 4096 ? 1 : static_cast<long>(4096 / n); }
+// transforms per CTA of the single-CTA engine (Plan<L, min_cta>::TPC; 16 elements per thread)
+long tpc_of(size_t n, int min_cta = 256)
+{
+    const size_t per_cta = static_cast<size_t>(min_cta) * 16;
+    return n >= per_cta ? 1 : static_cast<long>(per_cta / n);
+}
 
 } // namespace
 
@@ -302,6 +313,13 @@ void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
     for (auto &kv : ctx->rfft_tables) cudaFree(kv.second.dev);
     for (int i = 0; i < 5; i++)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
+    if (ctx->pipe_ready) {
+        for (int i = 0; i < 3; i++) {
+            cudaStreamSynchronize(ctx->pipe_stream[i]);
+            cudaStreamDestroy(ctx->pipe_stream[i]);
+            for (int j = 0; j < kofft_cuda_ctx::kPipeSlots; j++) cudaEventDestroy(ctx->pipe_event[i][j]);
+        }
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -343,6 +361,11 @@ int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames)
 int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable)
 {
     ctx->large_fused = enable != 0;
+    return KOFFT_OK;
+}
+int kofft_cuda_set_host_pipeline(kofft_cuda_ctx *ctx, size_t chunk_bytes)
+{
+    ctx->host_chunk_bytes = chunk_bytes;
     return KOFFT_OK;
 }
 int kofft_cuda_set_rfft_table_fma(kofft_cuda_ctx *ctx, int fma_mul)
@@ -502,7 +525,7 @@ int kofft_cuda_stft_f32(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, 
     io.p1 = static_cast<long>(nframes);
     io.p2 = static_cast<long>(hop);
     // TMA staging needs 16-byte aligned, whole-float4 segments that never straddle a channel
-    const long tpc = tpc_of(win_len);
+    const long tpc = tpc_of(win_len, IoTraits<IoStft>::kMinCta);
     const bool staged = aligned16(d_signal) && len % 4 == 0 && hop % 4 == 0 && nframes % tpc == 0 &&
                         ((tpc - 1) * static_cast<long>(hop) + static_cast<long>(win_len)) * 4 <= tpc * static_cast<long>(win_len) * 8;
     return dispatch(ctx, KIND_STFT, io, win_len, channels * nframes, pick_stream(ctx, stream), staged);
@@ -589,6 +612,80 @@ int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nfram
     return KOFFT_OK;
 }
 
+} // extern "C"
+
+namespace {
+
+// Chunked, three-stream pipeline behind the host-pointer batch entry points.  `rows` independent
+// rows of in_row_bytes (host, read) -> out_row_bytes (host, written); launch(d_in, d_out, nrows,
+// stream) enqueues the kernels for one chunk.  Chunk i uses staging slot i % kPipeSlots; the copy
+// engines and the SMs are decoupled by events, so H2D of chunk i+1, the kernels of chunk i and
+// D2H of chunk i-1 run at the same time.  All kernels go to ONE stream (they may share context
+// workspaces).  in_place: the kernel overwrites its input slot, which is then copied back.
+template <class Launch>
+int host_pipeline(kofft_cuda_ctx *ctx, const void *h_in, size_t in_row_bytes, void *h_out, size_t out_row_bytes,
+                  size_t rows, bool in_place, Launch launch)
+{
+    constexpr int NS = kofft_cuda_ctx::kPipeSlots;
+    if (!ctx->pipe_ready) {
+        for (int i = 0; i < 3; i++) {
+            CU(cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking));
+            for (int j = 0; j < NS; j++) CU(cudaEventCreateWithFlags(&ctx->pipe_event[i][j], cudaEventDisableTiming));
+        }
+        ctx->pipe_ready = true;
+    }
+    const size_t big_row = in_row_bytes > out_row_bytes ? in_row_bytes : out_row_bytes;
+    size_t chunk = ctx->host_chunk_bytes / big_row;
+    if (chunk < 1) chunk = 1;
+    if (chunk > rows) chunk = rows;
+    const size_t nchunks = (rows + chunk - 1) / chunk;
+    const int slots = nchunks < size_t(NS) ? static_cast<int>(nchunks) : NS;
+    // slot strides rounded up to 256 bytes so every slot keeps the alignment TMA staging wants
+    const size_t in_slot = (chunk * in_row_bytes + 255) & ~size_t(255);
+    const size_t out_slot = (chunk * out_row_bytes + 255) & ~size_t(255);
+    void *d_in = nullptr, *d_out = nullptr;
+    int rc = ensure_ws(ctx, 0, in_slot * slots, &d_in);
+    if (rc) return rc;
+    if (!in_place) {
+        rc = ensure_ws(ctx, 1, out_slot * slots, &d_out);
+        if (rc) return rc;
+    }
+    cudaStream_t s_in = ctx->pipe_stream[0], s_k = ctx->pipe_stream[1], s_out = ctx->pipe_stream[2];
+    for (size_t i = 0; i < nchunks; i++) {
+        const int slot = static_cast<int>(i % slots);
+        const size_t r0 = i * chunk;
+        const size_t nr = rows - r0 < chunk ? rows - r0 : chunk;
+        char *di = static_cast<char *>(d_in) + slot * in_slot;
+        char *dout = in_place ? di : static_cast<char *>(d_out) + slot * out_slot;
+        if (i >= size_t(slots)) CU(cudaStreamWaitEvent(s_in, ctx->pipe_event[2][slot], 0)); // slot drained
+        CU(cudaMemcpyAsync(di, static_cast<const char *>(h_in) + r0 * in_row_bytes, nr * in_row_bytes,
+                           cudaMemcpyHostToDevice, s_in));
+        CU(cudaEventRecord(ctx->pipe_event[0][slot], s_in));
+        CU(cudaStreamWaitEvent(s_k, ctx->pipe_event[0][slot], 0));
+        rc = launch(di, dout, nr, s_k);
+        if (rc) {
+            cudaDeviceSynchronize();
+            return rc;
+        }
+        CU(cudaEventRecord(ctx->pipe_event[1][slot], s_k));
+        CU(cudaStreamWaitEvent(s_out, ctx->pipe_event[1][slot], 0));
+        CU(cudaMemcpyAsync(static_cast<char *>(h_out) + r0 * out_row_bytes, dout, nr * out_row_bytes,
+                           cudaMemcpyDeviceToHost, s_out));
+        CU(cudaEventRecord(ctx->pipe_event[2][slot], s_out));
+    }
+    CU(cudaStreamSynchronize(s_out));
+    return KOFFT_OK;
+}
+
+bool use_host_pipeline(const kofft_cuda_ctx *ctx, size_t total_bytes)
+{
+    return ctx->host_chunk_bytes != 0 && total_bytes > ctx->host_chunk_bytes;
+}
+
+} // namespace
+
+extern "C" {
+
 // ---- host-pointer drop-ins ------------------------------------------------------------------
 static int host_roundtrip_begin(kofft_cuda_ctx *ctx, const void *src, size_t bytes, int which, void **dev)
 {
@@ -605,6 +702,11 @@ int kofft_cuda_fft_batch_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, si
     if (n == 1 || batch == 0) return KOFFT_OK;
     CU(cudaSetDevice(ctx->device));
     const size_t bytes = n * batch * sizeof(float2);
+    if (use_host_pipeline(ctx, bytes))
+        return host_pipeline(ctx, data, n * sizeof(float2), data, n * sizeof(float2), batch, true,
+                             [&](void *di, void *dout, size_t nr, cudaStream_t s) {
+                                 return kofft_cuda_fft_c2c_f32(ctx, di, dout, n, nr, inverse, s);
+                             });
     void *d = nullptr;
     rc = host_roundtrip_begin(ctx, data, bytes, 0, &d);
     if (rc) return rc;
@@ -700,6 +802,11 @@ int kofft_cuda_rfft_batch_host_f32(kofft_cuda_ctx *ctx, const float *input, size
     if (rc) return rc;
     if (batch == 0) return KOFFT_OK;
     CU(cudaSetDevice(ctx->device));
+    if (use_host_pipeline(ctx, (m + 1) * batch * sizeof(float2)))
+        return host_pipeline(ctx, input, n * sizeof(float), output, (m + 1) * sizeof(float2), batch, false,
+                             [&](void *di, void *dout, size_t nr, cudaStream_t s) {
+                                 return kofft_cuda_rfft_f32(ctx, static_cast<const float *>(di), dout, n, nr, s);
+                             });
     void *din = nullptr, *dout = nullptr;
     rc = host_roundtrip_begin(ctx, input, n * batch * sizeof(float), 0, &din);
     if (rc) return rc;
@@ -730,6 +837,11 @@ int kofft_cuda_irfft_batch_host_f32(kofft_cuda_ctx *ctx, const float *input, siz
     if (rc) return rc;
     if (batch == 0) return KOFFT_OK;
     CU(cudaSetDevice(ctx->device));
+    if (use_host_pipeline(ctx, (m + 1) * batch * sizeof(float2)))
+        return host_pipeline(ctx, input, (m + 1) * sizeof(float2), output, n * sizeof(float), batch, false,
+                             [&](void *di, void *dout, size_t nr, cudaStream_t s) {
+                                 return kofft_cuda_irfft_f32(ctx, di, static_cast<float *>(dout), n, nr, s);
+                             });
     void *din = nullptr, *dout = nullptr;
     rc = host_roundtrip_begin(ctx, input, (m + 1) * batch * sizeof(float2), 0, &din);
     if (rc) return rc;

@@ -95,6 +95,10 @@ class Context:
     def set_tma_staging(self, enable: bool) -> None:
         check(_lib.lib().kofft_cuda_set_tma_staging(self.handle, int(bool(enable))))
 
+    def set_host_pipeline(self, chunk_bytes: int) -> None:
+        """chunk size of the H2D / kernel / D2H pipeline behind the host-pointer batch calls (0 = off)"""
+        check(_lib.lib().kofft_cuda_set_host_pipeline(self.handle, int(chunk_bytes)))
+
     def set_istft_fusion(self, enable: bool, run_frames: int = 0) -> None:
         check(_lib.lib().kofft_cuda_set_istft_fusion(self.handle, int(bool(enable)), int(run_frames)))
 

@@ -38,7 +38,7 @@ Tw0 make_tw0(int L, int R0, const float *table)
 template <int L, bool EXACT, class IO>
 int run_cta(const IO &io, const float *table, long rows, bool staged, int grid)
 {
-    using P = Plan<L>;
+    using P = Plan<L, IoTraits<IO>::kMinCta>; // the plan the shipped kernel uses for this IO
     Tw0 tw0 = make_tw0(L, P::R0, table);
     const long groups = (rows + P::TPC - 1) / P::TPC;
     if (grid > groups) grid = (int)groups;

@@ -726,3 +726,39 @@ def test_config3_full_size_rfft_65536x16384(cuda_fft, oracle):
     err = torch.linalg.vector_norm(z - x, dim=1) / torch.linalg.vector_norm(x, dim=1)
     assert float(err.max()) < 1e-2
     assert np.array_equal(z[idx].cpu().numpy(), oracle.irfft_batch(ref, n, nthreads=8))
+
+
+@pytest.mark.parametrize("chunk_bytes", [1 << 16, 1 << 20, 3 << 20])
+def test_host_pipeline_matches_single_shot(cuda_fft, oracle, chunk_bytes):
+    """Host-pointer batch calls cut into chunks over three streams (H2D / kernels / D2H) give the
+    same bits as one copy + one launch, for ragged chunk counts, pinned and pageable buffers."""
+    import torch
+
+    ctx = cuda_fft.ctx
+    rng = np.random.default_rng(chunk_bytes)
+    try:
+        # C2C in place, 301 rows of 1024 (2.4 MB): several chunks with a ragged tail
+        x = uniform_c64(rng, (301, 1024))
+        ref = oracle.fft_batch(x, nthreads=4)
+        ctx.set_host_pipeline(chunk_bytes)
+        y = x.copy()
+        cuda_fft.fft_batch(y)
+        assert np.array_equal(y, ref)
+        pinned = torch.from_numpy(x.copy()).pin_memory()
+        cuda_fft.fft_batch(pinned.numpy(), inverse=True)
+        assert np.array_equal(pinned.numpy(), oracle.fft_batch(x, inverse=True, nthreads=4))
+        # rfft / irfft out of place (row strides differ between input and output)
+        r = rng.uniform(-1, 1, (77, 8192)).astype(np.float32)
+        spec = cuda_fft.rfft_batch(r)
+        assert np.array_equal(spec, oracle.rfft_batch(r))
+        back = cuda_fft.irfft_batch(spec, 8192)
+        ctx.set_host_pipeline(0)
+        assert np.array_equal(back, cuda_fft.irfft_batch(spec, 8192))
+        # large-N path shares one scratch between chunks: kernels must stay on one stream
+        ctx.set_host_pipeline(chunk_bytes)
+        big = uniform_c64(rng, (9, 32768))
+        z = big.copy()
+        cuda_fft.fft_batch(z)
+        assert np.array_equal(z, oracle.fft_batch(big, nthreads=4))
+    finally:
+        ctx.set_host_pipeline(32 << 20)
