@@ -165,6 +165,36 @@ int kofft_cuda_istft_host_f32(kofft_cuda_ctx *ctx, const float *frames, size_t n
                               const float *window, size_t win_len, size_t hop, float *output, size_t out_len,
                               float *scratch, size_t scratch_len, int zero_uncovered);
 
+/* ---- one C2C transform sharded over the GPUs of a box (BASELINE configs[4]) -------------------
+ * No reference equivalent: kofft is single-process CPU code and `FftPlanner::get_twiddles`
+ * (src/fft.rs:391-405) degenerates at these sizes (cos(2 pi / 2^30) rounds to 1.0f), so this
+ * path uses correctly rounded twiddles and is validated against f64 instead.
+ *
+ * N = 2^log2n = N1 * N2 (N1 = 2^(log2n/2)); rank g of `world` (a power of two <= 16) owns the
+ * contiguous slice [g N/world, (g+1) N/world) of the input, i.e. rows [g N1/world, ...) of x
+ * viewed as [N1][N2].  The transform is four phases per rank; the all-to-all exchanges between
+ * the phases are performed by the kernels themselves as peer-to-peer stores over NVLink into the
+ * other ranks' buffers (no NCCL call, no staging).  The CALLER must place a barrier between
+ * phases: every rank finishes phase p (stream synchronize) before any rank starts phase p + 1.
+ *   natural_order == 0: d_out [N1/world][N2] holds X[(g N1/world + r) + N1 k2] at [r][k2]
+ *                       ("transposed" spectrum, two exchanges)
+ *   natural_order != 0: d_out holds the contiguous slice X[g N/world ...] (three exchanges)
+ * One process per GPU: create, exchange the 128-byte IPC handles of all ranks (any transport),
+ * connect_ipc.  One process driving several GPUs: create one per device, connect_local, then
+ * kofft_cuda_dist_run_local runs all phases with device-synchronising barriers. */
+typedef struct kofft_cuda_dist kofft_cuda_dist;
+int kofft_cuda_dist_create(kofft_cuda_ctx *ctx, int rank, int world, int log2n, kofft_cuda_dist **out);
+void kofft_cuda_dist_destroy(kofft_cuda_dist *d);
+size_t kofft_cuda_dist_shard_len(const kofft_cuda_dist *d); /* complex elements per rank */
+void *kofft_cuda_dist_buffer(const kofft_cuda_dist *d, int which); /* 0: A, 1: B (device) */
+int kofft_cuda_dist_ipc_handles(kofft_cuda_dist *d, void *out128);
+int kofft_cuda_dist_connect_ipc(kofft_cuda_dist *d, const void *all_handles /* world * 128 bytes, rank order */);
+int kofft_cuda_dist_connect_local(kofft_cuda_dist *const *dists, int world);
+int kofft_cuda_dist_phase(kofft_cuda_dist *d, int phase /* 0..3 */, const void *d_in, void *d_out, int inverse,
+                          int natural_order, void *stream);
+int kofft_cuda_dist_run_local(kofft_cuda_dist *const *dists, int world, const void *const *d_in,
+                              void *const *d_out, int inverse, int natural_order);
+
 #ifdef __cplusplus
 }
 #endif

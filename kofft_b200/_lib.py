@@ -55,6 +55,15 @@ SIGNATURES = {
     "kofft_cuda_irfft_host_f32": (_i, [_vp, _vp, _sz, _vp, _sz, _sz]),
     "kofft_cuda_irfft_batch_host_f32": (_i, [_vp, _vp, _sz, _sz, _vp]),
     "kofft_cuda_stft_host_f32": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _sz]),
+    "kofft_cuda_dist_create": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
+    "kofft_cuda_dist_destroy": (None, [_vp]),
+    "kofft_cuda_dist_shard_len": (_sz, [_vp]),
+    "kofft_cuda_dist_buffer": (_vp, [_vp, _i]),
+    "kofft_cuda_dist_ipc_handles": (_i, [_vp, _vp]),
+    "kofft_cuda_dist_connect_ipc": (_i, [_vp, _vp]),
+    "kofft_cuda_dist_connect_local": (_i, [C.POINTER(_vp), _i]),
+    "kofft_cuda_dist_phase": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
+    "kofft_cuda_dist_run_local": (_i, [C.POINTER(_vp), _i, C.POINTER(_vp), C.POINTER(_vp), _i, _i]),
     "kofft_cuda_istft_host_f32": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _vp, _sz, _i]),
 }
 

@@ -16,7 +16,8 @@ cudaError_t launch_variant(const IO &io, const LaunchArgs &a)
     using P = Plan<L, IoTraits<IO>::kMinCta>;
     constexpr int smem = STAGED ? P::SMEM_BYTES_STAGED : P::SMEM_BYTES;
     auto kern = fft_cta_kernel<L, EXACT, IO, STAGED>;
-    static int occ = 0; // per instantiation
+    static PerDevice occ_pd; // per instantiation and device
+    int &occ = occ_pd.get();
     if (occ == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;

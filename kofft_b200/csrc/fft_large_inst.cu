@@ -28,7 +28,8 @@ cudaError_t launch_col(const IO &io, const LaunchArgs &a, const LargeArgs &g)
 {
     using C = ColPass<EXACT, IO>;
     auto kern = colpass_kernel<EXACT, IO>;
-    static int occ = 0;
+    static PerDevice occ_pd;
+    int &occ = occ_pd.get();
     cudaError_t e = prep(kern, C::SMEM_BYTES, 256, &occ);
     if (e != cudaSuccess) return e;
     const long tiles = g.chunk_rows << (g.lsub - 4);
@@ -43,7 +44,8 @@ cudaError_t launch_row(const IO &io, const LaunchArgs &a, const LargeArgs &g)
 {
     using R = RowPass<LB, EXACT, IO, EPI>;
     auto kern = rowpass_kernel<LB, EXACT, IO, EPI>;
-    static int occ = 0;
+    static PerDevice occ_pd;
+    int &occ = occ_pd.get();
     cudaError_t e = prep(kern, R::SMEM_BYTES, 256, &occ);
     if (e != cudaSuccess) return e;
     const long tiles = g.chunk_rows * R::NKB;
@@ -61,7 +63,8 @@ cudaError_t launch_fused(const IO &io, const LaunchArgs &a, const LargeArgs &g)
 {
     using F = LargeFused<LB, EXACT, IO, EPI>;
     auto kern = large_fused_kernel<LB, EXACT, IO, EPI>;
-    static int max_clusters = 0;
+    static PerDevice mc_pd;
+    int &max_clusters = mc_pd.get();
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

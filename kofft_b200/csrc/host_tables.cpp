@@ -34,6 +34,21 @@ void host_fft_twiddles(size_t n, float *out)
     }
 }
 
+// Correctly rounded roots of unity exp(-2 pi i k stride / n), k < count, evaluated in f64.  NOT the
+// reference's table: used only where the reference has no usable output (the multi-GPU
+// transform of BASELINE configs[4]) and for the inter-step twiddles of that path.
+void host_accurate_twiddles(size_t n, size_t stride, size_t count, float *out)
+{
+    const double step = -2.0 * 3.14159265358979323846 / static_cast<double>(n);
+    for (size_t k = 0; k < count; ++k) {
+        // reduce k*stride mod n exactly before scaling so large exponents keep full accuracy
+        const size_t e = (k * stride) % n;
+        // use the octant symmetry-free direct form: |step*e| <= 2 pi, f64 error ~1e-16
+        out[2 * k] = static_cast<float>(cos(step * static_cast<double>(e)));
+        out[2 * k + 1] = static_cast<float>(sin(step * static_cast<double>(e)));
+    }
+}
+
 // build_twiddle_table, reference src/rfft.rs:172-183; `current = current.mul(w)` with
 // Complex::mul unfused (src/num.rs:160-165) or fused under +fma (src/num.rs:173-178)
 void host_rfft_twiddles(size_t m, float *out, bool fma_mul)

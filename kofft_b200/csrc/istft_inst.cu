@@ -11,7 +11,8 @@ cudaError_t launch_one(const IstftFusedArgs &f, const LaunchArgs &a)
 {
     using K = IstftFused<L, EXACT>;
     auto kern = istft_fused_kernel<L, EXACT>;
-    static int occ = 0;
+    static PerDevice occ_pd;
+    int &occ = occ_pd.get();
     if (occ == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
         if (e != cudaSuccess) return e;

@@ -15,6 +15,7 @@
 #include <utility>
 #include <vector>
 
+#include "dist_kernels.h"
 #include "host_tables.h"
 #include "istft_fused.cuh"
 #include "launch.h"
@@ -70,7 +71,8 @@ struct kofft_cuda_ctx {
     bool rfft_fma = false;
     int max_ctas = 0;
     unsigned long long launches = 0;
-    std::map<size_t, Table> fft_tables;                  // key n
+    std::map<std::pair<size_t, int>, Table> fft_tables;  // key (n, accurate)
+    bool accurate_tables = false; // true: correctly rounded roots of unity instead of the reference's recurrence
     std::map<std::pair<size_t, int>, Table> rfft_tables; // key (m, fma)
     // grow-only device workspaces: [0] host-API staging in, [1] staging out, [2] istft time frames,
     // [3] small staging (windows), [4] two-pass (N > 16384) intermediate
@@ -112,16 +114,20 @@ int ensure_ws(kofft_cuda_ctx *ctx, int which, size_t bytes, void **out)
 
 int get_fft_table(kofft_cuda_ctx *ctx, size_t n, const Table **out)
 {
-    auto it = ctx->fft_tables.find(n);
+    const auto key = std::make_pair(n, ctx->accurate_tables ? 1 : 0);
+    auto it = ctx->fft_tables.find(key);
     if (it == ctx->fft_tables.end()) {
         Table t;
         size_t half = n / 2;
         t.host.resize(2 * (half ? half : 1));
-        host_fft_twiddles(n, t.host.data());
+        if (ctx->accurate_tables)
+            host_accurate_twiddles(n, 1, half, t.host.data());
+        else
+            host_fft_twiddles(n, t.host.data());
         CU(cudaMalloc(&t.dev, sizeof(float2) * (half ? half : 1)));
         CU(cudaMemcpyAsync(t.dev, t.host.data(), sizeof(float2) * half, cudaMemcpyHostToDevice, ctx->stream));
         // the host vector must outlive the async copy: it is owned by the map entry below
-        it = ctx->fft_tables.emplace(n, std::move(t)).first;
+        it = ctx->fft_tables.emplace(key, std::move(t)).first;
         CU(cudaStreamSynchronize(ctx->stream));
     }
     *out = &it->second;
@@ -919,6 +925,247 @@ int kofft_cuda_istft_host_f32(kofft_cuda_ctx *ctx, const float *frames, size_t n
     if (obytes) CU(cudaMemcpyAsync(output, d_out, obytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (scratch && obytes) CU(cudaMemcpyAsync(scratch, d_norm, obytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+} // extern "C"
+
+// ---- one transform sharded over several GPUs (BASELINE configs[4]) -----------------
+// Four-step split N = N1 * N2 (n = N2 n1 + n2, k = k1 + N1 k2):
+//   X[k1 + N1 k2] = sum_n2 W_N2^{n2 k2} * W_N^{n2 k1} * sum_n1 W_N1^{n1 k1} x[N2 n1 + n2]
+// Rank g owns rows n1 in [g R1, (g+1) R1) of x viewed as [N1][N2] (a contiguous slice of the
+// input), R1 = N1 / world, C2 = N2 / world.
+//   phase 0  transpose-scatter x_g [R1][N2] -> A_h [C2][N1] on every rank h      (P2P stores)
+//   phase 1  N1-point FFTs of the C2 rows of A (in place), then transpose-scatter with the
+//            inter-step twiddle W_N^{n2 k1} -> B_h [R1][N2] on every rank h       (P2P stores)
+//   phase 2  N2-point FFTs of the R1 rows of B: B[r][k2] = X[(g R1 + r) + N1 k2] (transposed
+//            order, written to d_out) -- or, natural order: in place, then transpose-scatter
+//            -> A_h [C2][N1] (= X[h N/world ...], the contiguous slice of the spectrum)
+//   phase 3  natural order only: copy A -> d_out
+// Ranks must not start phase p+1 before every rank has finished phase p (the caller puts a
+// barrier between phases: stream synchronize + process barrier, or kofft_cuda_dist_run_local).
+// Twiddles are correctly rounded (f64-evaluated) -- the reference's recurrence table degenerates
+// at this size, so this path is validated against f64, not against kofft.
+struct kofft_cuda_dist {
+    kofft_cuda_ctx *ctx = nullptr;
+    int rank = 0, world = 1, log2n = 0, l1 = 0, l2 = 0, llo = 0;
+    size_t n1 = 0, n2 = 0, r1 = 0, c2 = 0;
+    float2 *bufA = nullptr, *bufB = nullptr;
+    float2 *peerA[kMaxDistWorld] = {}, *peerB[kMaxDistWorld] = {};
+    bool ipc_open[kMaxDistWorld] = {};
+    bool connected = false;
+    float2 *tlo = nullptr, *thi = nullptr;
+};
+
+namespace {
+
+int dist_scatter(kofft_cuda_dist *d, const float2 *src, float2 *const *peers, size_t rows, size_t cb, int twiddle,
+                 cudaStream_t s)
+{
+    ScatterArgs a;
+    a.src = src;
+    for (int g = 0; g < d->world; g++) a.dst[g] = peers[g];
+    a.rows = static_cast<long>(rows);
+    a.cb = static_cast<long>(cb);
+    a.world = d->world;
+    a.dst_pitch = static_cast<long>(rows) * d->world;
+    a.dst_off = static_cast<long>(rows) * d->rank;
+    a.twiddle = twiddle;
+    a.row0 = static_cast<long>(rows) * d->rank;
+    a.log2n = d->log2n;
+    a.llo = d->llo;
+    a.tlo = d->tlo;
+    a.thi = d->thi;
+    (void)cudaGetLastError();
+    cudaError_t e = launch_transpose_scatter(a, d->ctx->num_sms, s);
+    if (e != cudaSuccess) return fail_cuda(e, "transpose_scatter launch");
+    d->ctx->launches++;
+    return KOFFT_OK;
+}
+
+// batched C2C with correctly rounded tables, restoring the context's table mode afterwards
+int dist_local_fft(kofft_cuda_dist *d, const void *in, void *out, size_t n, size_t batch, int inverse, cudaStream_t s)
+{
+    const bool saved = d->ctx->accurate_tables;
+    d->ctx->accurate_tables = true;
+    int rc = kofft_cuda_fft_c2c_f32(d->ctx, in, out, n, batch, inverse, s);
+    d->ctx->accurate_tables = saved;
+    return rc;
+}
+
+} // namespace
+
+extern "C" {
+
+int kofft_cuda_dist_create(kofft_cuda_ctx *ctx, int rank, int world, int log2n, kofft_cuda_dist **out)
+{
+    if (!out) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null out pointer");
+    *out = nullptr;
+    if (world < 1 || world > kMaxDistWorld || (world & (world - 1)) != 0 || rank < 0 || rank >= world)
+        return fail_msg(KOFFT_ERR_INVALID_VALUE, "world must be a power of two <= 16 and 0 <= rank < world");
+    const int l1 = log2n / 2, l2 = log2n - l1;
+    const int lw = log2_of(static_cast<size_t>(world));
+    if (l2 > 16 || l1 - lw < 5)
+        return fail_msg(KOFFT_ERR_INVALID_VALUE, "log2n must satisfy 10 + 2 log2(world) <= log2n <= 32");
+    CU(cudaSetDevice(ctx->device));
+    kofft_cuda_dist *d = new kofft_cuda_dist();
+    d->ctx = ctx;
+    d->rank = rank;
+    d->world = world;
+    d->log2n = log2n;
+    d->l1 = l1;
+    d->l2 = l2;
+    d->n1 = size_t(1) << l1;
+    d->n2 = size_t(1) << l2;
+    d->r1 = d->n1 / world;
+    d->c2 = d->n2 / world;
+    d->llo = (log2n + 1) / 2;
+    const size_t shard = (size_t(1) << log2n) / world * sizeof(float2);
+    const size_t nlo = size_t(1) << d->llo, nhi = size_t(1) << (log2n - d->llo);
+    std::vector<float> h(2 * (nlo > nhi ? nlo : nhi));
+    cudaError_t e = cudaMalloc(&d->bufA, shard);
+    if (e == cudaSuccess) e = cudaMalloc(&d->bufB, shard);
+    if (e == cudaSuccess) e = cudaMalloc(&d->tlo, nlo * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&d->thi, nhi * sizeof(float2));
+    if (e == cudaSuccess) {
+        host_accurate_twiddles(size_t(1) << log2n, 1, nlo, h.data());
+        e = cudaMemcpy(d->tlo, h.data(), nlo * sizeof(float2), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        host_accurate_twiddles(size_t(1) << log2n, nlo, nhi, h.data());
+        e = cudaMemcpy(d->thi, h.data(), nhi * sizeof(float2), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(d->bufA);
+        cudaFree(d->bufB);
+        cudaFree(d->tlo);
+        cudaFree(d->thi);
+        delete d;
+        return fail_cuda(e, "kofft_cuda_dist_create");
+    }
+    d->peerA[rank] = d->bufA;
+    d->peerB[rank] = d->bufB;
+    d->connected = world == 1;
+    *out = d;
+    return KOFFT_OK;
+}
+
+void kofft_cuda_dist_destroy(kofft_cuda_dist *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    cudaDeviceSynchronize();
+    for (int g = 0; g < d->world; g++)
+        if (d->ipc_open[g]) {
+            cudaIpcCloseMemHandle(d->peerA[g]);
+            cudaIpcCloseMemHandle(d->peerB[g]);
+        }
+    cudaFree(d->bufA);
+    cudaFree(d->bufB);
+    cudaFree(d->tlo);
+    cudaFree(d->thi);
+    delete d;
+}
+
+size_t kofft_cuda_dist_shard_len(const kofft_cuda_dist *d) { return (size_t(1) << d->log2n) / d->world; }
+void *kofft_cuda_dist_buffer(const kofft_cuda_dist *d, int which) { return which == 0 ? d->bufA : d->bufB; }
+
+int kofft_cuda_dist_ipc_handles(kofft_cuda_dist *d, void *out128)
+{
+    CU(cudaSetDevice(d->ctx->device));
+    cudaIpcMemHandle_t h[2];
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "two 64-byte handles per rank");
+    CU(cudaIpcGetMemHandle(&h[0], d->bufA));
+    CU(cudaIpcGetMemHandle(&h[1], d->bufB));
+    memcpy(out128, h, sizeof h);
+    return KOFFT_OK;
+}
+
+int kofft_cuda_dist_connect_ipc(kofft_cuda_dist *d, const void *all_handles)
+{
+    CU(cudaSetDevice(d->ctx->device));
+    const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+    for (int g = 0; g < d->world; g++) {
+        if (g == d->rank || d->ipc_open[g]) continue;
+        void *pa = nullptr, *pb = nullptr;
+        CU(cudaIpcOpenMemHandle(&pa, h[2 * g], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&pb, h[2 * g + 1], cudaIpcMemLazyEnablePeerAccess));
+        d->peerA[g] = static_cast<float2 *>(pa);
+        d->peerB[g] = static_cast<float2 *>(pb);
+        d->ipc_open[g] = true;
+    }
+    d->connected = true;
+    return KOFFT_OK;
+}
+
+int kofft_cuda_dist_connect_local(kofft_cuda_dist *const *dists, int world)
+{
+    for (int g = 0; g < world; g++)
+        if (!dists[g] || dists[g]->world != world || dists[g]->rank != g || dists[g]->log2n != dists[0]->log2n)
+            return fail_msg(KOFFT_ERR_INVALID_VALUE, "dists[g] must be rank g of the same world and size");
+    for (int g = 0; g < world; g++) {
+        CU(cudaSetDevice(dists[g]->ctx->device));
+        for (int h = 0; h < world; h++) {
+            dists[g]->peerA[h] = dists[h]->bufA;
+            dists[g]->peerB[h] = dists[h]->bufB;
+            const int dg = dists[g]->ctx->device, dh = dists[h]->ctx->device;
+            if (dg != dh) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, dg, dh));
+                if (!can) return fail_msg(-static_cast<int>(cudaErrorPeerAccessUnsupported), "no peer access between the devices");
+                cudaError_t e = cudaDeviceEnablePeerAccess(dh, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail_cuda(e, "cudaDeviceEnablePeerAccess");
+                (void)cudaGetLastError();
+            }
+        }
+        dists[g]->connected = true;
+    }
+    return KOFFT_OK;
+}
+
+int kofft_cuda_dist_phase(kofft_cuda_dist *d, int phase, const void *d_in, void *d_out, int inverse,
+                          int natural_order, void *stream)
+{
+    if (!d->connected) return fail_msg(KOFFT_ERR_INVALID_VALUE, "connect the ranks first (connect_ipc / connect_local)");
+    CU(cudaSetDevice(d->ctx->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int tw = inverse ? 2 : 1;
+    switch (phase) {
+    case 0:
+        return dist_scatter(d, static_cast<const float2 *>(d_in), d->peerA, d->r1, d->c2, 0, s);
+    case 1: {
+        int rc = dist_local_fft(d, d->bufA, d->bufA, d->n1, d->c2, inverse, s);
+        if (rc) return rc;
+        return dist_scatter(d, d->bufA, d->peerB, d->c2, d->r1, tw, s);
+    }
+    case 2: {
+        if (!natural_order) return dist_local_fft(d, d->bufB, d_out, d->n2, d->r1, inverse, s);
+        int rc = dist_local_fft(d, d->bufB, d->bufB, d->n2, d->r1, inverse, s);
+        if (rc) return rc;
+        return dist_scatter(d, d->bufB, d->peerA, d->r1, d->c2, 0, s);
+    }
+    case 3:
+        if (natural_order && d_out != d->bufA)
+            CU(cudaMemcpyAsync(d_out, d->bufA, kofft_cuda_dist_shard_len(d) * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+        return KOFFT_OK;
+    default:
+        return fail_msg(KOFFT_ERR_INVALID_VALUE, "phase must be 0..3");
+    }
+}
+
+int kofft_cuda_dist_run_local(kofft_cuda_dist *const *dists, int world, const void *const *d_in, void *const *d_out,
+                              int inverse, int natural_order)
+{
+    for (int phase = 0; phase < 4; phase++) {
+        for (int g = 0; g < world; g++) {
+            int rc = kofft_cuda_dist_phase(dists[g], phase, d_in[g], d_out[g], inverse, natural_order, dists[g]->ctx->stream);
+            if (rc) return rc;
+        }
+        for (int g = 0; g < world; g++) { // the barrier between phases
+            CU(cudaSetDevice(dists[g]->ctx->device));
+            CU(cudaStreamSynchronize(dists[g]->ctx->stream));
+        }
+    }
     return KOFFT_OK;
 }
 

@@ -46,6 +46,18 @@ struct LaunchArgs {
     cudaStream_t stream = nullptr;
 };
 
+// Function attributes (dynamic shared memory opt-in) and occupancy are per device: every kernel
+// instantiation keeps one cached value per device so one process can drive several GPUs.
+struct PerDevice {
+    int v[64] = {};
+    int &get()
+    {
+        int d = 0;
+        cudaGetDevice(&d);
+        return v[d & 63];
+    }
+};
+
 // N = 32 .. 16384 (L = 5 .. 14)
 cudaError_t launch_cta_fft(int L, const LaunchArgs &a);
 // N = 1 .. 16

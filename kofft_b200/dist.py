@@ -1,0 +1,100 @@
+"""One C2C transform sharded over the GPUs of a box (BASELINE configs[4]).
+
+No reference equivalent: kofft is single-process CPU code and its planner table degenerates at
+2^30.  Host side of `kofft_cuda_dist_*` (include/kofft_cuda.h): a four-step split
+N = N1 * N2 whose all-to-all exchanges are peer-to-peer stores issued by the kernels themselves
+over NVLink.  Two ways to drive it:
+
+  * one process per GPU (`DistFft` + `torch.distributed`): the process group is used only to
+    exchange the 128-byte CUDA IPC handles and as the barrier between phases;
+  * one process, several devices (`run_local`): also usable with every rank on ONE device, which
+    is how the single-GPU tests exercise the multi-rank index math.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+from . import _lib
+from .errors import check
+from .fft import Context
+
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+class DistFft:
+    """Rank `rank` of `world` for one N = 2**log2n transform; owns two shard-sized device buffers."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, log2n: int):
+        self.ctx, self.rank, self.world, self.log2n = ctx, int(rank), int(world), int(log2n)
+        h = C.c_void_p()
+        check(_lib.lib().kofft_cuda_dist_create(ctx.handle, self.rank, self.world, self.log2n, C.byref(h)))
+        self._h = h
+        self.shard_len = int(_lib.lib().kofft_cuda_dist_shard_len(h))
+        self.n1 = 1 << (self.log2n // 2)
+        self.n2 = 1 << (self.log2n - self.log2n // 2)
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise RuntimeError("DistFft already destroyed")
+        return self._h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            _lib.lib().kofft_cuda_dist_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- one process per GPU ------------------------------------------------------------------
+    def connect(self, group=None) -> None:
+        """Exchange IPC handles over a torch.distributed process group and map the peers' buffers."""
+        import torch.distributed as dist
+
+        mine = C.create_string_buffer(128)
+        check(_lib.lib().kofft_cuda_dist_ipc_handles(self.handle, mine))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(mine.raw), group=group)
+        blob = C.create_string_buffer(b"".join(gathered), 128 * self.world)
+        check(_lib.lib().kofft_cuda_dist_connect_ipc(self.handle, blob))
+        self._group = group
+
+    def phase(self, p: int, x, out, inverse: bool = False, natural_order: bool = True, stream: Optional[int] = None):
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        check(_lib.lib().kofft_cuda_dist_phase(self.handle, int(p), C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+                                               int(inverse), int(natural_order), C.c_void_p(s)))
+
+    def transform(self, x, out=None, inverse: bool = False, natural_order: bool = True, barrier=None):
+        """x: this rank's contiguous slice (CUDA complex64, N/world elements).  Returns this rank's
+        slice of the spectrum (natural_order) or rows [rank*N1/world ...) of X[k1 + N1*k2] as [r][k2]."""
+        import torch.distributed as dist
+
+        if out is None:
+            out = torch.empty_like(x)
+        if barrier is None:
+            def barrier():
+                torch.cuda.synchronize()
+                if self.world > 1:
+                    dist.barrier(group=getattr(self, "_group", None))
+        for p in range(4 if natural_order else 3):
+            self.phase(p, x, out, inverse, natural_order)
+            barrier()
+        return out
+
+
+def run_local(dists: Sequence[DistFft], xs, outs, inverse: bool = False, natural_order: bool = True) -> None:
+    """All ranks driven from this process (devices may repeat): phases with device-synchronising barriers."""
+    world = len(dists)
+    hs = (C.c_void_p * world)(*[d.handle for d in dists])
+    check(_lib.lib().kofft_cuda_dist_connect_local(hs, world))
+    ins = (C.c_void_p * world)(*[C.c_void_p(x.data_ptr()) for x in xs])
+    os_ = (C.c_void_p * world)(*[C.c_void_p(o.data_ptr()) for o in outs])
+    check(_lib.lib().kofft_cuda_dist_run_local(hs, world, ins, os_, int(inverse), int(natural_order)))
