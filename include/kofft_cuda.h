@@ -66,7 +66,7 @@ unsigned long long kofft_cuda_launch_count(const kofft_cuda_ctx *ctx);
 int kofft_cuda_set_tma_staging(kofft_cuda_ctx *ctx, int enable);
 /* istft, window 512..4096: enable (default) / disable the single fused kernel (inverse FFT +
  * window + ordered overlap-add + normalisation); run_frames > 0 sets the frames a CTA owns per
- * run (default 64).  Disabled or out of range -> two kernels with an f32 intermediate. */
+ * run (default 128).  Disabled or out of range -> two kernels with an f32 intermediate. */
 int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames);
 /* N > 16384: enable (default) / disable the single persistent thread-block-cluster kernel;
  * when disabled (or unavailable) two kernels per L2-sized batch chunk are used instead */

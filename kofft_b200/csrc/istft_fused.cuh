@@ -2,16 +2,29 @@
 // normalisation fused behind the last FFT stage (reference: src/stft.rs:117-156; the
 // `inverse_parallel` variant :289-343 via zero_uncovered).
 //
-// A CTA owns a run of G consecutive frames of one channel and the output samples
-// [F0*hop, Fend*hop) they start (the channel's last run also owns the tail up to out_len).
-// It walks the frames in increasing order -- first the H = ceil(N/hop)-1 halo frames before F0,
-// whose tails reach into the owned samples (recomputed, not communicated) -- and adds each
-// frame's windowed real part into an N-sample ring buffer in shared memory.  After frame f has
-// been added no later frame touches samples [f*hop, (f+1)*hop), so they are normalised by the
-// summed window power, stored, and their ring slots recycled (re-initialised from the caller's
-// `output`, which the reference accumulates into).  Per sample this performs exactly the
-// reference's sequence of f32 additions, in the same (frame) order, so the result is
-// bit-identical and deterministic; no atomics, no intermediate frame buffer in HBM.
+// One CTA = one frame at a time (N/16 threads, 16 bins per thread); a CTA owns a run of G
+// consecutive frames of one channel and the output samples [F0*hop, Fend*hop) they start (the
+// channel's last run also owns the tail up to out_len).  It walks the frames in increasing
+// order -- first the H = ceil(N/hop)-1 halo frames before F0, whose tails reach into the owned
+// samples (recomputed, not communicated) -- and ADDS each frame's windowed real part into an
+// N-sample accumulator ring in shared memory, every thread adding its own 16 samples.  After
+// frame f has been added no later frame touches samples [f*hop, (f+1)*hop): they are
+// normalised by the summed window power, stored, and their ring slots recycled
+// (re-initialised from the caller's `output`, which the reference accumulates into).  Per sample
+// this is exactly the reference's sequence of f32 additions, in the same (frame) order, so the
+// result is bit-identical and deterministic; no atomics, no intermediate frame buffer in HBM.
+//
+// Pipeline inside the frame loop (no barrier beyond the two the FFT exchanges need anyway):
+//   iteration f:  P0 | sync A | finalise + recycle region f-1 | P1 | sync B | P2 | ring += frame f
+// The ring add of frame f-1 precedes sync A of iteration f, the recycling of region f-1
+// precedes sync B, and the ring add of frame f follows it.  The next frame is fetched by one TMA
+// bulk copy while the current one is transformed; the initial-output values for the recycled
+// slots are loaded at the top of the iteration so their latency hides behind pass 0.
+//
+// Window power: sample p = f*hop + r is covered by K(r) = floor((N-1-r)/hop)+1 frames in steady
+// state; normtab[r] = w[r+(K-1)hop]^2 + ... + w[r]^2 summed in the reference's (frame) order is
+// built once per CTA in shared memory.  The first ceil(N/hop)-1 regions of a channel and the
+// tail after the last frame have fewer covering frames and take the generic loop.
 //
 // HBM traffic per frame: 8N (frame) * (1 + H/G) + 4 hop (initial output) + 4 hop (result).
 #pragma once
@@ -32,19 +45,26 @@ struct IstftFusedArgs {
 
 template <int L, bool EXACT>
 struct IstftFused {
-    using P = Plan<L>;
-    static_assert(P::NP == 3 && P::NBUF == 2, "fused istft covers N = 512 .. 4096");
+    using P = Plan<L, 32>; // one frame per CTA: N/16 threads
+    static_assert(P::NP == 3 && P::NBUF == 2 && P::TPC == 1, "fused istft covers N = 512 .. 4096");
     using IO = IoIstft;
     using H = CtaFft<P, EXACT, IO>;
     using P0 = Pass<P, 0, EXACT>;
     using P1 = Pass<P, 1, EXACT>;
     using P2 = Pass<P, 2, EXACT>;
     static constexpr int N = P::N;
-    static constexpr int TPC = P::TPC;
-    static constexpr int SMEM_BYTES = P::STAGE_BYTES + P::XCHG_BYTES + N * 4 + 16;
+    static constexpr int CTA = P::CTA;
+    // CTAs per SM are bounded by shared memory (estimated at hop = N/4); give the registers that leaves
+    static constexpr int SMEM_EST = P::STAGE_BYTES + P::XCHG_BYTES + N * 4 + N + 16;
+    static constexpr int BY_SMEM = 227 * 1024 / (SMEM_EST + 1024);
+    static constexpr int BY_REGS = 65536 / (CTA * 168); // the body wants ~168 registers to stay spill-free
+    static constexpr int BY_BOTH = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
+    static constexpr int MIN_BLOCKS = BY_BOTH > 8 ? 8 : (BY_BOTH < 1 ? 1 : BY_BOTH);
+    // [stage N*8][exchange 2*PADN*8][ring N*4][normtab hop*4][mbarrier 8]
+    static constexpr int smem_bytes(long hop) { return P::STAGE_BYTES + P::XCHG_BYTES + N * 4 + (int)((hop * 4 + 15) & ~15L) + 16; }
 
-    // normalise (or leave / zero) one finished sample and write it back
-    static KD void finalize(const IstftFusedArgs &a, long c, long p, float acc)
+    // generic window-power sum of sample p (frames f_lo..f_hi in increasing order, src/stft.rs:146-148)
+    static KD float norm_generic(const IstftFusedArgs &a, long p)
     {
         const long f_hi = (p / a.hop < a.nframes - 1) ? p / a.hop : a.nframes - 1;
         const long f_lo = p >= N ? (p - N) / a.hop + 1 : 0;
@@ -53,6 +73,11 @@ struct IstftFused {
             const float w = KOFFT_LDG(a.window + (p - f * a.hop));
             nrm = add_rn(nrm, mul_rn(w, w));
         }
+        return nrm;
+    }
+    // normalise (or leave / zero) one finished sample and write it back (src/stft.rs:150-154, 335-341)
+    static KD void emit(const IstftFusedArgs &a, long c, long p, float acc, float nrm)
+    {
         if (nrm > 1e-8f)
             acc = div_rn(acc, nrm);
         else if (a.zero_uncovered)
@@ -63,17 +88,17 @@ struct IstftFused {
 
     static KD void run(const IstftFusedArgs &a, const Tw0 &tw0, const float2 *__restrict__ table, float2 *smem)
     {
-        const int tid = threadIdx.x;
-        const int slot = tid / P::T;
-        const int t = tid - slot * P::T;
+        const int t = threadIdx.x;
         unsigned char *stage = reinterpret_cast<unsigned char *>(smem);
         float2 *xch = smem + P::STAGE_BYTES / 8;
-        float2 *buf0 = xch + slot * P::PADN;
-        float2 *buf1 = buf0 + TPC * P::PADN;
+        float2 *buf0 = xch;
+        float2 *buf1 = buf0 + P::PADN;
         float *ring = reinterpret_cast<float *>(xch + P::XCHG_BYTES / 8);
-        unsigned long long *mbar = reinterpret_cast<unsigned long long *>(ring + N); // 8-byte aligned: N*4 % 8 == 0
+        float *normtab = ring + N;
+        const long hop = a.hop;
+        unsigned long long *mbar = reinterpret_cast<unsigned long long *>(normtab + ((hop + 3) & ~3L));
         unsigned phase = 0;
-        if (tid == 0) {
+        if (t == 0) {
             mbar_init(mbar, 1);
             fence_mbar_init();
         }
@@ -83,16 +108,23 @@ struct IstftFused {
         float wv[EPT]; // window at this thread's output positions
 #pragma unroll
         for (int w = 0; w < P2::R; w++) wv[w] = KOFFT_LDG(a.window + P2::dst_index(t, 0, w));
+        // steady-state window power per residue, summed in frame order (earliest frame = largest offset first)
+        for (long r = t; r < hop; r += CTA) {
+            float nrm = 0.0f;
+            for (long i = (N - 1 - r) / hop; i >= 0; i--) {
+                const float w = KOFFT_LDG(a.window + r + i * hop);
+                nrm = add_rn(nrm, mul_rn(w, w));
+            }
+            normtab[r] = nrm;
+        }
         __syncthreads();
 
-        const long hop = a.hop;
         long nfe = (a.out_len + hop - 1) / hop; // frames that can reach the output
         if (nfe > a.nframes) nfe = a.nframes;
         const long G = a.run_frames;
         const long runs_per_ch = (nfe + G - 1) / G;
         const long total = a.channels * runs_per_ch;
-        const long halo = (N + hop - 1) / hop - 1;
-        int par = 0;
+        const long halo = (N + hop - 1) / hop - 1; // == frames before f that still reach region f
 
         for (long run = blockIdx.x; run < total; run += gridDim.x) {
             const long c = run / runs_per_ch;
@@ -104,20 +136,56 @@ struct IstftFused {
             const float2 *fr_base = a.frames + c * a.nframes * N;
             const float *out0 = a.output + c * a.out_len;
 
-            // first group of the run
-            if (tid == 0) {
-                const long nf = Fend - fs < TPC ? Fend - fs : TPC;
-                mbar_expect_tx(mbar, (unsigned)(nf * N * 8));
-                bulk_copy_g2s(stage, fr_base + fs * N, (unsigned)(nf * N * 8), mbar);
+            if (t == 0) { // first frame of the run
+                mbar_expect_tx(mbar, (unsigned)(N * 8));
+                bulk_copy_g2s(stage, fr_base + fs * N, (unsigned)(N * 8), mbar);
             }
             // ring <- initial output for the owned samples among [fs*hop, fs*hop + N)
-            for (int j = tid; j < N; j += P::CTA) {
+            for (int j = t; j < N; j += CTA) {
                 const long p = fs * hop + j;
                 ring[p & (N - 1)] = (p >= own_lo && p < own_hi) ? out0[p] : 0.0f;
             }
             __syncthreads();
 
-            for (long f = fs; f < Fend; f += TPC) {
+            // finalise region fr = [fr*hop, (fr+1)*hop) and recycle its slots for the samples N later.
+            // pre: the recycled slots' initial values, loaded by the caller ahead of time (hop <= PRE*CTA)
+            constexpr int PRE = 4;
+            const bool use_pre = hop <= (long)PRE * CTA;
+            auto recycled_init = [&](long p2) { return (p2 >= own_lo && p2 < own_hi) ? out0[p2] : 0.0f; };
+            auto finalize_region = [&](long fr, const float *pre) {
+                const bool steady = fr >= halo; // every residue has its full set of covering frames
+                if (use_pre) {
+#pragma unroll
+                    for (int i = 0; i < PRE; i++) {
+                        const long j = t + (long)i * CTA;
+                        if (j < hop) {
+                            const long p = fr * hop + j;
+                            float *r = ring + (p & (N - 1));
+                            if (fr >= F0 && p < own_hi) emit(a, c, p, *r, steady ? normtab[j] : norm_generic(a, p));
+                            *r = pre[i];
+                        }
+                    }
+                } else {
+                    for (long j = t; j < hop; j += CTA) {
+                        const long p = fr * hop + j;
+                        float *r = ring + (p & (N - 1));
+                        if (fr >= F0 && p < own_hi) emit(a, c, p, *r, steady ? normtab[j] : norm_generic(a, p));
+                        *r = recycled_init(p + N);
+                    }
+                }
+            };
+
+            int par = 0;
+            for (long f = fs; f < Fend; f++) {
+                // initial values of the slots recycled in this iteration: loaded now, used after sync A
+                float pre[PRE];
+                if (use_pre && f > fs) {
+#pragma unroll
+                    for (int i = 0; i < PRE; i++) {
+                        const long j = t + (long)i * CTA;
+                        pre[i] = j < hop ? recycled_init((f - 1) * hop + j + N) : 0.0f;
+                    }
+                }
                 mbar_wait(mbar, phase);
                 phase ^= 1;
                 float2 x[EPT];
@@ -125,74 +193,65 @@ struct IstftFused {
                 for (int u = 0; u < P0::U; u++)
 #pragma unroll
                     for (int q = 0; q < P0::R; q++)
-                        x[u * P0::R + q] = pre_conj<true>(
-                            reinterpret_cast<const float2 *>(stage)[slot * N + P0::src_index(t, u, q)]);
+                        x[u * P0::R + q] =
+                            pre_conj<true>(reinterpret_cast<const float2 *>(stage)[P0::src_index(t, u, q)]);
                 P0::compute(x, tw0.v);
                 float2 *b = par ? buf1 : buf0;
                 par ^= 1;
                 H::template store_smem<P0>(b, t, x);
-                __syncthreads();
-                if (tid == 0 && f + TPC < Fend) { // stage consumed: prefetch the run's next group
-                    const long nf = Fend - (f + TPC) < TPC ? Fend - (f + TPC) : TPC;
-                    mbar_expect_tx(mbar, (unsigned)(nf * N * 8));
-                    bulk_copy_g2s(stage, fr_base + (f + TPC) * N, (unsigned)(nf * N * 8), mbar);
+                __syncthreads(); // A
+                if (t == 0 && f + 1 < Fend) { // stage consumed: prefetch the run's next frame
+                    mbar_expect_tx(mbar, (unsigned)(N * 8));
+                    bulk_copy_g2s(stage, fr_base + (f + 1) * N, (unsigned)(N * 8), mbar);
                 }
+                if (f > fs) finalize_region(f - 1, pre);
                 H::template load_smem<P1>(b, t, x);
                 P1::compute(x, tw1);
                 b = par ? buf1 : buf0;
                 par ^= 1;
                 H::template store_smem<P1>(b, t, x);
-                __syncthreads();
+                __syncthreads(); // B
                 H::template load_smem<P2>(b, t, x);
                 P2::compute(x, tw2);
-
-                // ordered overlap-add: one frame of the group at a time
-#pragma unroll 1
-                for (int sl = 0; sl < TPC; sl++) {
-                    const long fr = f + sl;
-                    if (fr >= Fend) break;
-                    if (slot == sl) {
+                // ordered overlap-add of frame f: ifft = conj, re*scale (src/fft.rs:1163-1172),
+                // then frame.re * window (src/stft.rs:144)
 #pragma unroll
-                        for (int w = 0; w < P2::R; w++) {
-                            const long p = fr * hop + P2::dst_index(t, 0, w);
-                            // ifft: conj, re*scale (src/fft.rs:1163-1172); then frame.re * window (src/stft.rs:144)
-                            const float v = mul_rn(mul_rn(x[w].x, a.scale), wv[w]);
-                            float *r = ring + (p & (N - 1));
-                            *r = add_rn(*r, v);
-                        }
-                    }
-                    __syncthreads();
-                    // samples [fr*hop, (fr+1)*hop) are complete: write them, recycle their slots
-                    for (long j = tid; j < hop; j += P::CTA) {
-                        const long p = fr * hop + j;
-                        float *r = ring + (p & (N - 1));
-                        if (fr >= F0 && p < own_hi) finalize(a, c, p, *r);
-                        const long p2 = p + N;
-                        *r = (p2 >= own_lo && p2 < own_hi) ? out0[p2] : 0.0f;
-                    }
-                    __syncthreads();
+                for (int w = 0; w < P2::R; w++) {
+                    const long p = f * hop + P2::dst_index(t, 0, w);
+                    const float v = mul_rn(mul_rn(x[w].x, a.scale), wv[w]);
+                    float *r = ring + (p & (N - 1));
+                    *r = add_rn(*r, v);
+                }
+            }
+            __syncthreads();
+            if (Fend > fs) {
+                const long fr = Fend - 1;
+                const bool steady = fr >= halo;
+                for (long j = t; j < hop; j += CTA) {
+                    const long p = fr * hop + j;
+                    if (fr >= F0 && p < own_hi) emit(a, c, p, ring[p & (N - 1)], steady ? normtab[j] : norm_generic(a, p));
                 }
             }
             // the channel's last run also owns everything after its last frame's hop
             if (Fend == nfe) {
                 const long covered = nfe > 0 ? (nfe - 1) * hop + N : 0;
-                for (long p = Fend * hop + tid; p < a.out_len; p += P::CTA) {
+                for (long p = Fend * hop + t; p < a.out_len; p += CTA) {
                     if (p < covered) {
-                        finalize(a, c, p, ring[p & (N - 1)]);
+                        emit(a, c, p, ring[p & (N - 1)], norm_generic(a, p));
                     } else { // no frame reaches this sample
                         if (a.zero_uncovered) a.output[c * a.out_len + p] = 0.0f;
                         if (a.norm) a.norm[c * a.out_len + p] = 0.0f;
                     }
                 }
             }
-            __syncthreads();
+            __syncthreads(); // the ring is re-initialised by the next run
         }
     }
 };
 
 #ifdef __CUDACC__
 template <int L, bool EXACT>
-__global__ void __launch_bounds__(Plan<L>::CTA, 2)
+__global__ void __launch_bounds__((IstftFused<L, EXACT>::CTA), (IstftFused<L, EXACT>::MIN_BLOCKS))
     istft_fused_kernel(const __grid_constant__ IstftFusedArgs a, const __grid_constant__ Tw0 tw0,
                        const float2 *__restrict__ table)
 {

@@ -13,11 +13,17 @@ cudaError_t launch_one(const IstftFusedArgs &f, const LaunchArgs &a)
     auto kern = istft_fused_kernel<L, EXACT>;
     static PerDevice occ_pd;
     int &occ = occ_pd.get();
-    if (occ == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+    const int smem = K::smem_bytes(f.hop);
+    static PerDevice smem_pd; // largest dynamic shared memory size opted into so far
+    int &smem_set = smem_pd.get();
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, Plan<L>::CTA, K::SMEM_BYTES);
+        smem_set = smem;
+    }
+    {
+        int o = 0; // occupancy depends on hop through the shared-memory size
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, K::CTA, smem);
         if (e != cudaSuccess) return e;
         occ = o > 0 ? o : 1;
     }
@@ -27,7 +33,7 @@ cudaError_t launch_one(const IstftFusedArgs &f, const LaunchArgs &a)
     long cap = a.max_ctas > 0 ? a.max_ctas : (long)occ * a.num_sms;
     int grid = (int)(runs < cap ? runs : cap);
     if (grid <= 0) return cudaSuccess;
-    kern<<<grid, Plan<L>::CTA, K::SMEM_BYTES, a.stream>>>(f, a.tw0, a.table);
+    kern<<<grid, K::CTA, smem, a.stream>>>(f, a.tw0, a.table);
     return cudaGetLastError();
 }
 

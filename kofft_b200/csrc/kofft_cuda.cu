@@ -83,7 +83,7 @@ struct kofft_cuda_ctx {
     bool use_tma = true; // TMA-staged input prefetch where alignment allows
     bool large_fused = true; // N > 16384: one persistent thread-block-cluster kernel
     bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
-    int istft_run_frames = 64;
+    int istft_run_frames = 128;
     // host-pointer batch entry points: the batch is cut into chunks that flow through three
     // streams (H2D copy engine, SMs, D2H copy engine) so both PCIe directions and the kernels overlap
     size_t host_chunk_bytes = size_t(32) << 20; // 0 = one copy in, one launch, one copy out

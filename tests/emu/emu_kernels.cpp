@@ -195,10 +195,10 @@ static int run_istft(const IstftFusedArgs &a, const float *table, int grid)
 {
     using K = IstftFused<L, EXACT>;
     Tw0 tw0 = make_tw0(L, Plan<L>::R0, table);
-    std::vector<float2> smem((K::SMEM_BYTES + 256) / 8);
+    std::vector<float2> smem((K::smem_bytes(a.hop) + 256) / 8);
     float2 *sm = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
     const float2 *tab = reinterpret_cast<const float2 *>(table);
-    cuda_emu::launch(grid, Plan<L>::CTA, [&] { K::run(a, tw0, tab, sm); });
+    cuda_emu::launch(grid, K::CTA, [&] { K::run(a, tw0, tab, sm); });
     return 0;
 }
 
