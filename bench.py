@@ -265,7 +265,8 @@ def run_gpu(args) -> None:
     nbytes = ROWS_PER_GPU * N * 8
     e2e = {"value": FLOPS_PER_TRANSFORM * ROWS_PER_GPU * n_gpus / e2e_s / 1e9, "unit": UNIT,
            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_s * 1e3,
-           "steps": e2e_steps, "api": "kofft_cuda_fft_batch_host_f32 (CudaFftImpl.fft_batch on pinned host rows)"}
+           "steps": e2e_steps, "api": "kofft_cuda_fft_batch_host_f32 (CudaFftImpl.fft_batch on pinned host rows; "
+                                      "32 MiB chunks pipelined over H2D / kernel / D2H streams)"}
     del host, h
 
     # ---- extra: STFT (configs[3] shape) and FAST-mode C2C, after the headline region ------------
@@ -305,9 +306,9 @@ def run_gpu(args) -> None:
         algo = (4 * rn + 8 * (rn // 2 + 1)) * rb
         extra["rfft_65536x16384"] = {"ms": ms, "gflops_nominal": 2.5 * rn * 16 * rb / ms / 1e6, "hbm_gbs": algo / ms / 1e6,
                                      "frac_of_measured_peak": algo / ms / 1e6 / peak,
-                                     "note": "one persistent thread-block-cluster kernel (column pass, cluster barrier, "
-                                             "row pass + twist), L2-resident intermediate"}
-        fft.ctx.set_cluster_fusion(False)
+                                     "note": "column pass + row pass with fused Hermitian twist, two kernels per "
+                                             "256 MB batch chunk (default path)"}
+        fft.ctx.set_cluster_fusion(True)
         fft.rfft_batch(xr, out=yr)
         torch.cuda.synchronize()
         e0.record()
@@ -315,10 +316,11 @@ def run_gpu(args) -> None:
             fft.rfft_batch(xr, out=yr)
         e1.record()
         torch.cuda.synchronize()
-        fft.ctx.set_cluster_fusion(True)
+        fft.ctx.set_cluster_fusion(False)
         ms2 = e0.elapsed_time(e1) / reps
-        extra["rfft_65536x16384_two_kernel_path"] = {"ms": ms2, "hbm_gbs": algo / ms2 / 1e6,
-                                                     "frac_of_measured_peak": algo / ms2 / 1e6 / peak}
+        extra["rfft_65536x16384_cluster_kernel_path"] = {
+            "ms": ms2, "hbm_gbs": algo / ms2 / 1e6, "frac_of_measured_peak": algo / ms2 / 1e6 / peak,
+            "note": "one persistent thread-block-cluster kernel (column pass, cluster barrier, row pass + twist)"}
         del xr, yr
         torch.cuda.empty_cache()
         free, _ = torch.cuda.mem_get_info()
@@ -379,6 +381,35 @@ def run_gpu(args) -> None:
         del sig, frames, out
     except Exception as e:  # extras never invalidate the headline line
         extra["error"] = f"{type(e).__name__}: {e}"
+
+    # ---- extra (N > 1): ONE transform sharded over the ranks (BASELINE configs[4] shape: 2^27 points per GPU) --
+    if world > 1 and (world & (world - 1)) == 0:
+        try:
+            from kofft_b200 import dist as KD
+
+            torch.cuda.empty_cache()
+            log2n = 27 + int(math.log2(world))
+            dfft = KD.DistFft(fft.ctx, rank, world, log2n)
+            dfft.connect()
+            shard = (1 << log2n) // world
+            xs = torch.view_as_complex(torch.rand((shard, 2), generator=g, device=dev) * 2 - 1).contiguous()
+            os_ = torch.empty_like(xs)
+            walls = []
+            for it in range(5):
+                barrier()
+                t0 = time.perf_counter()
+                dfft.transform(xs, out=os_, natural_order=True)
+                if it >= 2:
+                    walls.append(time.perf_counter() - t0)
+            w = max_over_ranks(statistics.median(walls))
+            extra["dist_c2c_one_transform"] = {
+                "log2n": log2n, "points_per_gpu": shard, "ms": w * 1e3, "gflops": 5.0 * (1 << log2n) * log2n / w / 1e9,
+                "note": "four-step split; all-to-all exchanges are P2P stores issued by the transpose-scatter kernels "
+                        "(CUDA IPC over NVLink), host barriers between phases; natural-order output (3 exchanges); "
+                        "validated against f64, no kofft reference at this size (SURVEY 0.5)"}
+            dfft.close()
+        except Exception as e:
+            extra["dist_error"] = f"{type(e).__name__}: {e}"
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ------------------------
     cpu = None

@@ -68,8 +68,9 @@ int kofft_cuda_set_tma_staging(kofft_cuda_ctx *ctx, int enable);
  * window + ordered overlap-add + normalisation); run_frames > 0 sets the frames a CTA owns per
  * run (default 128).  Disabled or out of range -> two kernels with an f32 intermediate. */
 int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames);
-/* N > 16384: enable (default) / disable the single persistent thread-block-cluster kernel;
- * when disabled (or unavailable) two kernels per L2-sized batch chunk are used instead */
+/* N > 16384: two kernels (column pass, row pass) per 256 MB batch chunk by default; enable != 0
+ * selects the single persistent thread-block-cluster kernel instead (measured slower, kept for
+ * comparison) */
 int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable);
 /* Host-pointer batch entry points (fft_batch_host, rfft_batch_host, irfft_batch_host): batches
  * larger than chunk_bytes are cut into chunks of about chunk_bytes that flow through three

@@ -49,6 +49,14 @@ KD void bulk_copy_g2s(void *dst_smem, const void *src, unsigned bytes, unsigned 
                  : "memory");
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, L2 only), grouped completion per thread
+KD void cp_async16(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+KD void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+KD void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // thread-block cluster barrier with release/acquire semantics (all threads of all CTAs)
 KD void cluster_sync()
 {
@@ -63,6 +71,14 @@ KD unsigned cluster_ctarank()
 }
 
 #elif defined(KOFFT_EMU)
+
+inline void cp_async16(void *dst_smem, const void *src)
+{
+    if ((reinterpret_cast<uintptr_t>(dst_smem) & 15) || (reinterpret_cast<uintptr_t>(src) & 15)) abort();
+    memcpy(dst_smem, src, 16);
+}
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
 
 inline void cluster_sync() { cuda_emu::cluster_sync(); }
 inline unsigned cluster_ctarank() { return cuda_emu::cluster_rank(); }

@@ -74,6 +74,9 @@ struct IoC2C {
     {
         return pre_conj<INV>(reinterpret_cast<const float2 *>(stage)[slot * n + i]);
     }
+    // large-N column pass: raw row pointer for asynchronous tile copies + the load-side transform
+    KHD const float2 *row_ptr(long row) const { return in + row * n; }
+    KHD float2 from_raw(float2 v) const { return pre_conj<INV>(v); }
     KHD bool row_full(int) const { return true; }
 };
 
@@ -257,9 +260,16 @@ struct IoRfft {
     {
         return reinterpret_cast<const float2 *>(stage)[slot * m + i];
     }
+    KHD const float2 *row_ptr(long row) const { return in + row * m; }
+    KHD float2 from_raw(float2 v) const { return v; }
     KHD bool row_full(int) const { return true; }
     // Hermitian twist of bin k (src/rfft.rs:450-463): a = Y[k], ym = Y[m-k] (for k = 0: a = Y[0])
     KHD void twist_store(long row, long k, float2 a, float2 ym) const
+    {
+        twist_store_tw(row, k, a, ym, k == 0 ? make_float2(1.0f, 0.0f) : KOFFT_LDG(rtw + k));
+    }
+    // same, with the table entry T'[k] supplied by the caller
+    KHD void twist_store_tw(long row, long k, float2 a, float2 ym, float2 tw) const
     {
         float2 *o = out + row * (m + 1);
         if (k == 0) {
@@ -269,7 +279,7 @@ struct IoRfft {
         }
         float2 b = make_float2(ym.x, -ym.y);
         float2 sum = add2(a, b), diff = sub2(a, b);
-        float2 t = cmul<EXACT>(KOFFT_LDG(rtw + k), diff);
+        float2 t = cmul<EXACT>(tw, diff);
         float2 temp = make_float2(add_rn(sum.x, t.y), sub_rn(sum.y, t.x)); // sum + (t.im, -t.re)
         o[k] = make_float2(mul_rn(temp.x, 0.5f), mul_rn(temp.y, 0.5f));
     }
@@ -329,11 +339,25 @@ template <class IO>
 struct IoTraits {
     static constexpr bool kRealInput = false;
     static constexpr int kMinCta = 256;
+    static constexpr bool kRowPtr = false; // has row_ptr()/from_raw(): rows are plain contiguous float2
+};
+template <bool INV>
+struct IoTraits<IoC2C<INV>> {
+    static constexpr bool kRealInput = false;
+    static constexpr int kMinCta = 256;
+    static constexpr bool kRowPtr = true;
+};
+template <bool EXACT>
+struct IoTraits<IoRfft<EXACT>> {
+    static constexpr bool kRealInput = false;
+    static constexpr int kMinCta = 256;
+    static constexpr bool kRowPtr = true;
 };
 template <>
 struct IoTraits<IoStft> {
     static constexpr bool kRealInput = KOFFT_STFT_REAL != 0;
     static constexpr int kMinCta = KOFFT_STFT_MIN_CTA;
+    static constexpr bool kRowPtr = false;
 };
 
 // ------------------------------------------------------------------------------------------

@@ -38,6 +38,8 @@ struct ColPass {
     static constexpr int COLS = 16;            // columns per CTA tile
     static constexpr int RS = P::PADN + 1;     // odd region stride: column-fastest threads hit distinct banks
     static constexpr int SMEM_BYTES = 2 * COLS * RS * 8;
+    static constexpr int STAGE_BYTES = 256 * COLS * 8; // next tile's raw input: [256 rows][16 columns]
+    static constexpr int SMEM_BYTES_STAGED = SMEM_BYTES + STAGE_BYTES;
     static_assert(P::T == 16 && P::CTA == 256 && P::TPC == COLS, "tile shape");
 
     // one tile: 16 adjacent columns starting at j0 of transform `row` (io) -> scratch_row.
@@ -63,13 +65,18 @@ struct ColPass {
 
     // n = 2^L elements per transform, lsub = L - 8, tiles = batch * (2^lsub / 16)
     // row0: index of the chunk's first transform in the caller's batch (scratch is chunk-local)
+    // STAGED (plain contiguous rows only): the CTA's next tile -- 256 segments of 128 bytes -- is
+    // fetched with 16-byte asynchronous copies (cp.async / LDGSTS) while the current tile is transformed.
+    template <bool STAGED = false>
     static KD void run(const IO &io, const Tw0 &tw0, const float2 *__restrict__ table, int lsub, long tiles,
                        long row0, float2 *__restrict__ scratch, float2 *smem)
     {
         const int tid = threadIdx.x;
         const int slot = tid & (COLS - 1); // column within the tile (fastest)
         const int t = tid >> 4;            // thread within the column's 256-point transform
-        float2 *buf0 = smem + slot * RS;
+        float2 *stage = smem;
+        float2 *xch = STAGED ? smem + STAGE_BYTES / 8 : smem;
+        float2 *buf0 = xch + slot * RS;
         float2 *buf1 = buf0 + COLS * RS;
         int par = 0;
         TwMap map;
@@ -78,11 +85,50 @@ struct ColPass {
         P1::load_tw(table, t, tw1, map);
         const int ltiles = lsub - 4; // log2 tiles per transform
         const long n = 1L << (LARGE_S1 + lsub);
-        for (long tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
-            const long b = tl >> ltiles;
-            const long j0 = (tl & ((1L << ltiles) - 1)) << 4;
-            tile(io, tw0, tw1, lsub, row0 + b, j0, scratch + b * n, par ? buf1 : buf0, t, slot);
-            par ^= 1;
+        if constexpr (STAGED && IoTraits<IO>::kRowPtr) {
+            // thread i copies 16-byte piece (i & 7) of rows (i >> 3) + 32 m, m = 0..7
+            auto prefetch = [&](long tl) {
+                const long b = tl >> ltiles;
+                const long j0 = (tl & ((1L << ltiles) - 1)) << 4;
+                const float2 *src = io.row_ptr(row0 + b) + j0 + 2 * (tid & 7);
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    const int r = (tid >> 3) + 32 * m;
+                    cp_async16(stage + r * COLS + 2 * (tid & 7), src + ((long)r << lsub));
+                }
+                cp_async_commit();
+            };
+            if ((long)blockIdx.x < tiles) prefetch(blockIdx.x);
+            for (long tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+                const long b = tl >> ltiles;
+                const long j0 = (tl & ((1L << ltiles) - 1)) << 4;
+                cp_async_wait_all();
+                __syncthreads(); // every thread's pieces of this tile have landed
+                float2 *bf = par ? buf1 : buf0;
+                par ^= 1;
+                const long j = j0 + slot;
+                float2 x[EPT];
+#pragma unroll
+                for (int q = 0; q < P0::R; q++) x[q] = io.from_raw(stage[P0::src_index(t, 0, q) * COLS + slot]);
+                P0::compute(x, tw0.v);
+#pragma unroll
+                for (int w = 0; w < P0::R; w++) bf[P0::dst_pad(P0::dst_base(t, 0), w)] = x[w];
+                __syncthreads(); // exchange; also: the stage has been consumed by everyone
+                if (tl + gridDim.x < tiles) prefetch(tl + gridDim.x);
+#pragma unroll
+                for (int q = 0; q < P1::R; q++) x[q] = bf[P1::src_pad(P1::src_base(t, 0), q)];
+                P1::compute(x, tw1);
+                float2 *o = scratch + b * n + j;
+#pragma unroll
+                for (int w = 0; w < P1::R; w++) o[(long)P1::dst_index(t, 0, w) << lsub] = x[w];
+            }
+        } else {
+            for (long tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+                const long b = tl >> ltiles;
+                const long j0 = (tl & ((1L << ltiles) - 1)) << 4;
+                tile(io, tw0, tw1, lsub, row0 + b, j0, scratch + b * n, par ? buf1 : buf0, t, slot);
+                par ^= 1;
+            }
         }
     }
 };
@@ -102,8 +148,25 @@ struct RowPass {
     static constexpr int TPC = P::TPC;          // sub-transforms (values of k) per CTA: 32 or 16
     static constexpr int NKB = 256 / TPC;       // k-blocks per transform
     static constexpr int RS = P::PADN + 1;      // odd region stride for the transposed read-back
-    static constexpr int SMEM_BYTES = 2 * TPC * RS * 8;
+    // Exchange regions: slot s starts at slot_off(s).  Sub-transforms of 128 points use 8 threads, so
+    // a half-warp spans two slots: threads are mapped so that these are slots s and s + 16, whose
+    // regions differ by 8 (mod 16) eight-byte banks -> the per-slot padded layout stays conflict-free
+    // across the pair, while 16 consecutive slots (the transposed read-back) still differ by the odd RS.
+    static constexpr bool PAIRED = P::T < 16;
+    static_assert(P::T == 8 || P::T == 16, "row pass sub-transforms are 128 or 256 points");
+    static KHD int slot_of(int tid) { return PAIRED ? (tid >> 4) + 16 * ((tid >> 3) & 1) : tid / P::T; }
+    static KHD int slot_off(int s) { return s * RS + (PAIRED ? 8 * (s >> 4) : 0); }
+    static constexpr int BUF = TPC * RS + 16;       // float2 per exchange buffer
+    static constexpr int NBUFS = EPI == ROW_TWIST ? 3 : 2; // twist: + the CTA's rfft twiddles, same layout
+    static constexpr int SMEM_BYTES = NBUFS * BUF * 8;
+    static constexpr int STAGE_BYTES = TPC * NB * 8; // next tile's TPC sub-transforms, unpadded
+    static constexpr int SMEM_BYTES_STAGED = SMEM_BYTES + STAGE_BYTES;
     static constexpr int HALF = TPC / 2;
+
+    // STAGED: where the slot's sub-transform sits in the stage.  Plain store: slot order.  Twist:
+    // the mirrored half {256 - HALF kb - i} is one ascending run of k, so it is staged ascending
+    // (one bulk copy) and read back reversed; k = 128 of block 0 takes the last stage row.
+    static KHD int stage_row(int slot) { return (EPI == ROW_TWIST && slot >= HALF) ? TPC - 1 - (slot - HALF) : slot; }
 
     // which k the CTA's slot handles in block kb
     static KHD int kmap(int kb, int slot)
@@ -125,22 +188,33 @@ struct RowPass {
     // one tile: the TPC sub-transforms of k-block kb of one transform, read from scratch_row
     // (LDCG: the intermediate was written by other CTAs), stored / twisted through io as `row`.
     // bfa/bfb: this thread's two exchange regions, alla/allb: the same buffers seen CTA-wide.
+    // staged_in != nullptr: the slot's sub-transform is already in shared memory (TMA bulk copy);
+    // after_sync(): called by every thread right after the first barrier (the stage is free again)
+    template <class AfterSync>
     static KD void tile(const IO &io, const float2 *tw0, const float2 *tw1, long row, int kb, int k,
                         const float2 *__restrict__ scratch_row, float2 *bfa, float2 *bfb, const float2 *allb, int t,
-                        int tid)
+                        int tid, const float2 *staged_in, AfterSync after_sync, const float2 *rtwb = nullptr)
     {
-        const float2 *in = scratch_row + (long)k * NB;
         float2 x[EPT];
+        if (staged_in) {
 #pragma unroll
-        for (int u = 0; u < P0::U; u++)
+            for (int u = 0; u < P0::U; u++)
 #pragma unroll
-            for (int q = 0; q < P0::R; q++) x[u * P0::R + q] = KOFFT_LDCG(in + P0::src_index(t, u, q));
+                for (int q = 0; q < P0::R; q++) x[u * P0::R + q] = staged_in[P0::src_index(t, u, q)];
+        } else {
+            const float2 *in = scratch_row + (long)k * NB;
+#pragma unroll
+            for (int u = 0; u < P0::U; u++)
+#pragma unroll
+                for (int q = 0; q < P0::R; q++) x[u * P0::R + q] = KOFFT_LDCG(in + P0::src_index(t, u, q));
+        }
         P0::compute(x, tw0);
 #pragma unroll
         for (int u = 0; u < P0::U; u++)
 #pragma unroll
             for (int w = 0; w < P0::R; w++) bfa[P0::dst_pad(P0::dst_base(t, u), w)] = x[u * P0::R + w];
         __syncthreads();
+        after_sync();
 #pragma unroll
         for (int q = 0; q < P1::R; q++) x[q] = bfa[P1::src_pad(P1::src_base(t, 0), q)];
         P1::compute(x, tw1);
@@ -153,33 +227,80 @@ struct RowPass {
             const int flat = e * P::CTA + tid;
             const int s2 = flat % TPC, c = flat / TPC;
             const long K = kmap(kb, s2) + ((long)c << LARGE_S1);
-            const float2 a = allb[s2 * RS + pad(c)];
+            const float2 a = allb[slot_off(s2) + pad(c)];
             if constexpr (EPI == ROW_TWIST) {
                 const int kk = kmap(kb, s2);
                 float2 ym;
                 if (kk == 0)
-                    ym = c == 0 ? a : allb[s2 * RS + pad(NB - c)]; // m - K = 256 (NB - c)
+                    ym = c == 0 ? a : allb[slot_off(s2) + pad(NB - c)]; // m - K = 256 (NB - c)
                 else
-                    ym = allb[mirror_slot(kb, s2) * RS + pad(NB - 1 - c)];
-                io.twist_store(row, K, a, ym);
+                    ym = allb[slot_off(mirror_slot(kb, s2)) + pad(NB - 1 - c)];
+                io.twist_store_tw(row, K, a, ym, rtwb[slot_off(s2) + pad(c)]);
             } else {
                 io.store(row, (int)K, a);
             }
         }
     }
 
+    // the CTA's share of the rfft table T' (src/rfft.rs:172-183), laid out like the transposed bins:
+    // a CTA keeps its k-block, so this is loaded once per CTA, not once per element per tile
+    static KD void load_rtw(const IO &io, int kb, int tid, float2 *rtwb)
+    {
+        if constexpr (EPI == ROW_TWIST) {
+#pragma unroll
+            for (int e = 0; e < EPT; e++) {
+                const int flat = e * P::CTA + tid;
+                const int s2 = flat % TPC, c = flat / TPC;
+                rtwb[slot_off(s2) + pad(c)] = KOFFT_LDG(io.rtw + kmap(kb, s2) + ((long)c << LARGE_S1));
+            }
+        }
+    }
+
     // tiles = batch * NKB; the grid is a multiple of NKB so a CTA keeps its k-block (and with it
     // its twiddles, which live in registers) for every tile it processes.
+    // one thread: bulk copies of the TPC sub-transforms of k-block kb of one transform into the stage
+    static KD void stage_issue(const float2 *scratch_row, int kb, float2 *stage, unsigned long long *bar)
+    {
+        mbar_expect_tx(bar, (unsigned)STAGE_BYTES);
+        if (EPI == ROW_TWIST) {
+            bulk_copy_g2s(stage, scratch_row + (long)(HALF * kb) * NB, HALF * NB * 8, bar);
+            if (kb == 0) { // k = 128, then 255 .. 257 - HALF (ascending: 257 - HALF .. 255)
+                bulk_copy_g2s(stage + (long)HALF * NB, scratch_row + (long)(257 - HALF) * NB, (HALF - 1) * NB * 8, bar);
+                bulk_copy_g2s(stage + (long)(TPC - 1) * NB, scratch_row + 128L * NB, NB * 8, bar);
+            } else {
+                bulk_copy_g2s(stage + (long)HALF * NB, scratch_row + (long)(257 - HALF * kb - HALF) * NB, HALF * NB * 8, bar);
+            }
+        } else {
+            bulk_copy_g2s(stage, scratch_row + (long)(kb * TPC) * NB, STAGE_BYTES, bar);
+        }
+    }
+
+    // STAGED: the CTA's next tile is fetched from the (L2-resident) intermediate with TMA bulk
+    // copies while the current one is transformed, twisted and stored.
+    template <bool STAGED = false>
     static KD void run(const IO &io, const float2 *__restrict__ table, long tiles, long row0,
-                       const float2 *__restrict__ scratch, float2 *smem)
+                       const float2 *__restrict__ scratch, float2 *smem_all)
     {
         const int tid = threadIdx.x;
-        const int slot = tid / P::T;
-        const int t = tid - slot * P::T;
+        const int slot = slot_of(tid);
+        const int t = tid & (P::T - 1);
         const int kb = blockIdx.x % NKB;
         const int k = kmap(kb, slot);
-        float2 *buf0 = smem + slot * RS;
-        float2 *buf1 = buf0 + TPC * RS;
+        float2 *stage = smem_all;
+        float2 *smem = STAGED ? smem_all + STAGE_BYTES / 8 : smem_all;
+        __shared__ __align__(8) unsigned long long mbar;
+        unsigned phase = 0;
+        if constexpr (STAGED) {
+            if (tid == 0) {
+                mbar_init(&mbar, 1);
+                fence_mbar_init();
+            }
+            __syncthreads();
+        }
+        float2 *buf0 = smem + slot_off(slot);
+        float2 *buf1 = buf0 + BUF;
+        const float2 *rtwb = smem + 2 * BUF;
+        load_rtw(io, kb, tid, smem + 2 * BUF); // made visible by the first tile's barriers
         TwMap map;
         map.k0 = k;
         map.sh1 = LARGE_S1;
@@ -187,11 +308,25 @@ struct RowPass {
         P0::load_tw(table, t, tw0, map);
         P1::load_tw(table, t, tw1, map);
         const long n = (long)NB << LARGE_S1;
+        if constexpr (STAGED) {
+            if (tid == 0 && (long)blockIdx.x < tiles) stage_issue(scratch + (blockIdx.x / NKB) * n, kb, stage, &mbar);
+        }
         for (long tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
             const long b = tl / NKB;
             // buffer A of this tile was last read before the previous tile's second barrier and
             // buffer B before this tile's first barrier, so two buffers suffice
-            tile(io, tw0, tw1, row0 + b, kb, k, scratch + b * n, buf0, buf1, smem + TPC * RS, t, tid);
+            if constexpr (STAGED) {
+                mbar_wait(&mbar, phase);
+                phase ^= 1;
+                const long nxt = tl + gridDim.x;
+                tile(io, tw0, tw1, row0 + b, kb, k, scratch + b * n, buf0, buf1, smem + BUF, t, tid,
+                     stage + (long)stage_row(slot) * NB, [&] {
+                         if (tid == 0 && nxt < tiles) stage_issue(scratch + (nxt / NKB) * n, kb, stage, &mbar);
+                     }, rtwb);
+            } else {
+                tile(io, tw0, tw1, row0 + b, kb, k, scratch + b * n, buf0, buf1, smem + BUF, t, tid,
+                     (const float2 *)nullptr, [] {}, rtwb);
+            }
             __syncthreads();
         }
     }
@@ -234,7 +369,7 @@ struct LargeFused {
             for (int i = 0; i < C::P1::NTW; i++) twA[tid * 16 + i] = tmp[i];
         }
         // pass B (sub-transform-major mapping); k-block == cluster rank, twiddles in registers
-        const int slotB = tid / R::P::T, tB = tid - slotB * R::P::T;
+        const int slotB = R::slot_of(tid), tB = tid & (R::P::T - 1);
         const int kb = rank, k = R::kmap(kb, slotB);
         TwMap mapB;
         mapB.k0 = k;
@@ -245,35 +380,36 @@ struct LargeFused {
         __syncthreads();
 
         float2 *bufA0 = smem + slotA * C::RS;
-        float2 *bufB0 = smem + slotB * R::RS, *bufB1 = bufB0 + R::TPC * R::RS;
+        float2 *bufB0 = smem + R::slot_off(slotB), *bufB1 = bufB0 + R::BUF;
+        R::load_rtw(io, kb, tid, smem + 2 * R::BUF); // beyond both passes' exchange regions
         int it = 0;
         for (long b = cluster_id; b < rows; b += nclusters, it ^= 1) {
             float2 *sc = scratch + (cluster_id * 2 + it) * n;
             C::tile(io, tw0, twA + tA * 16, LB, b, (long)rank * C::COLS, sc, bufA0, tA, slotA);
             cluster_sync(); // every column tile of this transform is in `sc` (also a CTA barrier)
-            R::tile(io, twB0, twB1, b, kb, k, sc, bufB0, bufB1, smem + R::TPC * R::RS, tB, tid);
+            R::tile(io, twB0, twB1, b, kb, k, sc, bufB0, bufB1, smem + R::BUF, tB, tid, (const float2 *)nullptr, [] {}, smem + 2 * R::BUF);
             __syncthreads(); // smem is reused by the next transform's column tile
         }
     }
 };
 
 #ifdef __CUDACC__
-template <bool EXACT, class IO>
+template <bool EXACT, class IO, bool STAGED>
 __global__ void __launch_bounds__(256, 2)
     colpass_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0 tw0, const float2 *__restrict__ table,
                    int lsub, long tiles, long row0, float2 *__restrict__ scratch)
 {
     extern __shared__ __align__(128) float2 smem[];
-    ColPass<EXACT, IO>::run(io, tw0, table, lsub, tiles, row0, scratch, smem);
+    ColPass<EXACT, IO>::template run<STAGED>(io, tw0, table, lsub, tiles, row0, scratch, smem);
 }
 
-template <int LB, bool EXACT, class IO, int EPI>
+template <int LB, bool EXACT, class IO, int EPI, bool STAGED>
 __global__ void __launch_bounds__(256, 2)
     rowpass_kernel(const __grid_constant__ IO io, const float2 *__restrict__ table, long tiles, long row0,
                    const float2 *__restrict__ scratch)
 {
     extern __shared__ __align__(128) float2 smem[];
-    RowPass<LB, EXACT, IO, EPI>::run(io, table, tiles, row0, scratch, smem);
+    RowPass<LB, EXACT, IO, EPI>::template run<STAGED>(io, table, tiles, row0, scratch, smem);
 }
 template <int LB, bool EXACT, class IO, int EPI>
 __global__ void __launch_bounds__(256, 2)

@@ -23,37 +23,63 @@ cudaError_t prep(K kern, int smem, int threads, int *occ)
     return cudaSuccess;
 }
 
-template <bool EXACT, class IO>
-cudaError_t launch_col(const IO &io, const LaunchArgs &a, const LargeArgs &g)
+template <bool EXACT, class IO, bool STAGED>
+cudaError_t launch_col_v(const IO &io, const LaunchArgs &a, const LargeArgs &g)
 {
     using C = ColPass<EXACT, IO>;
-    auto kern = colpass_kernel<EXACT, IO>;
+    constexpr int smem = STAGED ? C::SMEM_BYTES_STAGED : C::SMEM_BYTES;
+    auto kern = colpass_kernel<EXACT, IO, STAGED>;
     static PerDevice occ_pd;
     int &occ = occ_pd.get();
-    cudaError_t e = prep(kern, C::SMEM_BYTES, 256, &occ);
+    cudaError_t e = prep(kern, smem, 256, &occ);
     if (e != cudaSuccess) return e;
     const long tiles = g.chunk_rows << (g.lsub - 4);
     long cap = a.max_ctas > 0 ? a.max_ctas : (long)occ * a.num_sms;
     int grid = (int)(tiles < cap ? tiles : cap);
-    kern<<<grid, 256, C::SMEM_BYTES, a.stream>>>(io, a.tw0, a.table, g.lsub, tiles, g.row0, g.scratch);
+    kern<<<grid, 256, smem, a.stream>>>(io, a.tw0, a.table, g.lsub, tiles, g.row0, g.scratch);
     return cudaGetLastError();
 }
+
+// a.staged: the host verified 16-byte alignment of the rows (asynchronous 16-byte copies)
+template <bool EXACT, class IO>
+cudaError_t launch_col(const IO &io, const LaunchArgs &a, const LargeArgs &g)
+{
+    if constexpr (IoTraits<IO>::kRowPtr) {
+        if (a.staged) return launch_col_v<EXACT, IO, true>(io, a, g);
+    }
+    return launch_col_v<EXACT, IO, false>(io, a, g);
+}
+
+template <int LB, bool EXACT, class IO, int EPI, bool STAGED>
+cudaError_t launch_row_v(const IO &io, const LaunchArgs &a, const LargeArgs &g);
 
 template <int LB, bool EXACT, class IO, int EPI>
 cudaError_t launch_row(const IO &io, const LaunchArgs &a, const LargeArgs &g)
 {
+    // the intermediate is the library's own 16-byte aligned scratch: staging is always possible.  The
+    // twist variant spends its shared memory on the CTA's rfft twiddles instead (two CTAs per SM).
+    if constexpr (EPI != ROW_TWIST) {
+        if (g.stage_rows) return launch_row_v<LB, EXACT, IO, EPI, true>(io, a, g);
+    }
+    return launch_row_v<LB, EXACT, IO, EPI, false>(io, a, g);
+}
+
+template <int LB, bool EXACT, class IO, int EPI, bool STAGED>
+cudaError_t launch_row_v(const IO &io, const LaunchArgs &a, const LargeArgs &g)
+{
     using R = RowPass<LB, EXACT, IO, EPI>;
-    auto kern = rowpass_kernel<LB, EXACT, IO, EPI>;
+    constexpr int smem_bytes = STAGED ? R::SMEM_BYTES_STAGED : R::SMEM_BYTES;
+    auto kern = rowpass_kernel<LB, EXACT, IO, EPI, STAGED>;
     static PerDevice occ_pd;
     int &occ = occ_pd.get();
-    cudaError_t e = prep(kern, R::SMEM_BYTES, 256, &occ);
+    cudaError_t e = prep(kern, smem_bytes, 256, &occ);
     if (e != cudaSuccess) return e;
     const long tiles = g.chunk_rows * R::NKB;
     long cap = a.max_ctas > 0 ? a.max_ctas : (long)occ * a.num_sms;
     long grid = tiles < cap ? tiles : cap;
     grid = grid / R::NKB * R::NKB; // a CTA keeps its k-block: the grid is a multiple of NKB
     if (grid < R::NKB) grid = R::NKB;
-    kern<<<(int)grid, 256, R::SMEM_BYTES, a.stream>>>(io, a.table, tiles, g.row0, g.scratch);
+    kern<<<(int)grid, 256, smem_bytes, a.stream>>>(io, a.table, tiles, g.row0, g.scratch);
     return cudaGetLastError();
 }
 

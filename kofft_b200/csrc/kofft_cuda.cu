@@ -9,6 +9,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -78,10 +79,11 @@ struct kofft_cuda_ctx {
     // [3] small staging (windows), [4] two-pass (N > 16384) intermediate
     void *ws[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t ws_bytes[5] = {0, 0, 0, 0, 0};
-    size_t large_scratch_bytes = size_t(48) << 20; // two-pass intermediate per chunk: stays in the 126 MB L2
+    size_t large_scratch_bytes = size_t(256) << 20; // two-pass intermediate per batch chunk (measured: kernel
+                                                   // length matters more than L2 residency, profiles/r01n)
     size_t istft_ws_limit = size_t(1) << 30;
     bool use_tma = true; // TMA-staged input prefetch where alignment allows
-    bool large_fused = true; // N > 16384: one persistent thread-block-cluster kernel
+    bool large_fused = false; // N > 16384: one persistent thread-block-cluster kernel instead of two kernels per chunk
     bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
     int istft_run_frames = 128;
     // host-pointer batch entry points: the batch is cut into chunks that flow through three
@@ -235,6 +237,7 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
                 g.chunk_rows = static_cast<long>(rows - r0 < chunk ? rows - r0 : chunk);
                 g.scratch = static_cast<float2 *>(scratch);
                 g.fused = false;
+                g.stage_rows = ctx->use_tma;
                 e = launch_large_fft(L, a, g);
                 if (e != cudaSuccess) return fail_cuda(e, "large-N kernel launch");
                 ctx->launches += 2;
@@ -299,6 +302,8 @@ int kofft_cuda_create(kofft_cuda_ctx **out, int device)
         return fail_msg(-static_cast<int>(cudaErrorNoKernelImageForDevice),
                         "libkofft_cuda is built for sm_100a (B200) only");
     kofft_cuda_ctx *ctx = new kofft_cuda_ctx();
+    if (const char *mb = getenv("KOFFT_LARGE_SCRATCH_MB"))
+        if (atoi(mb) > 0) ctx->large_scratch_bytes = size_t(atoi(mb)) << 20;
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);

@@ -71,6 +71,7 @@ struct LargeArgs {
                                // fused path: clusters * 2 * 2^L complex (L2-resident either way)
     bool fused = true;         // one persistent cluster kernel instead of two kernels per chunk
     int max_clusters = 0;      // fused path: 0 = as many clusters as fit on the device
+    bool stage_rows = true;    // two-kernel path: row pass prefetches its next tile with TMA bulk copies
 };
 // upper bound on the clusters the fused kernel runs with (sizes its scratch)
 constexpr int kMaxFusedClusters = 148;

@@ -68,6 +68,8 @@ int run_cta_sized(int L, const IO &io, const float *table, long rows, bool stage
 }
 
 // ---- two-pass large-N path: the real ColPass::run + RowPass::run --------------------------------
+static bool g_large_staged = false; // the prefetching variants (cp.async column tiles, TMA row tiles)
+
 template <int LB, bool EXACT, class IO, int EPI>
 int run_large(const IO &io, const float *table, long rows, int grid_col, int grid_row)
 {
@@ -78,7 +80,7 @@ int run_large(const IO &io, const float *table, long rows, int grid_col, int gri
     std::vector<float2> scratch((size_t)rows * n);
     using C = ColPass<EXACT, IO>;
     using R = RowPass<LB, EXACT, IO, EPI>;
-    std::vector<float2> smem((std::max(C::SMEM_BYTES, R::SMEM_BYTES) + 256) / 8);
+    std::vector<float2> smem((std::max(C::SMEM_BYTES_STAGED, R::SMEM_BYTES_STAGED) + 256) / 8);
     float2 *sm = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
     // process the batch in two chunks to exercise row0
     const long half = rows > 1 ? rows / 2 : rows;
@@ -86,11 +88,21 @@ int run_large(const IO &io, const float *table, long rows, int grid_col, int gri
         const long nr = std::min(half, rows - r0);
         const long tiles_c = nr << (LB - 4);
         int gc = (int)std::min<long>(grid_col, tiles_c);
-        cuda_emu::launch(gc, 256, [&] { C::run(io, tw0, tab, LB, tiles_c, r0, scratch.data(), sm); });
+        bool col_staged = false;
+        if constexpr (IoTraits<IO>::kRowPtr) {
+            if (g_large_staged) {
+                col_staged = true;
+                cuda_emu::launch(gc, 256, [&] { C::template run<true>(io, tw0, tab, LB, tiles_c, r0, scratch.data(), sm); });
+            }
+        }
+        if (!col_staged) cuda_emu::launch(gc, 256, [&] { C::template run<false>(io, tw0, tab, LB, tiles_c, r0, scratch.data(), sm); });
         const long tiles_r = nr * R::NKB;
         long gr = std::min<long>(grid_row, tiles_r) / R::NKB * R::NKB;
         if (gr < R::NKB) gr = R::NKB;
-        cuda_emu::launch((int)gr, 256, [&] { R::run(io, tab, tiles_r, r0, scratch.data(), sm); });
+        if (g_large_staged)
+            cuda_emu::launch((int)gr, 256, [&] { R::template run<true>(io, tab, tiles_r, r0, scratch.data(), sm); });
+        else
+            cuda_emu::launch((int)gr, 256, [&] { R::template run<false>(io, tab, tiles_r, r0, scratch.data(), sm); });
     }
     return 0;
 }
@@ -173,6 +185,7 @@ API int kofft_emuk_cta(int kind, int exact, int L, long rows, const void *in, co
 }
 
 API void kofft_emuk_set_fused(int fused) { g_fused = fused != 0; }
+API void kofft_emuk_set_large_staged(int staged) { g_large_staged = staged != 0; }
 
 // the real two-pass kernel bodies; L = 15 or 16 is the length of the complex core
 API int kofft_emuk_large(int kind, int exact, int L, long rows, const void *in, const void *in2, void *out,

@@ -164,3 +164,30 @@ def test_large_fused_cluster_kernel_body(emuk, oracle, L):
     emuk.large("irfft", True, L, rows, tab, inp=yr, out=zr, aux=rtw, scale=float(np.float32(1) / np.float32(n)),
                grid_col=3, fused=True)
     assert np.array_equal(zr, oracle.irfft_batch(yr, 2 * n))
+
+
+@pytest.mark.parametrize("L", [15, 16])
+def test_large_two_pass_prefetching_variants(emuk, oracle, L):
+    """ColPass::run<true> (cp.async column tiles) + RowPass::run<true> (TMA bulk row tiles, mirrored
+    half staged ascending and read back reversed for the rfft twist) are bit-identical too."""
+    n = 1 << L
+    rng = np.random.default_rng(300 + L)
+    rows = 3
+    x = uniform_c64(rng, (rows, n))
+    tab = oracle.twiddles(n)
+    y = np.zeros_like(x)
+    emuk.large("c2c_fwd", True, L, rows, tab, inp=x, out=y, grid_col=5, grid_row=16, staged=True)
+    assert np.array_equal(y, oracle.fft_batch(x))
+    y[...] = 0
+    emuk.large("c2c_inv", True, L, rows, tab, inp=x, out=y, scale=float(np.float32(1) / np.float32(n)),
+               grid_col=3, grid_row=32, staged=True)
+    assert np.array_equal(y, oracle.fft_batch(x, inverse=True))
+    xr = rng.uniform(-1, 1, (rows, 2 * n)).astype(np.float32)
+    rtw = oracle.rfft_twiddles(n)
+    yr = np.zeros((rows, n + 1), np.complex64)
+    emuk.large("rfft", True, L, rows, tab, inp=xr, out=yr, aux=rtw, staged=True)
+    ref = oracle.rfft_batch(xr)
+    assert np.array_equal(yr, ref)
+    zr = np.zeros((rows, 2 * n), np.float32)  # irfft: column pass has no raw rows -> plain loads, row pass staged
+    emuk.large("irfft", True, L, rows, tab, inp=ref, out=zr, aux=rtw, scale=float(np.float32(1) / np.float32(n)), staged=True)
+    assert np.array_equal(zr, oracle.irfft_batch(ref, 2 * n))
