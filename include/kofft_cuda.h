@@ -11,9 +11,10 @@
  *  - Complex data is interleaved {re, im} f32 == `#[repr(C)] Complex<f32>` (src/num.rs:105-110).
  *  - Return value: 0 = Ok; 1..6 = kofft's `FftError` variants in declaration order
  *    (src/fft.rs:446-454); negative = -(cudaError_t) with text in kofft_cuda_last_error().
- *  - Only power-of-two lengths run on the GPU.  Non-power-of-two lengths return
- *    KOFFT_ERR_NON_POWER_OF_TWO_NO_STD (the reference's Bluestein path, src/fft.rs:1083-1132,
- *    is outside this backend's scope).
+ *  - C2C transforms of non-power-of-two length n <= 32768 take the reference's Bluestein path
+ *    (src/fft.rs:411-433, 1083-1132: chirp, two transforms of length next_pow2(2n-1)), with the
+ *    same tables and arithmetic.  The rfft / stft / split / strided cores are power-of-two only
+ *    and return KOFFT_ERR_NON_POWER_OF_TWO_NO_STD otherwise.
  *  - Host-pointer functions are synchronous and never retain the caller's pointers.
  *    Device-pointer functions are stream-ordered on `stream`, a cudaStream_t passed as
  *    void* with CUDA's own meaning (NULL = the legacy default stream; kofft_cuda_stream()
@@ -120,6 +121,13 @@ int kofft_cuda_irfft_f32(kofft_cuda_ctx *ctx, const void *d_in, float *d_out, si
 int kofft_cuda_stft_f32(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, size_t channels,
                         const float *d_window, size_t win_len, size_t hop, void *d_frames, size_t nframes,
                         void *stream);
+/* stft_magnitudes() per channel (src/visual/spectrogram.rs:52-76): the only in-tree consumer of
+ * large STFTs keeps |X[k]| for k < win_len/2 and the largest magnitude.  Fused behind the last
+ * FFT stage: mags [channels][nframes][win_len/2] f32 (8x fewer output bytes than the complex
+ * frames), d_max [channels] f32.  win_len >= 32. */
+int kofft_cuda_stft_magnitudes_f32(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, size_t channels,
+                                   const float *d_window, size_t win_len, size_t hop, float *d_mags,
+                                   size_t nframes, float *d_max, void *stream);
 /* istft() per channel (src/stft.rs:117-156): frames [channels][nframes][win_len] (left
  * untouched), output [channels][out_len] is ACCUMULATED into as in the reference, d_norm
  * (optional, [channels][out_len]) receives the reference's `scratch` (sum of window^2).
@@ -160,6 +168,10 @@ int kofft_cuda_irfft_batch_host_f32(kofft_cuda_ctx *ctx, const float *input, siz
  * channels > 1 processes [channels][len] -> [channels][nframes][win_len]. */
 int kofft_cuda_stft_host_f32(kofft_cuda_ctx *ctx, const float *signal, size_t len, size_t channels,
                              const float *window, size_t win_len, size_t hop, float *frames, size_t nframes);
+/* stft_magnitudes(samples, win_len, hop) (src/visual/spectrogram.rs:52-76): Hann window,
+ * nframes = ceil(len / hop) rows of win_len/2 magnitudes, *max_mag = the largest one. */
+int kofft_cuda_stft_magnitudes_host_f32(kofft_cuda_ctx *ctx, const float *samples, size_t len, size_t win_len,
+                                        size_t hop, float *mags, size_t nframes, float *max_mag);
 /* istft() (src/stft.rs:117-156); scratch receives the window-power sums like the reference.
  * zero_uncovered != 0: inverse_parallel semantics (scratch may then be NULL). */
 int kofft_cuda_istft_host_f32(kofft_cuda_ctx *ctx, const float *frames, size_t nframes, size_t channels,

@@ -5,6 +5,8 @@ Package layout (only what the path needs):
   fft.py     mirror of `FftImpl` / `FftPlanner` / the batch free functions   (src/fft.rs)
   rfft.py    mirror of `RfftPlanner` / `RealFftImpl`                          (src/rfft.rs)
   stft.py    mirror of `stft` / `istft` / streams                              (src/stft.rs)
+  spectrogram.py  `stft_magnitudes` with the magnitude + maximum fused behind the FFT (src/visual/spectrogram.rs)
+  dist.py    one transform sharded over several GPUs (BASELINE configs[4])
   window.py  `hann` / `hamming` / `blackman` / `kaiser`                        (src/window.rs)
 
 There is no CPU fallback: the compute entry points raise if the CUDA library is missing.
@@ -17,11 +19,12 @@ from .fft import (Context, CudaFftImpl, FftPlanner, FftStrategy, batch, batch_in
                   multi_channel_inverse, new_fft_impl)
 from .rfft import RfftPlanner  # noqa: F401
 from . import stft  # noqa: F401
+from . import spectrogram  # noqa: F401
 
 __all__ = [
     "Context", "CudaFftImpl", "FftPlanner", "FftStrategy", "RfftPlanner", "new_fft_impl",
     "batch", "batch_inverse", "multi_channel", "multi_channel_inverse",
     "fft_parallel", "ifft_parallel", "fft_split", "ifft_split",
     "FftError", "EmptyInput", "NonPowerOfTwoNoStd", "MismatchedLengths", "InvalidStride",
-    "InvalidHopSize", "InvalidValue", "CudaBackendError", "stft", "window", "errors",
+    "InvalidHopSize", "InvalidValue", "CudaBackendError", "stft", "spectrogram", "window", "errors",
 ]

@@ -44,6 +44,8 @@ SIGNATURES = {
     "kofft_cuda_rfft_f32": (_i, [_vp, _vp, _vp, _sz, _sz, _vp]),
     "kofft_cuda_irfft_f32": (_i, [_vp, _vp, _vp, _sz, _sz, _vp]),
     "kofft_cuda_stft_f32": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _vp]),
+    "kofft_cuda_stft_magnitudes_f32": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _vp, _vp]),
+    "kofft_cuda_stft_magnitudes_host_f32": (_i, [_vp, _vp, _sz, _sz, _sz, _vp, _sz, _vp]),
     "kofft_cuda_istft_f32": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _vp, _i, _vp]),
     "kofft_cuda_fft_host_f32": (_i, [_vp, _vp, _sz, _i]),
     "kofft_cuda_fft_batch_host_f32": (_i, [_vp, _vp, _sz, _sz, _i]),

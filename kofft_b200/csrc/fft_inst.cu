@@ -71,6 +71,11 @@ cudaError_t launch_kind(const LaunchArgs &a)
         IoStft io{(const float *)q.in, (const float *)q.aux, (float2 *)q.out, q.p0, q.p1, q.p2, q.n};
         return launch_one<L, EXACT>(io, a);
     }
+    case KIND_STFT_MAG: {
+        IoStftMag io{{(const float *)q.in, (const float *)q.aux, nullptr, q.p0, q.p1, q.p2, q.n}, (float *)q.out,
+                     (int *)q.out2, 0.0f};
+        return launch_one<L, EXACT>(io, a);
+    }
     case KIND_ISTFT: {
         IoIstft io{(const float2 *)q.in, (const float *)q.aux, (float *)q.out, q.n, q.scale};
         return launch_one<L, EXACT>(io, a);

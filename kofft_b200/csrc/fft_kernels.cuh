@@ -181,6 +181,30 @@ struct IoStft {
     KHD bool row_full(int rem) const { return rem >= (int)n; }
 };
 
+// stft_magnitudes (src/visual/spectrogram.rs:52-76): the spectrogram consumer keeps only
+// |X[k]| for k < win_len/2 and the largest magnitude.  Fused behind the last FFT stage: the
+// complex frames never reach HBM (4*(N/2) instead of 8*N bytes per frame).  mag is
+// sqrt(re*re + im*im) with every operation rounded as in the reference; the maximum is exact and
+// order-independent (non-negative floats order like their bit patterns -> integer atomicMax).
+struct IoStftMag : IoStft {
+    float *__restrict__ mags; // [rows][n/2]
+    int *max_bits;            // running maximum of this launch, as float bits (initialised to 0)
+    mutable float tmax;       // this thread's running maximum
+    KHD void store(long row, int i, float2 v) const
+    {
+        const int half = (int)(n >> 1);
+        if (i < half) {
+            const float mag = sqrt_rn(add_rn(mul_rn(v.x, v.x), mul_rn(v.y, v.y)));
+            mags[row * half + i] = mag;
+            if (mag > tmax) tmax = mag; // NaN never becomes the maximum (src/visual/spectrogram.rs:70)
+        }
+    }
+    KHD void finish() const
+    {
+        if (tmax > 0.0f) atomicMax(max_bits, float_bits(tmax));
+    }
+};
+
 // istft stage 1: time[row][i] = (ifft(frame).re) * window[i]; the overlap-add is a second,
 // order-preserving gather kernel (ola_kernel below).
 struct IoIstft {
@@ -340,24 +364,35 @@ struct IoTraits {
     static constexpr bool kRealInput = false;
     static constexpr int kMinCta = 256;
     static constexpr bool kRowPtr = false; // has row_ptr()/from_raw(): rows are plain contiguous float2
+    static constexpr bool kFinish = false; // has finish(): called once per thread when the CTA is done
 };
 template <bool INV>
 struct IoTraits<IoC2C<INV>> {
     static constexpr bool kRealInput = false;
     static constexpr int kMinCta = 256;
     static constexpr bool kRowPtr = true;
+    static constexpr bool kFinish = false;
 };
 template <bool EXACT>
 struct IoTraits<IoRfft<EXACT>> {
     static constexpr bool kRealInput = false;
     static constexpr int kMinCta = 256;
     static constexpr bool kRowPtr = true;
+    static constexpr bool kFinish = false;
 };
 template <>
 struct IoTraits<IoStft> {
     static constexpr bool kRealInput = KOFFT_STFT_REAL != 0;
     static constexpr int kMinCta = KOFFT_STFT_MIN_CTA;
     static constexpr bool kRowPtr = false;
+    static constexpr bool kFinish = false;
+};
+template <>
+struct IoTraits<IoStftMag> {
+    static constexpr bool kRealInput = KOFFT_STFT_REAL != 0;
+    static constexpr int kMinCta = KOFFT_STFT_MIN_CTA;
+    static constexpr bool kRowPtr = false;
+    static constexpr bool kFinish = true;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -560,6 +595,7 @@ struct CtaFft {
                 if (active) store_global<PL>(io, row, t, x);
             }
         }
+        if constexpr (IoTraits<IO>::kFinish) io.finish();
     }
 
     // one thread: arm the barrier with the byte count and start the bulk copy of io's current group

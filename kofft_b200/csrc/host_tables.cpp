@@ -49,6 +49,26 @@ void host_accurate_twiddles(size_t n, size_t stride, size_t count, float *out)
     }
 }
 
+// FftPlanner::get_bluestein, reference src/fft.rs:411-428: chirp[i] = expi(-angle), b[i] = expi(angle)
+// for i < n, b[m - i] = b[i], zero elsewhere; angle = pi * ((i*i) as f32) / (n as f32) in f32,
+// expi = (cos, sin) through libm.  (The reference then transforms b with its own FFT: done on the
+// device with the bit-exact kernels.)
+void host_bluestein_chirp(size_t n, size_t m, float *chirp, float *b)
+{
+    for (size_t i = 0; i < 2 * m; ++i) b[i] = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        const float angle = kPi32 * static_cast<float>(i * i) / static_cast<float>(n);
+        chirp[2 * i] = cosf(-angle);
+        chirp[2 * i + 1] = sinf(-angle);
+        b[2 * i] = cosf(angle);
+        b[2 * i + 1] = sinf(angle);
+    }
+    for (size_t i = 1; i < n; ++i) {
+        b[2 * (m - i)] = b[2 * i];
+        b[2 * (m - i) + 1] = b[2 * i + 1];
+    }
+}
+
 // build_twiddle_table, reference src/rfft.rs:172-183; `current = current.mul(w)` with
 // Complex::mul unfused (src/num.rs:160-165) or fused under +fma (src/num.rs:173-178)
 void host_rfft_twiddles(size_t m, float *out, bool fma_mul)

@@ -29,6 +29,8 @@ KD float add_rn(float a, float b) { return __fadd_rn(a, b); }
 KD float sub_rn(float a, float b) { return __fsub_rn(a, b); }
 KD float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 KD float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+KD float sqrt_rn(float a) { return __fsqrt_rn(a); }
+KD int float_bits(float a) { return __float_as_int(a); }
 #else
 // host: translation units including this header are compiled with -ffp-contract=off
 KHD float mul_rn(float a, float b) { return a * b; }
@@ -36,6 +38,13 @@ KHD float add_rn(float a, float b) { return a + b; }
 KHD float sub_rn(float a, float b) { return a - b; }
 KHD float div_rn(float a, float b) { return a / b; }
 KHD float fma_rn(float a, float b, float c) { return fmaf(a, b, c); }
+KHD float sqrt_rn(float a) { return sqrtf(a); }
+KHD int float_bits(float a)
+{
+    int i;
+    __builtin_memcpy(&i, &a, 4);
+    return i;
+}
 #endif
 
 // ---- packed f32x2 ops (sm_100a FADD2 / FMUL2 / FFMA2) -----------------------------------------

@@ -73,6 +73,11 @@ struct kofft_cuda_ctx {
     int max_ctas = 0;
     unsigned long long launches = 0;
     std::map<std::pair<size_t, int>, Table> fft_tables;  // key (n, accurate)
+    struct Blue {
+        float2 *chirp = nullptr, *bfft = nullptr;
+        size_t m = 0;
+    };
+    std::map<size_t, Blue> blue_tables; // key n (non-power-of-two): the planner's bluestein_cache
     bool accurate_tables = false; // true: correctly rounded roots of unity instead of the reference's recurrence
     std::map<std::pair<size_t, int>, Table> rfft_tables; // key (m, fma)
     // grow-only device workspaces: [0] host-API staging in, [1] staging out, [2] istft time frames,
@@ -322,6 +327,10 @@ void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->fft_tables) cudaFree(kv.second.dev);
     for (auto &kv : ctx->rfft_tables) cudaFree(kv.second.dev);
+    for (auto &kv : ctx->blue_tables) {
+        cudaFree(kv.second.chirp);
+        cudaFree(kv.second.bfft);
+    }
     for (int i = 0; i < 5; i++)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     if (ctx->pipe_ready) {
@@ -421,9 +430,17 @@ int kofft_cuda_window_host_f32(int kind, size_t len, float beta, float *out)
 }
 
 // ---- device-pointer entry points ----------------------------------------------------------
+static int bluestein_c2c(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch, int inverse,
+                         cudaStream_t s);
+
 int kofft_cuda_fft_c2c_f32(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch,
                            int inverse, void *stream)
 {
+    if (n != 0 && !is_pow2(n)) { // the reference's std build takes Bluestein here (src/fft.rs:1083-1132)
+        if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
+        CU(cudaSetDevice(ctx->device));
+        return bluestein_c2c(ctx, d_in, d_out, n, batch, inverse, pick_stream(ctx, stream));
+    }
     int rc = check_fft_len(n);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
@@ -438,6 +455,71 @@ int kofft_cuda_fft_c2c_f32(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, s
     io.out = d_out;
     io.scale = 1.0f / static_cast<float>(n); // src/fft.rs:1163
     return dispatch(ctx, inverse ? KIND_C2C_INV : KIND_C2C_FWD, io, n, batch, s, aligned16(d_in) && n >= 2);
+}
+
+// Non-power-of-two C2C: chirp multiply, two length-m power-of-two transforms, chirp multiply.
+static int bluestein_c2c(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch, int inverse,
+                         cudaStream_t s)
+{
+    size_t m = 1;
+    while (m < 2 * n - 1) m <<= 1; // (2n - 1).next_power_of_two()
+    if (m > 65536)
+        return fail_msg(-static_cast<int>(cudaErrorNotSupported), "non-power-of-two lengths above 32768 are not supported");
+    if (batch == 0) return KOFFT_OK;
+    auto it = ctx->blue_tables.find(n);
+    if (it == ctx->blue_tables.end()) {
+        kofft_cuda_ctx::Blue bt;
+        bt.m = m;
+        std::vector<float> chirp(2 * n), b(2 * m);
+        host_bluestein_chirp(n, m, chirp.data(), b.data());
+        CU(cudaMalloc(&bt.chirp, n * sizeof(float2)));
+        CU(cudaMalloc(&bt.bfft, m * sizeof(float2)));
+        CU(cudaMemcpy(bt.chirp, chirp.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(bt.bfft, b.data(), m * sizeof(float2), cudaMemcpyHostToDevice));
+        // fft(b) with the reference's arithmetic whatever mode the context is in (the planner table is mode-free)
+        const bool saved_exact = ctx->exact, saved_acc = ctx->accurate_tables;
+        ctx->exact = true;
+        ctx->accurate_tables = false;
+        int rc = kofft_cuda_fft_c2c_f32(ctx, bt.bfft, bt.bfft, m, 1, 0, ctx->stream);
+        ctx->exact = saved_exact;
+        ctx->accurate_tables = saved_acc;
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+        it = ctx->blue_tables.emplace(n, bt).first;
+    }
+    const kofft_cuda_ctx::Blue &bt = it->second;
+    // workspace rows of m complex, a bounded number of rows at a time
+    size_t chunk = ctx->istft_ws_limit / (m * sizeof(float2));
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    void *ws = nullptr;
+    int rc = ensure_ws(ctx, 2, chunk * m * sizeof(float2), &ws);
+    if (rc) return rc;
+    for (size_t r0 = 0; r0 < batch; r0 += chunk) {
+        BluesteinArgs b;
+        b.rows = static_cast<long>(batch - r0 < chunk ? batch - r0 : chunk);
+        b.x = static_cast<const float2 *>(d_in) + r0 * n;
+        b.out = static_cast<float2 *>(d_out) + r0 * n;
+        b.a = static_cast<float2 *>(ws);
+        b.chirp = bt.chirp;
+        b.bfft = bt.bfft;
+        b.n = static_cast<long>(n);
+        b.m = static_cast<long>(m);
+        b.inverse = inverse ? 1 : 0;
+        b.scale_m = 1.0f / static_cast<float>(m); // src/fft.rs:1116
+        b.scale_n = 1.0f / static_cast<float>(n); // src/fft.rs:1163
+        (void)cudaGetLastError();
+        for (int step = 0; step < 3; step++) {
+            cudaError_t e = launch_bluestein_step(step, b, ctx->exact, ctx->num_sms, s);
+            if (e != cudaSuccess) return fail_cuda(e, "bluestein step launch");
+            ctx->launches++;
+            if (step < 2) {
+                rc = kofft_cuda_fft_c2c_f32(ctx, b.a, b.a, m, static_cast<size_t>(b.rows), 0, s);
+                if (rc) return rc;
+            }
+        }
+    }
+    return KOFFT_OK;
 }
 
 int kofft_cuda_fft_strided_f32(kofft_cuda_ctx *ctx, const void *d_in, size_t in_stride, size_t in_dist,
@@ -540,6 +622,72 @@ int kofft_cuda_stft_f32(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, 
     const bool staged = aligned16(d_signal) && len % 4 == 0 && hop % 4 == 0 && nframes % tpc == 0 &&
                         ((tpc - 1) * static_cast<long>(hop) + static_cast<long>(win_len)) * 4 <= tpc * static_cast<long>(win_len) * 8;
     return dispatch(ctx, KIND_STFT, io, win_len, channels * nframes, pick_stream(ctx, stream), staged);
+}
+
+int kofft_cuda_stft_magnitudes_f32(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, size_t channels,
+                                   const float *d_window, size_t win_len, size_t hop, float *d_mags, size_t nframes,
+                                   float *d_max, void *stream)
+{
+    if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE;             // src/stft.rs:83-85 via compute_stft
+    if (nframes < (len + hop - 1) / hop) return KOFFT_ERR_MISMATCHED_LENGTHS;
+    if (channels == 0) return KOFFT_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    CU(cudaMemsetAsync(d_max, 0, channels * sizeof(float), s)); // max_mag starts at 0.0 (spectrogram.rs:64)
+    if (nframes == 0) return KOFFT_OK;
+    int rc = check_fft_len(win_len);
+    if (rc) return rc;
+    if (win_len < 32)
+        return fail_msg(-static_cast<int>(cudaErrorNotSupported), "fused stft magnitudes need win_len >= 32");
+    const long tpc = tpc_of(win_len, IoTraits<IoStftMag>::kMinCta);
+    const bool staged = aligned16(d_signal) && len % 4 == 0 && hop % 4 == 0 && nframes % tpc == 0 &&
+                        ((tpc - 1) * static_cast<long>(hop) + static_cast<long>(win_len)) * 4 <= tpc * static_cast<long>(win_len) * 8;
+    // one launch per channel: each has its own running maximum
+    for (size_t c = 0; c < channels; c++) {
+        IoArgs io;
+        io.in = d_signal + c * len;
+        io.aux = d_window;
+        io.out = d_mags + c * nframes * (win_len / 2);
+        io.out2 = d_max + c;
+        io.p0 = static_cast<long>(len);
+        io.p1 = static_cast<long>(nframes);
+        io.p2 = static_cast<long>(hop);
+        rc = dispatch(ctx, KIND_STFT_MAG, io, win_len, nframes, s, staged);
+        if (rc) return rc;
+    }
+    return KOFFT_OK;
+}
+
+static int host_roundtrip_begin(kofft_cuda_ctx *ctx, const void *src, size_t bytes, int which, void **dev);
+
+int kofft_cuda_stft_magnitudes_host_f32(kofft_cuda_ctx *ctx, const float *samples, size_t len, size_t win_len,
+                                        size_t hop, float *mags, size_t nframes, float *max_mag)
+{
+    if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE;
+    if (nframes < (len + hop - 1) / hop) return KOFFT_ERR_MISMATCHED_LENGTHS;
+    int rc = nframes ? check_fft_len(win_len) : KOFFT_OK;
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<float> w(win_len ? win_len : 1);
+    host_window(KOFFT_WINDOW_HANN, win_len, 0.0f, w.data()); // stft_magnitudes always uses hann (spectrogram.rs:57)
+    void *dsig = nullptr, *dwin = nullptr, *dout = nullptr;
+    rc = host_roundtrip_begin(ctx, samples, len * sizeof(float), 0, &dsig);
+    if (rc) return rc;
+    rc = host_roundtrip_begin(ctx, w.data(), win_len * sizeof(float), 3, &dwin);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream)); // `w` is a local: its upload must finish before it goes away
+    const size_t mbytes = nframes * (win_len / 2) * sizeof(float);
+    rc = ensure_ws(ctx, 1, mbytes + 256, &dout);
+    if (rc) return rc;
+    float *d_mags = static_cast<float *>(dout);
+    float *d_max = reinterpret_cast<float *>(static_cast<char *>(dout) + ((mbytes + 15) & ~size_t(15)));
+    rc = kofft_cuda_stft_magnitudes_f32(ctx, static_cast<const float *>(dsig), len, 1, static_cast<const float *>(dwin),
+                                        win_len, hop, d_mags, nframes, d_max, ctx->stream);
+    if (rc) return rc;
+    if (mbytes) CU(cudaMemcpyAsync(mags, d_mags, mbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(max_mag, d_max, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
 }
 
 int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nframes, size_t channels,
@@ -708,7 +856,7 @@ static int host_roundtrip_begin(kofft_cuda_ctx *ctx, const void *src, size_t byt
 
 int kofft_cuda_fft_batch_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, size_t batch, int inverse)
 {
-    int rc = check_fft_len(n);
+    int rc = n == 0 ? KOFFT_ERR_EMPTY_INPUT : KOFFT_OK; // non-power-of-two lengths take Bluestein in fft_c2c
     if (rc) return rc;
     if (n == 1 || batch == 0) return KOFFT_OK;
     CU(cudaSetDevice(ctx->device));

@@ -17,7 +17,8 @@ enum Kind : int {
     KIND_ISTFT = 5,
     KIND_RFFT = 6,
     KIND_IRFFT = 7,
-    KIND_COUNT = 8
+    KIND_STFT_MAG = 8,
+    KIND_COUNT = 9
 };
 
 // Untyped operands; their meaning per kind is documented at the IO policy they feed
@@ -93,6 +94,19 @@ struct OlaArgs {
     int zero_uncovered; // 0: istft (leave sample untouched), 1: inverse_parallel (write 0)
 };
 cudaError_t launch_ola(const OlaArgs &a, cudaStream_t stream);
+
+// Bluestein's element-wise steps (bluestein.cu): 0 = pre, 1 = mid, 2 = post
+struct BluesteinArgs {
+    const float2 *x = nullptr;     // [rows][n] input
+    float2 *out = nullptr;         // [rows][n] output
+    float2 *a = nullptr;           // [rows][m] workspace
+    const float2 *chirp = nullptr; // n entries
+    const float2 *bfft = nullptr;  // m entries: fft(b)
+    long n = 0, m = 0, rows = 0;
+    int inverse = 0;
+    float scale_m = 1.0f, scale_n = 1.0f;
+};
+cudaError_t launch_bluestein_step(int step, const BluesteinArgs &b, bool exact, int num_sms, cudaStream_t s);
 
 // fused single-kernel istft (istft_fused.cuh), N = 512 .. 4096
 struct IstftFusedArgs;

@@ -282,6 +282,47 @@ static int plan_ensure(ko_plan *p, size_t n)
 }
 
 /* ScalarFftImpl::fft, src/fft.rs:1054-1082 + stockham_fft_with_threshold :642-706 */
+static int fft_with_plan(ko_plan *p, c32 *x, size_t n);
+
+/* Bluestein for non-power-of-two n (std builds): FftPlanner::get_bluestein src/fft.rs:411-433 and
+ * ScalarFftImpl::fft src/fft.rs:1083-1132.  chirp[i] = expi(-angle), b[i] = expi(angle) with
+ * angle = pi * ((i*i) as f32) / (n as f32) evaluated in f32 (unreduced, so large i are inexact --
+ * deterministically, through the same libm sinf/cosf); b is transformed with a fresh
+ * ScalarFftImpl (same algorithm); Complex::mul is the unfused form (src/num.rs:160-165). */
+static int bluestein_with_plan(ko_plan *p, c32 *x, size_t n)
+{
+    size_t m = 1;
+    while (m < 2 * n - 1) m <<= 1; /* (2n-1).next_power_of_two() */
+    c32 *chirp = (c32 *)malloc(n * sizeof(c32));
+    c32 *b = (c32 *)calloc(m, sizeof(c32));
+    c32 *a = (c32 *)calloc(m, sizeof(c32));
+    if (!chirp || !b || !a) { free(chirp); free(b); free(a); return -1; }
+    for (size_t i = 0; i < n; i++) {
+        float angle = KO_PI32 * (float)(i * i) / (float)n;
+        chirp[i].re = cosf(-angle); chirp[i].im = sinf(-angle);
+        b[i].re = cosf(angle); b[i].im = sinf(angle);
+    }
+    for (size_t i = 1; i < n; i++) b[m - i] = b[i];
+    ko_plan fresh; memset(&fresh, 0, sizeof fresh);
+    int rc = fft_with_plan(&fresh, b, m);
+    plan_free(&fresh);
+    if (!rc) {
+        for (size_t i = 0; i < n; i++) a[i] = c_mul(x[i], chirp[i]);
+        rc = fft_with_plan(p, a, m);
+    }
+    if (!rc) {
+        for (size_t i = 0; i < m; i++) { a[i] = c_mul(a[i], b[i]); a[i].im = -a[i].im; }
+        rc = fft_with_plan(p, a, m);
+    }
+    if (!rc) {
+        float scale = 1.0f / (float)m;
+        for (size_t i = 0; i < m; i++) { a[i].im = -a[i].im; a[i].re = a[i].re * scale; a[i].im = a[i].im * scale; }
+        for (size_t i = 0; i < n; i++) x[i] = c_mul(a[i], chirp[i]);
+    }
+    free(chirp); free(b); free(a);
+    return rc;
+}
+
 static int fft_with_plan(ko_plan *p, c32 *x, size_t n)
 {
     if (n == 0) return KO_EMPTY_INPUT;
@@ -295,7 +336,7 @@ static int fft_with_plan(ko_plan *p, c32 *x, size_t n)
         }
         return KO_OK;
     }
-    if (!is_pow2(n)) return KO_NON_POW2_NO_STD; /* Bluestein (std) is outside the hot path */
+    if (!is_pow2(n)) return bluestein_with_plan(p, x, n); /* std build (src/fft.rs:1083-1132) */
     if (plan_ensure(p, n)) return -1;
     for (size_t i = 0; i < n; i++) { p->re[i] = x[i].re; p->im[i] = x[i].im; } /* :690-693 */
     stockham_soa(p->re, p->im, p->sre, p->sim, n, p->tw);

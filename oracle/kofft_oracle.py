@@ -260,3 +260,18 @@ def dft_bins_f64(x, bins) -> np.ndarray:
     out = np.empty(b.size, dtype=np.complex128)
     lib().kofft_oracle_dft_bins_f64(_p(a), a.size, _p(b), b.size, _p(out))
     return out
+
+
+def stft_magnitudes(samples, win_len: int, hop: int):
+    """src/visual/spectrogram.rs:52-76: Hann STFT, |X[k]| = sqrt(re*re + im*im) for k < win_len/2
+    (each operation rounded to f32, no fusion) and the largest magnitude (NaN never wins)."""
+    s = _f32(samples)
+    nframes = -(-s.size // hop)
+    fr = stft(s, hann(win_len), hop, nframes)[:, : win_len // 2]
+    re, im = fr.real.astype(np.float32), fr.imag.astype(np.float32)
+    mags = np.sqrt((re * re).astype(np.float32) + (im * im).astype(np.float32), dtype=np.float32)
+    mx = np.float32(0.0)
+    if mags.size:
+        finite_max = np.nanmax(mags) if not np.all(np.isnan(mags)) else np.float32(0.0)
+        mx = np.float32(max(mx, finite_max))
+    return mags, mx

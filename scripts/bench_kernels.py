@@ -42,7 +42,7 @@ def report(name, mode, ms, best, nbytes, **kw):
 
 
 def main():
-    which = sys.argv[1:] or ["c2c", "c2c2048", "stft", "istft", "rfft", "large"]
+    which = sys.argv[1:] or ["c2c", "c2c2048", "stft", "stftmag", "istft", "rfft", "large"]
     g = torch.Generator(device="cuda").manual_seed(0)
     for exact in (True, False):
         mode = "exact" if exact else "fast"
@@ -60,7 +60,7 @@ def main():
                 ms, best = timeit(lambda: fft.fft_batch(x, out=y), 10)
                 report(f"c2c_{n}x{2 ** 28 // n}", mode, ms, best, 2 * x.numel() * 8)
                 del x, y
-        if "stft" in which or "istft" in which:
+        if "stft" in which or "istft" in which or "stftmag" in which:
             ch, length, hop, win = 64, 28_800_000, 512, 2048
             nframes = -(-length // hop)
             sig = (torch.rand((ch, length), generator=g, device="cuda") * 2 - 1).contiguous()
@@ -70,6 +70,13 @@ def main():
             if "stft" in which:
                 ms, best = timeit(lambda: S.stft_batch(fft, sig, w, hop, nframes, out=frames), 6, 2)
                 report("stft_2048_512_64ch", mode, ms, best, nbytes, frames_per_s=round(ch * nframes / ms * 1e3))
+            if "stftmag" in which:
+                from kofft_b200 import spectrogram as SP
+                mags = torch.empty((ch, nframes, win // 2), dtype=torch.float32, device="cuda")
+                mbytes = 4 * ch * length + 4 * ch * nframes * (win // 2)
+                ms, best = timeit(lambda: SP.stft_magnitudes_batch(fft, sig, w, hop, nframes, out=mags), 6, 2)
+                report("stft_magnitudes_2048_512_64ch", mode, ms, best, mbytes, frames_per_s=round(ch * nframes / ms * 1e3))
+                del mags
             if "istft" in which:
                 S.stft_batch(fft, sig, w, hop, nframes, out=frames)
                 out = torch.zeros((ch, length), device="cuda")

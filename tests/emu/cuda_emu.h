@@ -33,6 +33,8 @@ inline emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 #define __ldg(p) (*(p))
+// threads are cooperative coroutines: a plain read-modify-write is atomic
+inline int atomicMax(int *a, int v) { int old = *a; if (v > old) *a = v; return old; }
 
 namespace cuda_emu {
 

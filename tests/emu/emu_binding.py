@@ -12,7 +12,7 @@ _SO = os.path.join(_HERE, "libkofft_emu.so")
 _SRC = os.path.join(_HERE, "emu_engine.cpp")
 _CSRC = os.path.join(_HERE, "..", "..", "kofft_b200", "csrc")
 
-KIND = {"c2c_fwd": 0, "c2c_inv": 1, "gen_fwd": 2, "gen_inv": 3, "stft": 4, "istft": 5, "rfft": 6, "irfft": 7}
+KIND = {"c2c_fwd": 0, "c2c_inv": 1, "gen_fwd": 2, "gen_inv": 3, "stft": 4, "istft": 5, "rfft": 6, "irfft": 7, "stft_mag": 8}
 
 
 def _stale() -> bool:

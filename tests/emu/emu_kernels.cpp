@@ -164,6 +164,7 @@ int run_cta_kind(int kind, int L, const Args &q, const float *table, long rows, 
     case 3: { IoGeneric<true> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
     case 4: { IoStft io{(const float *)q.in, (const float *)q.aux, (float2 *)q.out, q.p0, q.p1, q.p2, q.n}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
     case 5: { IoIstft io{(const float2 *)q.in, (const float *)q.aux, (float *)q.out, q.n, q.scale}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
+    case 8: { IoStftMag io{{(const float *)q.in, (const float *)q.aux, nullptr, q.p0, q.p1, q.p2, q.n}, (float *)q.out, (int *)q.out2, 0.0f}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
     case 6: { IoRfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
     case 7: { IoIrfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n, q.scale}; return run_cta_sized<EXACT>(L, io, table, rows, staged, grid); }
     default: return -2;

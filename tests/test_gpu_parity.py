@@ -59,8 +59,11 @@ def test_fft_empty_single_nonpow2(cuda_fft):  # src/lib.rs:313-318, 342-349
     d = c32(1)
     cuda_fft.fft(d)
     assert d[0] == 1
-    with pytest.raises(k.NonPowerOfTwoNoStd):  # Bluestein is out of scope for this backend
-        cuda_fft.fft(c32(1, 2, 3))
+    d = c32(1, 2, 3)  # non-power-of-two: Bluestein, like the reference's std build (src/fft.rs:1083-1132)
+    cuda_fft.fft(d)
+    assert np.allclose(d, np.fft.fft([1, 2, 3]), atol=1e-5)
+    with pytest.raises(k.NonPowerOfTwoNoStd):  # the rfft / stft cores stay power-of-two only
+        cuda_fft.rfft_batch(np.zeros((1, 24), np.float32))
 
 
 def test_fft_out_of_place(cuda_fft, oracle):  # src/lib.rs:281-311, 320-329
@@ -762,3 +765,62 @@ def test_host_pipeline_matches_single_shot(cuda_fft, oracle, chunk_bytes):
         assert np.array_equal(z, oracle.fft_batch(big, nthreads=4))
     finally:
         ctx.set_host_pipeline(32 << 20)
+
+
+@pytest.mark.parametrize("win_len,hop,length", [(2048, 512, 100_000), (1024, 256, 33_333), (256, 64, 5000), (4096, 4096, 40_000)])
+def test_stft_magnitudes_fused(cuda_fft, oracle, win_len, hop, length):
+    """stft_magnitudes (src/visual/spectrogram.rs:52-76) with |X| and max fused behind the FFT."""
+    import torch
+
+    from kofft_b200 import spectrogram as SP
+
+    rng = np.random.default_rng(win_len + hop)
+    sig = rng.uniform(-1, 1, length).astype(np.float32)
+    want, want_max = oracle.stft_magnitudes(sig, win_len, hop)
+    mags, mx = SP.stft_magnitudes(cuda_fft, sig, win_len, hop)
+    assert mags.shape == want.shape and np.array_equal(mags, want)
+    assert mx == want_max
+    # device tensors, several channels: one maximum per channel
+    sig2 = rng.uniform(-1, 1, (3, length)).astype(np.float32)
+    sig2[1] *= 0.25
+    nframes = -(-length // hop)
+    dm, dmx = SP.stft_magnitudes_batch(cuda_fft, torch.from_numpy(sig2).cuda(), torch.from_numpy(oracle.hann(win_len)).cuda(),
+                                       hop, nframes)
+    torch.cuda.synchronize()
+    for c in range(3):
+        w, wm = oracle.stft_magnitudes(sig2[c], win_len, hop)
+        assert np.array_equal(dm[c].cpu().numpy(), w) and dmx[c].item() == wm
+    with pytest.raises(Exception):
+        SP.stft_magnitudes(cuda_fft, sig, win_len, 0)
+
+
+@pytest.mark.parametrize("n", [3, 5, 6, 7, 12, 15, 100, 1000, 3000, 4097, 32767])
+def test_bluestein_non_power_of_two(cuda_fft, cuda_fft_fast, oracle, n):
+    """Non-power-of-two lengths (SURVEY.md 8f-3): chirp tables generated like FftPlanner::get_bluestein
+    (src/fft.rs:411-433), two power-of-two transforms of m = next_pow2(2n-1), Complex::mul unfused
+    (src/fft.rs:1083-1132).  EXACT is bit-identical to the oracle; KAT tests/bluestein.rs:47-65."""
+    rng = np.random.default_rng(n)
+    rows = 3 if n > 1000 else 7
+    x = uniform_c64(rng, (rows, n))
+    ref = oracle.fft_batch(x)
+    y = x.copy()
+    cuda_fft.fft_batch(y)
+    assert np.array_equal(y, ref), rel_l2(y, ref)
+    z = x.copy()
+    cuda_fft.fft_batch(z, inverse=True)
+    assert np.array_equal(z, oracle.fft_batch(x, inverse=True))
+    f = x.copy()
+    cuda_fft_fast.fft_batch(f)
+    assert rel_l2(f, ref) <= 20 * TOL  # FAST differs by ~1e-7 per transform, amplified by the chirp products
+    if n == 15:  # tests/bluestein.rs:47-65: (i, -i) against a naive DFT, 1e-3 absolute
+        d = (np.arange(n) - 1j * np.arange(n)).astype(np.complex64)
+        want = np.fft.fft(d.astype(np.complex128))
+        cuda_fft.fft(d)
+        assert np.max(np.abs(d - want)) < 1e-3
+
+
+def test_bluestein_too_long_is_an_error(cuda_fft):
+    import kofft_b200 as k
+
+    with pytest.raises(k.CudaBackendError):
+        cuda_fft.fft(np.zeros(40000, np.complex64))

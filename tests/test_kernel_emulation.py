@@ -191,3 +191,20 @@ def test_large_two_pass_prefetching_variants(emuk, oracle, L):
     zr = np.zeros((rows, 2 * n), np.float32)  # irfft: column pass has no raw rows -> plain loads, row pass staged
     emuk.large("irfft", True, L, rows, tab, inp=ref, out=zr, aux=rtw, scale=float(np.float32(1) / np.float32(n)), staged=True)
     assert np.array_equal(zr, oracle.irfft_batch(ref, 2 * n))
+
+
+@pytest.mark.parametrize("staged", [False, True])
+def test_cta_kernel_body_stft_magnitudes(emuk, oracle, staged):
+    """IoStftMag: |X[k]|, k < win_len/2, and the running maximum fused behind the last FFT stage
+    (src/visual/spectrogram.rs:52-76) -- bit-identical magnitudes, exact maximum."""
+    rng = np.random.default_rng(8)
+    win_len, hop, length = 2048, 512, 9216
+    sig = rng.uniform(-1, 1, length).astype(np.float32)
+    want, want_max = oracle.stft_magnitudes(sig, win_len, hop)
+    nframes = want.shape[0]
+    mags = np.zeros_like(want)
+    mx = np.zeros(1, np.int32)
+    emuk.cta("stft_mag", True, 11, nframes, oracle.twiddles(win_len), inp=sig, out=mags, out2=mx, aux=oracle.hann(win_len),
+             p=(length, nframes, hop, 0), staged=staged, grid=3)
+    assert np.array_equal(mags, want)
+    assert mx.view(np.float32)[0] == want_max
