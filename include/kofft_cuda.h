@@ -107,6 +107,10 @@ int kofft_cuda_fft_c2c_f32(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, s
 int kofft_cuda_fft_strided_f32(kofft_cuda_ctx *ctx, const void *d_in, size_t in_stride, size_t in_dist,
                                void *d_out, size_t out_stride, size_t out_dist, size_t n, size_t batch,
                                int inverse, void *stream);
+/* fft2d_inplace / fft3d_inplace (src/ndfft.rs:74-153): row-major data, in place; the column /
+ * depth passes are the strided entry point batched over all columns. */
+int kofft_cuda_fft2d_f32(kofft_cuda_ctx *ctx, void *d_data, size_t rows, size_t cols, void *stream);
+int kofft_cuda_fft3d_f32(kofft_cuda_ctx *ctx, void *d_data, size_t depth, size_t rows, size_t cols, void *stream);
 /* fft_split / ifft_split (src/fft.rs:1365-1439): SoA rows [batch][n]. */
 int kofft_cuda_fft_split_f32(kofft_cuda_ctx *ctx, const float *d_in_re, const float *d_in_im, float *d_out_re,
                              float *d_out_im, size_t n, size_t batch, int inverse, void *stream);
@@ -152,6 +156,12 @@ int kofft_cuda_fft_strided_host_f32(kofft_cuda_ctx *ctx, float *input, size_t in
 int kofft_cuda_fft_out_of_place_strided_host_f32(kofft_cuda_ctx *ctx, const float *input, size_t input_len,
                                                  size_t in_stride, float *output, size_t output_len,
                                                  size_t out_stride, int inverse);
+/* fft2d_inplace(data, rows, cols, fft, scratch_col) / fft3d_inplace (src/ndfft.rs:74-153); the
+ * scratch lengths are checked like the reference's (the scratch itself is not needed). */
+int kofft_cuda_fft2d_host_f32(kofft_cuda_ctx *ctx, float *data, size_t data_len, size_t rows, size_t cols,
+                              size_t scratch_col_len);
+int kofft_cuda_fft3d_host_f32(kofft_cuda_ctx *ctx, float *data, size_t data_len, size_t depth, size_t rows,
+                              size_t cols, size_t tube_len, size_t row_len, size_t col_len);
 /* RealFftImpl::rfft_with_scratch (src/rfft.rs:780-788): output_len must be n/2+1 and
  * scratch_len >= n/2 (the scratch itself is not needed on the GPU; its length is checked
  * so error behaviour matches). */
@@ -191,7 +201,9 @@ int kofft_cuda_istft_host_f32(kofft_cuda_ctx *ctx, const float *frames, size_t n
  * phases: every rank finishes phase p (stream synchronize) before any rank starts phase p + 1.
  *   natural_order == 0: d_out [N1/world][N2] holds X[(g N1/world + r) + N1 k2] at [r][k2]
  *                       ("transposed" spectrum, two exchanges)
- *   natural_order != 0: d_out holds the contiguous slice X[g N/world ...] (three exchanges)
+ *   natural_order != 0: d_out holds the contiguous slice X[g N/world ...] (three exchanges); pass
+ *                       d_out == NULL to leave it in buffer A (kofft_cuda_dist_buffer(d, 0)) and
+ *                       save the final device copy
  * One process per GPU: create, exchange the 128-byte IPC handles of all ranks (any transport),
  * connect_ipc.  One process driving several GPUs: create one per device, connect_local, then
  * kofft_cuda_dist_run_local runs all phases with device-synchronising barriers. */
@@ -199,6 +211,9 @@ typedef struct kofft_cuda_dist kofft_cuda_dist;
 int kofft_cuda_dist_create(kofft_cuda_ctx *ctx, int rank, int world, int log2n, kofft_cuda_dist **out);
 void kofft_cuda_dist_destroy(kofft_cuda_dist *d);
 size_t kofft_cuda_dist_shard_len(const kofft_cuda_dist *d); /* complex elements per rank */
+/* the local transforms of a phase run in `pieces` (default 4, 1..8) pieces, each scattered to the
+ * peers on a second stream while the next one is transformed (NVLink traffic overlaps compute) */
+int kofft_cuda_dist_set_pieces(kofft_cuda_dist *d, int pieces);
 void *kofft_cuda_dist_buffer(const kofft_cuda_dist *d, int which); /* 0: A, 1: B (device) */
 int kofft_cuda_dist_ipc_handles(kofft_cuda_dist *d, void *out128);
 int kofft_cuda_dist_connect_ipc(kofft_cuda_dist *d, const void *all_handles /* world * 128 bytes, rank order */);

@@ -6,6 +6,7 @@ Package layout (only what the path needs):
   rfft.py    mirror of `RfftPlanner` / `RealFftImpl`                          (src/rfft.rs)
   stft.py    mirror of `stft` / `istft` / streams                              (src/stft.rs)
   spectrogram.py  `stft_magnitudes` with the magnitude + maximum fused behind the FFT (src/visual/spectrogram.rs)
+  ndfft.py   `fft2d_inplace` / `fft3d_inplace`                               (src/ndfft.rs)
   dist.py    one transform sharded over several GPUs (BASELINE configs[4])
   window.py  `hann` / `hamming` / `blackman` / `kaiser`                        (src/window.rs)
 
@@ -20,11 +21,12 @@ from .fft import (Context, CudaFftImpl, FftPlanner, FftStrategy, batch, batch_in
 from .rfft import RfftPlanner  # noqa: F401
 from . import stft  # noqa: F401
 from . import spectrogram  # noqa: F401
+from . import ndfft  # noqa: F401
 
 __all__ = [
     "Context", "CudaFftImpl", "FftPlanner", "FftStrategy", "RfftPlanner", "new_fft_impl",
     "batch", "batch_inverse", "multi_channel", "multi_channel_inverse",
     "fft_parallel", "ifft_parallel", "fft_split", "ifft_split",
     "FftError", "EmptyInput", "NonPowerOfTwoNoStd", "MismatchedLengths", "InvalidStride",
-    "InvalidHopSize", "InvalidValue", "CudaBackendError", "stft", "spectrogram", "window", "errors",
+    "InvalidHopSize", "InvalidValue", "CudaBackendError", "stft", "spectrogram", "ndfft", "window", "errors",
 ]

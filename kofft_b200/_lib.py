@@ -40,6 +40,10 @@ SIGNATURES = {
     "kofft_cuda_window_host_f32": (_i, [_i, _sz, _f, _vp]),
     "kofft_cuda_fft_c2c_f32": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _vp]),
     "kofft_cuda_fft_strided_f32": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _sz, _sz, _i, _vp]),
+    "kofft_cuda_fft2d_f32": (_i, [_vp, _vp, _sz, _sz, _vp]),
+    "kofft_cuda_fft3d_f32": (_i, [_vp, _vp, _sz, _sz, _sz, _vp]),
+    "kofft_cuda_fft2d_host_f32": (_i, [_vp, _vp, _sz, _sz, _sz, _sz]),
+    "kofft_cuda_fft3d_host_f32": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, _sz, _sz]),
     "kofft_cuda_fft_split_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _i, _vp]),
     "kofft_cuda_rfft_f32": (_i, [_vp, _vp, _vp, _sz, _sz, _vp]),
     "kofft_cuda_irfft_f32": (_i, [_vp, _vp, _vp, _sz, _sz, _vp]),
@@ -60,6 +64,7 @@ SIGNATURES = {
     "kofft_cuda_dist_create": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
     "kofft_cuda_dist_destroy": (None, [_vp]),
     "kofft_cuda_dist_shard_len": (_sz, [_vp]),
+    "kofft_cuda_dist_set_pieces": (_i, [_vp, _i]),
     "kofft_cuda_dist_buffer": (_vp, [_vp, _i]),
     "kofft_cuda_dist_ipc_handles": (_i, [_vp, _vp]),
     "kofft_cuda_dist_connect_ipc": (_i, [_vp, _vp]),

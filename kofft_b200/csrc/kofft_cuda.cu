@@ -543,6 +543,67 @@ int kofft_cuda_fft_strided_f32(kofft_cuda_ctx *ctx, const void *d_in, size_t in_
     return dispatch(ctx, inverse ? KIND_GEN_INV : KIND_GEN_FWD, io, n, batch, pick_stream(ctx, stream));
 }
 
+// fft2d_inplace (src/ndfft.rs:74-101): rows, then columns through the strided entry point.
+int kofft_cuda_fft2d_f32(kofft_cuda_ctx *ctx, void *d_data, size_t rows, size_t cols, void *stream)
+{
+    if (rows == 0 || cols == 0) return KOFFT_OK; // :88-90
+    int rc = kofft_cuda_fft_c2c_f32(ctx, d_data, d_data, cols, rows, 0, stream); // :95-98
+    if (rc) return rc;
+    // column c: elements d_data[c + r*cols], r < rows (:100-102); all columns in one batched launch
+    return kofft_cuda_fft_strided_f32(ctx, d_data, cols, 1, d_data, cols, 1, rows, cols, 0, stream);
+}
+
+// fft3d_inplace (src/ndfft.rs:114-153): depth axis, row axis, column axis.
+int kofft_cuda_fft3d_f32(kofft_cuda_ctx *ctx, void *d_data, size_t depth, size_t rows, size_t cols, void *stream)
+{
+    if (depth == 0 || rows == 0 || cols == 0) return KOFFT_OK; // :128-130
+    const size_t plane = rows * cols;
+    int rc = kofft_cuda_fft_strided_f32(ctx, d_data, plane, 1, d_data, plane, 1, depth, plane, 0, stream); // z :135-140
+    if (rc) return rc;
+    for (size_t d = 0; d < depth; d++) { // y :142-147
+        float2 *p = static_cast<float2 *>(d_data) + d * plane;
+        rc = kofft_cuda_fft_strided_f32(ctx, p, cols, 1, p, cols, 1, rows, cols, 0, stream);
+        if (rc) return rc;
+    }
+    return kofft_cuda_fft_c2c_f32(ctx, d_data, d_data, cols, depth * rows, 0, stream); // x :149-154
+}
+
+static int host_roundtrip_begin(kofft_cuda_ctx *ctx, const void *src, size_t bytes, int which, void **dev);
+
+int kofft_cuda_fft2d_host_f32(kofft_cuda_ctx *ctx, float *data, size_t data_len, size_t rows, size_t cols,
+                              size_t scratch_col_len)
+{
+    if (rows * cols != data_len) return KOFFT_ERR_MISMATCHED_LENGTHS; // src/ndfft.rs:85-87
+    if (rows == 0 || cols == 0) return KOFFT_OK;
+    if (scratch_col_len != rows) return KOFFT_ERR_MISMATCHED_LENGTHS;  // :91-93
+    CU(cudaSetDevice(ctx->device));
+    void *d = nullptr;
+    int rc = host_roundtrip_begin(ctx, data, data_len * sizeof(float2), 0, &d);
+    if (rc) return rc;
+    rc = kofft_cuda_fft2d_f32(ctx, d, rows, cols, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(data, d, data_len * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_fft3d_host_f32(kofft_cuda_ctx *ctx, float *data, size_t data_len, size_t depth, size_t rows,
+                              size_t cols, size_t tube_len, size_t row_len, size_t col_len)
+{
+    if (depth * rows * cols != data_len) return KOFFT_ERR_MISMATCHED_LENGTHS; // src/ndfft.rs:125-127
+    if (depth == 0 || rows == 0 || cols == 0) return KOFFT_OK;
+    if (tube_len != depth || row_len != rows || col_len != cols) return KOFFT_ERR_MISMATCHED_LENGTHS; // :131-133
+    CU(cudaSetDevice(ctx->device));
+    void *d = nullptr;
+    int rc = host_roundtrip_begin(ctx, data, data_len * sizeof(float2), 0, &d);
+    if (rc) return rc;
+    rc = kofft_cuda_fft3d_f32(ctx, d, depth, rows, cols, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(data, d, data_len * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
 int kofft_cuda_fft_split_f32(kofft_cuda_ctx *ctx, const float *d_in_re, const float *d_in_im, float *d_out_re,
                              float *d_out_im, size_t n, size_t batch, int inverse, void *stream)
 {
@@ -1108,23 +1169,30 @@ struct kofft_cuda_dist {
     bool ipc_open[kMaxDistWorld] = {};
     bool connected = false;
     float2 *tlo = nullptr, *thi = nullptr;
+    // the local transforms of a phase are cut into pieces; piece i is scattered to the peers on a
+    // second stream while piece i+1 is transformed, so NVLink traffic overlaps the butterflies
+    int pieces = 4;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fft[8] = {}, ev_done = nullptr;
 };
 
 namespace {
 
+// rows [r_begin, r_begin + r_count) of the local matrix src [rows][world * cb]
 int dist_scatter(kofft_cuda_dist *d, const float2 *src, float2 *const *peers, size_t rows, size_t cb, int twiddle,
-                 cudaStream_t s)
+                 cudaStream_t s, size_t r_begin = 0, size_t r_count = 0)
 {
+    if (r_count == 0) r_count = rows - r_begin;
     ScatterArgs a;
-    a.src = src;
+    a.src = src + r_begin * cb * d->world;
     for (int g = 0; g < d->world; g++) a.dst[g] = peers[g];
-    a.rows = static_cast<long>(rows);
+    a.rows = static_cast<long>(r_count);
     a.cb = static_cast<long>(cb);
     a.world = d->world;
     a.dst_pitch = static_cast<long>(rows) * d->world;
-    a.dst_off = static_cast<long>(rows) * d->rank;
+    a.dst_off = static_cast<long>(rows) * d->rank + static_cast<long>(r_begin);
     a.twiddle = twiddle;
-    a.row0 = static_cast<long>(rows) * d->rank;
+    a.row0 = static_cast<long>(rows) * d->rank + static_cast<long>(r_begin);
     a.log2n = d->log2n;
     a.llo = d->llo;
     a.tlo = d->tlo;
@@ -1144,6 +1212,33 @@ int dist_local_fft(kofft_cuda_dist *d, const void *in, void *out, size_t n, size
     int rc = kofft_cuda_fft_c2c_f32(d->ctx, in, out, n, batch, inverse, s);
     d->ctx->accurate_tables = saved;
     return rc;
+}
+
+// `batch` transforms of length n in place on buf, each piece followed by its transpose-scatter on the
+// side stream; on return `s` waits for the last scatter, so the phase completes in stream order.
+int dist_fft_then_scatter(kofft_cuda_dist *d, float2 *buf, size_t n, size_t batch, int inverse, float2 *const *peers,
+                          int twiddle, cudaStream_t s)
+{
+    int pieces = d->pieces;
+    while (pieces > 1 && (batch % pieces != 0 || (batch / pieces) % 32 != 0)) pieces >>= 1;
+    if (pieces <= 1 || !d->side) {
+        int rc = dist_local_fft(d, buf, buf, n, batch, inverse, s);
+        if (rc) return rc;
+        return dist_scatter(d, buf, peers, batch, n / d->world, twiddle, s);
+    }
+    const size_t per = batch / pieces;
+    for (int i = 0; i < pieces; i++) {
+        float2 *p = buf + i * per * n;
+        int rc = dist_local_fft(d, p, p, n, per, inverse, s);
+        if (rc) return rc;
+        CU(cudaEventRecord(d->ev_fft[i], s));
+        CU(cudaStreamWaitEvent(d->side, d->ev_fft[i], 0));
+        rc = dist_scatter(d, buf, peers, batch, n / d->world, twiddle, d->side, i * per, per);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(d->ev_done, d->side));
+    CU(cudaStreamWaitEvent(s, d->ev_done, 0));
+    return KOFFT_OK;
 }
 
 } // namespace
@@ -1198,6 +1293,13 @@ int kofft_cuda_dist_create(kofft_cuda_ctx *ctx, int rank, int world, int log2n, 
     }
     d->peerA[rank] = d->bufA;
     d->peerB[rank] = d->bufB;
+    if (cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking) == cudaSuccess) {
+        for (int i = 0; i < 8; i++) cudaEventCreateWithFlags(&d->ev_fft[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming);
+    } else {
+        d->side = nullptr;
+        (void)cudaGetLastError();
+    }
     d->connected = world == 1;
     *out = d;
     return KOFFT_OK;
@@ -1213,6 +1315,11 @@ void kofft_cuda_dist_destroy(kofft_cuda_dist *d)
             cudaIpcCloseMemHandle(d->peerA[g]);
             cudaIpcCloseMemHandle(d->peerB[g]);
         }
+    if (d->side) {
+        cudaStreamDestroy(d->side);
+        for (int i = 0; i < 8; i++) cudaEventDestroy(d->ev_fft[i]);
+        cudaEventDestroy(d->ev_done);
+    }
     cudaFree(d->bufA);
     cudaFree(d->bufB);
     cudaFree(d->tlo);
@@ -1220,6 +1327,11 @@ void kofft_cuda_dist_destroy(kofft_cuda_dist *d)
     delete d;
 }
 
+int kofft_cuda_dist_set_pieces(kofft_cuda_dist *d, int pieces)
+{
+    d->pieces = pieces < 1 ? 1 : (pieces > 8 ? 8 : pieces);
+    return KOFFT_OK;
+}
 size_t kofft_cuda_dist_shard_len(const kofft_cuda_dist *d) { return (size_t(1) << d->log2n) / d->world; }
 void *kofft_cuda_dist_buffer(const kofft_cuda_dist *d, int which) { return which == 0 ? d->bufA : d->bufB; }
 
@@ -1286,19 +1398,13 @@ int kofft_cuda_dist_phase(kofft_cuda_dist *d, int phase, const void *d_in, void 
     switch (phase) {
     case 0:
         return dist_scatter(d, static_cast<const float2 *>(d_in), d->peerA, d->r1, d->c2, 0, s);
-    case 1: {
-        int rc = dist_local_fft(d, d->bufA, d->bufA, d->n1, d->c2, inverse, s);
-        if (rc) return rc;
-        return dist_scatter(d, d->bufA, d->peerB, d->c2, d->r1, tw, s);
-    }
-    case 2: {
+    case 1:
+        return dist_fft_then_scatter(d, d->bufA, d->n1, d->c2, inverse, d->peerB, tw, s);
+    case 2:
         if (!natural_order) return dist_local_fft(d, d->bufB, d_out, d->n2, d->r1, inverse, s);
-        int rc = dist_local_fft(d, d->bufB, d->bufB, d->n2, d->r1, inverse, s);
-        if (rc) return rc;
-        return dist_scatter(d, d->bufB, d->peerA, d->r1, d->c2, 0, s);
-    }
-    case 3:
-        if (natural_order && d_out != d->bufA)
+        return dist_fft_then_scatter(d, d->bufB, d->n2, d->r1, inverse, d->peerA, 0, s);
+    case 3: // natural order: the result is in buffer A; d_out == NULL or == buffer A leaves it there
+        if (natural_order && d_out && d_out != d->bufA)
             CU(cudaMemcpyAsync(d_out, d->bufA, kofft_cuda_dist_shard_len(d) * sizeof(float2), cudaMemcpyDeviceToDevice, s));
         return KOFFT_OK;
     default:

@@ -67,9 +67,24 @@ class DistFft:
         check(_lib.lib().kofft_cuda_dist_connect_ipc(self.handle, blob))
         self._group = group
 
+    def set_pieces(self, pieces: int) -> None:
+        check(_lib.lib().kofft_cuda_dist_set_pieces(self.handle, int(pieces)))
+
+    def result_view(self):
+        """Buffer A as a CUDA complex64 tensor (zero-copy): where a natural-order transform leaves this
+        rank's slice of the spectrum when `out` is None.  Valid until ANY rank starts the next
+        transform (`transform()` begins with a barrier for exactly this reason)."""
+        ptr = int(_lib.lib().kofft_cuda_dist_buffer(self.handle, 0))
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (self.shard_len, 2), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+        return torch.view_as_complex(torch.as_tensor(_Raw(), device=f"cuda:{self.ctx.device}"))
+
     def phase(self, p: int, x, out, inverse: bool = False, natural_order: bool = True, stream: Optional[int] = None):
         s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        check(_lib.lib().kofft_cuda_dist_phase(self.handle, int(p), C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+        optr = C.c_void_p(out.data_ptr()) if out is not None else C.c_void_p(0)
+        check(_lib.lib().kofft_cuda_dist_phase(self.handle, int(p), C.c_void_p(x.data_ptr()), optr,
                                                int(inverse), int(natural_order), C.c_void_p(s)))
 
     def transform(self, x, out=None, inverse: bool = False, natural_order: bool = True, barrier=None):
@@ -77,17 +92,23 @@ class DistFft:
         slice of the spectrum (natural_order) or rows [rank*N1/world ...) of X[k1 + N1*k2] as [r][k2]."""
         import torch.distributed as dist
 
-        if out is None:
+        if x.data_ptr() == int(_lib.lib().kofft_cuda_dist_buffer(self.handle, 0)):
+            x = x.clone()  # phase 0 scatters INTO buffer A on every rank: the input must not live there
+        zero_copy = out is None and natural_order
+        if out is None and not natural_order:
             out = torch.empty_like(x)
         if barrier is None:
             def barrier():
                 torch.cuda.synchronize()
                 if self.world > 1:
                     dist.barrier(group=getattr(self, "_group", None))
-        for p in range(4 if natural_order else 3):
+        # entry barrier: phase 0 stores into EVERY rank's buffer A, which may still hold the previous
+        # (zero-copy) result a slower rank is reading; all ranks have let go of it once they are here
+        barrier()
+        for p in range(3 if (zero_copy or not natural_order) else 4):
             self.phase(p, x, out, inverse, natural_order)
             barrier()
-        return out
+        return self.result_view() if zero_copy else out
 
 
 def run_local(dists: Sequence[DistFft], xs, outs, inverse: bool = False, natural_order: bool = True) -> None:

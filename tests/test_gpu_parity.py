@@ -824,3 +824,41 @@ def test_bluestein_too_long_is_an_error(cuda_fft):
 
     with pytest.raises(k.CudaBackendError):
         cuda_fft.fft(np.zeros(40000, np.complex64))
+
+
+def test_ndfft_2d_3d(cuda_fft, oracle):
+    """fft2d_inplace / fft3d_inplace (src/ndfft.rs:74-153): rows then strided columns (then depth),
+    bit-identical to composing the oracle's 1-D transform the same way; error cases :85-93, :125-133."""
+    import torch
+
+    import kofft_b200 as k
+    from kofft_b200 import ndfft
+
+    rng = np.random.default_rng(77)
+    rows, cols = 64, 256
+    x = uniform_c64(rng, (rows, cols))
+    want = oracle.fft_batch(x)                                   # rows
+    want = np.ascontiguousarray(oracle.fft_batch(np.ascontiguousarray(want.T)).T)  # columns (gather, fft, scatter)
+    got = x.copy().reshape(-1)
+    ndfft.fft2d_inplace(got, rows, cols, cuda_fft, np.zeros(rows, np.complex64))
+    assert np.array_equal(got.reshape(rows, cols), want)
+    assert np.allclose(want, np.fft.fft2(x.astype(np.complex128)), atol=1e-2)
+    d = torch.from_numpy(x.copy()).cuda()
+    ndfft.fft2d_inplace(d, rows, cols, cuda_fft)
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy(), want)
+    with pytest.raises(k.MismatchedLengths):
+        ndfft.fft2d_inplace(x.copy().reshape(-1), rows, cols + 1, cuda_fft, np.zeros(rows, np.complex64))
+    with pytest.raises(k.MismatchedLengths):
+        ndfft.fft2d_inplace(x.copy().reshape(-1), rows, cols, cuda_fft, np.zeros(rows + 1, np.complex64))
+    depth, rows, cols = 8, 16, 32
+    v = uniform_c64(rng, (depth, rows, cols))
+    w3 = np.moveaxis(oracle.fft_batch(np.ascontiguousarray(np.moveaxis(v, 0, 2).reshape(-1, depth))).reshape(rows, cols, depth), 2, 0)
+    w3 = np.moveaxis(oracle.fft_batch(np.ascontiguousarray(np.moveaxis(w3, 1, 2).reshape(-1, rows))).reshape(depth, cols, rows), 2, 1)
+    w3 = oracle.fft_batch(np.ascontiguousarray(w3.reshape(-1, cols))).reshape(depth, rows, cols)
+    g3 = v.copy().reshape(-1)
+    ndfft.fft3d_inplace(g3, depth, rows, cols, cuda_fft)
+    assert np.array_equal(g3.reshape(depth, rows, cols), w3)
+    assert np.allclose(w3, np.fft.fftn(v.astype(np.complex128)), atol=1e-2)
+    with pytest.raises(k.MismatchedLengths):
+        ndfft.fft3d_inplace(v.copy().reshape(-1), depth, rows, cols, cuda_fft, (np.zeros(depth), np.zeros(rows), np.zeros(cols + 1)))
