@@ -3,8 +3,8 @@
 //!
 //! The kernel sources live in `../kofft_b200/csrc` of this repository (the same files the
 //! Python mirror builds into `libkofft_cuda.so`):
-//!   fft_inst.cu (once per L = 5..14 with -DKOFFT_L), small_inst.cu, fft_large_inst.cu, ola.cu,
-//!   kofft_cuda.cu (the C ABI) and host_tables.cpp (bit-exact twiddle/window generators; must
+//!   fft_inst.cu (once per L = 5..14 with -DKOFFT_L), small_inst.cu, fft_large_inst.cu, istft_inst.cu,
+//!   ola.cu, dist_kernels.cu, bluestein.cu, kofft_cuda.cu (the C ABI) and host_tables.cpp (bit-exact twiddle/window generators; must
 //!   be built with -ffp-contract=off).
 use std::{env, path::PathBuf, process::Command};
 
@@ -29,7 +29,8 @@ fn main() {
             .arg(csrc.join("fft_inst.cu")).arg("-o").arg(&o));
         objs.push(o);
     }
-    for src in ["small_inst.cu", "fft_large_inst.cu", "ola.cu", "kofft_cuda.cu"] {
+    for src in ["small_inst.cu", "fft_large_inst.cu", "istft_inst.cu", "ola.cu", "dist_kernels.cu", "bluestein.cu",
+                "kofft_cuda.cu"] {
         let o = out.join(format!("{src}.o"));
         run(Command::new(&nvcc).args(flags).arg("-c").arg(csrc.join(src)).arg("-o").arg(&o));
         objs.push(o);

@@ -41,6 +41,23 @@ extern "C" {
     fn kofft_cuda_istft_host_f32(ctx: *mut RawCtx, frames: *const f32, nframes: usize, channels: usize,
                                  window: *const f32, win_len: usize, hop: usize, output: *mut f32, out_len: usize,
                                  scratch: *mut f32, scratch_len: usize, zero_uncovered: c_int) -> c_int;
+    fn kofft_cuda_stft_magnitudes_host_f32(ctx: *mut RawCtx, samples: *const f32, len: usize, win_len: usize, hop: usize,
+                                           mags: *mut f32, nframes: usize, max_mag: *mut f32) -> c_int;
+    fn kofft_cuda_fft2d_host_f32(ctx: *mut RawCtx, data: *mut f32, data_len: usize, rows: usize, cols: usize,
+                                 scratch_col_len: usize) -> c_int;
+    fn kofft_cuda_fft3d_host_f32(ctx: *mut RawCtx, data: *mut f32, data_len: usize, depth: usize, rows: usize,
+                                 cols: usize, tube_len: usize, row_len: usize, col_len: usize) -> c_int;
+    fn kofft_cuda_set_host_pipeline(ctx: *mut RawCtx, chunk_bytes: usize) -> c_int;
+    // one transform sharded over several GPUs (include/kofft_cuda.h, "kofft_cuda_dist_*")
+    pub fn kofft_cuda_dist_create(ctx: *mut RawCtx, rank: c_int, world: c_int, log2n: c_int, out: *mut *mut c_void) -> c_int;
+    pub fn kofft_cuda_dist_destroy(d: *mut c_void);
+    pub fn kofft_cuda_dist_ipc_handles(d: *mut c_void, out128: *mut c_void) -> c_int;
+    pub fn kofft_cuda_dist_connect_ipc(d: *mut c_void, all_handles: *const c_void) -> c_int;
+    pub fn kofft_cuda_dist_connect_local(dists: *const *mut c_void, world: c_int) -> c_int;
+    pub fn kofft_cuda_dist_phase(d: *mut c_void, phase: c_int, d_in: *const c_void, d_out: *mut c_void, inverse: c_int,
+                                 natural_order: c_int, stream: *mut c_void) -> c_int;
+    pub fn kofft_cuda_dist_run_local(dists: *const *mut c_void, world: c_int, d_in: *const *const c_void,
+                                     d_out: *const *mut c_void, inverse: c_int, natural_order: c_int) -> c_int;
     // device-pointer entry points (stream-ordered) for callers that keep data on the GPU
     pub fn kofft_cuda_fft_c2c_f32(ctx: *mut RawCtx, d_in: *const c_void, d_out: *mut c_void, n: usize, batch: usize,
                                   inverse: c_int, stream: *mut c_void) -> c_int;
@@ -153,6 +170,40 @@ impl CudaFftImpl {
                                       window.len(), hop, output.as_mut_ptr(), output.len() / channels,
                                       scratch.as_mut_ptr(), scratch.len(), 0)
         })
+    }
+}
+
+impl CudaFftImpl {
+    /// `stft_magnitudes(samples, win_len, hop)` (src/visual/spectrogram.rs:52-76) with the magnitude
+    /// and the running maximum fused behind the last FFT stage.  Returns (flat mags, frames, max).
+    pub fn stft_magnitudes(&self, samples: &[f32], win_len: usize, hop: usize) -> Result<(Vec<f32>, usize, f32), FftError> {
+        if hop == 0 {
+            return Err(FftError::InvalidHopSize);
+        }
+        let nframes = samples.len().div_ceil(hop);
+        let mut mags = vec![0.0f32; nframes * (win_len / 2)];
+        let mut max_mag = 0.0f32;
+        check(unsafe {
+            kofft_cuda_stft_magnitudes_host_f32(self.ctx, samples.as_ptr(), samples.len(), win_len, hop, mags.as_mut_ptr(),
+                                                nframes, &mut max_mag)
+        })?;
+        Ok((mags, nframes, max_mag))
+    }
+    /// `fft2d_inplace` (src/ndfft.rs:74-105)
+    pub fn fft2d_inplace(&self, data: &mut [Complex32], rows: usize, cols: usize, scratch_col: &mut [Complex32]) -> Result<(), FftError> {
+        check(unsafe { kofft_cuda_fft2d_host_f32(self.ctx, data.as_mut_ptr() as *mut f32, data.len(), rows, cols, scratch_col.len()) })
+    }
+    /// `fft3d_inplace` (src/ndfft.rs:114-156); scratch lengths = (depth, rows, cols)
+    pub fn fft3d_inplace(&self, data: &mut [Complex32], depth: usize, rows: usize, cols: usize,
+                         scratch_lens: (usize, usize, usize)) -> Result<(), FftError> {
+        check(unsafe {
+            kofft_cuda_fft3d_host_f32(self.ctx, data.as_mut_ptr() as *mut f32, data.len(), depth, rows, cols, scratch_lens.0,
+                                      scratch_lens.1, scratch_lens.2)
+        })
+    }
+    /// chunk size of the H2D / kernel / D2H pipeline behind the batch calls (0 = off, default 32 MiB)
+    pub fn set_host_pipeline(&self, chunk_bytes: usize) {
+        unsafe { kofft_cuda_set_host_pipeline(self.ctx, chunk_bytes) };
     }
 }
 

@@ -29,9 +29,16 @@ __global__ void __launch_bounds__(256) transpose_scatter_kernel(const __grid_con
     const long ntiles = tiles_c * tiles_r;
     const unsigned lomask = (1u << a.llo) - 1u;
     for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        // consecutive CTAs walk down a tile column: their stores extend each other's runs at the destination
-        const long tc = t / tiles_r, tr = t - tc * tiles_r;
-        const long r0 = tr << 5, c0 = tc << 5;
+        // Consecutive tiles go to DIFFERENT destinations, starting with this rank's right neighbour:
+        // every GPU keeps all peers busy at once and no peer is the target of everybody at the same
+        // time (all ranks run this loop in lock step; destination-major order makes the all-to-all an
+        // 8-to-1 incast, measured 249 GB/s per GPU instead of the link rate).  Within a destination,
+        // consecutive tiles walk down a tile column, extending each other's runs at the destination.
+        const int di = (int)(t % a.world);
+        const long u = t / a.world;
+        const long tcd = u / tiles_r, tr = u - tcd * tiles_r;
+        const int dsel = (a.rank + 1 + di) % a.world;
+        const long r0 = tr << 5, c0 = (long)dsel * a.cb + (tcd << 5);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const long r = r0 + ty + 8 * i, c = c0 + tx;
@@ -47,8 +54,8 @@ __global__ void __launch_bounds__(256) transpose_scatter_kernel(const __grid_con
             tile[ty + 8 * i][tx] = v;
         }
         __syncthreads();
-        const int d = (int)(c0 / a.cb);
-        const long cin = c0 - (long)d * a.cb; // column inside the destination block
+        const int d = dsel;
+        const long cin = tcd << 5; // column inside the destination block
         float2 *dst = a.dst[d];
 #pragma unroll
         for (int i = 0; i < 4; i++) {

@@ -11,6 +11,7 @@ struct ScatterArgs {
     float2 *dst[kMaxDistWorld] = {};  // destination buffers (local or peer device memory)
     long rows = 0, cb = 0;            // both multiples of 32
     int world = 1;
+    int rank = 0;                     // destinations are visited starting at rank + 1 (no incast)
     long dst_pitch = 0;               // elements between consecutive destination rows
     long dst_off = 0;                 // column offset at the destination
     int twiddle = 0;                  // 1: multiply by W_N^{(row0 + r) * c}; 2: by its conjugate

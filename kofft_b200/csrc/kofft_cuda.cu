@@ -1172,6 +1172,7 @@ struct kofft_cuda_dist {
     // the local transforms of a phase are cut into pieces; piece i is scattered to the peers on a
     // second stream while piece i+1 is transformed, so NVLink traffic overlaps the butterflies
     int pieces = 4;
+    int reserve_sms = 32; // SMs the piece transforms leave free so the concurrent scatter kernel gets on the machine
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fft[8] = {}, ev_done = nullptr;
 };
@@ -1189,6 +1190,7 @@ int dist_scatter(kofft_cuda_dist *d, const float2 *src, float2 *const *peers, si
     a.rows = static_cast<long>(r_count);
     a.cb = static_cast<long>(cb);
     a.world = d->world;
+    a.rank = d->rank;
     a.dst_pitch = static_cast<long>(rows) * d->world;
     a.dst_off = static_cast<long>(rows) * d->rank + static_cast<long>(r_begin);
     a.twiddle = twiddle;
@@ -1227,9 +1229,15 @@ int dist_fft_then_scatter(kofft_cuda_dist *d, float2 *buf, size_t n, size_t batc
         return dist_scatter(d, buf, peers, batch, n / d->world, twiddle, s);
     }
     const size_t per = batch / pieces;
+    // the transform kernels are persistent and would fill every SM: shrink their grid a little so
+    // the scatter of the previous piece (side stream) runs at the same time
+    const int all_sms = d->ctx->num_sms;
+    const int fft_sms = all_sms - d->reserve_sms > all_sms / 2 ? all_sms - d->reserve_sms : all_sms;
     for (int i = 0; i < pieces; i++) {
         float2 *p = buf + i * per * n;
+        d->ctx->num_sms = i == 0 ? all_sms : fft_sms; // nothing to overlap with during the first piece
         int rc = dist_local_fft(d, p, p, n, per, inverse, s);
+        d->ctx->num_sms = all_sms;
         if (rc) return rc;
         CU(cudaEventRecord(d->ev_fft[i], s));
         CU(cudaStreamWaitEvent(d->side, d->ev_fft[i], 0));
@@ -1293,6 +1301,10 @@ int kofft_cuda_dist_create(kofft_cuda_ctx *ctx, int rank, int world, int log2n, 
     }
     d->peerA[rank] = d->bufA;
     d->peerB[rank] = d->bufB;
+    if (const char *e = getenv("KOFFT_DIST_PIECES")) // tuning aids
+        if (atoi(e) >= 1 && atoi(e) <= 8) d->pieces = atoi(e);
+    if (const char *e = getenv("KOFFT_DIST_RESERVE_SMS"))
+        if (atoi(e) >= 0 && atoi(e) < ctx->num_sms) d->reserve_sms = atoi(e);
     if (cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking) == cudaSuccess) {
         for (int i = 0; i < 8; i++) cudaEventCreateWithFlags(&d->ev_fft[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming);
