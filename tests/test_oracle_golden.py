@@ -230,3 +230,27 @@ def test_oracle_pinned_fixture(oracle):
     assert np.array_equal(oracle.rfft(g["xr_8192"]), g["yr_8192"])
     assert np.array_equal(oracle.hann(2048), g["hann_2048"])
     assert np.array_equal(oracle.stft(g["sig"], g["hann_2048"], 512, 8), g["stft_frames"])
+
+
+def test_bluestein_matches_dft(oracle):  # tests/bluestein.rs:47-65 (n = 15, (i, -i), 1e-3 absolute) + other lengths
+    n = 15
+    x = (np.arange(n) - 1j * np.arange(n)).astype(np.complex64)
+    want = np.fft.fft(x.astype(np.complex128))
+    got = oracle.fft(x)
+    assert np.max(np.abs(got.real - want.real)) < 1e-3 and np.max(np.abs(got.imag - want.imag)) < 1e-3
+    rng = np.random.default_rng(15)
+    for n in (3, 5, 6, 7, 12, 100, 1000):
+        x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+        want = np.fft.fft(x.astype(np.complex128))
+        assert np.linalg.norm(oracle.fft(x) - want) / np.linalg.norm(want) < 2e-4
+        assert np.linalg.norm(oracle.ifft(oracle.fft(x)) - x) / np.linalg.norm(x) < 4e-4
+
+
+def test_stft_magnitudes_restatement(oracle):  # src/visual/spectrogram.rs:52-76
+    rng = np.random.default_rng(52)
+    sig = rng.uniform(-1, 1, 3000).astype(np.float32)
+    mags, mx = oracle.stft_magnitudes(sig, 256, 64)
+    assert mags.shape == (47, 128) and mags.dtype == np.float32
+    fr = oracle.stft(sig, oracle.hann(256), 64, 47)[:, :128]
+    assert np.allclose(mags, np.abs(fr), rtol=2e-7, atol=0) or np.max(np.abs(mags - np.abs(fr))) < 1e-5
+    assert mx == mags.max() and mx > 0
