@@ -18,6 +18,8 @@
 #define KD inline
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+// phase-by-phase host replay (tests/emu/emu_engine.cpp) is single-threaded
+static inline int atomicMax(int *a, int v) { int old = *a; if (v > old) *a = v; return old; }
 #endif
 
 namespace kofft {
