@@ -19,7 +19,7 @@ echo "== bench reference arm" | tee -a $OUT/summary.txt
 timeout 600 python bench.py --impl reference --steps 10 --warmup 2 > $OUT/bench_ref.json 2>> $OUT/bench.err
 cat $OUT/bench_ref.json | tee -a $OUT/summary.txt
 echo "== ncu launch list" | tee -a $OUT/summary.txt
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 3 --warmup 3 > $OUT/ncu_launches.log 2>&1; echo "ncu list exit $?" | tee -a $OUT/summary.txt
 echo "== ncu full" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_cta_kernel -s 3 -c 2 -o $OUT/prof_c2c \
