@@ -7,6 +7,11 @@
 
 namespace kofft {
 
+// L2 eviction-priority policies of one thread (see make_l2_policy below)
+struct L2Policy {
+    unsigned long long first = 0, last = 0;
+};
+
 #if defined(__CUDACC__)
 
 KD unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -70,7 +75,73 @@ KD unsigned cluster_ctarank()
     return r;
 }
 
+// ---- L2 eviction-priority hints (createpolicy + .L2::cache_hint) ------------------------------
+// The pipelined large-N kernel streams its input and output through L2 (evict_first) and pins the
+// pass-A -> pass-B intermediate (evict_last) so that it never makes the round trip to HBM.
+KD L2Policy make_l2_policy()
+{
+    L2Policy p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.first));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.last));
+    return p;
+}
+// read-only streaming load (never written during the launch)
+KD float2 ldg_hint(const float2 *p, unsigned long long pol)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
+                 : "=f"(v.x), "=f"(v.y)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+// L2-only load of data written by other CTAs of the same launch
+KD float2 ldcg_hint(const float2 *p, unsigned long long pol)
+{
+    float2 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+// (volatile, no memory clobber: ordered against the other hinted accesses, __syncthreads and
+// __threadfence, but the compiler may still schedule shared-memory traffic around it; the
+// kernels never touch these addresses with plain loads or stores)
+KD void stg_hint(float2 *p, float2 v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol));
+}
+
+// ---- grid-wide barrier for persistent kernels whose CTAs are all co-resident (cooperative launch)
+// `bar` counts arrivals since the launch (zeroed by the host); split into arrive / wait so that a
+// CTA can do independent work in between.  Same fence pattern as cooperative_groups::grid_group::sync.
+KD void grid_arrive(unsigned *bar)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+    }
+}
+KD void grid_wait(unsigned *bar, unsigned target)
+{
+    if (threadIdx.x == 0) {
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 #elif defined(KOFFT_EMU)
+
+inline L2Policy make_l2_policy() { return L2Policy{1ull, 2ull}; }
+inline float2 ldg_hint(const float2 *p, unsigned long long) { return *p; }
+inline float2 ldcg_hint(const float2 *p, unsigned long long) { return *p; }
+inline void stg_hint(float2 *p, float2 v, unsigned long long) { *p = v; }
+// the emulator runs one CTA at a time: a multi-phase launch is emulated phase by phase, so the
+// grid barrier is never reached with other CTAs outstanding
+inline void grid_arrive(unsigned *bar) { __syncthreads(); if (threadIdx.x == 0) ++*bar; }
+inline void grid_wait(unsigned *, unsigned) { __syncthreads(); }
 
 inline void cp_async16(void *dst_smem, const void *src)
 {

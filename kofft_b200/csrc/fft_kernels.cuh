@@ -78,6 +78,15 @@ struct IoC2C {
     KHD const float2 *row_ptr(long row) const { return in + row * n; }
     KHD float2 from_raw(float2 v) const { return pre_conj<INV>(v); }
     KHD bool row_full(int) const { return true; }
+#if defined(__CUDACC__) || defined(KOFFT_EMU)
+    // L2-hinted accessors of the pipelined large-N kernel (fft_large.cuh LargePipe): the rows stream
+    // through L2 with evict_first so they do not displace the pinned intermediate
+    KD float2 load_hint(long row, int i, unsigned long long pol) const { return pre_conj<INV>(ldg_hint(in + row * n + i, pol)); }
+    KD void store_hint(long row, int i, float2 v, unsigned long long pol) const
+    {
+        stg_hint(out + row * n + i, post_conj_scale<INV>(v, scale), pol);
+    }
+#endif
 };
 
 // element e of row r lives at  re[r*row_stride + e*elem_stride]  (strides in floats);
@@ -301,12 +310,31 @@ struct IoRfft {
             o[m] = make_float2(sub_rn(a.x, a.y), 0.0f);
             return;
         }
+        o[k] = twist(a, ym, tw);
+    }
+    // out[k] for 0 < k < m (src/rfft.rs:453-461)
+    KHD float2 twist(float2 a, float2 ym, float2 tw) const
+    {
         float2 b = make_float2(ym.x, -ym.y);
         float2 sum = add2(a, b), diff = sub2(a, b);
         float2 t = cmul<EXACT>(tw, diff);
         float2 temp = make_float2(add_rn(sum.x, t.y), sub_rn(sum.y, t.x)); // sum + (t.im, -t.re)
-        o[k] = make_float2(mul_rn(temp.x, 0.5f), mul_rn(temp.y, 0.5f));
+        return make_float2(mul_rn(temp.x, 0.5f), mul_rn(temp.y, 0.5f));
     }
+#if defined(__CUDACC__) || defined(KOFFT_EMU)
+    // L2-hinted accessors of the pipelined large-N kernel (see IoC2C)
+    KD float2 load_hint(long row, int i, unsigned long long pol) const { return ldg_hint(in + row * m + i, pol); }
+    KD void twist_store_tw_hint(long row, long k, float2 a, float2 ym, float2 tw, unsigned long long pol) const
+    {
+        float2 *o = out + row * (m + 1);
+        if (k == 0) {
+            stg_hint(o, make_float2(add_rn(a.x, a.y), 0.0f), pol);
+            stg_hint(o + m, make_float2(sub_rn(a.x, a.y), 0.0f), pol);
+            return;
+        }
+        stg_hint(o + k, twist(a, ym, tw), pol);
+    }
+#endif
     // Y: padded shared copy of the m FFT bins of this row
     KHD void epilogue(long row, int k, const float2 *Y) const
     {
@@ -365,6 +393,7 @@ struct IoTraits {
     static constexpr int kMinCta = 256;
     static constexpr bool kRowPtr = false; // has row_ptr()/from_raw(): rows are plain contiguous float2
     static constexpr bool kFinish = false; // has finish(): called once per thread when the CTA is done
+    static constexpr bool kHint = false;   // has load_hint()/store_hint(): L2-hinted row accessors
 };
 template <bool INV>
 struct IoTraits<IoC2C<INV>> {
@@ -372,6 +401,7 @@ struct IoTraits<IoC2C<INV>> {
     static constexpr int kMinCta = 256;
     static constexpr bool kRowPtr = true;
     static constexpr bool kFinish = false;
+    static constexpr bool kHint = true;
 };
 template <bool EXACT>
 struct IoTraits<IoRfft<EXACT>> {
@@ -379,6 +409,7 @@ struct IoTraits<IoRfft<EXACT>> {
     static constexpr int kMinCta = 256;
     static constexpr bool kRowPtr = true;
     static constexpr bool kFinish = false;
+    static constexpr bool kHint = true;
 };
 template <>
 struct IoTraits<IoStft> {
@@ -386,6 +417,7 @@ struct IoTraits<IoStft> {
     static constexpr int kMinCta = KOFFT_STFT_MIN_CTA;
     static constexpr bool kRowPtr = false;
     static constexpr bool kFinish = false;
+    static constexpr bool kHint = false;
 };
 template <>
 struct IoTraits<IoStftMag> {
@@ -393,6 +425,7 @@ struct IoTraits<IoStftMag> {
     static constexpr int kMinCta = KOFFT_STFT_MIN_CTA;
     static constexpr bool kRowPtr = false;
     static constexpr bool kFinish = true;
+    static constexpr bool kHint = false;
 };
 
 // ------------------------------------------------------------------------------------------

@@ -393,6 +393,190 @@ struct LargeFused {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Both passes in ONE persistent kernel, software-pipelined over batch chunks ("phases"):
+//     phase p:  pass A of chunk p   (HBM -> intermediate buffer p mod NBUF)
+//               pass B of chunk p-1 (intermediate buffer (p-1) mod NBUF -> HBM)
+// with a grid-wide barrier between phases (all CTAs co-resident: cooperative launch).  A chunk is
+// a few tiles per CTA, so the NBUF intermediate buffers are a few tens of MB: they are written
+// with the L2 evict_last policy and the rows stream through with evict_first, so the
+// intermediate never makes the round trip to HBM (the two-kernel path above needs long launches
+// to amortise launch + ramp + tail, and at those chunk sizes the intermediate spills: measured
+// 2x the algorithmic DRAM traffic, profiles/r01u_rfft_*pass_kernel.json).  With NBUF = 3 the
+// barrier is split: a CTA arrives after its last pass-A tile of the phase and waits only after
+// its last pass-B tile, so the skew between CTAs is hidden behind useful work.
+// CTA j keeps column tile / k-block  j mod NKB  for its lifetime (the grid is a multiple of NKB),
+// so its pass-B twiddles stay in registers and its rfft-table slice in shared memory.
+// phase_begin/phase_end: the phases this launch runs (one launch runs them all; the CPU emulator
+// and the non-cooperative fallback run one phase per launch, the launch boundary being the barrier).
+// ---------------------------------------------------------------------------------------------
+template <int LB, bool EXACT, class IO, int EPI>
+struct LargePipe {
+    using C = ColPass<EXACT, IO>;
+    using R = RowPass<LB, EXACT, IO, EPI>;
+    static constexpr int NKB = R::NKB;                 // 8 (N = 2^15) or 16 (N = 2^16)
+    static constexpr int LOG_NKB = ilog2c(NKB);
+    static_assert((1 << LB) / C::COLS == NKB, "one column tile per k-block");
+    static constexpr int BUFA = C::COLS * C::RS;
+    static constexpr int BUF = (BUFA > R::BUF ? BUFA : R::BUF); // float2 per exchange buffer
+    static constexpr int NBUFS = EPI == ROW_TWIST ? 3 : 2;      // twist: + the CTA's rfft twiddles
+    static constexpr int TW_SMEM = 16 * 16;                     // pass-A pass-1 twiddles: [t][15] float2
+    static constexpr int SMEM_BYTES = (NBUFS * BUF + TW_SMEM) * 8;
+    static constexpr bool HINT = IoTraits<IO>::kHint;
+
+    // pass A tile (ColPass::tile with L2 hints): 16 adjacent columns of transform `row` -> scratch_row
+    static KD void tile_a(const IO &io, const Tw0 &tw0, const float2 *tw1, long row, long j0,
+                          float2 *__restrict__ scratch_row, float2 *bf, int t, int slot, const L2Policy &pol)
+    {
+        using P0 = typename C::P0;
+        using P1 = typename C::P1;
+        const long j = j0 + slot;
+        float2 x[EPT];
+#pragma unroll
+        for (int q = 0; q < P0::R; q++) {
+            const int idx = (int)(((long)P0::src_index(t, 0, q) << LB) + j);
+            if constexpr (HINT)
+                x[q] = io.load_hint(row, idx, pol.first);
+            else
+                x[q] = io.load(row, idx);
+        }
+        P0::compute(x, tw0.v);
+#pragma unroll
+        for (int w = 0; w < P0::R; w++) bf[P0::dst_pad(P0::dst_base(t, 0), w)] = x[w];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < P1::R; q++) x[q] = bf[P1::src_pad(P1::src_base(t, 0), q)];
+        P1::compute(x, tw1);
+        float2 *o = scratch_row + j;
+#pragma unroll
+        for (int w = 0; w < P1::R; w++) stg_hint(o + ((long)P1::dst_index(t, 0, w) << LB), x[w], pol.last);
+    }
+
+    // pass B tile (RowPass::tile with L2 hints): bfa / bfb are this thread's exchange regions in two
+    // different buffers, allb is bfb's buffer seen CTA-wide, rtwb the CTA's slice of T' (twist only)
+    static KD void tile_b(const IO &io, const float2 *tw0, const float2 *tw1, long row, int kb, int k,
+                          const float2 *__restrict__ scratch_row, float2 *bfa, float2 *bfb, const float2 *allb, int t,
+                          int tid, const float2 *rtwb, const L2Policy &pol)
+    {
+        using P = typename R::P;
+        using P0 = typename R::P0;
+        using P1 = typename R::P1;
+        constexpr int NB = R::NB, TPC = R::TPC;
+        float2 x[EPT];
+        const float2 *in = scratch_row + (long)k * NB;
+#pragma unroll
+        for (int u = 0; u < P0::U; u++)
+#pragma unroll
+            for (int q = 0; q < P0::R; q++) x[u * P0::R + q] = ldcg_hint(in + P0::src_index(t, u, q), pol.first);
+        P0::compute(x, tw0);
+#pragma unroll
+        for (int u = 0; u < P0::U; u++)
+#pragma unroll
+            for (int w = 0; w < P0::R; w++) bfa[P0::dst_pad(P0::dst_base(t, u), w)] = x[u * P0::R + w];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < P1::R; q++) x[q] = bfa[P1::src_pad(P1::src_base(t, 0), q)];
+        P1::compute(x, tw1);
+#pragma unroll
+        for (int w = 0; w < P1::R; w++) bfb[P1::dst_pad(P1::dst_base(t, 0), w)] = x[w];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const int flat = e * P::CTA + tid;
+            const int s2 = flat % TPC, c = flat / TPC;
+            const int kk = R::kmap(kb, s2);
+            const long K = kk + ((long)c << LARGE_S1);
+            const float2 a = allb[R::slot_off(s2) + pad(c)];
+            if constexpr (EPI == ROW_TWIST) {
+                float2 ym;
+                if (kk == 0)
+                    ym = c == 0 ? a : allb[R::slot_off(s2) + pad(NB - c)]; // m - K = 256 (NB - c)
+                else
+                    ym = allb[R::slot_off(R::mirror_slot(kb, s2)) + pad(NB - 1 - c)];
+                if constexpr (HINT)
+                    io.twist_store_tw_hint(row, K, a, ym, rtwb[R::slot_off(s2) + pad(c)], pol.first);
+                else
+                    io.twist_store_tw(row, K, a, ym, rtwb[R::slot_off(s2) + pad(c)]);
+            } else {
+                if constexpr (HINT)
+                    io.store_hint(row, (int)K, a, pol.first);
+                else
+                    io.store(row, (int)K, a);
+            }
+        }
+    }
+
+    // rows: transforms in the batch; chunk_rows: transforms per phase; scratch: nbuf * chunk_rows * n
+    // complex; bar: arrival counter of this launch (zero at launch), unused when the launch runs one phase.
+    static KD void run(const IO &io, const Tw0 &tw0, const float2 *__restrict__ table, long rows, long chunk_rows,
+                       float2 *__restrict__ scratch, int nbuf, float2 *smem, int phase_begin, int phase_end,
+                       unsigned *bar)
+    {
+        const int tid = threadIdx.x;
+        const long n = 1L << (LARGE_S1 + LB);
+        const int kb = blockIdx.x % NKB; // column tile of pass A == k-block of pass B
+        const L2Policy pol = make_l2_policy();
+        // pass A (column-fastest mapping); its pass-1 twiddles are shared by the 16 columns -> shared memory
+        const int slotA = tid & (C::COLS - 1), tA = tid >> 4;
+        float2 *twA = smem + NBUFS * BUF;
+        if (tid < 16) {
+            TwMap map;
+            map.sh2 = LB;
+            float2 tmp[C::P1::NTW];
+            C::P1::load_tw(table, tid, tmp, map);
+#pragma unroll
+            for (int i = 0; i < C::P1::NTW; i++) twA[tid * 16 + i] = tmp[i];
+        }
+        // pass B (sub-transform-major mapping); twiddles of the CTA's k-block in registers
+        const int slotB = R::slot_of(tid), tB = tid & (R::P::T - 1);
+        const int k = R::kmap(kb, slotB);
+        TwMap mapB;
+        mapB.k0 = k;
+        mapB.sh1 = LARGE_S1;
+        float2 twB0[R::P0::NTW], twB1[R::P1::NTW];
+        R::P0::load_tw(table, tB, twB0, mapB);
+        R::P1::load_tw(table, tB, twB1, mapB);
+        float2 *buf0 = smem, *buf1 = smem + BUF;
+        const float2 *rtwb = smem + 2 * BUF;
+        R::load_rtw(io, kb, tid, smem + 2 * BUF);
+        __syncthreads();
+
+        // exchange buffers: pass A uses buf0; pass B uses buf1 (between its two register passes) and
+        // buf0 (transposed bins).  Every reuse is separated from the previous readers by a barrier.
+        float2 *bufA = buf0 + slotA * C::RS;
+        float2 *bfa = buf1 + R::slot_off(slotB), *bfb = buf0 + R::slot_off(slotB);
+        const long nchunks = (rows + chunk_rows - 1) / chunk_rows;
+        const bool split = nbuf >= 3;
+        for (int p = phase_begin; p < phase_end; p++) {
+            const long rowA0 = (long)p * chunk_rows, rowB0 = (long)(p - 1) * chunk_rows;
+            long rowsA = p < nchunks ? rows - rowA0 : 0, rowsB = p >= 1 ? rows - rowB0 : 0;
+            if (rowsA > chunk_rows) rowsA = chunk_rows;
+            if (rowsB > chunk_rows) rowsB = chunk_rows;
+            float2 *scA = scratch + (long)(p % nbuf) * chunk_rows * n;
+            const float2 *scB = scratch + (long)((p + nbuf - 1) % nbuf) * chunk_rows * n;
+            const long tilesA = rowsA << LOG_NKB, tilesB = rowsB << LOG_NKB;
+            const long tiles = tilesA > tilesB ? tilesA : tilesB;
+            const bool more = p + 1 < phase_end;
+            bool arrived = false;
+            for (long tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+                const long b = tl >> LOG_NKB;
+                if (tl < tilesA) tile_a(io, tw0, twA + tA * 16, rowA0 + b, (long)kb * C::COLS, scA + b * n, bufA, tA, slotA, pol);
+                if (more && split && tl + gridDim.x >= tilesA && !arrived) {
+                    grid_arrive(bar); // this CTA's share of chunk p is in scA
+                    arrived = true;
+                }
+                if (tl < tilesB)
+                    tile_b(io, twB0, twB1, rowB0 + b, kb, k, scB + b * n, bfa, bfb, buf0, tB, tid, rtwb, pol);
+                __syncthreads(); // buf0 is rewritten by the next tile
+            }
+            if (more) {
+                if (!arrived) grid_arrive(bar);
+                grid_wait(bar, gridDim.x * (unsigned)(p - phase_begin + 1));
+            }
+        }
+    }
+};
+
 #ifdef __CUDACC__
 template <bool EXACT, class IO, bool STAGED>
 __global__ void __launch_bounds__(256, 2)
@@ -420,6 +604,15 @@ __global__ void __launch_bounds__(256, 2)
     using F = LargeFused<LB, EXACT, IO, EPI>;
     const int rank = (int)cluster_ctarank();
     F::run(io, tw0, table, rows, scratch, smem, rank, blockIdx.x / F::CLUSTER, gridDim.x / F::CLUSTER);
+}
+template <int LB, bool EXACT, class IO, int EPI>
+__global__ void __launch_bounds__(256, 2)
+    large_pipe_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0 tw0, const float2 *__restrict__ table,
+                      long rows, long chunk_rows, float2 *__restrict__ scratch, int nbuf, int phase_begin, int phase_end,
+                      unsigned *bar)
+{
+    extern __shared__ __align__(128) float2 smem[];
+    LargePipe<LB, EXACT, IO, EPI>::run(io, tw0, table, rows, chunk_rows, scratch, nbuf, smem, phase_begin, phase_end, bar);
 }
 #endif
 

@@ -126,17 +126,63 @@ cudaError_t launch_fused(const IO &io, const LaunchArgs &a, const LargeArgs &g)
     return cudaLaunchKernelEx(&cfg, kern, io, a.tw0, a.table, g.chunk_rows, g.scratch);
 }
 
+// one persistent cooperative launch: pass A of chunk p overlapped with pass B of chunk p-1
 template <int LB, bool EXACT, class IO, int EPI>
-cudaError_t launch_both(const IO &io, const LaunchArgs &a, const LargeArgs &g)
+cudaError_t launch_pipe(const IO &io, const LaunchArgs &a, LargeArgs &g)
 {
-    if (g.fused) return launch_fused<LB, EXACT, IO, EPI>(io, a, g);
+    using F = LargePipe<LB, EXACT, IO, EPI>;
+    auto kern = large_pipe_kernel<LB, EXACT, IO, EPI>;
+    static PerDevice occ_pd;
+    int &occ = occ_pd.get();
+    cudaError_t e = prep(kern, F::SMEM_BYTES, 256, &occ);
+    if (e != cudaSuccess) return e;
+    int per_sm = occ < kMaxPipeCtasPerSm ? occ : kMaxPipeCtasPerSm;
+    long cap = a.max_ctas > 0 ? a.max_ctas : (long)per_sm * a.num_sms;
+    if (cap > (long)per_sm * a.num_sms) cap = (long)per_sm * a.num_sms; // every CTA must be resident
+    long grid = cap / F::NKB * F::NKB;
+    if (grid < F::NKB) return cudaErrorLaunchOutOfResources;
+    long rows = g.chunk_rows;
+    if (grid > rows * F::NKB) grid = rows * F::NKB;
+    long chunk_rows = (long)g.pipe_iters * (grid / F::NKB);
+    int nbuf = g.pipe_nbuf;
+    int phases = (int)((rows + chunk_rows - 1) / chunk_rows) + 1;
+    float2 *scratch = g.scratch;
+    unsigned *bar = g.bar;
+    const float2 *table = a.table;
+    if (g.pipe_coop) {
+        int p0 = 0, p1 = phases;
+        void *args[] = {(void *)&io, (void *)&a.tw0, (void *)&table, (void *)&rows, (void *)&chunk_rows,
+                        (void *)&scratch, (void *)&nbuf, (void *)&p0, (void *)&p1, (void *)&bar};
+        e = cudaMemsetAsync(bar, 0, sizeof(unsigned), a.stream);
+        if (e != cudaSuccess) return e;
+        g.launches = 1;
+        return cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(256), args, F::SMEM_BYTES, a.stream);
+    }
+    for (int p = 0; p < phases; p++) {
+        kern<<<(int)grid, 256, F::SMEM_BYTES, a.stream>>>(io, a.tw0, table, rows, chunk_rows, scratch, nbuf, p, p + 1, bar);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    g.launches = phases;
+    return cudaSuccess;
+}
+
+template <int LB, bool EXACT, class IO, int EPI>
+cudaError_t launch_both(const IO &io, const LaunchArgs &a, LargeArgs &g)
+{
+    if (g.pipe) return launch_pipe<LB, EXACT, IO, EPI>(io, a, g);
+    if (g.fused) {
+        g.launches = 1;
+        return launch_fused<LB, EXACT, IO, EPI>(io, a, g);
+    }
+    g.launches = 2;
     cudaError_t e = launch_col<EXACT>(io, a, g);
     if (e != cudaSuccess) return e;
     return launch_row<LB, EXACT, IO, EPI>(io, a, g);
 }
 
 template <int LB, bool EXACT>
-cudaError_t launch_pair(const LaunchArgs &a, const LargeArgs &g)
+cudaError_t launch_pair(const LaunchArgs &a, LargeArgs &g)
 {
     const IoArgs &q = a.io;
     switch (a.kind) {
@@ -173,7 +219,7 @@ cudaError_t launch_pair(const LaunchArgs &a, const LargeArgs &g)
 
 } // namespace
 
-cudaError_t launch_large_fft(int L, const LaunchArgs &a, const LargeArgs &g)
+cudaError_t launch_large_fft(int L, const LaunchArgs &a, LargeArgs &g)
 {
     switch (L) {
     case 15: return a.exact ? launch_pair<7, true>(a, g) : launch_pair<7, false>(a, g);

@@ -89,6 +89,12 @@ struct kofft_cuda_ctx {
     size_t istft_ws_limit = size_t(1) << 30;
     bool use_tma = true; // TMA-staged input prefetch where alignment allows
     bool large_fused = false; // N > 16384: one persistent thread-block-cluster kernel instead of two kernels per chunk
+    // N > 16384 default: one persistent cooperative kernel, pass A of chunk p overlapped with pass B of
+    // chunk p-1, intermediate pinned in L2 (fft_large.cuh LargePipe)
+    bool large_pipe = true;
+    int pipe_iters = 3, pipe_nbuf = 3;
+    bool pipe_coop = true;
+    unsigned *pipe_bar = nullptr;
     bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
     int istft_run_frames = 128;
     // host-pointer batch entry points: the batch is cut into chunks that flow through three
@@ -211,6 +217,28 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
                 }
             const size_t row_bytes = n * sizeof(float2);
             void *scratch = nullptr;
+            if (ctx->large_pipe && !ctx->large_fused) {
+                const int nkb = L == 15 ? 8 : 16;
+                const size_t chunk_max = size_t(ctx->pipe_iters) * (size_t(kMaxPipeCtasPerSm) * ctx->num_sms / nkb);
+                rc = ensure_ws(ctx, 4, size_t(ctx->pipe_nbuf) * chunk_max * row_bytes, &scratch);
+                if (rc) return rc;
+                if (!ctx->pipe_bar) CU(cudaMalloc(&ctx->pipe_bar, sizeof(unsigned)));
+                LargeArgs g;
+                g.lsub = L - 8;
+                g.row0 = 0;
+                g.chunk_rows = static_cast<long>(rows);
+                g.scratch = static_cast<float2 *>(scratch);
+                g.fused = false;
+                g.pipe = true;
+                g.pipe_iters = ctx->pipe_iters;
+                g.pipe_nbuf = ctx->pipe_nbuf;
+                g.pipe_coop = ctx->pipe_coop;
+                g.bar = ctx->pipe_bar;
+                e = launch_large_fft(L, a, g);
+                if (e != cudaSuccess) return fail_cuda(e, "large-N pipelined kernel launch");
+                ctx->launches += g.launches;
+                return KOFFT_OK;
+            }
             if (ctx->large_fused) {
                 // one persistent launch; each cluster double-buffers one transform in scratch
                 rc = ensure_ws(ctx, 4, size_t(kMaxFusedClusters) * 2 * row_bytes, &scratch);
@@ -309,6 +337,16 @@ int kofft_cuda_create(kofft_cuda_ctx **out, int device)
     kofft_cuda_ctx *ctx = new kofft_cuda_ctx();
     if (const char *mb = getenv("KOFFT_LARGE_SCRATCH_MB"))
         if (atoi(mb) > 0) ctx->large_scratch_bytes = size_t(atoi(mb)) << 20;
+    // N > 16384 path selection and tuning knobs (see kofft_cuda_set_large_mode)
+    if (const char *m = getenv("KOFFT_LARGE_MODE")) {
+        ctx->large_pipe = strcmp(m, "pipe") == 0;
+        ctx->large_fused = strcmp(m, "cluster") == 0;
+    }
+    if (const char *v = getenv("KOFFT_LARGE_PIPE_ITERS"))
+        if (atoi(v) > 0) ctx->pipe_iters = atoi(v);
+    if (const char *v = getenv("KOFFT_LARGE_PIPE_NBUF"))
+        if (atoi(v) == 2 || atoi(v) == 3) ctx->pipe_nbuf = atoi(v);
+    if (const char *v = getenv("KOFFT_LARGE_PIPE_COOP")) ctx->pipe_coop = atoi(v) != 0;
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -333,6 +371,7 @@ void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
     }
     for (int i = 0; i < 5; i++)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
+    if (ctx->pipe_bar) cudaFree(ctx->pipe_bar);
     if (ctx->pipe_ready) {
         for (int i = 0; i < 3; i++) {
             cudaStreamSynchronize(ctx->pipe_stream[i]);
@@ -376,6 +415,16 @@ int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames)
 {
     ctx->istft_fused = enable != 0;
     if (run_frames > 0) ctx->istft_run_frames = run_frames;
+    return KOFFT_OK;
+}
+int kofft_cuda_set_large_mode(kofft_cuda_ctx *ctx, int mode, int iters, int nbuf)
+{
+    if (mode < 0 || mode > 2 || (nbuf != 0 && nbuf != 2 && nbuf != 3) || iters < 0 || iters > 64)
+        return fail_msg(KOFFT_ERR_INVALID_VALUE, "set_large_mode: mode 0..2, iters 0..64, nbuf 0, 2 or 3");
+    ctx->large_pipe = mode == 2;
+    ctx->large_fused = mode == 1;
+    if (iters > 0) ctx->pipe_iters = iters;
+    if (nbuf > 0) ctx->pipe_nbuf = nbuf;
     return KOFFT_OK;
 }
 int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable)

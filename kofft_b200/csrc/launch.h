@@ -73,10 +73,20 @@ struct LargeArgs {
     bool fused = true;         // one persistent cluster kernel instead of two kernels per chunk
     int max_clusters = 0;      // fused path: 0 = as many clusters as fit on the device
     bool stage_rows = true;    // two-kernel path: row pass prefetches its next tile with TMA bulk copies
+    // pipelined persistent kernel (LargePipe): chunk_rows = every transform of the batch, scratch =
+    // pipe_nbuf * pipe_iters * (kMaxPipeCtas / NKB) * 2^L complex, bar = zeroed arrival counter
+    bool pipe = false;
+    int pipe_iters = 3;        // tiles per CTA per phase
+    int pipe_nbuf = 3;         // intermediate buffers (3: split arrive/wait barrier, 2: plain barrier)
+    bool pipe_coop = true;     // one cooperative launch; false: one launch per phase
+    unsigned *bar = nullptr;
+    int launches = 0;          // out: kernels launched
 };
+// upper bound on the CTAs of the pipelined kernel per SM (sizes its scratch)
+constexpr int kMaxPipeCtasPerSm = 2;
 // upper bound on the clusters the fused kernel runs with (sizes its scratch)
 constexpr int kMaxFusedClusters = 148;
-cudaError_t launch_large_fft(int L, const LaunchArgs &a, const LargeArgs &g);
+cudaError_t launch_large_fft(int L, const LaunchArgs &a, LargeArgs &g);
 
 // per-L entry points (one per fft_inst.cu build)
 #define KOFFT_DECL_L(L) cudaError_t launch_cta_fft_L##L(const LaunchArgs &a);

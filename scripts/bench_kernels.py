@@ -1,5 +1,5 @@
 """Times the device-pointer kernels of every BASELINE config shape (CUDA events, data resident in HBM).
-   python scripts/bench_kernels.py [which ...]    which: c2c c2c2048 stft istft rfft large   (default: all)
+   python scripts/bench_kernels.py [which ...]    which: c2c c2c2048 stft stftmag istft rfft large [pipesweep]   (default: all but pipesweep)
 Prints one JSON line per measurement.  Used to compare tuning variants (KOFFT_CUDA_LIB=...)."""
 import json
 import os
@@ -88,25 +88,38 @@ def main():
                 fft.ctx.set_istft_fusion(True)
                 del out
             del sig, frames
+        modes = [("pipelined", 2), ("two_kernel", 0), ("cluster", 1)]
         if "rfft" in which:
             x = (torch.rand((16384, 65536), generator=g, device="cuda") * 2 - 1).contiguous()
             out = torch.empty((16384, 32769), dtype=torch.complex64, device="cuda")
             nbytes = x.numel() * 4 + out.numel() * 8
-            for fused in (True, False):
-                fft.ctx.set_cluster_fusion(fused)
+            for name, m in modes:
+                fft.ctx.set_large_mode(m)
                 ms, best = timeit(lambda: fft.rfft_batch(x, out=out), 6, 2)
-                report("rfft_65536x16384_" + ("cluster" if fused else "two_kernel"), mode, ms, best, nbytes)
-            fft.ctx.set_cluster_fusion(True)
+                report("rfft_65536x16384_" + name, mode, ms, best, nbytes)
+            if "pipesweep" in which:
+                for nbuf in (3, 2):
+                    for iters in (1, 2, 3, 4, 6, 8):
+                        fft.ctx.set_large_mode(2, iters, nbuf)
+                        ms, best = timeit(lambda: fft.rfft_batch(x, out=out), 6, 2)
+                        report(f"rfft_65536x16384_pipelined_iters{iters}_nbuf{nbuf}", mode, ms, best, nbytes)
+            fft.ctx.set_large_mode(2, 3, 3)
             del x, out
         if "large" in which:
             for n in (32768, 65536):
                 x = torch.view_as_complex(torch.rand((2 ** 28 // n, n, 2), generator=g, device="cuda") * 2 - 1).contiguous()
                 y = torch.empty_like(x)
-                for fused in (True, False):
-                    fft.ctx.set_cluster_fusion(fused)
+                for name, m in modes:
+                    fft.ctx.set_large_mode(m)
                     ms, best = timeit(lambda: fft.fft_batch(x, out=y), 6, 2)
-                    report(f"c2c_{n}x{2 ** 28 // n}_" + ("cluster" if fused else "two_kernel"), mode, ms, best, 2 * x.numel() * 8)
-                fft.ctx.set_cluster_fusion(True)
+                    report(f"c2c_{n}x{2 ** 28 // n}_" + name, mode, ms, best, 2 * x.numel() * 8)
+                if "pipesweep" in which:
+                    for nbuf in (3, 2):
+                        for iters in (1, 2, 4, 8):
+                            fft.ctx.set_large_mode(2, iters, nbuf)
+                            ms, best = timeit(lambda: fft.fft_batch(x, out=y), 6, 2)
+                            report(f"c2c_{n}x{2 ** 28 // n}_pipelined_iters{iters}_nbuf{nbuf}", mode, ms, best, 2 * x.numel() * 8)
+                fft.ctx.set_large_mode(2, 3, 3)
                 del x, y
         fft.close() if hasattr(fft, "close") else None
 

@@ -34,7 +34,7 @@ elif which == "istft":
     for _ in range(4):
         S.istft_batch(fft, frames, w, hop, out)
 elif which == "rfft2":  # two-kernel large-N path (column pass + row pass per L2-sized chunk)
-    fft.ctx.set_cluster_fusion(False)
+    fft.ctx.set_large_mode(0)
     x = (torch.rand((4096, 65536), generator=g, device="cuda") * 2 - 1).contiguous()
     for _ in range(3):
         fft.rfft_batch(x)

@@ -132,11 +132,40 @@ int run_fused(const IO &io, const float *table, long rows, int nclusters)
     return 0;
 }
 
+// the pipelined persistent kernel body (LargePipe::run), one emulated launch per phase: `grid` CTAs,
+// `iters` tiles per CTA per phase, `nbuf` intermediate buffers
+static bool g_pipe = false;
+static int g_pipe_iters = 1, g_pipe_nbuf = 3;
+
+template <int LB, bool EXACT, class IO, int EPI>
+int run_pipe(const IO &io, const float *table, long rows, int grid)
+{
+    using F = LargePipe<LB, EXACT, IO, EPI>;
+    const int L = LB + LARGE_S1;
+    const long n = 1L << L;
+    Tw0 tw0 = make_tw0(L, 4, table);
+    const float2 *tab = reinterpret_cast<const float2 *>(table);
+    grid = grid / F::NKB * F::NKB;
+    if (grid < F::NKB) grid = F::NKB;
+    if (grid > rows * F::NKB) grid = (int)(rows * F::NKB);
+    const long chunk_rows = (long)g_pipe_iters * (grid / F::NKB);
+    const int phases = (int)((rows + chunk_rows - 1) / chunk_rows) + 1;
+    std::vector<float2> scratch((size_t)g_pipe_nbuf * chunk_rows * n);
+    std::vector<float2> smem((F::SMEM_BYTES + 256) / 8);
+    float2 *sm = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
+    for (int p = 0; p < phases; p++)
+        cuda_emu::launch((unsigned)grid, 256, [&] {
+            F::run(io, tw0, tab, rows, chunk_rows, scratch.data(), g_pipe_nbuf, sm, p, p + 1, nullptr);
+        });
+    return 0;
+}
+
 static bool g_fused = false;
 
 template <int LB, bool EXACT, class IO, int EPI>
 int run_large_any(const IO &io, const float *table, long rows, int gc, int gr)
 {
+    if (g_pipe) return run_pipe<LB, EXACT, IO, EPI>(io, table, rows, gc);
     return g_fused ? run_fused<LB, EXACT, IO, EPI>(io, table, rows, gc) : run_large<LB, EXACT, IO, EPI>(io, table, rows, gc, gr);
 }
 
@@ -186,6 +215,12 @@ API int kofft_emuk_cta(int kind, int exact, int L, long rows, const void *in, co
 }
 
 API void kofft_emuk_set_fused(int fused) { g_fused = fused != 0; }
+API void kofft_emuk_set_pipe(int pipe, int iters, int nbuf)
+{
+    g_pipe = pipe != 0;
+    g_pipe_iters = iters > 0 ? iters : 1;
+    g_pipe_nbuf = nbuf == 2 ? 2 : 3;
+}
 API void kofft_emuk_set_large_staged(int staged) { g_large_staged = staged != 0; }
 
 // the real two-pass kernel bodies; L = 15 or 16 is the length of the complex core

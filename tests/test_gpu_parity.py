@@ -666,25 +666,63 @@ def test_large_c2c(cuda_fft, cuda_fft_fast, oracle, n):
 
 
 @pytest.mark.parametrize("n", [32768, 65536])
-def test_large_cluster_fused_and_two_kernel_paths_agree(cuda_fft, oracle, n):
-    """N > 16384 runs as one persistent thread-block-cluster kernel by default; the two-kernel
-    chunked path is the fallback.  Both must be bit-identical to the oracle (enough rows that
-    every cluster iterates several times)."""
+def test_large_paths_agree(cuda_fft, oracle, n):
+    """N > 16384 runs as one persistent pipelined kernel (pass A of chunk p overlapped with pass B
+    of chunk p-1, grid barrier between phases) by default; the two-kernel chunked path and the
+    thread-block-cluster kernel are kept for comparison.  All must be bit-identical to the oracle
+    (enough rows that the pipelined kernel runs several phases and every cluster iterates)."""
     rng = np.random.default_rng(n + 1)
     rows = 150
     x = uniform_c64(rng, (rows, n))
     ref = oracle.fft_batch(x, nthreads=8)
+    iref = oracle.fft_batch(x, inverse=True, nthreads=8)
     xr = rng.uniform(-1, 1, (rows, 2 * n)).astype(np.float32)
     rref = oracle.rfft_batch(xr, nthreads=8)
+    bref = oracle.irfft_batch(rref, 2 * n, nthreads=8)
+    C = cuda_fft.ctx
     try:
-        for fused in (True, False):
-            cuda_fft.ctx.set_cluster_fusion(fused)
+        for mode, iters, nbuf in ((C.LARGE_PIPELINED, 1, 3), (C.LARGE_PIPELINED, 1, 2), (C.LARGE_PIPELINED, 3, 3),
+                                  (C.LARGE_CLUSTER, 0, 0), (C.LARGE_TWO_KERNEL, 0, 0)):
+            C.set_cluster_fusion(False)
+            C.set_large_mode(mode, iters, nbuf)
+            tag = f"mode={mode} iters={iters} nbuf={nbuf}"
             y = x.copy()
             cuda_fft.fft_batch(y)
-            assert np.array_equal(y, ref), f"fused={fused}"
-            assert np.array_equal(cuda_fft.rfft_batch(xr), rref), f"fused={fused}"
+            assert np.array_equal(y, ref), tag
+            y = x.copy()
+            cuda_fft.fft_batch(y, inverse=True)
+            assert np.array_equal(y, iref), tag
+            assert np.array_equal(cuda_fft.rfft_batch(xr), rref), tag
+            assert np.array_equal(cuda_fft.irfft_batch(rref, 2 * n), bref), tag
     finally:
-        cuda_fft.ctx.set_cluster_fusion(True)
+        C.set_large_mode(C.LARGE_PIPELINED, 3, 3)
+
+
+def test_large_pipelined_many_phases_on_device(cuda_fft, oracle):
+    """The pipelined kernel on device-resident rows, ~40 phases, every mode of the barrier: sampled
+    rows bit-identical to the oracle, and the whole batch identical across (iters, nbuf)."""
+    import torch
+
+    n, rows = 32768, 1500
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.view_as_complex((torch.rand((rows, n, 2), generator=g, device="cuda") * 2 - 1).contiguous())
+    C = cuda_fft.ctx
+    outs = []
+    try:
+        for iters, nbuf in ((1, 3), (1, 2), (2, 3), (4, 2)):
+            C.set_large_mode(C.LARGE_PIPELINED, iters, nbuf)
+            y = torch.empty_like(x)
+            for _ in range(3):  # repeated launches reuse the arrival counter
+                cuda_fft.fft_batch(x, out=y)
+            torch.cuda.synchronize()
+            outs.append(y)
+    finally:
+        C.set_large_mode(C.LARGE_PIPELINED, 3, 3)
+    pick = [0, 1, 36, 37, 73, 74, 700, rows - 2, rows - 1]
+    ref = oracle.fft_batch(x[pick].cpu().numpy(), nthreads=8)
+    assert np.array_equal(outs[0][pick].cpu().numpy(), ref)
+    for y in outs[1:]:
+        assert torch.equal(torch.view_as_real(y), torch.view_as_real(outs[0]))
 
 
 @pytest.mark.parametrize("n", [65536, 131072])
