@@ -395,22 +395,30 @@ struct LargeFused {
 
 // ---------------------------------------------------------------------------------------------
 // Both passes in ONE persistent kernel, software-pipelined over batch chunks ("phases"):
-//     phase p:  pass A of chunk p   (HBM -> intermediate buffer p mod NBUF)
-//               pass B of chunk p-1 (intermediate buffer (p-1) mod NBUF -> HBM)
-// with a grid-wide barrier between phases (all CTAs co-resident: cooperative launch).  A chunk is
-// a few tiles per CTA, so the NBUF intermediate buffers are a few tens of MB: they are written
-// with the L2 evict_last policy and the rows stream through with evict_first, so the
-// intermediate never makes the round trip to HBM (the two-kernel path above needs long launches
-// to amortise launch + ramp + tail, and at those chunk sizes the intermediate spills: measured
-// 2x the algorithmic DRAM traffic, profiles/r01u_rfft_*pass_kernel.json).  With NBUF = 3 the
-// barrier is split: a CTA arrives after its last pass-A tile of the phase and waits only after
-// its last pass-B tile, so the skew between CTAs is hidden behind useful work.
+//     phase p:  wait until every CTA has arrived in phase p-1
+//               pass A of chunk p   (HBM -> intermediate buffer p mod 3), then ARRIVE
+//               pass B of chunk p-1 (intermediate buffer (p-1) mod 3 -> HBM)
+// All CTAs are co-resident (cooperative launch); the grid barrier is split, so the whole pass-B
+// part of a phase separates a CTA's arrival from its next wait and the skew between CTAs is
+// hidden behind useful work.  A chunk is a few tiles per CTA, so the three intermediate buffers
+// are a few tens of MB: they are written with the L2 evict_last policy and the rows stream
+// through with evict_first, so the intermediate is never read back from HBM (the two-kernel path
+// above needs long launches to amortise launch + ramp + tail, and at those chunk sizes the
+// intermediate spills: 2x the algorithmic DRAM traffic, profiles/r01u_rfft_*pass_kernel.json).
+// Buffer reuse: pass A of phase p overwrites the buffer pass B read in phase p-2; a CTA starts
+// phase p only after every CTA has arrived in phase p-1, i.e. has finished phase p-2.
+//
 // CTA j keeps column tile / k-block  j mod NKB  for its lifetime (the grid is a multiple of NKB),
 // so its pass-B twiddles stay in registers and its rfft-table slice in shared memory.
+// Shared memory: two exchange buffers (+ the T' slice for the twist).  Pass A exchanges through
+// buf0 and (STAGED) uses the idle buf1 as the landing zone of its next tile, fetched with 16-byte
+// asynchronous copies while the current tile is transformed -- the first tile of a phase is
+// requested during the last pass-B tile of the previous phase.  Pass B exchanges through buf1
+// (between its register passes) and buf0 (transposed bins).
 // phase_begin/phase_end: the phases this launch runs (one launch runs them all; the CPU emulator
 // and the non-cooperative fallback run one phase per launch, the launch boundary being the barrier).
 // ---------------------------------------------------------------------------------------------
-template <int LB, bool EXACT, class IO, int EPI>
+template <int LB, bool EXACT, class IO, int EPI, bool STAGED = false>
 struct LargePipe {
     using C = ColPass<EXACT, IO>;
     using R = RowPass<LB, EXACT, IO, EPI>;
@@ -419,31 +427,60 @@ struct LargePipe {
     static_assert((1 << LB) / C::COLS == NKB, "one column tile per k-block");
     static constexpr int BUFA = C::COLS * C::RS;
     static constexpr int BUF = (BUFA > R::BUF ? BUFA : R::BUF); // float2 per exchange buffer
+    static_assert(BUF * 8 >= C::STAGE_BYTES, "the idle exchange buffer holds pass A's next tile");
     static constexpr int NBUFS = EPI == ROW_TWIST ? 3 : 2;      // twist: + the CTA's rfft twiddles
     static constexpr int TW_SMEM = 16 * 16;                     // pass-A pass-1 twiddles: [t][15] float2
     static constexpr int SMEM_BYTES = (NBUFS * BUF + TW_SMEM) * 8;
     static constexpr bool HINT = IoTraits<IO>::kHint;
+    static_assert(!STAGED || IoTraits<IO>::kRowPtr, "staging needs plain contiguous rows");
+    static constexpr int NIBUF = 3; // intermediate buffers
 
-    // pass A tile (ColPass::tile with L2 hints): 16 adjacent columns of transform `row` -> scratch_row
+    // thread i copies 16-byte piece (i & 7) of rows (i >> 3) + 32 m, m = 0..7, of the tile
+    // [256 rows][16 columns] starting at column j0 of transform `row`
+    static KD void prefetch_a(const IO &io, long row, long j0, float2 *stage, int tid, const L2Policy &pol)
+    {
+        if constexpr (STAGED) {
+            const float2 *src = io.row_ptr(row) + j0 + 2 * (tid & 7);
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int r = (tid >> 3) + 32 * m;
+                cp_async16_hint(stage + r * C::COLS + 2 * (tid & 7), src + ((long)r << LB), pol.first);
+            }
+            cp_async_commit();
+        }
+    }
+
+    // pass A tile: 16 adjacent columns of transform `row` -> scratch_row.  STAGED: the tile is in
+    // `stage`; after the exchange barrier (stage consumed by everyone) next() issues the next prefetch.
+    template <class Next>
     static KD void tile_a(const IO &io, const Tw0 &tw0, const float2 *tw1, long row, long j0,
-                          float2 *__restrict__ scratch_row, float2 *bf, int t, int slot, const L2Policy &pol)
+                          float2 *__restrict__ scratch_row, float2 *bf, const float2 *stage, int t, int slot,
+                          const L2Policy &pol, Next next)
     {
         using P0 = typename C::P0;
         using P1 = typename C::P1;
         const long j = j0 + slot;
         float2 x[EPT];
+        if constexpr (STAGED) {
+            cp_async_wait_all();
+            __syncthreads(); // every thread's pieces have landed; the previous tile's readers of bf are done
 #pragma unroll
-        for (int q = 0; q < P0::R; q++) {
-            const int idx = (int)(((long)P0::src_index(t, 0, q) << LB) + j);
-            if constexpr (HINT)
-                x[q] = io.load_hint(row, idx, pol.first);
-            else
-                x[q] = io.load(row, idx);
+            for (int q = 0; q < P0::R; q++) x[q] = io.from_raw(stage[P0::src_index(t, 0, q) * C::COLS + slot]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < P0::R; q++) {
+                const int idx = (int)(((long)P0::src_index(t, 0, q) << LB) + j);
+                if constexpr (HINT)
+                    x[q] = io.load_hint(row, idx, pol.first);
+                else
+                    x[q] = io.load(row, idx);
+            }
         }
         P0::compute(x, tw0.v);
 #pragma unroll
         for (int w = 0; w < P0::R; w++) bf[P0::dst_pad(P0::dst_base(t, 0), w)] = x[w];
         __syncthreads();
+        next();
 #pragma unroll
         for (int q = 0; q < P1::R; q++) x[q] = bf[P1::src_pad(P1::src_base(t, 0), q)];
         P1::compute(x, tw1);
@@ -452,18 +489,30 @@ struct LargePipe {
         for (int w = 0; w < P1::R; w++) stg_hint(o + ((long)P1::dst_index(t, 0, w) << LB), x[w], pol.last);
     }
 
-    // pass B tile (RowPass::tile with L2 hints): bfa / bfb are this thread's exchange regions in two
-    // different buffers, allb is bfb's buffer seen CTA-wide, rtwb the CTA's slice of T' (twist only)
-    static KD void tile_b(const IO &io, const float2 *tw0, const float2 *tw1, long row, int kb, int k,
+    // Per-thread constants of pass B's transposed epilogue.  Element e of thread tid is bin
+    // c = c0 + STEP e of sub-transform slot s2, with s2 = tid mod TPC and c0 = tid / TPC fixed for the
+    // thread's lifetime, so every shared-memory and output address is "base + compile-time offset".
+    static constexpr int STEP = R::P::CTA / R::TPC;                        // 8 or 16 bins between a thread's elements
+    static constexpr int cpad(int e) { return STEP * e + ((STEP * e) >> 4); } // pad(c0 + STEP e) - c0   (c0 < STEP <= 16)
+    static constexpr int mpad(int e) { return R::NB - 2 + (R::NB >> 4) - cpad(e); } // pad(NB-1-c) + c0
+    struct Epi {
+        int own, mir; // float2 offsets into a buffer: slot_off(s2) + c0, slot_off(mirror) - c0
+        int kk, c0;   // this thread's k and first bin
+    };
+
+    // pass B tile: bfa / bfb are this thread's exchange regions (buf1 / buf0), allb is buf0 seen
+    // CTA-wide, rtwb the CTA's slice of T' (twist only).  after_exchange(): called by every thread
+    // right after the second barrier (buf1 is free from there on).
+    template <class After>
+    static KD void tile_b(const IO &io, const float2 *tw0, const float2 *tw1, long row, int kb,
                           const float2 *__restrict__ scratch_row, float2 *bfa, float2 *bfb, const float2 *allb, int t,
-                          int tid, const float2 *rtwb, const L2Policy &pol)
+                          const Epi &ep, const float2 *rtwb, const L2Policy &pol, After after_exchange)
     {
-        using P = typename R::P;
         using P0 = typename R::P0;
         using P1 = typename R::P1;
-        constexpr int NB = R::NB, TPC = R::TPC;
+        constexpr int NB = R::NB;
         float2 x[EPT];
-        const float2 *in = scratch_row + (long)k * NB;
+        const float2 *in = scratch_row;
 #pragma unroll
         for (int u = 0; u < P0::U; u++)
 #pragma unroll
@@ -480,37 +529,52 @@ struct LargePipe {
 #pragma unroll
         for (int w = 0; w < P1::R; w++) bfb[P1::dst_pad(P1::dst_base(t, 0), w)] = x[w];
         __syncthreads();
+        after_exchange();
+        // transposed read-back: bins of all TPC sub-transforms, k fastest -> 128-byte store runs
+        const float2 *pa = allb + ep.own;
+        if constexpr (EPI == ROW_TWIST) {
+            const float2 *pr = rtwb + ep.own;
+            const float2 *pm = allb + ep.mir;
+            if (ep.kk == 0) { // lane 0 of the k-block-0 CTAs: mirror inside the own sub-transform, bins 0 and m
+                (void)kb;
 #pragma unroll
-        for (int e = 0; e < EPT; e++) {
-            const int flat = e * P::CTA + tid;
-            const int s2 = flat % TPC, c = flat / TPC;
-            const int kk = R::kmap(kb, s2);
-            const long K = kk + ((long)c << LARGE_S1);
-            const float2 a = allb[R::slot_off(s2) + pad(c)];
-            if constexpr (EPI == ROW_TWIST) {
-                float2 ym;
-                if (kk == 0)
-                    ym = c == 0 ? a : allb[R::slot_off(s2) + pad(NB - c)]; // m - K = 256 (NB - c)
-                else
-                    ym = allb[R::slot_off(R::mirror_slot(kb, s2)) + pad(NB - 1 - c)];
-                if constexpr (HINT)
-                    io.twist_store_tw_hint(row, K, a, ym, rtwb[R::slot_off(s2) + pad(c)], pol.first);
-                else
-                    io.twist_store_tw(row, K, a, ym, rtwb[R::slot_off(s2) + pad(c)]);
+                for (int e = 0; e < EPT; e++) {
+                    const int c = ep.c0 + STEP * e;
+                    const float2 a = pa[cpad(e)];
+                    const float2 ym = c == 0 ? a : allb[ep.own - ep.c0 + pad(NB - c)]; // m - K = 256 (NB - c)
+                    const long K = (long)c << LARGE_S1;
+                    if constexpr (HINT)
+                        io.twist_store_tw_hint(row, K, a, ym, pr[cpad(e)], pol.first);
+                    else
+                        io.twist_store_tw(row, K, a, ym, pr[cpad(e)]);
+                }
             } else {
+                float2 *o = io.out + row * (io.m + 1) + ep.kk + ((long)ep.c0 << LARGE_S1);
+#pragma unroll
+                for (int e = 0; e < EPT; e++) {
+                    const float2 v = io.twist(pa[cpad(e)], pm[mpad(e)], pr[cpad(e)]);
+                    if constexpr (HINT)
+                        stg_hint(o + ((long)(STEP * e) << LARGE_S1), v, pol.first);
+                    else
+                        o[(long)(STEP * e) << LARGE_S1] = v;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPT; e++) {
+                const int K = ep.kk + ((ep.c0 + STEP * e) << LARGE_S1);
                 if constexpr (HINT)
-                    io.store_hint(row, (int)K, a, pol.first);
+                    io.store_hint(row, K, pa[cpad(e)], pol.first);
                 else
-                    io.store(row, (int)K, a);
+                    io.store(row, K, pa[cpad(e)]);
             }
         }
     }
 
-    // rows: transforms in the batch; chunk_rows: transforms per phase; scratch: nbuf * chunk_rows * n
+    // rows: transforms in the batch; chunk_rows: transforms per phase; scratch: 3 * chunk_rows * n
     // complex; bar: arrival counter of this launch (zero at launch), unused when the launch runs one phase.
     static KD void run(const IO &io, const Tw0 &tw0, const float2 *__restrict__ table, long rows, long chunk_rows,
-                       float2 *__restrict__ scratch, int nbuf, float2 *smem, int phase_begin, int phase_end,
-                       unsigned *bar)
+                       float2 *__restrict__ scratch, float2 *smem, int phase_begin, int phase_end, unsigned *bar)
     {
         const int tid = threadIdx.x;
         const long n = 1L << (LARGE_S1 + LB);
@@ -539,40 +603,59 @@ struct LargePipe {
         float2 *buf0 = smem, *buf1 = smem + BUF;
         const float2 *rtwb = smem + 2 * BUF;
         R::load_rtw(io, kb, tid, smem + 2 * BUF);
+        Epi ep;
+        {
+            const int s2 = tid % R::TPC;
+            ep.c0 = tid / R::TPC;
+            ep.kk = R::kmap(kb, s2);
+            ep.own = R::slot_off(s2) + ep.c0;
+            ep.mir = EPI == ROW_TWIST ? R::slot_off(R::mirror_slot(kb, s2)) - ep.c0 : 0;
+        }
         __syncthreads();
 
-        // exchange buffers: pass A uses buf0; pass B uses buf1 (between its two register passes) and
-        // buf0 (transposed bins).  Every reuse is separated from the previous readers by a barrier.
         float2 *bufA = buf0 + slotA * C::RS;
         float2 *bfa = buf1 + R::slot_off(slotB), *bfb = buf0 + R::slot_off(slotB);
         const long nchunks = (rows + chunk_rows - 1) / chunk_rows;
-        const bool split = nbuf >= 3;
+        const long j0 = (long)kb * C::COLS;
+        // tiles of a chunk this CTA owns: tl = blockIdx.x + i * gridDim.x  (transform tl >> LOG_NKB)
+        auto chunk_tiles = [&](long p) -> long {
+            if (p < 0 || p >= nchunks) return 0;
+            long r = rows - p * chunk_rows;
+            return (r > chunk_rows ? chunk_rows : r) << LOG_NKB;
+        };
+        if (STAGED && phase_begin < nchunks && (long)blockIdx.x < chunk_tiles(phase_begin))
+            prefetch_a(io, (long)phase_begin * chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid, pol);
         for (int p = phase_begin; p < phase_end; p++) {
             const long rowA0 = (long)p * chunk_rows, rowB0 = (long)(p - 1) * chunk_rows;
-            long rowsA = p < nchunks ? rows - rowA0 : 0, rowsB = p >= 1 ? rows - rowB0 : 0;
-            if (rowsA > chunk_rows) rowsA = chunk_rows;
-            if (rowsB > chunk_rows) rowsB = chunk_rows;
-            float2 *scA = scratch + (long)(p % nbuf) * chunk_rows * n;
-            const float2 *scB = scratch + (long)((p + nbuf - 1) % nbuf) * chunk_rows * n;
-            const long tilesA = rowsA << LOG_NKB, tilesB = rowsB << LOG_NKB;
-            const long tiles = tilesA > tilesB ? tilesA : tilesB;
+            float2 *scA = scratch + (long)(p % NIBUF) * chunk_rows * n;
+            const float2 *scB = scratch + (long)((p + NIBUF - 1) % NIBUF) * chunk_rows * n;
+            const long tilesA = chunk_tiles(p), tilesB = chunk_tiles(p - 1), tilesA1 = chunk_tiles(p + 1);
             const bool more = p + 1 < phase_end;
-            bool arrived = false;
-            for (long tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+            if (p > phase_begin) grid_wait(bar, gridDim.x * (unsigned)(p - phase_begin));
+            for (long tl = blockIdx.x; tl < tilesA; tl += gridDim.x) {
                 const long b = tl >> LOG_NKB;
-                if (tl < tilesA) tile_a(io, tw0, twA + tA * 16, rowA0 + b, (long)kb * C::COLS, scA + b * n, bufA, tA, slotA, pol);
-                if (more && split && tl + gridDim.x >= tilesA && !arrived) {
-                    grid_arrive(bar); // this CTA's share of chunk p is in scA
-                    arrived = true;
-                }
-                if (tl < tilesB)
-                    tile_b(io, twB0, twB1, rowB0 + b, kb, k, scB + b * n, bfa, bfb, buf0, tB, tid, rtwb, pol);
-                __syncthreads(); // buf0 is rewritten by the next tile
+                const long nx = tl + gridDim.x;
+                tile_a(io, tw0, twA + tA * 16, rowA0 + b, j0, scA + b * n, bufA, buf1, tA, slotA, pol, [&] {
+                    if (nx < tilesA) prefetch_a(io, rowA0 + (nx >> LOG_NKB), j0, buf1, tid, pol);
+                });
+                if (!STAGED) __syncthreads(); // buf0 is rewritten by the next tile
             }
-            if (more) {
-                if (!arrived) grid_arrive(bar);
-                grid_wait(bar, gridDim.x * (unsigned)(p - phase_begin + 1));
+            if (more) grid_arrive(bar); // this CTA's share of chunk p is in scA
+            if (STAGED && tilesA > 0) __syncthreads(); // pass B rewrites buf0
+            for (long tl = blockIdx.x; tl < tilesB; tl += gridDim.x) {
+                const long b = tl >> LOG_NKB;
+                const bool last = tl + gridDim.x >= tilesB;
+                tile_b(io, twB0, twB1, rowB0 + b, kb, scB + b * n + (long)k * R::NB, bfa, bfb, buf0, tB, ep, rtwb, pol, [&] {
+                    // buf1 is idle from here to the next pass-B tile: the last one of the phase requests
+                    // the first pass-A tile of the next phase (only if this launch runs that phase)
+                    if (last && more && (long)blockIdx.x < tilesA1)
+                        prefetch_a(io, rowA0 + chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid, pol);
+                });
+                __syncthreads(); // both buffers are rewritten by the next tile
             }
+            // no pass-B tile in this phase (first phase, or fewer tiles than CTAs): request it here
+            if (more && tilesB <= (long)blockIdx.x && (long)blockIdx.x < tilesA1)
+                prefetch_a(io, rowA0 + chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid, pol);
         }
     }
 };
@@ -605,14 +688,14 @@ __global__ void __launch_bounds__(256, 2)
     const int rank = (int)cluster_ctarank();
     F::run(io, tw0, table, rows, scratch, smem, rank, blockIdx.x / F::CLUSTER, gridDim.x / F::CLUSTER);
 }
-template <int LB, bool EXACT, class IO, int EPI>
+template <int LB, bool EXACT, class IO, int EPI, bool STAGED>
 __global__ void __launch_bounds__(256, 2)
     large_pipe_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0 tw0, const float2 *__restrict__ table,
-                      long rows, long chunk_rows, float2 *__restrict__ scratch, int nbuf, int phase_begin, int phase_end,
+                      long rows, long chunk_rows, float2 *__restrict__ scratch, int phase_begin, int phase_end,
                       unsigned *bar)
 {
     extern __shared__ __align__(128) float2 smem[];
-    LargePipe<LB, EXACT, IO, EPI>::run(io, tw0, table, rows, chunk_rows, scratch, nbuf, smem, phase_begin, phase_end, bar);
+    LargePipe<LB, EXACT, IO, EPI, STAGED>::run(io, tw0, table, rows, chunk_rows, scratch, smem, phase_begin, phase_end, bar);
 }
 #endif
 

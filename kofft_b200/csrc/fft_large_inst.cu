@@ -127,11 +127,11 @@ cudaError_t launch_fused(const IO &io, const LaunchArgs &a, const LargeArgs &g)
 }
 
 // one persistent cooperative launch: pass A of chunk p overlapped with pass B of chunk p-1
-template <int LB, bool EXACT, class IO, int EPI>
-cudaError_t launch_pipe(const IO &io, const LaunchArgs &a, LargeArgs &g)
+template <int LB, bool EXACT, class IO, int EPI, bool STAGED>
+cudaError_t launch_pipe_v(const IO &io, const LaunchArgs &a, LargeArgs &g)
 {
-    using F = LargePipe<LB, EXACT, IO, EPI>;
-    auto kern = large_pipe_kernel<LB, EXACT, IO, EPI>;
+    using F = LargePipe<LB, EXACT, IO, EPI, STAGED>;
+    auto kern = large_pipe_kernel<LB, EXACT, IO, EPI, STAGED>;
     static PerDevice occ_pd;
     int &occ = occ_pd.get();
     cudaError_t e = prep(kern, F::SMEM_BYTES, 256, &occ);
@@ -144,7 +144,6 @@ cudaError_t launch_pipe(const IO &io, const LaunchArgs &a, LargeArgs &g)
     long rows = g.chunk_rows;
     if (grid > rows * F::NKB) grid = rows * F::NKB;
     long chunk_rows = (long)g.pipe_iters * (grid / F::NKB);
-    int nbuf = g.pipe_nbuf;
     int phases = (int)((rows + chunk_rows - 1) / chunk_rows) + 1;
     float2 *scratch = g.scratch;
     unsigned *bar = g.bar;
@@ -152,19 +151,29 @@ cudaError_t launch_pipe(const IO &io, const LaunchArgs &a, LargeArgs &g)
     if (g.pipe_coop) {
         int p0 = 0, p1 = phases;
         void *args[] = {(void *)&io, (void *)&a.tw0, (void *)&table, (void *)&rows, (void *)&chunk_rows,
-                        (void *)&scratch, (void *)&nbuf, (void *)&p0, (void *)&p1, (void *)&bar};
+                        (void *)&scratch, (void *)&p0, (void *)&p1, (void *)&bar};
         e = cudaMemsetAsync(bar, 0, sizeof(unsigned), a.stream);
         if (e != cudaSuccess) return e;
         g.launches = 1;
         return cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(256), args, F::SMEM_BYTES, a.stream);
     }
     for (int p = 0; p < phases; p++) {
-        kern<<<(int)grid, 256, F::SMEM_BYTES, a.stream>>>(io, a.tw0, table, rows, chunk_rows, scratch, nbuf, p, p + 1, bar);
+        kern<<<(int)grid, 256, F::SMEM_BYTES, a.stream>>>(io, a.tw0, table, rows, chunk_rows, scratch, p, p + 1, bar);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     g.launches = phases;
     return cudaSuccess;
+}
+
+// a.staged: the host verified 16-byte alignment of the rows (asynchronous 16-byte copies)
+template <int LB, bool EXACT, class IO, int EPI>
+cudaError_t launch_pipe(const IO &io, const LaunchArgs &a, LargeArgs &g)
+{
+    if constexpr (IoTraits<IO>::kRowPtr) {
+        if (a.staged) return launch_pipe_v<LB, EXACT, IO, EPI, true>(io, a, g);
+    }
+    return launch_pipe_v<LB, EXACT, IO, EPI, false>(io, a, g);
 }
 
 template <int LB, bool EXACT, class IO, int EPI>

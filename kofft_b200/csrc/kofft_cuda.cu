@@ -92,7 +92,7 @@ struct kofft_cuda_ctx {
     // N > 16384 default: one persistent cooperative kernel, pass A of chunk p overlapped with pass B of
     // chunk p-1, intermediate pinned in L2 (fft_large.cuh LargePipe)
     bool large_pipe = true;
-    int pipe_iters = 3, pipe_nbuf = 3;
+    int pipe_iters = 3;
     bool pipe_coop = true;
     unsigned *pipe_bar = nullptr;
     bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
@@ -220,7 +220,7 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
             if (ctx->large_pipe && !ctx->large_fused) {
                 const int nkb = L == 15 ? 8 : 16;
                 const size_t chunk_max = size_t(ctx->pipe_iters) * (size_t(kMaxPipeCtasPerSm) * ctx->num_sms / nkb);
-                rc = ensure_ws(ctx, 4, size_t(ctx->pipe_nbuf) * chunk_max * row_bytes, &scratch);
+                rc = ensure_ws(ctx, 4, size_t(3) * chunk_max * row_bytes, &scratch);
                 if (rc) return rc;
                 if (!ctx->pipe_bar) CU(cudaMalloc(&ctx->pipe_bar, sizeof(unsigned)));
                 LargeArgs g;
@@ -231,7 +231,6 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
                 g.fused = false;
                 g.pipe = true;
                 g.pipe_iters = ctx->pipe_iters;
-                g.pipe_nbuf = ctx->pipe_nbuf;
                 g.pipe_coop = ctx->pipe_coop;
                 g.bar = ctx->pipe_bar;
                 e = launch_large_fft(L, a, g);
@@ -344,8 +343,6 @@ int kofft_cuda_create(kofft_cuda_ctx **out, int device)
     }
     if (const char *v = getenv("KOFFT_LARGE_PIPE_ITERS"))
         if (atoi(v) > 0) ctx->pipe_iters = atoi(v);
-    if (const char *v = getenv("KOFFT_LARGE_PIPE_NBUF"))
-        if (atoi(v) == 2 || atoi(v) == 3) ctx->pipe_nbuf = atoi(v);
     if (const char *v = getenv("KOFFT_LARGE_PIPE_COOP")) ctx->pipe_coop = atoi(v) != 0;
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
@@ -417,14 +414,13 @@ int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames)
     if (run_frames > 0) ctx->istft_run_frames = run_frames;
     return KOFFT_OK;
 }
-int kofft_cuda_set_large_mode(kofft_cuda_ctx *ctx, int mode, int iters, int nbuf)
+int kofft_cuda_set_large_mode(kofft_cuda_ctx *ctx, int mode, int iters)
 {
-    if (mode < 0 || mode > 2 || (nbuf != 0 && nbuf != 2 && nbuf != 3) || iters < 0 || iters > 64)
-        return fail_msg(KOFFT_ERR_INVALID_VALUE, "set_large_mode: mode 0..2, iters 0..64, nbuf 0, 2 or 3");
+    if (mode < 0 || mode > 2 || iters < 0 || iters > 64)
+        return fail_msg(KOFFT_ERR_INVALID_VALUE, "set_large_mode: mode 0..2, iters 0..64");
     ctx->large_pipe = mode == 2;
     ctx->large_fused = mode == 1;
     if (iters > 0) ctx->pipe_iters = iters;
-    if (nbuf > 0) ctx->pipe_nbuf = nbuf;
     return KOFFT_OK;
 }
 int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable)

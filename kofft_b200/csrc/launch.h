@@ -74,10 +74,9 @@ struct LargeArgs {
     int max_clusters = 0;      // fused path: 0 = as many clusters as fit on the device
     bool stage_rows = true;    // two-kernel path: row pass prefetches its next tile with TMA bulk copies
     // pipelined persistent kernel (LargePipe): chunk_rows = every transform of the batch, scratch =
-    // pipe_nbuf * pipe_iters * (kMaxPipeCtas / NKB) * 2^L complex, bar = zeroed arrival counter
+    // 3 * pipe_iters * (kMaxPipeCtasPerSm * SMs / NKB) * 2^L complex, bar = arrival counter
     bool pipe = false;
     int pipe_iters = 3;        // tiles per CTA per phase
-    int pipe_nbuf = 3;         // intermediate buffers (3: split arrive/wait barrier, 2: plain barrier)
     bool pipe_coop = true;     // one cooperative launch; false: one launch per phase
     unsigned *bar = nullptr;
     int launches = 0;          // out: kernels launched

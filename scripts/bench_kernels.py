@@ -98,12 +98,11 @@ def main():
                 ms, best = timeit(lambda: fft.rfft_batch(x, out=out), 6, 2)
                 report("rfft_65536x16384_" + name, mode, ms, best, nbytes)
             if "pipesweep" in which:
-                for nbuf in (3, 2):
-                    for iters in (1, 2, 3, 4, 6, 8):
-                        fft.ctx.set_large_mode(2, iters, nbuf)
-                        ms, best = timeit(lambda: fft.rfft_batch(x, out=out), 6, 2)
-                        report(f"rfft_65536x16384_pipelined_iters{iters}_nbuf{nbuf}", mode, ms, best, nbytes)
-            fft.ctx.set_large_mode(2, 3, 3)
+                for iters in (1, 2, 3, 4, 5, 6, 8):
+                    fft.ctx.set_large_mode(2, iters)
+                    ms, best = timeit(lambda: fft.rfft_batch(x, out=out), 6, 2)
+                    report(f"rfft_65536x16384_pipelined_iters{iters}", mode, ms, best, nbytes)
+            fft.ctx.set_large_mode(2, 3)
             del x, out
         if "large" in which:
             for n in (32768, 65536):
@@ -114,12 +113,11 @@ def main():
                     ms, best = timeit(lambda: fft.fft_batch(x, out=y), 6, 2)
                     report(f"c2c_{n}x{2 ** 28 // n}_" + name, mode, ms, best, 2 * x.numel() * 8)
                 if "pipesweep" in which:
-                    for nbuf in (3, 2):
-                        for iters in (1, 2, 4, 8):
-                            fft.ctx.set_large_mode(2, iters, nbuf)
-                            ms, best = timeit(lambda: fft.fft_batch(x, out=y), 6, 2)
-                            report(f"c2c_{n}x{2 ** 28 // n}_pipelined_iters{iters}_nbuf{nbuf}", mode, ms, best, 2 * x.numel() * 8)
-                fft.ctx.set_large_mode(2, 3, 3)
+                    for iters in (1, 2, 4, 6, 8):
+                        fft.ctx.set_large_mode(2, iters)
+                        ms, best = timeit(lambda: fft.fft_batch(x, out=y), 6, 2)
+                        report(f"c2c_{n}x{2 ** 28 // n}_pipelined_iters{iters}", mode, ms, best, 2 * x.numel() * 8)
+                fft.ctx.set_large_mode(2, 3)
                 del x, y
         fft.close() if hasattr(fft, "close") else None
 

@@ -133,14 +133,14 @@ int run_fused(const IO &io, const float *table, long rows, int nclusters)
 }
 
 // the pipelined persistent kernel body (LargePipe::run), one emulated launch per phase: `grid` CTAs,
-// `iters` tiles per CTA per phase, `nbuf` intermediate buffers
+// `iters` tiles per CTA per phase
 static bool g_pipe = false;
-static int g_pipe_iters = 1, g_pipe_nbuf = 3;
+static int g_pipe_iters = 1;
 
-template <int LB, bool EXACT, class IO, int EPI>
-int run_pipe(const IO &io, const float *table, long rows, int grid)
+template <int LB, bool EXACT, class IO, int EPI, bool STAGED>
+int run_pipe_v(const IO &io, const float *table, long rows, int grid)
 {
-    using F = LargePipe<LB, EXACT, IO, EPI>;
+    using F = LargePipe<LB, EXACT, IO, EPI, STAGED>;
     const int L = LB + LARGE_S1;
     const long n = 1L << L;
     Tw0 tw0 = make_tw0(L, 4, table);
@@ -150,14 +150,23 @@ int run_pipe(const IO &io, const float *table, long rows, int grid)
     if (grid > rows * F::NKB) grid = (int)(rows * F::NKB);
     const long chunk_rows = (long)g_pipe_iters * (grid / F::NKB);
     const int phases = (int)((rows + chunk_rows - 1) / chunk_rows) + 1;
-    std::vector<float2> scratch((size_t)g_pipe_nbuf * chunk_rows * n);
+    std::vector<float2> scratch((size_t)F::NIBUF * chunk_rows * n);
     std::vector<float2> smem((F::SMEM_BYTES + 256) / 8);
     float2 *sm = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
     for (int p = 0; p < phases; p++)
         cuda_emu::launch((unsigned)grid, 256, [&] {
-            F::run(io, tw0, tab, rows, chunk_rows, scratch.data(), g_pipe_nbuf, sm, p, p + 1, nullptr);
+            F::run(io, tw0, tab, rows, chunk_rows, scratch.data(), sm, p, p + 1, nullptr);
         });
     return 0;
+}
+
+template <int LB, bool EXACT, class IO, int EPI>
+int run_pipe(const IO &io, const float *table, long rows, int grid)
+{
+    if constexpr (IoTraits<IO>::kRowPtr) {
+        if (g_large_staged) return run_pipe_v<LB, EXACT, IO, EPI, true>(io, table, rows, grid);
+    }
+    return run_pipe_v<LB, EXACT, IO, EPI, false>(io, table, rows, grid);
 }
 
 static bool g_fused = false;
@@ -215,11 +224,10 @@ API int kofft_emuk_cta(int kind, int exact, int L, long rows, const void *in, co
 }
 
 API void kofft_emuk_set_fused(int fused) { g_fused = fused != 0; }
-API void kofft_emuk_set_pipe(int pipe, int iters, int nbuf)
+API void kofft_emuk_set_pipe(int pipe, int iters)
 {
     g_pipe = pipe != 0;
     g_pipe_iters = iters > 0 ? iters : 1;
-    g_pipe_nbuf = nbuf == 2 ? 2 : 3;
 }
 API void kofft_emuk_set_large_staged(int staged) { g_large_staged = staged != 0; }
 

@@ -681,11 +681,10 @@ def test_large_paths_agree(cuda_fft, oracle, n):
     bref = oracle.irfft_batch(rref, 2 * n, nthreads=8)
     C = cuda_fft.ctx
     try:
-        for mode, iters, nbuf in ((C.LARGE_PIPELINED, 1, 3), (C.LARGE_PIPELINED, 1, 2), (C.LARGE_PIPELINED, 3, 3),
-                                  (C.LARGE_CLUSTER, 0, 0), (C.LARGE_TWO_KERNEL, 0, 0)):
+        for mode, iters in ((C.LARGE_PIPELINED, 1), (C.LARGE_PIPELINED, 3), (C.LARGE_CLUSTER, 0), (C.LARGE_TWO_KERNEL, 0)):
             C.set_cluster_fusion(False)
-            C.set_large_mode(mode, iters, nbuf)
-            tag = f"mode={mode} iters={iters} nbuf={nbuf}"
+            C.set_large_mode(mode, iters)
+            tag = f"mode={mode} iters={iters}"
             y = x.copy()
             cuda_fft.fft_batch(y)
             assert np.array_equal(y, ref), tag
@@ -695,12 +694,12 @@ def test_large_paths_agree(cuda_fft, oracle, n):
             assert np.array_equal(cuda_fft.rfft_batch(xr), rref), tag
             assert np.array_equal(cuda_fft.irfft_batch(rref, 2 * n), bref), tag
     finally:
-        C.set_large_mode(C.LARGE_PIPELINED, 3, 3)
+        C.set_large_mode(C.LARGE_PIPELINED, 3)
 
 
 def test_large_pipelined_many_phases_on_device(cuda_fft, oracle):
     """The pipelined kernel on device-resident rows, ~40 phases, every mode of the barrier: sampled
-    rows bit-identical to the oracle, and the whole batch identical across (iters, nbuf)."""
+    rows bit-identical to the oracle, and the whole batch identical across chunk sizes."""
     import torch
 
     n, rows = 32768, 1500
@@ -709,15 +708,15 @@ def test_large_pipelined_many_phases_on_device(cuda_fft, oracle):
     C = cuda_fft.ctx
     outs = []
     try:
-        for iters, nbuf in ((1, 3), (1, 2), (2, 3), (4, 2)):
-            C.set_large_mode(C.LARGE_PIPELINED, iters, nbuf)
+        for iters in (1, 2, 3, 5):
+            C.set_large_mode(C.LARGE_PIPELINED, iters)
             y = torch.empty_like(x)
             for _ in range(3):  # repeated launches reuse the arrival counter
                 cuda_fft.fft_batch(x, out=y)
             torch.cuda.synchronize()
             outs.append(y)
     finally:
-        C.set_large_mode(C.LARGE_PIPELINED, 3, 3)
+        C.set_large_mode(C.LARGE_PIPELINED, 3)
     pick = [0, 1, 36, 37, 73, 74, 700, rows - 2, rows - 1]
     ref = oracle.fft_batch(x[pick].cpu().numpy(), nthreads=8)
     assert np.array_equal(outs[0][pick].cpu().numpy(), ref)
