@@ -59,11 +59,8 @@ KD void cp_async16(void *dst_smem, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
-KD void cp_async16_hint(void *dst_smem, const void *src, unsigned long long pol)
-{
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "l"(pol)
-                 : "memory");
-}
+// (a .L2::cache_hint variant of this copy is not used: ptxas 12.9 allocates an odd uniform-register
+// pair for the LDGSTS descriptor -- desc[UR1] -- which the hardware rejects as an illegal instruction)
 KD void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 KD void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -153,7 +150,6 @@ inline void cp_async16(void *dst_smem, const void *src)
     if ((reinterpret_cast<uintptr_t>(dst_smem) & 15) || (reinterpret_cast<uintptr_t>(src) & 15)) abort();
     memcpy(dst_smem, src, 16);
 }
-inline void cp_async16_hint(void *dst_smem, const void *src, unsigned long long) { cp_async16(dst_smem, src); }
 inline void cp_async_commit() {}
 inline void cp_async_wait_all() {}
 

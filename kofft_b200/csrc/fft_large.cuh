@@ -437,14 +437,14 @@ struct LargePipe {
 
     // thread i copies 16-byte piece (i & 7) of rows (i >> 3) + 32 m, m = 0..7, of the tile
     // [256 rows][16 columns] starting at column j0 of transform `row`
-    static KD void prefetch_a(const IO &io, long row, long j0, float2 *stage, int tid, const L2Policy &pol)
+    static KD void prefetch_a(const IO &io, long row, long j0, float2 *stage, int tid)
     {
         if constexpr (STAGED) {
             const float2 *src = io.row_ptr(row) + j0 + 2 * (tid & 7);
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 const int r = (tid >> 3) + 32 * m;
-                cp_async16_hint(stage + r * C::COLS + 2 * (tid & 7), src + ((long)r << LB), pol.first);
+                cp_async16(stage + r * C::COLS + 2 * (tid & 7), src + ((long)r << LB));
             }
             cp_async_commit();
         }
@@ -624,7 +624,7 @@ struct LargePipe {
             return (r > chunk_rows ? chunk_rows : r) << LOG_NKB;
         };
         if (STAGED && phase_begin < nchunks && (long)blockIdx.x < chunk_tiles(phase_begin))
-            prefetch_a(io, (long)phase_begin * chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid, pol);
+            prefetch_a(io, (long)phase_begin * chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid);
         for (int p = phase_begin; p < phase_end; p++) {
             const long rowA0 = (long)p * chunk_rows, rowB0 = (long)(p - 1) * chunk_rows;
             float2 *scA = scratch + (long)(p % NIBUF) * chunk_rows * n;
@@ -636,7 +636,7 @@ struct LargePipe {
                 const long b = tl >> LOG_NKB;
                 const long nx = tl + gridDim.x;
                 tile_a(io, tw0, twA + tA * 16, rowA0 + b, j0, scA + b * n, bufA, buf1, tA, slotA, pol, [&] {
-                    if (nx < tilesA) prefetch_a(io, rowA0 + (nx >> LOG_NKB), j0, buf1, tid, pol);
+                    if (nx < tilesA) prefetch_a(io, rowA0 + (nx >> LOG_NKB), j0, buf1, tid);
                 });
                 if (!STAGED) __syncthreads(); // buf0 is rewritten by the next tile
             }
@@ -649,13 +649,13 @@ struct LargePipe {
                     // buf1 is idle from here to the next pass-B tile: the last one of the phase requests
                     // the first pass-A tile of the next phase (only if this launch runs that phase)
                     if (last && more && (long)blockIdx.x < tilesA1)
-                        prefetch_a(io, rowA0 + chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid, pol);
+                        prefetch_a(io, rowA0 + chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid);
                 });
                 __syncthreads(); // both buffers are rewritten by the next tile
             }
             // no pass-B tile in this phase (first phase, or fewer tiles than CTAs): request it here
             if (more && tilesB <= (long)blockIdx.x && (long)blockIdx.x < tilesA1)
-                prefetch_a(io, rowA0 + chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid, pol);
+                prefetch_a(io, rowA0 + chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid);
         }
     }
 };
