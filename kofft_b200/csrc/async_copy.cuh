@@ -59,8 +59,14 @@ KD void cp_async16(void *dst_smem, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
-// (a .L2::cache_hint variant of this copy is not used: ptxas 12.9 allocates an odd uniform-register
-// pair for the LDGSTS descriptor -- desc[UR1] -- which the hardware rejects as an illegal instruction)
+// same with an L2 eviction-priority hint.  NOTE: check the SASS of every kernel using this
+// (scripts/check_sass.sh): ptxas 12.9 can allocate an ODD uniform-register pair for the LDGSTS
+// descriptor (desc[UR1]), which the hardware rejects as an illegal instruction.
+KD void cp_async16_hint(void *dst_smem, const void *src, unsigned long long pol)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "l"(pol)
+                 : "memory");
+}
 KD void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 KD void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -82,9 +88,10 @@ KD unsigned cluster_ctarank()
 // pass-A -> pass-B intermediate (evict_last) so that it never makes the round trip to HBM.
 KD L2Policy make_l2_policy()
 {
+    // the encodings createpolicy.fractional.L2::evict_first / evict_last (fraction 1.0) produce
     L2Policy p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.first));
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.last));
+    p.first = 0x12F0000000000000ull;
+    p.last = 0x14F0000000000000ull;
     return p;
 }
 // read-only streaming load (never written during the launch)
@@ -126,8 +133,8 @@ KD void grid_wait(unsigned *bar, unsigned target)
 {
     if (threadIdx.x == 0) {
         unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        do { // relaxed polling (an acquire load would invalidate L1 on every iteration), one fence at the end
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
         } while (v < target);
         __threadfence();
     }
@@ -150,6 +157,7 @@ inline void cp_async16(void *dst_smem, const void *src)
     if ((reinterpret_cast<uintptr_t>(dst_smem) & 15) || (reinterpret_cast<uintptr_t>(src) & 15)) abort();
     memcpy(dst_smem, src, 16);
 }
+inline void cp_async16_hint(void *dst_smem, const void *src, unsigned long long) { cp_async16(dst_smem, src); }
 inline void cp_async_commit() {}
 inline void cp_async_wait_all() {}
 

@@ -437,14 +437,14 @@ struct LargePipe {
 
     // thread i copies 16-byte piece (i & 7) of rows (i >> 3) + 32 m, m = 0..7, of the tile
     // [256 rows][16 columns] starting at column j0 of transform `row`
-    static KD void prefetch_a(const IO &io, long row, long j0, float2 *stage, int tid)
+    static KD void prefetch_a(const IO &io, long row, long j0, float2 *stage, int tid, const L2Policy &pol)
     {
         if constexpr (STAGED) {
             const float2 *src = io.row_ptr(row) + j0 + 2 * (tid & 7);
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 const int r = (tid >> 3) + 32 * m;
-                cp_async16(stage + r * C::COLS + 2 * (tid & 7), src + ((long)r << LB));
+                cp_async16(stage + r * C::COLS + 2 * (tid & 7), src + ((long)r << LB)); // no L2 hint: see cp_async16_hint
             }
             cp_async_commit();
         }
@@ -500,23 +500,29 @@ struct LargePipe {
         int kk, c0;   // this thread's k and first bin
     };
 
-    // pass B tile: bfa / bfb are this thread's exchange regions (buf1 / buf0), allb is buf0 seen
-    // CTA-wide, rtwb the CTA's slice of T' (twist only).  after_exchange(): called by every thread
-    // right after the second barrier (buf1 is free from there on).
+    // this thread's 16 inputs of a pass-B tile (sub: the slot's contiguous sub-transform in the intermediate)
+    static KD void load_b(float2 *x, const float2 *__restrict__ sub, int t, const L2Policy &pol)
+    {
+        using P0 = typename R::P0;
+#pragma unroll
+        for (int u = 0; u < P0::U; u++)
+#pragma unroll
+            for (int q = 0; q < P0::R; q++) x[u * P0::R + q] = ldcg_hint(sub + P0::src_index(t, u, q), pol.first);
+    }
+
+    // pass B tile.  x: the tile's inputs (load_b), replaced by the NEXT tile's inputs (next_sub, or
+    // null) once the registers are free, so that their L2 latency hides behind the epilogue.
+    // bfa / bfb are this thread's exchange regions (buf1 / buf0), allb is buf0 seen CTA-wide, rtwb the
+    // CTA's slice of T' (twist only).  after_exchange(): called by every thread right after the
+    // second barrier (buf1 is free from there on).
     template <class After>
-    static KD void tile_b(const IO &io, const float2 *tw0, const float2 *tw1, long row, int kb,
-                          const float2 *__restrict__ scratch_row, float2 *bfa, float2 *bfb, const float2 *allb, int t,
-                          const Epi &ep, const float2 *rtwb, const L2Policy &pol, After after_exchange)
+    static KD void tile_b(const IO &io, float2 *x, const float2 *tw0, const float2 *tw1, long row, int kb,
+                          const float2 *__restrict__ next_sub, float2 *bfa, float2 *bfb, const float2 *allb, int t,
+                          int tid, const Epi &ep, const float2 *rtwb, const L2Policy &pol, After after_exchange)
     {
         using P0 = typename R::P0;
         using P1 = typename R::P1;
         constexpr int NB = R::NB;
-        float2 x[EPT];
-        const float2 *in = scratch_row;
-#pragma unroll
-        for (int u = 0; u < P0::U; u++)
-#pragma unroll
-            for (int q = 0; q < P0::R; q++) x[u * P0::R + q] = ldcg_hint(in + P0::src_index(t, u, q), pol.first);
         P0::compute(x, tw0);
 #pragma unroll
         for (int u = 0; u < P0::U; u++)
@@ -530,34 +536,33 @@ struct LargePipe {
         for (int w = 0; w < P1::R; w++) bfb[P1::dst_pad(P1::dst_base(t, 0), w)] = x[w];
         __syncthreads();
         after_exchange();
+        if (next_sub) load_b(x, next_sub, t, pol);
         // transposed read-back: bins of all TPC sub-transforms, k fastest -> 128-byte store runs
         const float2 *pa = allb + ep.own;
         if constexpr (EPI == ROW_TWIST) {
             const float2 *pr = rtwb + ep.own;
             const float2 *pm = allb + ep.mir;
-            if (ep.kk == 0) { // lane 0 of the k-block-0 CTAs: mirror inside the own sub-transform, bins 0 and m
-                (void)kb;
+            float2 *o = io.out + row * (io.m + 1) + ep.kk + ((long)ep.c0 << LARGE_S1);
+            const bool mine = ep.kk != 0; // k = 0 mirrors inside its own sub-transform: fixed up below
 #pragma unroll
-                for (int e = 0; e < EPT; e++) {
-                    const int c = ep.c0 + STEP * e;
-                    const float2 a = pa[cpad(e)];
-                    const float2 ym = c == 0 ? a : allb[ep.own - ep.c0 + pad(NB - c)]; // m - K = 256 (NB - c)
-                    const long K = (long)c << LARGE_S1;
-                    if constexpr (HINT)
-                        io.twist_store_tw_hint(row, K, a, ym, pr[cpad(e)], pol.first);
-                    else
-                        io.twist_store_tw(row, K, a, ym, pr[cpad(e)]);
-                }
-            } else {
-                float2 *o = io.out + row * (io.m + 1) + ep.kk + ((long)ep.c0 << LARGE_S1);
-#pragma unroll
-                for (int e = 0; e < EPT; e++) {
-                    const float2 v = io.twist(pa[cpad(e)], pm[mpad(e)], pr[cpad(e)]);
+            for (int e = 0; e < EPT; e++) {
+                const float2 v = io.twist(pa[cpad(e)], pm[mpad(e)], pr[cpad(e)]);
+                if (mine) {
                     if constexpr (HINT)
                         stg_hint(o + ((long)(STEP * e) << LARGE_S1), v, pol.first);
                     else
                         o[(long)(STEP * e) << LARGE_S1] = v;
                 }
+            }
+            if (kb == 0 && tid < NB) { // k = 0 (slot 0): bin K = 256 c pairs with m - K = 256 (NB - c); bins 0 and m
+                const int c = tid;
+                const float2 a = allb[R::slot_off(0) + pad(c)];
+                const float2 ym = c == 0 ? a : allb[R::slot_off(0) + pad(NB - c)];
+                const float2 tw = rtwb[R::slot_off(0) + pad(c)];
+                if constexpr (HINT)
+                    io.twist_store_tw_hint(row, (long)c << LARGE_S1, a, ym, tw, pol.first);
+                else
+                    io.twist_store_tw(row, (long)c << LARGE_S1, a, ym, tw);
             }
         } else {
 #pragma unroll
@@ -624,7 +629,7 @@ struct LargePipe {
             return (r > chunk_rows ? chunk_rows : r) << LOG_NKB;
         };
         if (STAGED && phase_begin < nchunks && (long)blockIdx.x < chunk_tiles(phase_begin))
-            prefetch_a(io, (long)phase_begin * chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid);
+            prefetch_a(io, (long)phase_begin * chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid, pol);
         for (int p = phase_begin; p < phase_end; p++) {
             const long rowA0 = (long)p * chunk_rows, rowB0 = (long)(p - 1) * chunk_rows;
             float2 *scA = scratch + (long)(p % NIBUF) * chunk_rows * n;
@@ -636,26 +641,31 @@ struct LargePipe {
                 const long b = tl >> LOG_NKB;
                 const long nx = tl + gridDim.x;
                 tile_a(io, tw0, twA + tA * 16, rowA0 + b, j0, scA + b * n, bufA, buf1, tA, slotA, pol, [&] {
-                    if (nx < tilesA) prefetch_a(io, rowA0 + (nx >> LOG_NKB), j0, buf1, tid);
+                    if (nx < tilesA) prefetch_a(io, rowA0 + (nx >> LOG_NKB), j0, buf1, tid, pol);
                 });
                 if (!STAGED) __syncthreads(); // buf0 is rewritten by the next tile
             }
             if (more) grid_arrive(bar); // this CTA's share of chunk p is in scA
             if (STAGED && tilesA > 0) __syncthreads(); // pass B rewrites buf0
+            float2 xb[EPT];
+            const float2 *subB = scB + (long)k * R::NB; // this slot's sub-transform of the chunk's first transform
+            if ((long)blockIdx.x < tilesB) load_b(xb, subB + (blockIdx.x >> LOG_NKB) * n, tB, pol);
             for (long tl = blockIdx.x; tl < tilesB; tl += gridDim.x) {
                 const long b = tl >> LOG_NKB;
-                const bool last = tl + gridDim.x >= tilesB;
-                tile_b(io, twB0, twB1, rowB0 + b, kb, scB + b * n + (long)k * R::NB, bfa, bfb, buf0, tB, ep, rtwb, pol, [&] {
+                const long nx = tl + gridDim.x;
+                const bool last = nx >= tilesB;
+                tile_b(io, xb, twB0, twB1, rowB0 + b, kb, last ? (const float2 *)nullptr : subB + (nx >> LOG_NKB) * n, bfa, bfb,
+                       buf0, tB, tid, ep, rtwb, pol, [&] {
                     // buf1 is idle from here to the next pass-B tile: the last one of the phase requests
                     // the first pass-A tile of the next phase (only if this launch runs that phase)
                     if (last && more && (long)blockIdx.x < tilesA1)
-                        prefetch_a(io, rowA0 + chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid);
+                        prefetch_a(io, rowA0 + chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid, pol);
                 });
                 __syncthreads(); // both buffers are rewritten by the next tile
             }
             // no pass-B tile in this phase (first phase, or fewer tiles than CTAs): request it here
             if (more && tilesB <= (long)blockIdx.x && (long)blockIdx.x < tilesA1)
-                prefetch_a(io, rowA0 + chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid);
+                prefetch_a(io, rowA0 + chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid, pol);
         }
     }
 };
