@@ -70,14 +70,13 @@ int kofft_cuda_set_tma_staging(kofft_cuda_ctx *ctx, int enable);
  * run (default 128).  Disabled or out of range -> two kernels with an f32 intermediate. */
 int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames);
 /* N > 16384 (rfft above 32768): which of the three implementations of the two-pass split runs.
- *   mode 2 (default): one persistent cooperative kernel; pass A of batch chunk p is overlapped with
- *          pass B of chunk p-1 behind a split (arrive / wait) grid barrier, and the intermediate is
- *          pinned in L2 (evict_last), so HBM sees the rows once in and once out.
- *          iters = tiles per CTA per chunk (0 = keep; default 3).
+ *   mode 2 (default): one persistent cooperative kernel; teams of 8 / 16 CTAs overlap pass A of their
+ *          next transform with pass B of the current one behind dependency flags, and the intermediate
+ *          (3 transforms per team) is pinned in L2, so HBM sees the rows once in and once out.
  *   mode 0: two kernels (column pass, row pass) per 256 MB batch chunk.
  *   mode 1: one persistent thread-block-cluster kernel (cluster barrier between the passes).
  * All three are bit-identical; 0 and 1 are kept for comparison (profiles/). */
-int kofft_cuda_set_large_mode(kofft_cuda_ctx *ctx, int mode, int iters);
+int kofft_cuda_set_large_mode(kofft_cuda_ctx *ctx, int mode);
 /* enable != 0: mode 1 above; 0: back to the current non-cluster mode */
 int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable);
 /* Host-pointer batch entry points (fft_batch_host, rfft_batch_host, irfft_batch_host): batches

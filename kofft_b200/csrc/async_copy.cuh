@@ -118,28 +118,25 @@ KD void stg_hint(float2 *p, float2 v, unsigned long long pol)
     asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol));
 }
 
-// ---- grid-wide barrier for persistent kernels whose CTAs are all co-resident (cooperative launch)
-// `bar` counts arrivals since the launch (zeroed by the host); split into arrive / wait so that a
-// CTA can do independent work in between.  Same fence pattern as cooperative_groups::grid_group::sync.
-KD void grid_arrive(unsigned *bar)
+// ---- dependency flags between co-resident CTAs of a persistent kernel (cooperative launch) ------
+// A counter is incremented by one thread of a CTA after a barrier that orders the CTA's global
+// stores before it (release: __threadfence + atomicAdd, the pattern cooperative_groups' grid sync
+// uses); a consumer polls with relaxed loads (an acquire load would invalidate L1 on every
+// iteration) and fences once when the count is reached, then releases its CTA through a barrier.
+KD unsigned flag_load(const unsigned *c)
 {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
-    }
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+    return v;
 }
-KD void grid_wait(unsigned *bar, unsigned target)
+KD void flag_acquire() { __threadfence(); }
+KD void flag_arrive(unsigned *c)
 {
-    if (threadIdx.x == 0) {
-        unsigned v;
-        do { // relaxed polling (an acquire load would invalidate L1 on every iteration), one fence at the end
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-        } while (v < target);
-        __threadfence();
-    }
-    __syncthreads();
+    __threadfence();
+    atomicAdd(c, 1u);
 }
+// the arriving CTA only READ the guarded data (its loads have completed): no fence needed
+KD void flag_arrive_relaxed(unsigned *c) { atomicAdd(c, 1u); }
 
 #elif defined(KOFFT_EMU)
 
@@ -147,10 +144,15 @@ inline L2Policy make_l2_policy() { return L2Policy{1ull, 2ull}; }
 inline float2 ldg_hint(const float2 *p, unsigned long long) { return *p; }
 inline float2 ldcg_hint(const float2 *p, unsigned long long) { return *p; }
 inline void stg_hint(float2 *p, float2 v, unsigned long long) { *p = v; }
-// the emulator runs one CTA at a time: a multi-phase launch is emulated phase by phase, so the
-// grid barrier is never reached with other CTAs outstanding
-inline void grid_arrive(unsigned *bar) { __syncthreads(); if (threadIdx.x == 0) ++*bar; }
-inline void grid_wait(unsigned *, unsigned) { __syncthreads(); }
+// the emulator runs the CTAs of one "cluster" (here: a team) as interleaved coroutines: a poll yields
+inline unsigned flag_load(const unsigned *c)
+{
+    cuda_emu::yield_to_scheduler();
+    return *c;
+}
+inline void flag_acquire() {}
+inline void flag_arrive(unsigned *c) { ++*c; }
+inline void flag_arrive_relaxed(unsigned *c) { ++*c; }
 
 inline void cp_async16(void *dst_smem, const void *src)
 {

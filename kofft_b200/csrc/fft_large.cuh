@@ -394,29 +394,31 @@ struct LargeFused {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Both passes in ONE persistent kernel, software-pipelined over batch chunks ("phases"):
-//     phase p:  wait until every CTA has arrived in phase p-1
-//               pass A of chunk p   (HBM -> intermediate buffer p mod 3), then ARRIVE
-//               pass B of chunk p-1 (intermediate buffer (p-1) mod 3 -> HBM)
-// All CTAs are co-resident (cooperative launch); the grid barrier is split, so the whole pass-B
-// part of a phase separates a CTA's arrival from its next wait and the skew between CTAs is
-// hidden behind useful work.  A chunk is a few tiles per CTA, so the three intermediate buffers
-// are a few tens of MB: they are written with the L2 evict_last policy and the rows stream
-// through with evict_first, so the intermediate is never read back from HBM (the two-kernel path
-// above needs long launches to amortise launch + ramp + tail, and at those chunk sizes the
-// intermediate spills: 2x the algorithmic DRAM traffic, profiles/r01u_rfft_*pass_kernel.json).
-// Buffer reuse: pass A of phase p overwrites the buffer pass B read in phase p-2; a CTA starts
-// phase p only after every CTA has arrived in phase p-1, i.e. has finished phase p-2.
+// Both passes in ONE persistent kernel, software-pipelined per transform with dependency flags.
+// A "team" of NKB consecutive CTAs (one per column tile / k-block) owns the transforms
+// q, q + teams, q + 2 teams, ...; member kb runs, for its i-th transform,
+//     step i:   pass A tile of transform i+1  (HBM -> intermediate slot (i+1) mod 3)  ... arrive A
+//               pass B tile of transform i    (intermediate slot i mod 3 -> HBM)      ... arrive B
+// Pass B of transform i needs the NKB pass-A tiles of that transform: counter cntA >= NKB (i+1).
+// Pass A of transform i+1 overwrites the slot of transform i-2: counter cntB >= NKB (i-1).
+// Both conditions were met about one step earlier unless a member lags by more than a step, and
+// the polling thread issues its flag load a register pass ahead of the check, so neither the
+// skew between CTAs nor the flag's L2 round trip is normally exposed.  There is no grid-wide
+// synchronisation: a slow SM delays only its own team (the first version of this kernel used a
+// grid barrier per batch chunk and lost 14 % of the warp time to it, profiles/r01x).  The
+// cooperative launch guarantees that all CTAs are co-resident, which the flag waits rely on.
 //
-// CTA j keeps column tile / k-block  j mod NKB  for its lifetime (the grid is a multiple of NKB),
-// so its pass-B twiddles stay in registers and its rfft-table slice in shared memory.
-// Shared memory: two exchange buffers (+ the T' slice for the twist).  Pass A exchanges through
-// buf0 and (STAGED) uses the idle buf1 as the landing zone of its next tile, fetched with 16-byte
-// asynchronous copies while the current tile is transformed -- the first tile of a phase is
-// requested during the last pass-B tile of the previous phase.  Pass B exchanges through buf1
-// (between its register passes) and buf0 (transposed bins).
-// phase_begin/phase_end: the phases this launch runs (one launch runs them all; the CPU emulator
-// and the non-cooperative fallback run one phase per launch, the launch boundary being the barrier).
+// The intermediate is teams * 3 * 2^L complex (28 MB for N = 2^15): written with the L2
+// evict_last policy while the rows stream through with evict_first where the instruction allows,
+// so it never makes the round trip to HBM (the two-kernel path above needs long launches to
+// amortise launch + ramp + tail, and at those chunk sizes the intermediate spills: 2x the
+// algorithmic DRAM traffic, profiles/r01u_rfft_*pass_kernel.json).
+//
+// CTA j keeps column tile / k-block  j mod NKB  for its lifetime, so its pass-B twiddles stay in
+// registers and its rfft-table slice in shared memory.  Shared memory: two exchange buffers (+ the
+// T' slice for the twist).  Pass A exchanges through buf0 and (STAGED) reads its tile from buf1,
+// where 16-byte asynchronous copies put it while the previous pass-B tile ran its epilogue; pass B
+// exchanges through buf1 (between its register passes) and buf0 (transposed bins).
 // ---------------------------------------------------------------------------------------------
 template <int LB, bool EXACT, class IO, int EPI, bool STAGED = false>
 struct LargePipe {
@@ -433,7 +435,6 @@ struct LargePipe {
     static constexpr int SMEM_BYTES = (NBUFS * BUF + TW_SMEM) * 8;
     static constexpr bool HINT = IoTraits<IO>::kHint;
     static_assert(!STAGED || IoTraits<IO>::kRowPtr, "staging needs plain contiguous rows");
-    static constexpr int NIBUF = 3; // intermediate buffers
 
     // thread i copies 16-byte piece (i & 7) of rows (i >> 3) + 32 m, m = 0..7, of the tile
     // [256 rows][16 columns] starting at column j0 of transform `row`
@@ -451,11 +452,12 @@ struct LargePipe {
     }
 
     // pass A tile: 16 adjacent columns of transform `row` -> scratch_row.  STAGED: the tile is in
-    // `stage`; after the exchange barrier (stage consumed by everyone) next() issues the next prefetch.
-    template <class Next>
+    // `stage`.  before_store(): called by every thread before the exchange barrier -- the polling
+    // thread returns from it only when the destination slot may be overwritten.
+    template <class Before>
     static KD void tile_a(const IO &io, const Tw0 &tw0, const float2 *tw1, long row, long j0,
                           float2 *__restrict__ scratch_row, float2 *bf, const float2 *stage, int t, int slot,
-                          const L2Policy &pol, Next next)
+                          const L2Policy &pol, Before before_store)
     {
         using P0 = typename C::P0;
         using P1 = typename C::P1;
@@ -463,7 +465,7 @@ struct LargePipe {
         float2 x[EPT];
         if constexpr (STAGED) {
             cp_async_wait_all();
-            __syncthreads(); // every thread's pieces have landed; the previous tile's readers of bf are done
+            __syncthreads(); // every thread's pieces have landed
 #pragma unroll
             for (int q = 0; q < P0::R; q++) x[q] = io.from_raw(stage[P0::src_index(t, 0, q) * C::COLS + slot]);
         } else {
@@ -479,8 +481,8 @@ struct LargePipe {
         P0::compute(x, tw0.v);
 #pragma unroll
         for (int w = 0; w < P0::R; w++) bf[P0::dst_pad(P0::dst_base(t, 0), w)] = x[w];
+        before_store();
         __syncthreads();
-        next();
 #pragma unroll
         for (int q = 0; q < P1::R; q++) x[q] = bf[P1::src_pad(P1::src_base(t, 0), q)];
         P1::compute(x, tw1);
@@ -513,12 +515,15 @@ struct LargePipe {
     // pass B tile.  x: the tile's inputs (load_b), replaced by the NEXT tile's inputs (next_sub, or
     // null) once the registers are free, so that their L2 latency hides behind the epilogue.
     // bfa / bfb are this thread's exchange regions (buf1 / buf0), allb is buf0 seen CTA-wide, rtwb the
-    // CTA's slice of T' (twist only).  after_exchange(): called by every thread right after the
-    // second barrier (buf1 is free from there on).
-    template <class After>
+    // CTA's slice of T' (twist only).  Hooks, called by every thread: after_first() right after the
+    // first barrier (every thread's earlier global stores are ordered before it); before_second()
+    // before the second barrier -- the polling thread returns from it only when next_sub is complete;
+    // after_second() right after the second barrier (the tile's inputs are consumed, buf1 is free).
+    template <class H1, class H2, class H3>
     static KD void tile_b(const IO &io, float2 *x, const float2 *tw0, const float2 *tw1, long row, int kb,
                           const float2 *__restrict__ next_sub, float2 *bfa, float2 *bfb, const float2 *allb, int t,
-                          int tid, const Epi &ep, const float2 *rtwb, const L2Policy &pol, After after_exchange)
+                          int tid, const Epi &ep, const float2 *rtwb, const L2Policy &pol, H1 after_first,
+                          H2 before_second, H3 after_second)
     {
         using P0 = typename R::P0;
         using P1 = typename R::P1;
@@ -529,13 +534,15 @@ struct LargePipe {
 #pragma unroll
             for (int w = 0; w < P0::R; w++) bfa[P0::dst_pad(P0::dst_base(t, u), w)] = x[u * P0::R + w];
         __syncthreads();
+        after_first();
 #pragma unroll
         for (int q = 0; q < P1::R; q++) x[q] = bfa[P1::src_pad(P1::src_base(t, 0), q)];
         P1::compute(x, tw1);
 #pragma unroll
         for (int w = 0; w < P1::R; w++) bfb[P1::dst_pad(P1::dst_base(t, 0), w)] = x[w];
+        before_second();
         __syncthreads();
-        after_exchange();
+        after_second();
         if (next_sub) load_b(x, next_sub, t, pol);
         // transposed read-back: bins of all TPC sub-transforms, k fastest -> 128-byte store runs
         const float2 *pa = allb + ep.own;
@@ -576,14 +583,19 @@ struct LargePipe {
         }
     }
 
-    // rows: transforms in the batch; chunk_rows: transforms per phase; scratch: 3 * chunk_rows * n
-    // complex; bar: arrival counter of this launch (zero at launch), unused when the launch runs one phase.
-    static KD void run(const IO &io, const Tw0 &tw0, const float2 *__restrict__ table, long rows, long chunk_rows,
-                       float2 *__restrict__ scratch, float2 *smem, int phase_begin, int phase_end, unsigned *bar)
+    static constexpr int SLOTS = 3;         // intermediate slots per team
+    static constexpr int FLAG_STRIDE = 32;  // unsigned per team: {cntA, cntB} in a 128-byte line of their own
+
+    // rows: transforms in the batch; scratch: teams * SLOTS * n complex; flags: teams * FLAG_STRIDE
+    // counters, zero at launch.  gridDim.x is a multiple of NKB and every CTA is resident.
+    static KD void run(const IO &io, const Tw0 &tw0, const float2 *__restrict__ table, long rows,
+                       float2 *__restrict__ scratch, float2 *smem, unsigned *flags)
     {
         const int tid = threadIdx.x;
         const long n = 1L << (LARGE_S1 + LB);
         const int kb = blockIdx.x % NKB; // column tile of pass A == k-block of pass B
+        const long team = blockIdx.x / NKB, teams = gridDim.x / NKB;
+        unsigned *cntA = flags + team * FLAG_STRIDE, *cntB = cntA + 1;
         const L2Policy pol = make_l2_policy();
         // pass A (column-fastest mapping); its pass-1 twiddles are shared by the 16 columns -> shared memory
         const int slotA = tid & (C::COLS - 1), tA = tid >> 4;
@@ -620,52 +632,61 @@ struct LargePipe {
 
         float2 *bufA = buf0 + slotA * C::RS;
         float2 *bfa = buf1 + R::slot_off(slotB), *bfb = buf0 + R::slot_off(slotB);
-        const long nchunks = (rows + chunk_rows - 1) / chunk_rows;
         const long j0 = (long)kb * C::COLS;
-        // tiles of a chunk this CTA owns: tl = blockIdx.x + i * gridDim.x  (transform tl >> LOG_NKB)
-        auto chunk_tiles = [&](long p) -> long {
-            if (p < 0 || p >= nchunks) return 0;
-            long r = rows - p * chunk_rows;
-            return (r > chunk_rows ? chunk_rows : r) << LOG_NKB;
+        const long cnt = team < rows ? (rows - team + teams - 1) / teams : 0; // transforms of this team
+        float2 *slots = scratch + team * SLOTS * n;
+        auto row_of = [&](long i) { return team + i * teams; };
+        auto slot_of_i = [&](long i) { return slots + (i % SLOTS) * n; };
+        // the polling thread's view of the two counters: loaded ahead of time, re-read only while short
+        unsigned seenA = 0, seenB = 0;
+        auto peek = [&](unsigned *c) -> unsigned { return tid == 0 ? flag_load(c) : 0u; };
+        auto await = [&](unsigned *c, unsigned &seen, unsigned target) {
+            if (tid == 0) {
+                while (seen < target) seen = flag_load(c);
+                flag_acquire();
+            }
         };
-        if (STAGED && phase_begin < nchunks && (long)blockIdx.x < chunk_tiles(phase_begin))
-            prefetch_a(io, (long)phase_begin * chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid, pol);
-        for (int p = phase_begin; p < phase_end; p++) {
-            const long rowA0 = (long)p * chunk_rows, rowB0 = (long)(p - 1) * chunk_rows;
-            float2 *scA = scratch + (long)(p % NIBUF) * chunk_rows * n;
-            const float2 *scB = scratch + (long)((p + NIBUF - 1) % NIBUF) * chunk_rows * n;
-            const long tilesA = chunk_tiles(p), tilesB = chunk_tiles(p - 1), tilesA1 = chunk_tiles(p + 1);
-            const bool more = p + 1 < phase_end;
-            if (p > phase_begin) grid_wait(bar, gridDim.x * (unsigned)(p - phase_begin));
-            for (long tl = blockIdx.x; tl < tilesA; tl += gridDim.x) {
-                const long b = tl >> LOG_NKB;
-                const long nx = tl + gridDim.x;
-                tile_a(io, tw0, twA + tA * 16, rowA0 + b, j0, scA + b * n, bufA, buf1, tA, slotA, pol, [&] {
-                    if (nx < tilesA) prefetch_a(io, rowA0 + (nx >> LOG_NKB), j0, buf1, tid, pol);
-                });
-                if (!STAGED) __syncthreads(); // buf0 is rewritten by the next tile
+        if (cnt == 0) return;
+
+        // prologue: pass A of the team's first transform
+        prefetch_a(io, row_of(0), j0, buf1, tid, pol);
+        tile_a(io, tw0, twA + tA * 16, row_of(0), j0, slot_of_i(0), bufA, buf1, tA, slotA, pol, [] {});
+        __syncthreads();
+        if (tid == 0) flag_arrive(cntA);
+        if (cnt > 1) prefetch_a(io, row_of(1), j0, buf1, tid, pol); // buf1 is idle until the first pass-B tile
+        float2 xb[EPT];
+        bool have_xb = false;
+        for (long i = 0; i < cnt; i++) {
+            const bool nextA = i + 1 < cnt;
+            if (nextA) {
+                // pass A of transform i+1 into the slot transform i-2 occupied: every member must have
+                // consumed it (cntB >= NKB (i-1)); the flag load is issued before the tile's first pass
+                seenB = peek(cntB);
+                tile_a(io, tw0, twA + tA * 16, row_of(i + 1), j0, slot_of_i(i + 1), bufA, buf1, tA, slotA, pol,
+                       [&] { if (i >= 2) await(cntB, seenB, (unsigned)(NKB * (i - 1))); });
             }
-            if (more) grid_arrive(bar); // this CTA's share of chunk p is in scA
-            if (STAGED && tilesA > 0) __syncthreads(); // pass B rewrites buf0
-            float2 xb[EPT];
-            const float2 *subB = scB + (long)k * R::NB; // this slot's sub-transform of the chunk's first transform
-            if ((long)blockIdx.x < tilesB) load_b(xb, subB + (blockIdx.x >> LOG_NKB) * n, tB, pol);
-            for (long tl = blockIdx.x; tl < tilesB; tl += gridDim.x) {
-                const long b = tl >> LOG_NKB;
-                const long nx = tl + gridDim.x;
-                const bool last = nx >= tilesB;
-                tile_b(io, xb, twB0, twB1, rowB0 + b, kb, last ? (const float2 *)nullptr : subB + (nx >> LOG_NKB) * n, bfa, bfb,
-                       buf0, tB, tid, ep, rtwb, pol, [&] {
-                    // buf1 is idle from here to the next pass-B tile: the last one of the phase requests
-                    // the first pass-A tile of the next phase (only if this launch runs that phase)
-                    if (last && more && (long)blockIdx.x < tilesA1)
-                        prefetch_a(io, rowA0 + chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid, pol);
-                });
-                __syncthreads(); // both buffers are rewritten by the next tile
+            // pass B of transform i
+            if (!have_xb) { // first tile: its inputs could not be requested behind an epilogue
+                if (nextA) __syncthreads(); // pass A's reads of buf0 / stores precede the arrival below
+                if (nextA && tid == 0) flag_arrive(cntA);
+                seenA = peek(cntA);
+                await(cntA, seenA, (unsigned)(NKB * (i + 1)));
+                __syncthreads();
+                load_b(xb, slot_of_i(i) + (long)k * R::NB, tB, pol);
             }
-            // no pass-B tile in this phase (first phase, or fewer tiles than CTAs): request it here
-            if (more && tilesB <= (long)blockIdx.x && (long)blockIdx.x < tilesA1)
-                prefetch_a(io, rowA0 + chunk_rows + (blockIdx.x >> LOG_NKB), j0, buf1, tid, pol);
+            const bool arrive_in_b = have_xb && nextA; // pass A's arrival rides on pass B's first barrier
+            const bool nextB = i + 1 < cnt;
+            seenA = peek(cntA);
+            tile_b(io, xb, twB0, twB1, row_of(i), kb, nextB ? slot_of_i(i + 1) + (long)k * R::NB : (const float2 *)nullptr,
+                   bfa, bfb, buf0, tB, tid, ep, rtwb, pol,
+                   [&] { if (arrive_in_b && tid == 0) flag_arrive(cntA); },
+                   [&] { if (nextB) await(cntA, seenA, (unsigned)(NKB * (i + 2))); },
+                   [&] {
+                       if (tid == 0) flag_arrive_relaxed(cntB); // this CTA's reads of slot i are in registers
+                       if (i + 2 < cnt) prefetch_a(io, row_of(i + 2), j0, buf1, tid, pol);
+                   });
+            have_xb = nextB;
+            __syncthreads(); // both buffers are rewritten by the next tile
         }
     }
 };
@@ -701,11 +722,10 @@ __global__ void __launch_bounds__(256, 2)
 template <int LB, bool EXACT, class IO, int EPI, bool STAGED>
 __global__ void __launch_bounds__(256, 2)
     large_pipe_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0 tw0, const float2 *__restrict__ table,
-                      long rows, long chunk_rows, float2 *__restrict__ scratch, int phase_begin, int phase_end,
-                      unsigned *bar)
+                      long rows, float2 *__restrict__ scratch, unsigned *flags)
 {
     extern __shared__ __align__(128) float2 smem[];
-    LargePipe<LB, EXACT, IO, EPI, STAGED>::run(io, tw0, table, rows, chunk_rows, scratch, smem, phase_begin, phase_end, bar);
+    LargePipe<LB, EXACT, IO, EPI, STAGED>::run(io, tw0, table, rows, scratch, smem, flags);
 }
 #endif
 

@@ -126,7 +126,8 @@ cudaError_t launch_fused(const IO &io, const LaunchArgs &a, const LargeArgs &g)
     return cudaLaunchKernelEx(&cfg, kern, io, a.tw0, a.table, g.chunk_rows, g.scratch);
 }
 
-// one persistent cooperative launch: pass A of chunk p overlapped with pass B of chunk p-1
+// one persistent cooperative launch: teams of NKB CTAs, pass A of a team's next transform overlapped
+// with pass B of its current one, dependency flags inside the team
 template <int LB, bool EXACT, class IO, int EPI, bool STAGED>
 cudaError_t launch_pipe_v(const IO &io, const LaunchArgs &a, LargeArgs &g)
 {
@@ -139,31 +140,20 @@ cudaError_t launch_pipe_v(const IO &io, const LaunchArgs &a, LargeArgs &g)
     int per_sm = occ < kMaxPipeCtasPerSm ? occ : kMaxPipeCtasPerSm;
     long cap = a.max_ctas > 0 ? a.max_ctas : (long)per_sm * a.num_sms;
     if (cap > (long)per_sm * a.num_sms) cap = (long)per_sm * a.num_sms; // every CTA must be resident
-    long grid = cap / F::NKB * F::NKB;
-    if (grid < F::NKB) return cudaErrorLaunchOutOfResources;
+    long teams = cap / F::NKB;
+    if (teams < 1) return cudaErrorLaunchOutOfResources;
     long rows = g.chunk_rows;
-    if (grid > rows * F::NKB) grid = rows * F::NKB;
-    long chunk_rows = (long)g.pipe_iters * (grid / F::NKB);
-    int phases = (int)((rows + chunk_rows - 1) / chunk_rows) + 1;
+    if (teams > rows) teams = rows;
+    if (teams > g.pipe_max_teams) teams = g.pipe_max_teams; // what the caller sized scratch and flags for
     float2 *scratch = g.scratch;
-    unsigned *bar = g.bar;
+    unsigned *flags = g.flags;
     const float2 *table = a.table;
-    if (g.pipe_coop) {
-        int p0 = 0, p1 = phases;
-        void *args[] = {(void *)&io, (void *)&a.tw0, (void *)&table, (void *)&rows, (void *)&chunk_rows,
-                        (void *)&scratch, (void *)&p0, (void *)&p1, (void *)&bar};
-        e = cudaMemsetAsync(bar, 0, sizeof(unsigned), a.stream);
-        if (e != cudaSuccess) return e;
-        g.launches = 1;
-        return cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(256), args, F::SMEM_BYTES, a.stream);
-    }
-    for (int p = 0; p < phases; p++) {
-        kern<<<(int)grid, 256, F::SMEM_BYTES, a.stream>>>(io, a.tw0, table, rows, chunk_rows, scratch, p, p + 1, bar);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
-    g.launches = phases;
-    return cudaSuccess;
+    void *args[] = {(void *)&io, (void *)&a.tw0, (void *)&table, (void *)&rows, (void *)&scratch, (void *)&flags};
+    e = cudaMemsetAsync(flags, 0, sizeof(unsigned) * F::FLAG_STRIDE * teams, a.stream);
+    if (e != cudaSuccess) return e;
+    g.launches = 1;
+    return cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)(teams * F::NKB)), dim3(256), args, F::SMEM_BYTES,
+                                       a.stream);
 }
 
 // a.staged: the host verified 16-byte alignment of the rows (asynchronous 16-byte copies)

@@ -89,12 +89,10 @@ struct kofft_cuda_ctx {
     size_t istft_ws_limit = size_t(1) << 30;
     bool use_tma = true; // TMA-staged input prefetch where alignment allows
     bool large_fused = false; // N > 16384: one persistent thread-block-cluster kernel instead of two kernels per chunk
-    // N > 16384 default: one persistent cooperative kernel, pass A of chunk p overlapped with pass B of
-    // chunk p-1, intermediate pinned in L2 (fft_large.cuh LargePipe)
+    // N > 16384 default: one persistent cooperative kernel, per-team dependency flags, intermediate
+    // pinned in L2 (fft_large.cuh LargePipe)
     bool large_pipe = true;
-    int pipe_iters = 3;
-    bool pipe_coop = true;
-    unsigned *pipe_bar = nullptr;
+    unsigned *pipe_flags = nullptr;
     bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
     int istft_run_frames = 128;
     // host-pointer batch entry points: the batch is cut into chunks that flow through three
@@ -219,10 +217,10 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
             void *scratch = nullptr;
             if (ctx->large_pipe && !ctx->large_fused) {
                 const int nkb = L == 15 ? 8 : 16;
-                const size_t chunk_max = size_t(ctx->pipe_iters) * (size_t(kMaxPipeCtasPerSm) * ctx->num_sms / nkb);
-                rc = ensure_ws(ctx, 4, size_t(3) * chunk_max * row_bytes, &scratch);
+                const int max_teams = kMaxPipeCtasPerSm * ctx->num_sms / nkb;
+                rc = ensure_ws(ctx, 4, size_t(3) * max_teams * row_bytes, &scratch);
                 if (rc) return rc;
-                if (!ctx->pipe_bar) CU(cudaMalloc(&ctx->pipe_bar, sizeof(unsigned)));
+                if (!ctx->pipe_flags) CU(cudaMalloc(&ctx->pipe_flags, sizeof(unsigned) * kPipeFlagStride * max_teams));
                 LargeArgs g;
                 g.lsub = L - 8;
                 g.row0 = 0;
@@ -230,9 +228,8 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
                 g.scratch = static_cast<float2 *>(scratch);
                 g.fused = false;
                 g.pipe = true;
-                g.pipe_iters = ctx->pipe_iters;
-                g.pipe_coop = ctx->pipe_coop;
-                g.bar = ctx->pipe_bar;
+                g.pipe_max_teams = max_teams;
+                g.flags = ctx->pipe_flags;
                 e = launch_large_fft(L, a, g);
                 if (e != cudaSuccess) return fail_cuda(e, "large-N pipelined kernel launch");
                 ctx->launches += g.launches;
@@ -341,9 +338,7 @@ int kofft_cuda_create(kofft_cuda_ctx **out, int device)
         ctx->large_pipe = strcmp(m, "pipe") == 0;
         ctx->large_fused = strcmp(m, "cluster") == 0;
     }
-    if (const char *v = getenv("KOFFT_LARGE_PIPE_ITERS"))
-        if (atoi(v) > 0) ctx->pipe_iters = atoi(v);
-    if (const char *v = getenv("KOFFT_LARGE_PIPE_COOP")) ctx->pipe_coop = atoi(v) != 0;
+
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -368,7 +363,7 @@ void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
     }
     for (int i = 0; i < 5; i++)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
-    if (ctx->pipe_bar) cudaFree(ctx->pipe_bar);
+    if (ctx->pipe_flags) cudaFree(ctx->pipe_flags);
     if (ctx->pipe_ready) {
         for (int i = 0; i < 3; i++) {
             cudaStreamSynchronize(ctx->pipe_stream[i]);
@@ -414,13 +409,11 @@ int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames)
     if (run_frames > 0) ctx->istft_run_frames = run_frames;
     return KOFFT_OK;
 }
-int kofft_cuda_set_large_mode(kofft_cuda_ctx *ctx, int mode, int iters)
+int kofft_cuda_set_large_mode(kofft_cuda_ctx *ctx, int mode)
 {
-    if (mode < 0 || mode > 2 || iters < 0 || iters > 64)
-        return fail_msg(KOFFT_ERR_INVALID_VALUE, "set_large_mode: mode 0..2, iters 0..64");
+    if (mode < 0 || mode > 2) return fail_msg(KOFFT_ERR_INVALID_VALUE, "set_large_mode: mode 0..2");
     ctx->large_pipe = mode == 2;
     ctx->large_fused = mode == 1;
-    if (iters > 0) ctx->pipe_iters = iters;
     return KOFFT_OK;
 }
 int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable)

@@ -74,15 +74,15 @@ struct LargeArgs {
     int max_clusters = 0;      // fused path: 0 = as many clusters as fit on the device
     bool stage_rows = true;    // two-kernel path: row pass prefetches its next tile with TMA bulk copies
     // pipelined persistent kernel (LargePipe): chunk_rows = every transform of the batch, scratch =
-    // 3 * pipe_iters * (kMaxPipeCtasPerSm * SMs / NKB) * 2^L complex, bar = arrival counter
+    // pipe_max_teams * 3 * 2^L complex, flags = pipe_max_teams * kPipeFlagStride counters
     bool pipe = false;
-    int pipe_iters = 3;        // tiles per CTA per phase
-    bool pipe_coop = true;     // one cooperative launch; false: one launch per phase
-    unsigned *bar = nullptr;
+    int pipe_max_teams = 0;
+    unsigned *flags = nullptr;
     int launches = 0;          // out: kernels launched
 };
-// upper bound on the CTAs of the pipelined kernel per SM (sizes its scratch)
+// upper bound on the CTAs of the pipelined kernel per SM (sizes its scratch); counters per team
 constexpr int kMaxPipeCtasPerSm = 2;
+constexpr int kPipeFlagStride = 32;
 // upper bound on the clusters the fused kernel runs with (sizes its scratch)
 constexpr int kMaxFusedClusters = 148;
 cudaError_t launch_large_fft(int L, const LaunchArgs &a, LargeArgs &g);

@@ -107,10 +107,9 @@ class Context:
 
     LARGE_TWO_KERNEL, LARGE_CLUSTER, LARGE_PIPELINED = 0, 1, 2
 
-    def set_large_mode(self, mode: int, iters: int = 0) -> None:
-        """N > 16384: 2 = persistent pipelined kernel (default), 0 = two kernels per chunk, 1 = cluster kernel;
-        iters = tiles per CTA per chunk of the pipelined kernel (0 = keep)."""
-        check(_lib.lib().kofft_cuda_set_large_mode(self.handle, int(mode), int(iters)))
+    def set_large_mode(self, mode: int) -> None:
+        """N > 16384: 2 = persistent pipelined kernel (default), 0 = two kernels per chunk, 1 = cluster kernel."""
+        check(_lib.lib().kofft_cuda_set_large_mode(self.handle, int(mode)))
 
     def set_rfft_table_fma(self, fma: bool) -> None:
         check(_lib.lib().kofft_cuda_set_rfft_table_fma(self.handle, int(bool(fma))))

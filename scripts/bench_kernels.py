@@ -1,5 +1,5 @@
 """Times the device-pointer kernels of every BASELINE config shape (CUDA events, data resident in HBM).
-   python scripts/bench_kernels.py [which ...]    which: c2c c2c2048 stft stftmag istft rfft large [pipesweep]   (default: all but pipesweep)
+   python scripts/bench_kernels.py [which ...]    which: c2c c2c2048 stft stftmag istft rfft large   (default: all)
 Prints one JSON line per measurement.  Used to compare tuning variants (KOFFT_CUDA_LIB=...)."""
 import json
 import os
@@ -97,12 +97,7 @@ def main():
                 fft.ctx.set_large_mode(m)
                 ms, best = timeit(lambda: fft.rfft_batch(x, out=out), 6, 2)
                 report("rfft_65536x16384_" + name, mode, ms, best, nbytes)
-            if "pipesweep" in which:
-                for iters in (1, 2, 3, 4, 5, 6, 8):
-                    fft.ctx.set_large_mode(2, iters)
-                    ms, best = timeit(lambda: fft.rfft_batch(x, out=out), 6, 2)
-                    report(f"rfft_65536x16384_pipelined_iters{iters}", mode, ms, best, nbytes)
-            fft.ctx.set_large_mode(2, 3)
+            fft.ctx.set_large_mode(2)
             del x, out
         if "large" in which:
             for n in (32768, 65536):
@@ -112,12 +107,7 @@ def main():
                     fft.ctx.set_large_mode(m)
                     ms, best = timeit(lambda: fft.fft_batch(x, out=y), 6, 2)
                     report(f"c2c_{n}x{2 ** 28 // n}_" + name, mode, ms, best, 2 * x.numel() * 8)
-                if "pipesweep" in which:
-                    for iters in (1, 2, 4, 6, 8):
-                        fft.ctx.set_large_mode(2, iters)
-                        ms, best = timeit(lambda: fft.fft_batch(x, out=y), 6, 2)
-                        report(f"c2c_{n}x{2 ** 28 // n}_pipelined_iters{iters}", mode, ms, best, 2 * x.numel() * 8)
-                fft.ctx.set_large_mode(2, 3)
+                fft.ctx.set_large_mode(2)
                 del x, y
         fft.close() if hasattr(fft, "close") else None
 

@@ -1,6 +1,6 @@
 #!/bin/bash
-# GPU-box session for the N > 16384 paths: parity of the three implementations, timing sweep of the
-# pipelined kernel (tiles per phase x intermediate buffers), launch-per-phase variant, ncu capture.
+# GPU-box session for the N > 16384 paths: parity and timing of the three implementations, ncu capture
+# of the pipelined kernel.
 # Usage (under gpurun): bash scripts/gpu_large.sh [tag]
 TAG=${1:-large}
 OUT=gpurun_out/$TAG
@@ -11,13 +11,10 @@ timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cachepr
 echo "pytest exit $?" | tee -a $OUT/summary.txt
 tail -15 $OUT/pytest_large.log | tee -a $OUT/summary.txt
 echo "== sweep" | tee -a $OUT/summary.txt
-KOFFT_CUDA_VERBOSE=1 timeout 600 python scripts/bench_kernels.py rfft large pipesweep > $OUT/large_kernels.jsonl 2> $OUT/sweep.err
+KOFFT_CUDA_VERBOSE=1 timeout 600 python scripts/bench_kernels.py rfft large > $OUT/large_kernels.jsonl 2> $OUT/sweep.err
 echo "sweep exit $?" | tee -a $OUT/summary.txt
 cat $OUT/large_kernels.jsonl | tee -a $OUT/summary.txt
 tail -5 $OUT/sweep.err | tee -a $OUT/summary.txt
-echo "== one launch per phase (no grid barrier)" | tee -a $OUT/summary.txt
-KOFFT_LARGE_PIPE_COOP=0 timeout 300 python scripts/bench_kernels.py rfft > $OUT/large_kernels_noncoop.jsonl 2>> $OUT/sweep.err
-cat $OUT/large_kernels_noncoop.jsonl | tee -a $OUT/summary.txt
 echo "== ncu full (pipelined rfft)" | tee -a $OUT/summary.txt
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:large_pipe -s 2 -c 1 -o $OUT/prof_rfft_pipe \
     python scripts/one_kernel.py rfft > $OUT/ncu_rfft_pipe.log 2>&1; echo "ncu exit $?" | tee -a $OUT/summary.txt

@@ -132,10 +132,9 @@ int run_fused(const IO &io, const float *table, long rows, int nclusters)
     return 0;
 }
 
-// the pipelined persistent kernel body (LargePipe::run), one emulated launch per phase: `grid` CTAs,
-// `iters` tiles per CTA per phase
+// the pipelined persistent kernel body (LargePipe::run): `grid` CTAs = grid / NKB teams; the CTAs of a
+// team run as interleaved coroutines (the emulator's cluster mode), so the dependency flags are live
 static bool g_pipe = false;
-static int g_pipe_iters = 1;
 
 template <int LB, bool EXACT, class IO, int EPI, bool STAGED>
 int run_pipe_v(const IO &io, const float *table, long rows, int grid)
@@ -145,18 +144,19 @@ int run_pipe_v(const IO &io, const float *table, long rows, int grid)
     const long n = 1L << L;
     Tw0 tw0 = make_tw0(L, 4, table);
     const float2 *tab = reinterpret_cast<const float2 *>(table);
-    grid = grid / F::NKB * F::NKB;
-    if (grid < F::NKB) grid = F::NKB;
-    if (grid > rows * F::NKB) grid = (int)(rows * F::NKB);
-    const long chunk_rows = (long)g_pipe_iters * (grid / F::NKB);
-    const int phases = (int)((rows + chunk_rows - 1) / chunk_rows) + 1;
-    std::vector<float2> scratch((size_t)F::NIBUF * chunk_rows * n);
-    std::vector<float2> smem((F::SMEM_BYTES + 256) / 8);
-    float2 *sm = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
-    for (int p = 0; p < phases; p++)
-        cuda_emu::launch((unsigned)grid, 256, [&] {
-            F::run(io, tw0, tab, rows, chunk_rows, scratch.data(), sm, p, p + 1, nullptr);
-        });
+    long teams = grid / F::NKB;
+    if (teams < 1) teams = 1;
+    if (teams > rows) teams = rows;
+    std::vector<float2> scratch((size_t)teams * F::SLOTS * n);
+    std::vector<unsigned> flags((size_t)teams * F::FLAG_STRIDE, 0u);
+    // one shared-memory block per CTA of the team
+    const size_t per = ((F::SMEM_BYTES + 255) / 8 + 15) / 16 * 16;
+    std::vector<float2> smem(per * F::NKB + 32);
+    float2 *base = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
+    cuda_emu::launch((unsigned)(teams * F::NKB), 256, [&] {
+        float2 *sm = base + (size_t)cuda_emu::cluster_rank() * per;
+        F::run(io, tw0, tab, rows, scratch.data(), sm, flags.data());
+    }, F::NKB);
     return 0;
 }
 
@@ -224,11 +224,7 @@ API int kofft_emuk_cta(int kind, int exact, int L, long rows, const void *in, co
 }
 
 API void kofft_emuk_set_fused(int fused) { g_fused = fused != 0; }
-API void kofft_emuk_set_pipe(int pipe, int iters)
-{
-    g_pipe = pipe != 0;
-    g_pipe_iters = iters > 0 ? iters : 1;
-}
+API void kofft_emuk_set_pipe(int pipe) { g_pipe = pipe != 0; }
 API void kofft_emuk_set_large_staged(int staged) { g_large_staged = staged != 0; }
 
 // the real two-pass kernel bodies; L = 15 or 16 is the length of the complex core

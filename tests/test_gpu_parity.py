@@ -681,10 +681,10 @@ def test_large_paths_agree(cuda_fft, oracle, n):
     bref = oracle.irfft_batch(rref, 2 * n, nthreads=8)
     C = cuda_fft.ctx
     try:
-        for mode, iters in ((C.LARGE_PIPELINED, 1), (C.LARGE_PIPELINED, 3), (C.LARGE_CLUSTER, 0), (C.LARGE_TWO_KERNEL, 0)):
+        for mode in (C.LARGE_PIPELINED, C.LARGE_CLUSTER, C.LARGE_TWO_KERNEL):
             C.set_cluster_fusion(False)
-            C.set_large_mode(mode, iters)
-            tag = f"mode={mode} iters={iters}"
+            C.set_large_mode(mode)
+            tag = f"mode={mode}"
             y = x.copy()
             cuda_fft.fft_batch(y)
             assert np.array_equal(y, ref), tag
@@ -694,34 +694,39 @@ def test_large_paths_agree(cuda_fft, oracle, n):
             assert np.array_equal(cuda_fft.rfft_batch(xr), rref), tag
             assert np.array_equal(cuda_fft.irfft_batch(rref, 2 * n), bref), tag
     finally:
-        C.set_large_mode(C.LARGE_PIPELINED, 3)
+        C.set_large_mode(C.LARGE_PIPELINED)
 
 
-def test_large_pipelined_many_phases_on_device(cuda_fft, oracle):
-    """The pipelined kernel on device-resident rows, ~40 phases, every mode of the barrier: sampled
-    rows bit-identical to the oracle, and the whole batch identical across chunk sizes."""
+def test_large_pipelined_many_transforms_per_team_on_device(cuda_fft, oracle):
+    """The pipelined kernel on device-resident rows: ~40 transforms per team (slot reuse, both
+    dependency counters), grids of one team up to the full device, repeated launches (the counters
+    are re-zeroed); sampled rows bit-identical to the oracle, whole batch identical across grids."""
     import torch
 
     n, rows = 32768, 1500
     g = torch.Generator(device="cuda").manual_seed(11)
     x = torch.view_as_complex((torch.rand((rows, n, 2), generator=g, device="cuda") * 2 - 1).contiguous())
+    xr = (torch.rand((rows, 2 * n), generator=g, device="cuda") * 2 - 1).contiguous()
     C = cuda_fft.ctx
-    outs = []
+    outs, routs = [], []
     try:
-        for iters in (1, 2, 3, 5):
-            C.set_large_mode(C.LARGE_PIPELINED, iters)
+        for max_ctas in (0, 8, 24, 160):
+            C.set_max_ctas(max_ctas)
             y = torch.empty_like(x)
-            for _ in range(3):  # repeated launches reuse the arrival counter
+            for _ in range(3):
                 cuda_fft.fft_batch(x, out=y)
             torch.cuda.synchronize()
             outs.append(y)
+            routs.append(cuda_fft.rfft_batch(xr))
+            torch.cuda.synchronize()
     finally:
-        C.set_large_mode(C.LARGE_PIPELINED, 3)
+        C.set_max_ctas(0)
     pick = [0, 1, 36, 37, 73, 74, 700, rows - 2, rows - 1]
-    ref = oracle.fft_batch(x[pick].cpu().numpy(), nthreads=8)
-    assert np.array_equal(outs[0][pick].cpu().numpy(), ref)
-    for y in outs[1:]:
+    assert np.array_equal(outs[0][pick].cpu().numpy(), oracle.fft_batch(x[pick].cpu().numpy(), nthreads=8))
+    assert np.array_equal(routs[0][pick].cpu().numpy(), oracle.rfft_batch(xr[pick].cpu().numpy(), nthreads=8))
+    for y, yr in zip(outs[1:], routs[1:]):
         assert torch.equal(torch.view_as_real(y), torch.view_as_real(outs[0]))
+        assert torch.equal(torch.view_as_real(yr), torch.view_as_real(routs[0]))
 
 
 @pytest.mark.parametrize("n", [65536, 131072])
