@@ -399,9 +399,9 @@ struct LargeFused {
 // q, q + teams, q + 2 teams, ...; member kb runs, for its i-th transform,
 //     step i:   pass A tile of transform i+1  (HBM -> intermediate slot (i+1) mod 3)  ... arrive A
 //               pass B tile of transform i    (intermediate slot i mod 3 -> HBM)      ... arrive B
-// Pass B of transform i needs the NKB pass-A tiles of that transform: counter cntA >= NKB (i+1).
-// Pass A of transform i+1 overwrites the slot of transform i-2: counter cntB >= NKB (i-1).
-// Both conditions were met about one step earlier unless a member lags by more than a step, and
+// Pass B of transform i needs the NKB pass-A tiles of that transform, pass A of transform i+1
+// overwrites the slot of transform i-2 and needs its NKB pass-B tiles to have consumed it: one
+// arrival counter per team, slot and pass.  Both conditions were met about one step earlier unless a member lags by more than a step, and
 // the polling thread issues its flag load a register pass ahead of the check, so neither the
 // skew between CTAs nor the flag's L2 round trip is normally exposed.  There is no grid-wide
 // synchronisation: a slow SM delays only its own team (the first version of this kernel used a
@@ -595,7 +595,15 @@ struct LargePipe {
         const long n = 1L << (LARGE_S1 + LB);
         const int kb = blockIdx.x % NKB; // column tile of pass A == k-block of pass B
         const long team = blockIdx.x / NKB, teams = gridDim.x / NKB;
-        unsigned *cntA = flags + team * FLAG_STRIDE, *cntB = cntA + 1;
+        // per team and per intermediate slot: arrivals of pass-A tiles / of pass-B tiles.  One counter per
+        // SLOT, not per team: a member may run up to two steps ahead of another, and a single running
+        // count would let its early arrivals stand in for a late member's missing one (seen on the GPU as
+        // a wrong first transform of the teams whose CTAs start in the second placement wave).  Per slot
+        // this cannot happen: nobody arrives for transform i+3 before everybody has finished transform i.
+        unsigned *cntA = flags + team * FLAG_STRIDE, *cntB = cntA + SLOTS;
+        auto doneA = [&](long i) { return cntA + i % SLOTS; };
+        auto doneB = [&](long i) { return cntB + i % SLOTS; };
+        auto goal = [&](long i) { return (unsigned)(NKB * (i / SLOTS + 1)); };
         const L2Policy pol = make_l2_policy();
         // pass A (column-fastest mapping); its pass-1 twiddles are shared by the 16 columns -> shared memory
         const int slotA = tid & (C::COLS - 1), tA = tid >> 4;
@@ -652,7 +660,7 @@ struct LargePipe {
         prefetch_a(io, row_of(0), j0, buf1, tid, pol);
         tile_a(io, tw0, twA + tA * 16, row_of(0), j0, slot_of_i(0), bufA, buf1, tA, slotA, pol, [] {});
         __syncthreads();
-        if (tid == 0) flag_arrive(cntA);
+        if (tid == 0) flag_arrive(doneA(0));
         if (cnt > 1) prefetch_a(io, row_of(1), j0, buf1, tid, pol); // buf1 is idle until the first pass-B tile
         float2 xb[EPT];
         bool have_xb = false;
@@ -660,29 +668,29 @@ struct LargePipe {
             const bool nextA = i + 1 < cnt;
             if (nextA) {
                 // pass A of transform i+1 into the slot transform i-2 occupied: every member must have
-                // consumed it (cntB >= NKB (i-1)); the flag load is issued before the tile's first pass
-                seenB = peek(cntB);
+                // consumed it; the flag load is issued before the tile's first pass
+                if (i >= 2) seenB = peek(doneB(i - 2));
                 tile_a(io, tw0, twA + tA * 16, row_of(i + 1), j0, slot_of_i(i + 1), bufA, buf1, tA, slotA, pol,
-                       [&] { if (i >= 2) await(cntB, seenB, (unsigned)(NKB * (i - 1))); });
+                       [&] { if (i >= 2) await(doneB(i - 2), seenB, goal(i - 2)); });
             }
             // pass B of transform i
             if (!have_xb) { // first tile: its inputs could not be requested behind an epilogue
                 if (nextA) __syncthreads(); // pass A's reads of buf0 / stores precede the arrival below
-                if (nextA && tid == 0) flag_arrive(cntA);
-                seenA = peek(cntA);
-                await(cntA, seenA, (unsigned)(NKB * (i + 1)));
+                if (nextA && tid == 0) flag_arrive(doneA(i + 1));
+                seenA = peek(doneA(i));
+                await(doneA(i), seenA, goal(i));
                 __syncthreads();
                 load_b(xb, slot_of_i(i) + (long)k * R::NB, tB, pol);
             }
             const bool arrive_in_b = have_xb && nextA; // pass A's arrival rides on pass B's first barrier
             const bool nextB = i + 1 < cnt;
-            seenA = peek(cntA);
+            if (nextB) seenA = peek(doneA(i + 1));
             tile_b(io, xb, twB0, twB1, row_of(i), kb, nextB ? slot_of_i(i + 1) + (long)k * R::NB : (const float2 *)nullptr,
                    bfa, bfb, buf0, tB, tid, ep, rtwb, pol,
-                   [&] { if (arrive_in_b && tid == 0) flag_arrive(cntA); },
-                   [&] { if (nextB) await(cntA, seenA, (unsigned)(NKB * (i + 2))); },
+                   [&] { if (arrive_in_b && tid == 0) flag_arrive(doneA(i + 1)); },
+                   [&] { if (nextB) await(doneA(i + 1), seenA, goal(i + 1)); },
                    [&] {
-                       if (tid == 0) flag_arrive_relaxed(cntB); // this CTA's reads of slot i are in registers
+                       if (tid == 0) flag_arrive_relaxed(doneB(i)); // this CTA's reads of slot i are in registers
                        if (i + 2 < cnt) prefetch_a(io, row_of(i + 2), j0, buf1, tid, pol);
                    });
             have_xb = nextB;

@@ -65,6 +65,8 @@ struct Scheduler {
 };
 
 inline Scheduler *g_sched = nullptr;
+inline unsigned g_late_from = ~0u;      // see run_cluster
+inline unsigned long long g_late_ratio = 1;
 
 inline void yield_to_scheduler()
 {
@@ -150,15 +152,25 @@ inline void run_cluster(unsigned first_block, unsigned cluster, unsigned grid_x,
             makecontext(&t.ctx, reinterpret_cast<void (*)()>(trampoline), 0);
         }
     }
+    // g_late_from / g_late_ratio: blocks with cluster rank >= g_late_from get one scheduling pass for
+    // every g_late_ratio passes of the others -- a crude model of CTAs that start (or run) late, to
+    // shake out flag protocols that only work while the CTAs of a team advance in lockstep
+    unsigned long long pass = 0;
     while (s.alive > 0) {
+        const bool late_turn = g_late_ratio <= 1 || pass % g_late_ratio == g_late_ratio - 1;
+        bool ran = false;
         for (size_t i = 0; i < s.threads.size(); i++) {
             Thread &t = s.threads[i];
             if (t.done) continue;
+            if (!late_turn && t.block >= g_late_from) continue;
+            ran = true;
             s.current = static_cast<int>(i);
             threadIdx = t.tid;
             blockIdx = s.blocks[t.block].bid;
             swapcontext(&s.main_ctx, &t.ctx);
         }
+        pass++;
+        (void)ran;
     }
     g_sched = nullptr;
 }

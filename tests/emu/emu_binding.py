@@ -92,12 +92,13 @@ class EmuKernels:
         assert rc == 0, rc
 
     def large(self, kind, exact, L, rows, table, inp=None, in2=None, out=None, out2=None, aux=None,
-              p=(0, 0, 0, 0), scale=1.0, grid_col=5, grid_row=16, fused=False, staged=False, pipe=False):
+              p=(0, 0, 0, 0), scale=1.0, grid_col=5, grid_row=16, fused=False, staged=False, pipe=False, skew=None):
         """ColPass::run + RowPass::run (two chunks) for a complex core of length 2^L, or (fused)
         LargeFused::run on `grid_col` thread-block clusters, or (pipe) LargePipe::run on `grid_col` CTAs
         (teams of 8 / 16 CTAs run concurrently, so the dependency flags are exercised)."""
         self.lib.kofft_emuk_set_fused(int(fused))
         self.lib.kofft_emuk_set_pipe(int(bool(pipe)))
+        self.lib.kofft_emuk_set_skew(*(skew or (0, 0)))  # (late_from, ratio): CTAs of a team that run late
         self.lib.kofft_emuk_set_large_staged(int(staged))
         rc = self.lib.kofft_emuk_large(KIND[kind], int(exact), L, rows, self._ptr(inp), self._ptr(in2),
                                        self._ptr(out), self._ptr(out2), self._ptr(aux), *[int(v) for v in p],

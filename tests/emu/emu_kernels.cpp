@@ -225,6 +225,12 @@ API int kofft_emuk_cta(int kind, int exact, int L, long rows, const void *in, co
 
 API void kofft_emuk_set_fused(int fused) { g_fused = fused != 0; }
 API void kofft_emuk_set_pipe(int pipe) { g_pipe = pipe != 0; }
+// CTAs with team rank >= late_from run `ratio` times slower than the others (0 / 1 = off)
+API void kofft_emuk_set_skew(int late_from, int ratio)
+{
+    cuda_emu::g_late_from = ratio > 1 ? (unsigned)late_from : ~0u;
+    cuda_emu::g_late_ratio = ratio > 1 ? (unsigned long long)ratio : 1;
+}
 API void kofft_emuk_set_large_staged(int staged) { g_large_staged = staged != 0; }
 
 // the real two-pass kernel bodies; L = 15 or 16 is the length of the complex core

@@ -166,36 +166,38 @@ def test_large_fused_cluster_kernel_body(emuk, oracle, L):
     assert np.array_equal(zr, oracle.irfft_batch(yr, 2 * n))
 
 
-@pytest.mark.parametrize("L,grid,rows,staged", [(15, 16, 7, True), (16, 16, 4, False), (15, 8, 5, True)])
-def test_large_pipelined_kernel_body(emuk, oracle, L, grid, rows, staged):
+@pytest.mark.parametrize("L,grid,rows,staged,skew", [(15, 16, 7, True, None), (16, 16, 4, False, (5, 7)), (15, 8, 5, True, (4, 25))])
+def test_large_pipelined_kernel_body(emuk, oracle, L, grid, rows, staged, skew):
     """LargePipe::run: teams of 8 / 16 CTAs (run concurrently by the emulator), pass A of a team's next
     transform ahead of pass B of the current one, dependency flags, three rotating intermediate
-    slots per team, pass A's tile staged in the idle exchange buffer with asynchronous copies."""
+    slots per team, pass A's tile staged in the idle exchange buffer with asynchronous copies.
+    skew = (late_from, ratio): the team's CTAs from rank late_from on run `ratio` times slower, so the
+    others run ahead as far as the flags allow (a single running counter per team fails this)."""
     n = 1 << L
     rng = np.random.default_rng(900 + L + grid)
     x = uniform_c64(rng, (rows, n))
     tab = oracle.twiddles(n)
     y = np.zeros_like(x)
-    emuk.large("c2c_fwd", True, L, rows, tab, inp=x, out=y, grid_col=grid, pipe=True, staged=staged)
+    emuk.large("c2c_fwd", True, L, rows, tab, inp=x, out=y, grid_col=grid, pipe=True, staged=staged, skew=skew)
     assert np.array_equal(y, oracle.fft_batch(x))
     y[...] = 0
     emuk.large("c2c_inv", True, L, rows, tab, inp=x, out=y, scale=float(np.float32(1) / np.float32(n)),
-               grid_col=grid, pipe=True, staged=staged)
+               grid_col=grid, pipe=True, staged=staged, skew=skew)
     assert np.array_equal(y, oracle.fft_batch(x, inverse=True))
     xr = rng.uniform(-1, 1, (rows, 2 * n)).astype(np.float32)
     rtw = oracle.rfft_twiddles(n)
     yr = np.zeros((rows, n + 1), np.complex64)
-    emuk.large("rfft", True, L, rows, tab, inp=xr, out=yr, aux=rtw, grid_col=grid, pipe=True, staged=staged)
+    emuk.large("rfft", True, L, rows, tab, inp=xr, out=yr, aux=rtw, grid_col=grid, pipe=True, staged=staged, skew=skew)
     ref = oracle.rfft_batch(xr)
     assert np.array_equal(yr, ref)
     zr = np.zeros((rows, 2 * n), np.float32)
     emuk.large("irfft", True, L, rows, tab, inp=ref, out=zr, aux=rtw, scale=float(np.float32(1) / np.float32(n)),
-               grid_col=grid, pipe=True, staged=staged)
+               grid_col=grid, pipe=True, staged=staged, skew=skew)
     assert np.array_equal(zr, oracle.irfft_batch(ref, 2 * n))
     re, im = np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag)
     ore, oim = np.zeros_like(re), np.zeros_like(im)
     emuk.large("gen_fwd", True, L, rows, tab, inp=re, in2=im, out=ore, out2=oim, p=(1, n, 1, n), grid_col=grid,
-               pipe=True, staged=staged)
+               pipe=True, staged=staged, skew=skew)
     want = oracle.fft_batch(x)
     assert np.array_equal(ore, want.real) and np.array_equal(oim, want.imag)
 
