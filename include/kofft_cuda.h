@@ -72,7 +72,7 @@ int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames)
 /* N > 16384 (rfft above 32768): which of the three implementations of the two-pass split runs.
  *   mode 2 (default): one persistent cooperative kernel; teams of 8 / 16 CTAs overlap pass A of their
  *          next transform with pass B of the current one behind dependency flags, and the intermediate
- *          (3 transforms per team) is pinned in L2, so HBM sees the rows once in and once out.
+ *          (4 transforms per team) is pinned in L2, so HBM sees the rows once in and once out.
  *   mode 0: two kernels (column pass, row pass) per 256 MB batch chunk.
  *   mode 1: one persistent thread-block-cluster kernel (cluster barrier between the passes).
  * All three are bit-identical; 0 and 1 are kept for comparison (profiles/). */

@@ -397,18 +397,19 @@ struct LargeFused {
 // Both passes in ONE persistent kernel, software-pipelined per transform with dependency flags.
 // A "team" of NKB consecutive CTAs (one per column tile / k-block) owns the transforms
 // q, q + teams, q + 2 teams, ...; member kb runs, for its i-th transform,
-//     step i:   pass A tile of transform i+1  (HBM -> intermediate slot (i+1) mod 3)  ... arrive A
-//               pass B tile of transform i    (intermediate slot i mod 3 -> HBM)      ... arrive B
-// Pass B of transform i needs the NKB pass-A tiles of that transform, pass A of transform i+1
-// overwrites the slot of transform i-2 and needs its NKB pass-B tiles to have consumed it: one
-// arrival counter per team, slot and pass.  Both conditions were met about one step earlier unless a member lags by more than a step, and
+//     step i:   pass A tile of transform i+2  (HBM -> intermediate slot (i+2) mod 4)  ... arrive A
+//               pass B tile of transform i    (intermediate slot i mod 4 -> HBM)      ... arrive B
+// Pass B of transform i needs the NKB pass-A tiles of that transform (its inputs are requested one
+// step early, behind the previous tile's epilogue), pass A of transform i+2 overwrites the slot of
+// transform i-2 and needs its NKB pass-B tiles to have consumed it: one arrival counter per team,
+// slot and pass.  Both conditions were met about one step earlier unless a member lags by more than a step, and
 // the polling thread issues its flag load a register pass ahead of the check, so neither the
 // skew between CTAs nor the flag's L2 round trip is normally exposed.  There is no grid-wide
 // synchronisation: a slow SM delays only its own team (the first version of this kernel used a
 // grid barrier per batch chunk and lost 14 % of the warp time to it, profiles/r01x).  The
 // cooperative launch guarantees that all CTAs are co-resident, which the flag waits rely on.
 //
-// The intermediate is teams * 3 * 2^L complex (28 MB for N = 2^15): written with the L2
+// The intermediate is teams * 4 * 2^L complex (37 MB for N = 2^15): written with the L2
 // evict_last policy while the rows stream through with evict_first where the instruction allows,
 // so it never makes the round trip to HBM (the two-kernel path above needs long launches to
 // amortise launch + ramp + tail, and at those chunk sizes the intermediate spills: 2x the
@@ -583,7 +584,8 @@ struct LargePipe {
         }
     }
 
-    static constexpr int SLOTS = 3;         // intermediate slots per team
+    static constexpr int AHEAD = 2;         // pass A runs this many transforms ahead of pass B
+    static constexpr int SLOTS = AHEAD + 2; // intermediate slots per team
     static constexpr int FLAG_STRIDE = 32;  // unsigned per team: {cntA, cntB} in a 128-byte line of their own
 
     // rows: transforms in the batch; scratch: teams * SLOTS * n complex; flags: teams * FLAG_STRIDE
@@ -656,27 +658,29 @@ struct LargePipe {
         };
         if (cnt == 0) return;
 
-        // prologue: pass A of the team's first transform
+        // prologue: pass A of the team's first two transforms
         prefetch_a(io, row_of(0), j0, buf1, tid, pol);
-        tile_a(io, tw0, twA + tA * 16, row_of(0), j0, slot_of_i(0), bufA, buf1, tA, slotA, pol, [] {});
-        __syncthreads();
-        if (tid == 0) flag_arrive(doneA(0));
-        if (cnt > 1) prefetch_a(io, row_of(1), j0, buf1, tid, pol); // buf1 is idle until the first pass-B tile
+        for (long a0 = 0; a0 < AHEAD && a0 < cnt; a0++) {
+            tile_a(io, tw0, twA + tA * 16, row_of(a0), j0, slot_of_i(a0), bufA, buf1, tA, slotA, pol, [] {});
+            __syncthreads();
+            if (tid == 0) flag_arrive(doneA(a0));
+            if (a0 + 1 < cnt) prefetch_a(io, row_of(a0 + 1), j0, buf1, tid, pol); // buf1 is idle until the next tile
+        }
         float2 xb[EPT];
         bool have_xb = false;
         for (long i = 0; i < cnt; i++) {
-            const bool nextA = i + 1 < cnt;
+            const bool nextA = i + AHEAD < cnt;
             if (nextA) {
-                // pass A of transform i+1 into the slot transform i-2 occupied: every member must have
+                // pass A of transform i+AHEAD into the slot transform i-2 occupied: every member must have
                 // consumed it; the flag load is issued before the tile's first pass
                 if (i >= 2) seenB = peek(doneB(i - 2));
-                tile_a(io, tw0, twA + tA * 16, row_of(i + 1), j0, slot_of_i(i + 1), bufA, buf1, tA, slotA, pol,
+                tile_a(io, tw0, twA + tA * 16, row_of(i + AHEAD), j0, slot_of_i(i + AHEAD), bufA, buf1, tA, slotA, pol,
                        [&] { if (i >= 2) await(doneB(i - 2), seenB, goal(i - 2)); });
             }
             // pass B of transform i
             if (!have_xb) { // first tile: its inputs could not be requested behind an epilogue
                 if (nextA) __syncthreads(); // pass A's reads of buf0 / stores precede the arrival below
-                if (nextA && tid == 0) flag_arrive(doneA(i + 1));
+                if (nextA && tid == 0) flag_arrive(doneA(i + AHEAD));
                 seenA = peek(doneA(i));
                 await(doneA(i), seenA, goal(i));
                 __syncthreads();
@@ -687,11 +691,11 @@ struct LargePipe {
             if (nextB) seenA = peek(doneA(i + 1));
             tile_b(io, xb, twB0, twB1, row_of(i), kb, nextB ? slot_of_i(i + 1) + (long)k * R::NB : (const float2 *)nullptr,
                    bfa, bfb, buf0, tB, tid, ep, rtwb, pol,
-                   [&] { if (arrive_in_b && tid == 0) flag_arrive(doneA(i + 1)); },
+                   [&] { if (arrive_in_b && tid == 0) flag_arrive(doneA(i + AHEAD)); },
                    [&] { if (nextB) await(doneA(i + 1), seenA, goal(i + 1)); },
                    [&] {
                        if (tid == 0) flag_arrive_relaxed(doneB(i)); // this CTA's reads of slot i are in registers
-                       if (i + 2 < cnt) prefetch_a(io, row_of(i + 2), j0, buf1, tid, pol);
+                       if (i + AHEAD + 1 < cnt) prefetch_a(io, row_of(i + AHEAD + 1), j0, buf1, tid, pol);
                    });
             have_xb = nextB;
             __syncthreads(); // both buffers are rewritten by the next tile

@@ -132,6 +132,7 @@ template <int LB, bool EXACT, class IO, int EPI, bool STAGED>
 cudaError_t launch_pipe_v(const IO &io, const LaunchArgs &a, LargeArgs &g)
 {
     using F = LargePipe<LB, EXACT, IO, EPI, STAGED>;
+    static_assert(F::SLOTS == kLargePipeSlots && F::FLAG_STRIDE == kPipeFlagStride, "host-side sizes");
     auto kern = large_pipe_kernel<LB, EXACT, IO, EPI, STAGED>;
     static PerDevice occ_pd;
     int &occ = occ_pd.get();

@@ -218,7 +218,7 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
             if (ctx->large_pipe && !ctx->large_fused) {
                 const int nkb = L == 15 ? 8 : 16;
                 const int max_teams = kMaxPipeCtasPerSm * ctx->num_sms / nkb;
-                rc = ensure_ws(ctx, 4, size_t(3) * max_teams * row_bytes, &scratch);
+                rc = ensure_ws(ctx, 4, size_t(kLargePipeSlots) * max_teams * row_bytes, &scratch);
                 if (rc) return rc;
                 if (!ctx->pipe_flags) // sized for the smaller team (8 CTAs), whatever length comes first
                     CU(cudaMalloc(&ctx->pipe_flags, sizeof(unsigned) * kPipeFlagStride * (kMaxPipeCtasPerSm * ctx->num_sms / 8)));

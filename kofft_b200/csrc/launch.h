@@ -74,7 +74,7 @@ struct LargeArgs {
     int max_clusters = 0;      // fused path: 0 = as many clusters as fit on the device
     bool stage_rows = true;    // two-kernel path: row pass prefetches its next tile with TMA bulk copies
     // pipelined persistent kernel (LargePipe): chunk_rows = every transform of the batch, scratch =
-    // pipe_max_teams * 3 * 2^L complex, flags = pipe_max_teams * kPipeFlagStride counters
+    // pipe_max_teams * kLargePipeSlots * 2^L complex, flags = pipe_max_teams * kPipeFlagStride counters
     bool pipe = false;
     int pipe_max_teams = 0;
     unsigned *flags = nullptr;
@@ -83,6 +83,7 @@ struct LargeArgs {
 // upper bound on the CTAs of the pipelined kernel per SM (sizes its scratch); counters per team
 constexpr int kMaxPipeCtasPerSm = 2;
 constexpr int kPipeFlagStride = 32;
+constexpr int kLargePipeSlots = 4; // intermediate transforms per team (LargePipe::SLOTS)
 // upper bound on the clusters the fused kernel runs with (sizes its scratch)
 constexpr int kMaxFusedClusters = 148;
 cudaError_t launch_large_fft(int L, const LaunchArgs &a, LargeArgs &g);
