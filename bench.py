@@ -326,7 +326,7 @@ def run_gpu(args) -> None:
             torch.cuda.synchronize()
             ms2 = e0.elapsed_time(e1) / reps
             extra[key] = {"ms": ms2, "hbm_gbs": algo / ms2 / 1e6, "frac_of_measured_peak": algo / ms2 / 1e6 / peak, "note": note}
-        fft.ctx.set_large_mode(2)
+        fft.ctx.set_large_mode(3)
         del xr, yr
         torch.cuda.empty_cache()
         free, _ = torch.cuda.mem_get_info()

@@ -70,12 +70,13 @@ int kofft_cuda_set_tma_staging(kofft_cuda_ctx *ctx, int enable);
  * run (default 128).  Disabled or out of range -> two kernels with an f32 intermediate. */
 int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames);
 /* N > 16384 (rfft above 32768): which of the three implementations of the two-pass split runs.
- *   mode 2 (default): one persistent cooperative kernel; teams of 8 / 16 CTAs overlap pass A of their
- *          next transform with pass B of the current one behind dependency flags, and the intermediate
- *          (4 transforms per team) is pinned in L2, so HBM sees the rows once in and once out.
+ *   mode 3 (default): mode 2 for rfft (where it measured faster, profiles/r02a), mode 0 otherwise.
+ *   mode 2: one persistent cooperative kernel; teams of 8 / 16 CTAs run pass A two transforms ahead
+ *          of pass B behind dependency flags, and the intermediate (4 transforms per team) is pinned
+ *          in L2, so HBM sees the rows once in and once out.
  *   mode 0: two kernels (column pass, row pass) per 256 MB batch chunk.
  *   mode 1: one persistent thread-block-cluster kernel (cluster barrier between the passes).
- * All three are bit-identical; 0 and 1 are kept for comparison (profiles/). */
+ * All are bit-identical. */
 int kofft_cuda_set_large_mode(kofft_cuda_ctx *ctx, int mode);
 /* enable != 0: mode 1 above; 0: back to the current non-cluster mode */
 int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable);

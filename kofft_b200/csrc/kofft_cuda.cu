@@ -92,6 +92,7 @@ struct kofft_cuda_ctx {
     // N > 16384 default: one persistent cooperative kernel, per-team dependency flags, intermediate
     // pinned in L2 (fft_large.cuh LargePipe)
     bool large_pipe = true;
+    bool large_auto = true; // pipelined kernel only where it measured faster (rfft), two kernels otherwise
     unsigned *pipe_flags = nullptr;
     bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
     int istft_run_frames = 128;
@@ -215,7 +216,7 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
                 }
             const size_t row_bytes = n * sizeof(float2);
             void *scratch = nullptr;
-            if (ctx->large_pipe && !ctx->large_fused) {
+            if (ctx->large_pipe && !ctx->large_fused && (!ctx->large_auto || kind == KIND_RFFT)) {
                 const int nkb = L == 15 ? 8 : 16;
                 const int max_teams = kMaxPipeCtasPerSm * ctx->num_sms / nkb;
                 rc = ensure_ws(ctx, 4, size_t(kLargePipeSlots) * max_teams * row_bytes, &scratch);
@@ -336,7 +337,8 @@ int kofft_cuda_create(kofft_cuda_ctx **out, int device)
         if (atoi(mb) > 0) ctx->large_scratch_bytes = size_t(atoi(mb)) << 20;
     // N > 16384 path selection and tuning knobs (see kofft_cuda_set_large_mode)
     if (const char *m = getenv("KOFFT_LARGE_MODE")) {
-        ctx->large_pipe = strcmp(m, "pipe") == 0;
+        ctx->large_auto = strcmp(m, "auto") == 0;
+        ctx->large_pipe = ctx->large_auto || strcmp(m, "pipe") == 0;
         ctx->large_fused = strcmp(m, "cluster") == 0;
     }
 
@@ -412,8 +414,9 @@ int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames)
 }
 int kofft_cuda_set_large_mode(kofft_cuda_ctx *ctx, int mode)
 {
-    if (mode < 0 || mode > 2) return fail_msg(KOFFT_ERR_INVALID_VALUE, "set_large_mode: mode 0..2");
-    ctx->large_pipe = mode == 2;
+    if (mode < 0 || mode > 3) return fail_msg(KOFFT_ERR_INVALID_VALUE, "set_large_mode: mode 0..3");
+    ctx->large_auto = mode == 3;
+    ctx->large_pipe = mode >= 2;
     ctx->large_fused = mode == 1;
     return KOFFT_OK;
 }

@@ -105,10 +105,11 @@ class Context:
     def set_cluster_fusion(self, enable: bool) -> None:
         check(_lib.lib().kofft_cuda_set_cluster_fusion(self.handle, int(bool(enable))))
 
-    LARGE_TWO_KERNEL, LARGE_CLUSTER, LARGE_PIPELINED = 0, 1, 2
+    LARGE_TWO_KERNEL, LARGE_CLUSTER, LARGE_PIPELINED, LARGE_AUTO = 0, 1, 2, 3
 
     def set_large_mode(self, mode: int) -> None:
-        """N > 16384: 2 = persistent pipelined kernel (default), 0 = two kernels per chunk, 1 = cluster kernel."""
+        """N > 16384: 3 = auto (default: pipelined for rfft, two kernels otherwise), 2 = persistent pipelined
+        kernel, 0 = two kernels per chunk, 1 = cluster kernel."""
         check(_lib.lib().kofft_cuda_set_large_mode(self.handle, int(mode)))
 
     def set_rfft_table_fma(self, fma: bool) -> None:

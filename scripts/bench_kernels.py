@@ -97,7 +97,7 @@ def main():
                 fft.ctx.set_large_mode(m)
                 ms, best = timeit(lambda: fft.rfft_batch(x, out=out), 6, 2)
                 report("rfft_65536x16384_" + name, mode, ms, best, nbytes)
-            fft.ctx.set_large_mode(2)
+            fft.ctx.set_large_mode(3)
             del x, out
         if "large" in which:
             for n in (32768, 65536):
@@ -107,7 +107,7 @@ def main():
                     fft.ctx.set_large_mode(m)
                     ms, best = timeit(lambda: fft.fft_batch(x, out=y), 6, 2)
                     report(f"c2c_{n}x{2 ** 28 // n}_" + name, mode, ms, best, 2 * x.numel() * 8)
-                fft.ctx.set_large_mode(2)
+                fft.ctx.set_large_mode(3)
                 del x, y
         fft.close() if hasattr(fft, "close") else None
 

@@ -667,10 +667,10 @@ def test_large_c2c(cuda_fft, cuda_fft_fast, oracle, n):
 
 @pytest.mark.parametrize("n", [32768, 65536])
 def test_large_paths_agree(cuda_fft, oracle, n):
-    """N > 16384 runs as one persistent pipelined kernel (pass A of chunk p overlapped with pass B
-    of chunk p-1, grid barrier between phases) by default; the two-kernel chunked path and the
-    thread-block-cluster kernel are kept for comparison.  All must be bit-identical to the oracle
-    (enough rows that the pipelined kernel runs several phases and every cluster iterates)."""
+    """N > 16384 has three implementations of the two-pass split: the persistent pipelined kernel
+    (teams of CTAs, dependency flags; the default for rfft), two kernels per batch chunk (the default
+    otherwise) and the thread-block-cluster kernel.  All must be bit-identical to the oracle (enough
+    rows that every team / cluster iterates several times and reuses its intermediate slots)."""
     rng = np.random.default_rng(n + 1)
     rows = 150
     x = uniform_c64(rng, (rows, n))
@@ -694,7 +694,7 @@ def test_large_paths_agree(cuda_fft, oracle, n):
             assert np.array_equal(cuda_fft.rfft_batch(xr), rref), tag
             assert np.array_equal(cuda_fft.irfft_batch(rref, 2 * n), bref), tag
     finally:
-        C.set_large_mode(C.LARGE_PIPELINED)
+        C.set_large_mode(C.LARGE_AUTO)
 
 
 def test_large_pipelined_many_transforms_per_team_on_device(cuda_fft, oracle):
@@ -710,6 +710,7 @@ def test_large_pipelined_many_transforms_per_team_on_device(cuda_fft, oracle):
     C = cuda_fft.ctx
     outs, routs = [], []
     try:
+        C.set_large_mode(C.LARGE_PIPELINED)
         for max_ctas in (0, 8, 24, 160):
             C.set_max_ctas(max_ctas)
             y = torch.empty_like(x)
@@ -721,6 +722,7 @@ def test_large_pipelined_many_transforms_per_team_on_device(cuda_fft, oracle):
             torch.cuda.synchronize()
     finally:
         C.set_max_ctas(0)
+        C.set_large_mode(C.LARGE_AUTO)
     pick = [0, 1, 36, 37, 73, 74, 700, rows - 2, rows - 1]
     assert np.array_equal(outs[0][pick].cpu().numpy(), oracle.fft_batch(x[pick].cpu().numpy(), nthreads=8))
     assert np.array_equal(routs[0][pick].cpu().numpy(), oracle.rfft_batch(xr[pick].cpu().numpy(), nthreads=8))
