@@ -291,6 +291,26 @@ def run_gpu(args) -> None:
                                   "frac_of_measured_peak": ALGO_BYTES_PER_TRANSFORM * ROWS_PER_GPU / ms / 1e6 / peak}
         del x, y
         torch.cuda.empty_cache()
+        # f64 twin: C2C N = 4096 x 16384 complex128 rows (1 GiB in + 1 GiB out)
+        fft64 = kofft_b200.CudaFftImpl64(ctx=fft.ctx)
+        dn, db = 4096, 16384
+        xd = torch.view_as_complex((torch.rand((db, dn, 2), generator=g, device=dev, dtype=torch.float64) * 2 - 1).contiguous())
+        yd = torch.empty_like(xd)
+        for _ in range(3):
+            fft64.fft_batch(xd, out=yd)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fft64.fft_batch(xd, out=yd)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        extra["c2c_f64_4096x16384"] = {"ms": ms, "gflops": 5 * dn * 12 * db / ms / 1e6, "hbm_gbs": 32 * dn * db / ms / 1e6,
+                                       "frac_of_measured_peak": 32 * dn * db / ms / 1e6 / peak,
+                                       "note": "f64 twin of the single-CTA engine (fft_f64.cuh), bit-identical to the f64 oracle"}
+        del xd, yd
+        torch.cuda.empty_cache()
         # rfft N = 2^16 x batch 16384 (BASELINE configs[2]): two-pass path with the fused twist
         rn, rb = 65536, 16384
         xr = (torch.rand((rb, rn), generator=g, device=dev) * 2 - 1).contiguous()

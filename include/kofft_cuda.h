@@ -152,6 +152,17 @@ int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nfram
 int kofft_cuda_fft_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, int inverse);
 /* batch() / batch_inverse() on dense rows (src/fft.rs:2156-2175). */
 int kofft_cuda_fft_batch_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, size_t batch, int inverse);
+/* ---- f64 twin: what `impl FftImpl<f64> for CudaFftImpl64` calls (ScalarFftImpl<f64>, src/fft.rs:914-1051
+ * behind the same dispatch :1054-1082 and ifft :1134-1174).  Power-of-two n = 1 .. 8192; elements are
+ * interleaved doubles = #[repr(C)] Complex<f64>.  Non-power-of-two / larger n: negative (not supported). */
+/* FftPlanner::<f64>::get_twiddles(n) (src/fft.rs:391-405 with T = f64): n/2 complex doubles */
+int kofft_cuda_twiddles_host_f64(size_t n, double *out);
+/* batched, device pointers, stream-ordered, in place allowed */
+int kofft_cuda_fft_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch, int inverse,
+                           void *stream);
+/* FftImpl::<f64>::fft / ifft in place on n complex doubles; batch variant on dense rows */
+int kofft_cuda_fft_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, int inverse);
+int kofft_cuda_fft_batch_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, size_t batch, int inverse);
 /* FftImpl::fft_split / ifft_split (src/fft.rs:556-586, 1365-1439). */
 int kofft_cuda_fft_split_host_f32(kofft_cuda_ctx *ctx, float *re, size_t re_len, float *im, size_t im_len,
                                   int inverse);

@@ -40,6 +40,10 @@ SIGNATURES = {
     "kofft_cuda_set_rfft_table_fma": (_i, [_vp, _i]),
     "kofft_cuda_window_host_f32": (_i, [_i, _sz, _f, _vp]),
     "kofft_cuda_fft_c2c_f32": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _vp]),
+    "kofft_cuda_twiddles_host_f64": (_i, [_sz, _vp]),
+    "kofft_cuda_fft_c2c_f64": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _vp]),
+    "kofft_cuda_fft_host_f64": (_i, [_vp, _vp, _sz, _i]),
+    "kofft_cuda_fft_batch_host_f64": (_i, [_vp, _vp, _sz, _sz, _i]),
     "kofft_cuda_fft_strided_f32": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _sz, _sz, _i, _vp]),
     "kofft_cuda_fft2d_f32": (_i, [_vp, _vp, _sz, _sz, _vp]),
     "kofft_cuda_fft3d_f32": (_i, [_vp, _vp, _sz, _sz, _sz, _vp]),

@@ -71,6 +71,10 @@ KHD constexpr int pad(int i) { return i + (i >> 4); }
 struct Tw0 {
     float2 v[16];
 };
+// the same for the f64 twin (fft_f64.cuh)
+struct Tw0D {
+    double2 v[16];
+};
 
 // Where a sub-transform sits inside a larger transform of length 2^Lbig (large-N two-pass
 // path, fft_large.cuh).  The engine's stage s of the sub-transform is stage s + sh1 of the big

@@ -1,0 +1,179 @@
+// fft_f64.cuh -- the f64 twin of the single-CTA engine: ScalarFftImpl<f64>::fft / ifft for
+// power-of-two N = 32 .. 8192 (reference: src/fft.rs:914-1051 fft_split_simd for f64; dispatch
+// :642-706 and :1054-1082; ifft :1134-1174; table :391-405 in f64).
+//
+// Same radix-2 Stockham stage structure, same fused register passes and the same index algebra
+// as the f32 engine (Plan / Pass in fft_engine.cuh are reused for every address), with double2
+// elements, unfused f64 arithmetic and the planner's f64 table.  What differs from the f32
+// kernel is sized by the element: 16 elements per thread are 64 registers, so the later-pass
+// twiddles are read from the (L1/L2-resident) table per pass instead of living in registers,
+// and the exchange goes through ONE padded shared-memory buffer (two barriers per exchange).
+// An HBM-bound kernel like its f32 twin (32 B per point), measured in profiles/.
+#pragma once
+#include "fft_kernels.cuh"
+
+namespace kofft {
+
+template <int L_>
+struct PlanD : Plan<L_, 64> {
+    using Base = Plan<L_, 64>;
+    static_assert(L_ >= 5 && L_ <= 13, "f64 single-CTA engine covers N = 32 .. 8192");
+    static constexpr int SMEM_BYTES = Base::TPC * Base::PADN * 16; // one exchange buffer
+};
+
+// Pass<P, p> supplies the index functions; compute / load_tw are restated for double2
+template <class P, int p>
+struct PassD : Pass<P, p, true> {
+    using B = Pass<P, p, true>;
+    static KHD void load_tw(const double2 *__restrict__ table, int t, double2 *tw /*[NTW]*/)
+    {
+#pragma unroll
+        for (int u = 0; u < B::U; u++) {
+            int k = B::bfly(t, u) >> B::LJ;
+#pragma unroll
+            for (int tl = 0; tl < B::r; tl++)
+#pragma unroll
+                for (int c = 0; c < (1 << tl); c++)
+                    tw[u * (B::R - 1) + (1 << tl) - 1 + c] = table[tw_index<P>(p, tl, k, c)];
+        }
+    }
+    // r layers of radix-2 butterflies; tw: per-thread twiddles (p >= 1) or Tw0D::v (p == 0)
+    static KHD void compute(double2 *x, const double2 *tw)
+    {
+#pragma unroll
+        for (int u = 0; u < B::U; u++) {
+#pragma unroll
+            for (int tl = 0; tl < B::r; tl++) {
+                const int bit = 1 << (B::r - 1 - tl);
+#pragma unroll
+                for (int w0 = 0; w0 < B::R; w0++) {
+                    if (w0 & bit) continue;
+                    const int c_low = bitrev(w0 >> (B::r - tl), tl);
+                    double2 &a = x[u * B::R + w0];
+                    double2 &b = x[u * B::R + (w0 | bit)];
+                    if (p == 0) {
+                        if (c_low == 0)
+                            butterfly_unit_f64(a, b); // T[0] == (1, 0) exactly
+                        else
+                            butterfly_f64(a, b, tw[(1 << tl) - 1 + c_low]);
+                    } else {
+                        butterfly_f64(a, b, tw[u * (B::R - 1) + (1 << tl) - 1 + c_low]);
+                    }
+                }
+            }
+        }
+    }
+};
+
+// FftImpl<f64>::fft / ifft on contiguous rows; ifft = conj -> fft -> conj, * 1/n (src/fft.rs:1163-1172)
+template <bool INV>
+struct IoC2CD {
+    typedef void is_f64;
+    static constexpr bool kEpilogueExchange = false;
+    const double2 *__restrict__ in;
+    double2 *__restrict__ out;
+    long n;
+    double scale; // 1/n, computed on the host as 1.0 / (double)(float)n
+    KHD double2 load(long row, int i) const
+    {
+        double2 v = in[row * n + i];
+        if (INV) v.y = -v.y;
+        return v;
+    }
+    KHD void store(long row, int i, double2 v) const
+    {
+        if (INV) {
+            v.y = -v.y;
+            v.x = dmul(v.x, scale);
+            v.y = dmul(v.y, scale);
+        }
+        out[row * n + i] = v;
+    }
+};
+
+template <int L, class IO>
+struct CtaFftD {
+    using P = PlanD<L>;
+    using P0 = PassD<P, 0>;
+    using P1 = PassD<P, 1>;
+    using P2 = PassD<P, (P::NP > 2 ? 2 : 1)>;
+    using P3 = PassD<P, (P::NP > 3 ? 3 : 1)>;
+
+#if defined(__CUDACC__) || defined(KOFFT_EMU)
+    template <class PA, class PB>
+    static KD void xchg(double2 *buf, int t, double2 *x)
+    {
+#pragma unroll
+        for (int u = 0; u < PA::U; u++)
+#pragma unroll
+            for (int w = 0; w < PA::R; w++) buf[PA::dst_pad(PA::dst_base(t, u), w)] = x[u * PA::R + w];
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PB::U; u++)
+#pragma unroll
+            for (int q = 0; q < PB::R; q++) x[u * PB::R + q] = buf[PB::src_pad(PB::src_base(t, u), q)];
+        __syncthreads(); // one buffer: everyone has read before the next exchange overwrites it
+    }
+
+    static KD void run(const IO &io, const Tw0D &tw0, const double2 *__restrict__ table, long rows, double2 *smem)
+    {
+        const int tid = threadIdx.x;
+        const int slot = tid / P::T;
+        const int t = tid - slot * P::T;
+        double2 *buf = smem + slot * P::PADN;
+        const long groups = (rows + P::TPC - 1) / P::TPC;
+        for (long g = blockIdx.x; g < groups; g += gridDim.x) {
+            const long row = g * P::TPC + slot;
+            const bool active = row < rows;
+            double2 x[EPT];
+            if (active) {
+#pragma unroll
+                for (int u = 0; u < P0::U; u++)
+#pragma unroll
+                    for (int q = 0; q < P0::R; q++) x[u * P0::R + q] = io.load(row, P0::src_index(t, u, q));
+            } else {
+#pragma unroll
+                for (int e = 0; e < EPT; e++) x[e] = make_double2(0.0, 0.0);
+            }
+            P0::compute(x, tw0.v);
+            xchg<P0, P1>(buf, t, x);
+            {
+                double2 tw[P1::NTW];
+                P1::load_tw(table, t, tw);
+                P1::compute(x, tw);
+            }
+            if (P::NP > 2) {
+                xchg<P1, P2>(buf, t, x);
+                double2 tw[P2::NTW];
+                P2::load_tw(table, t, tw);
+                P2::compute(x, tw);
+            }
+            if (P::NP > 3) {
+                xchg<P2, P3>(buf, t, x);
+                double2 tw[P3::NTW];
+                P3::load_tw(table, t, tw);
+                P3::compute(x, tw);
+            }
+            using PL = PassD<P, P::NP - 1>;
+            if (active) {
+#pragma unroll
+                for (int u = 0; u < PL::U; u++)
+#pragma unroll
+                    for (int w = 0; w < PL::R; w++) io.store(row, PL::dst_index(t, u, w), x[u * PL::R + w]);
+            }
+        }
+    }
+#endif
+};
+
+#ifdef __CUDACC__
+template <int L, class IO>
+__global__ void __launch_bounds__((PlanD<L>::CTA)) fft_f64_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0D tw0,
+                                                                 const double2 *__restrict__ table, long rows)
+{
+    extern __shared__ __align__(128) double2 smem_d[];
+    CtaFftD<L, IO>::run(io, tw0, table, rows, smem_d);
+}
+#endif
+
+} // namespace kofft

@@ -34,6 +34,24 @@ void host_fft_twiddles(size_t n, float *out)
     }
 }
 
+// FftPlanner<f64>::get_twiddles, the same lines for T = f64: angle = -from_f32(2.0) * PI / from_f32(n as f32),
+// f64::sin_cos and f64::mul_add (libm sin / cos / fma)
+void host_fft_twiddles_f64(size_t n, double *out)
+{
+    const size_t half = n / 2;
+    const double pi = 3.14159265358979323846; // core::f64::consts::PI
+    const double angle = -static_cast<double>(2.0f) * pi / static_cast<double>(static_cast<float>(n));
+    const double s = sin(angle), c = cos(angle);
+    double re = 1.0, im = 0.0;
+    for (size_t k = 0; k < half; ++k) {
+        out[2 * k] = re;
+        out[2 * k + 1] = im;
+        const double re_old = re;
+        re = fma(re, c, -(im * s));
+        im = fma(im, c, re_old * s);
+    }
+}
+
 // Correctly rounded roots of unity exp(-2 pi i k stride / n), k < count, evaluated in f64.  NOT the
 // reference's table: used only where the reference has no usable output (the multi-GPU
 // transform of BASELINE configs[4]) and for the inter-step twiddles of that path.

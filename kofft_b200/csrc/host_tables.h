@@ -4,6 +4,7 @@
 
 namespace kofft {
 void host_fft_twiddles(size_t n, float *out);                  // n/2 complex
+void host_fft_twiddles_f64(size_t n, double *out);             // n/2 complex, FftPlanner<f64>
 void host_accurate_twiddles(size_t n, size_t stride, size_t count, float *out); // exp(-2 pi i k stride / n)
 void host_bluestein_chirp(size_t n, size_t m, float *chirp, float *b); // n and m complex
 void host_rfft_twiddles(size_t m, float *out, bool fma_mul);   // m complex

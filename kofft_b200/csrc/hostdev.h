@@ -18,6 +18,8 @@
 #define KD inline
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 // phase-by-phase host replay (tests/emu/emu_engine.cpp) is single-threaded
 static inline int atomicMax(int *a, int v) { int old = *a; if (v > old) *a = v; return old; }
 #endif
@@ -172,5 +174,51 @@ KHD float2 cmul(const float2 a, const float2 b)
         return make_float2(sub_rn(mul_rn(a.x, b.x), mul_rn(a.y, b.y)), add_rn(mul_rn(a.x, b.y), mul_rn(a.y, b.x)));
     return make_float2(fma_rn(a.x, b.x, -(a.y * b.y)), fma_rn(a.x, b.y, a.y * b.x));
 }
+
+// ---- f64 twin (ScalarFftImpl<f64>, src/fft.rs:914-1051): the same radix-2 butterfly in double, every
+// product and sum rounded individually (the reference's f64 path has no fused form either).  There is
+// no FAST variant: B200's FP64 pipe is not the limit of this HBM-bound kernel.
+#if defined(__CUDA_ARCH__)
+KD double dmul(double a, double b) { return __dmul_rn(a, b); }
+KD double dadd(double a, double b) { return __dadd_rn(a, b); }
+KD double dsub(double a, double b) { return __dsub_rn(a, b); }
+#else
+KHD double dmul(double a, double b) { return a * b; }
+KHD double dadd(double a, double b) { return a + b; }
+KHD double dsub(double a, double b) { return a - b; }
+#endif
+KHD double2 add2(double2 a, double2 b) { return make_double2(dadd(a.x, b.x), dadd(a.y, b.y)); }
+KHD double2 sub2(double2 a, double2 b) { return make_double2(dsub(a.x, b.x), dsub(a.y, b.y)); }
+// Complex::mul, unfused (src/num.rs:160-165)
+template <bool EXACT>
+KHD double2 cmul(const double2 a, const double2 b)
+{
+    return make_double2(dsub(dmul(a.x, b.x), dmul(a.y, b.y)), dadd(dmul(a.x, b.y), dmul(a.y, b.x)));
+}
+// t = v * w ;  u' = u + t ;  v' = u - t   (src/fft.rs:1019-1030)
+KHD void butterfly_f64(double2 &u, double2 &v, const double2 w)
+{
+    const double2 t = make_double2(dsub(dmul(v.x, w.x), dmul(v.y, w.y)), dadd(dmul(v.x, w.y), dmul(v.y, w.x)));
+    const double2 a = add2(u, t);
+    v = sub2(u, t);
+    u = a;
+}
+KHD void butterfly_unit_f64(double2 &u, double2 &v)
+{
+    const double2 a = add2(u, v);
+    v = sub2(u, v);
+    u = a;
+}
+// element constructors by type, so that the N <= 16 literal kernels are written once for both precisions;
+// a float literal widened to double is exactly the reference's T::from_f32(literal)
+template <class C2> struct Cx;
+template <> struct Cx<float2> {
+    typedef float real;
+    static KHD float2 make(float x, float y) { return make_float2(x, y); }
+};
+template <> struct Cx<double2> {
+    typedef double real;
+    static KHD double2 make(double x, double y) { return make_double2(x, y); }
+};
 
 } // namespace kofft

@@ -80,6 +80,11 @@ struct kofft_cuda_ctx {
     std::map<size_t, Blue> blue_tables; // key n (non-power-of-two): the planner's bluestein_cache
     bool accurate_tables = false; // true: correctly rounded roots of unity instead of the reference's recurrence
     std::map<std::pair<size_t, int>, Table> rfft_tables; // key (m, fma)
+    struct TableD {
+        std::vector<double> host; // interleaved
+        double2 *dev = nullptr;
+    };
+    std::map<size_t, TableD> fft_tables_f64; // FftPlanner<f64>
     // grow-only device workspaces: [0] host-API staging in, [1] staging out, [2] istft time frames,
     // [3] small staging (windows), [4] two-pass (N > 16384) intermediate
     void *ws[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -367,6 +372,8 @@ void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
     for (int i = 0; i < 5; i++)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     if (ctx->pipe_flags) cudaFree(ctx->pipe_flags);
+    for (auto &kv : ctx->fft_tables_f64)
+        if (kv.second.dev) cudaFree(kv.second.dev);
     if (ctx->pipe_ready) {
         for (int i = 0; i < 3; i++) {
             cudaStreamSynchronize(ctx->pipe_stream[i]);
@@ -982,6 +989,89 @@ int kofft_cuda_fft_batch_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, si
 int kofft_cuda_fft_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, int inverse)
 {
     return kofft_cuda_fft_batch_host_f32(ctx, data, n, 1, inverse);
+}
+
+// ---- f64 twin: FftImpl<f64>::fft / ifft (src/fft.rs:914-1051, 1054-1082, 1134-1174) -----------------
+int kofft_cuda_twiddles_host_f64(size_t n, double *out)
+{
+    host_fft_twiddles_f64(n, out);
+    return KOFFT_OK;
+}
+
+int kofft_cuda_fft_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch, int inverse,
+                           void *stream)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT; // src/fft.rs:1055-1058
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
+    if (!is_pow2(n))
+        return fail_msg(-static_cast<int>(cudaErrorNotSupported), "f64: non-power-of-two lengths (Bluestein) are not built");
+    if (n > 8192) return fail_msg(-static_cast<int>(cudaErrorNotSupported), "f64: transform lengths above 8192 are not supported yet");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    if (n == 1) { // identity for fft; ifft: conj, conj, * (1/1) (src/fft.rs:1139-1141 returns early)
+        if (d_in != d_out && batch)
+            CU(cudaMemcpyAsync(d_out, d_in, batch * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        return KOFFT_OK;
+    }
+    if (batch == 0) return KOFFT_OK;
+    LaunchF64Args a;
+    a.in = static_cast<const double2 *>(d_in);
+    a.out = static_cast<double2 *>(d_out);
+    a.n = static_cast<long>(n);
+    a.rows = static_cast<long>(batch);
+    a.inverse = inverse != 0;
+    a.scale = 1.0 / static_cast<double>(static_cast<float>(n)); // T::one() / T::from_f32(n as f32), src/fft.rs:1167
+    a.num_sms = ctx->num_sms;
+    a.max_ctas = ctx->max_ctas;
+    a.stream = s;
+    if (n >= 32) {
+        auto it = ctx->fft_tables_f64.find(n);
+        if (it == ctx->fft_tables_f64.end()) {
+            kofft_cuda_ctx::TableD t;
+            t.host.resize(n);
+            host_fft_twiddles_f64(n, t.host.data());
+            CU(cudaMalloc(&t.dev, (n / 2) * sizeof(double2)));
+            CU(cudaMemcpy(t.dev, t.host.data(), (n / 2) * sizeof(double2), cudaMemcpyHostToDevice));
+            it = ctx->fft_tables_f64.emplace(n, std::move(t)).first;
+        }
+        a.table = it->second.dev;
+        const int L = log2_of(n);
+        const int NP = L <= 8 ? 2 : (L <= 12 ? 3 : 4);
+        const int R0 = L - 4 * (NP - 1);
+        const std::vector<double> &h = it->second.host;
+        for (int tl = 0; tl < R0; tl++)
+            for (int c = 0; c < (1 << tl); c++) {
+                const size_t idx = static_cast<size_t>(c) << (L - 1 - tl);
+                a.tw0.v[(1 << tl) - 1 + c] = make_double2(h[2 * idx], h[2 * idx + 1]);
+            }
+    }
+    (void)cudaGetLastError();
+    cudaError_t e = launch_fft_f64(a);
+    if (e != cudaSuccess) return fail_cuda(e, "f64 kernel launch");
+    ctx->launches += 1;
+    return KOFFT_OK;
+}
+
+int kofft_cuda_fft_batch_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, size_t batch, int inverse)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
+    if (n == 1 || batch == 0) return KOFFT_OK;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = n * batch * sizeof(double2);
+    void *d = nullptr;
+    int rc = host_roundtrip_begin(ctx, data, bytes, 0, &d);
+    if (rc) return rc;
+    rc = kofft_cuda_fft_c2c_f64(ctx, d, d, n, batch, inverse, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_fft_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, int inverse)
+{
+    return kofft_cuda_fft_batch_host_f64(ctx, data, n, 1, inverse);
 }
 
 int kofft_cuda_fft_split_host_f32(kofft_cuda_ctx *ctx, float *re, size_t re_len, float *im, size_t im_len,

@@ -118,6 +118,20 @@ struct BluesteinArgs {
 };
 cudaError_t launch_bluestein_step(int step, const BluesteinArgs &b, bool exact, int num_sms, cudaStream_t s);
 
+// f64 twin (fft_f64.cuh): FftImpl<f64>::fft / ifft, N = 1 .. 8192 (power of two), contiguous rows
+struct LaunchF64Args {
+    const double2 *in = nullptr;
+    double2 *out = nullptr;
+    long n = 0, rows = 0;
+    bool inverse = false;
+    double scale = 1.0;               // 1/n for the inverse
+    const double2 *table = nullptr;   // device-resident FftPlanner<f64> table for n (n >= 32)
+    Tw0D tw0 = {};                    // pass-0 twiddles: v[(2^t - 1) + c] = T[c << (L-1-t)]
+    int num_sms = 148, max_ctas = 0;
+    cudaStream_t stream = nullptr;
+};
+cudaError_t launch_fft_f64(const LaunchF64Args &a);
+
 // fused single-kernel istft (istft_fused.cuh), N = 512 .. 4096
 struct IstftFusedArgs;
 cudaError_t launch_istft_fused(int L, const LaunchArgs &a, const IstftFusedArgs &f);

@@ -32,8 +32,8 @@ class OracleError(Exception):
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "kofft_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("kofft_oracle.c", "kofft_oracle_f64.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
     return _SO
 
@@ -44,8 +44,7 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()
         _lib = C.CDLL(_SO)
         sz, fp, ip = C.c_size_t, C.c_void_p, C.c_int
         sigs = {
@@ -72,6 +71,9 @@ def lib() -> C.CDLL:
             "kofft_oracle_rfft_batch_f32": (ip, [fp, sz, sz, fp, ip, ip]),
             "kofft_oracle_irfft_batch_f32": (ip, [fp, sz, sz, fp, ip, ip]),
             "kofft_oracle_stft_batch_f32": (ip, [fp, sz, sz, fp, sz, sz, fp, sz, ip, ip]),
+            "kofft_oracle_twiddles_f64": (None, [sz, fp]),
+            "kofft_oracle_fft_f64": (ip, [fp, sz, ip]),
+            "kofft_oracle_fft_batch_f64": (ip, [fp, sz, sz, ip, ip]),
         }
         for name, (res, args) in sigs.items():
             f = getattr(_lib, name)
@@ -154,6 +156,36 @@ def fft_batch_inplace(a: np.ndarray, inverse: bool = False, nthreads: int = 1) -
     """Timed-baseline entry: no copies."""
     assert a.dtype == np.complex64 and a.flags.c_contiguous and a.ndim == 2
     _chk(lib().kofft_oracle_fft_batch_f32(_p(a), a.shape[1], a.shape[0], int(inverse), nthreads))
+
+
+# ---- f64 twin (kofft_oracle_f64.c) ----------------------------------------------------------
+def _c128(a) -> np.ndarray:
+    return np.ascontiguousarray(np.array(a, dtype=np.complex128, copy=True))
+
+
+def twiddles_f64(n: int) -> np.ndarray:
+    out = np.empty(max(n // 2, 1), dtype=np.complex128)
+    lib().kofft_oracle_twiddles_f64(n, _p(out))
+    return out[: n // 2]
+
+
+def fft_f64(x, inverse: bool = False) -> np.ndarray:
+    a = _c128(x)
+    _chk(lib().kofft_oracle_fft_f64(_p(a), a.size, int(inverse)))
+    return a
+
+
+def fft_batch_f64(x, inverse: bool = False, nthreads: int = 1) -> np.ndarray:
+    a = _c128(x)
+    assert a.ndim == 2
+    _chk(lib().kofft_oracle_fft_batch_f64(_p(a), a.shape[1], a.shape[0], int(inverse), nthreads))
+    return a
+
+
+def fft_batch_f64_inplace(a: np.ndarray, inverse: bool = False, nthreads: int = 1) -> None:
+    """Timed-baseline entry: no copies."""
+    assert a.dtype == np.complex128 and a.flags.c_contiguous and a.ndim == 2
+    _chk(lib().kofft_oracle_fft_batch_f64(_p(a), a.shape[1], a.shape[0], int(inverse), nthreads))
 
 
 # ---- real -------------------------------------------------------------------------------

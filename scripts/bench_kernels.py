@@ -1,5 +1,5 @@
 """Times the device-pointer kernels of every BASELINE config shape (CUDA events, data resident in HBM).
-   python scripts/bench_kernels.py [which ...]    which: c2c c2c2048 stft stftmag istft rfft large   (default: all)
+   python scripts/bench_kernels.py [which ...]    which: c2c c2c2048 stft stftmag istft rfft large f64   (default: all)
 Prints one JSON line per measurement.  Used to compare tuning variants (KOFFT_CUDA_LIB=...)."""
 import json
 import os
@@ -42,7 +42,7 @@ def report(name, mode, ms, best, nbytes, **kw):
 
 
 def main():
-    which = sys.argv[1:] or ["c2c", "c2c2048", "stft", "stftmag", "istft", "rfft", "large"]
+    which = sys.argv[1:] or ["c2c", "c2c2048", "stft", "stftmag", "istft", "rfft", "large", "f64"]
     g = torch.Generator(device="cuda").manual_seed(0)
     for exact in (True, False):
         mode = "exact" if exact else "fast"
@@ -88,6 +88,15 @@ def main():
                 fft.ctx.set_istft_fusion(True)
                 del out
             del sig, frames
+        if "f64" in which and exact:
+            fft64 = kofft_b200.CudaFftImpl64(ctx=fft.ctx)
+            for n in (256, 1024, 4096, 8192):
+                rows = 2 ** 26 // n
+                x = torch.view_as_complex((torch.rand((rows, n, 2), generator=g, device="cuda", dtype=torch.float64) * 2 - 1).contiguous())
+                y = torch.empty_like(x)
+                ms, best = timeit(lambda: fft64.fft_batch(x, out=y), 10)
+                report(f"c2c_f64_{n}x{rows}", "f64", ms, best, 2 * x.numel() * 16)
+                del x, y
         modes = [("pipelined", 2), ("two_kernel", 0), ("cluster", 1)]
         if "rfft" in which:
             x = (torch.rand((16384, 65536), generator=g, device="cuda") * 2 - 1).contiguous()

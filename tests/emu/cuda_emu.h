@@ -19,6 +19,8 @@
 
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 inline emu_dim3 threadIdx, blockIdx, blockDim, gridDim;

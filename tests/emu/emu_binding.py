@@ -67,7 +67,7 @@ def _stale_k() -> bool:
     t = os.path.getmtime(_SOK)
     deps = [_SRCK, os.path.join(_HERE, "cuda_emu.h")] + [
         os.path.join(_CSRC, f) for f in ("hostdev.h", "async_copy.cuh", "fft_engine.cuh", "fft_kernels.cuh",
-                                         "fft_large.cuh", "istft_fused.cuh", "small_kernels.cuh")]
+                                         "fft_large.cuh", "fft_f64.cuh", "istft_fused.cuh", "small_kernels.cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -104,6 +104,19 @@ class EmuKernels:
                                        self._ptr(out), self._ptr(out2), self._ptr(aux), *[int(v) for v in p],
                                        C.c_float(scale), self._ptr(table), grid_col, grid_row)
         assert rc == 0, rc
+
+
+def _f64(self, n, rows, inp, out, table, inverse=False, grid=2):
+    """CtaFftD::run (n >= 32) / the literal kernels (n <= 16) for complex128 rows."""
+    f = self.lib.kofft_emuk_f64
+    f.restype = C.c_int
+    f.argtypes = [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]
+    scale = 1.0 / float(np.float32(n))
+    rc = f(n, rows, inp.ctypes.data, out.ctypes.data, int(inverse), scale, table.ctypes.data if table is not None else None, grid)
+    assert rc == 0, rc
+
+
+EmuKernels.f64 = _f64
 
 
 def _bind_istft(lib):

@@ -7,7 +7,9 @@
 #include <cstring>
 #include <vector>
 
+#include "../../kofft_b200/csrc/fft_f64.cuh"
 #include "../../kofft_b200/csrc/fft_large.cuh"
+#include "../../kofft_b200/csrc/small_kernels.cuh"
 #include "../../kofft_b200/csrc/istft_fused.cuh"
 
 using namespace kofft;
@@ -283,4 +285,58 @@ API int kofft_emuk_istft_fused(int exact, int L, const void *frames, const float
 #undef CASE_L
     default: return -1;
     }
+}
+
+// ---- f64 twin: the real CtaFftD::run (fft_f64.cuh) and the N <= 16 literal kernels for double2 ----
+template <int L, class IO>
+static int run_f64_L(const IO &io, const double *table, long rows, int grid)
+{
+    using P = PlanD<L>;
+    Tw0D tw0;
+    memset(&tw0, 0, sizeof tw0);
+    for (int tl = 0; tl < P::R0; tl++)
+        for (int c = 0; c < (1 << tl); c++) {
+            long idx = (long)c << (L - 1 - tl);
+            tw0.v[(1 << tl) - 1 + c] = make_double2(table[2 * idx], table[2 * idx + 1]);
+        }
+    const long groups = (rows + P::TPC - 1) / P::TPC;
+    if (grid > groups) grid = (int)groups;
+    if (grid < 1) grid = 1;
+    std::vector<double2> smem(P::SMEM_BYTES / 16 + 16);
+    const double2 *tab = reinterpret_cast<const double2 *>(table);
+    cuda_emu::launch(grid, P::CTA, [&] { CtaFftD<L, IO>::run(io, tw0, tab, rows, smem.data()); });
+    return 0;
+}
+
+template <int N, class IO>
+static int run_f64_small(const IO &io, long rows)
+{
+    for (long r = 0; r < rows; r++) small_transform<N, true, IO>(io, r);
+    return 0;
+}
+
+template <class IO>
+static int run_f64_io(const IO &io, long n, const double *table, long rows, int grid)
+{
+    switch (n) {
+    case 2: return run_f64_small<2>(io, rows);
+    case 4: return run_f64_small<4>(io, rows);
+    case 8: return run_f64_small<8>(io, rows);
+    case 16: return run_f64_small<16>(io, rows);
+#define CASE_L(L) case (1 << L): return run_f64_L<L>(io, table, rows, grid);
+    CASE_L(5) CASE_L(6) CASE_L(7) CASE_L(8) CASE_L(9) CASE_L(10) CASE_L(11) CASE_L(12) CASE_L(13)
+#undef CASE_L
+    default: return -1;
+    }
+}
+
+// in / out: [rows][n] complex doubles; table: FftPlanner<f64> table of n (n >= 32)
+API int kofft_emuk_f64(long n, long rows, const void *in, void *out, int inverse, double scale, const double *table, int grid)
+{
+    if (inverse) {
+        IoC2CD<true> io{(const double2 *)in, (double2 *)out, n, scale};
+        return run_f64_io(io, n, table, rows, grid);
+    }
+    IoC2CD<false> io{(const double2 *)in, (double2 *)out, n, scale};
+    return run_f64_io(io, n, table, rows, grid);
 }

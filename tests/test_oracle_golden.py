@@ -254,3 +254,50 @@ def test_stft_magnitudes_restatement(oracle):  # src/visual/spectrogram.rs:52-76
     fr = oracle.stft(sig, oracle.hann(256), 64, 47)[:, :128]
     assert np.allclose(mags, np.abs(fr), rtol=2e-7, atol=0) or np.max(np.abs(mags - np.abs(fr))) < 1e-5
     assert mx == mags.max() and mx > 0
+
+
+# ---- f64 twin (oracle/kofft_oracle_f64.c) -------------------------------------------------------
+def test_f64_split_matches_aos_and_roundtrip(oracle):
+    """tests/split64.rs:4-17 (fft of (i, 0), n = 16, the split and AoS entries agree -- one code path
+    here) and :36-56 (ifft(fft(x)) == x within 1e-9 for x = (i, -i), n = 16)."""
+    n = 16
+    x = np.arange(n, dtype=np.float64) + 0j
+    y = oracle.fft_f64(x)
+    ref = np.fft.fft(x)
+    assert np.allclose(y, ref, atol=1e-5)  # the n = 16 kernel's constants are f32 literals widened to f64
+    x2 = np.arange(n, dtype=np.float64) * (1 - 1j)
+    back = oracle.fft_f64(oracle.fft_f64(x2), inverse=True)
+    assert np.abs(back - x2).max() < 1e-5
+    # power-of-two sizes on the Stockham path: f64 accuracy
+    for n in (32, 64, 1024, 8192):
+        rng = np.random.default_rng(n)
+        x = rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)
+        y = oracle.fft_f64(x)
+        assert np.linalg.norm(y - np.fft.fft(x)) / np.linalg.norm(y) < 1e-12
+        assert np.linalg.norm(oracle.fft_f64(y, inverse=True) - x) / np.linalg.norm(x) < 1e-12
+
+
+def test_f64_small_kernels_use_f32_literals(oracle):
+    """src/fft_kernels.rs builds its constants with T::from_f32(0.70710677) etc., so the f64 results for
+    n = 8, 16 carry an f32-sized error (~1e-8) while n = 2, 4 and n >= 32 are f64-accurate: the oracle
+    must reproduce that, not 'fix' it."""
+    rng = np.random.default_rng(5)
+    errs = {}
+    for n in (2, 4, 8, 16, 32):
+        x = rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)
+        y = oracle.fft_f64(x)
+        errs[n] = np.linalg.norm(y - np.fft.fft(x)) / np.linalg.norm(y)
+    assert errs[2] < 1e-15 and errs[4] < 1e-15 and errs[32] < 1e-14
+    assert 1e-10 < errs[8] < 1e-6 and 1e-10 < errs[16] < 1e-6
+
+
+def test_f64_twiddle_table_and_errors(oracle):
+    """static / planner table checks of tests/twiddle.rs restated for f64: entry 1 of n = 8 is
+    exp(-2 pi i / 8); the recurrence stays within 1e-12 of the exact roots up to n = 8192."""
+    t = oracle.twiddles_f64(8)
+    assert abs(t[1] - np.exp(-2j * np.pi / 8)) < 1e-15
+    t = oracle.twiddles_f64(8192)
+    assert np.abs(t - np.exp(-2j * np.pi * np.arange(4096) / 8192)).max() < 1e-12
+    with pytest.raises(oracle.OracleError) as e:
+        oracle.fft_f64(np.zeros(0, np.complex128))
+    assert e.value.variant == "EmptyInput"
