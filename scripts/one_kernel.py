@@ -17,6 +17,12 @@ if which == "c2c":
     y = torch.empty_like(x)
     for _ in range(6):
         fft.fft_batch(x, out=y)
+elif which == "f64":
+    x = torch.view_as_complex((torch.rand((16384, 4096, 2), generator=g, device="cuda", dtype=torch.float64) * 2 - 1).contiguous())
+    y = torch.empty_like(x)
+    f64 = kofft_b200.CudaFftImpl64(ctx=fft.ctx)
+    for _ in range(5):
+        f64.fft_batch(x, out=y)
 elif which == "stft":
     ch, length, hop, win = 16, 28_800_000, 512, 2048
     nframes = -(-length // hop)
@@ -38,7 +44,7 @@ elif which == "rfft2":  # two-kernel large-N path (column pass + row pass per L2
     x = (torch.rand((4096, 65536), generator=g, device="cuda") * 2 - 1).contiguous()
     for _ in range(3):
         fft.rfft_batch(x)
-elif which == "rfft":
+elif which == "rfft":  # default large-N path for rfft: the persistent pipelined kernel
     x = (torch.rand((4096, 65536), generator=g, device="cuda") * 2 - 1).contiguous()
     for _ in range(6):
         fft.rfft_batch(x)
