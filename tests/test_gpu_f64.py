@@ -53,7 +53,7 @@ def test_f64_device_pointer_path_and_large_batch(fft64, oracle):
     assert abs(ey / n - ex) / ex < 1e-12  # Parseval
     fft64.fft_batch(y, inverse=True)  # in place
     torch.cuda.synchronize()
-    assert float((y - x).abs().max()) < 1e-12
+    assert float((y - x).abs().max()) < 1e-11  # 12 stages of the f64 recurrence table, there and back
 
 
 def test_f64_reference_checks(fft64, oracle):
