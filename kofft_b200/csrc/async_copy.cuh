@@ -40,6 +40,8 @@ KD void mbar_wait(unsigned long long *bar, unsigned parity)
         "r"(parity)
         : "memory");
 }
+// generic-proxy accesses to shared memory (ld/st) ordered before later async-proxy (TMA) writes to it
+KD void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // one arrival + the number of bytes the bulk copies of this phase will deliver
 KD void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
 {
@@ -176,6 +178,7 @@ static_assert(sizeof(EmuMbar) == 8, "fits the kernels' 8-byte mbarrier word");
 inline EmuMbar &emu_mbar(unsigned long long *bar) { return *reinterpret_cast<EmuMbar *>(bar); }
 inline void mbar_init(unsigned long long *bar, unsigned) { emu_mbar(bar) = EmuMbar{0u, 0}; }
 inline void fence_mbar_init() {}
+inline void fence_proxy_async() {}
 inline void mbar_wait(unsigned long long *bar, unsigned parity)
 {
     while ((emu_mbar(bar).completed & 1u) == parity) cuda_emu::yield_to_scheduler();

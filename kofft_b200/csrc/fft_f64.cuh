@@ -8,6 +8,10 @@
 // kernel is sized by the element: 16 elements per thread are 64 registers, so the later-pass
 // twiddles are read from the (L1/L2-resident) table per pass instead of living in registers,
 // and the exchange goes through ONE padded shared-memory buffer (two barriers per exchange).
+// STAGED: that buffer is idle from the last exchange of a row group until the first exchange of
+// the next one, so the next group's rows are fetched into it by one TMA bulk copy while the last
+// register pass runs and the results are stored -- input prefetch without a byte of extra shared
+// memory (two CTAs of N = 4096 per SM either way).
 // An HBM-bound kernel like its f32 twin (32 B per point), measured in profiles/.
 #pragma once
 #include "fft_kernels.cuh"
@@ -74,12 +78,12 @@ struct IoC2CD {
     double2 *__restrict__ out;
     long n;
     double scale; // 1/n, computed on the host as 1.0 / (double)(float)n
-    KHD double2 load(long row, int i) const
+    KHD double2 from_raw(double2 v) const
     {
-        double2 v = in[row * n + i];
         if (INV) v.y = -v.y;
         return v;
     }
+    KHD double2 load(long row, int i) const { return from_raw(in[row * n + i]); }
     KHD void store(long row, int i, double2 v) const
     {
         if (INV) {
@@ -115,6 +119,7 @@ struct CtaFftD {
         __syncthreads(); // one buffer: everyone has read before the next exchange overwrites it
     }
 
+    template <bool STAGED>
     static KD void run(const IO &io, const Tw0D &tw0, const double2 *__restrict__ table, long rows, double2 *smem)
     {
         const int tid = threadIdx.x;
@@ -122,11 +127,39 @@ struct CtaFftD {
         const int t = tid - slot * P::T;
         double2 *buf = smem + slot * P::PADN;
         const long groups = (rows + P::TPC - 1) / P::TPC;
+        __shared__ __align__(8) unsigned long long mbar;
+        unsigned phase = 0;
+        // the rows of group g are one contiguous byte range; it lands unpadded at the start of the buffer
+        auto stage_issue = [&](long g) {
+            long nr = rows - g * P::TPC;
+            if (nr > P::TPC) nr = P::TPC;
+            const unsigned bytes = (unsigned)(nr * P::N * 16);
+            fence_proxy_async(); // the exchange's generic-proxy traffic precedes the bulk copy's writes
+            mbar_expect_tx(&mbar, bytes);
+            bulk_copy_g2s(smem, io.in + g * P::TPC * io.n, bytes, &mbar);
+        };
+        if constexpr (STAGED) {
+            if (tid == 0) {
+                mbar_init(&mbar, 1);
+                fence_mbar_init();
+            }
+            __syncthreads();
+            if (tid == 0 && (long)blockIdx.x < groups) stage_issue(blockIdx.x);
+        }
         for (long g = blockIdx.x; g < groups; g += gridDim.x) {
             const long row = g * P::TPC + slot;
             const bool active = row < rows;
             double2 x[EPT];
-            if (active) {
+            if constexpr (STAGED) {
+                mbar_wait(&mbar, phase);
+                phase ^= 1;
+#pragma unroll
+                for (int u = 0; u < P0::U; u++)
+#pragma unroll
+                    for (int q = 0; q < P0::R; q++)
+                        x[u * P0::R + q] = io.from_raw(smem[slot * P::N + P0::src_index(t, u, q)]);
+                __syncthreads(); // everyone has read the stage before the exchange overwrites it
+            } else if (active) {
 #pragma unroll
                 for (int u = 0; u < P0::U; u++)
 #pragma unroll
@@ -135,8 +168,14 @@ struct CtaFftD {
 #pragma unroll
                 for (int e = 0; e < EPT; e++) x[e] = make_double2(0.0, 0.0);
             }
+            const long gn = g + gridDim.x;
+            // after the group's LAST exchange the buffer is idle: request the next group's rows
+            auto prefetch = [&](int pass_after) {
+                if (STAGED && pass_after == P::NP - 1 && tid == 0 && gn < groups) stage_issue(gn);
+            };
             P0::compute(x, tw0.v);
             xchg<P0, P1>(buf, t, x);
+            prefetch(1);
             {
                 double2 tw[P1::NTW];
                 P1::load_tw(table, t, tw);
@@ -144,12 +183,14 @@ struct CtaFftD {
             }
             if (P::NP > 2) {
                 xchg<P1, P2>(buf, t, x);
+                prefetch(2);
                 double2 tw[P2::NTW];
                 P2::load_tw(table, t, tw);
                 P2::compute(x, tw);
             }
             if (P::NP > 3) {
                 xchg<P2, P3>(buf, t, x);
+                prefetch(3);
                 double2 tw[P3::NTW];
                 P3::load_tw(table, t, tw);
                 P3::compute(x, tw);
@@ -167,12 +208,12 @@ struct CtaFftD {
 };
 
 #ifdef __CUDACC__
-template <int L, class IO>
+template <int L, class IO, bool STAGED>
 __global__ void __launch_bounds__((PlanD<L>::CTA)) fft_f64_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0D tw0,
                                                                  const double2 *__restrict__ table, long rows)
 {
     extern __shared__ __align__(128) double2 smem_d[];
-    CtaFftD<L, IO>::run(io, tw0, table, rows, smem_d);
+    CtaFftD<L, IO>::template run<STAGED>(io, tw0, table, rows, smem_d);
 }
 #endif
 

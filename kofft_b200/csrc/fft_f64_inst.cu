@@ -7,11 +7,11 @@ namespace kofft {
 
 namespace {
 
-template <int L, class IO>
-cudaError_t launch_f64_L(const IO &io, const LaunchF64Args &a)
+template <int L, class IO, bool STAGED>
+cudaError_t launch_f64_L_v(const IO &io, const LaunchF64Args &a)
 {
     using P = PlanD<L>;
-    auto kern = fft_f64_kernel<L, IO>;
+    auto kern = fft_f64_kernel<L, IO, STAGED>;
     static PerDevice occ_pd;
     int &occ = occ_pd.get();
     if (occ == 0) {
@@ -28,6 +28,14 @@ cudaError_t launch_f64_L(const IO &io, const LaunchF64Args &a)
     if (grid <= 0) return cudaSuccess;
     kern<<<grid, P::CTA, P::SMEM_BYTES, a.stream>>>(io, a.tw0, a.table, a.rows);
     return cudaGetLastError();
+}
+
+// a.staged: TMA input prefetch (the rows are 16-byte aligned, which double2 rows always are; the switch
+// exists for A/B measurements, kofft_cuda_set_tma_staging)
+template <int L, class IO>
+cudaError_t launch_f64_L(const IO &io, const LaunchF64Args &a)
+{
+    return a.staged ? launch_f64_L_v<L, IO, true>(io, a) : launch_f64_L_v<L, IO, false>(io, a);
 }
 
 template <int N, class IO>

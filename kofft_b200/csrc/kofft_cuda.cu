@@ -1023,6 +1023,7 @@ int kofft_cuda_fft_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, s
     a.scale = 1.0 / static_cast<double>(static_cast<float>(n)); // T::one() / T::from_f32(n as f32), src/fft.rs:1167
     a.num_sms = ctx->num_sms;
     a.max_ctas = ctx->max_ctas;
+    a.staged = ctx->use_tma && aligned16(d_in);
     a.stream = s;
     if (n >= 32) {
         auto it = ctx->fft_tables_f64.find(n);

@@ -128,6 +128,7 @@ struct LaunchF64Args {
     const double2 *table = nullptr;   // device-resident FftPlanner<f64> table for n (n >= 32)
     Tw0D tw0 = {};                    // pass-0 twiddles: v[(2^t - 1) + c] = T[c << (L-1-t)]
     int num_sms = 148, max_ctas = 0;
+    bool staged = true;               // TMA prefetch of the next row group into the idle exchange buffer
     cudaStream_t stream = nullptr;
 };
 cudaError_t launch_fft_f64(const LaunchF64Args &a);

@@ -106,8 +106,9 @@ class EmuKernels:
         assert rc == 0, rc
 
 
-def _f64(self, n, rows, inp, out, table, inverse=False, grid=2):
-    """CtaFftD::run (n >= 32) / the literal kernels (n <= 16) for complex128 rows."""
+def _f64(self, n, rows, inp, out, table, inverse=False, grid=2, staged=False):
+    """CtaFftD::run<STAGED> (n >= 32) / the literal kernels (n <= 16) for complex128 rows."""
+    self.lib.kofft_emuk_set_f64_staged(int(staged))
     f = self.lib.kofft_emuk_f64
     f.restype = C.c_int
     f.argtypes = [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]

@@ -288,6 +288,8 @@ API int kofft_emuk_istft_fused(int exact, int L, const void *frames, const float
 }
 
 // ---- f64 twin: the real CtaFftD::run (fft_f64.cuh) and the N <= 16 literal kernels for double2 ----
+static bool g_f64_staged = false;
+API void kofft_emuk_set_f64_staged(int staged) { g_f64_staged = staged != 0; }
 template <int L, class IO>
 static int run_f64_L(const IO &io, const double *table, long rows, int grid)
 {
@@ -302,9 +304,13 @@ static int run_f64_L(const IO &io, const double *table, long rows, int grid)
     const long groups = (rows + P::TPC - 1) / P::TPC;
     if (grid > groups) grid = (int)groups;
     if (grid < 1) grid = 1;
-    std::vector<double2> smem(P::SMEM_BYTES / 16 + 16);
+    std::vector<double2> smem(P::SMEM_BYTES / 16 + 32);
     const double2 *tab = reinterpret_cast<const double2 *>(table);
-    cuda_emu::launch(grid, P::CTA, [&] { CtaFftD<L, IO>::run(io, tw0, tab, rows, smem.data()); });
+    double2 *sm = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
+    if (g_f64_staged)
+        cuda_emu::launch(grid, P::CTA, [&] { CtaFftD<L, IO>::template run<true>(io, tw0, tab, rows, sm); });
+    else
+        cuda_emu::launch(grid, P::CTA, [&] { CtaFftD<L, IO>::template run<false>(io, tw0, tab, rows, sm); });
     return 0;
 }
 

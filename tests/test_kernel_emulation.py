@@ -249,14 +249,15 @@ def test_cta_kernel_body_stft_magnitudes(emuk, oracle, staged):
 @pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 256, 1024, 4096, 8192])
 def test_f64_kernel_body(emuk, oracle, n):
     """CtaFftD::run (fft_f64.cuh; N <= 16: the literal kernels instantiated for double2) against the
-    f64 oracle, bit for bit, forward and inverse, persistent grids smaller than the work."""
+    f64 oracle, bit for bit, forward and inverse, persistent grids smaller than the work; staged = the
+    next row group prefetched into the idle exchange buffer by a TMA bulk copy (ragged last group)."""
     rng = np.random.default_rng(64 + n)
     rows = 7 if n <= 1024 else 3
     x = (rng.uniform(-1, 1, (rows, n)) + 1j * rng.uniform(-1, 1, (rows, n))).astype(np.complex128)
     tab = oracle.twiddles_f64(n) if n >= 32 else None
     for inverse in (False, True):
         ref = oracle.fft_batch_f64(x, inverse=inverse)
-        for grid in (1, 2):
+        for grid, staged in ((1, False), (2, True), (1, True)):
             y = np.zeros_like(x)
-            emuk.f64(n, rows, x, y, tab, inverse=inverse, grid=grid)
-            assert np.array_equal(y, ref), (n, inverse, grid)
+            emuk.f64(n, rows, x, y, tab, inverse=inverse, grid=grid, staged=staged)
+            assert np.array_equal(y, ref), (n, inverse, grid, staged)
