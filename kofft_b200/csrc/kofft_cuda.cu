@@ -1023,7 +1023,9 @@ int kofft_cuda_fft_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, s
     a.scale = 1.0 / static_cast<double>(static_cast<float>(n)); // T::one() / T::from_f32(n as f32), src/fft.rs:1167
     a.num_sms = ctx->num_sms;
     a.max_ctas = ctx->max_ctas;
-    a.staged = ctx->use_tma && aligned16(d_in);
+    // measured (profiles/r02b, r02c): the prefetch pays from N = 1024 up (4096: 65 -> 80 % of the HBM peak);
+    // below, its extra barrier per row group costs more than the latency it hides (256: 93 -> 84 %)
+    a.staged = ctx->use_tma && aligned16(d_in) && n >= 1024;
     a.stream = s;
     if (n >= 32) {
         auto it = ctx->fft_tables_f64.find(n);
