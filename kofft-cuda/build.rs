@@ -29,7 +29,7 @@ fn main() {
             .arg(csrc.join("fft_inst.cu")).arg("-o").arg(&o));
         objs.push(o);
     }
-    for src in ["small_inst.cu", "fft_large_inst.cu", "istft_inst.cu", "ola.cu", "dist_kernels.cu", "bluestein.cu",
+    for src in ["small_inst.cu", "fft_large_inst.cu", "fft_f64_inst.cu", "istft_inst.cu", "ola.cu", "dist_kernels.cu", "bluestein.cu",
                 "kofft_cuda.cu"] {
         let o = out.join(format!("{src}.o"));
         run(Command::new(&nvcc).args(flags).arg("-c").arg(csrc.join(src)).arg("-o").arg(&o));
