@@ -28,9 +28,14 @@ ls -la $OUT | tee -a $OUT/summary.txt
 echo "== ncu stft / rfft" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_cta_kernel -s 3 -c 1 -o $OUT/prof_stft \
     python scripts/one_kernel.py stft > $OUT/ncu_stft.log 2>&1; echo "ncu stft exit $?" | tee -a $OUT/summary.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:large_pipe -s 2 -c 1 -o $OUT/prof_rfft_pipe \
+    python scripts/one_kernel.py rfft > $OUT/ncu_rfft_pipe.log 2>&1; echo "ncu rfft (pipelined, default) exit $?" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:rowpass -s 4 -c 1 -o $OUT/prof_rfft_row \
-    python scripts/one_kernel.py rfft > $OUT/ncu_rfft_row.log 2>&1; echo "ncu rfft row exit $?" | tee -a $OUT/summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:colpass -s 4 -c 1 -o $OUT/prof_rfft_col \
-    python scripts/one_kernel.py rfft > $OUT/ncu_rfft_col.log 2>&1; echo "ncu rfft col exit $?" | tee -a $OUT/summary.txt
+    python scripts/one_kernel.py rfft2 > $OUT/ncu_rfft_row.log 2>&1; echo "ncu rfft row exit $?" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:istft_fused -s 2 -c 1 -o $OUT/prof_istft \
     python scripts/one_kernel.py istft > $OUT/ncu_istft.log 2>&1; echo "ncu istft exit $?" | tee -a $OUT/summary.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_f64_kernel -s 2 -c 1 -o $OUT/prof_f64 \
+    python scripts/one_kernel.py f64 > $OUT/ncu_f64.log 2>&1; echo "ncu f64 exit $?" | tee -a $OUT/summary.txt
+echo "== per-shape kernel timings" | tee -a $OUT/summary.txt
+timeout 900 python scripts/bench_kernels.py > $OUT/kernels.jsonl 2> $OUT/kernels.err; echo "kernels exit $?" | tee -a $OUT/summary.txt
+cat $OUT/kernels.jsonl | tee -a $OUT/summary.txt
