@@ -39,3 +39,15 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_
 echo "== per-shape kernel timings" | tee -a $OUT/summary.txt
 timeout 900 python scripts/bench_kernels.py > $OUT/kernels.jsonl 2> $OUT/kernels.err; echo "kernels exit $?" | tee -a $OUT/summary.txt
 cat $OUT/kernels.jsonl | tee -a $OUT/summary.txt
+# summaries are produced on the box (the raw .ncu-rep files together exceed what gpurun copies back);
+# only the headline capture travels home as a report
+echo "== summaries" | tee -a $OUT/summary.txt
+mkdir -p $OUT/profiles
+python scripts/summarize_ncu.py $TAG prof_c2c c2c --headline >> $OUT/summary.txt 2>&1
+for pair in "prof_stft stft" "prof_rfft_pipe rfft_pipe" "prof_rfft_row rfft_rowpass" "prof_istft istft" "prof_f64 f64"; do
+    set -- $pair
+    [ -f $OUT/$1.ncu-rep ] && python scripts/summarize_ncu.py $TAG $1 $2 >> $OUT/summary.txt 2>&1
+done
+cp profiles/${TAG}_* profiles/headline_kernel_traffic.json $OUT/profiles/ 2>/dev/null
+for r in prof_stft prof_rfft_pipe prof_rfft_row prof_istft prof_f64; do rm -f $OUT/$r.ncu-rep; done
+du -sh $OUT | tee -a $OUT/summary.txt
