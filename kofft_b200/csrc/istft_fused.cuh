@@ -118,6 +118,14 @@ struct IstftFused {
             normtab[r] = nrm;
         }
         __syncthreads();
+        // Steady-state fast path (hop == PRE * CTA, the common 4x overlap with one frame per CTA): every
+        // thread finalises exactly PRE samples per frame, at fixed residues j = t + i CTA, so their
+        // window power lives in registers and every address is "per-frame base + compile-time offset".
+        constexpr int PRE = 4;
+        const bool fast_shape = hop == (long)PRE * CTA;
+        float nreg[PRE];
+#pragma unroll
+        for (int i = 0; i < PRE; i++) nreg[i] = fast_shape ? normtab[t + i * CTA] : 0.0f;
 
         long nfe = (a.out_len + hop - 1) / hop; // frames that can reach the output
         if (nfe > a.nframes) nfe = a.nframes;
@@ -149,12 +157,30 @@ struct IstftFused {
 
             // finalise region fr = [fr*hop, (fr+1)*hop) and recycle its slots for the samples N later.
             // pre: the recycled slots' initial values, loaded by the caller ahead of time (hop <= PRE*CTA)
-            constexpr int PRE = 4;
             const bool use_pre = hop <= (long)PRE * CTA;
             auto recycled_init = [&](long p2) { return (p2 >= own_lo && p2 < own_hi) ? out0[p2] : 0.0f; };
+            // fast(fr): region fr is owned, in steady state and lies wholly inside the owned samples
+            auto fast = [&](long fr) { return fast_shape && fr >= F0 && fr >= halo && (fr + 1) * hop <= own_hi; };
             auto finalize_region = [&](long fr, const float *pre) {
                 const bool steady = fr >= halo; // every residue has its full set of covering frames
-                if (use_pre) {
+                if (fast(fr)) { // warp-uniform
+                    const int rb = (int)((fr * hop) & (N - 1)) + t;
+                    float *o = a.output + c * a.out_len + fr * hop + t;
+                    float *no = a.norm ? a.norm + c * a.out_len + fr * hop + t : nullptr;
+#pragma unroll
+                    for (int i = 0; i < PRE; i++) {
+                        float *r = ring + ((rb + i * CTA) & (N - 1));
+                        float acc = *r;
+                        const float nrm = nreg[i];
+                        if (nrm > 1e-8f)
+                            acc = div_rn(acc, nrm);
+                        else if (a.zero_uncovered)
+                            acc = 0.0f;
+                        o[i * CTA] = acc;
+                        if (no) no[i * CTA] = nrm;
+                        *r = pre[i];
+                    }
+                } else if (use_pre) {
 #pragma unroll
                     for (int i = 0; i < PRE; i++) {
                         const long j = t + (long)i * CTA;
@@ -180,10 +206,20 @@ struct IstftFused {
                 // initial values of the slots recycled in this iteration: loaded now, used after sync A
                 float pre[PRE];
                 if (use_pre && f > fs) {
+                    const long p0 = (f - 1) * hop + N; // first recycled sample
+                    if (fast_shape && p0 >= own_lo && p0 + hop <= own_hi) { // wholly inside the owned samples
+                        const float *src = out0 + p0 + t;
 #pragma unroll
-                    for (int i = 0; i < PRE; i++) {
-                        const long j = t + (long)i * CTA;
-                        pre[i] = j < hop ? recycled_init((f - 1) * hop + j + N) : 0.0f;
+                        for (int i = 0; i < PRE; i++) pre[i] = src[i * CTA];
+                    } else if (fast_shape && p0 >= own_hi) { // wholly beyond them
+#pragma unroll
+                        for (int i = 0; i < PRE; i++) pre[i] = 0.0f;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < PRE; i++) {
+                            const long j = t + (long)i * CTA;
+                            pre[i] = j < hop ? recycled_init((f - 1) * hop + j + N) : 0.0f;
+                        }
                     }
                 }
                 mbar_wait(mbar, phase);
@@ -215,11 +251,11 @@ struct IstftFused {
                 P2::compute(x, tw2);
                 // ordered overlap-add of frame f: ifft = conj, re*scale (src/fft.rs:1163-1172),
                 // then frame.re * window (src/stft.rs:144)
+                const int fb = (int)((f * hop) & (N - 1)) + P2::dst_base(t, 0); // slot of the thread's first sample
 #pragma unroll
                 for (int w = 0; w < P2::R; w++) {
-                    const long p = f * hop + P2::dst_index(t, 0, w);
                     const float v = mul_rn(mul_rn(x[w].x, a.scale), wv[w]);
-                    float *r = ring + (p & (N - 1));
+                    float *r = ring + ((fb + P2::dst_off(w)) & (N - 1));
                     *r = add_rn(*r, v);
                 }
             }

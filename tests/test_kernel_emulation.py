@@ -107,6 +107,7 @@ def test_large_two_pass_rfft_irfft(emuk, oracle, L):
     (10, 1024, 5000, 3000, 2, 2),  # hop == N (no overlap), output longer than the covered range
     (9, 200, 2600, 100, 64, 1),    # hop does not divide N; one run per channel
     (12, 1024, 9000, 0, 2, 2),     # one frame per CTA group (TPC = 1)
+    (11, 512, 30000, 0, 24, 2),    # long runs: the steady-state fast path (register window power, fixed offsets)
 ])
 def test_fused_istft_kernel_body(emuk, oracle, L, hop, length, extra_out, run_frames, grid):
     """IstftFused::run (ifft + window + ordered overlap-add + normalisation in one kernel) is
