@@ -30,6 +30,17 @@
 #pragma once
 #include "fft_kernels.cuh"
 
+// registers per thread the fused kernel is compiled for (168 = three 128-thread CTAs per SM, spill-free;
+// 128 = four CTAs per SM) -- a build-time knob for scripts/build_variants.sh
+#ifndef KOFFT_ISTFT_REGS
+#define KOFFT_ISTFT_REGS 168
+#endif
+// 1: ONE exchange buffer (a second barrier per exchange) -> 43 KB of shared memory per CTA at N = 2048,
+// which together with KOFFT_ISTFT_REGS = 128 puts four CTAs on an SM instead of three
+#ifndef KOFFT_ISTFT_ONEBUF
+#define KOFFT_ISTFT_ONEBUF 0
+#endif
+
 namespace kofft {
 
 struct IstftFusedArgs {
@@ -55,13 +66,19 @@ struct IstftFused {
     static constexpr int N = P::N;
     static constexpr int CTA = P::CTA;
     // CTAs per SM are bounded by shared memory (estimated at hop = N/4); give the registers that leaves
-    static constexpr int SMEM_EST = P::STAGE_BYTES + P::XCHG_BYTES + N * 4 + N + 16;
+    static constexpr bool ONEBUF = KOFFT_ISTFT_ONEBUF != 0;
+    static constexpr int XCHG_BYTES = ONEBUF ? P::PADN * 8 : P::XCHG_BYTES;
+    static constexpr int SMEM_EST = P::STAGE_BYTES + XCHG_BYTES + N * 4 + N + 16;
     static constexpr int BY_SMEM = 227 * 1024 / (SMEM_EST + 1024);
-    static constexpr int BY_REGS = 65536 / (CTA * 168); // the body wants ~168 registers to stay spill-free
+    static constexpr int BY_REGS = 65536 / (CTA * KOFFT_ISTFT_REGS); // registers per thread the body is given
     static constexpr int BY_BOTH = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
+#ifdef KOFFT_ISTFT_FORCE_BLOCKS
+    static constexpr int MIN_BLOCKS = KOFFT_ISTFT_FORCE_BLOCKS;
+#else
     static constexpr int MIN_BLOCKS = BY_BOTH > 8 ? 8 : (BY_BOTH < 1 ? 1 : BY_BOTH);
+#endif
     // [stage N*8][exchange 2*PADN*8][ring N*4][normtab hop*4][mbarrier 8]
-    static constexpr int smem_bytes(long hop) { return P::STAGE_BYTES + P::XCHG_BYTES + N * 4 + (int)((hop * 4 + 15) & ~15L) + 16; }
+    static constexpr int smem_bytes(long hop) { return P::STAGE_BYTES + XCHG_BYTES + N * 4 + (int)((hop * 4 + 15) & ~15L) + 16; }
 
     // generic window-power sum of sample p (frames f_lo..f_hi in increasing order, src/stft.rs:146-148)
     static KD float norm_generic(const IstftFusedArgs &a, long p)
@@ -92,8 +109,8 @@ struct IstftFused {
         unsigned char *stage = reinterpret_cast<unsigned char *>(smem);
         float2 *xch = smem + P::STAGE_BYTES / 8;
         float2 *buf0 = xch;
-        float2 *buf1 = buf0 + P::PADN;
-        float *ring = reinterpret_cast<float *>(xch + P::XCHG_BYTES / 8);
+        float2 *buf1 = ONEBUF ? buf0 : buf0 + P::PADN;
+        float *ring = reinterpret_cast<float *>(xch + XCHG_BYTES / 8);
         float *normtab = ring + N;
         const long hop = a.hop;
         unsigned long long *mbar = reinterpret_cast<unsigned long long *>(normtab + ((hop + 3) & ~3L));
@@ -242,12 +259,14 @@ struct IstftFused {
                 }
                 if (f > fs) finalize_region(f - 1, pre);
                 H::template load_smem<P1>(b, t, x);
+                if (ONEBUF) __syncthreads(); // everyone has read the buffer before the next exchange overwrites it
                 P1::compute(x, tw1);
                 b = par ? buf1 : buf0;
                 par ^= 1;
                 H::template store_smem<P1>(b, t, x);
                 __syncthreads(); // B
                 H::template load_smem<P2>(b, t, x);
+                if (ONEBUF) __syncthreads();
                 P2::compute(x, tw2);
                 // ordered overlap-add of frame f: ifft = conj, re*scale (src/fft.rs:1163-1172),
                 // then frame.re * window (src/stft.rs:144)
