@@ -238,9 +238,15 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
                 g.pipe_max_teams = max_teams;
                 g.flags = ctx->pipe_flags;
                 e = launch_large_fft(L, a, g);
-                if (e != cudaSuccess) return fail_cuda(e, "large-N pipelined kernel launch");
-                ctx->launches += g.launches;
-                return KOFFT_OK;
+                if (e == cudaSuccess) {
+                    ctx->launches += g.launches;
+                    return KOFFT_OK;
+                }
+                // the cooperative launch needs every CTA resident at once; where the device cannot grant
+                // that (e.g. a partitioned GPU) the two-kernel path below computes the same bits
+                if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorLaunchOutOfResources && e != cudaErrorNotSupported)
+                    return fail_cuda(e, "large-N pipelined kernel launch");
+                (void)cudaGetLastError();
             }
             if (ctx->large_fused) {
                 // one persistent launch; each cluster double-buffers one transform in scratch
