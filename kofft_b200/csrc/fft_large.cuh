@@ -421,6 +421,15 @@ struct LargeFused {
 // where 16-byte asynchronous copies put it while the previous pass-B tile ran its epilogue; pass B
 // exchanges through buf1 (between its register passes) and buf0 (transposed bins).
 // ---------------------------------------------------------------------------------------------
+// pipeline depth of the persistent kernel: build-time knobs (scripts/build_variants.sh); the host sizes the
+// intermediate from kLargePipeSlots (launch.h), which follows KOFFT_PIPE_SLOTS
+#ifndef KOFFT_PIPE_AHEAD
+#define KOFFT_PIPE_AHEAD 2
+#endif
+#ifndef KOFFT_PIPE_SLOTS
+#define KOFFT_PIPE_SLOTS (KOFFT_PIPE_AHEAD + 2)
+#endif
+
 template <int LB, bool EXACT, class IO, int EPI, bool STAGED = false>
 struct LargePipe {
     using C = ColPass<EXACT, IO>;
@@ -584,8 +593,9 @@ struct LargePipe {
         }
     }
 
-    static constexpr int AHEAD = 2;         // pass A runs this many transforms ahead of pass B
-    static constexpr int SLOTS = AHEAD + 2; // intermediate slots per team
+    static constexpr int AHEAD = KOFFT_PIPE_AHEAD; // pass A runs this many transforms ahead of pass B
+    static constexpr int SLOTS = KOFFT_PIPE_SLOTS; // intermediate slots per team
+    static_assert(AHEAD >= 1 && SLOTS >= AHEAD + 2, "a slot is rewritten at least one full step after its last reader");
     static constexpr int FLAG_STRIDE = 32;  // unsigned per team: {cntA, cntB} in a 128-byte line of their own
 
     // rows: transforms in the batch; scratch: teams * SLOTS * n complex; flags: teams * FLAG_STRIDE
@@ -671,11 +681,12 @@ struct LargePipe {
         for (long i = 0; i < cnt; i++) {
             const bool nextA = i + AHEAD < cnt;
             if (nextA) {
-                // pass A of transform i+AHEAD into the slot transform i-2 occupied: every member must have
-                // consumed it; the flag load is issued before the tile's first pass
-                if (i >= 2) seenB = peek(doneB(i - 2));
+                // pass A of transform i+AHEAD into the slot transform i+AHEAD-SLOTS occupied: every member
+                // must have consumed that one; the flag load is issued before the tile's first pass
+                const long victim = i + AHEAD - SLOTS;
+                if (victim >= 0) seenB = peek(doneB(victim));
                 tile_a(io, tw0, twA + tA * 16, row_of(i + AHEAD), j0, slot_of_i(i + AHEAD), bufA, buf1, tA, slotA, pol,
-                       [&] { if (i >= 2) await(doneB(i - 2), seenB, goal(i - 2)); });
+                       [&] { if (victim >= 0) await(doneB(victim), seenB, goal(victim)); });
             }
             // pass B of transform i
             if (!have_xb) { // first tile: its inputs could not be requested behind an epilogue

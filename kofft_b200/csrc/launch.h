@@ -83,7 +83,13 @@ struct LargeArgs {
 // upper bound on the CTAs of the pipelined kernel per SM (sizes its scratch); counters per team
 constexpr int kMaxPipeCtasPerSm = 2;
 constexpr int kPipeFlagStride = 32;
-constexpr int kLargePipeSlots = 4; // intermediate transforms per team (LargePipe::SLOTS)
+#ifndef KOFFT_PIPE_AHEAD
+#define KOFFT_PIPE_AHEAD 2
+#endif
+#ifndef KOFFT_PIPE_SLOTS
+#define KOFFT_PIPE_SLOTS (KOFFT_PIPE_AHEAD + 2)
+#endif
+constexpr int kLargePipeSlots = KOFFT_PIPE_SLOTS; // intermediate transforms per team (LargePipe::SLOTS)
 // upper bound on the clusters the fused kernel runs with (sizes its scratch)
 constexpr int kMaxFusedClusters = 148;
 cudaError_t launch_large_fft(int L, const LaunchArgs &a, LargeArgs &g);
