@@ -359,18 +359,28 @@ def run_gpu(args) -> None:
         frames = torch.empty((ch, nframes, win), dtype=torch.complex64, device=dev)
         S.stft_batch(fft, sig, w, hop, nframes, out=frames)
         torch.cuda.synchronize()
-        reps = 3
+        reps = 6
+        stft_sampler = ClockSampler(local)  # the STFT is FP32-bound: its time moves with the SM clock
+        stft_sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
             S.stft_batch(fft, sig, w, hop, nframes, out=frames)
         e1.record()
         torch.cuda.synchronize()
+        stft_clocks = stft_sampler.stop()
         ms = e0.elapsed_time(e1) / reps
         algo = 4 * ch * length + 8 * ch * nframes * win
+        # FP32 floor of the EXACT kernel: 10 lane-operations per butterfly, (N/2) log2 N butterflies per
+        # frame minus the real-input shortcuts (8 %), 128 lanes per SM and clock
+        fma_floor_ms = {mhz: 10 * 0.92 * (win // 2) * 11 * ch * nframes / (128 * 148 * mhz * 1e6) * 1e3
+                        for mhz in (stft_clocks.get("sm_mhz") or 1965, 1965)}
         extra["stft"] = {"workload": f"Hann {win}, hop {hop}, {ch} ch x {length} samples (BASELINE configs[3])",
                          "frames_per_s": ch * nframes / (ms * 1e-3), "ms": ms, "hbm_gbs": algo / ms / 1e6,
-                         "frac_of_measured_peak": algo / ms / 1e6 / peak}
+                         "frac_of_measured_peak": algo / ms / 1e6 / peak, "clocks": stft_clocks,
+                         "fp32_floor_ms_at_measured_clock": fma_floor_ms[stft_clocks.get("sm_mhz") or 1965],
+                         "fp32_floor_ms_at_max_clock": fma_floor_ms[1965],
+                         "hbm_floor_ms": algo / peak / 1e6}
         S.stft_batch(fast, sig, w, hop, nframes, out=frames)
         torch.cuda.synchronize()
         e0.record()

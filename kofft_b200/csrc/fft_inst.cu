@@ -14,7 +14,7 @@ template <int L, bool EXACT, class IO, bool STAGED>
 cudaError_t launch_variant(const IO &io, const LaunchArgs &a)
 {
     using P = Plan<L, IoTraits<IO>::kMinCta>;
-    constexpr int smem = STAGED ? P::SMEM_BYTES_STAGED : P::SMEM_BYTES;
+    constexpr int smem = STAGED ? CtaFft<P, EXACT, IO>::SMEM_STAGED : P::SMEM_BYTES;
     auto kern = fft_cta_kernel<L, EXACT, IO, STAGED>;
     static PerDevice occ_pd; // per instantiation and device
     int &occ = occ_pd.get();

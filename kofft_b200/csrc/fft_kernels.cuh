@@ -387,6 +387,15 @@ struct IoIrfft {
 #ifndef KOFFT_STFT_REAL
 #define KOFFT_STFT_REAL 1
 #endif
+// STFT occupancy knobs (scripts/build_variants.sh): pass-1 twiddles from a small shared-memory table
+// instead of 30 registers, the stage sized for real samples (N*4 instead of N*8 bytes), and the
+// number of CTAs per SM the kernel is compiled for (0 = the generic 512 / CTA)
+#ifndef KOFFT_STFT_TW1_SMEM
+#define KOFFT_STFT_TW1_SMEM 0
+#endif
+#ifndef KOFFT_STFT_BLOCKS
+#define KOFFT_STFT_BLOCKS 0
+#endif
 template <class IO>
 struct IoTraits {
     static constexpr bool kRealInput = false;
@@ -394,6 +403,9 @@ struct IoTraits {
     static constexpr bool kRowPtr = false; // has row_ptr()/from_raw(): rows are plain contiguous float2
     static constexpr bool kFinish = false; // has finish(): called once per thread when the CTA is done
     static constexpr bool kHint = false;   // has load_hint()/store_hint(): L2-hinted row accessors
+    static constexpr bool kTw1Smem = false; // pass-1 twiddles from shared memory (staged kernel only)
+    static constexpr bool kStageHalf = false; // the staged input is real: N*4 bytes per transform
+    static constexpr int kMinBlocks = 0;    // CTAs per SM to compile for (0 = 512 / CTA)
 };
 template <bool INV>
 struct IoTraits<IoC2C<INV>> {
@@ -402,6 +414,9 @@ struct IoTraits<IoC2C<INV>> {
     static constexpr bool kRowPtr = true;
     static constexpr bool kFinish = false;
     static constexpr bool kHint = true;
+    static constexpr bool kTw1Smem = false;
+    static constexpr bool kStageHalf = false;
+    static constexpr int kMinBlocks = 0;
 };
 template <bool EXACT>
 struct IoTraits<IoRfft<EXACT>> {
@@ -410,6 +425,9 @@ struct IoTraits<IoRfft<EXACT>> {
     static constexpr bool kRowPtr = true;
     static constexpr bool kFinish = false;
     static constexpr bool kHint = true;
+    static constexpr bool kTw1Smem = false;
+    static constexpr bool kStageHalf = false;
+    static constexpr int kMinBlocks = 0;
 };
 template <>
 struct IoTraits<IoStft> {
@@ -418,6 +436,9 @@ struct IoTraits<IoStft> {
     static constexpr bool kRowPtr = false;
     static constexpr bool kFinish = false;
     static constexpr bool kHint = false;
+    static constexpr bool kTw1Smem = KOFFT_STFT_TW1_SMEM != 0;
+    static constexpr bool kStageHalf = KOFFT_STFT_TW1_SMEM != 0;
+    static constexpr int kMinBlocks = KOFFT_STFT_BLOCKS;
 };
 template <>
 struct IoTraits<IoStftMag> {
@@ -426,6 +447,9 @@ struct IoTraits<IoStftMag> {
     static constexpr bool kRowPtr = false;
     static constexpr bool kFinish = true;
     static constexpr bool kHint = false;
+    static constexpr bool kTw1Smem = KOFFT_STFT_TW1_SMEM != 0;
+    static constexpr bool kStageHalf = KOFFT_STFT_TW1_SMEM != 0;
+    static constexpr int kMinBlocks = KOFFT_STFT_BLOCKS;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -438,6 +462,13 @@ struct CtaFft {
     using P1 = Pass<P, 1, EXACT>;
     using P2 = Pass<P, (P::NP > 2 ? 2 : 1), EXACT>;
     using P3 = Pass<P, (P::NP > 3 ? 3 : 1), EXACT>;
+
+    // shared-memory layout of the staged kernel: [stage][exchange buffers][pass-1 twiddle table]
+    static constexpr bool TW1S = IoTraits<IO>::kTw1Smem && P::TW_REGS && P::NP == 3;
+    static constexpr int STAGE_B = IoTraits<IO>::kStageHalf ? P::STAGE_BYTES / 2 : P::STAGE_BYTES;
+    static constexpr int NK1 = P::T >> P1::LJ;             // distinct groups k of pass 1 per transform
+    static constexpr int TW1S_BYTES = TW1S ? NK1 * 16 * 8 : 0;
+    static constexpr int SMEM_STAGED = STAGE_B + P::XCHG_BYTES + TW1S_BYTES;
 
     template <class PS>
     static KHD void load_global(const IO &io, long row, int t, float2 *x)
@@ -502,7 +533,7 @@ struct CtaFft {
         const int slot = tid / P::T; // which of the CTA's TPC transforms
         const int t = tid - slot * P::T;
         unsigned char *stage = reinterpret_cast<unsigned char *>(smem);
-        float2 *xch = STAGED ? smem + P::STAGE_BYTES / 8 : smem;
+        float2 *xch = STAGED ? smem + STAGE_B / 8 : smem;
         float2 *buf0 = xch + slot * P::PADN;
         float2 *buf1 = P::NBUF == 2 ? buf0 + P::TPC * P::PADN : buf0;
         int par = 0;
@@ -520,10 +551,24 @@ struct CtaFft {
 
         io.init(t);
         float2 tw1[P1::NTW], tw2[P2::NTW], tw3[P3::NTW];
-        if (P::TW_REGS) {
+        // TW1S: the pass-1 twiddles depend only on the group k = t >> logJ (a handful of values), so they
+        // are read from a [k][16] table in shared memory (broadcast loads) instead of holding 30 registers
+        constexpr bool TW1_FROM_SMEM = STAGED && TW1S;
+        float2 *tw1s = xch + P::XCHG_BYTES / 8;
+        if constexpr (TW1_FROM_SMEM) {
+            for (int i = tid; i < NK1 * 15; i += P::CTA) {
+                const int k = i / 15, e = i - k * 15;
+                int tl = 0;
+                while ((2 << tl) - 1 <= e) tl++;
+                tw1s[k * 16 + e] = table[tw_index<P>(1, tl, k, e + 1 - (1 << tl))];
+            }
+            __syncthreads();
+            if (P::NP > 2) P2::load_tw(table, t, tw2);
+        } else if (P::TW_REGS) {
             P1::load_tw(table, t, tw1);
             if (P::NP > 2) P2::load_tw(table, t, tw2);
         }
+        const float2 *tw1p = TW1_FROM_SMEM ? tw1s + (t >> P1::LJ) * 16 : tw1;
         float aux[EPT]; // per-element constants of pass-0 loads (the STFT window), hoisted out of the row loop
         if constexpr (STAGED && IO::kLoadAux) {
 #pragma unroll
@@ -591,7 +636,7 @@ struct CtaFft {
             load_smem<P1>(b, t, x);
             if (P::NBUF == 1) __syncthreads();
             if (!P::TW_REGS) P1::load_tw(table, t, tw1);
-            P1::compute(x, tw1);
+            P1::compute(x, tw1p);
 
             if (P::NP > 2) {
                 b = par ? buf1 : buf0;
@@ -645,7 +690,9 @@ struct CtaFft {
 #ifdef __CUDACC__
 template <int L, bool EXACT, class IO, bool STAGED>
 __global__ void __launch_bounds__((Plan<L, IoTraits<IO>::kMinCta>::CTA),
-                                  (Plan<L, IoTraits<IO>::kMinCta>::CTA <= 512 ? 512 / Plan<L, IoTraits<IO>::kMinCta>::CTA : 1))
+                                  (IoTraits<IO>::kMinBlocks > 0 && Plan<L, IoTraits<IO>::kMinCta>::CTA == 128
+                                       ? IoTraits<IO>::kMinBlocks
+                                       : (Plan<L, IoTraits<IO>::kMinCta>::CTA <= 512 ? 512 / Plan<L, IoTraits<IO>::kMinCta>::CTA : 1)))
     fft_cta_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0 tw0,
                    const float2 *__restrict__ table, long rows)
 {
