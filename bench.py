@@ -24,6 +24,8 @@ cannot be built in this image) on the same config with all host threads.
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import math
 import os
@@ -486,10 +488,26 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_gpu(args)
+    # stdout carries exactly ONE line, the JSON record: anything a library writes to file descriptor 1 while
+    # the benchmark runs (NCCL prints its version banner there) is sent to stderr instead
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_gpu(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    out = buf.getvalue()
+    if out:
+        sys.stdout.write(out if out.endswith("\n") else out + "\n")
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":
