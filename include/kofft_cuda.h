@@ -206,6 +206,35 @@ int kofft_cuda_istft_host_f32(kofft_cuda_ctx *ctx, const float *frames, size_t n
                               const float *window, size_t win_len, size_t hop, float *output, size_t out_len,
                               float *scratch, size_t scratch_len, int zero_uncovered);
 
+/* ---- streaming STFT / ISTFT with device-resident state -----------------------------------------
+ * Device twins of StftStream (src/stft.rs:160-206) and IstftStream (src/stft.rs:407-520): the
+ * reference's streams are host structs around one fft per frame; here the carried samples / the open
+ * frame tails live on the device and one push handles any number of samples or frames for many
+ * channels with the batched kernels.  What a stream delivers is bit-identical to the offline
+ * stft / istft of the whole signal (the property the reference tests, tests/istft_stream.rs). */
+typedef struct kofft_cuda_stft_stream kofft_cuda_stft_stream;
+typedef struct kofft_cuda_istft_stream kofft_cuda_istft_stream;
+/* window: host pointer, copied.  hop == 0 -> InvalidHopSize (StftStream::new :178-180). */
+int kofft_cuda_stft_stream_create(kofft_cuda_ctx *ctx, size_t channels, const float *window, size_t win_len, size_t hop,
+                                  kofft_cuda_stft_stream **out);
+void kofft_cuda_stft_stream_destroy(kofft_cuda_stft_stream *s);
+/* frames the next push of n samples per channel emits (flush != 0: the remaining, zero-padded ones) */
+size_t kofft_cuda_stft_stream_frames(const kofft_cuda_stft_stream *s, size_t n, int flush);
+/* d_samples [channels][n] (row stride ld floats) -> d_frames [channels][*nframes_out][win_len] complex, dense;
+ * frames_cap = frames per channel d_frames can hold.  flush != 0 after the last samples (next_frame() keeps
+ * returning frames while pos < len, zero-padded past the end, :193-199). */
+int kofft_cuda_stft_stream_push(kofft_cuda_stft_stream *s, const float *d_samples, size_t n, size_t ld, void *d_frames,
+                                size_t frames_cap, size_t *nframes_out, int flush, void *stream);
+/* hop == 0 -> InvalidHopSize (IstftStream::new :434-436). */
+int kofft_cuda_istft_stream_create(kofft_cuda_ctx *ctx, size_t channels, const float *window, size_t win_len, size_t hop,
+                                   kofft_cuda_istft_stream **out);
+void kofft_cuda_istft_stream_destroy(kofft_cuda_istft_stream *s);
+/* push_frame() for k frames per channel at once (:449-495): d_frames [channels][k][win_len] complex, dense ->
+ * the next k * hop normalised samples of every channel in d_out (row stride ld floats).  flush != 0 (:497-519):
+ * the win_len - hop samples after the last frame (0 before the first frame or the second time). */
+int kofft_cuda_istft_stream_push(kofft_cuda_istft_stream *s, const void *d_frames, size_t k, float *d_out, size_t ld,
+                                 size_t *nsamples_out, int flush, void *stream);
+
 /* ---- one C2C transform sharded over the GPUs of a box (BASELINE configs[4]) -------------------
  * No reference equivalent: kofft is single-process CPU code and `FftPlanner::get_twiddles`
  * (src/fft.rs:391-405) degenerates at these sizes (cos(2 pi / 2^30) rounds to 1.0f), so this

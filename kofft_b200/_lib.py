@@ -40,6 +40,13 @@ SIGNATURES = {
     "kofft_cuda_set_rfft_table_fma": (_i, [_vp, _i]),
     "kofft_cuda_window_host_f32": (_i, [_i, _sz, _f, _vp]),
     "kofft_cuda_fft_c2c_f32": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _vp]),
+    "kofft_cuda_stft_stream_create": (_i, [_vp, _sz, _vp, _sz, _sz, C.POINTER(_vp)]),
+    "kofft_cuda_stft_stream_destroy": (None, [_vp]),
+    "kofft_cuda_stft_stream_frames": (_sz, [_vp, _sz, _i]),
+    "kofft_cuda_stft_stream_push": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, C.POINTER(_sz), _i, _vp]),
+    "kofft_cuda_istft_stream_create": (_i, [_vp, _sz, _vp, _sz, _sz, C.POINTER(_vp)]),
+    "kofft_cuda_istft_stream_destroy": (None, [_vp]),
+    "kofft_cuda_istft_stream_push": (_i, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz), _i, _vp]),
     "kofft_cuda_twiddles_host_f64": (_i, [_sz, _vp]),
     "kofft_cuda_fft_c2c_f64": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _vp]),
     "kofft_cuda_fft_host_f64": (_i, [_vp, _vp, _sz, _i]),

@@ -997,6 +997,221 @@ int kofft_cuda_fft_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, int inve
     return kofft_cuda_fft_batch_host_f32(ctx, data, n, 1, inverse);
 }
 
+// ---- streaming STFT / ISTFT with device-resident state (src/stft.rs:160-206, 407-520) ----------------
+// The reference's StftStream / IstftStream are host structs around one fft per frame.  Here the state
+// lives on the device and a push handles any number of samples / frames for many channels with the
+// batched kernels; the frames / samples produced are bit-identical to the offline stft / istft (and
+// therefore to the reference's streams, whose own test asserts stream == offline, tests/istft_stream.rs).
+struct kofft_cuda_stft_stream {
+    kofft_cuda_ctx *ctx = nullptr;
+    size_t channels = 0, win_len = 0, hop = 0;
+    float *d_window = nullptr;
+    float *d_carry = nullptr; // [channels][win_len]: samples received but not yet behind an emitted frame
+    size_t carry_len = 0;     // < win_len between calls
+    float *d_work = nullptr;  // [channels][carry_len + n], grow-only
+    size_t work_floats = 0;
+};
+
+namespace {
+int stft_launch_frames(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, size_t channels, const float *d_window,
+                       size_t win_len, size_t hop, void *d_frames, size_t nframes, cudaStream_t s)
+{
+    // exactly kofft_cuda_stft_f32 without the "enough frames for the whole signal" check: a push emits
+    // only the frames that are complete
+    IoArgs io;
+    io.in = d_signal;
+    io.aux = d_window;
+    io.out = d_frames;
+    io.p0 = static_cast<long>(len);
+    io.p1 = static_cast<long>(nframes);
+    io.p2 = static_cast<long>(hop);
+    const long tpc = tpc_of(win_len, IoTraits<IoStft>::kMinCta);
+    const bool staged = aligned16(d_signal) && len % 4 == 0 && hop % 4 == 0 && nframes % tpc == 0 &&
+                        ((tpc - 1) * static_cast<long>(hop) + static_cast<long>(win_len)) * 4 <= tpc * static_cast<long>(win_len) * 8;
+    return dispatch(ctx, KIND_STFT, io, win_len, channels * nframes, s, staged);
+}
+int stream_grow(float **buf, size_t *have, size_t want)
+{
+    if (*have >= want) return 0;
+    if (*buf) {
+        CU(cudaDeviceSynchronize());
+        CU(cudaFree(*buf));
+        *buf = nullptr;
+        *have = 0;
+    }
+    CU(cudaMalloc(buf, want * sizeof(float)));
+    *have = want;
+    return 0;
+}
+} // namespace
+
+int kofft_cuda_stft_stream_create(kofft_cuda_ctx *ctx, size_t channels, const float *window, size_t win_len, size_t hop,
+                                  kofft_cuda_stft_stream **out)
+{
+    if (!ctx || !out || !window) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null argument");
+    if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE; // StftStream::new, src/stft.rs:178-180
+    int rc = check_fft_len(win_len);
+    if (rc) return rc;
+    if (channels == 0) return fail_msg(KOFFT_ERR_INVALID_VALUE, "channels == 0");
+    CU(cudaSetDevice(ctx->device));
+    auto *s = new kofft_cuda_stft_stream;
+    s->ctx = ctx;
+    s->channels = channels;
+    s->win_len = win_len;
+    s->hop = hop;
+    CU(cudaMalloc(&s->d_window, win_len * sizeof(float)));
+    CU(cudaMemcpy(s->d_window, window, win_len * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&s->d_carry, channels * win_len * sizeof(float)));
+    *out = s;
+    return KOFFT_OK;
+}
+
+void kofft_cuda_stft_stream_destroy(kofft_cuda_stft_stream *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->d_window);
+    cudaFree(s->d_carry);
+    cudaFree(s->d_work);
+    delete s;
+}
+
+// frames a push of n more samples per channel will emit (flush: n = 0, flush != 0)
+size_t kofft_cuda_stft_stream_frames(const kofft_cuda_stft_stream *s, size_t n, int flush)
+{
+    const size_t have = s->carry_len + n;
+    if (flush) return (have + s->hop - 1) / s->hop; // every start position < total length (src/stft.rs:193)
+    return have >= s->win_len ? (have - s->win_len) / s->hop + 1 : 0;
+}
+
+int kofft_cuda_stft_stream_push(kofft_cuda_stft_stream *s, const float *d_samples, size_t n, size_t ld, void *d_frames,
+                                size_t frames_cap, size_t *nframes_out, int flush, void *stream)
+{
+    if (!s) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null stream");
+    kofft_cuda_ctx *ctx = s->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream);
+    if (n && ld < n) return KOFFT_ERR_MISMATCHED_LENGTHS;
+    const size_t have = s->carry_len + n;
+    const size_t k = kofft_cuda_stft_stream_frames(s, n, flush);
+    if (nframes_out) *nframes_out = k;
+    if (k > frames_cap) return KOFFT_ERR_MISMATCHED_LENGTHS;
+    if (have == 0) return KOFFT_OK;
+    int rc = stream_grow(&s->d_work, &s->work_floats, s->channels * have);
+    if (rc) return rc;
+    if (s->carry_len)
+        CU(cudaMemcpy2DAsync(s->d_work, have * 4, s->d_carry, s->win_len * 4, s->carry_len * 4, s->channels,
+                             cudaMemcpyDeviceToDevice, st));
+    if (n)
+        CU(cudaMemcpy2DAsync(s->d_work + s->carry_len, have * 4, d_samples, ld * 4, n * 4, s->channels,
+                             cudaMemcpyDeviceToDevice, st));
+    if (k) {
+        rc = stft_launch_frames(ctx, s->d_work, have, s->channels, s->d_window, s->win_len, s->hop, d_frames, k, st);
+        if (rc) return rc;
+    }
+    const size_t used = k * s->hop;
+    const size_t rest = (flush || used >= have) ? 0 : have - used;
+    if (rest)
+        CU(cudaMemcpy2DAsync(s->d_carry, s->win_len * 4, s->d_work + used, have * 4, rest * 4, s->channels,
+                             cudaMemcpyDeviceToDevice, st));
+    s->carry_len = rest;
+    return KOFFT_OK;
+}
+
+struct kofft_cuda_istft_stream {
+    kofft_cuda_ctx *ctx = nullptr;
+    size_t channels = 0, win_len = 0, hop = 0, halo = 0;
+    float *d_window = nullptr;
+    float *d_hist = nullptr;  // [channels][halo][win_len] complex: the last frames, whose tails are still open
+    size_t hist = 0;          // frames held (<= halo)
+    size_t pushed = 0;
+    bool flushed = false;
+    float *d_workf = nullptr, *d_worko = nullptr; // [channels][hist + k][win_len] complex, [channels][out_len]
+    size_t workf_floats = 0, worko_floats = 0;
+};
+
+int kofft_cuda_istft_stream_create(kofft_cuda_ctx *ctx, size_t channels, const float *window, size_t win_len, size_t hop,
+                                   kofft_cuda_istft_stream **out)
+{
+    if (!ctx || !out || !window) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null argument");
+    if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE; // IstftStream::new, src/stft.rs:434-436
+    int rc = check_fft_len(win_len);
+    if (rc) return rc;
+    if (channels == 0) return fail_msg(KOFFT_ERR_INVALID_VALUE, "channels == 0");
+    CU(cudaSetDevice(ctx->device));
+    auto *s = new kofft_cuda_istft_stream;
+    s->ctx = ctx;
+    s->channels = channels;
+    s->win_len = win_len;
+    s->hop = hop;
+    s->halo = (win_len + hop - 1) / hop - 1; // earlier frames that still reach a frame's first hop samples
+    CU(cudaMalloc(&s->d_window, win_len * sizeof(float)));
+    CU(cudaMemcpy(s->d_window, window, win_len * sizeof(float), cudaMemcpyHostToDevice));
+    if (s->halo) CU(cudaMalloc(&s->d_hist, channels * s->halo * win_len * 2 * sizeof(float)));
+    *out = s;
+    return KOFFT_OK;
+}
+
+void kofft_cuda_istft_stream_destroy(kofft_cuda_istft_stream *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->d_window);
+    cudaFree(s->d_hist);
+    cudaFree(s->d_workf);
+    cudaFree(s->d_worko);
+    delete s;
+}
+
+// push k frames per channel ([channels][k][win_len] complex, dense): writes the next k * hop samples of every
+// channel to d_out (row stride ld floats).  flush != 0 (k = 0): the win_len - hop samples after the last frame.
+int kofft_cuda_istft_stream_push(kofft_cuda_istft_stream *s, const void *d_frames, size_t k, float *d_out, size_t ld,
+                                 size_t *nsamples_out, int flush, void *stream)
+{
+    if (!s) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null stream");
+    kofft_cuda_ctx *ctx = s->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream);
+    const size_t w2 = s->win_len * 2; // floats per frame
+    if (flush) k = 0;
+    const size_t tail = s->win_len > s->hop ? s->win_len - s->hop : 0;
+    // IstftStream::flush (src/stft.rs:497-519): nothing before the first frame, nothing the second time
+    const size_t produce = flush ? ((s->pushed == 0 || s->flushed) ? 0 : tail) : k * s->hop;
+    if (nsamples_out) *nsamples_out = produce;
+    if (produce == 0) return KOFFT_OK;
+    if (ld < produce) return KOFFT_ERR_MISMATCHED_LENGTHS;
+    const size_t h = s->hist, nf = h + k;
+    const size_t out_len = flush ? h * s->hop + tail : nf * s->hop;
+    int rc = stream_grow(&s->d_workf, &s->workf_floats, s->channels * nf * w2);
+    if (rc) return rc;
+    rc = stream_grow(&s->d_worko, &s->worko_floats, s->channels * out_len);
+    if (rc) return rc;
+    if (h)
+        CU(cudaMemcpy2DAsync(s->d_workf, nf * w2 * 4, s->d_hist, s->halo * w2 * 4, h * w2 * 4, s->channels,
+                             cudaMemcpyDeviceToDevice, st));
+    if (k)
+        CU(cudaMemcpy2DAsync(s->d_workf + h * w2, nf * w2 * 4, d_frames, k * w2 * 4, k * w2 * 4, s->channels,
+                             cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync(s->d_worko, 0, s->channels * out_len * sizeof(float), st)); // istft accumulates into its output
+    rc = kofft_cuda_istft_f32(ctx, s->d_workf, nf, s->channels, s->d_window, s->win_len, s->hop, s->d_worko, out_len,
+                              nullptr, 0, st);
+    if (rc) return rc;
+    // the regions of the frames held from earlier pushes were final (and delivered) before; the new ones follow
+    CU(cudaMemcpy2DAsync(d_out, ld * 4, s->d_worko + h * s->hop, out_len * 4, produce * 4, s->channels,
+                         cudaMemcpyDeviceToDevice, st));
+    if (flush) {
+        s->flushed = true;
+        return KOFFT_OK;
+    }
+    const size_t keep = nf < s->halo ? nf : s->halo;
+    if (keep) // (src and dst never overlap: the source is the work buffer)
+        CU(cudaMemcpy2DAsync(s->d_hist, s->halo * w2 * 4, s->d_workf + (nf - keep) * w2, nf * w2 * 4, keep * w2 * 4,
+                             s->channels, cudaMemcpyDeviceToDevice, st));
+    s->hist = keep;
+    s->pushed += k;
+    return KOFFT_OK;
+}
+
 // ---- f64 twin: FftImpl<f64>::fft / ifft (src/fft.rs:914-1051, 1054-1082, 1134-1174) -----------------
 int kofft_cuda_twiddles_host_f64(size_t n, double *out)
 {

@@ -235,3 +235,117 @@ class IstftStream:
         self.norm_buf[o0:o1] = 0.0
         self.out_pos = o1
         return self.buffer[o0:o1]
+
+
+# -- device-resident streams (kofft_cuda_{stft,istft}_stream_*) -------------------------------------
+class DeviceStftStream:
+    """`StftStream` (src/stft.rs:160-206) with its state on the GPU: push any number of new samples for
+    every channel, get the frames that became complete; `flush()` emits the remaining zero-padded ones.
+    The concatenated frames are bit-identical to `stft_batch` of the whole signal."""
+
+    def __init__(self, fft: CudaFftImpl, channels: int, window, hop_size: int):
+        import ctypes as C
+
+        self.fft, self.channels, self.hop = fft, channels, hop_size
+        w = np.ascontiguousarray(window, dtype=np.float32)
+        self.win_len = w.size
+        self._lib = _lib.lib()
+        self._h = C.c_void_p()
+        check(self._lib.kofft_cuda_stft_stream_create(fft.ctx.handle, channels, w.ctypes.data, w.size, hop_size,
+                                                      C.byref(self._h)))
+
+    def _push(self, samples, flush: bool):
+        import ctypes as C
+
+        n = 0 if samples is None else samples.shape[1]
+        if samples is not None:
+            if (not samples.is_cuda or samples.dtype != torch.float32 or samples.dim() != 2
+                    or samples.shape[0] != self.channels or samples.stride(1) != 1):
+                raise TypeError("expected a CUDA float32 tensor [channels, n] with unit inner stride")
+        k = int(self._lib.kofft_cuda_stft_stream_frames(self._h, n, int(flush)))
+        dev = samples.device if samples is not None else torch.device("cuda", self.fft.ctx.device)
+        frames = torch.empty((self.channels, k, self.win_len), dtype=torch.complex64, device=dev)
+        got = C.c_size_t(0)
+        stream = _stream_of(frames)
+        check(self._lib.kofft_cuda_stft_stream_push(self._h, samples.data_ptr() if n else None, n,
+                                                    samples.stride(0) if n else 0, frames.data_ptr(), k, C.byref(got),
+                                                    int(flush), stream))
+        assert got.value == k
+        return frames
+
+    def push(self, samples):
+        """samples: CUDA float32 [channels, n] -> complex64 [channels, k, win_len] (k may be 0)."""
+        return self._push(samples, False)
+
+    def flush(self):
+        return self._push(None, True)
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.kofft_cuda_stft_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceIstftStream:
+    """`IstftStream` (src/stft.rs:407-520) with its state on the GPU: push k frames per channel, get the
+    next k * hop normalised samples; `flush()` returns the win_len - hop samples after the last frame.
+    Bit-identical to `istft_batch` of all frames (the reference asserts stream == offline)."""
+
+    def __init__(self, fft: CudaFftImpl, channels: int, window, hop: int):
+        import ctypes as C
+
+        self.fft, self.channels, self.hop = fft, channels, hop
+        w = np.ascontiguousarray(window, dtype=np.float32)
+        self.win_len = w.size
+        self._lib = _lib.lib()
+        self._h = C.c_void_p()
+        check(self._lib.kofft_cuda_istft_stream_create(fft.ctx.handle, channels, w.ctypes.data, w.size, hop,
+                                                       C.byref(self._h)))
+        self._pushed = 0
+        self._flushed = False
+
+    def push_frames(self, frames):
+        """frames: CUDA complex64 [channels, k, win_len] contiguous -> float32 [channels, k * hop]."""
+        import ctypes as C
+
+        if (not frames.is_cuda or frames.dtype != torch.complex64 or frames.dim() != 3 or not frames.is_contiguous()
+                or frames.shape[0] != self.channels):
+            raise TypeError("expected a contiguous CUDA complex64 tensor [channels, k, win_len]")
+        if frames.shape[2] != self.win_len:
+            raise MismatchedLengths()  # push_frame, src/stft.rs:450-452
+        k = frames.shape[1]
+        out = torch.empty((self.channels, k * self.hop), dtype=torch.float32, device=frames.device)
+        got = C.c_size_t(0)
+        check(self._lib.kofft_cuda_istft_stream_push(self._h, frames.data_ptr(), k, out.data_ptr(), max(k * self.hop, 1),
+                                                     C.byref(got), 0, _stream_of(frames)))
+        self._pushed += k
+        return out
+
+    def flush(self):
+        import ctypes as C
+
+        n = max(self.win_len - self.hop, 0) if (self._pushed and not self._flushed) else 0
+        out = torch.empty((self.channels, n), dtype=torch.float32, device=torch.device("cuda", self.fft.ctx.device))
+        got = C.c_size_t(0)
+        check(self._lib.kofft_cuda_istft_stream_push(self._h, None, 0, out.data_ptr() if n else None, max(n, 1),
+                                                     C.byref(got), 1, _stream_of(out)))
+        assert got.value == n
+        self._flushed = True
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.kofft_cuda_istft_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass

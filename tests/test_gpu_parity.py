@@ -906,3 +906,67 @@ def test_ndfft_2d_3d(cuda_fft, oracle):
     assert np.allclose(w3, np.fft.fftn(v.astype(np.complex128)), atol=1e-2)
     with pytest.raises(k.MismatchedLengths):
         ndfft.fft3d_inplace(v.copy().reshape(-1), depth, rows, cols, cuda_fft, (np.zeros(depth), np.zeros(rows), np.zeros(cols + 1)))
+
+
+@pytest.mark.parametrize("win_len,hop,chunks", [
+    (2048, 512, [100, 5000, 1948, 512, 511, 20000, 3]),   # BASELINE window / hop, ragged pushes
+    (1024, 300, [4096, 1, 1023, 7000]),                   # hop does not divide the window
+    (512, 512, [512, 1000, 24]),                          # no overlap
+])
+def test_device_streams_match_offline(cuda_fft, oracle, win_len, hop, chunks):
+    """Device twins of StftStream / IstftStream (src/stft.rs:160-206, 407-520; tests/istft_stream.rs):
+    whatever the push sizes, the frames equal the offline stft and the samples equal the offline istft
+    (and the oracle's restatement of IstftStream), bit for bit, for several channels at once."""
+    import torch
+
+    from kofft_b200 import stft as S
+
+    ch = 3
+    total = sum(chunks)
+    rng = np.random.default_rng(win_len + hop)
+    sig = rng.uniform(-1, 1, (ch, total)).astype(np.float32)
+    w = oracle.hann(win_len)
+    nframes = -(-total // hop)
+    ref_frames = oracle.stft_batch(sig, w, hop, nframes)
+    d_sig = torch.from_numpy(sig).cuda()
+    st = S.DeviceStftStream(cuda_fft, ch, w, hop)
+    got, pos = [], 0
+    for n in chunks:
+        got.append(st.push(d_sig[:, pos:pos + n]))  # a strided view: rows are `total` apart
+        pos += n
+    got.append(st.flush())
+    assert st.flush().shape[1] == 0
+    frames = torch.cat(got, dim=1)
+    torch.cuda.synchronize()
+    assert frames.shape[1] == nframes
+    assert np.array_equal(frames.cpu().numpy(), ref_frames)
+
+    ist = S.DeviceIstftStream(cuda_fft, ch, w, hop)
+    assert ist.flush().shape[1] == 0  # nothing before the first frame (src/stft.rs:498-500)
+    ist = S.DeviceIstftStream(cuda_fft, ch, w, hop)
+    outs, f0 = [], 0
+    for k in (1, 2, 7, 1, 30, 5, 10 ** 9):
+        k = min(k, nframes - f0)
+        if k <= 0:
+            break
+        outs.append(ist.push_frames(frames[:, f0:f0 + k].contiguous()))
+        f0 += k
+    outs.append(ist.flush())
+    assert ist.flush().shape[1] == 0
+    rec = torch.cat(outs, dim=1).cpu().numpy()
+    out_len = nframes * hop + max(win_len - hop, 0)
+    assert rec.shape[1] == out_len
+    for c in range(ch):
+        want = oracle.istft(ref_frames[c], w, hop, np.zeros(out_len, np.float32))
+        assert np.array_equal(rec[c], want), c
+        assert np.array_equal(rec[c], oracle.istft_stream(ref_frames[c], w, hop)[:out_len])
+
+
+def test_device_stream_errors(cuda_fft, oracle):
+    from kofft_b200 import stft as S
+    from kofft_b200.errors import InvalidHopSize
+
+    with pytest.raises(InvalidHopSize):
+        S.DeviceStftStream(cuda_fft, 1, oracle.hann(256), 0)
+    with pytest.raises(InvalidHopSize):
+        S.DeviceIstftStream(cuda_fft, 1, oracle.hann(256), 0)
