@@ -144,40 +144,52 @@ struct IoStft {
     static constexpr bool kStageable = true;
     static constexpr bool kLoadAux = true;
     KHD float load_aux(int i) const { return KOFFT_LDG(window + i); } // window value, kept in a register
-    // Group state: channel and first frame of the CTA's current group, advanced without
-    // divisions as the persistent CTA strides over the groups (two divisions per CTA lifetime).
-    long cur_c = 0, cur_f0 = 0, adv_c = 0, adv_f = 0;
+    // Group state of the staged kernel, advanced by ADDITIONS only as the persistent CTA strides over the
+    // groups (two divisions and a few products per CTA lifetime; the per-group bookkeeping used to be
+    // ~100 instructions of 64-bit multiplies and compares, a sixth of the issue slots of a frame):
+    //   cur_f0  first frame of the group within its channel
+    //   sig_off element offset of the group's first sample in `signal`  (= c*len + f0*hop)
+    //   rem     samples from there to the end of the channel            (= len - f0*hop, may be <= 0)
+    long cur_f0 = 0, adv_f = 0;
+    long sig_off = 0, rem = 0, adv_off = 0, adv_rem = 0, wrap_off = 0, wrap_rem = 0;
     KHD void group_init(long g0, long step, int tpc)
     {
-        long r0 = g0 * tpc;
-        cur_c = r0 / nframes;
-        cur_f0 = r0 - cur_c * nframes;
-        long a = step * tpc;
-        adv_c = a / nframes;
+        const long r0 = g0 * tpc;
+        const long c0 = r0 / nframes;
+        cur_f0 = r0 - c0 * nframes;
+        const long a = step * tpc;
+        const long adv_c = a / nframes;
         adv_f = a - adv_c * nframes;
+        sig_off = c0 * len + cur_f0 * hop;
+        rem = len - cur_f0 * hop;
+        adv_off = adv_c * len + adv_f * hop;
+        adv_rem = adv_f * hop;
+        wrap_off = len - nframes * hop; // passing the end of a channel: one more channel, nframes fewer frames
+        wrap_rem = nframes * hop;
     }
     KHD void group_next(int)
     {
-        cur_c += adv_c;
         cur_f0 += adv_f;
+        sig_off += adv_off;
+        rem -= adv_rem;
         if (cur_f0 >= nframes) {
             cur_f0 -= nframes;
-            cur_c++;
+            sig_off += wrap_off;
+            rem += wrap_rem;
         }
     }
     KHD unsigned stage_bytes(int tpc, long) const
     {
-        long avail = len - cur_f0 * hop;
-        long want = (long)(tpc - 1) * hop + n;
-        if (avail <= 0) return 0u;
-        return (unsigned)((avail < want ? avail : want) * 4);
+        const long want = (long)(tpc - 1) * hop + n;
+        if (rem <= 0) return 0u;
+        return (unsigned)((rem < want ? rem : want) * 4);
     }
-    KHD const void *stage_src(int) const { return signal + cur_c * len + cur_f0 * hop; }
+    KHD const void *stage_src(int) const { return signal + sig_off; }
     // samples of this slot's frame that lie inside the signal, clamped to [0, n]
     KHD int row_begin(int slot) const
     {
-        long rem = len - (cur_f0 + slot) * hop;
-        return rem <= 0 ? 0 : (rem >= n ? (int)n : (int)rem);
+        const long r = rem - (long)slot * hop;
+        return r <= 0 ? 0 : (r >= n ? (int)n : (int)r);
     }
     // FULL: the whole frame lies inside the signal (rem == n), no per-element bound check
     template <bool FULL>
@@ -530,7 +542,7 @@ struct CtaFft {
     static KD void run(IO io, const Tw0 &tw0, const float2 *__restrict__ table, long rows, float2 *smem)
     {
         const int tid = threadIdx.x;
-        const int slot = tid / P::T; // which of the CTA's TPC transforms
+        const int slot = P::TPC == 1 ? 0 : tid / P::T; // which of the CTA's TPC transforms
         const int t = tid - slot * P::T;
         unsigned char *stage = reinterpret_cast<unsigned char *>(smem);
         float2 *xch = STAGED ? smem + STAGE_B / 8 : smem;
