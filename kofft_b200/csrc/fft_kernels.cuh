@@ -542,7 +542,10 @@ struct CtaFft {
     static KD void run(IO io, const Tw0 &tw0, const float2 *__restrict__ table, long rows, float2 *smem)
     {
         const int tid = threadIdx.x;
-        const int slot = P::TPC == 1 ? 0 : tid / P::T; // which of the CTA's TPC transforms
+        // which of the CTA's TPC transforms.  A compile-time 0 for the one-frame STFT CTAs (it removes a
+        // per-thread 64-bit multiply from the staged load); the other kernels keep the division: with the
+        // constant the C2C N = 4096 kernel measured 1.5 % slower (different schedule, profiles/r02i)
+        const int slot = (P::TPC == 1 && IoTraits<IO>::kMinCta < 256) ? 0 : tid / P::T;
         const int t = tid - slot * P::T;
         unsigned char *stage = reinterpret_cast<unsigned char *>(smem);
         float2 *xch = STAGED ? smem + STAGE_B / 8 : smem;
