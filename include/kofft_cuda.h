@@ -160,9 +160,22 @@ int kofft_cuda_twiddles_host_f64(size_t n, double *out);
 /* batched, device pointers, stream-ordered, in place allowed */
 int kofft_cuda_fft_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch, int inverse,
                            void *stream);
+/* strided rows of interleaved complex doubles / split (SoA) rows, device pointers, as the f32 twins */
+int kofft_cuda_fft_strided_f64(kofft_cuda_ctx *ctx, const void *d_in, size_t in_stride, size_t in_dist, void *d_out,
+                               size_t out_stride, size_t out_dist, size_t n, size_t batch, int inverse, void *stream);
+int kofft_cuda_fft_split_f64(kofft_cuda_ctx *ctx, const double *d_in_re, const double *d_in_im, double *d_out_re,
+                             double *d_out_im, size_t n, size_t batch, int inverse, void *stream);
 /* FftImpl::<f64>::fft / ifft in place on n complex doubles; batch variant on dense rows */
 int kofft_cuda_fft_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, int inverse);
 int kofft_cuda_fft_batch_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, size_t batch, int inverse);
+/* FftImpl::<f64>::fft_split / ifft_split (src/fft.rs:1365-1439; KAT tests/split64.rs),
+ * fft_strided / ifft_strided (:1175-1259), fft_out_of_place_strided / ifft_... (:1260-1336) */
+int kofft_cuda_fft_split_host_f64(kofft_cuda_ctx *ctx, double *re, size_t re_len, double *im, size_t im_len, int inverse);
+int kofft_cuda_fft_strided_host_f64(kofft_cuda_ctx *ctx, double *input, size_t input_len, size_t stride, size_t n,
+                                    int inverse);
+int kofft_cuda_fft_out_of_place_strided_host_f64(kofft_cuda_ctx *ctx, const double *input, size_t input_len,
+                                                 size_t in_stride, double *output, size_t output_len, size_t out_stride,
+                                                 int inverse);
 /* FftImpl::fft_split / ifft_split (src/fft.rs:556-586, 1365-1439). */
 int kofft_cuda_fft_split_host_f32(kofft_cuda_ctx *ctx, float *re, size_t re_len, float *im, size_t im_len,
                                   int inverse);

@@ -49,6 +49,11 @@ SIGNATURES = {
     "kofft_cuda_istft_stream_push": (_i, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz), _i, _vp]),
     "kofft_cuda_twiddles_host_f64": (_i, [_sz, _vp]),
     "kofft_cuda_fft_c2c_f64": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _vp]),
+    "kofft_cuda_fft_strided_f64": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _sz, _sz, _i, _vp]),
+    "kofft_cuda_fft_split_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _i, _vp]),
+    "kofft_cuda_fft_split_host_f64": (_i, [_vp, _vp, _sz, _vp, _sz, _i]),
+    "kofft_cuda_fft_strided_host_f64": (_i, [_vp, _vp, _sz, _sz, _sz, _i]),
+    "kofft_cuda_fft_out_of_place_strided_host_f64": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i]),
     "kofft_cuda_fft_host_f64": (_i, [_vp, _vp, _sz, _i]),
     "kofft_cuda_fft_batch_host_f64": (_i, [_vp, _vp, _sz, _sz, _i]),
     "kofft_cuda_fft_strided_f32": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _sz, _sz, _i, _vp]),

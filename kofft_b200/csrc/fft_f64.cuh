@@ -74,6 +74,7 @@ template <bool INV>
 struct IoC2CD {
     typedef void is_f64;
     static constexpr bool kEpilogueExchange = false;
+    static constexpr bool kStageable = true; // dense 16-byte aligned rows: TMA prefetch possible
     const double2 *__restrict__ in;
     double2 *__restrict__ out;
     long n;
@@ -92,6 +93,38 @@ struct IoC2CD {
             v.y = dmul(v.y, scale);
         }
         out[row * n + i] = v;
+    }
+};
+
+// strided and split (SoA) rows, FftImpl<f64>::fft_strided / fft_out_of_place_strided / fft_split / ifft_split
+// (src/fft.rs:1175-1336, 556-586 -> 1365-1439): element e of row r lives at re[r*row_stride + e*elem_stride]
+// (strides in doubles); interleaved data passes im = re + 1 and elem_stride = 2 * stride
+template <bool INV>
+struct IoGenericD {
+    typedef void is_f64;
+    static constexpr bool kEpilogueExchange = false;
+    static constexpr bool kStageable = false;
+    const double *__restrict__ in_re;
+    const double *__restrict__ in_im;
+    double *__restrict__ out_re;
+    double *__restrict__ out_im;
+    long in_es, in_rs, out_es, out_rs;
+    double scale;
+    KHD double2 load(long row, int i) const
+    {
+        const long o = row * in_rs + (long)i * in_es;
+        return make_double2(in_re[o], INV ? -in_im[o] : in_im[o]);
+    }
+    KHD void store(long row, int i, double2 v) const
+    {
+        if (INV) {
+            v.y = -v.y;
+            v.x = dmul(v.x, scale);
+            v.y = dmul(v.y, scale);
+        }
+        const long o = row * out_rs + (long)i * out_es;
+        out_re[o] = v.x;
+        out_im[o] = v.y;
     }
 };
 
@@ -131,12 +164,14 @@ struct CtaFftD {
         unsigned phase = 0;
         // the rows of group g are one contiguous byte range; it lands unpadded at the start of the buffer
         auto stage_issue = [&](long g) {
-            long nr = rows - g * P::TPC;
-            if (nr > P::TPC) nr = P::TPC;
-            const unsigned bytes = (unsigned)(nr * P::N * 16);
-            fence_proxy_async(); // the exchange's generic-proxy traffic precedes the bulk copy's writes
-            mbar_expect_tx(&mbar, bytes);
-            bulk_copy_g2s(smem, io.in + g * P::TPC * io.n, bytes, &mbar);
+            if constexpr (STAGED) {
+                long nr = rows - g * P::TPC;
+                if (nr > P::TPC) nr = P::TPC;
+                const unsigned bytes = (unsigned)(nr * P::N * 16);
+                fence_proxy_async(); // the exchange's generic-proxy traffic precedes the bulk copy's writes
+                mbar_expect_tx(&mbar, bytes);
+                bulk_copy_g2s(smem, io.in + g * P::TPC * io.n, bytes, &mbar);
+            }
         };
         if constexpr (STAGED) {
             if (tid == 0) {

@@ -35,7 +35,10 @@ cudaError_t launch_f64_L_v(const IO &io, const LaunchF64Args &a)
 template <int L, class IO>
 cudaError_t launch_f64_L(const IO &io, const LaunchF64Args &a)
 {
-    return a.staged ? launch_f64_L_v<L, IO, true>(io, a) : launch_f64_L_v<L, IO, false>(io, a);
+    if constexpr (IO::kStageable) {
+        if (a.staged) return launch_f64_L_v<L, IO, true>(io, a);
+    }
+    return launch_f64_L_v<L, IO, false>(io, a);
 }
 
 template <int N, class IO>
@@ -76,6 +79,14 @@ cudaError_t launch_f64_io(const IO &io, const LaunchF64Args &a)
 
 cudaError_t launch_fft_f64(const LaunchF64Args &a)
 {
+    if (a.generic) { // strided / split rows
+        if (a.inverse) {
+            IoGenericD<true> io{a.in_re, a.in_im, a.out_re, a.out_im, a.in_es, a.in_rs, a.out_es, a.out_rs, a.scale};
+            return launch_f64_io(io, a);
+        }
+        IoGenericD<false> io{a.in_re, a.in_im, a.out_re, a.out_im, a.in_es, a.in_rs, a.out_es, a.out_rs, a.scale};
+        return launch_f64_io(io, a);
+    }
     if (a.inverse) {
         IoC2CD<true> io{a.in, a.out, a.n, a.scale};
         return launch_f64_io(io, a);

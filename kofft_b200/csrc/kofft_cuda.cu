@@ -1219,34 +1219,28 @@ int kofft_cuda_twiddles_host_f64(size_t n, double *out)
     return KOFFT_OK;
 }
 
-int kofft_cuda_fft_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch, int inverse,
-                           void *stream)
+namespace {
+// shared by the dense, strided and split f64 entry points: length checks, the device-resident
+// FftPlanner<f64> table, pass-0 twiddles, launch.  a: addressing filled in by the caller.
+int f64_check_len(kofft_cuda_ctx *ctx, size_t n)
 {
     if (n == 0) return KOFFT_ERR_EMPTY_INPUT; // src/fft.rs:1055-1058
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     if (!is_pow2(n))
         return fail_msg(-static_cast<int>(cudaErrorNotSupported), "f64: non-power-of-two lengths (Bluestein) are not built");
     if (n > 8192) return fail_msg(-static_cast<int>(cudaErrorNotSupported), "f64: transform lengths above 8192 are not supported yet");
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t s = pick_stream(ctx, stream);
-    if (n == 1) { // identity for fft; ifft: conj, conj, * (1/1) (src/fft.rs:1139-1141 returns early)
-        if (d_in != d_out && batch)
-            CU(cudaMemcpyAsync(d_out, d_in, batch * sizeof(double2), cudaMemcpyDeviceToDevice, s));
-        return KOFFT_OK;
-    }
+    return KOFFT_OK;
+}
+int f64_dispatch(kofft_cuda_ctx *ctx, LaunchF64Args &a, size_t n, size_t batch, int inverse, cudaStream_t s)
+{
     if (batch == 0) return KOFFT_OK;
-    LaunchF64Args a;
-    a.in = static_cast<const double2 *>(d_in);
-    a.out = static_cast<double2 *>(d_out);
     a.n = static_cast<long>(n);
     a.rows = static_cast<long>(batch);
     a.inverse = inverse != 0;
-    a.scale = 1.0 / static_cast<double>(static_cast<float>(n)); // T::one() / T::from_f32(n as f32), src/fft.rs:1167
+    // T::one() / T::from_f32(n as f32) (ifft, src/fft.rs:1167); 1.0 / n as f64 (ifft_split, :1421): equal for these n
+    a.scale = 1.0 / static_cast<double>(static_cast<float>(n));
     a.num_sms = ctx->num_sms;
     a.max_ctas = ctx->max_ctas;
-    // measured (profiles/r02b, r02c): the prefetch pays from N = 1024 up (4096: 65 -> 80 % of the HBM peak);
-    // below, its extra barrier per row group costs more than the latency it hides (256: 93 -> 84 %)
-    a.staged = ctx->use_tma && aligned16(d_in) && n >= 1024;
     a.stream = s;
     if (n >= 32) {
         auto it = ctx->fft_tables_f64.find(n);
@@ -1275,6 +1269,68 @@ int kofft_cuda_fft_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, s
     ctx->launches += 1;
     return KOFFT_OK;
 }
+} // namespace
+
+int kofft_cuda_fft_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch, int inverse,
+                           void *stream)
+{
+    int rc = f64_check_len(ctx, n);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    if (n == 1) { // identity for fft; ifft: conj, conj, * (1/1) (src/fft.rs:1139-1141 returns early)
+        if (d_in != d_out && batch)
+            CU(cudaMemcpyAsync(d_out, d_in, batch * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        return KOFFT_OK;
+    }
+    LaunchF64Args a;
+    a.in = static_cast<const double2 *>(d_in);
+    a.out = static_cast<double2 *>(d_out);
+    // measured (profiles/r02b, r02c): the prefetch pays from N = 1024 up (4096: 65 -> 80 % of the HBM peak);
+    // below, its extra barrier per row group costs more than the latency it hides (256: 93 -> 84 %)
+    a.staged = ctx->use_tma && aligned16(d_in) && n >= 1024;
+    return f64_dispatch(ctx, a, n, batch, inverse, s);
+}
+
+// strided rows of interleaved complex doubles (strides / distances in complex elements), as
+// kofft_cuda_fft_strided_f32: FftImpl<f64>::fft_strided / fft_out_of_place_strided (src/fft.rs:1175-1336)
+int kofft_cuda_fft_strided_f64(kofft_cuda_ctx *ctx, const void *d_in, size_t in_stride, size_t in_dist, void *d_out,
+                               size_t out_stride, size_t out_dist, size_t n, size_t batch, int inverse, void *stream)
+{
+    if (in_stride == 0 || out_stride == 0) return KOFFT_ERR_INVALID_STRIDE;
+    int rc = f64_check_len(ctx, n);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    LaunchF64Args a;
+    a.generic = true;
+    a.in_re = static_cast<const double *>(d_in);
+    a.in_im = a.in_re + 1;
+    a.out_re = static_cast<double *>(d_out);
+    a.out_im = a.out_re + 1;
+    a.in_es = 2 * static_cast<long>(in_stride);
+    a.in_rs = 2 * static_cast<long>(in_dist);
+    a.out_es = 2 * static_cast<long>(out_stride);
+    a.out_rs = 2 * static_cast<long>(out_dist);
+    return f64_dispatch(ctx, a, n, batch, inverse, pick_stream(ctx, stream));
+}
+
+// split (SoA) rows: FftImpl<f64>::fft_split / ifft_split (src/fft.rs:556-586 -> 1365-1439), batched
+int kofft_cuda_fft_split_f64(kofft_cuda_ctx *ctx, const double *d_in_re, const double *d_in_im, double *d_out_re,
+                             double *d_out_im, size_t n, size_t batch, int inverse, void *stream)
+{
+    int rc = f64_check_len(ctx, n);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    LaunchF64Args a;
+    a.generic = true;
+    a.in_re = d_in_re;
+    a.in_im = d_in_im;
+    a.out_re = d_out_re;
+    a.out_im = d_out_im;
+    a.in_es = a.out_es = 1;
+    a.in_rs = a.out_rs = static_cast<long>(n);
+    return f64_dispatch(ctx, a, n, batch, inverse, pick_stream(ctx, stream));
+}
 
 int kofft_cuda_fft_batch_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, size_t batch, int inverse)
 {
@@ -1296,6 +1352,77 @@ int kofft_cuda_fft_batch_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, s
 int kofft_cuda_fft_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, int inverse)
 {
     return kofft_cuda_fft_batch_host_f64(ctx, data, n, 1, inverse);
+}
+
+int kofft_cuda_fft_split_host_f64(kofft_cuda_ctx *ctx, double *re, size_t re_len, double *im, size_t im_len, int inverse)
+{
+    if (re_len != im_len) return KOFFT_ERR_MISMATCHED_LENGTHS; // src/fft.rs:1366-1368
+    const size_t n = re_len;
+    int rc = f64_check_len(ctx, n);
+    if (rc) return rc;
+    if (n == 1) return KOFFT_OK; // identity; ifft_split: (negate, negate, * 1/1)
+    CU(cudaSetDevice(ctx->device));
+    void *d = nullptr;
+    rc = ensure_ws(ctx, 0, 2 * n * sizeof(double), &d);
+    if (rc) return rc;
+    double *dre = static_cast<double *>(d), *dim = dre + n;
+    CU(cudaMemcpyAsync(dre, re, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dim, im, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    rc = kofft_cuda_fft_split_f64(ctx, dre, dim, dre, dim, n, 1, inverse, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(re, dre, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(im, dim, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_fft_strided_host_f64(kofft_cuda_ctx *ctx, double *input, size_t input_len, size_t stride, size_t n,
+                                    int inverse)
+{
+    if (stride == 0) return KOFFT_ERR_INVALID_STRIDE;                           // src/fft.rs:1181-1183
+    if (n == 0) return KOFFT_OK;                                                // :1185-1187
+    if (input_len < (n - 1) * stride + 1) return KOFFT_ERR_MISMATCHED_LENGTHS; // :1188-1190
+    int rc = f64_check_len(ctx, n);
+    if (rc) return rc;
+    if (n == 1) return KOFFT_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t span = (n - 1) * stride + 1;
+    void *d = nullptr;
+    rc = host_roundtrip_begin(ctx, input, span * sizeof(double2), 0, &d);
+    if (rc) return rc;
+    rc = kofft_cuda_fft_strided_f64(ctx, d, stride, span, d, stride, span, n, 1, inverse, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(input, d, span * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_fft_out_of_place_strided_host_f64(kofft_cuda_ctx *ctx, const double *input, size_t input_len,
+                                                 size_t in_stride, double *output, size_t output_len, size_t out_stride,
+                                                 int inverse)
+{
+    if (in_stride == 0 || out_stride == 0) return KOFFT_ERR_INVALID_STRIDE;   // src/fft.rs:1267-1269
+    if (input_len % in_stride != 0 || output_len % out_stride != 0) return KOFFT_ERR_INVALID_STRIDE; // :1270-1272
+    const size_t n = input_len / in_stride;
+    if (output_len / out_stride != n) return KOFFT_ERR_MISMATCHED_LENGTHS;    // :1274-1276
+    int rc = f64_check_len(ctx, n);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    void *din = nullptr, *dout = nullptr;
+    rc = host_roundtrip_begin(ctx, input, input_len * sizeof(double2), 0, &din);
+    if (rc) return rc;
+    rc = host_roundtrip_begin(ctx, output, output_len * sizeof(double2), 1, &dout); // untouched elements survive
+    if (rc) return rc;
+    if (n == 1) { // a one-point transform copies the element (ifft: conj, conj, * 1)
+        CU(cudaMemcpyAsync(dout, din, sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        rc = kofft_cuda_fft_strided_f64(ctx, din, in_stride, input_len, dout, out_stride, output_len, n, 1, inverse,
+                                        ctx->stream);
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(output, dout, output_len * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
 }
 
 int kofft_cuda_fft_split_host_f32(kofft_cuda_ctx *ctx, float *re, size_t re_len, float *im, size_t im_len,

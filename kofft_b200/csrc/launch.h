@@ -135,6 +135,12 @@ struct LaunchF64Args {
     Tw0D tw0 = {};                    // pass-0 twiddles: v[(2^t - 1) + c] = T[c << (L-1-t)]
     int num_sms = 148, max_ctas = 0;
     bool staged = true;               // TMA prefetch of the next row group into the idle exchange buffer
+    // generic (strided / split) addressing instead of dense interleaved rows: element e of row r at
+    // re[r*rs + e*es], strides in doubles
+    bool generic = false;
+    const double *in_re = nullptr, *in_im = nullptr;
+    double *out_re = nullptr, *out_im = nullptr;
+    long in_es = 0, in_rs = 0, out_es = 0, out_rs = 0;
     cudaStream_t stream = nullptr;
 };
 cudaError_t launch_fft_f64(const LaunchF64Args &a);

@@ -58,6 +58,40 @@ class CudaFftImpl64:
         a = _c128(input)
         check(self._lib.kofft_cuda_fft_host_f64(self.ctx.handle, a.ctypes.data, a.size, 1))
 
+    @staticmethod
+    def _f64(a, name="input") -> np.ndarray:
+        if not isinstance(a, np.ndarray) or a.dtype != np.float64 or not a.flags.c_contiguous or not a.flags.writeable:
+            raise TypeError(f"{name}: expected a writable C-contiguous numpy float64 array")
+        return a
+
+    def fft_split(self, re: np.ndarray, im: np.ndarray) -> None:
+        """`fft_split` for f64 (src/fft.rs:1365-1391; tests/split64.rs)."""
+        r, i = self._f64(re, "re"), self._f64(im, "im")
+        check(self._lib.kofft_cuda_fft_split_host_f64(self.ctx.handle, r.ctypes.data, r.size, i.ctypes.data, i.size, 0))
+
+    def ifft_split(self, re: np.ndarray, im: np.ndarray) -> None:
+        r, i = self._f64(re, "re"), self._f64(im, "im")
+        check(self._lib.kofft_cuda_fft_split_host_f64(self.ctx.handle, r.ctypes.data, r.size, i.ctypes.data, i.size, 1))
+
+    def fft_strided(self, input: np.ndarray, stride: int, scratch: np.ndarray) -> None:
+        """`fft_strided` (src/fft.rs:1175-1199): n = len(scratch) elements, `stride` apart, in place."""
+        a = _c128(input)
+        check(self._lib.kofft_cuda_fft_strided_host_f64(self.ctx.handle, a.ctypes.data, a.size, stride, len(scratch), 0))
+
+    def ifft_strided(self, input: np.ndarray, stride: int, scratch: np.ndarray) -> None:
+        a = _c128(input)
+        check(self._lib.kofft_cuda_fft_strided_host_f64(self.ctx.handle, a.ctypes.data, a.size, stride, len(scratch), 1))
+
+    def fft_out_of_place_strided(self, input: np.ndarray, in_stride: int, output: np.ndarray, out_stride: int) -> None:
+        a, o = _c128(np.ascontiguousarray(input), "input"), _c128(output, "output")
+        check(self._lib.kofft_cuda_fft_out_of_place_strided_host_f64(self.ctx.handle, a.ctypes.data, a.size, in_stride,
+                                                                    o.ctypes.data, o.size, out_stride, 0))
+
+    def ifft_out_of_place_strided(self, input: np.ndarray, in_stride: int, output: np.ndarray, out_stride: int) -> None:
+        a, o = _c128(np.ascontiguousarray(input), "input"), _c128(output, "output")
+        check(self._lib.kofft_cuda_fft_out_of_place_strided_host_f64(self.ctx.handle, a.ctypes.data, a.size, in_stride,
+                                                                    o.ctypes.data, o.size, out_stride, 1))
+
     def fft_batch(self, x, inverse: bool = False, out=None):
         """Dense rows [batch][n]: numpy complex128 (in place, host path) or CUDA torch.complex128."""
         if _is_tensor(x):

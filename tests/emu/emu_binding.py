@@ -120,6 +120,19 @@ def _f64(self, n, rows, inp, out, table, inverse=False, grid=2, staged=False):
 EmuKernels.f64 = _f64
 
 
+def _f64_split(self, n, rows, re, im, ore, oim, table, inverse=False, grid=2):
+    """CtaFftD::run over IoGenericD: split (SoA) float64 rows."""
+    f = self.lib.kofft_emuk_f64_split
+    f.restype = C.c_int
+    f.argtypes = [C.c_long, C.c_long] + [C.c_void_p] * 4 + [C.c_int, C.c_double, C.c_void_p, C.c_int]
+    rc = f(n, rows, re.ctypes.data, im.ctypes.data, ore.ctypes.data, oim.ctypes.data, int(inverse), 1.0 / float(np.float32(n)),
+           table.ctypes.data if table is not None else None, grid)
+    assert rc == 0, rc
+
+
+EmuKernels.f64_split = _f64_split
+
+
 def _bind_istft(lib):
     f = lib.kofft_emuk_istft_fused
     f.restype = C.c_int

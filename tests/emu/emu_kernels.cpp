@@ -307,10 +307,13 @@ static int run_f64_L(const IO &io, const double *table, long rows, int grid)
     std::vector<double2> smem(P::SMEM_BYTES / 16 + 32);
     const double2 *tab = reinterpret_cast<const double2 *>(table);
     double2 *sm = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
-    if (g_f64_staged)
-        cuda_emu::launch(grid, P::CTA, [&] { CtaFftD<L, IO>::template run<true>(io, tw0, tab, rows, sm); });
-    else
-        cuda_emu::launch(grid, P::CTA, [&] { CtaFftD<L, IO>::template run<false>(io, tw0, tab, rows, sm); });
+    if constexpr (IO::kStageable) {
+        if (g_f64_staged) {
+            cuda_emu::launch(grid, P::CTA, [&] { CtaFftD<L, IO>::template run<true>(io, tw0, tab, rows, sm); });
+            return 0;
+        }
+    }
+    cuda_emu::launch(grid, P::CTA, [&] { CtaFftD<L, IO>::template run<false>(io, tw0, tab, rows, sm); });
     return 0;
 }
 
@@ -334,6 +337,24 @@ static int run_f64_io(const IO &io, long n, const double *table, long rows, int 
 #undef CASE_L
     default: return -1;
     }
+}
+
+// split (SoA) rows through IoGenericD: re / im [rows][n]
+API int kofft_emuk_f64_split(long n, long rows, const double *in_re, const double *in_im, double *out_re, double *out_im,
+                             int inverse, double scale, const double *table, int grid)
+{
+    const bool keep = g_f64_staged;
+    g_f64_staged = false; // generic rows are never staged
+    int rc;
+    if (inverse) {
+        IoGenericD<true> io{in_re, in_im, out_re, out_im, 1, n, 1, n, scale};
+        rc = run_f64_io(io, n, table, rows, grid);
+    } else {
+        IoGenericD<false> io{in_re, in_im, out_re, out_im, 1, n, 1, n, scale};
+        rc = run_f64_io(io, n, table, rows, grid);
+    }
+    g_f64_staged = keep;
+    return rc;
 }
 
 // in / out: [rows][n] complex doubles; table: FftPlanner<f64> table of n (n >= 32)

@@ -93,3 +93,51 @@ def test_f64_tables_and_errors(fft64, oracle):
         fft64.fft(np.zeros(12, np.complex128))
     with pytest.raises(CudaBackendError):
         fft64.fft(np.zeros(16384, np.complex128))
+
+
+def test_f64_split_strided_surface(fft64, oracle):
+    """tests/split64.rs: fft_split == AoS fft (n = 32, x = (i, 0)) and the ifft_split round trip (n = 64,
+    x = (i, -i)); plus fft_strided / fft_out_of_place_strided for f64 with the reference's argument
+    meaning and errors (src/fft.rs:1175-1336), all bit-identical to the f64 oracle."""
+    from kofft_b200.errors import InvalidStride, MismatchedLengths
+
+    n = 32
+    data = (np.arange(n) + 0j).astype(np.complex128)
+    re, im = np.ascontiguousarray(data.real), np.ascontiguousarray(data.imag)
+    fft64.fft_split(re, im)
+    ref = oracle.fft_f64(data)
+    assert np.array_equal(re, ref.real) and np.array_equal(im, ref.imag)
+    n = 64
+    data = (np.arange(n) * (1 - 1j)).astype(np.complex128)
+    re, im = np.ascontiguousarray(data.real), np.ascontiguousarray(data.imag)
+    fft64.fft_split(re, im)
+    fft64.ifft_split(re, im)
+    back = oracle.fft_f64(oracle.fft_f64(data), inverse=True)
+    assert np.array_equal(re, back.real) and np.array_equal(im, back.imag)
+    assert np.abs(re - data.real).max() < 1e-8 and np.abs(im - data.imag).max() < 1e-8
+    with pytest.raises(MismatchedLengths):
+        fft64.fft_split(np.zeros(8), np.zeros(4))
+    # strided, in place: every 3rd element of a longer buffer
+    rng = np.random.default_rng(3)
+    n, stride = 256, 3
+    buf = (rng.uniform(-1, 1, n * stride) + 1j * rng.uniform(-1, 1, n * stride)).astype(np.complex128)
+    want = buf.copy()
+    want[::stride] = oracle.fft_f64(buf[::stride])
+    fft64.fft_strided(buf, stride, np.zeros(n, np.complex128))
+    assert np.array_equal(buf, want)
+    want[::stride] = oracle.fft_f64(want[::stride], inverse=True)
+    fft64.ifft_strided(buf, stride, np.zeros(n, np.complex128))
+    assert np.array_equal(buf, want)
+    with pytest.raises(InvalidStride):
+        fft64.fft_strided(buf, 0, np.zeros(n, np.complex128))
+    with pytest.raises(MismatchedLengths):
+        fft64.fft_strided(buf[:10], stride, np.zeros(n, np.complex128))
+    # out of place, different strides; untouched output elements survive
+    src = (rng.uniform(-1, 1, 128 * 2) + 1j * rng.uniform(-1, 1, 128 * 2)).astype(np.complex128)
+    dst = np.full(128 * 5, 7 + 7j, np.complex128)
+    fft64.fft_out_of_place_strided(src, 2, dst, 5)
+    want = np.full(128 * 5, 7 + 7j, np.complex128)
+    want[::5] = oracle.fft_f64(src[::2])
+    assert np.array_equal(dst, want)
+    with pytest.raises(InvalidStride):
+        fft64.fft_out_of_place_strided(src, 0, dst, 5)

@@ -262,3 +262,18 @@ def test_f64_kernel_body(emuk, oracle, n):
             y = np.zeros_like(x)
             emuk.f64(n, rows, x, y, tab, inverse=inverse, grid=grid, staged=staged)
             assert np.array_equal(y, ref), (n, inverse, grid, staged)
+
+
+@pytest.mark.parametrize("n", [8, 64, 2048])
+def test_f64_split_rows_kernel_body(emuk, oracle, n):
+    """IoGenericD (split / strided addressing of the f64 engine) against the f64 oracle."""
+    rng = np.random.default_rng(128 + n)
+    rows = 5
+    x = (rng.uniform(-1, 1, (rows, n)) + 1j * rng.uniform(-1, 1, (rows, n))).astype(np.complex128)
+    re, im = np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag)
+    tab = oracle.twiddles_f64(n) if n >= 32 else None
+    for inverse in (False, True):
+        ref = oracle.fft_batch_f64(x, inverse=inverse)
+        ore, oim = np.zeros_like(re), np.zeros_like(im)
+        emuk.f64_split(n, rows, re, im, ore, oim, tab, inverse=inverse)
+        assert np.array_equal(ore, ref.real) and np.array_equal(oim, ref.imag), (n, inverse)
