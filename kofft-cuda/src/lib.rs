@@ -29,6 +29,13 @@ extern "C" {
     fn kofft_cuda_fft_batch_host_f32(ctx: *mut RawCtx, data: *mut f32, n: usize, batch: usize, inverse: c_int) -> c_int;
     fn kofft_cuda_fft_host_f64(ctx: *mut RawCtx, data: *mut f64, n: usize, inverse: c_int) -> c_int;
     fn kofft_cuda_fft_batch_host_f64(ctx: *mut RawCtx, data: *mut f64, n: usize, batch: usize, inverse: c_int) -> c_int;
+    fn kofft_cuda_fft_split_host_f64(ctx: *mut RawCtx, re: *mut f64, re_len: usize, im: *mut f64, im_len: usize,
+                                     inverse: c_int) -> c_int;
+    fn kofft_cuda_fft_strided_host_f64(ctx: *mut RawCtx, input: *mut f64, input_len: usize, stride: usize, n: usize,
+                                       inverse: c_int) -> c_int;
+    fn kofft_cuda_fft_out_of_place_strided_host_f64(ctx: *mut RawCtx, input: *const f64, input_len: usize,
+                                                    in_stride: usize, output: *mut f64, output_len: usize,
+                                                    out_stride: usize, inverse: c_int) -> c_int;
     fn kofft_cuda_fft_split_host_f32(ctx: *mut RawCtx, re: *mut f32, re_len: usize, im: *mut f32, im_len: usize,
                                      inverse: c_int) -> c_int;
     fn kofft_cuda_fft_strided_host_f32(ctx: *mut RawCtx, input: *mut f32, input_len: usize, stride: usize, n: usize,
@@ -259,8 +266,7 @@ impl FftImpl<f32> for CudaFftImpl {
 }
 
 /// The f64 twin: kofft's `ScalarFftImpl<f64>` (src/fft.rs:914-1051) on the GPU, power-of-two lengths
-/// 1..=8192, bit-identical.  The strided / split entry points gather into a dense row on the host
-/// (what the reference's own implementations do, src/fft.rs:1175-1336, 556-586) and call `fft`.
+/// 1..=8192, bit-identical, the whole trait surface (strided, out of place, split) on the device.
 pub struct CudaFftImpl64 {
     ctx: *mut RawCtx,
 }
@@ -289,45 +295,6 @@ impl CudaFftImpl64 {
             kofft_cuda_fft_batch_host_f64(self.ctx, rows.as_mut_ptr() as *mut f64, n, rows.len() / n, inverse as c_int)
         })
     }
-    fn strided(&self, input: &mut [Complex64], stride: usize, scratch: &mut [Complex64], inverse: bool) -> Result<(), FftError> {
-        if stride == 0 {
-            return Err(FftError::InvalidStride);
-        }
-        let n = scratch.len();
-        if n == 0 {
-            return Err(FftError::EmptyInput);
-        }
-        if input.len() < (n - 1) * stride + 1 {
-            return Err(FftError::MismatchedLengths);
-        }
-        for i in 0..n {
-            scratch[i] = input[i * stride];
-        }
-        if inverse { self.ifft(scratch)? } else { self.fft(scratch)? }
-        for i in 0..n {
-            input[i * stride] = scratch[i];
-        }
-        Ok(())
-    }
-    fn out_of_place(&self, input: &[Complex64], in_stride: usize, output: &mut [Complex64], out_stride: usize,
-                    inverse: bool) -> Result<(), FftError> {
-        if in_stride == 0 || out_stride == 0 {
-            return Err(FftError::InvalidStride);
-        }
-        let n = if input.is_empty() { 0 } else { (input.len() - 1) / in_stride + 1 };
-        if n == 0 {
-            return Err(FftError::EmptyInput);
-        }
-        if output.len() < (n - 1) * out_stride + 1 {
-            return Err(FftError::MismatchedLengths);
-        }
-        let mut row: Vec<Complex64> = (0..n).map(|i| input[i * in_stride]).collect();
-        if inverse { self.ifft(&mut row)? } else { self.fft(&mut row)? }
-        for i in 0..n {
-            output[i * out_stride] = row[i];
-        }
-        Ok(())
-    }
 }
 
 impl Drop for CudaFftImpl64 {
@@ -344,18 +311,34 @@ impl FftImpl<f64> for CudaFftImpl64 {
         check(unsafe { kofft_cuda_fft_host_f64(self.ctx, input.as_mut_ptr() as *mut f64, input.len(), 1) })
     }
     fn fft_strided(&self, input: &mut [Complex64], stride: usize, scratch: &mut [Complex64]) -> Result<(), FftError> {
-        self.strided(input, stride, scratch, false)
+        check(unsafe {
+            kofft_cuda_fft_strided_host_f64(self.ctx, input.as_mut_ptr() as *mut f64, input.len(), stride, scratch.len(), 0)
+        })
     }
     fn ifft_strided(&self, input: &mut [Complex64], stride: usize, scratch: &mut [Complex64]) -> Result<(), FftError> {
-        self.strided(input, stride, scratch, true)
+        check(unsafe {
+            kofft_cuda_fft_strided_host_f64(self.ctx, input.as_mut_ptr() as *mut f64, input.len(), stride, scratch.len(), 1)
+        })
     }
     fn fft_out_of_place_strided(&self, input: &[Complex64], in_stride: usize, output: &mut [Complex64],
                                 out_stride: usize) -> Result<(), FftError> {
-        self.out_of_place(input, in_stride, output, out_stride, false)
+        check(unsafe {
+            kofft_cuda_fft_out_of_place_strided_host_f64(self.ctx, input.as_ptr() as *const f64, input.len(), in_stride,
+                                                         output.as_mut_ptr() as *mut f64, output.len(), out_stride, 0)
+        })
     }
     fn ifft_out_of_place_strided(&self, input: &[Complex64], in_stride: usize, output: &mut [Complex64],
                                  out_stride: usize) -> Result<(), FftError> {
-        self.out_of_place(input, in_stride, output, out_stride, true)
+        check(unsafe {
+            kofft_cuda_fft_out_of_place_strided_host_f64(self.ctx, input.as_ptr() as *const f64, input.len(), in_stride,
+                                                         output.as_mut_ptr() as *mut f64, output.len(), out_stride, 1)
+        })
+    }
+    fn fft_split(&self, re: &mut [f64], im: &mut [f64]) -> Result<(), FftError> {
+        check(unsafe { kofft_cuda_fft_split_host_f64(self.ctx, re.as_mut_ptr(), re.len(), im.as_mut_ptr(), im.len(), 0) })
+    }
+    fn ifft_split(&self, re: &mut [f64], im: &mut [f64]) -> Result<(), FftError> {
+        check(unsafe { kofft_cuda_fft_split_host_f64(self.ctx, re.as_mut_ptr(), re.len(), im.as_mut_ptr(), im.len(), 1) })
     }
     fn fft_with_strategy(&self, input: &mut [Complex64], _strategy: FftStrategy) -> Result<(), FftError> {
         self.fft(input)
