@@ -165,6 +165,13 @@ int kofft_cuda_fft_strided_f64(kofft_cuda_ctx *ctx, const void *d_in, size_t in_
                                size_t out_stride, size_t out_dist, size_t n, size_t batch, int inverse, void *stream);
 int kofft_cuda_fft_split_f64(kofft_cuda_ctx *ctx, const double *d_in_re, const double *d_in_im, double *d_out_re,
                              double *d_out_im, size_t n, size_t batch, int inverse, void *stream);
+/* RealFftImpl<f64> (src/rfft.rs:775-837 -> rfft_direct / irfft_direct :425-508 with T = f64), batched; the
+ * table is build_twiddle_table::<f64> (:172-183).  n even, n/2 a power of two <= 8192; errors as the f32 twins. */
+int kofft_cuda_rfft_twiddles_host_f64(size_t m, double *out);
+int kofft_cuda_rfft_f64(kofft_cuda_ctx *ctx, const double *d_in, void *d_out, size_t n, size_t batch, void *stream);
+int kofft_cuda_irfft_f64(kofft_cuda_ctx *ctx, const void *d_in, double *d_out, size_t n, size_t batch, void *stream);
+int kofft_cuda_rfft_batch_host_f64(kofft_cuda_ctx *ctx, const double *input, size_t n, size_t batch, double *output);
+int kofft_cuda_irfft_batch_host_f64(kofft_cuda_ctx *ctx, const double *input, size_t n, size_t batch, double *output);
 /* FftImpl::<f64>::fft / ifft in place on n complex doubles; batch variant on dense rows */
 int kofft_cuda_fft_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, int inverse);
 int kofft_cuda_fft_batch_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, size_t batch, int inverse);

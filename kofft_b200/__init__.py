@@ -19,14 +19,14 @@ from .errors import (CudaBackendError, EmptyInput, FftError, InvalidHopSize, Inv
 from .fft import (Context, CudaFftImpl, FftPlanner, FftStrategy, batch, batch_inverse,  # noqa: F401
                   fft_parallel, fft_split, ifft_parallel, ifft_split, multi_channel,
                   multi_channel_inverse, new_fft_impl)
-from .fft64 import CudaFftImpl64, FftPlanner64  # noqa: F401
+from .fft64 import CudaFftImpl64, FftPlanner64, RfftPlanner64  # noqa: F401
 from .rfft import RfftPlanner  # noqa: F401
 from . import stft  # noqa: F401
 from . import spectrogram  # noqa: F401
 from . import ndfft  # noqa: F401
 
 __all__ = [
-    "Context", "CudaFftImpl", "CudaFftImpl64", "FftPlanner", "FftPlanner64", "FftStrategy", "RfftPlanner", "new_fft_impl",
+    "Context", "CudaFftImpl", "CudaFftImpl64", "FftPlanner", "FftPlanner64", "RfftPlanner64", "FftStrategy", "RfftPlanner", "new_fft_impl",
     "batch", "batch_inverse", "multi_channel", "multi_channel_inverse",
     "fft_parallel", "ifft_parallel", "fft_split", "ifft_split",
     "FftError", "EmptyInput", "NonPowerOfTwoNoStd", "MismatchedLengths", "InvalidStride",

@@ -54,6 +54,11 @@ SIGNATURES = {
     "kofft_cuda_fft_split_host_f64": (_i, [_vp, _vp, _sz, _vp, _sz, _i]),
     "kofft_cuda_fft_strided_host_f64": (_i, [_vp, _vp, _sz, _sz, _sz, _i]),
     "kofft_cuda_fft_out_of_place_strided_host_f64": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i]),
+    "kofft_cuda_rfft_twiddles_host_f64": (_i, [_sz, _vp]),
+    "kofft_cuda_rfft_f64": (_i, [_vp, _vp, _vp, _sz, _sz, _vp]),
+    "kofft_cuda_irfft_f64": (_i, [_vp, _vp, _vp, _sz, _sz, _vp]),
+    "kofft_cuda_rfft_batch_host_f64": (_i, [_vp, _vp, _sz, _sz, _vp]),
+    "kofft_cuda_irfft_batch_host_f64": (_i, [_vp, _vp, _sz, _sz, _vp]),
     "kofft_cuda_fft_host_f64": (_i, [_vp, _vp, _sz, _i]),
     "kofft_cuda_fft_batch_host_f64": (_i, [_vp, _vp, _sz, _sz, _i]),
     "kofft_cuda_fft_strided_f32": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _sz, _sz, _i, _vp]),

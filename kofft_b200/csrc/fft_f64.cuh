@@ -128,6 +128,78 @@ struct IoGenericD {
     }
 };
 
+// rfft for f64 (rfft_direct, src/rfft.rs:425-465 with T = f64): the row of 2m reals is read as m complex
+// (the pack is a reinterpretation); after the length-m FFT the bins go once more through the exchange
+// buffer and are twisted.  T'[k] = exp(-i pi k / m) from build_twiddle_table::<f64> (:172-183).
+struct IoRfftD {
+    typedef void is_f64;
+    static constexpr bool kEpilogueExchange = true;
+    static constexpr bool kStageable = true;
+    const double2 *__restrict__ in;  // [rows][m]
+    double2 *__restrict__ out;       // [rows][m + 1]
+    const double2 *__restrict__ rtw; // m entries
+    long n;                          // m (the engine's transform length; `n` so that staging is generic)
+    KHD double2 from_raw(double2 v) const { return v; }
+    KHD double2 load(long row, int i) const { return in[row * n + i]; }
+    KHD void store(long, int, double2) const {}
+    // Y: the m FFT bins of this row, padded layout (or a plain array for m <= 16, where pad(k) == k)
+    KHD void epilogue(long row, int k, const double2 *Y) const
+    {
+        const long m = n;
+        double2 *o = out + row * (m + 1);
+        const double2 a = Y[pad(k)];
+        if (k == 0) { // :451-453
+            o[0] = make_double2(dadd(a.x, a.y), 0.0);
+            o[m] = make_double2(dsub(a.x, a.y), 0.0);
+            return;
+        }
+        const double2 ym = Y[pad((int)m - k)];
+        const double2 b = make_double2(ym.x, -ym.y);
+        const double2 sum = add2(a, b), diff = sub2(a, b);
+        const double2 t = cmul<true>(rtw[k], diff);
+        const double2 temp = make_double2(dadd(sum.x, t.y), dsub(sum.y, t.x)); // sum + (t.im, -t.re)
+        o[k] = make_double2(dmul(temp.x, 0.5), dmul(temp.y, 0.5));
+    }
+};
+
+// irfft for f64 (irfft_direct, src/rfft.rs:468-508): the untwist is evaluated while loading element i
+// (it needs X[i] and X[m-i]), then ifft (conj, fft, conj, * 1/m), then the unpack is a reinterpretation
+struct IoIrfftD {
+    typedef void is_f64;
+    static constexpr bool kEpilogueExchange = false;
+    static constexpr bool kStageable = false;
+    const double2 *__restrict__ in;  // [rows][m + 1]
+    double2 *__restrict__ out;       // [rows][m] == 2m reals
+    const double2 *__restrict__ rtw;
+    long n;                          // m
+    double scale;                    // 1/m
+    KHD double2 load(long row, int i) const
+    {
+        const long m = n;
+        const double2 *X = in + row * (m + 1);
+        double2 v;
+        if (i == 0) {
+            const double2 x0 = X[0], xm = X[m];
+            v = make_double2(dmul(dadd(x0.x, xm.x), 0.5), dmul(dsub(x0.x, xm.x), 0.5));
+        } else {
+            const double2 a = X[i], xm = X[m - i];
+            const double2 b = make_double2(xm.x, -xm.y);
+            const double2 sum = add2(a, b), diff = sub2(a, b);
+            const double2 tw = rtw[i];
+            const double2 t = cmul<true>(make_double2(tw.x, -tw.y), diff);
+            const double2 temp = make_double2(dsub(sum.x, t.y), dadd(sum.y, t.x)); // sum - (t.im, -t.re)
+            v = make_double2(dmul(temp.x, 0.5), dmul(temp.y, 0.5));
+        }
+        v.y = -v.y; // ifft's leading conjugation
+        return v;
+    }
+    KHD void store(long row, int i, double2 v) const
+    {
+        v.y = -v.y;
+        out[row * n + i] = make_double2(dmul(v.x, scale), dmul(v.y, scale));
+    }
+};
+
 template <int L, class IO>
 struct CtaFftD {
     using P = PlanD<L>;
@@ -206,7 +278,7 @@ struct CtaFftD {
             const long gn = g + gridDim.x;
             // after the group's LAST exchange the buffer is idle: request the next group's rows
             auto prefetch = [&](int pass_after) {
-                if (STAGED && pass_after == P::NP - 1 && tid == 0 && gn < groups) stage_issue(gn);
+                if (STAGED && !IO::kEpilogueExchange && pass_after == P::NP - 1 && tid == 0 && gn < groups) stage_issue(gn);
             };
             P0::compute(x, tw0.v);
             xchg<P0, P1>(buf, t, x);
@@ -231,7 +303,21 @@ struct CtaFftD {
                 P3::compute(x, tw);
             }
             using PL = PassD<P, P::NP - 1>;
-            if (active) {
+            if constexpr (IO::kEpilogueExchange) {
+                // rfft: all bins of the row back into the (padded) buffer, then thread t twists bins t + u T.
+                // The staged prefetch (issued after the last exchange) has to wait for this one instead.
+#pragma unroll
+                for (int u = 0; u < PL::U; u++)
+#pragma unroll
+                    for (int w = 0; w < PL::R; w++) buf[PL::dst_pad(PL::dst_base(t, u), w)] = x[u * PL::R + w];
+                __syncthreads();
+                if (active) {
+#pragma unroll
+                    for (int u = 0; u < EPT; u++) io.epilogue(row, t + u * P::T, buf);
+                }
+                __syncthreads();
+                if (STAGED && tid == 0 && gn < groups) stage_issue(gn);
+            } else if (active) {
 #pragma unroll
                 for (int u = 0; u < PL::U; u++)
 #pragma unroll

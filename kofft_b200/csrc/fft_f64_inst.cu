@@ -87,6 +87,14 @@ cudaError_t launch_fft_f64(const LaunchF64Args &a)
         IoGenericD<false> io{a.in_re, a.in_im, a.out_re, a.out_im, a.in_es, a.in_rs, a.out_es, a.out_rs, a.scale};
         return launch_f64_io(io, a);
     }
+    if (a.real == 1) { // rfft: n = m
+        IoRfftD io{a.in, a.out, a.rtw, a.n};
+        return launch_f64_io(io, a);
+    }
+    if (a.real == 2) { // irfft
+        IoIrfftD io{a.in, a.out, a.rtw, a.n, a.scale};
+        return launch_f64_io(io, a);
+    }
     if (a.inverse) {
         IoC2CD<true> io{a.in, a.out, a.n, a.scale};
         return launch_f64_io(io, a);

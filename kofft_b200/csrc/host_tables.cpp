@@ -110,6 +110,23 @@ void host_rfft_twiddles(size_t m, float *out, bool fma_mul)
     }
 }
 
+// build_twiddle_table::<f64>, reference src/rfft.rs:172-183: angle = -PI / from_f32(m as f32), current *= w with
+// the unfused Complex::mul (src/num.rs:160-165)
+void host_rfft_twiddles_f64(size_t m, double *out)
+{
+    const double angle = -3.14159265358979323846 / static_cast<double>(static_cast<float>(m));
+    const double ws = sin(angle), wc = cos(angle);
+    double re = 1.0, im = 0.0;
+    for (size_t k = 0; k < m; ++k) {
+        out[2 * k] = re;
+        out[2 * k + 1] = im;
+        const double nre = re * wc - im * ws;
+        const double nim = re * ws + im * wc;
+        re = nre;
+        im = nim;
+    }
+}
+
 // I0 series, reference src/window.rs:9-21
 static float bessel_i0(float x)
 {

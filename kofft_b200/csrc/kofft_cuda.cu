@@ -84,7 +84,8 @@ struct kofft_cuda_ctx {
         std::vector<double> host; // interleaved
         double2 *dev = nullptr;
     };
-    std::map<size_t, TableD> fft_tables_f64; // FftPlanner<f64>
+    std::map<size_t, TableD> fft_tables_f64;  // FftPlanner<f64>
+    std::map<size_t, TableD> rfft_tables_f64; // RfftPlanner<f64>, key m
     // grow-only device workspaces: [0] host-API staging in, [1] staging out, [2] istft time frames,
     // [3] small staging (windows), [4] two-pass (N > 16384) intermediate
     void *ws[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -379,6 +380,8 @@ void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     if (ctx->pipe_flags) cudaFree(ctx->pipe_flags);
     for (auto &kv : ctx->fft_tables_f64)
+        if (kv.second.dev) cudaFree(kv.second.dev);
+    for (auto &kv : ctx->rfft_tables_f64)
         if (kv.second.dev) cudaFree(kv.second.dev);
     if (ctx->pipe_ready) {
         for (int i = 0; i < 3; i++) {
@@ -1330,6 +1333,100 @@ int kofft_cuda_fft_split_f64(kofft_cuda_ctx *ctx, const double *d_in_re, const d
     a.in_es = a.out_es = 1;
     a.in_rs = a.out_rs = static_cast<long>(n);
     return f64_dispatch(ctx, a, n, batch, inverse, pick_stream(ctx, stream));
+}
+
+// ---- f64 real transforms: RealFftImpl<f64> (src/rfft.rs:775-837 -> rfft_direct / irfft_direct :425-508) ----
+int kofft_cuda_rfft_twiddles_host_f64(size_t m, double *out)
+{
+    host_rfft_twiddles_f64(m, out);
+    return KOFFT_OK;
+}
+
+namespace {
+int get_rfft_table_f64(kofft_cuda_ctx *ctx, size_t m, const double2 **out)
+{
+    auto it = ctx->rfft_tables_f64.find(m);
+    if (it == ctx->rfft_tables_f64.end()) {
+        kofft_cuda_ctx::TableD t;
+        t.host.resize(2 * m);
+        host_rfft_twiddles_f64(m, t.host.data());
+        CU(cudaMalloc(&t.dev, m * sizeof(double2)));
+        CU(cudaMemcpy(t.dev, t.host.data(), m * sizeof(double2), cudaMemcpyHostToDevice));
+        it = ctx->rfft_tables_f64.emplace(m, std::move(t)).first;
+    }
+    *out = it->second.dev;
+    return 0;
+}
+int real_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch, int which, void *stream)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;        // src/rfft.rs:434-436 / 477-479
+    if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE;  // :437-439 / 480-482
+    const size_t m = n / 2;
+    int rc = f64_check_len(ctx, m);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    LaunchF64Args a;
+    a.real = which;
+    a.in = static_cast<const double2 *>(d_in);
+    a.out = static_cast<double2 *>(d_out);
+    rc = get_rfft_table_f64(ctx, m, &a.rtw);
+    if (rc) return rc;
+    a.staged = which == 1 && ctx->use_tma && aligned16(d_in) && m >= 1024;
+    return f64_dispatch(ctx, a, m, batch, which == 2, pick_stream(ctx, stream));
+}
+} // namespace
+
+// d_in [batch][n] doubles -> d_out [batch][n/2+1] complex doubles
+int kofft_cuda_rfft_f64(kofft_cuda_ctx *ctx, const double *d_in, void *d_out, size_t n, size_t batch, void *stream)
+{
+    return real_f64(ctx, d_in, d_out, n, batch, 1, stream);
+}
+// d_in [batch][n/2+1] complex doubles -> d_out [batch][n] doubles
+int kofft_cuda_irfft_f64(kofft_cuda_ctx *ctx, const void *d_in, double *d_out, size_t n, size_t batch, void *stream)
+{
+    return real_f64(ctx, d_in, d_out, n, batch, 2, stream);
+}
+
+int kofft_cuda_rfft_batch_host_f64(kofft_cuda_ctx *ctx, const double *input, size_t n, size_t batch, double *output)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
+    if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE;
+    int rc = f64_check_len(ctx, n / 2);
+    if (rc) return rc;
+    if (batch == 0) return KOFFT_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t ibytes = batch * n * sizeof(double), obytes = batch * (n / 2 + 1) * sizeof(double2);
+    void *din = nullptr, *dout = nullptr;
+    rc = host_roundtrip_begin(ctx, input, ibytes, 0, &din);
+    if (rc) return rc;
+    rc = ensure_ws(ctx, 1, obytes, &dout);
+    if (rc) return rc;
+    rc = kofft_cuda_rfft_f64(ctx, static_cast<const double *>(din), dout, n, batch, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(output, dout, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
+}
+
+int kofft_cuda_irfft_batch_host_f64(kofft_cuda_ctx *ctx, const double *input, size_t n, size_t batch, double *output)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
+    if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE;
+    int rc = f64_check_len(ctx, n / 2);
+    if (rc) return rc;
+    if (batch == 0) return KOFFT_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t ibytes = batch * (n / 2 + 1) * sizeof(double2), obytes = batch * n * sizeof(double);
+    void *din = nullptr, *dout = nullptr;
+    rc = host_roundtrip_begin(ctx, input, ibytes, 0, &din);
+    if (rc) return rc;
+    rc = ensure_ws(ctx, 1, obytes, &dout);
+    if (rc) return rc;
+    rc = kofft_cuda_irfft_f64(ctx, din, static_cast<double *>(dout), n, batch, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(output, dout, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KOFFT_OK;
 }
 
 int kofft_cuda_fft_batch_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, size_t batch, int inverse)

@@ -141,6 +141,9 @@ struct LaunchF64Args {
     const double *in_re = nullptr, *in_im = nullptr;
     double *out_re = nullptr, *out_im = nullptr;
     long in_es = 0, in_rs = 0, out_es = 0, out_rs = 0;
+    // real transforms: 1 = rfft (in: [rows][m] complex view of the reals, out: [rows][m+1]), 2 = irfft; n = m
+    int real = 0;
+    const double2 *rtw = nullptr;     // T'[k] = exp(-i pi k / m), m entries
     cudaStream_t stream = nullptr;
 };
 cudaError_t launch_fft_f64(const LaunchF64Args &a);

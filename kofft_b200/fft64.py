@@ -43,6 +43,21 @@ class FftPlanner64:
         return self._cache[n]
 
 
+class RfftPlanner64:
+    """`RfftPlanner<f64>`: T'[k] = exp(-i pi k / m) from the f64 recurrence (src/rfft.rs:172-183)."""
+
+    def __init__(self):
+        self._cache: dict[int, np.ndarray] = {}
+
+    def get_twiddles(self, m: int) -> np.ndarray:
+        if m not in self._cache:
+            out = np.empty(m, dtype=np.complex128)
+            check(_lib.lib().kofft_cuda_rfft_twiddles_host_f64(m, out.ctypes.data))
+            out.flags.writeable = False
+            self._cache[m] = out
+        return self._cache[m]
+
+
 class CudaFftImpl64:
     """`impl FftImpl<f64>`: fft / ifft in place, plus the batched inherent method."""
 
@@ -91,6 +106,55 @@ class CudaFftImpl64:
         a, o = _c128(np.ascontiguousarray(input), "input"), _c128(output, "output")
         check(self._lib.kofft_cuda_fft_out_of_place_strided_host_f64(self.ctx.handle, a.ctypes.data, a.size, in_stride,
                                                                     o.ctypes.data, o.size, out_stride, 1))
+
+    # -- RealFftImpl<f64> (src/rfft.rs:775-837) ------------------------------------------------------
+    def rfft(self, input: np.ndarray, output: np.ndarray) -> None:
+        """`rfft(input, output)`: n reals -> n/2 + 1 bins; errors as the reference (src/rfft.rs:433-443)."""
+        a = self._f64(input)
+        o = _c128(output, "output")
+        if a.size and a.size % 2 == 0 and o.size != a.size // 2 + 1:
+            raise MismatchedLengths()
+        check(self._lib.kofft_cuda_rfft_batch_host_f64(self.ctx.handle, a.ctypes.data, a.size, 1, o.ctypes.data))
+
+    def irfft(self, input: np.ndarray, output: np.ndarray) -> None:
+        a = _c128(np.ascontiguousarray(input), "input")
+        o = self._f64(output, "output")
+        if o.size and o.size % 2 == 0 and a.size != o.size // 2 + 1:
+            raise MismatchedLengths()
+        check(self._lib.kofft_cuda_irfft_batch_host_f64(self.ctx.handle, a.ctypes.data, o.size, 1, o.ctypes.data))
+
+    def rfft_batch(self, x, out=None):
+        """[batch][n] float64 -> [batch][n/2+1] complex128 (numpy: host path; CUDA tensors: stream-ordered)."""
+        if _is_tensor(x):
+            if x.dtype != torch.float64 or x.dim() != 2 or not x.is_contiguous() or not x.is_cuda:
+                raise TypeError("expected a contiguous CUDA float64 tensor [batch, n]")
+            b, n = x.shape
+            if out is None:
+                out = torch.empty((b, n // 2 + 1), dtype=torch.complex128, device=x.device)
+            check(self._lib.kofft_cuda_rfft_f64(self.ctx.handle, x.data_ptr(), out.data_ptr(), n, b, _stream_of(x)))
+            return out
+        a = self._f64(np.ascontiguousarray(x))
+        b, n = a.shape
+        o = np.empty((b, n // 2 + 1), dtype=np.complex128) if out is None else out
+        check(self._lib.kofft_cuda_rfft_batch_host_f64(self.ctx.handle, a.ctypes.data, n, b, o.ctypes.data))
+        return o
+
+    def irfft_batch(self, x, n: int, out=None):
+        if _is_tensor(x):
+            if x.dtype != torch.complex128 or x.dim() != 2 or not x.is_contiguous() or not x.is_cuda:
+                raise TypeError("expected a contiguous CUDA complex128 tensor [batch, n/2+1]")
+            if x.shape[1] != n // 2 + 1:
+                raise MismatchedLengths()
+            if out is None:
+                out = torch.empty((x.shape[0], n), dtype=torch.float64, device=x.device)
+            check(self._lib.kofft_cuda_irfft_f64(self.ctx.handle, x.data_ptr(), out.data_ptr(), n, x.shape[0], _stream_of(x)))
+            return out
+        a = _c128(np.ascontiguousarray(x))
+        if a.shape[1] != n // 2 + 1:
+            raise MismatchedLengths()
+        o = np.empty((a.shape[0], n), dtype=np.float64) if out is None else out
+        check(self._lib.kofft_cuda_irfft_batch_host_f64(self.ctx.handle, a.ctypes.data, n, a.shape[0], o.ctypes.data))
+        return o
 
     def fft_batch(self, x, inverse: bool = False, out=None):
         """Dense rows [batch][n]: numpy complex128 (in place, host path) or CUDA torch.complex128."""

@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
             "kofft_oracle_twiddles_f64": (None, [sz, fp]),
             "kofft_oracle_fft_f64": (ip, [fp, sz, ip]),
             "kofft_oracle_fft_batch_f64": (ip, [fp, sz, sz, ip, ip]),
+            "kofft_oracle_rfft_twiddles_f64": (None, [sz, fp]),
+            "kofft_oracle_rfft_batch_f64": (ip, [fp, sz, sz, fp, ip]),
         }
         for name, (res, args) in sigs.items():
             f = getattr(_lib, name)
@@ -186,6 +188,28 @@ def fft_batch_f64_inplace(a: np.ndarray, inverse: bool = False, nthreads: int = 
     """Timed-baseline entry: no copies."""
     assert a.dtype == np.complex128 and a.flags.c_contiguous and a.ndim == 2
     _chk(lib().kofft_oracle_fft_batch_f64(_p(a), a.shape[1], a.shape[0], int(inverse), nthreads))
+
+
+def rfft_twiddles_f64(m: int) -> np.ndarray:
+    out = np.empty(max(m, 1), dtype=np.complex128)
+    lib().kofft_oracle_rfft_twiddles_f64(m, _p(out))
+    return out[:m]
+
+
+def rfft_batch_f64(x) -> np.ndarray:
+    a = np.ascontiguousarray(np.array(x, dtype=np.float64, copy=True))
+    assert a.ndim == 2
+    out = np.zeros((a.shape[0], a.shape[1] // 2 + 1), dtype=np.complex128)
+    _chk(lib().kofft_oracle_rfft_batch_f64(_p(a), a.shape[1], a.shape[0], _p(out), 0))
+    return out
+
+
+def irfft_batch_f64(x, n: int) -> np.ndarray:
+    a = _c128(x)
+    assert a.ndim == 2 and a.shape[1] == n // 2 + 1
+    out = np.zeros((a.shape[0], n), dtype=np.float64)
+    _chk(lib().kofft_oracle_rfft_batch_f64(_p(a), n, a.shape[0], _p(out), 1))
+    return out
 
 
 # ---- real -------------------------------------------------------------------------------

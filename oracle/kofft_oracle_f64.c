@@ -290,3 +290,92 @@ KO_API int kofft_oracle_fft_batch_f64(double *data, size_t n, size_t batch, int 
     free(th); free(jobs);
     return rc;
 }
+
+/* ---- real transforms for f64: src/rfft.rs:172-183 (table), 425-465 (rfft_direct), 468-508 (irfft_direct) ---- */
+
+/* build_twiddle_table::<f64>.  out: m complex, T'[k] = exp(-i pi k / m) by current = current.mul(w). */
+KO_API void kofft_oracle_rfft_twiddles_f64(size_t m, double *out)
+{
+    double angle = -3.14159265358979323846 / (double)(float)m; /* -T::pi() / T::from_f32(m as f32) */
+    c64 w = z_new(cos(angle), sin(angle));
+    c64 cur = z_new(1.0, 0.0);
+    for (size_t k = 0; k < m; k++) {
+        out[2 * k] = cur.re;
+        out[2 * k + 1] = cur.im;
+        cur = z_mul(cur, w);
+    }
+}
+
+static int kd_rfft(kd_plan *p, const double *input, size_t n, c64 *output, const c64 *tw)
+{
+    if (n == 0) return KO_EMPTY_INPUT;
+    if (n % 2 != 0) return 6; /* InvalidValue */
+    size_t m = n / 2;
+    c64 *scratch = (c64 *)malloc((m ? m : 1) * sizeof(c64));
+    if (!scratch) return -1;
+    for (size_t i = 0; i < m; i++) output[i] = z_new(input[2 * i], input[2 * i + 1]); /* :444-446 */
+    int rc = kd_fft(p, output, m);
+    if (rc) { free(scratch); return rc; }
+    memcpy(scratch, output, m * sizeof(c64));
+    c64 y0 = scratch[0];
+    output[0] = z_new(y0.re + y0.im, 0.0);
+    output[m] = z_new(y0.re - y0.im, 0.0);
+    double half = (double)0.5f;
+    for (size_t k = 1; k < m; k++) { /* :454-462 */
+        c64 a = scratch[k];
+        c64 b = z_new(scratch[m - k].re, -scratch[m - k].im);
+        c64 sum = z_add(a, b), diff = z_sub(a, b);
+        c64 t = z_mul(tw[k], diff);
+        c64 temp = z_add(sum, z_new(t.im, -t.re));
+        output[k] = z_new(temp.re * half, temp.im * half);
+    }
+    free(scratch);
+    return KO_OK;
+}
+
+static int kd_irfft(kd_plan *p, const c64 *input, double *output, size_t n, const c64 *tw)
+{
+    if (n == 0) return KO_EMPTY_INPUT;
+    if (n % 2 != 0) return 6;
+    size_t m = n / 2;
+    c64 *scratch = (c64 *)malloc((m ? m : 1) * sizeof(c64));
+    if (!scratch) return -1;
+    double half = (double)0.5f;
+    scratch[0] = z_new((input[0].re + input[m].re) * half, (input[0].re - input[m].re) * half); /* :486-489 */
+    for (size_t k = 1; k < m; k++) { /* :490-498 */
+        c64 a = input[k];
+        c64 b = z_new(input[m - k].re, -input[m - k].im);
+        c64 sum = z_add(a, b), diff = z_sub(a, b);
+        c64 w = z_new(tw[k].re, -tw[k].im);
+        c64 t = z_mul(w, diff);
+        c64 temp = z_sub(sum, z_new(t.im, -t.re));
+        scratch[k] = z_new(temp.re * half, temp.im * half);
+    }
+    int rc = kd_ifft(p, scratch, m);
+    if (rc) { free(scratch); return rc; }
+    for (size_t i = 0; i < m; i++) { output[2 * i] = scratch[i].re; output[2 * i + 1] = scratch[i].im; }
+    free(scratch);
+    return KO_OK;
+}
+
+/* rows dense: in [batch][n] doubles -> out [batch][n/2+1] complex (inverse = 0), or the reverse (inverse = 1) */
+KO_API int kofft_oracle_rfft_batch_f64(const double *in, size_t n, size_t batch, double *out, int inverse)
+{
+    if (n == 0) return KO_EMPTY_INPUT;
+    if (n % 2 != 0) return 6;
+    size_t m = n / 2;
+    c64 *tw = (c64 *)malloc((m ? m : 1) * sizeof(c64));
+    if (!tw) return -1;
+    kofft_oracle_rfft_twiddles_f64(m, (double *)tw);
+    kd_plan p; memset(&p, 0, sizeof p);
+    int rc = KO_OK;
+    for (size_t r = 0; r < batch && !rc; r++) {
+        if (inverse)
+            rc = kd_irfft(&p, (const c64 *)in + r * (m + 1), out + r * n, n, tw);
+        else
+            rc = kd_rfft(&p, in + r * n, n, (c64 *)out + r * (m + 1), tw);
+    }
+    kd_plan_free(&p);
+    free(tw);
+    return rc;
+}

@@ -133,6 +133,20 @@ def _f64_split(self, n, rows, re, im, ore, oim, table, inverse=False, grid=2):
 EmuKernels.f64_split = _f64_split
 
 
+def _f64_real(self, m, rows, inp, out, table, rtw, which, grid=2, staged=False):
+    """CtaFftD::run over IoRfftD (which = 1) / IoIrfftD (which = 2); m = n/2 is the engine length."""
+    self.lib.kofft_emuk_set_f64_staged(int(staged))
+    f = self.lib.kofft_emuk_f64_real
+    f.restype = C.c_int
+    f.argtypes = [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+    rc = f(m, rows, inp.ctypes.data, out.ctypes.data, which, 1.0 / float(np.float32(m)),
+           table.ctypes.data if table is not None else None, rtw.ctypes.data, grid)
+    assert rc == 0, rc
+
+
+EmuKernels.f64_real = _f64_real
+
+
 def _bind_istft(lib):
     f = lib.kofft_emuk_istft_fused
     f.restype = C.c_int

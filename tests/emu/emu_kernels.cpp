@@ -328,6 +328,7 @@ template <class IO>
 static int run_f64_io(const IO &io, long n, const double *table, long rows, int grid)
 {
     switch (n) {
+    case 1: return run_f64_small<1>(io, rows);
     case 2: return run_f64_small<2>(io, rows);
     case 4: return run_f64_small<4>(io, rows);
     case 8: return run_f64_small<8>(io, rows);
@@ -353,6 +354,23 @@ API int kofft_emuk_f64_split(long n, long rows, const double *in_re, const doubl
         IoGenericD<false> io{in_re, in_im, out_re, out_im, 1, n, 1, n, scale};
         rc = run_f64_io(io, n, table, rows, grid);
     }
+    g_f64_staged = keep;
+    return rc;
+}
+
+// f64 real transforms: m = n/2 is the engine length; which = 1 rfft (in [rows][n] doubles, out [rows][m+1] complex),
+// 2 irfft (the reverse); rtw: T' table of m entries
+API int kofft_emuk_f64_real(long m, long rows, const void *in, void *out, int which, double scale, const double *table,
+                            const double *rtw, int grid)
+{
+    if (which == 1) {
+        IoRfftD io{(const double2 *)in, (double2 *)out, (const double2 *)rtw, m};
+        return run_f64_io(io, m, table, rows, grid);
+    }
+    const bool keep = g_f64_staged;
+    g_f64_staged = false;
+    IoIrfftD io{(const double2 *)in, (double2 *)out, (const double2 *)rtw, m, scale};
+    int rc = run_f64_io(io, m, table, rows, grid);
     g_f64_staged = keep;
     return rc;
 }

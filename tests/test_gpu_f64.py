@@ -141,3 +141,49 @@ def test_f64_split_strided_surface(fft64, oracle):
     assert np.array_equal(dst, want)
     with pytest.raises(InvalidStride):
         fft64.fft_out_of_place_strided(src, 0, dst, 5)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 256, 2048, 4096, 8192, 16384])
+def test_f64_rfft_irfft_bit_exact(fft64, oracle, n):
+    """RealFftImpl<f64>: rfft / irfft for every supported length, host and device paths, against the
+    f64 oracle bit for bit; tests/rfft_dispatch.rs round trip."""
+    import torch
+
+    rng = np.random.default_rng(700 + n)
+    rows = 9
+    x = rng.uniform(-1, 1, (rows, n))
+    ref = oracle.rfft_batch_f64(x)
+    y = fft64.rfft_batch(x)
+    assert np.array_equal(y, ref), n
+    back = oracle.irfft_batch_f64(ref, n)
+    assert np.array_equal(fft64.irfft_batch(ref, n), back), n
+    dx = torch.from_numpy(x).cuda()
+    dy = fft64.rfft_batch(dx)
+    dz = fft64.irfft_batch(dy, n)
+    torch.cuda.synchronize()
+    assert np.array_equal(dy.cpu().numpy(), ref) and np.array_equal(dz.cpu().numpy(), back)
+    one_out = np.zeros(n // 2 + 1, np.complex128)
+    fft64.rfft(x[0].copy(), one_out)
+    assert np.array_equal(one_out, ref[0])
+    one_back = np.zeros(n, np.float64)
+    fft64.irfft(one_out, one_back)
+    assert np.array_equal(one_back, back[0])
+
+
+def test_f64_rfft_reference_checks_and_errors(fft64, oracle):
+    import kofft_b200
+    from kofft_b200.errors import EmptyInput, InvalidValue, MismatchedLengths
+
+    x = np.array([1.0, 2.0, 3.0, 4.0])
+    freq = np.zeros(3, np.complex128)
+    fft64.rfft(x.copy(), freq)
+    out = np.zeros(4)
+    fft64.irfft(freq, out)
+    assert np.abs(out - x).max() < 1e-10  # tests/rfft_dispatch.rs:24-41
+    assert np.array_equal(kofft_b200.RfftPlanner64().get_twiddles(4096), oracle.rfft_twiddles_f64(4096))
+    with pytest.raises(EmptyInput):
+        fft64.rfft(np.zeros(0), np.zeros(1, np.complex128))
+    with pytest.raises(InvalidValue):
+        fft64.rfft(np.zeros(7), np.zeros(4, np.complex128))
+    with pytest.raises(MismatchedLengths):
+        fft64.rfft(np.zeros(8), np.zeros(4, np.complex128))

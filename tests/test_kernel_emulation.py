@@ -277,3 +277,23 @@ def test_f64_split_rows_kernel_body(emuk, oracle, n):
         ore, oim = np.zeros_like(re), np.zeros_like(im)
         emuk.f64_split(n, rows, re, im, ore, oim, tab, inverse=inverse)
         assert np.array_equal(ore, ref.real) and np.array_equal(oim, ref.imag), (n, inverse)
+
+
+@pytest.mark.parametrize("n", [2, 8, 32, 64, 512, 4096, 16384])
+def test_f64_rfft_irfft_kernel_body(emuk, oracle, n):
+    """IoRfftD (twist behind one more exchange; staged variant) and IoIrfftD (untwist at the load)
+    against the f64 oracle, bit for bit."""
+    m = n // 2
+    rng = np.random.default_rng(256 + n)
+    rows = 5 if n <= 4096 else 2
+    x = rng.uniform(-1, 1, (rows, n))
+    tab = oracle.twiddles_f64(m) if m >= 32 else None
+    rtw = oracle.rfft_twiddles_f64(m)
+    ref = oracle.rfft_batch_f64(x)
+    for staged in ((False, True) if m >= 32 else (False,)):
+        y = np.zeros((rows, m + 1), np.complex128)
+        emuk.f64_real(m, rows, x, y, tab, rtw, 1, grid=2, staged=staged)
+        assert np.array_equal(y, ref), (n, staged)
+    z = np.zeros((rows, n), np.float64)
+    emuk.f64_real(m, rows, ref, z, tab, rtw, 2, grid=1)
+    assert np.array_equal(z, oracle.irfft_batch_f64(ref, n)), n

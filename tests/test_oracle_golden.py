@@ -301,3 +301,20 @@ def test_f64_twiddle_table_and_errors(oracle):
     with pytest.raises(oracle.OracleError) as e:
         oracle.fft_f64(np.zeros(0, np.complex128))
     assert e.value.variant == "EmptyInput"
+
+
+def test_f64_rfft_roundtrip_dispatch(oracle):
+    """tests/rfft_dispatch.rs:24-41: rfft then irfft of [1, 2, 3, 4] in f64 returns the input within 1e-10;
+    plus agreement with numpy and the table's first entries."""
+    x = np.array([[1.0, 2.0, 3.0, 4.0]])
+    y = oracle.rfft_batch_f64(x)
+    assert np.allclose(y, np.fft.rfft(x, axis=1), atol=1e-12)
+    assert np.abs(oracle.irfft_batch_f64(y, 4) - x).max() < 1e-10
+    for n in (64, 1024, 16384):
+        rng = np.random.default_rng(n)
+        x = rng.uniform(-1, 1, (2, n))
+        y = oracle.rfft_batch_f64(x)
+        assert np.linalg.norm(y - np.fft.rfft(x, axis=1)) / np.linalg.norm(y) < 1e-11
+        assert np.abs(oracle.irfft_batch_f64(y, n) - x).max() < 1e-11
+    t = oracle.rfft_twiddles_f64(8)
+    assert t[0] == 1.0 and abs(t[1] - np.exp(-1j * np.pi / 8)) < 1e-15  # tests/rfft_twiddles.rs for f64
