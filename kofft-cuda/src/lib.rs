@@ -29,6 +29,8 @@ extern "C" {
     fn kofft_cuda_fft_batch_host_f32(ctx: *mut RawCtx, data: *mut f32, n: usize, batch: usize, inverse: c_int) -> c_int;
     fn kofft_cuda_fft_host_f64(ctx: *mut RawCtx, data: *mut f64, n: usize, inverse: c_int) -> c_int;
     fn kofft_cuda_fft_batch_host_f64(ctx: *mut RawCtx, data: *mut f64, n: usize, batch: usize, inverse: c_int) -> c_int;
+    fn kofft_cuda_rfft_batch_host_f64(ctx: *mut RawCtx, input: *const f64, n: usize, batch: usize, output: *mut f64) -> c_int;
+    fn kofft_cuda_irfft_batch_host_f64(ctx: *mut RawCtx, input: *const f64, n: usize, batch: usize, output: *mut f64) -> c_int;
     fn kofft_cuda_fft_split_host_f64(ctx: *mut RawCtx, re: *mut f64, re_len: usize, im: *mut f64, im_len: usize,
                                      inverse: c_int) -> c_int;
     fn kofft_cuda_fft_strided_host_f64(ctx: *mut RawCtx, input: *mut f64, input_len: usize, stride: usize, n: usize,
@@ -293,6 +295,33 @@ impl CudaFftImpl64 {
         }
         check(unsafe {
             kofft_cuda_fft_batch_host_f64(self.ctx, rows.as_mut_ptr() as *mut f64, n, rows.len() / n, inverse as c_int)
+        })
+    }
+}
+
+impl CudaFftImpl64 {
+    /// Fused pack + FFT + twist per row: `[batch][n]` reals -> `[batch][n/2+1]` bins (`rfft` / `irfft` one at a
+    /// time arrive through kofft's blanket `RealFftImpl<f64>`, src/rfft.rs:837).
+    pub fn rfft_batch(&self, input: &[f64], n: usize, output: &mut [Complex64]) -> Result<(), FftError> {
+        if n == 0 {
+            return Err(FftError::EmptyInput);
+        }
+        if input.len() % n != 0 || output.len() != input.len() / n * (n / 2 + 1) {
+            return Err(FftError::MismatchedLengths);
+        }
+        check(unsafe {
+            kofft_cuda_rfft_batch_host_f64(self.ctx, input.as_ptr(), n, input.len() / n, output.as_mut_ptr() as *mut f64)
+        })
+    }
+    pub fn irfft_batch(&self, input: &[Complex64], n: usize, output: &mut [f64]) -> Result<(), FftError> {
+        if n == 0 {
+            return Err(FftError::EmptyInput);
+        }
+        if output.len() % n != 0 || input.len() != output.len() / n * (n / 2 + 1) {
+            return Err(FftError::MismatchedLengths);
+        }
+        check(unsafe {
+            kofft_cuda_irfft_batch_host_f64(self.ctx, input.as_ptr() as *const f64, n, output.len() / n, output.as_mut_ptr())
         })
     }
 }
