@@ -97,6 +97,13 @@ def main():
                 ms, best = timeit(lambda: fft64.fft_batch(x, out=y), 10)
                 report(f"c2c_f64_{n}x{rows}", "f64", ms, best, 2 * x.numel() * 16)
                 del x, y
+            for n in (4096, 16384):
+                rows = 2 ** 27 // n
+                x = (torch.rand((rows, n), generator=g, device="cuda", dtype=torch.float64) * 2 - 1).contiguous()
+                y = torch.empty((rows, n // 2 + 1), dtype=torch.complex128, device="cuda")
+                ms, best = timeit(lambda: fft64.rfft_batch(x, out=y), 10)
+                report(f"rfft_f64_{n}x{rows}", "f64", ms, best, x.numel() * 8 + y.numel() * 16)
+                del x, y
         modes = [("pipelined", 2), ("two_kernel", 0), ("cluster", 1)]
         if "rfft" in which:
             x = (torch.rand((16384, 65536), generator=g, device="cuda") * 2 - 1).contiguous()
