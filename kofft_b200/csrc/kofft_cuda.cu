@@ -320,6 +320,10 @@ cudaStream_t pick_stream(kofft_cuda_ctx *, void *stream)
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // transforms per CTA of the single-CTA engine (Plan<L, min_cta>::TPC; 16 elements per thread)
+// bytes of landing zone per point of a staged STFT group: the complex-sized stage holds real samples, and with the
+// two-deep prefetch (or the half-size stage) a group may use only half of it
+constexpr long kStftStageBytesPerPoint = (IoTraits<IoStft>::kDeepStage || IoTraits<IoStft>::kStageHalf) ? 4 : 8;
+
 long tpc_of(size_t n, int min_cta = 256)
 {
     const size_t per_cta = static_cast<size_t>(min_cta) * 16;
@@ -739,7 +743,7 @@ int kofft_cuda_stft_f32(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, 
     // TMA staging needs 16-byte aligned, whole-float4 segments that never straddle a channel
     const long tpc = tpc_of(win_len, IoTraits<IoStft>::kMinCta);
     const bool staged = aligned16(d_signal) && len % 4 == 0 && hop % 4 == 0 && nframes % tpc == 0 &&
-                        ((tpc - 1) * static_cast<long>(hop) + static_cast<long>(win_len)) * 4 <= tpc * static_cast<long>(win_len) * 8;
+                        ((tpc - 1) * static_cast<long>(hop) + static_cast<long>(win_len)) * 4 <= tpc * static_cast<long>(win_len) * kStftStageBytesPerPoint;
     return dispatch(ctx, KIND_STFT, io, win_len, channels * nframes, pick_stream(ctx, stream), staged);
 }
 
@@ -760,7 +764,7 @@ int kofft_cuda_stft_magnitudes_f32(kofft_cuda_ctx *ctx, const float *d_signal, s
         return fail_msg(-static_cast<int>(cudaErrorNotSupported), "fused stft magnitudes need win_len >= 32");
     const long tpc = tpc_of(win_len, IoTraits<IoStftMag>::kMinCta);
     const bool staged = aligned16(d_signal) && len % 4 == 0 && hop % 4 == 0 && nframes % tpc == 0 &&
-                        ((tpc - 1) * static_cast<long>(hop) + static_cast<long>(win_len)) * 4 <= tpc * static_cast<long>(win_len) * 8;
+                        ((tpc - 1) * static_cast<long>(hop) + static_cast<long>(win_len)) * 4 <= tpc * static_cast<long>(win_len) * kStftStageBytesPerPoint;
     // one launch per channel: each has its own running maximum
     for (size_t c = 0; c < channels; c++) {
         IoArgs io;
@@ -1030,7 +1034,7 @@ int stft_launch_frames(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, s
     io.p2 = static_cast<long>(hop);
     const long tpc = tpc_of(win_len, IoTraits<IoStft>::kMinCta);
     const bool staged = aligned16(d_signal) && len % 4 == 0 && hop % 4 == 0 && nframes % tpc == 0 &&
-                        ((tpc - 1) * static_cast<long>(hop) + static_cast<long>(win_len)) * 4 <= tpc * static_cast<long>(win_len) * 8;
+                        ((tpc - 1) * static_cast<long>(hop) + static_cast<long>(win_len)) * 4 <= tpc * static_cast<long>(win_len) * kStftStageBytesPerPoint;
     return dispatch(ctx, KIND_STFT, io, win_len, channels * nframes, s, staged);
 }
 int stream_grow(float **buf, size_t *have, size_t want)
