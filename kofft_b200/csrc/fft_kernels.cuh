@@ -408,11 +408,11 @@ struct IoIrfft {
 #ifndef KOFFT_STFT_BLOCKS
 #define KOFFT_STFT_BLOCKS 0
 #endif
-// STFT: the stage holds real samples (half of the complex-sized allocation), so it is split into two
-// landing zones and the TMA prefetch runs TWO row groups ahead (the one-deep prefetch left 3.8 % of the
-// warp time waiting for the samples, profiles/r02m)
+// STFT build knob: the stage holds real samples (half of the complex-sized allocation), so it can be split
+// into two landing zones with the TMA prefetch running TWO row groups ahead.  Measured (profiles/r02n):
+// no gain over the one-deep prefetch (exact 16.43 vs 16.49 ms, fast 14.89 vs 14.73 ms median of 24), so off.
 #ifndef KOFFT_STFT_DEEP_STAGE
-#define KOFFT_STFT_DEEP_STAGE 1
+#define KOFFT_STFT_DEEP_STAGE 0
 #endif
 template <class IO>
 struct IoTraits {
