@@ -70,7 +70,8 @@ int kofft_cuda_set_tma_staging(kofft_cuda_ctx *ctx, int enable);
  * run (default 128).  Disabled or out of range -> two kernels with an f32 intermediate. */
 int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames);
 /* N > 16384 (rfft above 32768): which of the three implementations of the two-pass split runs.
- *   mode 3 (default): mode 2 for rfft (where it measured faster, profiles/r02a), mode 0 otherwise.
+ *   mode 3 (default): mode 2 for rfft and irfft (where it measured faster: rfft 2^16 4.06 vs 4.29 ms, irfft 4.40 vs
+ *          6.11 ms, profiles/r02a, r02p), mode 0 otherwise.
  *   mode 2: one persistent cooperative kernel; teams of 8 / 16 CTAs run pass A two transforms ahead
  *          of pass B behind dependency flags, and the intermediate (4 transforms per team) is pinned
  *          in L2, so HBM sees the rows once in and once out.

@@ -98,7 +98,7 @@ struct kofft_cuda_ctx {
     // N > 16384 default: one persistent cooperative kernel, per-team dependency flags, intermediate
     // pinned in L2 (fft_large.cuh LargePipe)
     bool large_pipe = true;
-    bool large_auto = true; // pipelined kernel only where it measured faster (rfft), two kernels otherwise
+    bool large_auto = true; // pipelined kernel only where it measured faster (rfft, irfft), two kernels otherwise
     unsigned *pipe_flags = nullptr;
     bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
     int istft_run_frames = 128;
@@ -222,7 +222,7 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
                 }
             const size_t row_bytes = n * sizeof(float2);
             void *scratch = nullptr;
-            if (ctx->large_pipe && !ctx->large_fused && (!ctx->large_auto || kind == KIND_RFFT)) {
+            if (ctx->large_pipe && !ctx->large_fused && (!ctx->large_auto || kind == KIND_RFFT || kind == KIND_IRFFT)) {
                 const int nkb = L == 15 ? 8 : 16;
                 const int max_teams = kMaxPipeCtasPerSm * ctx->num_sms / nkb;
                 rc = ensure_ws(ctx, 4, size_t(kLargePipeSlots) * max_teams * row_bytes, &scratch);

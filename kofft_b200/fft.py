@@ -108,7 +108,7 @@ class Context:
     LARGE_TWO_KERNEL, LARGE_CLUSTER, LARGE_PIPELINED, LARGE_AUTO = 0, 1, 2, 3
 
     def set_large_mode(self, mode: int) -> None:
-        """N > 16384: 3 = auto (default: pipelined for rfft, two kernels otherwise), 2 = persistent pipelined
+        """N > 16384: 3 = auto (default: pipelined for rfft / irfft, two kernels otherwise), 2 = persistent pipelined
         kernel, 0 = two kernels per chunk, 1 = cluster kernel."""
         check(_lib.lib().kofft_cuda_set_large_mode(self.handle, int(mode)))
 
