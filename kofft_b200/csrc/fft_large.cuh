@@ -601,23 +601,12 @@ struct LargePipe {
     // rows: transforms in the batch; scratch: teams * SLOTS * n complex; flags: teams * FLAG_STRIDE
     // counters, zero at launch.  gridDim.x is a multiple of NKB and every CTA is resident.
     static KD void run(const IO &io, const Tw0 &tw0, const float2 *__restrict__ table, long rows,
-                       float2 *__restrict__ scratch, float2 *smem, unsigned *flags, int pair_stride = 0)
+                       float2 *__restrict__ scratch, float2 *smem, unsigned *flags)
     {
         const int tid = threadIdx.x;
         const long n = 1L << (LARGE_S1 + LB);
-        // Team membership.  Default: NKB consecutive CTAs.  pair_stride = S > 0 (the host passes the SM count
-        // when the grid is exactly two CTAs per SM and S is a multiple of NKB/2): CTAs b and b + S, which the
-        // block scheduler places on the same SM, join the SAME team, so a team occupies NKB/2 whole SMs and no
-        // SM hosts two teams -- the teams no longer couple into one machine-wide pace through shared SMs.
-        // (Placement is a performance assumption only: any bijection of CTAs onto (team, member) is correct.)
-        int kb = blockIdx.x % NKB; // column tile of pass A == k-block of pass B
-        long team = blockIdx.x / NKB;
-        const long teams = gridDim.x / NKB;
-        if (pair_stride > 0) {
-            const int sm = blockIdx.x % pair_stride, wave = blockIdx.x / pair_stride;
-            team = sm / (NKB / 2);
-            kb = sm % (NKB / 2) + wave * (NKB / 2);
-        }
+        const int kb = blockIdx.x % NKB; // column tile of pass A == k-block of pass B
+        const long team = blockIdx.x / NKB, teams = gridDim.x / NKB;
         // per team and per intermediate slot: arrivals of pass-A tiles / of pass-B tiles.  One counter per
         // SLOT, not per team: a member may run up to two steps ahead of another, and a single running
         // count would let its early arrivals stand in for a late member's missing one (seen on the GPU as
@@ -756,10 +745,10 @@ __global__ void __launch_bounds__(256, 2)
 template <int LB, bool EXACT, class IO, int EPI, bool STAGED>
 __global__ void __launch_bounds__(256, 2)
     large_pipe_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0 tw0, const float2 *__restrict__ table,
-                      long rows, float2 *__restrict__ scratch, unsigned *flags, int pair_stride)
+                      long rows, float2 *__restrict__ scratch, unsigned *flags)
 {
     extern __shared__ __align__(128) float2 smem[];
-    LargePipe<LB, EXACT, IO, EPI, STAGED>::run(io, tw0, table, rows, scratch, smem, flags, pair_stride);
+    LargePipe<LB, EXACT, IO, EPI, STAGED>::run(io, tw0, table, rows, scratch, smem, flags);
 }
 #endif
 

@@ -149,11 +149,7 @@ cudaError_t launch_pipe_v(const IO &io, const LaunchArgs &a, LargeArgs &g)
     float2 *scratch = g.scratch;
     unsigned *flags = g.flags;
     const float2 *table = a.table;
-    // two CTAs per SM on every SM: pair the co-resident CTAs into the same team (see LargePipe::run)
-    int pair_stride = 0;
-    if (g.pipe_pair && per_sm == 2 && teams * F::NKB == 2L * a.num_sms && a.num_sms % (F::NKB / 2) == 0) pair_stride = a.num_sms;
-    void *args[] = {(void *)&io, (void *)&a.tw0, (void *)&table, (void *)&rows, (void *)&scratch, (void *)&flags,
-                    (void *)&pair_stride};
+    void *args[] = {(void *)&io, (void *)&a.tw0, (void *)&table, (void *)&rows, (void *)&scratch, (void *)&flags};
     e = cudaMemsetAsync(flags, 0, sizeof(unsigned) * F::FLAG_STRIDE * teams, a.stream);
     if (e != cudaSuccess) return e;
     g.launches = 1;

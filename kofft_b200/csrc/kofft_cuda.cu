@@ -100,7 +100,6 @@ struct kofft_cuda_ctx {
     bool large_pipe = true;
     bool large_auto = true; // pipelined kernel only where it measured faster (rfft, irfft), two kernels otherwise
     unsigned *pipe_flags = nullptr;
-    bool pipe_pair = true; // KOFFT_LARGE_PIPE_PAIR=0: teams of consecutive CTAs even on a full grid
     bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
     int istft_run_frames = 128;
     // host-pointer batch entry points: the batch is cut into chunks that flow through three
@@ -238,7 +237,6 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
                 g.fused = false;
                 g.pipe = true;
                 g.pipe_max_teams = max_teams;
-                g.pipe_pair = ctx->pipe_pair;
                 g.flags = ctx->pipe_flags;
                 e = launch_large_fft(L, a, g);
                 if (e == cudaSuccess) {
@@ -354,7 +352,6 @@ int kofft_cuda_create(kofft_cuda_ctx **out, int device)
     if (const char *mb = getenv("KOFFT_LARGE_SCRATCH_MB"))
         if (atoi(mb) > 0) ctx->large_scratch_bytes = size_t(atoi(mb)) << 20;
     // N > 16384 path selection and tuning knobs (see kofft_cuda_set_large_mode)
-    if (const char *v = getenv("KOFFT_LARGE_PIPE_PAIR")) ctx->pipe_pair = atoi(v) != 0;
     if (const char *m = getenv("KOFFT_LARGE_MODE")) {
         ctx->large_auto = strcmp(m, "auto") == 0;
         ctx->large_pipe = ctx->large_auto || strcmp(m, "pipe") == 0;

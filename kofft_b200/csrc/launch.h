@@ -77,7 +77,6 @@ struct LargeArgs {
     // pipe_max_teams * kLargePipeSlots * 2^L complex, flags = pipe_max_teams * kPipeFlagStride counters
     bool pipe = false;
     int pipe_max_teams = 0;
-    bool pipe_pair = true;     // co-resident CTAs join the same team when the grid is two CTAs on every SM
     unsigned *flags = nullptr;
     int launches = 0;          // out: kernels launched
 };
