@@ -154,6 +154,24 @@ def cpu_port_gflops(rows: int, reps: int, threads: int) -> tuple[float, float]:
     return FLOPS_PER_TRANSFORM * rows * reps / dt / 1e9, dt
 
 
+def cpu_port_stft_frames_per_s(threads: int, fresh_planner: bool) -> tuple[float, str]:
+    """kofft's CPU STFT (oracle port) on a bounded sample of configs[3]: 16 channels x 60 s of 48 kHz audio,
+    Hann 2048 / hop 512, channels split over `threads` cores.  fresh_planner = a new planner + twiddle table
+    per frame, which is what `stft::parallel` does (src/stft.rs:260); False = one shared table (fair)."""
+    from oracle import kofft_oracle as ko
+
+    ko.build()
+    ch, length, hop, win = 16, 2_880_000, 512, 2048
+    nframes = -(-length // hop)
+    rng = np.random.default_rng(2)
+    sig = rng.uniform(-1, 1, (ch, length)).astype(np.float32)
+    w = ko.hann(win)
+    t0 = time.perf_counter()
+    ko.stft_batch(sig, w, hop, nframes, fresh_planner=fresh_planner, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return ch * nframes / dt, f"{ch} ch x {length} samples ({ch * nframes} frames, {dt:.1f} s), {threads} threads over channels"
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -377,7 +395,18 @@ def run_gpu(args) -> None:
         # frame minus the real-input shortcuts (8 %), 128 lanes per SM and clock
         fma_floor_ms = {mhz: 10 * 0.92 * (win // 2) * 11 * ch * nframes / (128 * 148 * mhz * 1e6) * 1e3
                         for mhz in (stft_clocks.get("sm_mhz") or 1965, 1965)}
+        cpu_stft = {}
+        if rank == 0:
+            try:
+                threads_c = os.cpu_count() or 1
+                fps_shared, smp = cpu_port_stft_frames_per_s(threads_c, False)
+                fps_fresh, _ = cpu_port_stft_frames_per_s(threads_c, True)
+                cpu_stft = {"frames_per_s_shared_table": fps_shared, "frames_per_s_fresh_planner_per_frame": fps_fresh,
+                            "cores": threads_c, "kind": "port", "sample": smp}
+            except Exception as e:  # pragma: no cover
+                cpu_stft = {"error": repr(e)}
         extra["stft"] = {"workload": f"Hann {win}, hop {hop}, {ch} ch x {length} samples (BASELINE configs[3])",
+                         "cpu_baseline": cpu_stft,
                          "frames_per_s": ch * nframes / (ms * 1e-3), "ms": ms, "hbm_gbs": algo / ms / 1e6,
                          "frac_of_measured_peak": algo / ms / 1e6 / peak, "clocks": stft_clocks,
                          "fp32_floor_ms_at_measured_clock": fma_floor_ms[stft_clocks.get("sm_mhz") or 1965],
