@@ -408,12 +408,6 @@ struct IoIrfft {
 #ifndef KOFFT_STFT_BLOCKS
 #define KOFFT_STFT_BLOCKS 0
 #endif
-// STFT build knob: the stage holds real samples (half of the complex-sized allocation), so it can be split
-// into two landing zones with the TMA prefetch running TWO row groups ahead.  Measured (profiles/r02n):
-// no gain over the one-deep prefetch (exact 16.43 vs 16.49 ms, fast 14.89 vs 14.73 ms median of 24), so off.
-#ifndef KOFFT_STFT_DEEP_STAGE
-#define KOFFT_STFT_DEEP_STAGE 0
-#endif
 template <class IO>
 struct IoTraits {
     static constexpr bool kRealInput = false;
@@ -424,7 +418,6 @@ struct IoTraits {
     static constexpr bool kTw1Smem = false; // pass-1 twiddles from shared memory (staged kernel only)
     static constexpr bool kStageHalf = false; // the staged input is real: N*4 bytes per transform
     static constexpr int kMinBlocks = 0;    // CTAs per SM to compile for (0 = 512 / CTA)
-    static constexpr bool kDeepStage = false; // two half-size landing zones, prefetch two groups ahead
 };
 template <bool INV>
 struct IoTraits<IoC2C<INV>> {
@@ -436,7 +429,6 @@ struct IoTraits<IoC2C<INV>> {
     static constexpr bool kTw1Smem = false;
     static constexpr bool kStageHalf = false;
     static constexpr int kMinBlocks = 0;
-    static constexpr bool kDeepStage = false;
 };
 template <bool EXACT>
 struct IoTraits<IoRfft<EXACT>> {
@@ -448,7 +440,6 @@ struct IoTraits<IoRfft<EXACT>> {
     static constexpr bool kTw1Smem = false;
     static constexpr bool kStageHalf = false;
     static constexpr int kMinBlocks = 0;
-    static constexpr bool kDeepStage = false;
 };
 template <>
 struct IoTraits<IoStft> {
@@ -460,7 +451,6 @@ struct IoTraits<IoStft> {
     static constexpr bool kTw1Smem = KOFFT_STFT_TW1_SMEM != 0;
     static constexpr bool kStageHalf = KOFFT_STFT_TW1_SMEM != 0;
     static constexpr int kMinBlocks = KOFFT_STFT_BLOCKS;
-    static constexpr bool kDeepStage = KOFFT_STFT_DEEP_STAGE != 0 && KOFFT_STFT_TW1_SMEM == 0;
 };
 template <>
 struct IoTraits<IoStftMag> {
@@ -472,7 +462,6 @@ struct IoTraits<IoStftMag> {
     static constexpr bool kTw1Smem = KOFFT_STFT_TW1_SMEM != 0;
     static constexpr bool kStageHalf = KOFFT_STFT_TW1_SMEM != 0;
     static constexpr int kMinBlocks = KOFFT_STFT_BLOCKS;
-    static constexpr bool kDeepStage = KOFFT_STFT_DEEP_STAGE != 0 && KOFFT_STFT_TW1_SMEM == 0;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -564,18 +553,12 @@ struct CtaFft {
         float2 *buf1 = P::NBUF == 2 ? buf0 + P::TPC * P::PADN : buf0;
         int par = 0;
         __shared__ __align__(8) unsigned long long mbar;
-        __shared__ __align__(8) unsigned long long mbar_b; // DEEP: the second landing zone's barrier
-        unsigned phase = 0, phase_b = 0;
+        unsigned phase = 0;
         const long groups = (rows + P::TPC - 1) / P::TPC;
-        // DEEP: two landing zones of STAGE_B / 2 bytes used alternately, each refilled for the group TWO steps ahead
-        constexpr bool DEEP = STAGED && IoTraits<IO>::kDeepStage;
-        unsigned char *stage_b = smem_stage + STAGE_B / 2;
-        int zone = 0;
 
         if constexpr (STAGED) {
             if (tid == 0) {
                 mbar_init(&mbar, 1);
-                if (DEEP) mbar_init(&mbar_b, 1);
                 fence_mbar_init();
             }
             __syncthreads();
@@ -618,30 +601,19 @@ struct CtaFft {
                 for (int w = 0; w < PLast::R; w++) auxo[u * PLast::R + w] = io.store_aux_value(PLast::dst_index(t, u, w));
         }
 
-        IO ioq = io; // DEEP: the group being fetched (io describes the group being transformed)
         if constexpr (STAGED) {
             io.group_init(blockIdx.x, gridDim.x, P::TPC);
             if (tid == 0 && (long)blockIdx.x < groups) stage_issue(io, smem_stage, &mbar, rows);
-            if constexpr (DEEP) {
-                ioq = io;
-                ioq.group_next(P::TPC);
-                if (tid == 0 && (long)blockIdx.x + gridDim.x < groups) stage_issue(ioq, stage_b, &mbar_b, rows);
-            }
         }
         for (long g = blockIdx.x; g < groups; g += gridDim.x) {
             const long row = g * P::TPC + slot;
             const bool active = row < rows;
             float2 x[EPT];
             if constexpr (STAGED) {
-                const unsigned char *stage = (DEEP && zone) ? stage_b : smem_stage;
+                const unsigned char *stage = smem_stage;
                 if (io.stage_bytes(P::TPC, rows) != 0) {
-                    if (DEEP && zone) {
-                        mbar_wait(&mbar_b, phase_b);
-                        phase_b ^= 1;
-                    } else {
-                        mbar_wait(&mbar, phase);
-                        phase ^= 1;
-                    }
+                    mbar_wait(&mbar, phase);
+                    phase ^= 1;
                 }
                 const int rctx = io.row_begin(slot);
                 if (io.row_full(rctx)) { // warp-uniform: a slot's threads share the frame
@@ -673,16 +645,9 @@ struct CtaFft {
             par ^= 1;
             store_smem<P0>(b, t, x);
             __syncthreads();
-            if constexpr (STAGED) { // every thread has consumed the stage: refill it
+            if constexpr (STAGED) { // every thread has consumed the stage: refill it for this CTA's next group
                 io.group_next(P::TPC);
-                if constexpr (DEEP) { // ... for the group two steps ahead, into the zone just consumed
-                    ioq.group_next(P::TPC);
-                    if (tid == 0 && g + 2L * gridDim.x < groups)
-                        stage_issue(ioq, zone ? stage_b : smem_stage, zone ? &mbar_b : &mbar, rows);
-                    zone ^= 1;
-                } else {
-                    if (tid == 0 && g + gridDim.x < groups) stage_issue(io, smem_stage, &mbar, rows);
-                }
+                if (tid == 0 && g + gridDim.x < groups) stage_issue(io, smem_stage, &mbar, rows);
             }
             load_smem<P1>(b, t, x);
             if (P::NBUF == 1) __syncthreads();

@@ -320,9 +320,9 @@ cudaStream_t pick_stream(kofft_cuda_ctx *, void *stream)
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // transforms per CTA of the single-CTA engine (Plan<L, min_cta>::TPC; 16 elements per thread)
-// bytes of landing zone per point of a staged STFT group: the complex-sized stage holds real samples, and with the
-// two-deep prefetch (or the half-size stage) a group may use only half of it
-constexpr long kStftStageBytesPerPoint = (IoTraits<IoStft>::kDeepStage || IoTraits<IoStft>::kStageHalf) ? 4 : 8;
+// bytes of landing zone per point of a staged STFT group: the complex-sized stage holds real samples; the half-size
+// stage build knob (KOFFT_STFT_TW1_SMEM) leaves a group only half of it
+constexpr long kStftStageBytesPerPoint = IoTraits<IoStft>::kStageHalf ? 4 : 8;
 
 long tpc_of(size_t n, int min_cta = 256)
 {
