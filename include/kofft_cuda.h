@@ -79,6 +79,16 @@ int kofft_cuda_set_istft_fusion(kofft_cuda_ctx *ctx, int enable, int run_frames)
  *   mode 1: one persistent thread-block-cluster kernel (cluster barrier between the passes).
  * All are bit-identical. */
 int kofft_cuda_set_large_mode(kofft_cuda_ctx *ctx, int mode);
+/* Lengths 2^min_log2n .. 2^15 of the complex core (rfft / irfft: twice that) run the warp-specialised split
+ * kernel (fft_split32.cuh): ONE persistent cooperative launch, 512-thread CTAs whose "A warps" run the
+ * 2^(L-5)-point column transforms of an 8192-element tile while their "B warps" finish 32-point rows in
+ * registers (rfft twist by warp shuffles), intermediate pinned in L2.  Default 15; 13..15 select more lengths,
+ * 16 switches it off (kofft_cuda_set_large_mode then picks the implementation for 2^15).  Bit-identical. */
+int kofft_cuda_set_split_min_log2n(kofft_cuda_ctx *ctx, int min_log2n);
+/* The persistent large-N kernels need a cooperative launch (every CTA resident).  When the device cannot grant
+ * it (shared or partitioned GPU) the library computes the same bits with the slower multi-kernel path, bumps
+ * this counter and leaves a note in kofft_cuda_last_error(). */
+unsigned long long kofft_cuda_fallback_count(const kofft_cuda_ctx *ctx);
 /* enable != 0: mode 1 above; 0: back to the current non-cluster mode */
 int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable);
 /* Host-pointer batch entry points (fft_batch_host, rfft_batch_host, irfft_batch_host): batches

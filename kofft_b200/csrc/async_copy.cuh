@@ -140,7 +140,38 @@ KD void flag_arrive(unsigned *c)
 // the arriving CTA only READ the guarded data (its loads have completed): no fence needed
 KD void flag_arrive_relaxed(unsigned *c) { atomicAdd(c, 1u); }
 
+// ---- warp-level and partial-CTA primitives of the warp-specialised large-N kernel (fft_split32.cuh) ----
+// bar.sync id, n: barrier among the n threads (a multiple of 32) that name it; id 0 is __syncthreads
+KD void named_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+KD void warp_sync() { __syncwarp(); }
+KD float shfl_xor_f(float v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
+// warp-group register reallocation (setmaxnreg, sm_90+): executed by all four warps of a warp group
+template <int REGS> KD void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> KD void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+// 16-byte L2-only load of data written by other CTAs of the same launch
+KD float4 ldcg_hint4(const void *p, unsigned long long pol)
+{
+    float4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+KD void nano_sleep(unsigned ns) { __nanosleep(ns); }
+
 #elif defined(KOFFT_EMU)
+
+inline void named_barrier(int id, int nthreads) { cuda_emu::named_barrier(id, nthreads); }
+inline void warp_sync() { cuda_emu::syncwarp(); }
+inline float shfl_xor_f(float v, int mask) { return cuda_emu::shfl_xor(v, mask); }
+template <int REGS> inline void setmaxnreg_inc() {}
+template <int REGS> inline void setmaxnreg_dec() {}
+inline float4 ldcg_hint4(const void *p, unsigned long long)
+{
+    if (reinterpret_cast<uintptr_t>(p) & 15) abort();
+    return *reinterpret_cast<const float4 *>(p);
+}
+inline void nano_sleep(unsigned) {}
 
 inline L2Policy make_l2_policy() { return L2Policy{1ull, 2ull}; }
 inline float2 ldg_hint(const float2 *p, unsigned long long) { return *p; }

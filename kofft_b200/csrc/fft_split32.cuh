@@ -1,0 +1,341 @@
+// fft_split32.cuh -- N = 2^13 .. 2^15 complex (rfft / irfft 2^14 .. 2^16) as ONE persistent,
+// warp-specialised kernel: the faithful two-pass split of kofft's radix-2 Stockham
+// (src/fft.rs:789-912) with 32 elements per thread.
+//
+//   N = 2^LA * 32.   Index i = n * 32 + j'  (n: LA bits, j': 5 bits).
+//   pass A = stages 0 .. LA-1: for every column j' a 2^LA-point transform over n (stride 32).  It
+//       starts at stage 0, so its twiddles are those of a 2^LA-point transform read from the big
+//       table with stride 32.  A tile = COLS = 8192 / 2^LA adjacent columns = 8192 elements, done by
+//       the CTA's 8 "A warps" (256 threads x 32 elements) as two register passes with ONE exchange
+//       through shared memory.  Results go to the intermediate (global memory, pinned in L2).
+//   pass B = stages LA .. LA+4: for every k (the LA output bits produced by pass A) the 32
+//       contiguous elements k*32 .. k*32+31 form a 32-point transform done IN ONE THREAD's registers
+//       (twiddles T[(k + c_low 2^LA) << (4-t)], 31 per thread, resident for the kernel's lifetime);
+//       bin c lands at K = k + c 2^LA, so 16 lanes holding adjacent k store 128-byte runs directly.
+//       The CTA's 8 "B warps" work independently of each other: a warp owns 16 adjacent k and their
+//       16 mirrors 2^LA - k (the rfft twist pairs bin K with m - K = (2^LA - k) + (31 - c) 2^LA, i.e.
+//       lane l with lane 31 - l and register w with register 31 - w: two shuffles per bin), reads its
+//       32 rows with 16-byte coalesced loads, transposes them through a private shared-memory
+//       region (__syncwarp only) and never meets a block-wide barrier.
+//
+// Both roles run at the same time on every SM (A warps of transform i + 1 .. i + SLOTS - 1 next to
+// the B warps of transform i), so the barrier waits and memory latencies of one role are filled by
+// the other.  Compared with the 16-elements-per-thread pipeline in fft_large.cuh this halves the
+// shared-memory exchanges per element and takes the block barriers per element from six per 8192
+// to two per 8192 (both inside pass A).
+//
+// Dependencies: a "team" of NT = 32 / COLS consecutive CTAs owns the transforms team, team + teams,
+// ...; member kb runs column tile kb and the warp tiles 8 kb .. 8 kb + 7.  Per team and intermediate
+// slot one arrival counter per pass (see LargePipe in fft_large.cuh for why per slot).  The launch
+// is cooperative: every CTA is resident, which the flag waits rely on.
+#pragma once
+#include "fft_kernels.cuh"
+
+namespace kofft {
+
+constexpr int WIDE = 32; // elements per thread
+
+KHD constexpr int pad32(int i) { return i + (i >> 5); }
+
+// pass-0 twiddles (group k = 0) of a radix-32 first pass: v[(2^t - 1) + c] = T[c << (L-1-t)]
+struct Tw0W {
+    float2 v[32];
+};
+
+// Stages S .. S+RR-1 of a 2^LS-point (sub-)transform, 32 elements per thread: U = 32 >> RR
+// butterflies of radix 2^RR on x[u*R + w].  Index algebra as Pass<> in fft_engine.cuh.
+template <int LS, int S, int RR, bool EXACT, bool UNIT0>
+struct WidePass {
+    static constexpr int r = RR, R = 1 << RR, U = WIDE >> RR;
+    static constexpr int LJ = LS - S - RR, J = 1 << LJ;
+    static constexpr int T = (1 << LS) / WIDE; // threads per transform
+    static constexpr int NTW = U * (R - 1);
+    static_assert(RR >= 1 && RR <= 5 && LJ >= 0, "pass shape");
+    static KHD int bfly(int t, int u) { return t + u * T; }
+    static KHD int src_index(int t, int u, int q)
+    {
+        const int b = bfly(t, u);
+        return ((b >> LJ) << (LS - S)) + (b & (J - 1)) + (q << LJ);
+    }
+    static KHD int dst_index(int t, int u, int w)
+    {
+        const int b = bfly(t, u);
+        return ((b >> LJ) << LJ) + (b & (J - 1)) + (bitrev(w, r) << (S + LJ));
+    }
+    // tw: UNIT0 -> thread-independent [R-1] (k = 0); else per thread [U][R-1]
+    template <class TW>
+    static KHD void compute(float2 *x, const TW *tw)
+    {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+            for (int tl = 0; tl < r; tl++) {
+                const int bit = 1 << (r - 1 - tl);
+#pragma unroll
+                for (int w0 = 0; w0 < R; w0++) {
+                    if (w0 & bit) continue;
+                    const int c_low = bitrev(w0 >> (r - tl), tl);
+                    float2 &a = x[u * R + w0];
+                    float2 &b = x[u * R + (w0 | bit)];
+                    if (UNIT0) {
+                        if (c_low == 0)
+                            butterfly_unit(a, b); // T[0] == (1, 0) exactly
+                        else
+                            butterfly<EXACT>(a, b, tw[(1 << tl) - 1 + c_low]);
+                    } else {
+                        butterfly<EXACT>(a, b, tw[u * (R - 1) + (1 << tl) - 1 + c_low]);
+                    }
+                }
+            }
+        }
+    }
+};
+
+enum SplitEpilogue : int { SPLIT_STORE = 0, SPLIT_TWIST = 1 };
+
+#ifndef KOFFT_SPLIT_SLOTS
+#define KOFFT_SPLIT_SLOTS 4
+#endif
+// register budgets of the two roles (setmaxnreg): 256 * A + 256 * B == 512 * 128
+#ifndef KOFFT_SPLIT_REGS_A
+#define KOFFT_SPLIT_REGS_A 96
+#endif
+#ifndef KOFFT_SPLIT_REGS_B
+#define KOFFT_SPLIT_REGS_B 160
+#endif
+
+template <int LA, bool EXACT, class IO, int EPI>
+struct Split32 {
+    static_assert(LA >= 8 && LA <= 10, "N = 2^13 .. 2^15");
+    static constexpr int L = LA + 5;
+    static constexpr int NR = 1 << LA;            // rows of pass B per transform
+    static constexpr int COLS = 8192 >> LA;       // columns per pass-A tile: 8, 16, 32
+    static constexpr int NT = 32 / COLS;          // CTAs per team: 4, 2, 1
+    static constexpr int LOG_NT = ilog2c(NT);
+    static constexpr int RA0 = LA - 5;            // pass A = (RA0, 5) stages
+    using A0 = WidePass<LA, 0, RA0, EXACT, true>;
+    using A1 = WidePass<LA, RA0, 5, EXACT, false>;
+    using PB = WidePass<5, 0, 5, EXACT, false>;
+    static constexpr int TA = A0::T;              // threads per column: 32, 16, 8
+    static_assert(TA * COLS == 256 && A1::U == 1 && A1::LJ == 0, "pass-A tile shape");
+    static constexpr int A_THREADS = 256, B_THREADS = 256, CTA = A_THREADS + B_THREADS;
+    static constexpr int B_WARPS = B_THREADS / 32;
+    static constexpr int NTILES = NR / 32;        // warp tiles (16 rows + 16 mirrors) per transform
+    static_assert(NTILES == NT * B_WARPS, "a team's B warps cover one transform");
+    static constexpr int SLOTS = KOFFT_SPLIT_SLOTS;
+    static constexpr int FLAG_STRIDE = 32;        // unsigned per team: cntA[SLOTS], cntB[SLOTS] in one line
+    static_assert(2 * SLOTS <= FLAG_STRIDE, "flag line");
+
+    // ---- shared memory (float2 units) ----
+    // pass-A exchange: one padded region per column; the region stride makes the 16 lanes of a half
+    // warp (COLS columns x 16/COLS consecutive t) hit 16 distinct 8-byte banks
+    static constexpr int PADN = NR + (NR >> 5);
+    static constexpr int RSA = PADN + (COLS == 8 ? 2 : 1);
+    static constexpr int XA = COLS * RSA;
+    // pass-A second-pass twiddles: [TA][33] (k1-dependent, shared by the columns)
+    static constexpr int TWA = TA * 33;
+    // pass-B transposition: per warp two halves of 16 rows x 34 (16-byte accesses, conflict-free)
+    static constexpr int RSB = 34, HB = 16 * RSB, XB = 2 * HB;
+    // rfft: the CTA's slice of T' (src/rfft.rs:172-183), [warp][register][lane]
+    static constexpr int RTW = EPI == SPLIT_TWIST ? B_WARPS * 32 * 32 : 0;
+    static constexpr int OFF_TWA = (XA + 1) & ~1;
+    static constexpr int OFF_XB = (OFF_TWA + TWA + 1) & ~1;
+    static constexpr int OFF_RTW = OFF_XB + B_WARPS * XB;
+    static constexpr int SMEM_BYTES = (OFF_RTW + RTW) * 8;
+    static constexpr bool HINT = IoTraits<IO>::kHint;
+
+    static KD unsigned goal_a(long i) { return (unsigned)(NT * (i / SLOTS + 1)); }
+    static KD unsigned goal_b(long i) { return (unsigned)(NTILES * (i / SLOTS + 1)); }
+
+    // ------------------------------------------------------------------------------------------
+    // A warps: tid 0 .. 255
+    // ------------------------------------------------------------------------------------------
+    static KD void a_role(const IO &io, const Tw0W &tw0, const float2 *__restrict__ table, long cnt, long team,
+                          long teams, int kb, float2 *__restrict__ slots, float2 *smem, unsigned *cntA, unsigned *cntB,
+                          int tid)
+    {
+        const long n = 1L << L;
+        const int col = tid % COLS, t = tid / COLS;
+        float2 *bf = smem + col * RSA;
+        float2 *twa = smem + OFF_TWA;
+        const L2Policy pol = make_l2_policy();
+        // second-pass twiddles of the column transform: entry e = (2^tl - 1) + c of row k1 is
+        // T[(k1 + (c << RA0)) << (LA-1-RA0-tl + 5)]
+        for (int i = tid; i < TA * 31; i += A_THREADS) {
+            const int k1 = i / 31, e = i - k1 * 31;
+            int tl = 0;
+            while ((2 << tl) - 1 <= e) tl++;
+            const int c = e + 1 - (1 << tl);
+            twa[k1 * 33 + e] = table[(long)(k1 + (c << RA0)) << (LA - 1 - RA0 - tl + 5)];
+        }
+        named_barrier(1, A_THREADS);
+        const float2 *tw1 = twa + t * 33;
+        const long j0 = (long)kb * COLS + col;
+        for (long i = 0; i < cnt; i++) {
+            const long row = team + i * teams;
+            float2 x[WIDE];
+#pragma unroll
+            for (int u = 0; u < A0::U; u++)
+#pragma unroll
+                for (int q = 0; q < A0::R; q++) {
+                    const int idx = (int)(((long)A0::src_index(t, u, q) << 5) + j0);
+                    if constexpr (HINT)
+                        x[u * A0::R + q] = io.load_hint(row, idx, pol.first);
+                    else
+                        x[u * A0::R + q] = io.load(row, idx);
+                }
+            A0::compute(x, tw0.v);
+#pragma unroll
+            for (int u = 0; u < A0::U; u++)
+#pragma unroll
+                for (int w = 0; w < A0::R; w++) bf[pad32(A0::dst_index(t, u, w))] = x[u * A0::R + w];
+            // the slot is rewritten: every B warp of the team must have consumed transform i - SLOTS
+            if (tid == 0 && i >= SLOTS) {
+                const unsigned want = goal_b(i - SLOTS);
+                while (flag_load(cntB + i % SLOTS) < want) nano_sleep(32);
+                flag_acquire();
+            }
+            named_barrier(1, A_THREADS);
+#pragma unroll
+            for (int q = 0; q < 32; q++) x[q] = bf[pad32(A1::src_index(t, 0, q))];
+            A1::compute(x, tw1);
+            float2 *o = slots + (i % SLOTS) * n + j0;
+#pragma unroll
+            for (int w = 0; w < 32; w++) stg_hint(o + ((long)A1::dst_index(t, 0, w) << 5), x[w], pol.last);
+            named_barrier(1, A_THREADS); // the exchange buffer is free again; every thread's stores are issued
+            if (tid == 0) flag_arrive(cntA + i % SLOTS);
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // B warps: tid 256 .. 511.  SPECIAL: the transform's last warp tile, whose lane 16 would repeat
+    // row 2^(LA-1) (lane 15's, which mirrors itself) and takes row 0 (which mirrors itself) instead.
+    // ------------------------------------------------------------------------------------------
+    template <bool SPECIAL>
+    static KD void b_role(const IO &io, const float2 *__restrict__ table, long cnt, long team, long teams, int kb,
+                          const float2 *__restrict__ slots, float2 *smem, unsigned *cntA, unsigned *cntB, int wl)
+    {
+        const long n = 1L << L;
+        const int w = wl >> 5, lane = wl & 31, h = lane >> 4, lp = lane & 15;
+        const int wt = kb * B_WARPS + w; // warp tile of the transform
+        const int k0 = 1 + 16 * wt;      // low half: rows k0 .. k0 + 15
+        const int kh0 = NR - k0 - 15;    // high half: their mirrors, ascending (lane l mirrors lane 31 - l)
+        int k = h ? kh0 + lp : k0 + lp;
+        if (SPECIAL && lane == 16) k = 0;
+        const L2Policy pol = make_l2_policy();
+        float2 twb[31];
+#pragma unroll
+        for (int tl = 0; tl < 5; tl++)
+#pragma unroll
+            for (int c = 0; c < (1 << tl); c++) twb[(1 << tl) - 1 + c] = KOFFT_LDG(table + ((long)(k + (c << LA)) << (4 - tl)));
+        float2 *tb = smem + OFF_XB + w * XB + h * HB;
+        float2 *rtws = smem + OFF_RTW + w * (32 * 32) + lane;
+        if constexpr (EPI == SPLIT_TWIST) {
+#pragma unroll
+            for (int wi = 0; wi < 32; wi++) rtws[wi * 32] = KOFFT_LDG(io.rtw + k + ((long)bitrev(wi, 5) << LA));
+        }
+        warp_sync();
+        for (long i = 0; i < cnt; i++) {
+            const long row = team + i * teams;
+            const float2 *slot = slots + (i % SLOTS) * n;
+            if (lane == 0) {
+                const unsigned want = goal_a(i);
+                while (flag_load(cntA + i % SLOTS) < want) nano_sleep(32);
+                flag_acquire();
+            }
+            warp_sync();
+            // 16-byte coalesced loads: instruction j fetches row j of each half (256 bytes per half warp)
+            float4 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                int rj = h ? kh0 + j : k0 + j;
+                if (SPECIAL && j == 0 && h) rj = 0;
+                v[j] = ldcg_hint4(slot + (long)rj * 32 + 2 * lp, pol.first);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) *reinterpret_cast<float4 *>(tb + j * RSB + 2 * lp) = v[j];
+            warp_sync();
+            if (lane == 0) flag_arrive_relaxed(cntB + i % SLOTS); // the warp's reads of the slot are complete
+            float2 x[WIDE];
+#pragma unroll
+            for (int q2 = 0; q2 < 16; q2++) {
+                const float4 e = *reinterpret_cast<const float4 *>(tb + lp * RSB + 2 * q2);
+                x[2 * q2] = make_float2(e.x, e.y);
+                x[2 * q2 + 1] = make_float2(e.z, e.w);
+            }
+            warp_sync(); // the region is rewritten by the next tile
+            PB::compute(x, twb);
+            // register wi holds bin K = k + bitrev(wi) 2^LA
+            if constexpr (EPI == SPLIT_TWIST) {
+                float2 *o = io.out + row * (io.m + 1) + k;
+#pragma unroll
+                for (int wi = 0; wi < 32; wi++) {
+                    const float2 p = x[31 - wi];
+                    float2 ym = make_float2(shfl_xor_f(p.x, 31), shfl_xor_f(p.y, 31));
+                    if (SPECIAL) {
+                        if (lane == 15) ym = p; // row 2^(LA-1): m - K = 2^(LA-1) + (31 - c) 2^LA, its own register 31 - wi
+                        if (lane == 16) ym = x[bitrev((32 - bitrev(wi, 5)) & 31, 5)]; // row 0: m - K = (32 - c) 2^LA
+                    }
+                    const float2 tw = rtws[wi * 32];
+                    if (SPECIAL && wi == 0) {
+                        if (lane == 16) { // bins 0 and m (src/rfft.rs:450-452)
+                            stg_hint(o, make_float2(add_rn(x[0].x, x[0].y), 0.0f), pol.first);
+                            stg_hint(o + io.m, make_float2(sub_rn(x[0].x, x[0].y), 0.0f), pol.first);
+                        } else {
+                            stg_hint(o, io.twist(x[0], ym, tw), pol.first);
+                        }
+                    } else {
+                        stg_hint(o + ((long)bitrev(wi, 5) << LA), io.twist(x[wi], ym, tw), pol.first);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int wi = 0; wi < 32; wi++) {
+                    const int K = k + (bitrev(wi, 5) << LA);
+                    if constexpr (HINT)
+                        io.store_hint(row, K, x[wi], pol.first);
+                    else
+                        io.store(row, K, x[wi]);
+                }
+            }
+        }
+    }
+
+    // rows: transforms in the batch; scratch: teams * SLOTS * 2^L complex; flags: teams * FLAG_STRIDE
+    // counters, zero at launch.  gridDim.x is a multiple of NT and every CTA is resident.
+    static KD void run(const IO &io, const Tw0W &tw0, const float2 *__restrict__ table, long rows,
+                       float2 *__restrict__ scratch, float2 *smem, unsigned *flags)
+    {
+        const int tid = threadIdx.x;
+        const long n = 1L << L;
+        const int kb = blockIdx.x % NT;
+        const long team = blockIdx.x / NT, teams = gridDim.x / NT;
+        unsigned *cntA = flags + team * FLAG_STRIDE, *cntB = cntA + SLOTS;
+        const long cnt = team < rows ? (rows - team + teams - 1) / teams : 0;
+        float2 *slots = scratch + team * SLOTS * n;
+        if (tid < A_THREADS) {
+            setmaxnreg_dec<KOFFT_SPLIT_REGS_A>();
+            a_role(io, tw0, table, cnt, team, teams, kb, slots, smem, cntA, cntB, tid);
+        } else {
+            setmaxnreg_inc<KOFFT_SPLIT_REGS_B>();
+            const int wl = tid - A_THREADS;
+            if (kb == NT - 1 && (wl >> 5) == B_WARPS - 1)
+                b_role<true>(io, table, cnt, team, teams, kb, slots, smem, cntA, cntB, wl);
+            else
+                b_role<false>(io, table, cnt, team, teams, kb, slots, smem, cntA, cntB, wl);
+        }
+    }
+};
+
+#ifdef __CUDACC__
+template <int LA, bool EXACT, class IO, int EPI>
+__global__ void __launch_bounds__(512, 1)
+    split32_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0W tw0, const float2 *__restrict__ table,
+                   long rows, float2 *__restrict__ scratch, unsigned *flags)
+{
+    extern __shared__ __align__(128) float2 smem[];
+    Split32<LA, EXACT, IO, EPI>::run(io, tw0, table, rows, scratch, smem, flags);
+}
+#endif
+
+} // namespace kofft

@@ -100,6 +100,11 @@ struct kofft_cuda_ctx {
     bool large_pipe = true;
     bool large_auto = true; // pipelined kernel only where it measured faster (rfft, irfft), two kernels otherwise
     unsigned *pipe_flags = nullptr;
+    // N = 2^13 .. 2^15: the warp-specialised split kernel (fft_split32.cuh) serves lengths 2^split_min_l .. 2^15
+    // (16 = off).  Cooperative launch; when the device cannot make every CTA resident the older paths compute
+    // the same bits and coop_fallbacks counts it.
+    int split_min_l = 15;
+    unsigned long long coop_fallbacks = 0;
     bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
     int istft_run_frames = 128;
     // host-pointer batch entry points: the batch is cut into chunks that flow through three
@@ -211,6 +216,34 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
         int rc = get_fft_table(ctx, n, &t);
         if (rc) return rc;
         a.table = t->dev;
+        if (L >= ctx->split_min_l && L >= 13 && L <= 15 && kind != KIND_STFT && kind != KIND_ISTFT && kind != KIND_STFT_MAG) {
+            SplitArgs g;
+            const int ra0 = L - 10; // pass A's first register pass: stages 0 .. L-11 of the big transform
+            for (int tl = 0; tl < ra0; tl++)
+                for (int c = 0; c < (1 << tl); c++) {
+                    size_t idx = static_cast<size_t>(c) << (L - 1 - tl);
+                    g.v0[(1 << tl) - 1 + c] = make_float2(t->host[2 * idx], t->host[2 * idx + 1]);
+                }
+            const int nt = 1 << (L - 13); // CTAs per team
+            g.max_teams = ctx->num_sms / nt;
+            void *scratch = nullptr;
+            rc = ensure_ws(ctx, 4, size_t(kSplitSlots) * g.max_teams * n * sizeof(float2), &scratch);
+            if (rc) return rc;
+            if (!ctx->pipe_flags) // sized for the smallest team of any persistent large-N kernel
+                CU(cudaMalloc(&ctx->pipe_flags, sizeof(unsigned) * kPipeFlagStride * (kMaxPipeCtasPerSm * ctx->num_sms)));
+            g.scratch = static_cast<float2 *>(scratch);
+            g.flags = ctx->pipe_flags;
+            e = launch_split32_fft(L, a, g);
+            if (e == cudaSuccess) {
+                ctx->launches += 1;
+                return KOFFT_OK;
+            }
+            if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorLaunchOutOfResources && e != cudaErrorNotSupported)
+                return fail_cuda(e, "split kernel launch");
+            (void)cudaGetLastError();
+            ctx->coop_fallbacks++;
+            g_last_error = "cooperative launch not possible (device shared or partitioned): fell back to a slower path";
+        }
         if (L > 14) {
             // two-pass path: pass A's pass-0 twiddles are those of stage 0..3 of the big transform
             if (kind == KIND_STFT || kind == KIND_ISTFT)
@@ -227,8 +260,8 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
                 const int max_teams = kMaxPipeCtasPerSm * ctx->num_sms / nkb;
                 rc = ensure_ws(ctx, 4, size_t(kLargePipeSlots) * max_teams * row_bytes, &scratch);
                 if (rc) return rc;
-                if (!ctx->pipe_flags) // sized for the smaller team (8 CTAs), whatever length comes first
-                    CU(cudaMalloc(&ctx->pipe_flags, sizeof(unsigned) * kPipeFlagStride * (kMaxPipeCtasPerSm * ctx->num_sms / 8)));
+                if (!ctx->pipe_flags) // sized for the smallest team of any persistent large-N kernel
+                    CU(cudaMalloc(&ctx->pipe_flags, sizeof(unsigned) * kPipeFlagStride * (kMaxPipeCtasPerSm * ctx->num_sms)));
                 LargeArgs g;
                 g.lsub = L - 8;
                 g.row0 = 0;
@@ -248,6 +281,8 @@ int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t r
                 if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorLaunchOutOfResources && e != cudaErrorNotSupported)
                     return fail_cuda(e, "large-N pipelined kernel launch");
                 (void)cudaGetLastError();
+                ctx->coop_fallbacks++;
+                g_last_error = "cooperative launch not possible (device shared or partitioned): fell back to two kernels per chunk";
             }
             if (ctx->large_fused) {
                 // one persistent launch; each cluster double-buffers one transform in scratch
@@ -358,6 +393,9 @@ int kofft_cuda_create(kofft_cuda_ctx **out, int device)
         ctx->large_fused = strcmp(m, "cluster") == 0;
     }
 
+    if (const char *m = getenv("KOFFT_SPLIT_MIN_L"))
+        if (atoi(m) >= 13 && atoi(m) <= 16) ctx->split_min_l = atoi(m);
+
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -440,6 +478,13 @@ int kofft_cuda_set_large_mode(kofft_cuda_ctx *ctx, int mode)
     ctx->large_fused = mode == 1;
     return KOFFT_OK;
 }
+int kofft_cuda_set_split_min_log2n(kofft_cuda_ctx *ctx, int min_log2n)
+{
+    if (min_log2n < 13 || min_log2n > 16) return fail_msg(KOFFT_ERR_INVALID_VALUE, "set_split_min_log2n: 13..16 (16 = off)");
+    ctx->split_min_l = min_log2n;
+    return KOFFT_OK;
+}
+unsigned long long kofft_cuda_fallback_count(const kofft_cuda_ctx *ctx) { return ctx->coop_fallbacks; }
 int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable)
 {
     ctx->large_fused = enable != 0;

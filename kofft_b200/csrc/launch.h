@@ -94,6 +94,16 @@ constexpr int kLargePipeSlots = KOFFT_PIPE_SLOTS; // intermediate transforms per
 constexpr int kMaxFusedClusters = 148;
 cudaError_t launch_large_fft(int L, const LaunchArgs &a, LargeArgs &g);
 
+// N = 2^13 .. 2^15: the warp-specialised split kernel (fft_split32.cuh), one persistent cooperative launch
+constexpr int kSplitSlots = 4;      // intermediate transforms per team (Split32::SLOTS)
+struct SplitArgs {
+    float2 v0[32] = {};        // pass-0 twiddles: v[(2^t - 1) + c] = T[c << (L-1-t)]  (Tw0W)
+    float2 *scratch = nullptr; // max_teams * kSplitSlots * 2^L complex (stays in L2)
+    unsigned *flags = nullptr; // max_teams * kPipeFlagStride counters
+    int max_teams = 0;
+};
+cudaError_t launch_split32_fft(int L, const LaunchArgs &a, SplitArgs &g);
+
 // per-L entry points (one per fft_inst.cu build)
 #define KOFFT_DECL_L(L) cudaError_t launch_cta_fft_L##L(const LaunchArgs &a);
 KOFFT_DECL_L(5) KOFFT_DECL_L(6) KOFFT_DECL_L(7) KOFFT_DECL_L(8) KOFFT_DECL_L(9)

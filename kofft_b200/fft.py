@@ -112,6 +112,15 @@ class Context:
         kernel, 0 = two kernels per chunk, 1 = cluster kernel."""
         check(_lib.lib().kofft_cuda_set_large_mode(self.handle, int(mode)))
 
+    def set_split_min_log2n(self, min_log2n: int) -> None:
+        """complex cores of 2^min_log2n .. 2^15 points run the warp-specialised split kernel (default 15; 16 = off)"""
+        check(_lib.lib().kofft_cuda_set_split_min_log2n(self.handle, int(min_log2n)))
+
+    @property
+    def fallback_count(self) -> int:
+        """times a cooperative (persistent) launch was not possible and a slower path computed the result"""
+        return int(_lib.lib().kofft_cuda_fallback_count(self.handle))
+
     def set_rfft_table_fma(self, fma: bool) -> None:
         check(_lib.lib().kofft_cuda_set_rfft_table_fma(self.handle, int(bool(fma))))
 

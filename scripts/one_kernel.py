@@ -44,7 +44,13 @@ elif which == "rfft2":  # two-kernel large-N path (column pass + row pass per L2
     x = (torch.rand((4096, 65536), generator=g, device="cuda") * 2 - 1).contiguous()
     for _ in range(3):
         fft.rfft_batch(x)
-elif which == "rfft":  # default large-N path for rfft: the persistent pipelined kernel
+elif which == "split":  # rfft 2^16 through the warp-specialised split kernel (default for 2^15 cores)
+    x = (torch.rand((4096, 65536), generator=g, device="cuda") * 2 - 1).contiguous()
+    y = torch.empty((4096, 32769), dtype=torch.complex64, device="cuda")
+    for _ in range(6):
+        fft.rfft_batch(x, out=y)
+elif which == "rfft":  # the persistent pipelined kernel (16 elements per thread)
+    fft.ctx.set_split_min_log2n(16)
     x = (torch.rand((4096, 65536), generator=g, device="cuda") * 2 - 1).contiguous()
     for _ in range(6):
         fft.rfft_batch(x)

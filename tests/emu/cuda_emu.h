@@ -21,6 +21,8 @@ struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 inline emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -48,11 +50,23 @@ struct Thread {
     unsigned block = 0; // index of the thread's block inside the cluster
 };
 
+struct NamedBar {
+    unsigned long long generation = 0;
+    int arrived = 0;
+};
+struct WarpState {
+    unsigned long long generation = 0;
+    int arrived = 0;
+    int alive = 0;
+    float xchg[32] = {};
+};
 struct BlockState {
     unsigned long long generation = 0;
     int arrived = 0;
     int alive = 0;
     emu_dim3 bid;
+    NamedBar named[16];           // bar.sync id, n
+    std::vector<WarpState> warps; // __syncwarp / shuffles
 };
 
 struct Scheduler {
@@ -67,6 +81,7 @@ struct Scheduler {
 };
 
 inline Scheduler *g_sched = nullptr;
+inline size_t g_stack_bytes = 256 * 1024; // per coroutine; kernels with many threads per team lower it
 inline unsigned g_late_from = ~0u;      // see run_cluster
 inline unsigned long long g_late_ratio = 1;
 
@@ -105,6 +120,50 @@ inline void cluster_sync()
 
 inline unsigned cluster_rank() { return g_sched->threads[g_sched->current].block; }
 
+// bar.sync id, nthreads: the nthreads threads that name the barrier (all of them must be alive)
+inline void named_barrier(int id, int nthreads)
+{
+    Scheduler *s = g_sched;
+    NamedBar &b = s->blocks[s->threads[s->current].block].named[id & 15];
+    const unsigned long long gen = b.generation;
+    if (++b.arrived == nthreads) {
+        b.arrived = 0;
+        b.generation++;
+        return;
+    }
+    while (b.generation == gen) yield_to_scheduler();
+}
+
+inline WarpState &my_warp()
+{
+    Scheduler *s = g_sched;
+    Thread &t = s->threads[s->current];
+    return s->blocks[t.block].warps[t.tid.x >> 5];
+}
+// __syncwarp(): the live threads of the calling thread's warp
+inline void syncwarp()
+{
+    WarpState &w = my_warp();
+    const unsigned long long gen = w.generation;
+    if (++w.arrived == w.alive) {
+        w.arrived = 0;
+        w.generation++;
+        return;
+    }
+    while (w.generation == gen) yield_to_scheduler();
+}
+// __shfl_xor_sync over the full warp
+inline float shfl_xor(float v, int mask)
+{
+    WarpState &w = my_warp();
+    const unsigned lane = g_sched->threads[g_sched->current].tid.x & 31u;
+    w.xchg[lane] = v;
+    syncwarp();
+    const float r = w.xchg[(lane ^ (unsigned)mask) & 31u];
+    syncwarp();
+    return r;
+}
+
 inline void trampoline()
 {
     Scheduler *s = g_sched;
@@ -114,6 +173,14 @@ inline void trampoline()
     t.done = true;
     s->alive--;
     b.alive--;
+    {
+        WarpState &w = b.warps[t.tid.x >> 5];
+        w.alive--;
+        if (w.alive > 0 && w.arrived == w.alive) {
+            w.arrived = 0;
+            w.generation++;
+        }
+    }
     // an exited thread no longer takes part in barriers
     if (b.alive > 0 && b.arrived == b.alive) {
         b.arrived = 0;
@@ -138,10 +205,12 @@ inline void run_cluster(unsigned first_block, unsigned cluster, unsigned grid_x,
     g_sched = &s;
     gridDim.x = grid_x;
     blockDim.x = threads_x;
-    const size_t stack_bytes = 256 * 1024;
+    const size_t stack_bytes = g_stack_bytes;
     for (unsigned c = 0; c < cluster; c++) {
         s.blocks[c].alive = static_cast<int>(threads_x);
         s.blocks[c].bid.x = first_block + c;
+        s.blocks[c].warps.resize((threads_x + 31) / 32);
+        for (unsigned i = 0; i < threads_x; i++) s.blocks[c].warps[i >> 5].alive++;
         for (unsigned i = 0; i < threads_x; i++) {
             Thread &t = s.threads[c * threads_x + i];
             t.stack.resize(stack_bytes);

@@ -67,14 +67,14 @@ def _stale_k() -> bool:
     t = os.path.getmtime(_SOK)
     deps = [_SRCK, os.path.join(_HERE, "cuda_emu.h")] + [
         os.path.join(_CSRC, f) for f in ("hostdev.h", "async_copy.cuh", "fft_engine.cuh", "fft_kernels.cuh",
-                                         "fft_large.cuh", "fft_f64.cuh", "istft_fused.cuh", "small_kernels.cuh")]
+                                         "fft_large.cuh", "fft_split32.cuh", "fft_f64.cuh", "istft_fused.cuh", "small_kernels.cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 class EmuKernels:
     def __init__(self, lib):
         self.lib = lib
-        for f in (lib.kofft_emuk_cta, lib.kofft_emuk_large):
+        for f in (lib.kofft_emuk_cta, lib.kofft_emuk_large, lib.kofft_emuk_split32):
             f.restype = C.c_int
             f.argtypes = ([C.c_int, C.c_int, C.c_int, C.c_long] + [C.c_void_p] * 5 + [C.c_long] * 4
                           + [C.c_float, C.c_void_p, C.c_int, C.c_int])
@@ -104,6 +104,20 @@ class EmuKernels:
                                        self._ptr(out), self._ptr(out2), self._ptr(aux), *[int(v) for v in p],
                                        C.c_float(scale), self._ptr(table), grid_col, grid_row)
         assert rc == 0, rc
+
+
+def _split32(self, kind, exact, L, rows, table, inp=None, in2=None, out=None, out2=None, aux=None,
+             p=(0, 0, 0, 0), scale=1.0, grid=8, skew=None):
+    """Split32::run (fft_split32.cuh) on `grid` CTAs of 512 threads (teams of 4 / 2 / 1 CTAs run concurrently)."""
+    self.lib.kofft_emuk_set_skew(*(skew or (0, 0)))
+    rc = self.lib.kofft_emuk_split32(KIND[kind], int(exact), L, rows, self._ptr(inp), self._ptr(in2), self._ptr(out),
+                                     self._ptr(out2), self._ptr(aux), *[int(v) for v in p], C.c_float(scale),
+                                     self._ptr(table), grid, 0)
+    self.lib.kofft_emuk_set_skew(0, 0)
+    assert rc == 0, rc
+
+
+EmuKernels.split32 = _split32
 
 
 def _f64(self, n, rows, inp, out, table, inverse=False, grid=2, staged=False):

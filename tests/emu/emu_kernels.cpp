@@ -9,6 +9,7 @@
 
 #include "../../kofft_b200/csrc/fft_f64.cuh"
 #include "../../kofft_b200/csrc/fft_large.cuh"
+#include "../../kofft_b200/csrc/fft_split32.cuh"
 #include "../../kofft_b200/csrc/small_kernels.cuh"
 #include "../../kofft_b200/csrc/istft_fused.cuh"
 
@@ -248,6 +249,69 @@ API int kofft_emuk_large(int kind, int exact, int L, long rows, const void *in, 
         return exact ? run_large_kind<8, true>(kind, q, table, rows, grid_col, grid_row)
                      : run_large_kind<8, false>(kind, q, table, rows, grid_col, grid_row);
     return -1;
+}
+
+
+// ---- the warp-specialised split kernel (fft_split32.cuh): Split32::run on `grid` CTAs of 512 threads; the CTAs
+// of a team run as interleaved coroutines so the A-role / B-role dependency flags are live
+template <int LA, bool EXACT, class IO, int EPI>
+static int run_split32(const IO &io, const float *table, long rows, int grid)
+{
+    using F = Split32<LA, EXACT, IO, EPI>;
+    const long n = 1L << F::L;
+    Tw0W tw0;
+    memset(&tw0, 0, sizeof tw0);
+    for (int tl = 0; tl < F::RA0; tl++)
+        for (int c = 0; c < (1 << tl); c++) {
+            long idx = (long)c << (F::L - 1 - tl);
+            tw0.v[(1 << tl) - 1 + c] = make_float2(table[2 * idx], table[2 * idx + 1]);
+        }
+    const float2 *tab = reinterpret_cast<const float2 *>(table);
+    long teams = grid / F::NT;
+    if (teams < 1) teams = 1;
+    if (teams > rows) teams = rows;
+    std::vector<float2> scratch((size_t)teams * F::SLOTS * n);
+    std::vector<unsigned> flags((size_t)teams * F::FLAG_STRIDE, 0u);
+    const size_t per = ((F::SMEM_BYTES + 255) / 8 + 15) / 16 * 16;
+    std::vector<float2> smem(per * F::NT + 32);
+    float2 *base = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
+    const size_t keep = cuda_emu::g_stack_bytes;
+    cuda_emu::g_stack_bytes = 64 * 1024;
+    cuda_emu::launch((unsigned)(teams * F::NT), F::CTA, [&] {
+        float2 *sm = base + (size_t)cuda_emu::cluster_rank() * per;
+        F::run(io, tw0, tab, rows, scratch.data(), sm, flags.data());
+    }, F::NT);
+    cuda_emu::g_stack_bytes = keep;
+    return 0;
+}
+
+template <int LA, bool EXACT>
+static int run_split32_kind(int kind, const Args &q, const float *table, long rows, int grid)
+{
+    switch (kind) {
+    case 0: { IoC2C<false> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale}; return run_split32<LA, EXACT, IoC2C<false>, SPLIT_STORE>(io, table, rows, grid); }
+    case 1: { IoC2C<true> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale}; return run_split32<LA, EXACT, IoC2C<true>, SPLIT_STORE>(io, table, rows, grid); }
+    case 2: { IoGeneric<false> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_split32<LA, EXACT, IoGeneric<false>, SPLIT_STORE>(io, table, rows, grid); }
+    case 3: { IoGeneric<true> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_split32<LA, EXACT, IoGeneric<true>, SPLIT_STORE>(io, table, rows, grid); }
+    case 6: { IoRfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n}; return run_split32<LA, EXACT, IoRfft<EXACT>, SPLIT_TWIST>(io, table, rows, grid); }
+    case 7: { IoIrfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n, q.scale}; return run_split32<LA, EXACT, IoIrfft<EXACT>, SPLIT_STORE>(io, table, rows, grid); }
+    default: return -2;
+    }
+}
+
+// L = 13 .. 15 is the length of the complex core
+API int kofft_emuk_split32(int kind, int exact, int L, long rows, const void *in, const void *in2, void *out, void *out2,
+                           const void *aux, long p0, long p1, long p2, long p3, float scale, const float *table,
+                           int grid, int unused)
+{
+    (void)unused;
+    Args q{in, in2, out, out2, aux, 1L << L, p0, p1, p2, p3, scale};
+    switch (L) {
+    case 13: return exact ? run_split32_kind<8, true>(kind, q, table, rows, grid) : run_split32_kind<8, false>(kind, q, table, rows, grid);
+    case 14: return exact ? run_split32_kind<9, true>(kind, q, table, rows, grid) : run_split32_kind<9, false>(kind, q, table, rows, grid);
+    case 15: return exact ? run_split32_kind<10, true>(kind, q, table, rows, grid) : run_split32_kind<10, false>(kind, q, table, rows, grid);
+    default: return -1;
+    }
 }
 
 // the real fused istft kernel body (istft_fused.cuh)

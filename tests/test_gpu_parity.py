@@ -681,6 +681,7 @@ def test_large_paths_agree(cuda_fft, oracle, n):
     bref = oracle.irfft_batch(rref, 2 * n, nthreads=8)
     C = cuda_fft.ctx
     try:
+        C.set_split_min_log2n(16)  # 2^15 would otherwise take the split kernel whatever the mode (tested below)
         for mode in (C.LARGE_PIPELINED, C.LARGE_CLUSTER, C.LARGE_TWO_KERNEL):
             C.set_cluster_fusion(False)
             C.set_large_mode(mode)
@@ -695,6 +696,63 @@ def test_large_paths_agree(cuda_fft, oracle, n):
             assert np.array_equal(cuda_fft.irfft_batch(rref, 2 * n), bref), tag
     finally:
         C.set_large_mode(C.LARGE_AUTO)
+        C.set_split_min_log2n(15)
+
+
+@pytest.mark.parametrize("n", [8192, 16384, 32768])
+def test_split_kernel_on_device(cuda_fft, cuda_fft_fast, oracle, n):
+    """The warp-specialised split kernel (fft_split32.cuh; default for 2^15, selectable for 2^13 / 2^14): C2C
+    both directions, rfft / irfft, split (SoA) rows; ~20 transforms per team so every intermediate slot is
+    reused several times; grids of one team up to the full device; repeated launches (counters re-zeroed);
+    no cooperative-launch fallback happened."""
+    import torch
+
+    rows = 800 if n == 32768 else 3000
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.view_as_complex((torch.rand((rows, n, 2), generator=g, device="cuda") * 2 - 1).contiguous())
+    xr = (torch.rand((rows, 2 * n), generator=g, device="cuda") * 2 - 1).contiguous()
+    C = cuda_fft.ctx
+    fb0 = C.fallback_count
+    outs, routs = [], []
+    try:
+        C.set_split_min_log2n(13)
+        cuda_fft_fast.ctx.set_split_min_log2n(13)
+        for max_ctas in (0, 4, 24, 140):
+            C.set_max_ctas(max_ctas)
+            y = torch.empty_like(x)
+            for _ in range(3):
+                cuda_fft.fft_batch(x, out=y)
+            torch.cuda.synchronize()
+            outs.append(y)
+            routs.append(cuda_fft.rfft_batch(xr))
+            torch.cuda.synchronize()
+        C.set_max_ctas(0)
+        pick = [0, 1, 2, 36, 37, 73, 74, 148, 149, rows // 2, rows - 2, rows - 1]
+        xs, xrs = x[pick].cpu().numpy(), xr[pick].cpu().numpy()
+        ref = oracle.fft_batch(xs, nthreads=8)
+        rref = oracle.rfft_batch(xrs, nthreads=8)
+        assert np.array_equal(outs[0][pick].cpu().numpy(), ref)
+        assert np.array_equal(routs[0][pick].cpu().numpy(), rref)
+        for y, yr in zip(outs[1:], routs[1:]):
+            assert torch.equal(torch.view_as_real(y), torch.view_as_real(outs[0]))
+            assert torch.equal(torch.view_as_real(yr), torch.view_as_real(routs[0]))
+        # inverse, irfft, SoA rows, FAST mode on the sampled rows (host-pointer path)
+        y = xs.copy()
+        cuda_fft.fft_batch(y, inverse=True)
+        assert np.array_equal(y, oracle.fft_batch(xs, inverse=True, nthreads=8))
+        assert np.array_equal(cuda_fft.irfft_batch(rref, 2 * n), oracle.irfft_batch(rref, 2 * n, nthreads=8))
+        re, im = np.ascontiguousarray(xs[3].real), np.ascontiguousarray(xs[3].imag)
+        cuda_fft.fft_split(re, im)
+        assert np.array_equal(re, ref[3].real) and np.array_equal(im, ref[3].imag)
+        z = xs.copy()
+        cuda_fft_fast.fft_batch(z)
+        assert rel_l2(z, ref) <= TOL
+        assert rel_l2(cuda_fft_fast.rfft_batch(xrs), rref) <= TOL
+        assert C.fallback_count == fb0
+    finally:
+        C.set_max_ctas(0)
+        C.set_split_min_log2n(15)
+        cuda_fft_fast.ctx.set_split_min_log2n(15)
 
 
 def test_large_pipelined_many_transforms_per_team_on_device(cuda_fft, oracle):
@@ -710,6 +768,7 @@ def test_large_pipelined_many_transforms_per_team_on_device(cuda_fft, oracle):
     C = cuda_fft.ctx
     outs, routs = [], []
     try:
+        C.set_split_min_log2n(16)
         C.set_large_mode(C.LARGE_PIPELINED)
         for max_ctas in (0, 8, 24, 160):
             C.set_max_ctas(max_ctas)
@@ -723,6 +782,7 @@ def test_large_pipelined_many_transforms_per_team_on_device(cuda_fft, oracle):
     finally:
         C.set_max_ctas(0)
         C.set_large_mode(C.LARGE_AUTO)
+        C.set_split_min_log2n(15)
     pick = [0, 1, 36, 37, 73, 74, 700, rows - 2, rows - 1]
     assert np.array_equal(outs[0][pick].cpu().numpy(), oracle.fft_batch(x[pick].cpu().numpy(), nthreads=8))
     assert np.array_equal(routs[0][pick].cpu().numpy(), oracle.rfft_batch(xr[pick].cpu().numpy(), nthreads=8))
