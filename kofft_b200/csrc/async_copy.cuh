@@ -159,6 +159,29 @@ KD float4 ldcg_hint4(const void *p, unsigned long long pol)
 }
 KD void nano_sleep(unsigned ns) { __nanosleep(ns); }
 
+// one acquire load after a relaxed polling loop has seen the count: LDG.STRONG.GPU + CCTL.IVALL, no MEMBAR
+KD unsigned flag_load_acquire(const unsigned *c)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+    return v;
+}
+// warp vote: true iff the predicate holds on every lane (the result is warp-uniform by construction)
+KD bool warp_all(bool p) { return __all_sync(0xffffffffu, p) != 0; }
+
+// ---- TMA tensor-map loads (cp.async.bulk.tensor, SASS UTMALDG) -----------------------------------
+// The map is a CUtensorMap encoded on the host (cuTensorMapEncodeTiled) and passed as a __grid_constant__
+// kernel parameter.  c0 = element offset in the innermost dimension, c1 = row.
+struct alignas(64) TmaMap {
+    unsigned long long opaque[16];
+};
+KD void tma_load_2d(void *dst_smem, const TmaMap *map, int c0, int c1, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 #elif defined(KOFFT_EMU)
 
 inline void named_barrier(int id, int nthreads) { cuda_emu::named_barrier(id, nthreads); }
@@ -226,6 +249,30 @@ inline void bulk_copy_g2s(void *dst_smem, const void *src, unsigned bytes, unsig
     memcpy(dst_smem, src, bytes);
     EmuMbar &m = emu_mbar(bar);
     m.pending -= static_cast<int>(bytes);
+    if (m.pending == 0) m.completed++;
+}
+
+inline unsigned flag_load_acquire(const unsigned *c) { return *c; }
+inline bool warp_all(bool p) { return cuda_emu::warp_all(p); }
+// host stand-in of a 2-D tiled tensor map over f32 elements: dims / strides as cuTensorMapEncodeTiled takes them
+struct TmaMap {
+    const void *base;
+    unsigned long long dim0, dim1;   // elements
+    unsigned long long stride1;      // bytes between rows
+    unsigned box0, box1;             // elements
+    unsigned long long pad[11];
+};
+inline void tma_load_2d(void *dst_smem, const TmaMap *map, int c0, int c1, unsigned long long *bar)
+{
+    if ((reinterpret_cast<uintptr_t>(dst_smem) & 127) % 16) abort();
+    if ((map->box0 * 4) % 16 || (map->stride1 % 16) || (reinterpret_cast<uintptr_t>(map->base) & 15)) abort();
+    if (c0 < 0 || c1 < 0 || (unsigned long long)c0 + map->box0 > map->dim0 || (unsigned long long)c1 + map->box1 > map->dim1) abort();
+    char *d = static_cast<char *>(dst_smem);
+    for (unsigned r = 0; r < map->box1; r++)
+        memcpy(d + (size_t)r * map->box0 * 4, static_cast<const char *>(map->base) + (size_t)(c1 + r) * map->stride1 + (size_t)c0 * 4,
+               (size_t)map->box0 * 4);
+    EmuMbar &m = emu_mbar(bar);
+    m.pending -= static_cast<int>(map->box0 * map->box1 * 4);
     if (m.pending == 0) m.completed++;
 }
 

@@ -104,7 +104,12 @@ enum SplitEpilogue : int { SPLIT_STORE = 0, SPLIT_TWIST = 1 };
 #define KOFFT_SPLIT_REGS_B 160
 #endif
 
-template <int LA, bool EXACT, class IO, int EPI>
+// STAGED (LA = 10, plain contiguous rows): pass A's tile arrives by TMA tensor-map loads (four boxes of 256 rows x 8
+// columns, SASS UTMALDG) in the exchange buffer itself while the previous tile's second register pass runs and
+// stores -- the HBM latency of a tile is hidden behind the previous tile's arithmetic at no cost in shared
+// memory.  The first register pass is "in place" in index space (a thread reads and writes the same 32
+// positions of its column), so the landed tile doubles as the exchange buffer without an extra barrier.
+template <int LA, bool EXACT, class IO, int EPI, bool STAGED = false>
 struct Split32 {
     static_assert(LA >= 8 && LA <= 10, "N = 2^13 .. 2^15");
     static constexpr int L = LA + 5;
@@ -131,7 +136,11 @@ struct Split32 {
     // warp (COLS columns x 16/COLS consecutive t) hit 16 distinct 8-byte banks
     static constexpr int PADN = NR + (NR >> 5);
     static constexpr int RSA = PADN + (COLS == 8 ? 2 : 1);
-    static constexpr int XA = COLS * RSA;
+    // STAGED: the tile as the TMA delivers it, row-major [NR rows][COLS] in NBOX boxes of 256 rows
+    static constexpr int NBOX = NR / 256;
+    static_assert(!STAGED || (LA == 10 && IoTraits<IO>::kRowPtr), "staging: 2^15 points, plain contiguous rows");
+    static constexpr int XA = STAGED ? NR * COLS : COLS * RSA;
+    static constexpr unsigned TILE_BYTES = 8192u * 8u;
     // pass-A second-pass twiddles: [TA][33] (k1-dependent, shared by the columns)
     static constexpr int TWA = TA * 33;
     // pass-B transposition: per warp two halves of 16 rows x 34 (16-byte accesses, conflict-free)
@@ -141,7 +150,8 @@ struct Split32 {
     static constexpr int OFF_TWA = (XA + 1) & ~1;
     static constexpr int OFF_XB = (OFF_TWA + TWA + 1) & ~1;
     static constexpr int OFF_RTW = OFF_XB + B_WARPS * XB;
-    static constexpr int SMEM_BYTES = (OFF_RTW + RTW) * 8;
+    static constexpr int OFF_BAR = OFF_RTW + RTW; // the mbarrier of the staged tile loads
+    static constexpr int SMEM_BYTES = (OFF_BAR + 2) * 8;
     static constexpr bool HINT = IoTraits<IO>::kHint;
 
     static KD unsigned goal_a(long i) { return (unsigned)(NT * (i / SLOTS + 1)); }
@@ -193,7 +203,7 @@ struct Split32 {
             if (tid == 0 && i >= SLOTS) {
                 const unsigned want = goal_b(i - SLOTS);
                 while (flag_load(cntB + i % SLOTS) < want) nano_sleep(32);
-                flag_acquire();
+                (void)flag_load_acquire(cntB + i % SLOTS);
             }
             named_barrier(1, A_THREADS);
 #pragma unroll
@@ -204,6 +214,95 @@ struct Split32 {
             for (int w = 0; w < 32; w++) stg_hint(o + ((long)A1::dst_index(t, 0, w) << 5), x[w], pol.last);
             named_barrier(1, A_THREADS); // the exchange buffer is free again; every thread's stores are issued
             if (tid == 0) flag_arrive(cntA + i % SLOTS);
+        }
+    }
+
+
+    // ------------------------------------------------------------------------------------------
+    // A warps, STAGED variant (see the struct comment).  The tile lands row-major, [1024 rows][8 columns] (TMA
+    // destinations are 128-byte aligned, so the four boxes are contiguous).  Thread mappings (tid 0 .. 255):
+    //   first pass : column tid & 7, t0 = tid >> 3; reads rows q 32 + t0 (a half warp = 8 columns x 2 consecutive
+    //                rows = 16 consecutive banks).  A WARP owns, for every q, the four rows q 32 + 4w .. + 3 of
+    //                the 8 columns, reads them and writes its results back into the same set of positions
+    //                (__syncwarp in between): output c of thread t0 goes to row c 32 + (t0 ^ bit3(c)).
+    //   second pass: column tid & 7, k1 = ((tid >> 3) & 3) 8 + (tid >> 5); reads rows k1 32 + (q ^ bit3(k1)).  The
+    //                two k1 of a half warp differ in bit 3, so their rows have different parity = different banks
+    //                (rows are 64 bytes: without the swap every row of the same q would share a bank).
+    // ------------------------------------------------------------------------------------------
+    static KD void issue_tile(const TmaMap *map, float2 *stage, unsigned long long *bar, long row, int kb)
+    {
+        mbar_expect_tx(bar, TILE_BYTES);
+#pragma unroll
+        for (int b = 0; b < NBOX; b++)
+            tma_load_2d(stage + b * 256 * COLS, map, kb * COLS * 2, (int)(row * NR + b * 256), bar);
+    }
+    static KD void a_role_staged(const IO &io, const Tw0W &tw0, const float2 *__restrict__ table, long cnt, long team,
+                                 long teams, int kb, float2 *__restrict__ slots, float2 *smem, unsigned *cntA,
+                                 unsigned *cntB, int tid, const TmaMap *map, unsigned long long *bar)
+    {
+        const long n = 1L << L;
+        const int col = tid & 7, t0 = tid >> 3;
+        const int k1 = ((tid >> 3) & 3) * 8 + (tid >> 5);
+        float2 *stage = smem;
+        float2 *twa = smem + OFF_TWA;
+        const L2Policy pol = make_l2_policy();
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        for (int i = tid; i < TA * 31; i += A_THREADS) {
+            const int kk = i / 31, e = i - kk * 31;
+            int tl = 0;
+            while ((2 << tl) - 1 <= e) tl++;
+            const int c = e + 1 - (1 << tl);
+            twa[kk * 33 + e] = table[(long)(kk + (c << RA0)) << (LA - 1 - RA0 - tl + 5)];
+        }
+        named_barrier(1, A_THREADS);
+        if (tid == 0 && cnt > 0) issue_tile(map, stage, bar, team, kb);
+        const float2 *tw1 = twa + k1 * 33;
+        float2 *s0 = stage + t0 * COLS + col;        // row t0 (+ q 32 rows)
+        float2 *s0x = stage + (t0 ^ 1) * COLS + col; // the neighbour's row, for outputs with bit 3 set
+        const int sbit = (k1 >> 3) & 1;
+        const float2 *s1e = stage + (k1 * 32 + sbit) * COLS + col; // even q: row k1 32 + q + sbit
+        const float2 *s1o = stage + (k1 * 32 - sbit) * COLS + col; // odd q:  row k1 32 + q - sbit
+        const long j0 = (long)kb * COLS + col;
+        unsigned phase = 0;
+        for (long i = 0; i < cnt; i++) {
+            float2 x[WIDE];
+            mbar_wait(bar, phase);
+            phase ^= 1;
+#pragma unroll
+            for (int q = 0; q < 32; q++) x[q] = io.from_raw(s0[q * 32 * COLS]);
+            A0::compute(x, tw0.v);
+            warp_sync(); // the warp has read its rows: they may be rewritten
+#pragma unroll
+            for (int w = 0; w < 32; w++) {
+                const int c = bitrev(w, 5);
+                (((c >> 3) & 1) ? s0x : s0)[c * 32 * COLS] = x[w];
+            }
+            named_barrier(1, A_THREADS); // exchange; also: every thread is past the previous tile's stores
+            if (tid == 0 && i > 0) flag_arrive(cntA + (i - 1) % SLOTS);
+#pragma unroll
+            for (int q = 0; q < 32; q++) x[q] = ((q & 1) ? s1o : s1e)[q * COLS];
+            // the slot is rewritten: every B warp of the team must have consumed transform i - SLOTS
+            if (tid == 0 && i >= SLOTS) {
+                const unsigned want = goal_b(i - SLOTS);
+                while (flag_load(cntB + i % SLOTS) < want) nano_sleep(32);
+                (void)flag_load_acquire(cntB + i % SLOTS);
+            }
+            named_barrier(1, A_THREADS); // the buffer is free: the next tile may land
+            if (tid == 0 && i + 1 < cnt) {
+                fence_proxy_async();
+                issue_tile(map, stage, bar, team + (i + 1) * teams, kb);
+            }
+            A1::compute(x, tw1);
+            float2 *o = slots + (i % SLOTS) * n + j0;
+#pragma unroll
+            for (int w = 0; w < 32; w++) stg_hint(o + ((long)(k1 + (bitrev(w, 5) << 5)) << 5), x[w], pol.last);
+        }
+        if (cnt > 0) {
+            named_barrier(1, A_THREADS);
+            if (tid == 0) flag_arrive(cntA + (cnt - 1) % SLOTS);
         }
     }
 
@@ -222,7 +321,6 @@ struct Split32 {
         const int kh0 = NR - k0 - 15;    // high half: their mirrors, ascending (lane l mirrors lane 31 - l)
         int k = h ? kh0 + lp : k0 + lp;
         if (SPECIAL && lane == 16) k = 0;
-        const L2Policy pol = make_l2_policy();
         float2 twb[31];
 #pragma unroll
         for (int tl = 0; tl < 5; tl++)
@@ -235,25 +333,31 @@ struct Split32 {
             for (int wi = 0; wi < 32; wi++) rtws[wi * 32] = KOFFT_LDG(io.rtw + k + ((long)bitrev(wi, 5) << LA));
         }
         warp_sync();
-        for (long i = 0; i < cnt; i++) {
-            const long row = team + i * teams;
+        // 16-byte asynchronous copies (LDGSTS, L2 only): instruction j fetches row j of each half (256 bytes per
+        // half warp) straight into the transposition region
+        auto fetch = [&](long i) {
             const float2 *slot = slots + (i % SLOTS) * n;
-            if (lane == 0) {
-                const unsigned want = goal_a(i);
-                while (flag_load(cntA + i % SLOTS) < want) nano_sleep(32);
-                flag_acquire();
-            }
-            warp_sync();
-            // 16-byte coalesced loads: instruction j fetches row j of each half (256 bytes per half warp)
-            float4 v[16];
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 int rj = h ? kh0 + j : k0 + j;
                 if (SPECIAL && j == 0 && h) rj = 0;
-                v[j] = ldcg_hint4(slot + (long)rj * 32 + 2 * lp, pol.first);
+                cp_async16(tb + j * RSB + 2 * lp, slot + (long)rj * 32 + 2 * lp);
             }
-#pragma unroll
-            for (int j = 0; j < 16; j++) *reinterpret_cast<float4 *>(tb + j * RSB + 2 * lp) = v[j];
+            cp_async_commit();
+        };
+        bool fetched = false;
+        for (long i = 0; i < cnt; i++) {
+            const long row = team + i * teams;
+            if (!fetched) {
+                // every lane polls (one broadcast request per iteration): the warp stays converged, which keeps the
+                // shuffles below plain SHFL instructions (behind a one-lane polling loop the compiler guards every
+                // shuffle with a convergence sequence: 2600 extra instructions per tile, profiles/r03a)
+                const unsigned want = goal_a(i);
+                while (flag_load(cntA + i % SLOTS) < want) nano_sleep(32);
+                (void)flag_load_acquire(cntA + i % SLOTS);
+                fetch(i);
+            }
+            cp_async_wait_all();
             warp_sync();
             if (lane == 0) flag_arrive_relaxed(cntB + i % SLOTS); // the warp's reads of the slot are complete
             float2 x[WIDE];
@@ -263,7 +367,16 @@ struct Split32 {
                 x[2 * q2] = make_float2(e.x, e.y);
                 x[2 * q2 + 1] = make_float2(e.z, e.w);
             }
-            warp_sync(); // the region is rewritten by the next tile
+            warp_sync(); // the region is free again
+            // the next tile's rows, if its pass A is already complete: their L2 latency hides behind this tile's arithmetic
+            fetched = false;
+            if (i + 1 < cnt) {
+                if (warp_all(flag_load(cntA + (i + 1) % SLOTS) >= goal_a(i + 1))) {
+                    (void)flag_load_acquire(cntA + (i + 1) % SLOTS);
+                    fetch(i + 1);
+                    fetched = true;
+                }
+            }
             PB::compute(x, twb);
             // register wi holds bin K = k + bitrev(wi) 2^LA
             if constexpr (EPI == SPLIT_TWIST) {
@@ -272,30 +385,29 @@ struct Split32 {
                 for (int wi = 0; wi < 32; wi++) {
                     const float2 p = x[31 - wi];
                     float2 ym = make_float2(shfl_xor_f(p.x, 31), shfl_xor_f(p.y, 31));
-                    if (SPECIAL) {
-                        if (lane == 15) ym = p; // row 2^(LA-1): m - K = 2^(LA-1) + (31 - c) 2^LA, its own register 31 - wi
-                        if (lane == 16) ym = x[bitrev((32 - bitrev(wi, 5)) & 31, 5)]; // row 0: m - K = (32 - c) 2^LA
+                    if (SPECIAL) { // selects, not branches: the warp stays converged for the shuffles
+                        // row 2^(LA-1) (lane 15): m - K = 2^(LA-1) + (31 - c) 2^LA, its own register 31 - wi;
+                        // row 0 (lane 16): m - K = (32 - c) 2^LA
+                        const float2 q = x[bitrev((32 - bitrev(wi, 5)) & 31, 5)];
+                        ym.x = lane == 15 ? p.x : (lane == 16 ? q.x : ym.x);
+                        ym.y = lane == 15 ? p.y : (lane == 16 ? q.y : ym.y);
                     }
                     const float2 tw = rtws[wi * 32];
                     if (SPECIAL && wi == 0) {
-                        if (lane == 16) { // bins 0 and m (src/rfft.rs:450-452)
-                            stg_hint(o, make_float2(add_rn(x[0].x, x[0].y), 0.0f), pol.first);
-                            stg_hint(o + io.m, make_float2(sub_rn(x[0].x, x[0].y), 0.0f), pol.first);
-                        } else {
-                            stg_hint(o, io.twist(x[0], ym, tw), pol.first);
-                        }
+                        // lane 16 holds row 0: bins 0 and m (src/rfft.rs:450-452)
+                        float2 v0 = io.twist(x[0], ym, tw);
+                        if (lane == 16) v0 = make_float2(add_rn(x[0].x, x[0].y), 0.0f);
+                        o[0] = v0;
+                        if (lane == 16) o[io.m] = make_float2(sub_rn(x[0].x, x[0].y), 0.0f);
                     } else {
-                        stg_hint(o + ((long)bitrev(wi, 5) << LA), io.twist(x[wi], ym, tw), pol.first);
+                        o[(long)bitrev(wi, 5) << LA] = io.twist(x[wi], ym, tw);
                     }
                 }
             } else {
 #pragma unroll
                 for (int wi = 0; wi < 32; wi++) {
                     const int K = k + (bitrev(wi, 5) << LA);
-                    if constexpr (HINT)
-                        io.store_hint(row, K, x[wi], pol.first);
-                    else
-                        io.store(row, K, x[wi]);
+                    io.store(row, K, x[wi]);
                 }
             }
         }
@@ -304,7 +416,7 @@ struct Split32 {
     // rows: transforms in the batch; scratch: teams * SLOTS * 2^L complex; flags: teams * FLAG_STRIDE
     // counters, zero at launch.  gridDim.x is a multiple of NT and every CTA is resident.
     static KD void run(const IO &io, const Tw0W &tw0, const float2 *__restrict__ table, long rows,
-                       float2 *__restrict__ scratch, float2 *smem, unsigned *flags)
+                       float2 *__restrict__ scratch, float2 *smem, unsigned *flags, const TmaMap *map = nullptr)
     {
         const int tid = threadIdx.x;
         const long n = 1L << L;
@@ -315,7 +427,11 @@ struct Split32 {
         float2 *slots = scratch + team * SLOTS * n;
         if (tid < A_THREADS) {
             setmaxnreg_dec<KOFFT_SPLIT_REGS_A>();
-            a_role(io, tw0, table, cnt, team, teams, kb, slots, smem, cntA, cntB, tid);
+            if constexpr (STAGED)
+                a_role_staged(io, tw0, table, cnt, team, teams, kb, slots, smem, cntA, cntB, tid, map,
+                              reinterpret_cast<unsigned long long *>(smem + OFF_BAR));
+            else
+                a_role(io, tw0, table, cnt, team, teams, kb, slots, smem, cntA, cntB, tid);
         } else {
             setmaxnreg_inc<KOFFT_SPLIT_REGS_B>();
             const int wl = tid - A_THREADS;
@@ -328,13 +444,13 @@ struct Split32 {
 };
 
 #ifdef __CUDACC__
-template <int LA, bool EXACT, class IO, int EPI>
+template <int LA, bool EXACT, class IO, int EPI, bool STAGED>
 __global__ void __launch_bounds__(512, 1)
     split32_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0W tw0, const float2 *__restrict__ table,
-                   long rows, float2 *__restrict__ scratch, unsigned *flags)
+                   long rows, float2 *__restrict__ scratch, unsigned *flags, const __grid_constant__ TmaMap map)
 {
     extern __shared__ __align__(128) float2 smem[];
-    Split32<LA, EXACT, IO, EPI>::run(io, tw0, table, rows, scratch, smem, flags);
+    Split32<LA, EXACT, IO, EPI, STAGED>::run(io, tw0, table, rows, scratch, smem, flags, &map);
 }
 #endif
 

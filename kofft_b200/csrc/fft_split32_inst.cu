@@ -2,6 +2,9 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <cuda.h>
+#include <dlfcn.h>
+
 #include "fft_split32.cuh"
 #include "launch.h"
 
@@ -9,13 +12,59 @@ namespace kofft {
 
 namespace {
 
-// one persistent cooperative launch, one 512-thread CTA per SM, teams of NT CTAs
+// The [rows * 2^LA][32 complex] view of the input rows as a 2-D tensor of f32 (64 per row), boxes of 256 rows x
+// `cols` complex.  cuTensorMapEncodeTiled is a driver entry point: resolved through the runtime, no -lcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+cudaError_t encode_rows_map(TmaMap *out, const void *base, unsigned long long total_rows, unsigned cols)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) { // the driver library is already in the process (the runtime loaded it)
+        void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libcuda.so.1", RTLD_NOW);
+        void *p = h ? dlsym(h, "cuTensorMapEncodeTiled") : nullptr;
+        if (getenv("KOFFT_CUDA_VERBOSE")) fprintf(stderr, "[kofft_cuda] cuTensorMapEncodeTiled at %p\n", p);
+        if (!p) return cudaErrorNotSupported;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    static_assert(sizeof(TmaMap) == sizeof(CUtensorMap), "opaque tensor map");
+    const cuuint64_t dims[2] = {64, total_rows};
+    const cuuint64_t strides[1] = {256};
+    const cuuint32_t box[2] = {2 * cols, 256};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (getenv("KOFFT_CUDA_VERBOSE")) fprintf(stderr, "[kofft_cuda] tensor map over %llu rows of 256 B: CUresult %d\n", total_rows, (int)r);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int LA, bool EXACT, class IO, int EPI, bool STAGED>
+cudaError_t launch_split_v(const IO &io, const LaunchArgs &a, SplitArgs &g);
+
+// a.staged: the host verified 16-byte alignment of the rows (TMA tile loads)
 template <int LA, bool EXACT, class IO, int EPI>
 cudaError_t launch_split(const IO &io, const LaunchArgs &a, SplitArgs &g)
 {
-    using F = Split32<LA, EXACT, IO, EPI>;
+    if constexpr (LA == 10 && IoTraits<IO>::kRowPtr) {
+        if (a.staged && (a.rows << LA) < (1L << 31)) return launch_split_v<LA, EXACT, IO, EPI, true>(io, a, g);
+    }
+    return launch_split_v<LA, EXACT, IO, EPI, false>(io, a, g);
+}
+
+// one persistent cooperative launch, one 512-thread CTA per SM, teams of NT CTAs
+template <int LA, bool EXACT, class IO, int EPI, bool STAGED>
+cudaError_t launch_split_v(const IO &io, const LaunchArgs &a, SplitArgs &g)
+{
+    using F = Split32<LA, EXACT, IO, EPI, STAGED>;
     static_assert(F::SLOTS == kSplitSlots && F::FLAG_STRIDE == kPipeFlagStride, "host-side sizes");
-    auto kern = split32_kernel<LA, EXACT, IO, EPI>;
+    auto kern = split32_kernel<LA, EXACT, IO, EPI, STAGED>;
+    TmaMap map = {};
+    if constexpr (STAGED) {
+        cudaError_t e = encode_rows_map(&map, io.in, (unsigned long long)a.rows << LA, F::COLS);
+        if (e != cudaSuccess) return e;
+    }
     static PerDevice occ_pd;
     int &occ = occ_pd.get();
     if (occ == 0) {
@@ -39,7 +88,7 @@ cudaError_t launch_split(const IO &io, const LaunchArgs &a, SplitArgs &g)
     float2 *scratch = g.scratch;
     unsigned *flags = g.flags;
     const float2 *table = a.table;
-    void *args[] = {(void *)&io, (void *)&tw0, (void *)&table, (void *)&rows, (void *)&scratch, (void *)&flags};
+    void *args[] = {(void *)&io, (void *)&tw0, (void *)&table, (void *)&rows, (void *)&scratch, (void *)&flags, (void *)&map};
     cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(unsigned) * F::FLAG_STRIDE * teams, a.stream);
     if (e != cudaSuccess) return e;
     return cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)(teams * F::NT)), dim3(F::CTA), args,

@@ -90,6 +90,12 @@ struct kofft_cuda_ctx {
     // [3] small staging (windows), [4] two-pass (N > 16384) intermediate
     void *ws[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t ws_bytes[5] = {0, 0, 0, 0, 0};
+    // The device-pointer entry points are stream-ordered on the CALLER's stream, but [2] and [4] (and the
+    // dependency flags of the persistent kernels) are one per context: a call on another stream first waits for
+    // the event the previous user recorded (ws_acquire / ws_release), so two streams never share a scratch.
+    cudaEvent_t ws_event[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t ws_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ws_used[5] = {false, false, false, false, false};
     size_t large_scratch_bytes = size_t(256) << 20; // two-pass intermediate per batch chunk (measured: kernel
                                                    // length matters more than L2 residency, profiles/r01n)
     size_t istft_ws_limit = size_t(1) << 30;
@@ -132,6 +138,21 @@ int ensure_ws(kofft_cuda_ctx *ctx, int which, size_t bytes, void **out)
         ctx->ws_bytes[which] = bytes;
     }
     *out = ctx->ws[which];
+    return 0;
+}
+
+// before enqueuing work that uses workspace `which` on stream s / after enqueuing it
+int ws_acquire(kofft_cuda_ctx *ctx, int which, cudaStream_t s)
+{
+    if (ctx->ws_used[which] && ctx->ws_stream[which] != s) CU(cudaStreamWaitEvent(s, ctx->ws_event[which], 0));
+    return 0;
+}
+int ws_release(kofft_cuda_ctx *ctx, int which, cudaStream_t s)
+{
+    if (!ctx->ws_event[which]) CU(cudaEventCreateWithFlags(&ctx->ws_event[which], cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->ws_event[which], s));
+    ctx->ws_stream[which] = s;
+    ctx->ws_used[which] = true;
     return 0;
 }
 
@@ -187,9 +208,23 @@ void fill_tw0(const Table *t, int L, Tw0 *tw0)
         }
 }
 
+int dispatch_impl(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t rows, cudaStream_t stream, bool staged);
+
 // Common dispatch: the complex core has length n (power of two, >= 1), `rows` transforms.
 int dispatch(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t rows, cudaStream_t stream,
              bool staged = false)
+{
+    if (rows == 0) return KOFFT_OK;
+    if (n < 8192) return dispatch_impl(ctx, kind, io, n, rows, stream, staged);
+    // lengths that may run through the per-context intermediate / dependency flags (workspace 4)
+    int rc = ws_acquire(ctx, 4, stream);
+    if (rc) return rc;
+    rc = dispatch_impl(ctx, kind, io, n, rows, stream, staged);
+    if (rc) return rc;
+    return ws_release(ctx, 4, stream);
+}
+
+int dispatch_impl(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, size_t rows, cudaStream_t stream, bool staged)
 {
     if (rows == 0) return KOFFT_OK;
     LaunchArgs a;
@@ -411,7 +446,9 @@ void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize(); // tables and workspaces may still be in use on the callers' streams
+    for (int i = 0; i < 5; i++)
+        if (ctx->ws_event[i]) cudaEventDestroy(ctx->ws_event[i]);
     for (auto &kv : ctx->fft_tables) cudaFree(kv.second.dev);
     for (auto &kv : ctx->rfft_tables) cudaFree(kv.second.dev);
     for (auto &kv : ctx->blue_tables) {
@@ -602,6 +639,8 @@ static int bluestein_c2c(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, siz
     void *ws = nullptr;
     int rc = ensure_ws(ctx, 2, chunk * m * sizeof(float2), &ws);
     if (rc) return rc;
+    rc = ws_acquire(ctx, 2, s);
+    if (rc) return rc;
     for (size_t r0 = 0; r0 < batch; r0 += chunk) {
         BluesteinArgs b;
         b.rows = static_cast<long>(batch - r0 < chunk ? batch - r0 : chunk);
@@ -626,7 +665,7 @@ static int bluestein_c2c(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, siz
             }
         }
     }
-    return KOFFT_OK;
+    return ws_release(ctx, 2, s);
 }
 
 int kofft_cuda_fft_strided_f32(kofft_cuda_ctx *ctx, const void *d_in, size_t in_stride, size_t in_dist,
@@ -910,6 +949,8 @@ int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nfram
     void *time = nullptr;
     int rc = ensure_ws(ctx, 2, chunk * per_channel, &time);
     if (rc) return rc;
+    rc = ws_acquire(ctx, 2, s);
+    if (rc) return rc;
     for (size_t c0 = 0; c0 < channels; c0 += chunk) {
         const size_t nc = (channels - c0 < chunk) ? channels - c0 : chunk;
         if (nframes > 0) {
@@ -936,7 +977,7 @@ int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nfram
         if (e != cudaSuccess) return fail_cuda(e, "ola launch");
         ctx->launches++;
     }
-    return KOFFT_OK;
+    return ws_release(ctx, 2, s);
 }
 
 } // extern "C"
@@ -1060,6 +1101,7 @@ struct kofft_cuda_stft_stream {
     float *d_window = nullptr;
     float *d_carry = nullptr; // [channels][win_len]: samples received but not yet behind an emitted frame
     size_t carry_len = 0;     // < win_len between calls
+    size_t skip = 0;          // hop > win_len: samples still to drop before the next frame starts (carry_len == 0 then)
     float *d_work = nullptr;  // [channels][carry_len + n], grow-only
     size_t work_floats = 0;
 };
@@ -1131,7 +1173,7 @@ void kofft_cuda_stft_stream_destroy(kofft_cuda_stft_stream *s)
 // frames a push of n more samples per channel will emit (flush: n = 0, flush != 0)
 size_t kofft_cuda_stft_stream_frames(const kofft_cuda_stft_stream *s, size_t n, int flush)
 {
-    const size_t have = s->carry_len + n;
+    const size_t have = s->carry_len + (n > s->skip ? n - s->skip : 0);
     if (flush) return (have + s->hop - 1) / s->hop; // every start position < total length (src/stft.rs:193)
     return have >= s->win_len ? (have - s->win_len) / s->hop + 1 : 0;
 }
@@ -1144,10 +1186,15 @@ int kofft_cuda_stft_stream_push(kofft_cuda_stft_stream *s, const float *d_sample
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = pick_stream(ctx, stream);
     if (n && ld < n) return KOFFT_ERR_MISMATCHED_LENGTHS;
-    const size_t have = s->carry_len + n;
     const size_t k = kofft_cuda_stft_stream_frames(s, n, flush);
     if (nframes_out) *nframes_out = k;
     if (k > frames_cap) return KOFFT_ERR_MISMATCHED_LENGTHS;
+    // hop > win_len: the samples between the end of one frame's hop and the next frame's start are dropped
+    const size_t drop = s->skip < n ? s->skip : n;
+    s->skip -= drop;
+    d_samples += drop;
+    n -= drop;
+    const size_t have = s->carry_len + n;
     if (have == 0) return KOFFT_OK;
     int rc = stream_grow(&s->d_work, &s->work_floats, s->channels * have);
     if (rc) return rc;
@@ -1162,6 +1209,7 @@ int kofft_cuda_stft_stream_push(kofft_cuda_stft_stream *s, const float *d_sample
         if (rc) return rc;
     }
     const size_t used = k * s->hop;
+    if (!flush && used > have) s->skip += used - have; // the next frame starts beyond what has arrived
     const size_t rest = (flush || used >= have) ? 0 : have - used;
     if (rest)
         CU(cudaMemcpy2DAsync(s->d_carry, s->win_len * 4, s->d_work + used, have * 4, rest * 4, s->channels,

@@ -47,6 +47,25 @@ def _is_tensor(x) -> bool:
     return torch is not None and isinstance(x, torch.Tensor)
 
 
+def _check_tensor(t, dtype, ndim=None, device=None, name="input", shape=None):
+    """Every tensor whose data_ptr() reaches the C ABI goes through here: the kernels trust the pointer."""
+    if not _is_tensor(t):
+        raise TypeError(f"{name} must be a torch tensor")
+    if not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must have dtype {dtype}, not {t.dtype}")
+    if not t.is_contiguous():
+        raise TypeError(f"{name} must be contiguous")
+    if ndim is not None and t.dim() != ndim:
+        raise TypeError(f"{name} must have {ndim} dimensions")
+    if device is not None and t.device.index != device:
+        raise TypeError(f"{name} lives on cuda:{t.device.index}, the context on cuda:{device}")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise MismatchedLengths()
+    return t
+
+
 def _c64(a, name="input") -> np.ndarray:
     if not isinstance(a, np.ndarray) or a.dtype != np.complex64:
         raise TypeError(f"{name} must be a numpy complex64 array (it is transformed in place)")
@@ -123,6 +142,11 @@ class Context:
 
     def set_rfft_table_fma(self, fma: bool) -> None:
         check(_lib.lib().kofft_cuda_set_rfft_table_fma(self.handle, int(bool(fma))))
+        self._rfft_fma = bool(fma)
+
+    @property
+    def rfft_table_fma(self) -> bool:
+        return getattr(self, "_rfft_fma", False)
 
     @property
     def launch_count(self) -> int:
@@ -304,11 +328,8 @@ class CudaFftImpl:
         CUDA torch.complex64 2-D tensor: stream-ordered on the current torch stream; `out`
         defaults to in place.  Returns the array/tensor holding the result."""
         if _is_tensor(x):
-            if x.dtype != torch.complex64 or x.dim() != 2 or not x.is_contiguous() or not x.is_cuda:
-                raise TypeError("expected a contiguous CUDA complex64 tensor [batch, n]")
-            out = x if out is None else out
-            if out.shape != x.shape or out.dtype != x.dtype or not out.is_contiguous():
-                raise MismatchedLengths()
+            _check_tensor(x, torch.complex64, 2, self.ctx.device)
+            out = x if out is None else _check_tensor(out, torch.complex64, 2, self.ctx.device, "out", x.shape)
             check(self._lib.kofft_cuda_fft_c2c_f32(self.ctx.handle, x.data_ptr(), out.data_ptr(), x.shape[1],
                                                   x.shape[0], int(inverse), _stream_of(x)))
             return out
@@ -321,10 +342,8 @@ class CudaFftImpl:
 
     def fft_split_batch(self, re, im, inverse: bool = False):
         """SoA rows on the device: re, im CUDA float32 [batch, n], in place."""
-        if not (_is_tensor(re) and _is_tensor(im)):
-            raise TypeError("device tensors expected")
-        if re.shape != im.shape:
-            raise MismatchedLengths()
+        _check_tensor(re, torch.float32, 2, self.ctx.device, "re")
+        _check_tensor(im, torch.float32, 2, self.ctx.device, "im", re.shape)
         check(self._lib.kofft_cuda_fft_split_f32(self.ctx.handle, re.data_ptr(), im.data_ptr(), re.data_ptr(),
                                                 im.data_ptr(), re.shape[1], re.shape[0], int(inverse),
                                                 _stream_of(re)))
@@ -333,11 +352,16 @@ class CudaFftImpl:
     def fft_strided_batch(self, x, n: int, batch: int, in_stride: int, in_dist: int, out=None,
                           out_stride: Optional[int] = None, out_dist: Optional[int] = None, inverse: bool = False):
         """Batched `fft_out_of_place_strided` on a flat CUDA complex64 tensor."""
-        out = x if out is None else out
+        _check_tensor(x, torch.complex64, None, self.ctx.device)
+        out = x if out is None else _check_tensor(out, torch.complex64, None, self.ctx.device, "out")
         out_stride = in_stride if out_stride is None else out_stride
         out_dist = in_dist if out_dist is None else out_dist
         if in_stride == 0 or out_stride == 0:
             raise InvalidStride()
+        if n and batch:  # the last element either side touches must exist
+            if (batch - 1) * in_dist + (n - 1) * in_stride >= x.numel() or \
+                    (batch - 1) * out_dist + (n - 1) * out_stride >= out.numel():
+                raise MismatchedLengths()
         check(self._lib.kofft_cuda_fft_strided_f32(self.ctx.handle, x.data_ptr(), in_stride, in_dist,
                                                   out.data_ptr(), out_stride, out_dist, n, batch, int(inverse),
                                                   _stream_of(x)))
@@ -346,9 +370,12 @@ class CudaFftImpl:
     def rfft_batch(self, x, out=None):
         """Fused pack + FFT + twist per row: [batch, n] f32 -> [batch, n/2+1] complex64."""
         if _is_tensor(x):
+            _check_tensor(x, torch.float32, 2, self.ctx.device)
             b, n = x.shape
             if out is None:
                 out = torch.empty((b, n // 2 + 1), dtype=torch.complex64, device=x.device)
+            else:
+                _check_tensor(out, torch.complex64, 2, self.ctx.device, "out", (b, n // 2 + 1))
             check(self._lib.kofft_cuda_rfft_f32(self.ctx.handle, x.data_ptr(), out.data_ptr(), n, b, _stream_of(x)))
             return out
         a = _f32(x, writable=False)
@@ -361,11 +388,14 @@ class CudaFftImpl:
     def irfft_batch(self, x, n: int, out=None):
         """Fused untwist + IFFT + unpack per row: [batch, n/2+1] complex64 -> [batch, n] f32."""
         if _is_tensor(x):
+            _check_tensor(x, torch.complex64, 2, self.ctx.device)
             b = x.shape[0]
             if x.shape[1] != n // 2 + 1:
                 raise MismatchedLengths()
             if out is None:
                 out = torch.empty((b, n), dtype=torch.float32, device=x.device)
+            else:
+                _check_tensor(out, torch.float32, 2, self.ctx.device, "out", (b, n))
             check(self._lib.kofft_cuda_irfft_f32(self.ctx.handle, x.data_ptr(), out.data_ptr(), n, b, _stream_of(x)))
             return out
         a = _c64(x)

@@ -43,8 +43,12 @@ class RfftPlanner:
 
     def rfft_with_scratch(self, fft: CudaFftImpl, input, output, scratch) -> None:
         """src/rfft.rs:264-282"""
+        saved = fft.ctx.rfft_table_fma  # the table flavour is this planner's, not the shared context's
         fft.ctx.set_rfft_table_fma(self.fma_mul)
-        fft.rfft_with_scratch(input, output, scratch)
+        try:
+            fft.rfft_with_scratch(input, output, scratch)
+        finally:
+            fft.ctx.set_rfft_table_fma(saved)
 
     def rfft(self, fft: CudaFftImpl, input, output) -> None:
         """src/rfft.rs:285-299"""
@@ -52,8 +56,12 @@ class RfftPlanner:
 
     def irfft_with_scratch(self, fft: CudaFftImpl, input, output, scratch) -> None:
         """src/rfft.rs:302-320"""
+        saved = fft.ctx.rfft_table_fma
         fft.ctx.set_rfft_table_fma(self.fma_mul)
-        fft.irfft_with_scratch(input, output, scratch)
+        try:
+            fft.irfft_with_scratch(input, output, scratch)
+        finally:
+            fft.ctx.set_rfft_table_fma(saved)
 
     def irfft(self, fft: CudaFftImpl, input, output) -> None:
         """src/rfft.rs:323-337"""

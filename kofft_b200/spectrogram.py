@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from .errors import check
-from .fft import CudaFftImpl, _f32, _is_tensor, _stream_of
+from .fft import CudaFftImpl, _check_tensor, _f32, _is_tensor, _stream_of
 
 try:
     import torch
@@ -36,11 +36,15 @@ def stft_magnitudes(fft: CudaFftImpl, samples, win_len: int, hop: int):
 
 def stft_magnitudes_batch(fft: CudaFftImpl, signal, window, hop: int, nframes: int, out=None):
     """Device tensors: signal [channels, len], window [win_len] -> (mags [channels, nframes, win_len/2], max [channels])."""
-    assert _is_tensor(signal) and _is_tensor(window)
+    dev = fft.ctx.device
+    _check_tensor(signal, torch.float32, 2, dev, "signal")
+    _check_tensor(window, torch.float32, 1, dev, "window")
     ch, ln = signal.shape
     win_len = window.shape[0]
     if out is None:
         out = torch.empty((ch, nframes, win_len // 2), dtype=torch.float32, device=signal.device)
+    else:
+        _check_tensor(out, torch.float32, 3, dev, "out", (ch, nframes, win_len // 2))
     mx = torch.empty((ch,), dtype=torch.float32, device=signal.device)
     check(_lib.lib().kofft_cuda_stft_magnitudes_f32(fft.ctx.handle, signal.data_ptr(), ln, ch, window.data_ptr(), win_len,
                                                     hop, out.data_ptr(), nframes, mx.data_ptr(), _stream_of(signal)))

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib
 from .errors import InvalidHopSize, MismatchedLengths, check
-from .fft import CudaFftImpl, _f32, _is_tensor, _stream_of
+from .fft import CudaFftImpl, _check_tensor, _f32, _is_tensor, _stream_of
 
 try:
     import torch
@@ -35,10 +35,15 @@ def stft_batch(fft: CudaFftImpl, signal, window, hop_size: int, nframes: int, ou
     """signal [channels, len] -> frames [channels, nframes, win_len] complex64."""
     lib = _lib.lib()
     if _is_tensor(signal):
+        dev = fft.ctx.device
+        _check_tensor(signal, torch.float32, 2, dev, "signal")
+        _check_tensor(window, torch.float32, 1, dev, "window")
         ch, ln = signal.shape
         win_len = window.shape[0]
         if out is None:
             out = torch.empty((ch, nframes, win_len), dtype=torch.complex64, device=signal.device)
+        else:
+            _check_tensor(out, torch.complex64, 3, dev, "out", (ch, nframes, win_len))
         check(lib.kofft_cuda_stft_f32(fft.ctx.handle, signal.data_ptr(), ln, ch, window.data_ptr(), win_len,
                                       hop_size, out.data_ptr(), nframes, _stream_of(signal)))
         return out
@@ -56,7 +61,15 @@ def istft_batch(fft: CudaFftImpl, frames, window, hop_size: int, output, norm=No
     """frames [channels, nframes, win_len] -> accumulates into output [channels, out_len]."""
     lib = _lib.lib()
     if _is_tensor(frames):
+        dev = fft.ctx.device
+        _check_tensor(frames, torch.complex64, 3, dev, "frames")
         ch, nframes, win_len = frames.shape
+        _check_tensor(window, torch.float32, 1, dev, "window", (win_len,))
+        _check_tensor(output, torch.float32, 2, dev, "output")
+        if output.shape[0] != ch:
+            raise MismatchedLengths()
+        if norm is not None:
+            _check_tensor(norm, torch.float32, 2, dev, "norm", output.shape)
         out_len = output.shape[1]
         check(lib.kofft_cuda_istft_f32(fft.ctx.handle, frames.data_ptr(), nframes, ch, window.data_ptr(), win_len,
                                        hop_size, output.data_ptr(), out_len,

@@ -152,6 +152,18 @@ inline void syncwarp()
     }
     while (w.generation == gen) yield_to_scheduler();
 }
+// __all_sync over the full warp
+inline bool warp_all(bool p)
+{
+    WarpState &w = my_warp();
+    const unsigned lane = g_sched->threads[g_sched->current].tid.x & 31u;
+    w.xchg[lane] = p ? 1.0f : 0.0f;
+    syncwarp();
+    bool r = true;
+    for (int i = 0; i < 32; i++) r = r && w.xchg[i] != 0.0f;
+    syncwarp();
+    return r;
+}
 // __shfl_xor_sync over the full warp
 inline float shfl_xor(float v, int mask)
 {

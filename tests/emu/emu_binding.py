@@ -107,12 +107,12 @@ class EmuKernels:
 
 
 def _split32(self, kind, exact, L, rows, table, inp=None, in2=None, out=None, out2=None, aux=None,
-             p=(0, 0, 0, 0), scale=1.0, grid=8, skew=None):
+             p=(0, 0, 0, 0), scale=1.0, grid=8, skew=None, staged=False):
     """Split32::run (fft_split32.cuh) on `grid` CTAs of 512 threads (teams of 4 / 2 / 1 CTAs run concurrently)."""
     self.lib.kofft_emuk_set_skew(*(skew or (0, 0)))
     rc = self.lib.kofft_emuk_split32(KIND[kind], int(exact), L, rows, self._ptr(inp), self._ptr(in2), self._ptr(out),
                                      self._ptr(out2), self._ptr(aux), *[int(v) for v in p], C.c_float(scale),
-                                     self._ptr(table), grid, 0)
+                                     self._ptr(table), grid, int(staged))
     self.lib.kofft_emuk_set_skew(0, 0)
     assert rc == 0, rc
 

@@ -254,10 +254,12 @@ API int kofft_emuk_large(int kind, int exact, int L, long rows, const void *in, 
 
 // ---- the warp-specialised split kernel (fft_split32.cuh): Split32::run on `grid` CTAs of 512 threads; the CTAs
 // of a team run as interleaved coroutines so the A-role / B-role dependency flags are live
-template <int LA, bool EXACT, class IO, int EPI>
-static int run_split32(const IO &io, const float *table, long rows, int grid)
+static bool g_split_staged = false;
+
+template <int LA, bool EXACT, class IO, int EPI, bool STAGED>
+static int run_split32_v(const IO &io, const float *table, long rows, int grid)
 {
-    using F = Split32<LA, EXACT, IO, EPI>;
+    using F = Split32<LA, EXACT, IO, EPI, STAGED>;
     const long n = 1L << F::L;
     Tw0W tw0;
     memset(&tw0, 0, sizeof tw0);
@@ -277,12 +279,31 @@ static int run_split32(const IO &io, const float *table, long rows, int grid)
     float2 *base = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
     const size_t keep = cuda_emu::g_stack_bytes;
     cuda_emu::g_stack_bytes = 64 * 1024;
+    TmaMap map;
+    memset(&map, 0, sizeof map);
+    if constexpr (STAGED) { // the [rows * 2^LA][32 complex] view of the input, boxes of 256 rows x 8 complex
+        map.base = io.row_ptr(0);
+        map.dim0 = 64;
+        map.dim1 = (unsigned long long)rows << LA;
+        map.stride1 = 256;
+        map.box0 = 2 * F::COLS;
+        map.box1 = 256;
+    }
     cuda_emu::launch((unsigned)(teams * F::NT), F::CTA, [&] {
         float2 *sm = base + (size_t)cuda_emu::cluster_rank() * per;
-        F::run(io, tw0, tab, rows, scratch.data(), sm, flags.data());
+        F::run(io, tw0, tab, rows, scratch.data(), sm, flags.data(), &map);
     }, F::NT);
     cuda_emu::g_stack_bytes = keep;
     return 0;
+}
+
+template <int LA, bool EXACT, class IO, int EPI>
+static int run_split32(const IO &io, const float *table, long rows, int grid)
+{
+    if constexpr (LA == 10 && IoTraits<IO>::kRowPtr) {
+        if (g_split_staged) return run_split32_v<LA, EXACT, IO, EPI, true>(io, table, rows, grid);
+    }
+    return run_split32_v<LA, EXACT, IO, EPI, false>(io, table, rows, grid);
 }
 
 template <int LA, bool EXACT>
@@ -302,9 +323,9 @@ static int run_split32_kind(int kind, const Args &q, const float *table, long ro
 // L = 13 .. 15 is the length of the complex core
 API int kofft_emuk_split32(int kind, int exact, int L, long rows, const void *in, const void *in2, void *out, void *out2,
                            const void *aux, long p0, long p1, long p2, long p3, float scale, const float *table,
-                           int grid, int unused)
+                           int grid, int staged)
 {
-    (void)unused;
+    g_split_staged = staged != 0;
     Args q{in, in2, out, out2, aux, 1L << L, p0, p1, p2, p3, scale};
     switch (L) {
     case 13: return exact ? run_split32_kind<8, true>(kind, q, table, rows, grid) : run_split32_kind<8, false>(kind, q, table, rows, grid);

@@ -299,38 +299,42 @@ def test_f64_rfft_irfft_kernel_body(emuk, oracle, n):
     assert np.array_equal(z, oracle.irfft_batch_f64(ref, n)), n
 
 
-@pytest.mark.parametrize("L,grid,rows,skew", [(15, 8, 11, None), (15, 4, 6, (2, 9)), (14, 4, 7, None), (14, 2, 6, (1, 5)),
-                                              (13, 2, 5, None)])
-def test_split32_kernel_body(emuk, oracle, L, grid, rows, skew):
+@pytest.mark.parametrize("L,grid,rows,skew,staged", [(15, 8, 11, None, True), (15, 4, 6, (2, 9), True), (15, 8, 9, (1, 4), False),
+                                                     (14, 4, 7, None, False), (14, 2, 6, (1, 5), False), (13, 2, 5, None, False)])
+def test_split32_kernel_body(emuk, oracle, L, grid, rows, skew, staged):
     """Split32::run (fft_split32.cuh): warp-specialised CTAs (A warps: 2^(L-5)-point column transforms of an
     8192-element tile with one exchange; B warps: 32-point rows in one thread's registers, shuffle twist), teams
     of 4 / 2 / 1 CTAs, per-slot dependency counters between the roles; more transforms than 2 * SLOTS per team so
-    the intermediate ring wraps.  skew: part of the team runs late."""
+    the intermediate ring wraps.  skew: part of the team runs late.  staged: pass A's tiles arrive by TMA tensor-map
+    loads in the exchange buffer (C2C and rfft; irfft / SoA rows keep the plain loads)."""
+    import functools
+
+    emuk_split32 = functools.partial(emuk.split32, staged=staged)
     n = 1 << L
     rng = np.random.default_rng(1300 + L + grid)
     x = uniform_c64(rng, (rows, n))
     tab = oracle.twiddles(n)
     y = np.zeros_like(x)
-    emuk.split32("c2c_fwd", True, L, rows, tab, inp=x, out=y, grid=grid, skew=skew)
+    emuk_split32("c2c_fwd", True, L, rows, tab, inp=x, out=y, grid=grid, skew=skew)
     assert np.array_equal(y, oracle.fft_batch(x))
     y[...] = 0
-    emuk.split32("c2c_inv", True, L, rows, tab, inp=x, out=y, scale=float(np.float32(1) / np.float32(n)), grid=grid, skew=skew)
+    emuk_split32("c2c_inv", True, L, rows, tab, inp=x, out=y, scale=float(np.float32(1) / np.float32(n)), grid=grid, skew=skew)
     assert np.array_equal(y, oracle.fft_batch(x, inverse=True))
     xr = rng.uniform(-1, 1, (rows, 2 * n)).astype(np.float32)
     rtw = oracle.rfft_twiddles(n)
     yr = np.zeros((rows, n + 1), np.complex64)
-    emuk.split32("rfft", True, L, rows, tab, inp=xr, out=yr, aux=rtw, grid=grid, skew=skew)
+    emuk_split32("rfft", True, L, rows, tab, inp=xr, out=yr, aux=rtw, grid=grid, skew=skew)
     ref = oracle.rfft_batch(xr)
     assert np.array_equal(yr, ref)
     zr = np.zeros((rows, 2 * n), np.float32)
-    emuk.split32("irfft", True, L, rows, tab, inp=ref, out=zr, aux=rtw, scale=float(np.float32(1) / np.float32(n)), grid=grid, skew=skew)
+    emuk_split32("irfft", True, L, rows, tab, inp=ref, out=zr, aux=rtw, scale=float(np.float32(1) / np.float32(n)), grid=grid, skew=skew)
     assert np.array_equal(zr, oracle.irfft_batch(ref, 2 * n))
     yr[...] = 0
-    emuk.split32("rfft", False, L, rows, tab, inp=xr, out=yr, aux=rtw, grid=grid)
+    emuk_split32("rfft", False, L, rows, tab, inp=xr, out=yr, aux=rtw, grid=grid)
     assert rel_l2(yr, ref) <= TOL
     if L == 15 and skew is None:
         re, im = np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag)
         ore, oim = np.zeros_like(re), np.zeros_like(im)
-        emuk.split32("gen_fwd", True, L, rows, tab, inp=re, in2=im, out=ore, out2=oim, p=(1, n, 1, n), grid=grid)
+        emuk_split32("gen_fwd", True, L, rows, tab, inp=re, in2=im, out=ore, out2=oim, p=(1, n, 1, n), grid=grid)
         want = oracle.fft_batch(x)
         assert np.array_equal(ore, want.real) and np.array_equal(oim, want.imag)
