@@ -96,6 +96,12 @@ enum SplitEpilogue : int { SPLIT_STORE = 0, SPLIT_TWIST = 1 };
 #ifndef KOFFT_SPLIT_SLOTS
 #define KOFFT_SPLIT_SLOTS 4
 #endif
+// 1: every A warp polls / arrives by itself.  Measured slower (rfft 2^16 x 16384: 2.94 vs 2.61 ms, profiles/r03g):
+// a warp's release fence right behind its 32 stores waits for all of them, eight times per tile; the block-level
+// scheme arrives behind the NEXT tile's first barrier, when the stores have long landed.
+#ifndef KOFFT_SPLIT_WARP_FLAGS
+#define KOFFT_SPLIT_WARP_FLAGS 0
+#endif
 // register budgets of the two roles (setmaxnreg): 256 * A + 256 * B == 512 * 128
 #ifndef KOFFT_SPLIT_REGS_A
 #define KOFFT_SPLIT_REGS_A 96
@@ -154,8 +160,31 @@ struct Split32 {
     static constexpr int SMEM_BYTES = (OFF_BAR + 2) * 8;
     static constexpr bool HINT = IoTraits<IO>::kHint;
 
-    static KD unsigned goal_a(long i) { return (unsigned)(NT * (i / SLOTS + 1)); }
+    static constexpr int A_WARPS = A_THREADS / 32;
+    static constexpr bool WARP_FLAGS = KOFFT_SPLIT_WARP_FLAGS != 0;
+    static KD unsigned goal_a(long i) { return (unsigned)(NT * (WARP_FLAGS ? A_WARPS : 1) * (i / SLOTS + 1)); }
     static KD unsigned goal_b(long i) { return (unsigned)(NTILES * (i / SLOTS + 1)); }
+
+    // A warps, per tile: wait (whole warp polls: no block barrier involved) until every B warp of the team has consumed
+    // transform i - SLOTS, whose slot this tile's stores overwrite; after the stores each warp arrives by itself
+    // (a write-after-read dependency: the B warps arrive once their loads have RETURNED, so observing the count is
+    // enough -- no acquire.)  `seen` is a value of the counter loaded earlier: the L2 round trip of the flag load
+    // is not on the critical path when the slot is already free.
+    static KD void a_wait_slot(unsigned *cntB, long i, unsigned seen = 0)
+    {
+        if (i >= SLOTS) {
+            const unsigned want = goal_b(i - SLOTS);
+            while (seen < want) {
+                nano_sleep(32);
+                seen = flag_load(cntB + i % SLOTS);
+            }
+        }
+    }
+    static KD void a_arrive(unsigned *cntA, long i, int tid)
+    {
+        warp_sync(); // orders the warp's stores before lane 0's release
+        if ((tid & 31) == 0) flag_arrive(cntA + i % SLOTS);
+    }
 
     // ------------------------------------------------------------------------------------------
     // A warps: tid 0 .. 255
@@ -183,6 +212,8 @@ struct Split32 {
         const long j0 = (long)kb * COLS + col;
         for (long i = 0; i < cnt; i++) {
             const long row = team + i * teams;
+            unsigned seen = 0;
+            if (!WARP_FLAGS && tid == 0 && i >= SLOTS) seen = flag_load(cntB + i % SLOTS); // consumed before the second barrier
             float2 x[WIDE];
 #pragma unroll
             for (int u = 0; u < A0::U; u++)
@@ -199,24 +230,24 @@ struct Split32 {
             for (int u = 0; u < A0::U; u++)
 #pragma unroll
                 for (int w = 0; w < A0::R; w++) bf[pad32(A0::dst_index(t, u, w))] = x[u * A0::R + w];
-            // the slot is rewritten: every B warp of the team must have consumed transform i - SLOTS
-            if (tid == 0 && i >= SLOTS) {
-                const unsigned want = goal_b(i - SLOTS);
-                while (flag_load(cntB + i % SLOTS) < want) nano_sleep(32);
-                (void)flag_load_acquire(cntB + i % SLOTS);
-            }
-            named_barrier(1, A_THREADS);
+            named_barrier(1, A_THREADS); // exchange; also: every thread is past the previous tile's stores
+            if (!WARP_FLAGS && tid == 32 && i > 0) flag_arrive(cntA + (i - 1) % SLOTS); // (not the polling thread's warp)
 #pragma unroll
             for (int q = 0; q < 32; q++) x[q] = bf[pad32(A1::src_index(t, 0, q))];
+            if (!WARP_FLAGS && tid == 0) a_wait_slot(cntB, i, seen); // released to the others by the barrier
+            named_barrier(1, A_THREADS); // the exchange buffer is free again
             A1::compute(x, tw1);
+            if (WARP_FLAGS) a_wait_slot(cntB, i);
             float2 *o = slots + (i % SLOTS) * n + j0;
 #pragma unroll
             for (int w = 0; w < 32; w++) stg_hint(o + ((long)A1::dst_index(t, 0, w) << 5), x[w], pol.last);
-            named_barrier(1, A_THREADS); // the exchange buffer is free again; every thread's stores are issued
-            if (tid == 0) flag_arrive(cntA + i % SLOTS);
+            if (WARP_FLAGS) a_arrive(cntA, i, tid);
+        }
+        if (!WARP_FLAGS && cnt > 0) {
+            named_barrier(1, A_THREADS);
+            if (tid == 0) flag_arrive(cntA + (cnt - 1) % SLOTS);
         }
     }
-
 
     // ------------------------------------------------------------------------------------------
     // A warps, STAGED variant (see the struct comment).  The tile lands row-major, [1024 rows][8 columns] (TMA
@@ -268,6 +299,8 @@ struct Split32 {
         const long j0 = (long)kb * COLS + col;
         unsigned phase = 0;
         for (long i = 0; i < cnt; i++) {
+            unsigned seen = 0;
+            if (!WARP_FLAGS && tid == 0 && i >= SLOTS) seen = flag_load(cntB + i % SLOTS); // consumed before the second barrier
             float2 x[WIDE];
             mbar_wait(bar, phase);
             phase ^= 1;
@@ -281,26 +314,23 @@ struct Split32 {
                 (((c >> 3) & 1) ? s0x : s0)[c * 32 * COLS] = x[w];
             }
             named_barrier(1, A_THREADS); // exchange; also: every thread is past the previous tile's stores
-            if (tid == 0 && i > 0) flag_arrive(cntA + (i - 1) % SLOTS);
+            if (!WARP_FLAGS && tid == 32 && i > 0) flag_arrive(cntA + (i - 1) % SLOTS); // (not the polling thread's warp)
 #pragma unroll
             for (int q = 0; q < 32; q++) x[q] = ((q & 1) ? s1o : s1e)[q * COLS];
-            // the slot is rewritten: every B warp of the team must have consumed transform i - SLOTS
-            if (tid == 0 && i >= SLOTS) {
-                const unsigned want = goal_b(i - SLOTS);
-                while (flag_load(cntB + i % SLOTS) < want) nano_sleep(32);
-                (void)flag_load_acquire(cntB + i % SLOTS);
-            }
+            if (!WARP_FLAGS && tid == 0) a_wait_slot(cntB, i, seen); // released to the others by the barrier
             named_barrier(1, A_THREADS); // the buffer is free: the next tile may land
             if (tid == 0 && i + 1 < cnt) {
                 fence_proxy_async();
                 issue_tile(map, stage, bar, team + (i + 1) * teams, kb);
             }
             A1::compute(x, tw1);
+            if (WARP_FLAGS) a_wait_slot(cntB, i);
             float2 *o = slots + (i % SLOTS) * n + j0;
 #pragma unroll
             for (int w = 0; w < 32; w++) stg_hint(o + ((long)(k1 + (bitrev(w, 5) << 5)) << 5), x[w], pol.last);
+            if (WARP_FLAGS) a_arrive(cntA, i, tid);
         }
-        if (cnt > 0) {
+        if (!WARP_FLAGS && cnt > 0) {
             named_barrier(1, A_THREADS);
             if (tid == 0) flag_arrive(cntA + (cnt - 1) % SLOTS);
         }
@@ -368,16 +398,18 @@ struct Split32 {
                 x[2 * q2 + 1] = make_float2(e.z, e.w);
             }
             warp_sync(); // the region is free again
-            // the next tile's rows, if its pass A is already complete: their L2 latency hides behind this tile's arithmetic
+            // The next tile's rows, if its pass A is already complete: their L2 latency hides behind this tile's epilogue.
+            // The flag is loaded here and looked at after the register pass, so its own L2 round trip is hidden too.
+            const unsigned nxt = i + 1 < cnt ? flag_load(cntA + (i + 1) % SLOTS) : 0u;
+            PB::compute(x, twb);
             fetched = false;
             if (i + 1 < cnt) {
-                if (warp_all(flag_load(cntA + (i + 1) % SLOTS) >= goal_a(i + 1))) {
+                if (warp_all(nxt >= goal_a(i + 1))) {
                     (void)flag_load_acquire(cntA + (i + 1) % SLOTS);
                     fetch(i + 1);
                     fetched = true;
                 }
             }
-            PB::compute(x, twb);
             // register wi holds bin K = k + bitrev(wi) 2^LA
             if constexpr (EPI == SPLIT_TWIST) {
                 float2 *o = io.out + row * (io.m + 1) + k;

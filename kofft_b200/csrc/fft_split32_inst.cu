@@ -88,11 +88,28 @@ cudaError_t launch_split_v(const IO &io, const LaunchArgs &a, SplitArgs &g)
     float2 *scratch = g.scratch;
     unsigned *flags = g.flags;
     const float2 *table = a.table;
-    void *args[] = {(void *)&io, (void *)&tw0, (void *)&table, (void *)&rows, (void *)&scratch, (void *)&flags, (void *)&map};
     cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(unsigned) * F::FLAG_STRIDE * teams, a.stream);
     if (e != cudaSuccess) return e;
-    return cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)(teams * F::NT)), dim3(F::CTA), args,
-                                       F::SMEM_BYTES, a.stream);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.numAttrs = 1;
+    if (g.persist_l2) { // the intermediate as a persisting-L2 window (the caller raised cudaLimitPersistingL2CacheSize)
+        attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[1].val.accessPolicyWindow.base_ptr = scratch;
+        attr[1].val.accessPolicyWindow.num_bytes = sizeof(float2) * (size_t(1) << F::L) * F::SLOTS * teams;
+        attr[1].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.numAttrs = 2;
+    }
+    cfg.gridDim = dim3((unsigned)(teams * F::NT));
+    cfg.blockDim = dim3(F::CTA);
+    cfg.dynamicSmemBytes = F::SMEM_BYTES;
+    cfg.stream = a.stream;
+    cfg.attrs = attr;
+    return cudaLaunchKernelEx(&cfg, kern, io, tw0, table, rows, scratch, flags, map);
 }
 
 template <int LA, bool EXACT>

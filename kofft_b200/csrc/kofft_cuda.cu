@@ -111,6 +111,7 @@ struct kofft_cuda_ctx {
     // the same bits and coop_fallbacks counts it.
     int split_min_l = 15;
     unsigned long long coop_fallbacks = 0;
+    int l2_persist_mode = 0; // 0 off, 1 requested (KOFFT_L2_PERSIST=1), 2 active
     bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
     int istft_run_frames = 128;
     // host-pointer batch entry points: the batch is cut into chunks that flow through three
@@ -268,6 +269,16 @@ int dispatch_impl(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, siz
                 CU(cudaMalloc(&ctx->pipe_flags, sizeof(unsigned) * kPipeFlagStride * (kMaxPipeCtasPerSm * ctx->num_sms)));
             g.scratch = static_cast<float2 *>(scratch);
             g.flags = ctx->pipe_flags;
+            if (ctx->l2_persist_mode == 1) { // tuning aid (KOFFT_L2_PERSIST=1): reserve persisting L2 for the intermediate
+                int max_persist = 0;
+                CU(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device));
+                size_t want = size_t(kSplitSlots) * g.max_teams * n * sizeof(float2);
+                if (want > size_t(max_persist)) want = size_t(max_persist);
+                CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+                if (getenv("KOFFT_CUDA_VERBOSE")) fprintf(stderr, "[kofft_cuda] persisting L2: %zu of max %d bytes\n", want, max_persist);
+                ctx->l2_persist_mode = 2;
+            }
+            g.persist_l2 = ctx->l2_persist_mode == 2;
             e = launch_split32_fft(L, a, g);
             if (e == cudaSuccess) {
                 ctx->launches += 1;
@@ -428,6 +439,8 @@ int kofft_cuda_create(kofft_cuda_ctx **out, int device)
         ctx->large_fused = strcmp(m, "cluster") == 0;
     }
 
+    if (const char *m = getenv("KOFFT_L2_PERSIST"))
+        if (atoi(m) == 1) ctx->l2_persist_mode = 1;
     if (const char *m = getenv("KOFFT_SPLIT_MIN_L"))
         if (atoi(m) >= 13 && atoi(m) <= 16) ctx->split_min_l = atoi(m);
 
