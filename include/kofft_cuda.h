@@ -82,9 +82,14 @@ int kofft_cuda_set_large_mode(kofft_cuda_ctx *ctx, int mode);
 /* Lengths 2^min_log2n .. 2^15 of the complex core (rfft / irfft: twice that) run the warp-specialised split
  * kernel (fft_split32.cuh): ONE persistent cooperative launch, 512-thread CTAs whose "A warps" run the
  * 2^(L-5)-point column transforms of an 8192-element tile while their "B warps" finish 32-point rows in
- * registers (rfft twist by warp shuffles), intermediate pinned in L2.  Default 15; 13..15 select more lengths,
- * 16 switches it off (kofft_cuda_set_large_mode then picks the implementation for 2^15).  Bit-identical. */
+ * registers (rfft twist by warp shuffles), intermediate pinned in L2.  Default 14 (2^14 and 2^15: where it measured
+ * faster than the single-CTA / two-pass kernels); 13 adds 2^13, 16 switches it off (kofft_cuda_set_large_mode then
+ * picks the implementation for 2^15).  Bit-identical. */
 int kofft_cuda_set_split_min_log2n(kofft_cuda_ctx *ctx, int min_log2n);
+/* By default the split kernel serves C2C and rfft (2^15 cores: tiles arrive by TMA tensor-map loads).  all_kinds != 0
+ * also routes irfft and the strided / split (SoA) entry points through it (plain loads; measured slower than the
+ * older paths, kept for parity testing). */
+int kofft_cuda_set_split_all_kinds(kofft_cuda_ctx *ctx, int all_kinds);
 /* The persistent large-N kernels need a cooperative launch (every CTA resident).  When the device cannot grant
  * it (shared or partitioned GPU) the library computes the same bits with the slower multi-kernel path, bumps
  * this counter and leaves a note in kofft_cuda_last_error(). */

@@ -134,8 +134,10 @@ KD unsigned flag_load(const unsigned *c)
 KD void flag_acquire() { __threadfence(); }
 KD void flag_arrive(unsigned *c)
 {
-    __threadfence();
-    atomicAdd(c, 1u);
+    // release: fence.acq_rel (MEMBAR.ALL.GPU) + relaxed add; __threadfence() is a sequentially consistent fence
+    // (MEMBAR.SC.GPU), which the arrival does not need
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
 }
 // the arriving CTA only READ the guarded data (its loads have completed): no fence needed
 KD void flag_arrive_relaxed(unsigned *c) { atomicAdd(c, 1u); }
@@ -168,6 +170,14 @@ KD unsigned flag_load_acquire(const unsigned *c)
 }
 // warp vote: true iff the predicate holds on every lane (the result is warp-uniform by construction)
 KD bool warp_all(bool p) { return __all_sync(0xffffffffu, p) != 0; }
+// arrival on a CTA-local counter in shared memory (release before, acquire after); returns the previous count
+KD unsigned smem_count_arrive(unsigned *c)
+{
+    __threadfence_block();
+    const unsigned old = atomicAdd(c, 1u);
+    __threadfence_block();
+    return old;
+}
 
 // ---- TMA tensor-map loads (cp.async.bulk.tensor, SASS UTMALDG) -----------------------------------
 // The map is a CUtensorMap encoded on the host (cuTensorMapEncodeTiled) and passed as a __grid_constant__
@@ -254,13 +264,15 @@ inline void bulk_copy_g2s(void *dst_smem, const void *src, unsigned bytes, unsig
 
 inline unsigned flag_load_acquire(const unsigned *c) { return *c; }
 inline bool warp_all(bool p) { return cuda_emu::warp_all(p); }
+inline unsigned smem_count_arrive(unsigned *c) { return (*c)++; }
 // host stand-in of a 2-D tiled tensor map over f32 elements: dims / strides as cuTensorMapEncodeTiled takes them
 struct TmaMap {
     const void *base;
     unsigned long long dim0, dim1;   // elements
     unsigned long long stride1;      // bytes between rows
     unsigned box0, box1;             // elements
-    unsigned long long pad[11];
+    unsigned swizzle;                // 0 none, 64: CU_TENSOR_MAP_SWIZZLE_64B (address bits [5:4] ^= bits [8:7])
+    unsigned pad_[21];
 };
 inline void tma_load_2d(void *dst_smem, const TmaMap *map, int c0, int c1, unsigned long long *bar)
 {
@@ -268,9 +280,18 @@ inline void tma_load_2d(void *dst_smem, const TmaMap *map, int c0, int c1, unsig
     if ((map->box0 * 4) % 16 || (map->stride1 % 16) || (reinterpret_cast<uintptr_t>(map->base) & 15)) abort();
     if (c0 < 0 || c1 < 0 || (unsigned long long)c0 + map->box0 > map->dim0 || (unsigned long long)c1 + map->box1 > map->dim1) abort();
     char *d = static_cast<char *>(dst_smem);
-    for (unsigned r = 0; r < map->box1; r++)
-        memcpy(d + (size_t)r * map->box0 * 4, static_cast<const char *>(map->base) + (size_t)(c1 + r) * map->stride1 + (size_t)c0 * 4,
-               (size_t)map->box0 * 4);
+    if (map->swizzle == 64 && ((reinterpret_cast<uintptr_t>(dst_smem) & 511) || map->box0 * 4 != 64)) abort();
+    for (unsigned r = 0; r < map->box1; r++) {
+        const char *src = static_cast<const char *>(map->base) + (size_t)(c1 + r) * map->stride1 + (size_t)c0 * 4;
+        if (map->swizzle == 64) { // 16-byte chunk index ^= bits [8:7] of the destination address
+            for (unsigned ch = 0; ch < 4; ch++) {
+                const size_t off = (size_t)r * 64 + ch * 16;
+                memcpy(d + (off ^ (((off >> 7) & 3) << 4)), src + ch * 16, 16);
+            }
+        } else {
+            memcpy(d + (size_t)r * map->box0 * 4, src, (size_t)map->box0 * 4);
+        }
+    }
     EmuMbar &m = emu_mbar(bar);
     m.pending -= static_cast<int>(map->box0 * map->box1 * 4);
     if (m.pending == 0) m.completed++;

@@ -109,7 +109,8 @@ struct kofft_cuda_ctx {
     // N = 2^13 .. 2^15: the warp-specialised split kernel (fft_split32.cuh) serves lengths 2^split_min_l .. 2^15
     // (16 = off).  Cooperative launch; when the device cannot make every CTA resident the older paths compute
     // the same bits and coop_fallbacks counts it.
-    int split_min_l = 15;
+    int split_min_l = 14;
+    bool split_all_kinds = false; // default: C2C and rfft, where it measured faster; irfft / SoA rows keep the older paths
     unsigned long long coop_fallbacks = 0;
     int l2_persist_mode = 0; // 0 off, 1 requested (KOFFT_L2_PERSIST=1), 2 active
     bool istft_fused = true; // N = 512..4096: overlap-add fused behind the inverse FFT (one kernel)
@@ -252,7 +253,9 @@ int dispatch_impl(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, siz
         int rc = get_fft_table(ctx, n, &t);
         if (rc) return rc;
         a.table = t->dev;
-        if (L >= ctx->split_min_l && L >= 13 && L <= 15 && kind != KIND_STFT && kind != KIND_ISTFT && kind != KIND_STFT_MAG) {
+        const bool split_kind = kind == KIND_C2C_FWD || kind == KIND_C2C_INV || kind == KIND_RFFT ||
+                                (ctx->split_all_kinds && (kind == KIND_GEN_FWD || kind == KIND_GEN_INV || kind == KIND_IRFFT));
+        if (L >= ctx->split_min_l && L >= 13 && L <= 15 && split_kind) {
             SplitArgs g;
             const int ra0 = L - 10; // pass A's first register pass: stages 0 .. L-11 of the big transform
             for (int tl = 0; tl < ra0; tl++)
@@ -532,6 +535,11 @@ int kofft_cuda_set_split_min_log2n(kofft_cuda_ctx *ctx, int min_log2n)
 {
     if (min_log2n < 13 || min_log2n > 16) return fail_msg(KOFFT_ERR_INVALID_VALUE, "set_split_min_log2n: 13..16 (16 = off)");
     ctx->split_min_l = min_log2n;
+    return KOFFT_OK;
+}
+int kofft_cuda_set_split_all_kinds(kofft_cuda_ctx *ctx, int all_kinds)
+{
+    ctx->split_all_kinds = all_kinds != 0;
     return KOFFT_OK;
 }
 unsigned long long kofft_cuda_fallback_count(const kofft_cuda_ctx *ctx) { return ctx->coop_fallbacks; }

@@ -132,8 +132,12 @@ class Context:
         check(_lib.lib().kofft_cuda_set_large_mode(self.handle, int(mode)))
 
     def set_split_min_log2n(self, min_log2n: int) -> None:
-        """complex cores of 2^min_log2n .. 2^15 points run the warp-specialised split kernel (default 15; 16 = off)"""
+        """complex cores of 2^min_log2n .. 2^15 points run the warp-specialised split kernel (default 14; 16 = off)"""
         check(_lib.lib().kofft_cuda_set_split_min_log2n(self.handle, int(min_log2n)))
+
+    def set_split_all_kinds(self, all_kinds: bool) -> None:
+        """also route irfft and strided / SoA rows through the split kernel (default: C2C and rfft only)"""
+        check(_lib.lib().kofft_cuda_set_split_all_kinds(self.handle, int(bool(all_kinds))))
 
     @property
     def fallback_count(self) -> int:

@@ -56,7 +56,7 @@ def main():
                 ms, best = timeit(lambda: fft.rfft_batch(xr, out=yr), 8, 2)
                 rep(f"rfft_{n}x{rows}", mode, path, ms, best, xr.numel() * 4 + yr.numel() * 8)
             del xr, yr
-        C.set_split_min_log2n(15)
+        C.set_split_min_log2n(14)
 
 
 if __name__ == "__main__":

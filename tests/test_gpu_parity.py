@@ -696,7 +696,7 @@ def test_large_paths_agree(cuda_fft, oracle, n):
             assert np.array_equal(cuda_fft.irfft_batch(rref, 2 * n), bref), tag
     finally:
         C.set_large_mode(C.LARGE_AUTO)
-        C.set_split_min_log2n(15)
+        C.set_split_min_log2n(14)
 
 
 @pytest.mark.parametrize("n", [8192, 16384, 32768])
@@ -716,6 +716,7 @@ def test_split_kernel_on_device(cuda_fft, cuda_fft_fast, oracle, n):
     outs, routs = [], []
     try:
         C.set_split_min_log2n(13)
+        C.set_split_all_kinds(True)
         cuda_fft_fast.ctx.set_split_min_log2n(13)
         for max_ctas in (0, 4, 24, 140):
             C.set_max_ctas(max_ctas)
@@ -751,8 +752,9 @@ def test_split_kernel_on_device(cuda_fft, cuda_fft_fast, oracle, n):
         assert C.fallback_count == fb0
     finally:
         C.set_max_ctas(0)
-        C.set_split_min_log2n(15)
-        cuda_fft_fast.ctx.set_split_min_log2n(15)
+        C.set_split_min_log2n(14)
+        C.set_split_all_kinds(False)
+        cuda_fft_fast.ctx.set_split_min_log2n(14)
 
 
 def test_large_pipelined_many_transforms_per_team_on_device(cuda_fft, oracle):
@@ -782,7 +784,7 @@ def test_large_pipelined_many_transforms_per_team_on_device(cuda_fft, oracle):
     finally:
         C.set_max_ctas(0)
         C.set_large_mode(C.LARGE_AUTO)
-        C.set_split_min_log2n(15)
+        C.set_split_min_log2n(14)
     pick = [0, 1, 36, 37, 73, 74, 700, rows - 2, rows - 1]
     assert np.array_equal(outs[0][pick].cpu().numpy(), oracle.fft_batch(x[pick].cpu().numpy(), nthreads=8))
     assert np.array_equal(routs[0][pick].cpu().numpy(), oracle.rfft_batch(xr[pick].cpu().numpy(), nthreads=8))
