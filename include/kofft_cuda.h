@@ -11,10 +11,13 @@
  *  - Complex data is interleaved {re, im} f32 == `#[repr(C)] Complex<f32>` (src/num.rs:105-110).
  *  - Return value: 0 = Ok; 1..6 = kofft's `FftError` variants in declaration order
  *    (src/fft.rs:446-454); negative = -(cudaError_t) with text in kofft_cuda_last_error().
- *  - C2C transforms of non-power-of-two length n <= 32768 take the reference's Bluestein path
- *    (src/fft.rs:411-433, 1083-1132: chirp, two transforms of length next_pow2(2n-1)), with the
- *    same tables and arithmetic.  The rfft / stft / split / strided cores are power-of-two only
- *    and return KOFFT_ERR_NON_POWER_OF_TWO_NO_STD otherwise.
+ *  - Lengths: any power of two up to 2^27 (rfft / irfft: 2^28) on one GPU; above 2^16 the transform makes
+ *    several trips through global memory (fft_huge.cu).  Non-power-of-two lengths n <= 2^26 take the
+ *    reference's Bluestein path (src/fft.rs:411-433, 1083-1132: chirp, two transforms of length
+ *    next_pow2(2n-1)) with the same tables and arithmetic -- from fft / ifft and, as in the reference's
+ *    std build, from the rfft / irfft / stft / istft / split / strided entry points, which all end in
+ *    fft.fft().  KOFFT_ERR_NON_POWER_OF_TWO_NO_STD is only returned by the device-resident streams and the
+ *    fused magnitude kernel, which are built on the power-of-two kernels.
  *  - Host-pointer functions are synchronous and never retain the caller's pointers.
  *    Device-pointer functions are stream-ordered on `stream`, a cudaStream_t passed as
  *    void* with CUDA's own meaning (NULL = the legacy default stream; kofft_cuda_stream()

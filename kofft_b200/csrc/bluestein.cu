@@ -65,6 +65,104 @@ __global__ void __launch_bounds__(256) blue_post_kernel(const float2 *__restrict
     }
 }
 
+// ---- the element-wise steps around a non-power-of-two core in rfft / irfft / stft / istft / strided / split ----
+// (the reference reaches Bluestein from all of them because they call fft.fft(): src/rfft.rs:447, 502,
+// src/stft.rs:102, 141, src/fft.rs:797-809, 1191-1197)
+
+// gather (src/fft.rs:1191-1193, 800-804): a[r*n + i] = (re[r*rs + i*es], im[r*rs + i*es])
+__global__ void __launch_bounds__(256) gather_kernel(const float *__restrict__ re, const float *__restrict__ im, long es, long rs,
+                                                     float2 *__restrict__ a, long n, long rows)
+{
+    const long total = rows * n;
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        const long r = idx / n, i = idx - r * n;
+        a[idx] = make_float2(re[r * rs + i * es], im[r * rs + i * es]);
+    }
+}
+// scatter (src/fft.rs:1195-1197, 806-809)
+__global__ void __launch_bounds__(256) scatter_kernel(const float2 *__restrict__ a, float *__restrict__ re, float *__restrict__ im,
+                                                      long es, long rs, long n, long rows)
+{
+    const long total = rows * n;
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        const long r = idx / n, i = idx - r * n;
+        const float2 v = a[idx];
+        re[r * rs + i * es] = v.x;
+        im[r * rs + i * es] = v.y;
+    }
+}
+// stft framing + windowing (src/stft.rs:91-101): frames[row][i] = (signal[c][f*hop + i] * w[i] or 0, 0)
+__global__ void __launch_bounds__(256) frame_kernel(const float *__restrict__ signal, const float *__restrict__ window,
+                                                    float2 *__restrict__ frames, long len, long nframes, long hop, long n, long rows)
+{
+    const long total = rows * n;
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        const long row = idx / n, i = idx - row * n;
+        const long c = row / nframes, f = row - c * nframes;
+        const long pos = f * hop + i;
+        float x = 0.0f;
+        if (pos < len) x = mul_rn(signal[c * len + pos], __ldg(window + i));
+        frames[idx] = make_float2(x, 0.0f);
+    }
+}
+// istft: time[row][i] = ifft(frame)[i].re * w[i] (src/stft.rs:141-145); z already carries the 1/n of the ifft
+__global__ void __launch_bounds__(256) time_kernel(const float2 *__restrict__ z, const float *__restrict__ window,
+                                                   float *__restrict__ time, long n, long rows)
+{
+    const long total = rows * n;
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L)
+        time[idx] = mul_rn(z[idx].x, __ldg(window + (idx % n)));
+}
+// irfft untwist (src/rfft.rs:488-499): y[r][k] from X[r][0..m]
+template <bool EXACT>
+__global__ void __launch_bounds__(256) untwist_kernel(const float2 *__restrict__ x, const float2 *__restrict__ rtw,
+                                                      float2 *__restrict__ y, long m, long rows)
+{
+    const long total = rows * m;
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        const long r = idx / m, k = idx - r * m;
+        const float2 *X = x + r * (m + 1);
+        float2 v;
+        if (k == 0) {
+            const float2 x0 = X[0], xm = X[m];
+            v = make_float2(mul_rn(add_rn(x0.x, xm.x), 0.5f), mul_rn(sub_rn(x0.x, xm.x), 0.5f));
+        } else {
+            const float2 a = X[k], q = X[m - k];
+            const float2 b = make_float2(q.x, -q.y);
+            const float2 sum = make_float2(add_rn(a.x, b.x), add_rn(a.y, b.y));
+            const float2 diff = make_float2(sub_rn(a.x, b.x), sub_rn(a.y, b.y));
+            const float2 tw = __ldg(rtw + k);
+            const float2 t = cmul<EXACT>(make_float2(tw.x, -tw.y), diff);
+            v = make_float2(mul_rn(sub_rn(sum.x, t.y), 0.5f), mul_rn(add_rn(sum.y, t.x), 0.5f));
+        }
+        y[idx] = v;
+    }
+}
+// rfft twist (src/rfft.rs:450-463): out[r][k] from y = fft(m) of the packed row
+template <bool EXACT>
+__global__ void __launch_bounds__(256) twist_kernel(const float2 *__restrict__ y, const float2 *__restrict__ rtw,
+                                                    float2 *__restrict__ out, long m, long rows)
+{
+    const long total = rows * (m + 1);
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        const long r = idx / (m + 1), k = idx - r * (m + 1);
+        const float2 *Y = y + r * m;
+        float2 v;
+        if (k == 0 || k == m) {
+            const float2 a = Y[0];
+            v = make_float2(k == 0 ? add_rn(a.x, a.y) : sub_rn(a.x, a.y), 0.0f);
+        } else {
+            const float2 a = Y[k], q = Y[m - k];
+            const float2 b = make_float2(q.x, -q.y);
+            const float2 sum = make_float2(add_rn(a.x, b.x), add_rn(a.y, b.y));
+            const float2 diff = make_float2(sub_rn(a.x, b.x), sub_rn(a.y, b.y));
+            const float2 t = cmul<EXACT>(__ldg(rtw + k), diff);
+            v = make_float2(mul_rn(add_rn(sum.x, t.y), 0.5f), mul_rn(sub_rn(sum.y, t.x), 0.5f));
+        }
+        out[idx] = v;
+    }
+}
+
 int grid_for(long total, int num_sms)
 {
     long g = (total + 255) / 256;
@@ -98,6 +196,41 @@ cudaError_t launch_bluestein_step(int step, const BluesteinArgs &b, bool exact, 
             blue_post_kernel<false><<<grid_for(b.rows * b.n, num_sms), 256, 0, s>>>(b.a, b.chirp, b.out, b.n, b.m, b.rows, b.scale_m,
                                                                                    b.inverse, b.scale_n);
         break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_elementwise(const ElementwiseArgs &e, bool exact, int num_sms, cudaStream_t s)
+{
+    if (e.rows == 0 || e.n == 0) return cudaSuccess;
+    const int g = grid_for(e.rows * (e.op == EW_TWIST ? e.n + 1 : e.n), num_sms);
+    switch (e.op) {
+    case EW_GATHER:
+        gather_kernel<<<g, 256, 0, s>>>(e.re, e.im, e.es, e.rs, e.a, e.n, e.rows);
+        break;
+    case EW_SCATTER:
+        scatter_kernel<<<g, 256, 0, s>>>(e.a, e.out_re, e.out_im, e.es, e.rs, e.n, e.rows);
+        break;
+    case EW_FRAME:
+        frame_kernel<<<g, 256, 0, s>>>(e.re, e.aux_f, e.a, e.len, e.nframes, e.hop, e.n, e.rows);
+        break;
+    case EW_TIME:
+        time_kernel<<<g, 256, 0, s>>>(e.a, e.aux_f, e.out_re, e.n, e.rows);
+        break;
+    case EW_UNTWIST:
+        if (exact)
+            untwist_kernel<true><<<g, 256, 0, s>>>(e.x, e.rtw, e.a, e.n, e.rows);
+        else
+            untwist_kernel<false><<<g, 256, 0, s>>>(e.x, e.rtw, e.a, e.n, e.rows);
+        break;
+    case EW_TWIST:
+        if (exact)
+            twist_kernel<true><<<g, 256, 0, s>>>(e.x, e.rtw, e.a, e.n, e.rows);
+        else
+            twist_kernel<false><<<g, 256, 0, s>>>(e.x, e.rtw, e.a, e.n, e.rows);
+        break;
+    default:
+        return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }

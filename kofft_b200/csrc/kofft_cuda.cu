@@ -58,8 +58,9 @@ int log2_of(size_t n)
 }
 
 struct Table {
-    std::vector<float> host; // interleaved
+    std::vector<float> host; // interleaved; dropped after the upload for n > 2^20 (pre0 keeps what the host still needs)
     float2 *dev = nullptr;
+    float2 pre0[16] = {};    // pass-0 twiddles of a radix-16 first pass: pre0[(2^t - 1) + c] = T[c << (L-1-t)], t < 4
 };
 
 } // namespace
@@ -88,17 +89,20 @@ struct kofft_cuda_ctx {
     std::map<size_t, TableD> rfft_tables_f64; // RfftPlanner<f64>, key m
     // grow-only device workspaces: [0] host-API staging in, [1] staging out, [2] istft time frames,
     // [3] small staging (windows), [4] two-pass (N > 16384) intermediate
-    void *ws[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t ws_bytes[5] = {0, 0, 0, 0, 0};
+    // [5] dense complex rows of a non-power-of-two core (rfft / istft / strided / split), [6] its istft time frames
+    static constexpr int kNumWs = 8;
+    void *ws[kNumWs] = {};
+    size_t ws_bytes[kNumWs] = {};
     // The device-pointer entry points are stream-ordered on the CALLER's stream, but [2] and [4] (and the
     // dependency flags of the persistent kernels) are one per context: a call on another stream first waits for
     // the event the previous user recorded (ws_acquire / ws_release), so two streams never share a scratch.
-    cudaEvent_t ws_event[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t ws_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool ws_used[5] = {false, false, false, false, false};
+    cudaEvent_t ws_event[kNumWs] = {};
+    cudaStream_t ws_stream[kNumWs] = {};
+    bool ws_used[kNumWs] = {};
     size_t large_scratch_bytes = size_t(256) << 20; // two-pass intermediate per batch chunk (measured: kernel
                                                    // length matters more than L2 residency, profiles/r01n)
     size_t istft_ws_limit = size_t(1) << 30;
+    size_t huge_scratch_bytes = size_t(1) << 30; // N > 2^16: both scratch buffers together (at least one transform each)
     bool use_tma = true; // TMA-staged input prefetch where alignment allows
     bool large_fused = false; // N > 16384: one persistent thread-block-cluster kernel instead of two kernels per chunk
     // N > 16384 default: one persistent cooperative kernel, per-team dependency flags, intermediate
@@ -172,9 +176,18 @@ int get_fft_table(kofft_cuda_ctx *ctx, size_t n, const Table **out)
             host_fft_twiddles(n, t.host.data());
         CU(cudaMalloc(&t.dev, sizeof(float2) * (half ? half : 1)));
         CU(cudaMemcpyAsync(t.dev, t.host.data(), sizeof(float2) * half, cudaMemcpyHostToDevice, ctx->stream));
+        if (n >= 16) {
+            const int L = log2_of(n);
+            for (int tl = 0; tl < 4; tl++)
+                for (int c = 0; c < (1 << tl); c++) {
+                    const size_t idx = static_cast<size_t>(c) << (L - 1 - tl);
+                    t.pre0[(1 << tl) - 1 + c] = make_float2(t.host[2 * idx], t.host[2 * idx + 1]);
+                }
+        }
         // the host vector must outlive the async copy: it is owned by the map entry below
         it = ctx->fft_tables.emplace(key, std::move(t)).first;
         CU(cudaStreamSynchronize(ctx->stream));
+        if (n > (size_t(1) << 20)) std::vector<float>().swap(it->second.host); // 4 n bytes: keep big tables on the device only
     }
     *out = &it->second;
     return 0;
@@ -192,6 +205,7 @@ int get_rfft_table(kofft_cuda_ctx *ctx, size_t m, const Table **out)
         CU(cudaMemcpyAsync(t.dev, t.host.data(), sizeof(float2) * m, cudaMemcpyHostToDevice, ctx->stream));
         it = ctx->rfft_tables.emplace(key, std::move(t)).first;
         CU(cudaStreamSynchronize(ctx->stream));
+        if (m > (size_t(1) << 20)) std::vector<float>().swap(it->second.host);
     }
     *out = &it->second;
     return 0;
@@ -246,13 +260,34 @@ int dispatch_impl(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, siz
         e = launch_small_fft(static_cast<int>(n), a);
     } else {
         const int L = log2_of(n);
-        if (L > 16)
+        if (L > kHugeMaxLog2)
             return fail_msg(-static_cast<int>(cudaErrorNotSupported),
-                            "transform lengths above 65536 (rfft above 131072) are not supported yet");
+                            "transform lengths above 2^27 (rfft above 2^28) need the multi-GPU path (kofft_cuda_dist_*)");
         const Table *t = nullptr;
         int rc = get_fft_table(ctx, n, &t);
         if (rc) return rc;
         a.table = t->dev;
+        if (L > 16) {
+            // 256-point column pass + register passes through two scratch buffers (fft_huge.cu)
+            if (kind == KIND_STFT || kind == KIND_ISTFT || kind == KIND_STFT_MAG)
+                return fail_msg(-static_cast<int>(cudaErrorNotSupported), "STFT windows above 16384 are not supported");
+            for (int i = 0; i < 15; i++) a.tw0.v[i] = t->pre0[i];
+            const size_t row_bytes = n * sizeof(float2);
+            size_t chunk = ctx->huge_scratch_bytes / 2 / row_bytes;
+            if (chunk < 1) chunk = 1;
+            if (chunk > rows) chunk = rows;
+            void *scratch = nullptr;
+            rc = ensure_ws(ctx, 4, 2 * chunk * row_bytes, &scratch);
+            if (rc) return rc;
+            HugeArgs g;
+            g.scratch[0] = static_cast<float2 *>(scratch);
+            g.scratch[1] = g.scratch[0] + chunk * n;
+            g.chunk_rows = static_cast<long>(chunk);
+            e = launch_huge_fft(L, a, g);
+            if (e != cudaSuccess) return fail_cuda(e, "huge-N kernel launch");
+            ctx->launches += g.launches;
+            return KOFFT_OK;
+        }
         const bool split_kind = kind == KIND_C2C_FWD || kind == KIND_C2C_INV || kind == KIND_RFFT ||
                                 (ctx->split_all_kinds && (kind == KIND_GEN_FWD || kind == KIND_GEN_INV || kind == KIND_IRFFT));
         if (L >= ctx->split_min_l && L >= 13 && L <= 15 && split_kind) {
@@ -386,12 +421,34 @@ int dispatch_impl(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, siz
     return KOFFT_OK;
 }
 
-// length checks shared by every entry that ends in FftImpl::fft(n) (src/fft.rs:1054-1082)
+// length checks shared by every entry that ends in FftImpl::fft(n) (src/fft.rs:1054-1082): the std build takes
+// Bluestein for non-power-of-two lengths (:1083-1132), so only the empty input is an error
 int check_fft_len(size_t n)
+{
+    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
+    return KOFFT_OK;
+}
+// the device-resident streams and the fused magnitude kernel are built on the power-of-two kernels only
+int check_pow2_len(size_t n)
 {
     if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
     if (!is_pow2(n)) return KOFFT_ERR_NON_POWER_OF_TWO_NO_STD;
     return KOFFT_OK;
+}
+int elementwise(kofft_cuda_ctx *ctx, const ElementwiseArgs &e, cudaStream_t s)
+{
+    (void)cudaGetLastError();
+    cudaError_t err = launch_elementwise(e, ctx->exact, ctx->num_sms, s);
+    if (err != cudaSuccess) return fail_cuda(err, "element-wise kernel launch");
+    ctx->launches++;
+    return KOFFT_OK;
+}
+// rows of the non-power-of-two core per trip through workspace `which`
+size_t rows_per_trip(const kofft_cuda_ctx *ctx, size_t row_bytes, size_t rows)
+{
+    size_t chunk = row_bytes ? ctx->istft_ws_limit / row_bytes : rows;
+    if (chunk < 1) chunk = 1;
+    return chunk > rows ? rows : chunk;
 }
 
 // `stream` is a cudaStream_t exactly as the caller passed it (NULL = CUDA's legacy default
@@ -463,7 +520,7 @@ void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize(); // tables and workspaces may still be in use on the callers' streams
-    for (int i = 0; i < 5; i++)
+    for (int i = 0; i < kofft_cuda_ctx::kNumWs; i++)
         if (ctx->ws_event[i]) cudaEventDestroy(ctx->ws_event[i]);
     for (auto &kv : ctx->fft_tables) cudaFree(kv.second.dev);
     for (auto &kv : ctx->rfft_tables) cudaFree(kv.second.dev);
@@ -471,7 +528,7 @@ void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
         cudaFree(kv.second.chirp);
         cudaFree(kv.second.bfft);
     }
-    for (int i = 0; i < 5; i++)
+    for (int i = 0; i < kofft_cuda_ctx::kNumWs; i++)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     if (ctx->pipe_flags) cudaFree(ctx->pipe_flags);
     for (auto &kv : ctx->fft_tables_f64)
@@ -628,8 +685,8 @@ static int bluestein_c2c(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, siz
 {
     size_t m = 1;
     while (m < 2 * n - 1) m <<= 1; // (2n - 1).next_power_of_two()
-    if (m > 65536)
-        return fail_msg(-static_cast<int>(cudaErrorNotSupported), "non-power-of-two lengths above 32768 are not supported");
+    if (m > (size_t(1) << kHugeMaxLog2))
+        return fail_msg(-static_cast<int>(cudaErrorNotSupported), "non-power-of-two lengths above 2^26 are not supported");
     if (batch == 0) return KOFFT_OK;
     auto it = ctx->blue_tables.find(n);
     if (it == ctx->blue_tables.end()) {
@@ -697,6 +754,38 @@ int kofft_cuda_fft_strided_f32(kofft_cuda_ctx *ctx, const void *d_in, size_t in_
     int rc = check_fft_len(n);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
+    if (!is_pow2(n)) { // gather, fft (Bluestein), scatter: src/fft.rs:1191-1197
+        cudaStream_t s = pick_stream(ctx, stream);
+        const size_t chunk = rows_per_trip(ctx, n * sizeof(float2), batch);
+        void *buf = nullptr;
+        rc = ensure_ws(ctx, 5, chunk * n * sizeof(float2), &buf);
+        if (rc) return rc;
+        rc = ws_acquire(ctx, 5, s);
+        if (rc) return rc;
+        for (size_t r0 = 0; r0 < batch; r0 += chunk) {
+            ElementwiseArgs e;
+            e.op = EW_GATHER;
+            e.n = static_cast<long>(n);
+            e.rows = static_cast<long>(batch - r0 < chunk ? batch - r0 : chunk);
+            e.re = static_cast<const float *>(d_in) + 2 * r0 * in_dist;
+            e.im = e.re + 1;
+            e.es = 2 * static_cast<long>(in_stride);
+            e.rs = 2 * static_cast<long>(in_dist);
+            e.a = static_cast<float2 *>(buf);
+            rc = elementwise(ctx, e, s);
+            if (rc) return rc;
+            rc = bluestein_c2c(ctx, buf, buf, n, static_cast<size_t>(e.rows), inverse, s);
+            if (rc) return rc;
+            e.op = EW_SCATTER;
+            e.out_re = static_cast<float *>(d_out) + 2 * r0 * out_dist;
+            e.out_im = e.out_re + 1;
+            e.es = 2 * static_cast<long>(out_stride);
+            e.rs = 2 * static_cast<long>(out_dist);
+            rc = elementwise(ctx, e, s);
+            if (rc) return rc;
+        }
+        return ws_release(ctx, 5, s);
+    }
     IoArgs io;
     io.in = d_in;
     io.in2 = static_cast<const float *>(d_in) + 1;
@@ -777,6 +866,36 @@ int kofft_cuda_fft_split_f32(kofft_cuda_ctx *ctx, const float *d_in_re, const fl
     int rc = check_fft_len(n);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
+    if (!is_pow2(n)) { // AoS copy, fft (Bluestein), copy back: src/fft.rs:797-809
+        cudaStream_t s = pick_stream(ctx, stream);
+        const size_t chunk = rows_per_trip(ctx, n * sizeof(float2), batch);
+        void *buf = nullptr;
+        rc = ensure_ws(ctx, 5, chunk * n * sizeof(float2), &buf);
+        if (rc) return rc;
+        rc = ws_acquire(ctx, 5, s);
+        if (rc) return rc;
+        for (size_t r0 = 0; r0 < batch; r0 += chunk) {
+            ElementwiseArgs e;
+            e.op = EW_GATHER;
+            e.n = static_cast<long>(n);
+            e.rows = static_cast<long>(batch - r0 < chunk ? batch - r0 : chunk);
+            e.re = d_in_re + r0 * n;
+            e.im = d_in_im + r0 * n;
+            e.es = 1;
+            e.rs = static_cast<long>(n);
+            e.a = static_cast<float2 *>(buf);
+            rc = elementwise(ctx, e, s);
+            if (rc) return rc;
+            rc = bluestein_c2c(ctx, buf, buf, n, static_cast<size_t>(e.rows), inverse, s);
+            if (rc) return rc;
+            e.op = EW_SCATTER;
+            e.out_re = d_out_re + r0 * n;
+            e.out_im = d_out_im + r0 * n;
+            rc = elementwise(ctx, e, s);
+            if (rc) return rc;
+        }
+        return ws_release(ctx, 5, s);
+    }
     IoArgs io;
     io.in = d_in_re;
     io.in2 = d_in_im;
@@ -801,6 +920,30 @@ int kofft_cuda_rfft_f32(kofft_cuda_ctx *ctx, const float *d_in, void *d_out, siz
     const Table *t = nullptr;
     rc = get_rfft_table(ctx, m, &t);
     if (rc) return rc;
+    if (!is_pow2(m)) { // pack (a reinterpretation), fft(m) through Bluestein, twist: src/rfft.rs:444-463
+        cudaStream_t s = pick_stream(ctx, stream);
+        const size_t chunk = rows_per_trip(ctx, m * sizeof(float2), batch);
+        void *y = nullptr;
+        rc = ensure_ws(ctx, 5, chunk * m * sizeof(float2), &y);
+        if (rc) return rc;
+        rc = ws_acquire(ctx, 5, s);
+        if (rc) return rc;
+        for (size_t r0 = 0; r0 < batch; r0 += chunk) {
+            const size_t nr = batch - r0 < chunk ? batch - r0 : chunk;
+            rc = bluestein_c2c(ctx, d_in + r0 * n, y, m, nr, 0, s);
+            if (rc) return rc;
+            ElementwiseArgs e;
+            e.op = EW_TWIST;
+            e.n = static_cast<long>(m);
+            e.rows = static_cast<long>(nr);
+            e.x = static_cast<const float2 *>(y);
+            e.rtw = t->dev;
+            e.a = static_cast<float2 *>(d_out) + r0 * (m + 1);
+            rc = elementwise(ctx, e, s);
+            if (rc) return rc;
+        }
+        return ws_release(ctx, 5, s);
+    }
     IoArgs io;
     io.in = d_in;
     io.out = d_out;
@@ -819,6 +962,19 @@ int kofft_cuda_irfft_f32(kofft_cuda_ctx *ctx, const void *d_in, float *d_out, si
     const Table *t = nullptr;
     rc = get_rfft_table(ctx, m, &t);
     if (rc) return rc;
+    if (!is_pow2(m)) { // untwist, ifft(m) through Bluestein, unpack (a reinterpretation): src/rfft.rs:485-507
+        cudaStream_t s = pick_stream(ctx, stream);
+        ElementwiseArgs e;
+        e.op = EW_UNTWIST;
+        e.n = static_cast<long>(m);
+        e.rows = static_cast<long>(batch);
+        e.x = static_cast<const float2 *>(d_in);
+        e.rtw = t->dev;
+        e.a = reinterpret_cast<float2 *>(d_out);
+        rc = elementwise(ctx, e, s);
+        if (rc) return rc;
+        return bluestein_c2c(ctx, d_out, d_out, m, batch, 1, s);
+    }
     IoArgs io;
     io.in = d_in;
     io.out = d_out;
@@ -838,6 +994,22 @@ int kofft_cuda_stft_f32(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, 
     int rc = check_fft_len(win_len);                          // first fft.fft(frame) :102
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
+    if (!is_pow2(win_len) || win_len > 16384) { // framing kernel, then the C2C core (Bluestein / large-N) in place on the frames
+        cudaStream_t s = pick_stream(ctx, stream);
+        ElementwiseArgs e;
+        e.op = EW_FRAME;
+        e.n = static_cast<long>(win_len);
+        e.rows = static_cast<long>(channels * nframes);
+        e.re = d_signal;
+        e.aux_f = d_window;
+        e.a = static_cast<float2 *>(d_frames);
+        e.len = static_cast<long>(len);
+        e.nframes = static_cast<long>(nframes);
+        e.hop = static_cast<long>(hop);
+        rc = elementwise(ctx, e, s);
+        if (rc) return rc;
+        return kofft_cuda_fft_c2c_f32(ctx, d_frames, d_frames, win_len, channels * nframes, 0, stream);
+    }
     IoArgs io;
     io.in = d_signal;
     io.aux = d_window;
@@ -863,7 +1035,7 @@ int kofft_cuda_stft_magnitudes_f32(kofft_cuda_ctx *ctx, const float *d_signal, s
     cudaStream_t s = pick_stream(ctx, stream);
     CU(cudaMemsetAsync(d_max, 0, channels * sizeof(float), s)); // max_mag starts at 0.0 (spectrogram.rs:64)
     if (nframes == 0) return KOFFT_OK;
-    int rc = check_fft_len(win_len);
+    int rc = check_pow2_len(win_len);
     if (rc) return rc;
     if (win_len < 32)
         return fail_msg(-static_cast<int>(cudaErrorNotSupported), "fused stft magnitudes need win_len >= 32");
@@ -893,7 +1065,7 @@ int kofft_cuda_stft_magnitudes_host_f32(kofft_cuda_ctx *ctx, const float *sample
 {
     if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE;
     if (nframes < (len + hop - 1) / hop) return KOFFT_ERR_MISMATCHED_LENGTHS;
-    int rc = nframes ? check_fft_len(win_len) : KOFFT_OK;
+    int rc = nframes ? check_pow2_len(win_len) : KOFFT_OK;
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
     std::vector<float> w(win_len ? win_len : 1);
@@ -931,7 +1103,7 @@ int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nfram
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     const int Lw = log2_of(win_len);
-    if (ctx->istft_fused && nframes > 0 && out_len > 0 && Lw >= 9 && Lw <= 12 && hop <= win_len &&
+    if (ctx->istft_fused && nframes > 0 && out_len > 0 && is_pow2(win_len) && Lw >= 9 && Lw <= 12 && hop <= win_len &&
         aligned16(d_frames)) {
         // one kernel: ifft + window + ordered overlap-add + normalisation (istft_fused.cuh)
         const Table *t = nullptr;
@@ -961,6 +1133,54 @@ int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nfram
         if (e != cudaSuccess) return fail_cuda(e, "fused istft launch");
         ctx->launches++;
         return KOFFT_OK;
+    }
+    if (nframes > 0 && (!is_pow2(win_len) || win_len > 16384)) {
+        // ifft of every frame through the C2C core (Bluestein / large-N), real * window, ordered overlap-add
+        const size_t per_ch = nframes * win_len * sizeof(float2);
+        size_t chunk = per_ch ? ctx->istft_ws_limit / per_ch : channels;
+        if (chunk < 1) chunk = 1;
+        if (chunk > channels) chunk = channels;
+        void *z = nullptr, *tm = nullptr;
+        int rc = ensure_ws(ctx, 5, chunk * per_ch, &z);
+        if (rc) return rc;
+        rc = ensure_ws(ctx, 6, chunk * per_ch / 2, &tm);
+        if (rc) return rc;
+        rc = ws_acquire(ctx, 5, s);
+        if (rc) return rc;
+        rc = ws_acquire(ctx, 6, s);
+        if (rc) return rc;
+        for (size_t c0 = 0; c0 < channels; c0 += chunk) {
+            const size_t nc = (channels - c0 < chunk) ? channels - c0 : chunk;
+            rc = kofft_cuda_fft_c2c_f32(ctx, static_cast<const float2 *>(d_frames) + c0 * nframes * win_len, z, win_len,
+                                        nc * nframes, 1, stream);
+            if (rc) return rc;
+            ElementwiseArgs e;
+            e.op = EW_TIME;
+            e.n = static_cast<long>(win_len);
+            e.rows = static_cast<long>(nc * nframes);
+            e.a = static_cast<float2 *>(z);
+            e.aux_f = d_window;
+            e.out_re = static_cast<float *>(tm);
+            rc = elementwise(ctx, e, s);
+            if (rc) return rc;
+            OlaArgs o;
+            o.time = static_cast<const float *>(tm);
+            o.window = d_window;
+            o.output = d_output + c0 * out_len;
+            o.norm = d_norm ? d_norm + c0 * out_len : nullptr;
+            o.channels = static_cast<long>(nc);
+            o.nframes = static_cast<long>(nframes);
+            o.win_len = static_cast<long>(win_len);
+            o.hop = static_cast<long>(hop);
+            o.out_len = static_cast<long>(out_len);
+            o.zero_uncovered = zero_uncovered;
+            cudaError_t e2 = launch_ola(o, s);
+            if (e2 != cudaSuccess) return fail_cuda(e2, "ola launch");
+            ctx->launches++;
+        }
+        rc = ws_release(ctx, 5, s);
+        if (rc) return rc;
+        return ws_release(ctx, 6, s);
     }
     // stage 1 writes windowed real frames into a bounded workspace, a few channels at a time
     const size_t per_channel = nframes * win_len * sizeof(float);
@@ -1165,7 +1385,7 @@ int kofft_cuda_stft_stream_create(kofft_cuda_ctx *ctx, size_t channels, const fl
 {
     if (!ctx || !out || !window) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null argument");
     if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE; // StftStream::new, src/stft.rs:178-180
-    int rc = check_fft_len(win_len);
+    int rc = check_pow2_len(win_len);
     if (rc) return rc;
     if (channels == 0) return fail_msg(KOFFT_ERR_INVALID_VALUE, "channels == 0");
     CU(cudaSetDevice(ctx->device));
@@ -1256,7 +1476,7 @@ int kofft_cuda_istft_stream_create(kofft_cuda_ctx *ctx, size_t channels, const f
 {
     if (!ctx || !out || !window) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null argument");
     if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE; // IstftStream::new, src/stft.rs:434-436
-    int rc = check_fft_len(win_len);
+    int rc = check_pow2_len(win_len);
     if (rc) return rc;
     if (channels == 0) return fail_msg(KOFFT_ERR_INVALID_VALUE, "channels == 0");
     CU(cudaSetDevice(ctx->device));

@@ -108,6 +108,15 @@ struct SplitArgs {
 };
 cudaError_t launch_split32_fft(int L, const LaunchArgs &a, SplitArgs &g);
 
+// power-of-two lengths above 2^16 (fft_huge.cu): 256-point column pass + register passes through two scratch buffers
+constexpr int kHugeMaxLog2 = 27;
+struct HugeArgs {
+    float2 *scratch[2] = {nullptr, nullptr}; // chunk_rows * 2^L complex each
+    long chunk_rows = 1;                      // transforms per trip through the scratch buffers
+    int launches = 0;                         // out: kernels launched
+};
+cudaError_t launch_huge_fft(int L, const LaunchArgs &a, HugeArgs &g);
+
 // per-L entry points (one per fft_inst.cu build)
 #define KOFFT_DECL_L(L) cudaError_t launch_cta_fft_L##L(const LaunchArgs &a);
 KOFFT_DECL_L(5) KOFFT_DECL_L(6) KOFFT_DECL_L(7) KOFFT_DECL_L(8) KOFFT_DECL_L(9)
@@ -137,6 +146,23 @@ struct BluesteinArgs {
     float scale_m = 1.0f, scale_n = 1.0f;
 };
 cudaError_t launch_bluestein_step(int step, const BluesteinArgs &b, bool exact, int num_sms, cudaStream_t s);
+
+// element-wise steps around a non-power-of-two core (bluestein.cu): the reference's gather / scatter, framing,
+// untwist / twist and real * window loops, one kernel each
+enum ElementwiseOp : int { EW_GATHER = 0, EW_SCATTER = 1, EW_FRAME = 2, EW_TIME = 3, EW_UNTWIST = 4, EW_TWIST = 5 };
+struct ElementwiseArgs {
+    int op = 0;
+    long n = 0, rows = 0;          // core length (twist / untwist: m) and rows
+    const float *re = nullptr, *im = nullptr; // gather: source planes; frame: re = signal
+    float *out_re = nullptr, *out_im = nullptr; // scatter: destination planes; time: out_re = time frames
+    long es = 0, rs = 0;           // gather / scatter: element and row strides in floats
+    float2 *a = nullptr;           // the dense complex rows (gather / frame / untwist / twist: destination)
+    const float2 *x = nullptr;     // untwist: X [rows][m+1]; twist: Y [rows][m]
+    const float2 *rtw = nullptr;   // T' (src/rfft.rs:172-183)
+    const float *aux_f = nullptr;  // frame / time: window
+    long len = 0, nframes = 0, hop = 0;
+};
+cudaError_t launch_elementwise(const ElementwiseArgs &e, bool exact, int num_sms, cudaStream_t s);
 
 // f64 twin (fft_f64.cuh): FftImpl<f64>::fft / ifft, N = 1 .. 8192 (power of two), contiguous rows
 struct LaunchF64Args {

@@ -33,7 +33,9 @@ class OracleError(Exception):
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(_HERE, f) for f in ("kofft_oracle.c", "kofft_oracle_f64.c")]
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
+    fast = os.path.join(_HERE, "libkofft_oracle_fast.so")
+    newest = max(os.path.getmtime(f) for f in srcs + [os.path.join(_HERE, "Makefile")])
+    if force or not os.path.exists(_SO) or not os.path.exists(fast) or min(os.path.getmtime(_SO), os.path.getmtime(fast)) < newest:
         subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
     return _SO
 
@@ -154,10 +156,30 @@ def fft_batch(x, inverse: bool = False, nthreads: int = 1) -> np.ndarray:
     return a
 
 
-def fft_batch_inplace(a: np.ndarray, inverse: bool = False, nthreads: int = 1) -> None:
-    """Timed-baseline entry: no copies."""
+_fast = None
+
+
+def lib_fast() -> C.CDLL:
+    """The timing-only -O3 / 128-bit-vector build of the same sources (oracle/Makefile); only the batch entry
+    points used by bench.py are bound.  tests/test_oracle_golden.py asserts it is bit-identical to lib()."""
+    global _fast
+    if _fast is None:
+        build()
+        _fast = C.CDLL(os.path.join(_HERE, "libkofft_oracle_fast.so"))
+        sz, fp, ip = C.c_size_t, C.c_void_p, C.c_int
+        _fast.kofft_oracle_fft_batch_f32.restype = ip
+        _fast.kofft_oracle_fft_batch_f32.argtypes = [fp, sz, sz, ip, ip]
+        _fast.kofft_oracle_stft_batch_f32.restype = ip
+        _fast.kofft_oracle_stft_batch_f32.argtypes = [fp, sz, sz, fp, sz, sz, fp, sz, ip, ip]
+        _fast.kofft_oracle_rfft_batch_f32.restype = ip
+        _fast.kofft_oracle_rfft_batch_f32.argtypes = lib().kofft_oracle_rfft_batch_f32.argtypes
+    return _fast
+
+
+def fft_batch_inplace(a: np.ndarray, inverse: bool = False, nthreads: int = 1, fast: bool = False) -> None:
+    """Timed-baseline entry: no copies.  fast: the -O3 vectorised build (same bits, see lib_fast)."""
     assert a.dtype == np.complex64 and a.flags.c_contiguous and a.ndim == 2
-    _chk(lib().kofft_oracle_fft_batch_f32(_p(a), a.shape[1], a.shape[0], int(inverse), nthreads))
+    _chk((lib_fast() if fast else lib()).kofft_oracle_fft_batch_f32(_p(a), a.shape[1], a.shape[0], int(inverse), nthreads))
 
 
 # ---- f64 twin (kofft_oracle_f64.c) ----------------------------------------------------------
@@ -299,12 +321,13 @@ def istft_stream(frames, window, hop: int) -> np.ndarray:
     return out[: n.value].copy()
 
 
-def stft_batch(signal, window, hop: int, nframes: int, fresh_planner: bool = False, nthreads: int = 1) -> np.ndarray:
+def stft_batch(signal, window, hop: int, nframes: int, fresh_planner: bool = False, nthreads: int = 1,
+               fast: bool = False) -> np.ndarray:
     s, w = _f32(signal), _f32(window)
     assert s.ndim == 2
     ch, ln = s.shape
     frames = np.zeros((ch, nframes, w.size), dtype=np.complex64)
-    _chk(lib().kofft_oracle_stft_batch_f32(_p(s), ln, ch, _p(w), w.size, hop, _p(frames), nframes,
+    _chk((lib_fast() if fast else lib()).kofft_oracle_stft_batch_f32(_p(s), ln, ch, _p(w), w.size, hop, _p(frames), nframes,
                                            int(fresh_planner), nthreads))
     return frames
 

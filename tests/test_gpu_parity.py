@@ -925,11 +925,74 @@ def test_bluestein_non_power_of_two(cuda_fft, cuda_fft_fast, oracle, n):
         assert np.max(np.abs(d - want)) < 1e-3
 
 
-def test_bluestein_too_long_is_an_error(cuda_fft):
+def test_bluestein_beyond_32768(cuda_fft, oracle):
+    """Non-power-of-two lengths whose padded length exceeds 2^16 run through the huge-N passes (m = 2^17, 2^18)."""
+    rng = np.random.default_rng(40000)
+    for n in (40000, 100003):
+        x = uniform_c64(rng, (2, n))
+        y = x.copy()
+        cuda_fft.fft_batch(y)
+        assert np.array_equal(y, oracle.fft_batch(x, nthreads=4)), n
+    y = x.copy()
+    cuda_fft.fft_batch(y, inverse=True)
+    assert np.array_equal(y, oracle.fft_batch(x, inverse=True, nthreads=4))
+
+
+def test_lengths_beyond_the_single_gpu_range_are_an_error(cuda_fft):
+    import torch
+
     import kofft_b200 as k
 
+    x = torch.zeros((1, 1 << 28), dtype=torch.complex64, device="cuda")
     with pytest.raises(k.CudaBackendError):
-        cuda_fft.fft(np.zeros(40000, np.complex64))
+        cuda_fft.fft_batch(x)
+
+
+@pytest.mark.parametrize("log2n", [17, 18, 19, 20, 21, 22])
+def test_huge_c2c(cuda_fft, cuda_fft_fast, oracle, log2n):
+    """Lengths above 2^16 (the reference has no upper bound, src/fft.rs:1054-1082, and benchmarks 2^20,
+    benchmarks/README.md:5-7): 256-point column pass + register passes through global memory; every radix of the
+    last pass (2^17: 1 stage, 2^18: 2, 2^19: 3, 2^20: 4) and several passes (2^21, 2^22).  Bit-exact."""
+    n = 1 << log2n
+    rng = np.random.default_rng(log2n)
+    rows = 3 if log2n <= 20 else 2
+    x = uniform_c64(rng, (rows, n))
+    ref = oracle.fft_batch(x, nthreads=8)
+    y = x.copy()
+    cuda_fft.fft_batch(y)
+    assert np.array_equal(y, ref), rel_l2(y, ref)
+    if log2n in (17, 20, 22):
+        y = x.copy()
+        cuda_fft.fft_batch(y, inverse=True)
+        assert np.array_equal(y, oracle.fft_batch(x, inverse=True, nthreads=8))
+        z = x.copy()
+        cuda_fft_fast.fft_batch(z)
+        assert rel_l2(z, ref) <= TOL
+        re, im = np.ascontiguousarray(x[1].real), np.ascontiguousarray(x[1].imag)
+        cuda_fft.fft_split(re, im)
+        assert np.array_equal(re, ref[1].real) and np.array_equal(im, ref[1].imag)
+    if log2n == 20:  # the reference's bench input (i, 0) (kofft-bench/benches/bench_fft.rs:109), trait-level call
+        ramp = (np.arange(n, dtype=np.float32) + 0j).astype(np.complex64)
+        want = oracle.fft(ramp)
+        cuda_fft.fft(ramp)
+        assert np.array_equal(ramp, want)
+
+
+@pytest.mark.parametrize("log2n", [18, 20, 21])
+def test_huge_rfft_irfft(cuda_fft, cuda_fft_fast, oracle, log2n):
+    """rfft / irfft above 2^17 (complex core above 2^16): column pass, register passes, twist kernel."""
+    n = 1 << log2n
+    rng = np.random.default_rng(100 + log2n)
+    x = rng.uniform(-1, 1, (2, n)).astype(np.float32)
+    ref = oracle.rfft_batch(x, nthreads=8)
+    y = cuda_fft.rfft_batch(x)
+    assert np.array_equal(y, ref), rel_l2(y, ref)
+    assert np.array_equal(cuda_fft.irfft_batch(ref, n), oracle.irfft_batch(ref, n, nthreads=8))
+    assert rel_l2(cuda_fft_fast.rfft_batch(x), ref) <= TOL
+    import torch
+
+    d = torch.from_numpy(x).cuda()  # device-pointer path
+    assert np.array_equal(cuda_fft.rfft_batch(d).cpu().numpy(), ref)
 
 
 def test_ndfft_2d_3d(cuda_fft, oracle):
@@ -974,6 +1037,7 @@ def test_ndfft_2d_3d(cuda_fft, oracle):
     (2048, 512, [100, 5000, 1948, 512, 511, 20000, 3]),   # BASELINE window / hop, ragged pushes
     (1024, 300, [4096, 1, 1023, 7000]),                   # hop does not divide the window
     (512, 512, [512, 1000, 24]),                          # no overlap
+    (256, 700, [300, 1000, 5, 2000, 1, 699, 702]),        # hop > window: samples between frames are skipped across pushes
 ])
 def test_device_streams_match_offline(cuda_fft, oracle, win_len, hop, chunks):
     """Device twins of StftStream / IstftStream (src/stft.rs:160-206, 407-520; tests/istft_stream.rs):
@@ -1002,6 +1066,8 @@ def test_device_streams_match_offline(cuda_fft, oracle, win_len, hop, chunks):
     torch.cuda.synchronize()
     assert frames.shape[1] == nframes
     assert np.array_equal(frames.cpu().numpy(), ref_frames)
+    if hop > win_len:
+        return  # the inverse stream is defined for overlapping frames
 
     ist = S.DeviceIstftStream(cuda_fft, ch, w, hop)
     assert ist.flush().shape[1] == 0  # nothing before the first frame (src/stft.rs:498-500)
@@ -1032,3 +1098,138 @@ def test_device_stream_errors(cuda_fft, oracle):
         S.DeviceStftStream(cuda_fft, 1, oracle.hann(256), 0)
     with pytest.raises(InvalidHopSize):
         S.DeviceIstftStream(cuda_fft, 1, oracle.hann(256), 0)
+
+
+def test_two_streams_share_one_context(cuda_fft, oracle):
+    """The device-pointer calls are stream-ordered on the CALLER's stream, but the large-N intermediate, the
+    dependency flags and the Bluestein / unfused-ISTFT workspaces are one per context: calls issued on two
+    streams must not overlap on them (the library orders them with events).  Same results as one stream."""
+    import torch
+
+    n, rows = 32768, 300
+    g = torch.Generator(device="cuda").manual_seed(5)
+    xs = [torch.view_as_complex((torch.rand((rows, n, 2), generator=g, device="cuda") * 2 - 1).contiguous()) for _ in range(2)]
+    xr = [(torch.rand((rows, 2 * n), generator=g, device="cuda") * 2 - 1).contiguous() for _ in range(2)]
+    xb = [torch.view_as_complex((torch.rand((64, 3000, 2), generator=g, device="cuda") * 2 - 1).contiguous()) for _ in range(2)]
+    want = [cuda_fft.fft_batch(x, out=torch.empty_like(x)) for x in xs]
+    wantr = [cuda_fft.rfft_batch(x) for x in xr]
+    wantb = [cuda_fft.fft_batch(x, out=torch.empty_like(x)) for x in xb]  # non-power-of-two: Bluestein workspace
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = [[None] * 2 for _ in range(3)]
+    for rep in range(6):
+        for si in (0, 1):
+            with torch.cuda.stream(streams[si]):
+                got[0][si] = cuda_fft.fft_batch(xs[si], out=torch.empty_like(xs[si]))
+                got[1][si] = cuda_fft.rfft_batch(xr[si])
+                got[2][si] = cuda_fft.fft_batch(xb[si], out=torch.empty_like(xb[si]))
+    torch.cuda.synchronize()
+    for si in (0, 1):
+        assert torch.equal(torch.view_as_real(got[0][si]), torch.view_as_real(want[si]))
+        assert torch.equal(torch.view_as_real(got[1][si]), torch.view_as_real(wantr[si]))
+        assert torch.equal(torch.view_as_real(got[2][si]), torch.view_as_real(wantb[si]))
+    assert np.array_equal(want[0][:3].cpu().numpy(), oracle.fft_batch(xs[0][:3].cpu().numpy(), nthreads=4))
+
+
+def test_tensor_arguments_are_validated(cuda_fft):
+    """A wrong dtype, a CPU tensor, a non-contiguous view or an undersized `out` raises instead of handing a bad
+    pointer to the kernels."""
+    import torch
+
+    from kofft_b200 import spectrogram as SP
+    from kofft_b200 import stft as S
+    from kofft_b200.errors import MismatchedLengths
+
+    x = torch.zeros((4, 256), dtype=torch.complex64, device="cuda")
+    with pytest.raises(TypeError):
+        cuda_fft.fft_batch(x.to(torch.complex128))
+    with pytest.raises(TypeError):
+        cuda_fft.fft_batch(x[:, ::2])
+    with pytest.raises(MismatchedLengths):
+        cuda_fft.fft_batch(x, out=torch.zeros((4, 128), dtype=torch.complex64, device="cuda"))
+    r = torch.zeros((4, 256), dtype=torch.float32, device="cuda")
+    with pytest.raises(TypeError):
+        cuda_fft.rfft_batch(r.double())
+    with pytest.raises(MismatchedLengths):
+        cuda_fft.rfft_batch(r, out=torch.zeros((4, 128), dtype=torch.complex64, device="cuda"))
+    with pytest.raises(TypeError):
+        cuda_fft.irfft_batch(torch.zeros((4, 129), dtype=torch.complex64), 256)  # CPU tensor
+    with pytest.raises(TypeError):
+        cuda_fft.fft_split_batch(r, r.double())
+    w = torch.ones(64, device="cuda")
+    sig = torch.zeros((2, 1000), device="cuda")
+    with pytest.raises(TypeError):
+        S.stft_batch(cuda_fft, sig, w.cpu(), 16, 63)
+    with pytest.raises(MismatchedLengths):
+        S.stft_batch(cuda_fft, sig, w, 16, 63, out=torch.zeros((2, 63, 32), dtype=torch.complex64, device="cuda"))
+    frames = torch.zeros((2, 63, 64), dtype=torch.complex64, device="cuda")
+    with pytest.raises(TypeError):
+        S.istft_batch(cuda_fft, frames, w.double(), 16, torch.zeros((2, 1000), device="cuda"))
+    with pytest.raises(MismatchedLengths):
+        S.istft_batch(cuda_fft, frames, w, 16, torch.zeros((3, 1000), device="cuda"))
+    with pytest.raises(TypeError):
+        SP.stft_magnitudes_batch(cuda_fft, sig.double(), w, 16, 63)
+    with pytest.raises(MismatchedLengths):
+        cuda_fft.fft_strided_batch(torch.zeros(100, dtype=torch.complex64, device="cuda"), 64, 2, 1, 64)
+
+
+def test_rfft_planner_flavour_does_not_stick(cuda_fft, oracle):
+    """RfftPlanner(fma_mul=True) uses the fused-multiply table for ITS calls only (src/rfft.rs:172-183 under +fma);
+    the shared context goes back to the default table afterwards."""
+    from kofft_b200.rfft import RfftPlanner
+
+    rng = np.random.default_rng(17)
+    x = rng.uniform(-1, 1, 4096).astype(np.float32)
+    ref = oracle.rfft_batch(x[None])[0]
+    out = np.zeros(2049, np.complex64)
+    RfftPlanner(fma_mul=True).rfft(cuda_fft, x, out)
+    again = np.zeros(2049, np.complex64)
+    cuda_fft.rfft(x, again)
+    assert np.array_equal(again, ref)
+    assert np.array_equal(cuda_fft.rfft_batch(x[None])[0], ref)
+
+
+@pytest.mark.parametrize("n", [6, 30, 100, 1000, 6000])
+def test_non_power_of_two_through_every_core(cuda_fft, cuda_fft_fast, oracle, n):
+    """The reference's rfft / irfft / stft / istft / split / strided all end in fft.fft(), which takes Bluestein for
+    non-power-of-two lengths in the std build (src/rfft.rs:447, 502, src/stft.rs:102, 141, src/fft.rs:797-809,
+    1191-1197).  Same here: bit-identical to the oracle, which restates those call chains."""
+    from kofft_b200 import stft as S
+
+    rng = np.random.default_rng(n)
+    # rfft / irfft with a non-power-of-two half length m = n
+    x = rng.uniform(-1, 1, (3, 2 * n)).astype(np.float32)
+    ref = oracle.rfft_batch(x, nthreads=2)
+    got = cuda_fft.rfft_batch(x)
+    assert np.array_equal(got, ref), rel_l2(got, ref)
+    assert np.array_equal(cuda_fft.irfft_batch(ref, 2 * n), oracle.irfft_batch(ref, 2 * n, nthreads=2))
+    assert rel_l2(cuda_fft_fast.rfft_batch(x), ref) <= TOL
+    one = np.zeros(n + 1, np.complex64)
+    cuda_fft.rfft(x[0].copy(), one)  # trait-level call
+    assert np.array_equal(one, ref[0])
+    # split (SoA) and strided rows
+    c = uniform_c64(rng, (n,))
+    want = oracle.fft(c)
+    re, im = np.ascontiguousarray(c.real), np.ascontiguousarray(c.imag)
+    cuda_fft.fft_split(re, im)
+    assert np.array_equal(re, want.real) and np.array_equal(im, want.imag)
+    re, im = np.ascontiguousarray(c.real), np.ascontiguousarray(c.imag)
+    cuda_fft.ifft_split(re, im)
+    iwant = oracle.fft_batch(c[None], inverse=True)[0]
+    assert np.array_equal(re, iwant.real) and np.array_equal(im, iwant.imag)
+    buf = np.zeros(3 * n, np.complex64)
+    buf[::3] = c
+    cuda_fft.fft_strided(buf, 3, np.zeros(n, np.complex64))
+    assert np.array_equal(buf[::3], want) and not buf[1::3].any()
+    # stft / istft with a non-power-of-two window
+    hop = max(1, n // 3)
+    sig = rng.uniform(-1, 1, (2, 7 * n + 5)).astype(np.float32)
+    w = oracle.hann(n)
+    nframes = -(-sig.shape[1] // hop)
+    fref = oracle.stft_batch(sig, w, hop, nframes)
+    frames = S.stft_batch(cuda_fft, sig, w, hop, nframes)
+    assert np.array_equal(frames, fref)
+    rec = np.zeros_like(sig)
+    S.istft_batch(cuda_fft, fref, w, hop, rec)
+    wantr = np.stack([oracle.istft(fref[ch], w, hop, np.zeros(sig.shape[1], np.float32)) for ch in range(2)])
+    assert np.array_equal(rec, wantr)
