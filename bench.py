@@ -69,14 +69,89 @@ def peaks() -> tuple[float, str]:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic() -> float | None:
-    """dram bytes per launch of the headline kernel from the committed ncu summary, if any."""
+HEADLINE_KERNEL = "fft_cta_kernelILi12ELb1ENS_5IoC2CILb0EEELb1EE"  # mangled-name fragment of the headline instantiation
+
+
+def headline_sass_hash() -> str | None:
+    """sha256 of the headline kernel's SASS in the library that is loaded: the committed ncu traffic figure is only
+    quoted while the kernel it was measured on is the kernel that runs (scripts/summarize_ncu.py stamps it)."""
+    import hashlib
+    import subprocess
+
+    lib = os.environ.get("KOFFT_CUDA_LIB") or os.path.join(ROOT, "kofft_b200", "lib", "libkofft_cuda.so")
+    try:
+        names = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True, timeout=120).stdout
+        fn = next((w for w in names.split() if HEADLINE_KERNEL in w and w.startswith(".text.")), None)
+        if fn is None:
+            return None
+        sass = subprocess.run(["cuobjdump", "-sass", "-fun", fn[len(".text."):], lib], capture_output=True, text=True,
+                              timeout=300).stdout
+        body = "\n".join(l.split("/*")[1].split("*/")[1].strip() if l.count("/*") >= 2 else "" for l in sass.splitlines()
+                         if "/*" in l and "Function" not in l)
+        return hashlib.sha256(body.encode()).hexdigest() if body.strip() else None
+    except Exception:
+        return None
+
+
+def ncu_traffic() -> tuple[float | None, str]:
+    """dram bytes per launch of the headline kernel from the committed ncu summary -- only if that capture was
+    taken on the same SASS as the kernel that runs now; otherwise None (stale)."""
     path = os.path.join(ROOT, "profiles", "headline_kernel_traffic.json")
     try:
         with open(path) as f:
-            return float(json.load(f)["dram_bytes_per_launch"])
-    except Exception:
-        return None
+            d = json.load(f)
+        want = d.get("sass_sha256")
+        if not want:
+            return None, "committed ncu capture carries no SASS stamp"
+        have = headline_sass_hash()
+        if have != want:
+            return None, "stale: the committed ncu capture was taken on different SASS of the headline kernel"
+        return float(d["dram_bytes_per_launch"]), "ncu --set full capture of this SASS (profiles/%s)" % d.get("source", "")
+    except Exception as e:
+        return None, f"no committed capture ({type(e).__name__})"
+
+
+def bind_to_gpu_numa_node(index: int, props=None) -> dict:
+    """Pin this rank (and with it the pages of the pinned buffers it allocates afterwards: first touch) to the NUMA
+    node of its GPU.  Without this every rank of an 8-GPU run allocates on node 0 and the host side of the e2e
+    number collapses (SCALE_r01: 257 ms/step at 8 GPUs against 45 at 1)."""
+    info = {"node": None, "cpus_bound": False, "mem_bound": False}
+    try:
+        import ctypes
+
+        if props is not None and hasattr(props, "pci_bus_id"):  # the CUDA device's own PCI address (index != NVML index
+            bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"  # under CUDA_VISIBLE_DEVICES)
+        else:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            bus = bus.lower()
+            if len(bus.split(":")[0]) == 8:
+                bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        info["node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus_bound"] = True
+            info["cpus"] = len(allowed)
+        # set_mempolicy(MPOL_PREFERRED, {node}): pages of later allocations come from the GPU's node
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))  # __NR_set_mempolicy (x86-64), MPOL_PREFERRED
+        info["mem_bound"] = rc == 0
+    except Exception as e:
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
 
 
 # ---------------------------------------------------------------------------------------------
@@ -138,18 +213,34 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------
+_CPU_ROWS: dict = {}
+
+
+def _cpu_rows(rows: int) -> np.ndarray:
+    """uniform[-1,1) complex64 rows for the CPU legs, generated once (2 GiB for the full step)"""
+    if rows not in _CPU_ROWS:
+        rng = np.random.default_rng(0)
+        a = rng.random((rows, 2 * N), dtype=np.float32)
+        a *= 2.0
+        a -= 1.0
+        _CPU_ROWS.clear()
+        _CPU_ROWS[rows] = a.view(np.complex64)
+    return _CPU_ROWS[rows]
+
+
 def cpu_port_gflops(rows: int, reps: int, threads: int) -> tuple[float, float]:
     """kofft's CPU path (oracle port) on `rows` transforms of length N, all `threads` cores:
     rows split evenly over threads, one reused planner per thread.  Returns (GFLOP/s, seconds)."""
     from oracle import kofft_oracle as ko
 
     ko.build()
-    rng = np.random.default_rng(0)
-    x = (rng.uniform(-1, 1, (rows, N)) + 1j * rng.uniform(-1, 1, (rows, N))).astype(np.complex64)
-    ko.fft_batch_inplace(x[: max(threads, 1)].copy(), nthreads=threads)  # warm the threads / tables
+    x = _cpu_rows(rows)
+    # fast=True: the -O3 / 128-bit-vector build of the same sources (the reference's hot loop is explicit SSE,
+    # src/fft.rs:845-862); bit-identical to the -O2 oracle (tests/test_oracle_golden.py)
+    ko.fft_batch_inplace(x[: max(threads, 1)].copy(), nthreads=threads, fast=True)  # warm the threads / tables
     t0 = time.perf_counter()
     for _ in range(reps):
-        ko.fft_batch_inplace(x, nthreads=threads)
+        ko.fft_batch_inplace(x, nthreads=threads, fast=True)
     dt = time.perf_counter() - t0
     return FLOPS_PER_TRANSFORM * rows * reps / dt / 1e9, dt
 
@@ -166,9 +257,9 @@ def cpu_port_stft_frames_per_s(threads: int, fresh_planner: bool) -> tuple[float
     rng = np.random.default_rng(2)
     sig = rng.uniform(-1, 1, (ch, length)).astype(np.float32)
     w = ko.hann(win)
-    ko.stft_batch(sig[:, :48_000], w, hop, -(-48_000 // hop), fresh_planner=fresh_planner, nthreads=threads)  # warm-up
+    ko.stft_batch(sig[:, :48_000], w, hop, -(-48_000 // hop), fresh_planner=fresh_planner, nthreads=threads, fast=True)  # warm-up
     t0 = time.perf_counter()
-    ko.stft_batch(sig, w, hop, nframes, fresh_planner=fresh_planner, nthreads=threads)
+    ko.stft_batch(sig, w, hop, nframes, fresh_planner=fresh_planner, nthreads=threads, fast=True)
     dt = time.perf_counter() - t0
     return ch * nframes / dt, f"{ch} ch x {length} samples ({ch * nframes} frames, {dt:.1f} s), {threads} threads over channels"
 
@@ -178,14 +269,15 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rows = 4096
+    rows = ROWS_PER_GPU  # the whole step: 65536 rows take a fraction of a second on the host cores
     for _ in range(max(args.warmup, 1)):
         cpu_port_gflops(rows, 1, threads)
     t0 = time.perf_counter()
     vals = [cpu_port_gflops(rows, 1, threads)[0] for _ in range(args.steps)]
     total = time.perf_counter() - t0
     value = statistics.median(vals)
-    sample = f"{rows} of {ROWS_PER_GPU} rows per step (N={N}), {threads} threads, rows split evenly; scaled by flops"
+    sample = (f"all {rows} rows of the step (N={N}), {threads} threads, rows split evenly, one planner per thread; "
+              "-O3 / 128-bit-vector build of the port, bit-identical to the oracle")
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -196,7 +288,9 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "kofft is a Rust crate and cannot be built in this image (no rustc/cargo); this arm times the "
-                "bit-faithful C restatement of its CPU path (oracle/kofft_oracle.c) on the host cores",
+                "bit-faithful C restatement of its CPU path (oracle/kofft_oracle.c, built -O3 with 128-bit vectors like the "
+                "reference's explicit SSE loop) on the host cores.  kofft itself has no parallel batched FFT "
+                "(batch() is sequential, src/fft.rs:2156-2164): the thread pool over rows is the generous reading",
         "wall_s": total,
     }
     print(json.dumps(line), flush=True)
@@ -218,6 +312,8 @@ def run_gpu(args) -> None:
         raise SystemExit("bench.py needs a CUDA device: kofft_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    orig_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local, torch.cuda.get_device_properties(local))
     if world > 1:
         # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION/INFO level
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -266,8 +362,9 @@ def run_gpu(args) -> None:
     avg_launch_ms = sum(per_launch_ms) / len(per_launch_ms)
     peak, peak_src = peaks()
     achieved = ALGO_BYTES_PER_TRANSFORM * ROWS_PER_GPU / (avg_launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic() if rank == 0 else (None, "")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel": "fft_cta_kernel<12, exact, IoC2C<false>>",
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_TRANSFORM * ROWS_PER_GPU,
                 "launch_ms_avg": avg_launch_ms, "launch_ms_min": min(per_launch_ms),
@@ -291,11 +388,92 @@ def run_gpu(args) -> None:
            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_s * 1e3,
            "steps": e2e_steps, "api": "kofft_cuda_fft_batch_host_f32 (CudaFftImpl.fft_batch on pinned host rows; "
                                       "32 MiB chunks pipelined over H2D / kernel / D2H streams)"}
-    del host, h
+    # the ceiling of this API shape: the same bytes as plain pinned copies, H2D and D2H at the same time on two
+    # streams, every rank at once -- what the host side of the box can deliver to N GPUs
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    host2 = torch.empty((ROWS_PER_GPU, N), dtype=torch.complex64, pin_memory=True)
+    dbuf = torch.empty((ROWS_PER_GPU, N), dtype=torch.complex64, device=dev)
+
+    dbuf2 = torch.empty((ROWS_PER_GPU, N), dtype=torch.complex64, device=dev)
+
+    def copies():
+        with torch.cuda.stream(s_in):
+            dbuf.copy_(host, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            host2.copy_(dbuf2, non_blocking=True)
+
+    copies()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copies()
+        torch.cuda.synchronize()
+    barrier()
+    ceil_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    e2e["pcie_ceiling_ms_per_step"] = ceil_s * 1e3
+    e2e["pcie_ceiling_value"] = FLOPS_PER_TRANSFORM * ROWS_PER_GPU * n_gpus / ceil_s / 1e9
+    e2e["frac_of_pcie_ceiling"] = ceil_s / e2e_s
+    e2e["pcie_gbs_per_rank_each_way"] = nbytes / e2e_s / 1e9
+    e2e["pcie_ceiling_gbs_per_rank_each_way"] = nbytes / ceil_s / 1e9
+    e2e["numa"] = numa
+    del host, h, host2, dbuf, dbuf2
 
     # ---- extra: STFT (configs[3] shape) and FAST-mode C2C, after the headline region ------------
     extra = {}
     try:
+        if world > 1:
+            # strong scaling of configs[1]: the SAME 65536 rows cut over the ranks (65536 / N rows each)
+            rows_s = ROWS_PER_GPU // world
+            xs_, ys_ = x[:rows_s], y[:rows_s]
+            for _ in range(3):
+                fft.fft_batch(xs_, out=ys_)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                fft.fft_batch(xs_, out=ys_)
+            e1.record()
+            barrier()
+            ms_s = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+            extra["c2c_strong_scaling"] = {
+                "workload": f"N={N} x batch {ROWS_PER_GPU} in total, {rows_s} rows per GPU (BASELINE configs[1] cut over the ranks)",
+                "ms_per_step": ms_s, "gflops": FLOPS_PER_TRANSFORM * ROWS_PER_GPU / ms_s / 1e6,
+                "speedup_vs_one_gpu_same_run": ms_per_step / ms_s, "efficiency": ms_per_step / ms_s / world,
+                "hbm_frac_per_gpu": ALGO_BYTES_PER_TRANSFORM * rows_s / ms_s / 1e6 / peak,
+                "note": "one-GPU time = this run's 65536-row step on every rank (max over ranks); no collective"}
+        if rank == 0:
+            # BASELINE configs[0] (examples/basic_usage.rs:232-238): one 1024-point FFT + IFFT through the trait-level
+            # host-pointer call; latency is launch + two small PCIe copies + synchronisation
+            xin = (np.sin(0.1 * np.arange(1024, dtype=np.float32)) + 0j).astype(np.complex64)
+            buf = xin.copy()
+            for _ in range(20):
+                fft.fft(buf)
+                fft.ifft(buf)
+            lat = []
+            for _ in range(200):
+                buf[:] = xin
+                t0 = time.perf_counter()
+                fft.fft(buf)
+                fft.ifft(buf)
+                lat.append((time.perf_counter() - t0) * 1e6)
+            lat.sort()
+            dx = torch.from_numpy(xin).to(dev).reshape(1, 1024)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(10):
+                fft.fft_batch(dx)
+            e0.record()
+            for _ in range(100):
+                fft.fft_batch(dx)
+                fft.fft_batch(dx, inverse=True)
+            e1.record()
+            torch.cuda.synchronize()
+            extra["config1_latency"] = {
+                "workload": "ScalarFftImpl-style 1024-point C2C FFT then IFFT, batch 1 (BASELINE configs[0])",
+                "host_call_us_median": lat[len(lat) // 2], "host_call_us_p90": lat[int(len(lat) * 0.9)],
+                "host_call_us_min": lat[0], "device_resident_us_per_fft_ifft_pair": e0.elapsed_time(e1) * 1e3 / 100,
+                "api": "kofft_cuda_fft_host_f32 x 2 (host buffer in, host buffer out, synchronous)",
+                "max_roundtrip_err": float(np.abs(buf - xin).max())}
         fast = kofft_b200.CudaFftImpl(device=local, exact=False)
         for _ in range(3):
             fast.fft_batch(x, out=y)
@@ -350,13 +528,28 @@ def run_gpu(args) -> None:
         algo = (4 * rn + 8 * (rn // 2 + 1)) * rb
         extra["rfft_65536x16384"] = {"ms": ms, "gflops_nominal": 2.5 * rn * 16 * rb / ms / 1e6, "hbm_gbs": algo / ms / 1e6,
                                      "frac_of_measured_peak": algo / ms / 1e6 / peak,
-                                     "note": "default path: one persistent cooperative kernel, column pass of chunk p "
-                                             "overlapped with row pass + fused Hermitian twist of chunk p-1, "
-                                             "intermediate pinned in L2"}
-        for key, mode_id, note in (
-                ("rfft_65536x16384_two_kernel_path", 0, "column pass + row pass, two kernels per 256 MB batch chunk"),
-                ("rfft_65536x16384_cluster_kernel_path", 1,
-                 "one persistent thread-block-cluster kernel (column pass, cluster barrier, row pass + twist)")):
+                                     "note": "default path (fft_split32.cuh): one persistent warp-specialised kernel -- A warps run "
+                                             "the 1024-point column transforms of TMA-loaded tiles, B warps the 32-point rows in "
+                                             "registers with the Hermitian twist by warp shuffles; intermediate kept in L2",
+                                     "fallbacks": fft.ctx.fallback_count}
+        yi = torch.empty_like(xr)
+        for _ in range(2):
+            fft.irfft_batch(yr, rn, out=yi)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fft.irfft_batch(yr, rn, out=yi)
+        e1.record()
+        torch.cuda.synchronize()
+        msi = e0.elapsed_time(e1) / reps
+        extra["irfft_65536x16384"] = {"ms": msi, "hbm_gbs": algo / msi / 1e6, "frac_of_measured_peak": algo / msi / 1e6 / peak,
+                                      "note": "persistent pipelined kernel (fft_large.cuh), untwist fused into the first load"}
+        del yi
+        for key, min_l, mode_id, note in (
+                ("rfft_65536x16384_pipelined_16_per_thread_path", 16, 2,
+                 "round-1 default: persistent cooperative kernel, 16 elements per thread, teams of 8 CTAs"),
+                ("rfft_65536x16384_two_kernel_path", 16, 0, "column pass + row pass, two kernels per 256 MB batch chunk")):
+            fft.ctx.set_split_min_log2n(min_l)
             fft.ctx.set_large_mode(mode_id)
             fft.rfft_batch(xr, out=yr)
             torch.cuda.synchronize()
@@ -368,18 +561,53 @@ def run_gpu(args) -> None:
             ms2 = e0.elapsed_time(e1) / reps
             extra[key] = {"ms": ms2, "hbm_gbs": algo / ms2 / 1e6, "frac_of_measured_peak": algo / ms2 / 1e6 / peak, "note": note}
         fft.ctx.set_large_mode(3)
+        fft.ctx.set_split_min_log2n(14)
         del xr, yr
+        # C2C at the sizes between the single-CTA kernel and the headline config, and one length above 2^16
+        for cn in (8192, 16384, 32768, 65536, 1 << 20):
+            crows = (1 << 28) // cn
+            xc = torch.view_as_complex(torch.rand((crows, cn, 2), generator=g, device=dev) * 2 - 1).contiguous()
+            yc = torch.empty_like(xc)
+            for _ in range(2):
+                fft.fft_batch(xc, out=yc)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                fft.fft_batch(xc, out=yc)
+            e1.record()
+            torch.cuda.synchronize()
+            msc = e0.elapsed_time(e1) / reps
+            extra[f"c2c_{cn}x{crows}"] = {"ms": msc, "gflops": 5.0 * cn * math.log2(cn) * crows / msc / 1e6,
+                                          "hbm_gbs": 16.0 * cn * crows / msc / 1e6,
+                                          "frac_of_measured_peak": 16.0 * cn * crows / msc / 1e6 / peak}
+            del xc, yc
+        if rank == 0:  # the reference's own benchmark size N = 2^20 (benchmarks/README.md:5-7) beside the CPU port
+            try:
+                from oracle import kofft_oracle as ko
+
+                one = (np.random.default_rng(20).uniform(-1, 1, (4, 1 << 20)) + 0j).astype(np.complex64)
+                ko.fft_batch_inplace(one.copy(), nthreads=1, fast=True)
+                t0 = time.perf_counter()
+                ko.fft_batch_inplace(one, nthreads=1, fast=True)
+                dtc = (time.perf_counter() - t0) / 4
+                extra["c2c_1048576x256"]["cpu_port_one_thread_ms_per_transform"] = dtc * 1e3
+                extra["c2c_1048576x256"]["gpu_ms_per_transform"] = extra["c2c_1048576x256"]["ms"] / 256
+            except Exception as e:  # pragma: no cover
+                extra["c2c_1048576x256"]["cpu_error"] = repr(e)
         torch.cuda.empty_cache()
+
+        # ---- STFT / ISTFT (BASELINE configs[3]); N > 1: the 64 channels are sharded over the ranks ----------------
         free, _ = torch.cuda.mem_get_info()
-        ch, length, hop, win = 64, 28_800_000, 512, 2048
-        if free < 90e9:
-            ch = 8
+        ch_total, length, hop, win = 64, 28_800_000, 512, 2048
+        ch = ch_total // world if (world > 1 and ch_total % world == 0) else ch_total
+        if free < 90e9 and world == 1:
+            ch = ch_total = 8
         nframes = -(-length // hop)
         sig = (torch.rand((ch, length), generator=g, device=dev) * 2 - 1).contiguous()
         w = torch.from_numpy(W.hann(win)).to(dev)
         frames = torch.empty((ch, nframes, win), dtype=torch.complex64, device=dev)
         S.stft_batch(fft, sig, w, hop, nframes, out=frames)
-        torch.cuda.synchronize()
+        barrier()
         reps = 6
         stft_sampler = ClockSampler(local)  # the STFT is FP32-bound: its time moves with the SM clock
         stft_sampler.start()
@@ -388,67 +616,124 @@ def run_gpu(args) -> None:
         for _ in range(reps):
             S.stft_batch(fft, sig, w, hop, nframes, out=frames)
         e1.record()
-        torch.cuda.synchronize()
+        barrier()
         stft_clocks = stft_sampler.stop()
-        ms = e0.elapsed_time(e1) / reps
-        algo = 4 * ch * length + 8 * ch * nframes * win
+        ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+        algo = 4 * ch * length + 8 * ch * nframes * win  # per GPU
         # FP32 floor of the EXACT kernel: 10 lane-operations per butterfly, (N/2) log2 N butterflies per
         # frame minus the real-input shortcuts (8 %), 128 lanes per SM and clock
         fma_floor_ms = {mhz: 10 * 0.92 * (win // 2) * 11 * ch * nframes / (128 * 148 * mhz * 1e6) * 1e3
                         for mhz in (stft_clocks.get("sm_mhz") or 1965, 1965)}
         cpu_stft = {}
-        if rank == 0:
+        if rank == 0 and world == 1:
             try:
                 threads_c = os.cpu_count() or 1
+                os.sched_setaffinity(0, orig_affinity)  # the CPU legs use every host core, not just the GPU's NUMA node
                 fps_shared, smp = cpu_port_stft_frames_per_s(threads_c, False)
                 fps_fresh, _ = cpu_port_stft_frames_per_s(threads_c, True)
                 cpu_stft = {"frames_per_s_shared_table": fps_shared, "frames_per_s_fresh_planner_per_frame": fps_fresh,
                             "cores": threads_c, "kind": "port", "sample": smp}
             except Exception as e:  # pragma: no cover
                 cpu_stft = {"error": repr(e)}
-        extra["stft"] = {"workload": f"Hann {win}, hop {hop}, {ch} ch x {length} samples (BASELINE configs[3])",
-                         "cpu_baseline": cpu_stft,
-                         "frames_per_s": ch * nframes / (ms * 1e-3), "ms": ms, "hbm_gbs": algo / ms / 1e6,
+        shard_note = (f"{ch_total} channels sharded over {world} GPUs ({ch} each), no collective; time = max over ranks"
+                      if world > 1 else f"{ch} channels on one GPU")
+        extra["stft"] = {"workload": f"Hann {win}, hop {hop}, {ch_total} ch x {length} samples (BASELINE configs[3]); " + shard_note,
+                         "mode": "exact (bit-identical to the reference)", "cpu_baseline": cpu_stft,
+                         "frames_per_s": ch * world * nframes / (ms * 1e-3), "ms": ms, "hbm_gbs_per_gpu": algo / ms / 1e6,
                          "frac_of_measured_peak": algo / ms / 1e6 / peak, "clocks": stft_clocks,
                          "fp32_floor_ms_at_measured_clock": fma_floor_ms[stft_clocks.get("sm_mhz") or 1965],
                          "fp32_floor_ms_at_max_clock": fma_floor_ms[1965],
                          "hbm_floor_ms": algo / peak / 1e6}
         S.stft_batch(fast, sig, w, hop, nframes, out=frames)
-        torch.cuda.synchronize()
+        barrier()
         e0.record()
         for _ in range(reps):
             S.stft_batch(fast, sig, w, hop, nframes, out=frames)
         e1.record()
-        torch.cuda.synchronize()
-        msf = e0.elapsed_time(e1) / reps
-        extra["stft_fast_mode"] = {"frames_per_s": ch * nframes / (msf * 1e-3), "ms": msf, "hbm_gbs": algo / msf / 1e6,
-                                   "frac_of_measured_peak": algo / msf / 1e6 / peak}
+        barrier()
+        msf = max_over_ranks(e0.elapsed_time(e1) / reps)
+        # parity of the FAST mode against EXACT (which is bit-identical to the oracle): whole frames of a channel subset
+        pc = min(ch, 4)
+        fe = S.stft_batch(fft, sig[:pc], w, hop, nframes)
+        ff = frames[:pc]
+        d2 = (torch.view_as_real(ff) - torch.view_as_real(fe)).double().pow(2).sum(dim=(2, 3))
+        r2 = torch.view_as_real(fe).double().pow(2).sum(dim=(2, 3))
+        stft_fast_parity = {"rel_l2_vs_exact": float(torch.sqrt(d2.sum() / r2.sum()).item()),
+                            "worst_frame_rel_l2_vs_exact": float(torch.sqrt((d2 / r2.clamp_min(1e-30)).max()).item()),
+                            "frames_compared": int(pc * nframes), "tolerance": 1e-5}
+        del fe, ff, d2, r2
+        extra["stft_fast_mode"] = {"mode": "fast (fused multiply-add butterflies; inside the north star's 1e-5 rel-L2)",
+                                   "frames_per_s": ch * world * nframes / (msf * 1e-3), "ms": msf, "hbm_gbs_per_gpu": algo / msf / 1e6,
+                                   "frac_of_measured_peak": algo / msf / 1e6 / peak, "parity": stft_fast_parity}
+        S.stft_batch(fft, sig, w, hop, nframes, out=frames)  # exact frames for the inverse
         out = torch.zeros((ch, length), device=dev)
         S.istft_batch(fft, frames, w, hop, out)
-        torch.cuda.synchronize()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
             S.istft_batch(fft, frames, w, hop, out)
         e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        extra["istft"] = {"frames_per_s": ch * nframes / (ms * 1e-3), "ms": ms, "hbm_gbs": algo / ms / 1e6,
-                          "frac_of_measured_peak": algo / ms / 1e6 / peak,
-                          "note": "one fused kernel (ifft + window + ordered overlap-add + normalisation)"}
-        fft.ctx.set_istft_fusion(False)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+        out.zero_()
         S.istft_batch(fft, frames, w, hop, out)
-        torch.cuda.synchronize()
+        inner = slice(win, length - win)
+        rt = float(((out[:, inner] - sig[:, inner]).double().norm() / sig[:, inner].double().norm()).item())
+        extra["istft"] = {"mode": "exact", "frames_per_s": ch * world * nframes / (ms * 1e-3), "ms": ms, "hbm_gbs_per_gpu": algo / ms / 1e6,
+                          "frac_of_measured_peak": algo / ms / 1e6 / peak, "roundtrip_rel_l2_vs_signal": rt,
+                          "note": "one fused kernel (ifft + window + ordered overlap-add + normalisation); " + shard_note}
+        exact_out = out[:min(ch, 4)].clone()
+        out.zero_()
+        S.istft_batch(fast, frames, w, hop, out)
+        barrier()
         e0.record()
         for _ in range(reps):
-            S.istft_batch(fft, frames, w, hop, out)
+            S.istft_batch(fast, frames, w, hop, out)
         e1.record()
-        torch.cuda.synchronize()
-        fft.ctx.set_istft_fusion(True)
-        ms2 = e0.elapsed_time(e1) / reps
-        extra["istft_two_kernel_path"] = {"frames_per_s": ch * nframes / (ms2 * 1e-3), "ms": ms2,
-                                          "frac_of_measured_peak": algo / ms2 / 1e6 / peak}
+        barrier()
+        msf = max_over_ranks(e0.elapsed_time(e1) / reps)
+        out.zero_()
+        S.istft_batch(fast, frames, w, hop, out)
+        pf = float(((out[:exact_out.shape[0]] - exact_out).double().norm() / exact_out.double().norm()).item())
+        extra["istft_fast_mode"] = {"mode": "fast", "frames_per_s": ch * world * nframes / (msf * 1e-3), "ms": msf,
+                                    "frac_of_measured_peak": algo / msf / 1e6 / peak,
+                                    "parity": {"rel_l2_vs_exact": pf, "tolerance": 1e-5}}
+        del exact_out
+        if world == 1:
+            fft.ctx.set_istft_fusion(False)
+            S.istft_batch(fft, frames, w, hop, out)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                S.istft_batch(fft, frames, w, hop, out)
+            e1.record()
+            torch.cuda.synchronize()
+            fft.ctx.set_istft_fusion(True)
+            ms2 = e0.elapsed_time(e1) / reps
+            extra["istft_two_kernel_path"] = {"frames_per_s": ch * nframes / (ms2 * 1e-3), "ms": ms2,
+                                              "frac_of_measured_peak": algo / ms2 / 1e6 / peak}
         del sig, frames, out
+        torch.cuda.empty_cache()
+        if rank == 0 and world == 1:
+            # STFT end to end: pinned host signal -> pinned host frames through kofft_cuda_stft_host_f32 (one copy in,
+            # one kernel, one copy out); a bounded sample of configs[3] (4 channels x 10 min: 0.46 GB in, 3.7 GB out)
+            ech = 4
+            hs = torch.empty((ech, length), dtype=torch.float32, pin_memory=True)
+            hs.uniform_(-1, 1)
+            hf = torch.empty((ech, nframes, win), dtype=torch.complex64, pin_memory=True)
+            hw = W.hann(win)
+            S.stft_batch(fft, hs.numpy(), hw, hop, nframes, out=hf.numpy())
+            t0 = time.perf_counter()
+            for _ in range(3):
+                S.stft_batch(fft, hs.numpy(), hw, hop, nframes, out=hf.numpy())
+            dte = (time.perf_counter() - t0) / 3
+            extra["stft_e2e"] = {"frames_per_s": ech * nframes / dte, "ms": dte * 1e3, "h2d_bytes": ech * length * 4,
+                                 "d2h_bytes": ech * nframes * win * 8,
+                                 "sample": f"{ech} of 64 channels x {length} samples, pinned host buffers",
+                                 "api": "kofft_cuda_stft_host_f32 (H2D signal, fused framing + window + FFT kernel, D2H frames)",
+                                 "pcie_gbs_d2h": ech * nframes * win * 8 / dte / 1e9}
+            del hs, hf
     except Exception as e:  # extras never invalidate the headline line
         extra["error"] = f"{type(e).__name__}: {e}"
 
@@ -456,6 +741,7 @@ def run_gpu(args) -> None:
     if world > 1 and (world & (world - 1)) == 0:
         try:
             from kofft_b200 import dist as KD
+            from kofft_b200 import dist_validate
 
             torch.cuda.empty_cache()
             log2n = 27 + int(math.log2(world))
@@ -463,20 +749,41 @@ def run_gpu(args) -> None:
             dfft.connect()
             shard = (1 << log2n) // world
             xs = torch.view_as_complex(torch.rand((shard, 2), generator=g, device=dev) * 2 - 1).contiguous()
-            os_ = torch.empty_like(xs)
-            walls = []
-            for it in range(5):
-                barrier()
-                t0 = time.perf_counter()
-                dfft.transform(xs, out=os_, natural_order=True)
-                if it >= 2:
-                    walls.append(time.perf_counter() - t0)
-            w = max_over_ranks(statistics.median(walls))
+
+            def timed(fn, iters=5, skip=2):
+                walls = []
+                for it in range(iters):
+                    barrier()
+                    t0 = time.perf_counter()
+                    fn()
+                    torch.cuda.synchronize()
+                    if it >= skip:
+                        walls.append(time.perf_counter() - t0)
+                return max_over_ranks(statistics.median(walls))
+
+            t_p2p = timed(lambda: dfft.transform(xs, natural_order=True))
+            t_p2p_t = timed(lambda: dfft.transform(xs, natural_order=False))
+            t_col = timed(lambda: dfft.transform_collective(xs))
+            same = torch.equal(torch.view_as_real(dfft.transform_collective(xs).clone()),
+                               torch.view_as_real(dfft.transform(xs, natural_order=True)))
+            link_bytes = shard * 8 * (world - 1) // world  # per GPU, per direction, per exchange
+            check = dist_validate.validate(dfft)           # closed forms + f64 direct sums at the full size
             extra["dist_c2c_one_transform"] = {
-                "log2n": log2n, "points_per_gpu": shard, "ms": w * 1e3, "gflops": 5.0 * (1 << log2n) * log2n / w / 1e9,
-                "note": "four-step split; all-to-all exchanges are P2P stores issued by the transpose-scatter kernels "
-                        "(CUDA IPC over NVLink), host barriers between phases; natural-order output (3 exchanges); "
-                        "validated against f64, no kofft reference at this size (SURVEY 0.5)"}
+                "log2n": log2n, "points_per_gpu": shard, "ms": t_p2p * 1e3,
+                "gflops": 5.0 * (1 << log2n) * log2n / t_p2p / 1e9,
+                "ms_transposed_order_output": t_p2p_t * 1e3,
+                "ms_nccl_all_to_all_arm": t_col * 1e3,
+                "p2p_store_speedup_over_nccl_arm": t_col / t_p2p,
+                "arms_bit_identical": bool(same),
+                "nvlink_bytes_per_gpu_per_exchange": link_bytes,
+                "nvlink_floor_ms_natural_order_at_770GBs": 3 * link_bytes / 770e9 * 1e3,
+                "validation": check,
+                "note": "four-step split, natural-order output (3 exchanges).  'ms': the exchanges are peer-to-peer stores issued by "
+                        "the transpose-scatter kernels (CUDA IPC over NVLink) overlapped with the local transforms; "
+                        "'ms_nccl_all_to_all_arm': the same phases with pack -> torch.distributed.all_to_all_single (ncclAlltoAll) "
+                        "-> unpack.  Validation at the FULL size: K tones (exact spikes), an impulse (phase ramp at every bin), "
+                        "uniform noise with 64 bins against f64 direct sums over all N points; no kofft reference exists at "
+                        "this size (SURVEY 0.5)"}
             dfft.close()
         except Exception as e:
             extra["dist_error"] = f"{type(e).__name__}: {e}"
@@ -484,16 +791,18 @@ def run_gpu(args) -> None:
     # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ------------------------
     cpu = None
     if rank == 0 and n_gpus == 1:
+        os.sched_setaffinity(0, orig_affinity)  # every host core, not just the GPU's NUMA node
         threads = os.cpu_count() or 1
-        rows = 8192
+        rows = ROWS_PER_GPU  # the whole step
         reps = 1
         gf, dt = cpu_port_gflops(rows, reps, threads)
         while dt < 10.0 and reps < 4096:  # aim at >= 10 s of CPU work in the timed sample
             reps *= 2
             gf, dt = cpu_port_gflops(rows, reps, threads)
         cpu = {"value": gf, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{rows} rows x {reps} reps of N={N} ({dt:.1f} s), {threads} threads over rows, one planner "
-                         "per thread; oracle/kofft_oracle.c (C restatement; the Rust crate cannot be built here)"}
+               "sample": f"all {rows} rows of the step x {reps} reps of N={N} ({dt:.1f} s), {threads} threads over rows, one planner "
+                         "per thread; oracle/kofft_oracle.c built -O3 with 128-bit vectors (bit-identical to the -O2 oracle; "
+                         "the Rust crate cannot be built here)"}
 
     if rank == 0:
         line = {

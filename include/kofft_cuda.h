@@ -306,6 +306,14 @@ int kofft_cuda_dist_connect_ipc(kofft_cuda_dist *d, const void *all_handles /* w
 int kofft_cuda_dist_connect_local(kofft_cuda_dist *const *dists, int world);
 int kofft_cuda_dist_phase(kofft_cuda_dist *d, int phase /* 0..3 */, const void *d_in, void *d_out, int inverse,
                           int natural_order, void *stream);
+/* The same transform with a LIBRARY collective for the exchanges (NCCL all-to-all): the baseline the P2P-store
+ * exchange above is measured against (bench.py reports both).  kofft_cuda_dist_pack transposes (step 1: and
+ * twiddles) the local matrix into a send buffer laid out by destination rank; the caller runs the all-to-all and
+ * copies block s of the receive buffer, [cb][rows], to columns [s*rows, (s+1)*rows) of the destination buffer
+ * [cb][world*rows] (buffer A after steps 0 and 2, buffer B after step 1); kofft_cuda_dist_local_fft runs the local
+ * transforms of buffer A (which = 0) / B (which = 1) in place.  kofft_b200/dist.py: DistFft.transform_collective. */
+int kofft_cuda_dist_pack(kofft_cuda_dist *d, int step /* 0..2 */, const void *d_src, void *d_send, int inverse, void *stream);
+int kofft_cuda_dist_local_fft(kofft_cuda_dist *d, int which /* 0: A, 1: B */, int inverse, void *stream);
 int kofft_cuda_dist_run_local(kofft_cuda_dist *const *dists, int world, const void *const *d_in,
                               void *const *d_out, int inverse, int natural_order);
 

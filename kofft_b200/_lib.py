@@ -95,6 +95,8 @@ SIGNATURES = {
     "kofft_cuda_dist_connect_ipc": (_i, [_vp, _vp]),
     "kofft_cuda_dist_connect_local": (_i, [C.POINTER(_vp), _i]),
     "kofft_cuda_dist_phase": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
+    "kofft_cuda_dist_pack": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
+    "kofft_cuda_dist_local_fft": (_i, [_vp, _i, _i, _vp]),
     "kofft_cuda_dist_run_local": (_i, [C.POINTER(_vp), _i, C.POINTER(_vp), C.POINTER(_vp), _i, _i]),
     "kofft_cuda_istft_host_f32": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _vp, _sz, _i]),
 }

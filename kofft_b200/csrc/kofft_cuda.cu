@@ -2342,6 +2342,50 @@ int kofft_cuda_dist_phase(kofft_cuda_dist *d, int phase, const void *d_in, void 
     }
 }
 
+// ---- the library-collective arm of the same transform (the baseline the P2P-store exchange is measured against):
+// every exchange becomes  pack (local transpose [+ twiddle] into a send buffer laid out by destination)
+// -> all-to-all by the CALLER (ncclAlltoAll / torch.distributed.all_to_all_single) -> unpack by the caller:
+// what rank s sent to rank d arrives as a dense block [cb][rows_s]; the destination buffer is [cb][world][rows].
+// step 0: d_src = this rank's input slice x [R1][N2]            (no twiddle)   blocks [C2][R1]
+// step 1: d_src = buffer A [C2][N1] after its N1-point transforms (W_N^{n2 k1}) blocks [R1][C2]
+// step 2: d_src = buffer B [R1][N2] after its N2-point transforms (no twiddle)  blocks [C2][R1]
+int kofft_cuda_dist_pack(kofft_cuda_dist *d, int step, const void *d_src, void *d_send, int inverse, void *stream)
+{
+    CU(cudaSetDevice(d->ctx->device));
+    if (step < 0 || step > 2) return fail_msg(KOFFT_ERR_INVALID_VALUE, "dist_pack: step 0..2");
+    const size_t rows = step == 1 ? d->c2 : d->r1, cb = step == 1 ? d->r1 : d->c2;
+    ScatterArgs a;
+    a.src = static_cast<const float2 *>(d_src);
+    for (int g = 0; g < d->world; g++) a.dst[g] = static_cast<float2 *>(d_send) + static_cast<size_t>(g) * rows * cb;
+    a.rows = static_cast<long>(rows);
+    a.cb = static_cast<long>(cb);
+    a.world = d->world;
+    a.rank = d->rank;
+    a.dst_pitch = static_cast<long>(rows);
+    a.dst_off = 0;
+    a.twiddle = step == 1 ? (inverse ? 2 : 1) : 0;
+    a.row0 = static_cast<long>(rows) * d->rank;
+    a.log2n = d->log2n;
+    a.llo = d->llo;
+    a.tlo = d->tlo;
+    a.thi = d->thi;
+    (void)cudaGetLastError();
+    cudaError_t e = launch_transpose_scatter(a, d->ctx->num_sms, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "dist_pack launch");
+    d->ctx->launches++;
+    return KOFFT_OK;
+}
+
+// the local transforms of a phase on their own: which = 0: the C2 rows of buffer A (N1 points each), 1: the R1 rows
+// of buffer B (N2 points each); in place, correctly rounded tables (as kofft_cuda_dist_phase uses)
+int kofft_cuda_dist_local_fft(kofft_cuda_dist *d, int which, int inverse, void *stream)
+{
+    CU(cudaSetDevice(d->ctx->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (which == 0) return dist_local_fft(d, d->bufA, d->bufA, d->n1, d->c2, inverse, s);
+    return dist_local_fft(d, d->bufB, d->bufB, d->n2, d->r1, inverse, s);
+}
+
 int kofft_cuda_dist_run_local(kofft_cuda_dist *const *dists, int world, const void *const *d_in, void *const *d_out,
                               int inverse, int natural_order)
 {

@@ -111,6 +111,54 @@ class DistFft:
         return self.result_view() if zero_copy else out
 
 
+def _buffer_view(d: DistFft, which: int):
+    ptr = int(_lib.lib().kofft_cuda_dist_buffer(d.handle, which))
+
+    class _Raw:
+        __cuda_array_interface__ = {"shape": (d.shard_len, 2), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+    return torch.view_as_complex(torch.as_tensor(_Raw(), device=f"cuda:{d.ctx.device}"))
+
+
+def _transform_collective(self, x, inverse: bool = False, group=None):
+    """The same four-step transform with `torch.distributed.all_to_all_single` (ncclAlltoAll) for the three
+    exchanges instead of the kernels' peer-to-peer stores: pack -> all-to-all -> unpack per exchange (two extra
+    passes over the shard each).  Natural-order result, returned as a view of buffer A.  This is the baseline arm
+    bench.py times beside `transform`; both give bit-identical results."""
+    import torch.distributed as dist
+
+    lib = _lib.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    world, r1, c2 = self.world, self.n1 // self.world, self.n2 // self.world
+    if not hasattr(self, "_send"):
+        self._send = torch.empty(self.shard_len, dtype=torch.complex64, device=x.device)
+        self._recv = torch.empty(self.shard_len, dtype=torch.complex64, device=x.device)
+    send, recv = self._send, self._recv
+    bufs = [_buffer_view(self, 0), _buffer_view(self, 1)]
+
+    def exchange(step, src, dst):
+        rows, cb = (c2, r1) if step == 1 else (r1, c2)
+        check(lib.kofft_cuda_dist_pack(self.handle, step, C.c_void_p(src.data_ptr()), C.c_void_p(send.data_ptr()),
+                                       int(inverse), C.c_void_p(s)))
+        if world > 1:
+            dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=group)
+            got = recv
+        else:
+            got = send
+        # block s = [cb][rows] from rank s -> columns [s*rows, (s+1)*rows) of the destination [cb][world*rows]
+        dst.view(cb, world, rows).copy_(got.view(world, cb, rows).permute(1, 0, 2))
+
+    exchange(0, x, bufs[0])
+    check(lib.kofft_cuda_dist_local_fft(self.handle, 0, int(inverse), C.c_void_p(s)))
+    exchange(1, bufs[0], bufs[1])
+    check(lib.kofft_cuda_dist_local_fft(self.handle, 1, int(inverse), C.c_void_p(s)))
+    exchange(2, bufs[1], bufs[0])
+    return bufs[0]
+
+
+DistFft.transform_collective = _transform_collective
+
+
 def run_local(dists: Sequence[DistFft], xs, outs, inverse: bool = False, natural_order: bool = True) -> None:
     """All ranks driven from this process (devices may repeat): phases with device-synchronising barriers."""
     world = len(dists)

@@ -9,7 +9,7 @@ echo "== smoke" | tee -a $OUT/summary.txt
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke exit $?" | tee -a $OUT/summary.txt
 tail -3 $OUT/smoke.log | tee -a $OUT/summary.txt
 echo "== pytest -m gpu" | tee -a $OUT/summary.txt
-timeout 1500 python -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a $OUT/summary.txt
+timeout 2400 python -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a $OUT/summary.txt
 tail -40 $OUT/pytest_gpu.log | tee -a $OUT/summary.txt
 echo "== bench" | tee -a $OUT/summary.txt
 KOFFT_CUDA_VERBOSE=1 timeout 900 python bench.py --steps 50 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?" | tee -a $OUT/summary.txt
@@ -28,10 +28,10 @@ ls -la $OUT | tee -a $OUT/summary.txt
 echo "== ncu stft / rfft" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_cta_kernel -s 3 -c 1 -o $OUT/prof_stft \
     python scripts/one_kernel.py stft > $OUT/ncu_stft.log 2>&1; echo "ncu stft exit $?" | tee -a $OUT/summary.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:split32 -s 3 -c 1 -o $OUT/prof_rfft_split \
+    python scripts/one_kernel.py split > $OUT/ncu_rfft_split.log 2>&1; echo "ncu rfft (split kernel, default) exit $?" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:large_pipe -s 2 -c 1 -o $OUT/prof_rfft_pipe \
-    python scripts/one_kernel.py rfft > $OUT/ncu_rfft_pipe.log 2>&1; echo "ncu rfft (pipelined, default) exit $?" | tee -a $OUT/summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:rowpass -s 4 -c 1 -o $OUT/prof_rfft_row \
-    python scripts/one_kernel.py rfft2 > $OUT/ncu_rfft_row.log 2>&1; echo "ncu rfft row exit $?" | tee -a $OUT/summary.txt
+    python scripts/one_kernel.py rfft > $OUT/ncu_rfft_pipe.log 2>&1; echo "ncu rfft (pipelined) exit $?" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:istft_fused -s 2 -c 1 -o $OUT/prof_istft \
     python scripts/one_kernel.py istft > $OUT/ncu_istft.log 2>&1; echo "ncu istft exit $?" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_f64_kernel -s 2 -c 1 -o $OUT/prof_f64 \
@@ -44,10 +44,10 @@ cat $OUT/kernels.jsonl | tee -a $OUT/summary.txt
 echo "== summaries" | tee -a $OUT/summary.txt
 mkdir -p $OUT/profiles
 python scripts/summarize_ncu.py $TAG prof_c2c c2c --headline >> $OUT/summary.txt 2>&1
-for pair in "prof_stft stft" "prof_rfft_pipe rfft_pipe" "prof_rfft_row rfft_rowpass" "prof_istft istft" "prof_f64 f64"; do
+for pair in "prof_stft stft" "prof_rfft_split rfft_split" "prof_rfft_pipe rfft_pipe" "prof_istft istft" "prof_f64 f64"; do
     set -- $pair
     [ -f $OUT/$1.ncu-rep ] && python scripts/summarize_ncu.py $TAG $1 $2 >> $OUT/summary.txt 2>&1
 done
 cp profiles/${TAG}_* profiles/headline_kernel_traffic.json $OUT/profiles/ 2>/dev/null
-for r in prof_stft prof_rfft_pipe prof_rfft_row prof_istft prof_f64; do rm -f $OUT/$r.ncu-rep; done
+for r in prof_stft prof_rfft_split prof_rfft_pipe prof_istft prof_f64; do rm -f $OUT/$r.ncu-rep; done
 du -sh $OUT | tee -a $OUT/summary.txt

@@ -89,7 +89,11 @@ def kernel(tag, rep, name, headline):
         d = res[-1]
         gb = lambda k: d[k]["value"] * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[d[k]["unit"]]
         traffic = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
-        json.dump({"kernel": d["kernel"], "dram_bytes_per_launch": traffic, "source": os.path.basename(out)},
+        sys.path.insert(0, ROOT)
+        import bench  # the same hash bench.py recomputes at run time: a capture of other SASS is refused as stale
+
+        json.dump({"kernel": d["kernel"], "dram_bytes_per_launch": traffic, "source": os.path.basename(out),
+                   "sass_sha256": bench.headline_sass_hash()},
                   open(os.path.join(ROOT, "profiles", "headline_kernel_traffic.json"), "w"), indent=1)
 
 

@@ -27,11 +27,23 @@ want = np.fft.fft(x.astype(np.complex128))[rank * shard:(rank + 1) * shard]
 err = float(np.linalg.norm(out.cpu().numpy() - want) / np.linalg.norm(want))
 back = d.transform(out, inverse=True)
 err2 = float(np.linalg.norm(back.cpu().numpy() - x[rank * shard:(rank + 1) * shard]) / np.linalg.norm(x[:shard]))
-errs = torch.tensor([err, err2], device="cuda")
+# the library-collective arm (NCCL all-to-all instead of the kernels' peer stores) must give the same bits
+col = d.transform_collective(xs).clone()
+p2p = d.transform(xs)
+same = float(torch.equal(torch.view_as_real(col), torch.view_as_real(p2p)))
+# closed-form / direct-sum validation on the GPUs, the routine bench.py runs at 2^30
+from kofft_b200 import dist_validate  # noqa: E402
+
+v = dist_validate.validate(d, chunk=1 << 20, nbins=16)
+vc = dist_validate.validate(d, transform=lambda t: d.transform_collective(t), chunk=1 << 20, nbins=8)
+errs = torch.tensor([err, err2, 1.0 - same, v["rel_err_tones"], v["rel_err_impulse"], v["max_bin_err"],
+                     vc["rel_err_tones"], vc["rel_err_impulse"], vc["max_bin_err"]], device="cuda")
 dist.all_reduce(errs, op=dist.ReduceOp.MAX)
 d.close()
 dist.barrier()
 if rank == 0:
     assert errs[0].item() < 2e-6 and errs[1].item() < 2e-6, errs
+    assert errs[2].item() == 0.0, "collective arm differs from the peer-store arm"
+    assert errs[3:].max().item() < 5e-6, errs
     print(f"dist_worker ok world={world} log2n={log2n} rel_l2={errs[0].item():.2e} roundtrip={errs[1].item():.2e}")
 dist.destroy_process_group()
