@@ -8,8 +8,11 @@
 //! because the blanket impl cannot be specialised.
 //!
 //! FFI: `include/kofft_cuda.h` (C ABI of libkofft_cuda).  Return codes 1..=6 are the
-//! `FftError` variants in declaration order; a negative code is a CUDA failure, for which kofft
-//! has no variant, so it panics with the backend's message.
+//! `FftError` variants in declaration order.  A negative code is a CUDA failure, for which kofft
+//! has no variant: the shim panics with the backend's message -- except for "not supported"
+//! (lengths beyond the single-GPU range of 2^27, f64 lengths the f64 kernels do not cover), which is
+//! an ordinary property of the input and comes back as `FftError::InvalidValue`.  There is no CPU
+//! fallback of any kind.
 #![allow(clippy::missing_safety_doc)]
 
 use core::ffi::{c_char, c_int, c_void};
@@ -79,6 +82,9 @@ extern "C" {
                                nframes: usize, stream: *mut c_void) -> c_int;
 }
 
+/// -(cudaErrorNotSupported): the backend has no kernel for this length (see include/kofft_cuda.h, "Lengths")
+const NOT_SUPPORTED: c_int = -801;
+
 fn check(rc: c_int) -> Result<(), FftError> {
     match rc {
         0 => Ok(()),
@@ -88,6 +94,7 @@ fn check(rc: c_int) -> Result<(), FftError> {
         4 => Err(FftError::InvalidStride),
         5 => Err(FftError::InvalidHopSize),
         6 => Err(FftError::InvalidValue),
+        NOT_SUPPORTED => Err(FftError::InvalidValue),
         _ => {
             // kofft's FftError has no variant for a backend failure
             let msg = unsafe { std::ffi::CStr::from_ptr(kofft_cuda_last_error()) };

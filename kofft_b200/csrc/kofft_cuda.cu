@@ -552,6 +552,7 @@ void *kofft_cuda_stream(const kofft_cuda_ctx *ctx) { return ctx ? ctx->stream : 
 
 int kofft_cuda_synchronize(kofft_cuda_ctx *ctx)
 {
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     return KOFFT_OK;
@@ -629,6 +630,7 @@ int kofft_cuda_rfft_twiddles_host_f32(size_t m, float *out, int fma_mul)
 }
 int kofft_cuda_get_twiddles(kofft_cuda_ctx *ctx, size_t n, const void **dev_ptr)
 {
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     const Table *t = nullptr;
     int rc = get_fft_table(ctx, n, &t);
@@ -638,6 +640,7 @@ int kofft_cuda_get_twiddles(kofft_cuda_ctx *ctx, size_t n, const void **dev_ptr)
 }
 int kofft_cuda_get_rfft_twiddles(kofft_cuda_ctx *ctx, size_t m, const void **dev_ptr)
 {
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     const Table *t = nullptr;
     int rc = get_rfft_table(ctx, m, &t);
@@ -660,11 +663,13 @@ int kofft_cuda_fft_c2c_f32(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, s
 {
     if (n != 0 && !is_pow2(n)) { // the reference's std build takes Bluestein here (src/fft.rs:1083-1132)
         if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
-        CU(cudaSetDevice(ctx->device));
+        if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
+    CU(cudaSetDevice(ctx->device));
         return bluestein_c2c(ctx, d_in, d_out, n, batch, inverse, pick_stream(ctx, stream));
     }
     int rc = check_fft_len(n);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     if (n == 1) { // fft of one point is the identity (src/fft.rs:1059-1061)
@@ -753,6 +758,7 @@ int kofft_cuda_fft_strided_f32(kofft_cuda_ctx *ctx, const void *d_in, size_t in_
     if (in_stride == 0 || out_stride == 0) return KOFFT_ERR_INVALID_STRIDE;
     int rc = check_fft_len(n);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     if (!is_pow2(n)) { // gather, fft (Bluestein), scatter: src/fft.rs:1191-1197
         cudaStream_t s = pick_stream(ctx, stream);
@@ -832,6 +838,7 @@ int kofft_cuda_fft2d_host_f32(kofft_cuda_ctx *ctx, float *data, size_t data_len,
     if (rows * cols != data_len) return KOFFT_ERR_MISMATCHED_LENGTHS; // src/ndfft.rs:85-87
     if (rows == 0 || cols == 0) return KOFFT_OK;
     if (scratch_col_len != rows) return KOFFT_ERR_MISMATCHED_LENGTHS;  // :91-93
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     void *d = nullptr;
     int rc = host_roundtrip_begin(ctx, data, data_len * sizeof(float2), 0, &d);
@@ -849,6 +856,7 @@ int kofft_cuda_fft3d_host_f32(kofft_cuda_ctx *ctx, float *data, size_t data_len,
     if (depth * rows * cols != data_len) return KOFFT_ERR_MISMATCHED_LENGTHS; // src/ndfft.rs:125-127
     if (depth == 0 || rows == 0 || cols == 0) return KOFFT_OK;
     if (tube_len != depth || row_len != rows || col_len != cols) return KOFFT_ERR_MISMATCHED_LENGTHS; // :131-133
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     void *d = nullptr;
     int rc = host_roundtrip_begin(ctx, data, data_len * sizeof(float2), 0, &d);
@@ -865,6 +873,7 @@ int kofft_cuda_fft_split_f32(kofft_cuda_ctx *ctx, const float *d_in_re, const fl
 {
     int rc = check_fft_len(n);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     if (!is_pow2(n)) { // AoS copy, fft (Bluestein), copy back: src/fft.rs:797-809
         cudaStream_t s = pick_stream(ctx, stream);
@@ -916,6 +925,7 @@ int kofft_cuda_rfft_f32(kofft_cuda_ctx *ctx, const float *d_in, void *d_out, siz
     const size_t m = n / 2;
     int rc = check_fft_len(m);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     const Table *t = nullptr;
     rc = get_rfft_table(ctx, m, &t);
@@ -958,6 +968,7 @@ int kofft_cuda_irfft_f32(kofft_cuda_ctx *ctx, const void *d_in, float *d_out, si
     const size_t m = n / 2;
     int rc = check_fft_len(m);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     const Table *t = nullptr;
     rc = get_rfft_table(ctx, m, &t);
@@ -993,6 +1004,7 @@ int kofft_cuda_stft_f32(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, 
     if (nframes == 0 || channels == 0) return KOFFT_OK;
     int rc = check_fft_len(win_len);                          // first fft.fft(frame) :102
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     if (!is_pow2(win_len) || win_len > 16384) { // framing kernel, then the C2C core (Bluestein / large-N) in place on the frames
         cudaStream_t s = pick_stream(ctx, stream);
@@ -1031,6 +1043,7 @@ int kofft_cuda_stft_magnitudes_f32(kofft_cuda_ctx *ctx, const float *d_signal, s
     if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE;             // src/stft.rs:83-85 via compute_stft
     if (nframes < (len + hop - 1) / hop) return KOFFT_ERR_MISMATCHED_LENGTHS;
     if (channels == 0) return KOFFT_OK;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     CU(cudaMemsetAsync(d_max, 0, channels * sizeof(float), s)); // max_mag starts at 0.0 (spectrogram.rs:64)
@@ -1067,6 +1080,7 @@ int kofft_cuda_stft_magnitudes_host_f32(kofft_cuda_ctx *ctx, const float *sample
     if (nframes < (len + hop - 1) / hop) return KOFFT_ERR_MISMATCHED_LENGTHS;
     int rc = nframes ? check_pow2_len(win_len) : KOFFT_OK;
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     std::vector<float> w(win_len ? win_len : 1);
     host_window(KOFFT_WINDOW_HANN, win_len, 0.0f, w.data()); // stft_magnitudes always uses hann (spectrogram.rs:57)
@@ -1100,6 +1114,7 @@ int kofft_cuda_istft_f32(kofft_cuda_ctx *ctx, const void *d_frames, size_t nfram
         int rc = check_fft_len(win_len); // fft.ifft(frame) :141
         if (rc) return rc;
     }
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     const int Lw = log2_of(win_len);
@@ -1309,6 +1324,7 @@ int kofft_cuda_fft_batch_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, si
     int rc = n == 0 ? KOFFT_ERR_EMPTY_INPUT : KOFFT_OK; // non-power-of-two lengths take Bluestein in fft_c2c
     if (rc) return rc;
     if (n == 1 || batch == 0) return KOFFT_OK;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     const size_t bytes = n * batch * sizeof(float2);
     if (use_host_pipeline(ctx, bytes))
@@ -1388,6 +1404,7 @@ int kofft_cuda_stft_stream_create(kofft_cuda_ctx *ctx, size_t channels, const fl
     int rc = check_pow2_len(win_len);
     if (rc) return rc;
     if (channels == 0) return fail_msg(KOFFT_ERR_INVALID_VALUE, "channels == 0");
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     auto *s = new kofft_cuda_stft_stream;
     s->ctx = ctx;
@@ -1424,6 +1441,7 @@ int kofft_cuda_stft_stream_push(kofft_cuda_stft_stream *s, const float *d_sample
 {
     if (!s) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null stream");
     kofft_cuda_ctx *ctx = s->ctx;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = pick_stream(ctx, stream);
     if (n && ld < n) return KOFFT_ERR_MISMATCHED_LENGTHS;
@@ -1479,6 +1497,7 @@ int kofft_cuda_istft_stream_create(kofft_cuda_ctx *ctx, size_t channels, const f
     int rc = check_pow2_len(win_len);
     if (rc) return rc;
     if (channels == 0) return fail_msg(KOFFT_ERR_INVALID_VALUE, "channels == 0");
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     auto *s = new kofft_cuda_istft_stream;
     s->ctx = ctx;
@@ -1511,6 +1530,7 @@ int kofft_cuda_istft_stream_push(kofft_cuda_istft_stream *s, const void *d_frame
 {
     if (!s) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null stream");
     kofft_cuda_ctx *ctx = s->ctx;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = pick_stream(ctx, stream);
     const size_t w2 = s->win_len * 2; // floats per frame
@@ -1617,6 +1637,7 @@ int kofft_cuda_fft_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, s
 {
     int rc = f64_check_len(ctx, n);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     if (n == 1) { // identity for fft; ifft: conj, conj, * (1/1) (src/fft.rs:1139-1141 returns early)
@@ -1641,6 +1662,7 @@ int kofft_cuda_fft_strided_f64(kofft_cuda_ctx *ctx, const void *d_in, size_t in_
     if (in_stride == 0 || out_stride == 0) return KOFFT_ERR_INVALID_STRIDE;
     int rc = f64_check_len(ctx, n);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     LaunchF64Args a;
     a.generic = true;
@@ -1661,6 +1683,7 @@ int kofft_cuda_fft_split_f64(kofft_cuda_ctx *ctx, const double *d_in_re, const d
 {
     int rc = f64_check_len(ctx, n);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     LaunchF64Args a;
     a.generic = true;
@@ -1702,6 +1725,7 @@ int real_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_
     const size_t m = n / 2;
     int rc = f64_check_len(ctx, m);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     LaunchF64Args a;
     a.real = which;
@@ -1732,6 +1756,7 @@ int kofft_cuda_rfft_batch_host_f64(kofft_cuda_ctx *ctx, const double *input, siz
     int rc = f64_check_len(ctx, n / 2);
     if (rc) return rc;
     if (batch == 0) return KOFFT_OK;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     const size_t ibytes = batch * n * sizeof(double), obytes = batch * (n / 2 + 1) * sizeof(double2);
     void *din = nullptr, *dout = nullptr;
@@ -1753,6 +1778,7 @@ int kofft_cuda_irfft_batch_host_f64(kofft_cuda_ctx *ctx, const double *input, si
     int rc = f64_check_len(ctx, n / 2);
     if (rc) return rc;
     if (batch == 0) return KOFFT_OK;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     const size_t ibytes = batch * (n / 2 + 1) * sizeof(double2), obytes = batch * n * sizeof(double);
     void *din = nullptr, *dout = nullptr;
@@ -1771,6 +1797,7 @@ int kofft_cuda_fft_batch_host_f64(kofft_cuda_ctx *ctx, double *data, size_t n, s
 {
     if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
     if (n == 1 || batch == 0) return KOFFT_OK;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     const size_t bytes = n * batch * sizeof(double2);
@@ -1796,6 +1823,7 @@ int kofft_cuda_fft_split_host_f64(kofft_cuda_ctx *ctx, double *re, size_t re_len
     int rc = f64_check_len(ctx, n);
     if (rc) return rc;
     if (n == 1) return KOFFT_OK; // identity; ifft_split: (negate, negate, * 1/1)
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     void *d = nullptr;
     rc = ensure_ws(ctx, 0, 2 * n * sizeof(double), &d);
@@ -1820,6 +1848,7 @@ int kofft_cuda_fft_strided_host_f64(kofft_cuda_ctx *ctx, double *input, size_t i
     int rc = f64_check_len(ctx, n);
     if (rc) return rc;
     if (n == 1) return KOFFT_OK;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     const size_t span = (n - 1) * stride + 1;
     void *d = nullptr;
@@ -1842,6 +1871,7 @@ int kofft_cuda_fft_out_of_place_strided_host_f64(kofft_cuda_ctx *ctx, const doub
     if (output_len / out_stride != n) return KOFFT_ERR_MISMATCHED_LENGTHS;    // :1274-1276
     int rc = f64_check_len(ctx, n);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     void *din = nullptr, *dout = nullptr;
     rc = host_roundtrip_begin(ctx, input, input_len * sizeof(double2), 0, &din);
@@ -1867,6 +1897,7 @@ int kofft_cuda_fft_split_host_f32(kofft_cuda_ctx *ctx, float *re, size_t re_len,
     const size_t n = re_len;
     int rc = check_fft_len(n);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     void *d = nullptr;
     rc = ensure_ws(ctx, 0, 2 * n * sizeof(float), &d);
@@ -1893,6 +1924,7 @@ int kofft_cuda_fft_strided_host_f32(kofft_cuda_ctx *ctx, float *input, size_t in
     int rc = check_fft_len(n);
     if (rc) return rc;
     if (n == 1) return KOFFT_OK;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     const size_t span = (n - 1) * stride + 1;
     void *d = nullptr;
@@ -1915,6 +1947,7 @@ int kofft_cuda_fft_out_of_place_strided_host_f32(kofft_cuda_ctx *ctx, const floa
     if (output_len / out_stride != n) return KOFFT_ERR_MISMATCHED_LENGTHS;    // :1274-1276
     int rc = check_fft_len(n);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     void *din = nullptr, *dout = nullptr;
     rc = host_roundtrip_begin(ctx, input, input_len * sizeof(float2), 0, &din);
@@ -1939,6 +1972,7 @@ int kofft_cuda_rfft_batch_host_f32(kofft_cuda_ctx *ctx, const float *input, size
     int rc = check_fft_len(m);
     if (rc) return rc;
     if (batch == 0) return KOFFT_OK;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     if (use_host_pipeline(ctx, (m + 1) * batch * sizeof(float2)))
         return host_pipeline(ctx, input, n * sizeof(float), output, (m + 1) * sizeof(float2), batch, false,
@@ -1974,6 +2008,7 @@ int kofft_cuda_irfft_batch_host_f32(kofft_cuda_ctx *ctx, const float *input, siz
     int rc = check_fft_len(m);
     if (rc) return rc;
     if (batch == 0) return KOFFT_OK;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     if (use_host_pipeline(ctx, (m + 1) * batch * sizeof(float2)))
         return host_pipeline(ctx, input, (m + 1) * sizeof(float2), output, n * sizeof(float), batch, false,
@@ -2009,6 +2044,7 @@ int kofft_cuda_stft_host_f32(kofft_cuda_ctx *ctx, const float *signal, size_t le
     if (nframes == 0 || channels == 0) return KOFFT_OK;
     int rc = check_fft_len(win_len);
     if (rc) return rc;
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     void *dsig = nullptr, *dfr = nullptr, *dwin = nullptr;
     rc = host_roundtrip_begin(ctx, signal, len * channels * sizeof(float), 0, &dsig);
@@ -2038,6 +2074,7 @@ int kofft_cuda_istft_host_f32(kofft_cuda_ctx *ctx, const float *frames, size_t n
         int rc = check_fft_len(win_len);
         if (rc) return rc;
     }
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     void *dfr = nullptr, *dwin = nullptr, *dout = nullptr;
     int rc = host_roundtrip_begin(ctx, frames, channels * nframes * win_len * sizeof(float2), 0, &dfr);
@@ -2181,6 +2218,7 @@ int kofft_cuda_dist_create(kofft_cuda_ctx *ctx, int rank, int world, int log2n, 
     const int lw = log2_of(static_cast<size_t>(world));
     if (l2 > 16 || l1 - lw < 5)
         return fail_msg(KOFFT_ERR_INVALID_VALUE, "log2n must satisfy 10 + 2 log2(world) <= log2n <= 32");
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     kofft_cuda_dist *d = new kofft_cuda_dist();
     d->ctx = ctx;

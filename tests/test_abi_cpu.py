@@ -87,7 +87,8 @@ def test_argument_validation_precedes_device_work(lib):
     is touched (ctx = NULL here), in the reference's order."""
     z = None
     assert lib.kofft_cuda_fft_c2c_f32(z, z, z, 0, 1, 0, z) == 1        # EmptyInput
-    assert lib.kofft_cuda_rfft_f32(z, z, z, 24, 1, z) == 2             # NonPowerOfTwoNoStd (rfft core m = 12)
+    assert lib.kofft_cuda_rfft_f32(z, z, z, 24, 1, z) == 6             # m = 12 is fine (Bluestein, as the std build): fails on the NULL context only
+    assert lib.kofft_cuda_stft_stream_create(z, 1, z, 12, 4, z) == 6   # null arguments
     assert lib.kofft_cuda_fft_strided_f32(z, z, 0, 8, z, 1, 8, 8, 1, 0, z) == 4  # InvalidStride
     assert lib.kofft_cuda_rfft_f32(z, z, z, 0, 1, z) == 1
     assert lib.kofft_cuda_rfft_f32(z, z, z, 7, 1, z) == 6              # InvalidValue (odd)

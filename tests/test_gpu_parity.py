@@ -62,8 +62,13 @@ def test_fft_empty_single_nonpow2(cuda_fft):  # src/lib.rs:313-318, 342-349
     d = c32(1, 2, 3)  # non-power-of-two: Bluestein, like the reference's std build (src/fft.rs:1083-1132)
     cuda_fft.fft(d)
     assert np.allclose(d, np.fft.fft([1, 2, 3]), atol=1e-5)
-    with pytest.raises(k.NonPowerOfTwoNoStd):  # the rfft / stft cores stay power-of-two only
-        cuda_fft.rfft_batch(np.zeros((1, 24), np.float32))
+    # the rfft / stft cores reach Bluestein too (they call fft.fft(): src/rfft.rs:447, src/stft.rs:102); only the
+    # device-resident streams, built on the power-of-two kernels, refuse
+    assert cuda_fft.rfft_batch(np.ones((1, 24), np.float32)).shape == (1, 13)
+    from kofft_b200 import stft as S
+
+    with pytest.raises(k.NonPowerOfTwoNoStd):
+        S.DeviceStftStream(cuda_fft, 1, np.ones(12, np.float32), 4)
 
 
 def test_fft_out_of_place(cuda_fft, oracle):  # src/lib.rs:281-311, 320-329

@@ -318,3 +318,19 @@ def test_f64_rfft_roundtrip_dispatch(oracle):
         assert np.abs(oracle.irfft_batch_f64(y, n) - x).max() < 1e-11
     t = oracle.rfft_twiddles_f64(8)
     assert t[0] == 1.0 and abs(t[1] - np.exp(-1j * np.pi / 8)) < 1e-15  # tests/rfft_twiddles.rs for f64
+
+
+def test_timing_build_of_the_port_is_bit_identical(oracle):
+    """bench.py's CPU legs time the -O3 / 128-bit-vector build of the same sources (oracle/Makefile; the reference's
+    hot loop is explicit 4-wide SSE, src/fft.rs:845-862).  Vectorising must not change a bit."""
+    rng = np.random.default_rng(99)
+    for n in (64, 1024, 4096, 32768):
+        x = (rng.uniform(-1, 1, (6, n)) + 1j * rng.uniform(-1, 1, (6, n))).astype(np.complex64)
+        a, b = x.copy(), x.copy()
+        oracle.fft_batch_inplace(a, nthreads=2)
+        oracle.fft_batch_inplace(b, nthreads=2, fast=True)
+        assert np.array_equal(a, b), n
+    sig = rng.uniform(-1, 1, (2, 30000)).astype(np.float32)
+    w = oracle.hann(2048)
+    nf = -(-30000 // 512)
+    assert np.array_equal(oracle.stft_batch(sig, w, 512, nf), oracle.stft_batch(sig, w, 512, nf, fast=True))
