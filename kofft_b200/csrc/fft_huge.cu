@@ -211,7 +211,104 @@ cudaError_t launch_kind(const LaunchArgs &a, HugeArgs &g, int L)
     }
 }
 
+// ---- f64 twin above 8192 points (ScalarFftImpl<f64>, src/fft.rs:914-1051): every stage range is a register pass
+// through global memory (there is no f64 column pass); dense rows only.  First pass: conj on load for the inverse;
+// last pass: conj * (1/n) on store (src/fft.rs:1163-1172).
+template <int R, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(kPassThreads)
+    huge_pass_f64_kernel(const double2 *__restrict__ table, const double2 *__restrict__ src, double2 *__restrict__ dst, int L,
+                         int s, long rows, int inverse, double scale)
+{
+    constexpr int RAD = 1 << R;
+    const int lj = L - s - R;
+    const long per = 1L << (L - R);
+    const long total = rows * per;
+    const long n = 1L << L;
+    for (long g = blockIdx.x * (long)kPassThreads + threadIdx.x; g < total; g += (long)gridDim.x * kPassThreads) {
+        const long b = g >> (L - R);
+        const long bf = g & (per - 1);
+        const long k = bf >> lj, j = bf & ((1L << lj) - 1);
+        const double2 *in = src + b * n + (k << (L - s)) + j;
+        double2 x[RAD];
+#pragma unroll
+        for (int q = 0; q < RAD; q++) {
+            x[q] = in[(long)q << lj];
+            if (FIRST && inverse) x[q].y = -x[q].y;
+        }
+#pragma unroll
+        for (int tl = 0; tl < R; tl++) {
+            const int bit = 1 << (R - 1 - tl);
+#pragma unroll
+            for (int w0 = 0; w0 < RAD; w0++) {
+                if (w0 & bit) continue;
+                const int c_low = bitrev(w0 >> (R - tl), tl);
+                butterfly_f64(x[w0], x[w0 | bit], __ldg(table + ((k + ((long)c_low << s)) << (L - 1 - s - tl))));
+            }
+        }
+        double2 *o = dst + b * n + (k << lj) + j;
+#pragma unroll
+        for (int w = 0; w < RAD; w++) {
+            double2 v = x[w];
+            if (LAST && inverse) {
+                v.y = -v.y;
+                v.x = dmul(v.x, scale);
+                v.y = dmul(v.y, scale);
+            }
+            o[(long)bitrev(w, R) << (s + lj)] = v;
+        }
+    }
+}
+
+template <int R>
+cudaError_t launch_pass_f64(bool first, bool last, const LaunchF64Args &a, const double2 *src, double2 *dst, int L, int s)
+{
+    const long total = a.rows << (L - R);
+    long blocks = (total + kPassThreads - 1) / kPassThreads;
+    const long cap = (long)a.num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    const unsigned gb = (unsigned)blocks;
+    const int inv = a.inverse ? 1 : 0;
+    if (first && last)
+        return cudaErrorNotSupported; // L >= 14 always takes several passes
+    if (first)
+        huge_pass_f64_kernel<R, true, false><<<gb, kPassThreads, 0, a.stream>>>(a.table, src, dst, L, s, a.rows, inv, a.scale);
+    else if (last)
+        huge_pass_f64_kernel<R, false, true><<<gb, kPassThreads, 0, a.stream>>>(a.table, src, dst, L, s, a.rows, inv, a.scale);
+    else
+        huge_pass_f64_kernel<R, false, false><<<gb, kPassThreads, 0, a.stream>>>(a.table, src, dst, L, s, a.rows, inv, a.scale);
+    return cudaGetLastError();
+}
+
 } // namespace
+
+// a.in -> a.out through scratch[0] / scratch[1] (rows * n double2 each); launches: out
+cudaError_t launch_huge_fft_f64(int L, const LaunchF64Args &a, double2 *scratch0, double2 *scratch1, int *launches)
+{
+    if (L < 5 || L > kHugeMaxLog2F64) return cudaErrorNotSupported;
+    double2 *bufs[2] = {scratch0, scratch1};
+    const double2 *src = a.in;
+    int cur = 0;
+    *launches = 0;
+    for (int s = 0; s < L;) {
+        const int left = L - s;
+        const int r = left >= 4 ? 4 : left;
+        const bool first = s == 0, last = s + r == L;
+        double2 *dst = last ? a.out : bufs[cur];
+        cudaError_t e;
+        switch (r) {
+        case 1: e = launch_pass_f64<1>(first, last, a, src, dst, L, s); break;
+        case 2: e = launch_pass_f64<2>(first, last, a, src, dst, L, s); break;
+        case 3: e = launch_pass_f64<3>(first, last, a, src, dst, L, s); break;
+        default: e = launch_pass_f64<4>(first, last, a, src, dst, L, s); break;
+        }
+        if (e != cudaSuccess) return e;
+        (*launches)++;
+        src = dst;
+        cur ^= 1;
+        s += r;
+    }
+    return cudaSuccess;
+}
 
 cudaError_t launch_huge_fft(int L, const LaunchArgs &a, HugeArgs &g)
 {

@@ -1589,7 +1589,13 @@ int f64_check_len(kofft_cuda_ctx *ctx, size_t n)
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     if (!is_pow2(n))
         return fail_msg(-static_cast<int>(cudaErrorNotSupported), "f64: non-power-of-two lengths (Bluestein) are not built");
-    if (n > 8192) return fail_msg(-static_cast<int>(cudaErrorNotSupported), "f64: transform lengths above 8192 are not supported yet");
+    return KOFFT_OK;
+}
+// the single-CTA f64 kernel covers n <= 8192; dense C2C rows above that make several trips through global memory
+// (fft_huge.cu), the strided / split / real entry points stop at 8192 (16384 reals)
+int f64_check_small(size_t n)
+{
+    if (n > 8192) return fail_msg(-static_cast<int>(cudaErrorNotSupported), "f64: strided / split / real transforms above 8192 complex points are not supported");
     return KOFFT_OK;
 }
 int f64_dispatch(kofft_cuda_ctx *ctx, LaunchF64Args &a, size_t n, size_t batch, int inverse, cudaStream_t s)
@@ -1645,6 +1651,48 @@ int kofft_cuda_fft_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, s
             CU(cudaMemcpyAsync(d_out, d_in, batch * sizeof(double2), cudaMemcpyDeviceToDevice, s));
         return KOFFT_OK;
     }
+    if (n > 8192) {
+        const int L = log2_of(n);
+        if (L > kHugeMaxLog2F64)
+            return fail_msg(-static_cast<int>(cudaErrorNotSupported), "f64: transform lengths above 2^26 are not supported");
+        auto it = ctx->fft_tables_f64.find(n);
+        if (it == ctx->fft_tables_f64.end()) {
+            kofft_cuda_ctx::TableD t;
+            t.host.resize(n);
+            host_fft_twiddles_f64(n, t.host.data());
+            CU(cudaMalloc(&t.dev, (n / 2) * sizeof(double2)));
+            CU(cudaMemcpy(t.dev, t.host.data(), (n / 2) * sizeof(double2), cudaMemcpyHostToDevice));
+            std::vector<double>().swap(t.host);
+            it = ctx->fft_tables_f64.emplace(n, std::move(t)).first;
+        }
+        const size_t row_bytes = n * sizeof(double2);
+        size_t chunk = ctx->huge_scratch_bytes / 2 / row_bytes;
+        if (chunk < 1) chunk = 1;
+        if (chunk > batch) chunk = batch;
+        void *scratch = nullptr;
+        rc = ensure_ws(ctx, 4, 2 * chunk * row_bytes, &scratch);
+        if (rc) return rc;
+        rc = ws_acquire(ctx, 4, s);
+        if (rc) return rc;
+        for (size_t r0 = 0; r0 < batch; r0 += chunk) {
+            LaunchF64Args a;
+            a.in = static_cast<const double2 *>(d_in) + r0 * n;
+            a.out = static_cast<double2 *>(d_out) + r0 * n;
+            a.n = static_cast<long>(n);
+            a.rows = static_cast<long>(batch - r0 < chunk ? batch - r0 : chunk);
+            a.inverse = inverse != 0;
+            a.scale = 1.0 / static_cast<double>(static_cast<float>(n)); // src/fft.rs:1167
+            a.table = it->second.dev;
+            a.num_sms = ctx->num_sms;
+            a.stream = s;
+            int launches = 0;
+            (void)cudaGetLastError();
+            cudaError_t e = launch_huge_fft_f64(L, a, static_cast<double2 *>(scratch), static_cast<double2 *>(scratch) + chunk * n, &launches);
+            if (e != cudaSuccess) return fail_cuda(e, "f64 huge-N kernel launch");
+            ctx->launches += launches;
+        }
+        return ws_release(ctx, 4, s);
+    }
     LaunchF64Args a;
     a.in = static_cast<const double2 *>(d_in);
     a.out = static_cast<double2 *>(d_out);
@@ -1661,6 +1709,8 @@ int kofft_cuda_fft_strided_f64(kofft_cuda_ctx *ctx, const void *d_in, size_t in_
 {
     if (in_stride == 0 || out_stride == 0) return KOFFT_ERR_INVALID_STRIDE;
     int rc = f64_check_len(ctx, n);
+    if (rc) return rc;
+    rc = f64_check_small(n);
     if (rc) return rc;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
@@ -1682,6 +1732,8 @@ int kofft_cuda_fft_split_f64(kofft_cuda_ctx *ctx, const double *d_in_re, const d
                              double *d_out_im, size_t n, size_t batch, int inverse, void *stream)
 {
     int rc = f64_check_len(ctx, n);
+    if (rc) return rc;
+    rc = f64_check_small(n);
     if (rc) return rc;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
@@ -1725,6 +1777,8 @@ int real_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_
     const size_t m = n / 2;
     int rc = f64_check_len(ctx, m);
     if (rc) return rc;
+    rc = f64_check_small(m);
+    if (rc) return rc;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     LaunchF64Args a;
@@ -1755,6 +1809,8 @@ int kofft_cuda_rfft_batch_host_f64(kofft_cuda_ctx *ctx, const double *input, siz
     if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE;
     int rc = f64_check_len(ctx, n / 2);
     if (rc) return rc;
+    rc = f64_check_small(n / 2);
+    if (rc) return rc;
     if (batch == 0) return KOFFT_OK;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
@@ -1776,6 +1832,8 @@ int kofft_cuda_irfft_batch_host_f64(kofft_cuda_ctx *ctx, const double *input, si
     if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
     if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE;
     int rc = f64_check_len(ctx, n / 2);
+    if (rc) return rc;
+    rc = f64_check_small(n / 2);
     if (rc) return rc;
     if (batch == 0) return KOFFT_OK;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
@@ -1822,6 +1880,8 @@ int kofft_cuda_fft_split_host_f64(kofft_cuda_ctx *ctx, double *re, size_t re_len
     const size_t n = re_len;
     int rc = f64_check_len(ctx, n);
     if (rc) return rc;
+    rc = f64_check_small(n);
+    if (rc) return rc;
     if (n == 1) return KOFFT_OK; // identity; ifft_split: (negate, negate, * 1/1)
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
@@ -1847,6 +1907,8 @@ int kofft_cuda_fft_strided_host_f64(kofft_cuda_ctx *ctx, double *input, size_t i
     if (input_len < (n - 1) * stride + 1) return KOFFT_ERR_MISMATCHED_LENGTHS; // :1188-1190
     int rc = f64_check_len(ctx, n);
     if (rc) return rc;
+    rc = f64_check_small(n);
+    if (rc) return rc;
     if (n == 1) return KOFFT_OK;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
@@ -1870,6 +1932,8 @@ int kofft_cuda_fft_out_of_place_strided_host_f64(kofft_cuda_ctx *ctx, const doub
     const size_t n = input_len / in_stride;
     if (output_len / out_stride != n) return KOFFT_ERR_MISMATCHED_LENGTHS;    // :1274-1276
     int rc = f64_check_len(ctx, n);
+    if (rc) return rc;
+    rc = f64_check_small(n);
     if (rc) return rc;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));

@@ -187,6 +187,9 @@ struct LaunchF64Args {
     cudaStream_t stream = nullptr;
 };
 cudaError_t launch_fft_f64(const LaunchF64Args &a);
+// f64 above 8192 points: register passes through two scratch buffers (fft_huge.cu), dense rows
+constexpr int kHugeMaxLog2F64 = 26;
+cudaError_t launch_huge_fft_f64(int L, const LaunchF64Args &a, double2 *scratch0, double2 *scratch1, int *launches);
 
 // fused single-kernel istft (istft_fused.cuh), N = 512 .. 4096
 struct IstftFusedArgs;

@@ -91,8 +91,8 @@ def test_f64_tables_and_errors(fft64, oracle):
     assert one[0] == 3 - 2j  # n == 1 is a no-op (src/fft.rs:1059-1061, 1139-1141)
     with pytest.raises(CudaBackendError):  # Bluestein for f64 is not built
         fft64.fft(np.zeros(12, np.complex128))
-    with pytest.raises(CudaBackendError):
-        fft64.fft(np.zeros(16384, np.complex128))
+    with pytest.raises(CudaBackendError):  # f64 split / strided / real stop at 8192 complex points
+        fft64.fft_split(np.zeros(16384), np.zeros(16384))
 
 
 def test_f64_split_strided_surface(fft64, oracle):
@@ -187,3 +187,24 @@ def test_f64_rfft_reference_checks_and_errors(fft64, oracle):
         fft64.rfft(np.zeros(7), np.zeros(4, np.complex128))
     with pytest.raises(MismatchedLengths):
         fft64.rfft(np.zeros(8), np.zeros(4, np.complex128))
+
+
+@pytest.mark.parametrize("log2n", [14, 15, 17, 18, 20])
+def test_f64_above_8192(fft64, oracle, log2n):
+    """ScalarFftImpl<f64> has no upper bound either (src/fft.rs:914-1051): above the single-CTA kernel's 8192 points
+    the dense C2C rows make several register passes through global memory (fft_huge.cu); every last-pass radix
+    (2^14: 2 stages, 2^15: 3, 2^17: 1, 2^20: 4).  Bit-exact, both directions, host and device paths."""
+    import torch
+
+    n = 1 << log2n
+    rng = np.random.default_rng(6400 + log2n)
+    x = uniform_c128(rng, (3, n))
+    for inverse in (False, True):
+        ref = oracle.fft_batch_f64(x, inverse=inverse, nthreads=4)
+        y = x.copy()
+        fft64.fft_batch(y, inverse=inverse)
+        assert np.array_equal(y, ref), (log2n, inverse)
+    d = torch.from_numpy(x).cuda()
+    out = torch.empty_like(d)
+    fft64.fft_batch(d, out=out)
+    assert np.array_equal(out.cpu().numpy(), oracle.fft_batch_f64(x, nthreads=4))
