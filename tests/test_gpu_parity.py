@@ -1238,3 +1238,117 @@ def test_non_power_of_two_through_every_core(cuda_fft, cuda_fft_fast, oracle, n)
     S.istft_batch(cuda_fft, fref, w, hop, rec)
     wantr = np.stack([oracle.istft(fref[ch], w, hop, np.zeros(sig.shape[1], np.float32)) for ch in range(2)])
     assert np.array_equal(rec, wantr)
+
+
+def test_persistent_kernels_flag_stress(cuda_fft):
+    """The dependency flags of the two persistent cooperative kernels (split kernel: A warps / B warps over four
+    intermediate slots; pipelined kernel: teams of 8 / 16 CTAs): many back-to-back launches, odd batch sizes, grids
+    from one team up to the whole device, interleaved with other kernels on a second stream -- every result
+    compared bit for bit with the two-kernel path, and no cooperative-launch fallback may have happened."""
+    import torch
+
+    C = cuda_fft.ctx
+    g = torch.Generator(device="cuda").manual_seed(1)
+    side = torch.cuda.Stream()
+    noise = torch.rand((1 << 24,), device="cuda")
+    fb0 = C.fallback_count
+    runs = 0
+    try:
+        for n, rows in ((65536, 1111), (131072, 317), (65536, 37)):
+            xr = (torch.rand((rows, n), generator=g, device="cuda") * 2 - 1).contiguous()
+            xc = torch.view_as_complex((torch.rand((rows, n // 2, 2), generator=g, device="cuda") * 2 - 1).contiguous())
+            C.set_split_min_log2n(16)
+            C.set_large_mode(C.LARGE_TWO_KERNEL)
+            ref_r = cuda_fft.rfft_batch(xr).clone()
+            ref_c = cuda_fft.fft_batch(xc, out=torch.empty_like(xc)).clone()
+            torch.cuda.synchronize()
+            for split_min, mode in ((14, C.LARGE_AUTO), (16, C.LARGE_PIPELINED)):
+                C.set_split_min_log2n(split_min)
+                C.set_large_mode(mode)
+                for max_ctas in (0, 148, 136, 64, 32, 16):  # at least one team of the widest kernel (16 CTAs)
+                    C.set_max_ctas(max_ctas)
+                    for rep in range(4):
+                        with torch.cuda.stream(side):  # unrelated work competing for the SMs between the launches
+                            noise.mul_(1.0001)
+                        y = cuda_fft.rfft_batch(xr)
+                        z = cuda_fft.fft_batch(xc, out=torch.empty_like(xc))
+                        runs += 2
+                        assert torch.equal(torch.view_as_real(y), torch.view_as_real(ref_r)), (n, rows, split_min, max_ctas, rep)
+                        assert torch.equal(torch.view_as_real(z), torch.view_as_real(ref_c)), (n, rows, split_min, max_ctas, rep)
+                C.set_max_ctas(0)
+        torch.cuda.synchronize()
+        assert C.fallback_count == fb0
+        assert runs == 3 * 2 * 6 * 4 * 2
+    finally:
+        C.set_max_ctas(0)
+        C.set_large_mode(C.LARGE_AUTO)
+        C.set_split_min_log2n(14)
+
+
+def test_fast_mode_full_size_rfft_and_stft(cuda_fft, cuda_fft_fast, oracle):
+    """FAST mode (fused multiply-add butterflies) is the mode that meets the 70 % STFT target, so it gets the same
+    full-size treatment as EXACT: BASELINE configs[2] (rfft 2^16 x 16384) and configs[3] (Hann 2048 / hop 512, as many
+    channels as fit) -- whole batch against EXACT (which is bit-identical to the oracle) and sampled rows / frames
+    against the oracle itself: rel-L2 and the worst row / frame within the north star's 1e-5."""
+    import torch
+
+    from kofft_b200 import stft as S
+    from kofft_b200 import window as W
+
+    def rel_rows(a, b):  # per-row rel-L2 of complex tensors [rows, n]
+        d = (torch.view_as_real(a) - torch.view_as_real(b)).double().pow(2).sum(dim=(-2, -1))
+        r = torch.view_as_real(b).double().pow(2).sum(dim=(-2, -1)).clamp_min(1e-300)
+        return torch.sqrt(d.sum() / r.sum()).item(), torch.sqrt((d / r).max()).item()
+
+    n, batch = 65536, 16384
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = (torch.rand((batch, n), generator=g, device="cuda") * 2 - 1).contiguous()
+    ye = cuda_fft.rfft_batch(x)
+    yf = cuda_fft_fast.rfft_batch(x)
+    torch.cuda.synchronize()
+    whole, worst = rel_rows(yf, ye)
+    assert whole <= TOL and worst <= TOL, (whole, worst)
+    rows = np.random.default_rng(2).choice(batch, 12, replace=False)
+    ref = oracle.rfft_batch(x[torch.from_numpy(rows).cuda()].cpu().numpy(), nthreads=8)
+    assert rel_l2(yf[torch.from_numpy(rows).cuda()].cpu().numpy(), ref) <= TOL
+    zf = cuda_fft_fast.irfft_batch(yf, n)
+    ze = cuda_fft.irfft_batch(ye, n)
+    assert float((zf - ze).double().norm() / ze.double().norm()) <= TOL
+    del x, ye, yf, zf, ze
+    torch.cuda.empty_cache()
+
+    free, _ = torch.cuda.mem_get_info()
+    ch = 64 if free > 150e9 else (16 if free > 50e9 else 4)
+    length, hop, win_len = 28_800_000, 512, 2048
+    nframes = -(-length // hop)
+    sig = (torch.rand((ch, length), generator=g, device="cuda") * 2 - 1).contiguous()
+    w = W.hann(win_len)
+    d_w = torch.from_numpy(w).cuda()
+    fe = S.stft_batch(cuda_fft, sig, d_w, hop, nframes)
+    ff = S.stft_batch(cuda_fft_fast, sig, d_w, hop, nframes)
+    torch.cuda.synchronize()
+    worst_all, whole_num, whole_den = 0.0, 0.0, 0.0
+    for c in range(ch):  # channel by channel: the f64 temporaries stay small
+        d = (torch.view_as_real(ff[c]) - torch.view_as_real(fe[c])).double().pow(2).sum(dim=(1, 2))
+        r = torch.view_as_real(fe[c]).double().pow(2).sum(dim=(1, 2)).clamp_min(1e-300)
+        worst_all = max(worst_all, float(torch.sqrt((d / r).max())))
+        whole_num += float(d.sum())
+        whole_den += float(r.sum())
+    assert (whole_num / whole_den) ** 0.5 <= TOL and worst_all <= TOL, ((whole_num / whole_den) ** 0.5, worst_all)
+    rng = np.random.default_rng(4)
+    c = int(rng.integers(ch))
+    host_sig = sig[c].cpu().numpy()
+    for f in np.concatenate([rng.choice(nframes, 16, replace=False), [0, nframes - 1]]):
+        seg = np.zeros(win_len, np.float32)
+        part = host_sig[f * hop: f * hop + win_len]
+        seg[: len(part)] = part
+        want = oracle.fft((seg * w).astype(np.complex64))
+        assert rel_l2(ff[c, f].cpu().numpy(), want) <= TOL, (c, f)
+    del ff
+    oe = torch.zeros((ch, length), device="cuda")
+    of = torch.zeros((ch, length), device="cuda")
+    S.istft_batch(cuda_fft, fe, d_w, hop, oe)
+    S.istft_batch(cuda_fft_fast, fe, d_w, hop, of)
+    torch.cuda.synchronize()
+    per = (of - oe).double().norm(dim=1) / oe.double().norm(dim=1)
+    assert float(per.max()) <= TOL, float(per.max())
