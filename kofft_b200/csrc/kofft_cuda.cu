@@ -2190,9 +2190,9 @@ struct kofft_cuda_dist {
     float2 *tlo = nullptr, *thi = nullptr;
     // the local transforms of a phase are cut into pieces; piece i is scattered to the peers on a
     // second stream while piece i+1 is transformed, so NVLink traffic overlaps the butterflies
-    // 8 pieces / 48 SMs: 8-GPU sweep profiles/r04e (2^30: 5.25 ms against 5.57 ms with 4 / 32)
+    // 8 pieces / 64 SMs: 8-GPU sweeps profiles/r04e (2^30: 5.03 ms against 5.57 ms with 4 / 32)
     int pieces = 8;
-    int reserve_sms = 48; // SMs the piece transforms leave free so the concurrent scatter kernel gets on the machine
+    int reserve_sms = 64; // SMs the piece transforms leave free so the concurrent scatter kernel gets on the machine
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fft[16] = {}, ev_done = nullptr;
 };
