@@ -99,6 +99,11 @@ enum SplitEpilogue : int { SPLIT_STORE = 0, SPLIT_TWIST = 1 };
 // 1: every A warp polls / arrives by itself.  Measured slower (rfft 2^16 x 16384: 2.94 vs 2.61 ms, profiles/r03g):
 // a warp's release fence right behind its 32 stores waits for all of them, eight times per tile; the block-level
 // scheme arrives behind the NEXT tile's first barrier, when the stores have long landed.
+// timing experiments only (scripts/build_variants.sh): 1 = the A warps alone (B warps return, slots are never waited
+// for), 2 = the B warps alone (they do not wait for pass A and transform whatever the intermediate holds)
+#ifndef KOFFT_SPLIT_ONLY_ROLE
+#define KOFFT_SPLIT_ONLY_ROLE 0
+#endif
 #ifndef KOFFT_SPLIT_WARP_FLAGS
 #define KOFFT_SPLIT_WARP_FLAGS 0
 #endif
@@ -172,6 +177,7 @@ struct Split32 {
     // is not on the critical path when the slot is already free.
     static KD void a_wait_slot(unsigned *cntB, long i, unsigned seen = 0)
     {
+        if (KOFFT_SPLIT_ONLY_ROLE == 1) return;
         if (i >= SLOTS) {
             const unsigned want = goal_b(i - SLOTS);
             while (seen < want) {
@@ -383,7 +389,7 @@ struct Split32 {
                 // shuffles below plain SHFL instructions (behind a one-lane polling loop the compiler guards every
                 // shuffle with a convergence sequence: 2600 extra instructions per tile, profiles/r03a)
                 const unsigned want = goal_a(i);
-                while (flag_load(cntA + i % SLOTS) < want) nano_sleep(32);
+                while (KOFFT_SPLIT_ONLY_ROLE != 2 && flag_load(cntA + i % SLOTS) < want) nano_sleep(32);
                 (void)flag_load_acquire(cntA + i % SLOTS);
                 fetch(i);
             }
@@ -459,6 +465,7 @@ struct Split32 {
         float2 *slots = scratch + team * SLOTS * n;
         if (tid < A_THREADS) {
             setmaxnreg_dec<KOFFT_SPLIT_REGS_A>();
+            if (KOFFT_SPLIT_ONLY_ROLE == 2) return;
             if constexpr (STAGED)
                 a_role_staged(io, tw0, table, cnt, team, teams, kb, slots, smem, cntA, cntB, tid, map,
                               reinterpret_cast<unsigned long long *>(smem + OFF_BAR));
@@ -466,6 +473,7 @@ struct Split32 {
                 a_role(io, tw0, table, cnt, team, teams, kb, slots, smem, cntA, cntB, tid);
         } else {
             setmaxnreg_inc<KOFFT_SPLIT_REGS_B>();
+            if (KOFFT_SPLIT_ONLY_ROLE == 1) return;
             const int wl = tid - A_THREADS;
             if (kb == NT - 1 && (wl >> 5) == B_WARPS - 1)
                 b_role<true>(io, table, cnt, team, teams, kb, slots, smem, cntA, cntB, wl);
