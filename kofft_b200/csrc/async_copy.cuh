@@ -42,6 +42,8 @@ KD void mbar_wait(unsigned long long *bar, unsigned parity)
 }
 // generic-proxy accesses to shared memory (ld/st) ordered before later async-proxy (TMA) writes to it
 KD void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// the same for global memory: rows written with ordinary stores (and acquired) before a tensor-map copy reads them
+KD void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 // one arrival + the number of bytes the bulk copies of this phase will deliver
 KD void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
 {
@@ -69,8 +71,15 @@ KD void cp_async16_hint(void *dst_smem, const void *src, unsigned long long pol)
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "l"(pol)
                  : "memory");
 }
+// 8-byte variant (through L1; source rows that are only 8-byte aligned)
+KD void cp_async8(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
 KD void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 KD void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// all but the most recent PENDING committed groups are complete
+template <int PENDING> KD void cp_async_wait_but() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
 // thread-block cluster barrier with release/acquire semantics (all threads of all CTAs)
 KD void cluster_sync()
@@ -145,6 +154,8 @@ KD void flag_arrive_relaxed(unsigned *c) { atomicAdd(c, 1u); }
 // ---- warp-level and partial-CTA primitives of the warp-specialised large-N kernel (fft_split32.cuh) ----
 // bar.sync id, n: barrier among the n threads (a multiple of 32) that name it; id 0 is __syncthreads
 KD void named_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// bar.arrive: counts towards barrier `id` without waiting (the waiting threads use named_barrier)
+KD void named_barrier_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 KD void warp_sync() { __syncwarp(); }
 KD float shfl_xor_f(float v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
 // warp-group register reallocation (setmaxnreg, sm_90+): executed by all four warps of a warp group
@@ -195,6 +206,7 @@ KD void tma_load_2d(void *dst_smem, const TmaMap *map, int c0, int c1, unsigned 
 #elif defined(KOFFT_EMU)
 
 inline void named_barrier(int id, int nthreads) { cuda_emu::named_barrier(id, nthreads); }
+inline void named_barrier_arrive(int id, int nthreads) { cuda_emu::named_barrier_arrive(id, nthreads); }
 inline void warp_sync() { cuda_emu::syncwarp(); }
 inline float shfl_xor_f(float v, int mask) { return cuda_emu::shfl_xor(v, mask); }
 template <int REGS> inline void setmaxnreg_inc() {}
@@ -226,8 +238,14 @@ inline void cp_async16(void *dst_smem, const void *src)
     memcpy(dst_smem, src, 16);
 }
 inline void cp_async16_hint(void *dst_smem, const void *src, unsigned long long) { cp_async16(dst_smem, src); }
+inline void cp_async8(void *dst_smem, const void *src)
+{
+    if ((reinterpret_cast<uintptr_t>(dst_smem) & 7) || (reinterpret_cast<uintptr_t>(src) & 7)) abort();
+    memcpy(dst_smem, src, 8);
+}
 inline void cp_async_commit() {}
 inline void cp_async_wait_all() {}
+template <int PENDING> inline void cp_async_wait_but() {}
 
 inline void cluster_sync() { cuda_emu::cluster_sync(); }
 inline unsigned cluster_ctarank() { return cuda_emu::cluster_rank(); }
@@ -243,6 +261,7 @@ inline EmuMbar &emu_mbar(unsigned long long *bar) { return *reinterpret_cast<Emu
 inline void mbar_init(unsigned long long *bar, unsigned) { emu_mbar(bar) = EmuMbar{0u, 0}; }
 inline void fence_mbar_init() {}
 inline void fence_proxy_async() {}
+inline void fence_proxy_async_global() {}
 inline void mbar_wait(unsigned long long *bar, unsigned parity)
 {
     while ((emu_mbar(bar).completed & 1u) == parity) cuda_emu::yield_to_scheduler();

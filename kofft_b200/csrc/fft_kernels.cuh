@@ -377,25 +377,30 @@ struct IoIrfft {
     static constexpr bool kStageable = false;
     static constexpr bool kLoadAux = false;
     KHD void init(int) {}
+    // element 0 of the packed spectrum (src/rfft.rs:485-488) and element i from X[i], X[m-i], T'[i] (:489-498)
+    KHD float2 untwist0(float2 x0, float2 xm) const
+    {
+        return make_float2(mul_rn(add_rn(x0.x, xm.x), 0.5f), mul_rn(sub_rn(x0.x, xm.x), 0.5f));
+    }
+    KHD float2 untwist(float2 a, float2 xm, float2 tw) const
+    {
+        float2 b = make_float2(xm.x, -xm.y);
+        float2 sum = add2(a, b), diff = sub2(a, b);
+        float2 t = cmul<EXACT>(make_float2(tw.x, -tw.y), diff);
+        float2 temp = make_float2(sub_rn(sum.x, t.y), add_rn(sum.y, t.x)); // sum - (t.im, -t.re)
+        return make_float2(mul_rn(temp.x, 0.5f), mul_rn(temp.y, 0.5f));
+    }
     KHD float2 load(long row, int i) const
     {
         const float2 *X = in + row * (m + 1);
         float2 v;
-        if (i == 0) {
-            float2 x0 = KOFFT_LDG(X), xm = KOFFT_LDG(X + m);
-            v = make_float2(mul_rn(add_rn(x0.x, xm.x), 0.5f), mul_rn(sub_rn(x0.x, xm.x), 0.5f));
-        } else {
-            float2 a = KOFFT_LDG(X + i);
-            float2 xm = KOFFT_LDG(X + (m - i));
-            float2 b = make_float2(xm.x, -xm.y);
-            float2 sum = add2(a, b), diff = sub2(a, b);
-            float2 tw = KOFFT_LDG(rtw + i);
-            float2 t = cmul<EXACT>(make_float2(tw.x, -tw.y), diff);
-            float2 temp = make_float2(sub_rn(sum.x, t.y), add_rn(sum.y, t.x)); // sum - (t.im, -t.re)
-            v = make_float2(mul_rn(temp.x, 0.5f), mul_rn(temp.y, 0.5f));
-        }
+        if (i == 0)
+            v = untwist0(KOFFT_LDG(X), KOFFT_LDG(X + m));
+        else
+            v = untwist(KOFFT_LDG(X + i), KOFFT_LDG(X + (m - i)), KOFFT_LDG(rtw + i));
         return pre_conj<true>(v);
     }
+    KHD float2 from_raw(float2 v) const { return pre_conj<true>(v); } // an untwisted row (split kernel, PRE)
     KHD void store(long row, int i, float2 v) const { out[row * m + i] = post_conj_scale<true>(v, scale); }
 };
 

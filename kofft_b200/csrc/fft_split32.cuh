@@ -104,6 +104,17 @@ enum SplitEpilogue : int { SPLIT_STORE = 0, SPLIT_TWIST = 1 };
 #ifndef KOFFT_SPLIT_ONLY_ROLE
 #define KOFFT_SPLIT_ONLY_ROLE 0
 #endif
+// 1: the A warps' second block barrier per tile becomes bar.arrive for seven warps (only the warp that issues the
+// next tile's copy waits); the B warps' polling interval in ns
+#ifndef KOFFT_SPLIT_LAZY_BAR2
+#define KOFFT_SPLIT_LAZY_BAR2 0
+#endif
+#ifndef KOFFT_SPLIT_POLL_NS
+#define KOFFT_SPLIT_POLL_NS 32
+#endif
+#ifndef KOFFT_SPLIT_ZSLOTS
+#define KOFFT_SPLIT_ZSLOTS 4
+#endif
 #ifndef KOFFT_SPLIT_WARP_FLAGS
 #define KOFFT_SPLIT_WARP_FLAGS 0
 #endif
@@ -120,7 +131,7 @@ enum SplitEpilogue : int { SPLIT_STORE = 0, SPLIT_TWIST = 1 };
 // stores -- the HBM latency of a tile is hidden behind the previous tile's arithmetic at no cost in shared
 // memory.  The first register pass is "in place" in index space (a thread reads and writes the same 32
 // positions of its column), so the landed tile doubles as the exchange buffer without an extra barrier.
-template <int LA, bool EXACT, class IO, int EPI, bool STAGED = false>
+template <int LA, bool EXACT, class IO, int EPI, bool STAGED = false, bool PRE = false>
 struct Split32 {
     static_assert(LA >= 8 && LA <= 10, "N = 2^13 .. 2^15");
     static constexpr int L = LA + 5;
@@ -139,8 +150,11 @@ struct Split32 {
     static constexpr int NTILES = NR / 32;        // warp tiles (16 rows + 16 mirrors) per transform
     static_assert(NTILES == NT * B_WARPS, "a team's B warps cover one transform");
     static constexpr int SLOTS = KOFFT_SPLIT_SLOTS;
-    static constexpr int FLAG_STRIDE = 32;        // unsigned per team: cntA[SLOTS], cntB[SLOTS] in one line
-    static_assert(2 * SLOTS <= FLAG_STRIDE, "flag line");
+    static constexpr int FLAG_STRIDE = 32;        // unsigned per team: cntA[SLOTS], cntB[SLOTS] (PRE: + cntZ, cntZf[ZSLOTS])
+    // PRE (irfft): the B warps also untwist the rows (src/rfft.rs:485-498) ZAHEAD transforms ahead of pass A, into
+    // ZSLOTS L2-resident rows per team that pass A's tile loads read instead of the caller's input
+    static constexpr int ZSLOTS = KOFFT_SPLIT_ZSLOTS, ZAHEAD = 2;
+    static_assert(2 * SLOTS + (PRE ? 2 * ZSLOTS : 0) <= FLAG_STRIDE && ZAHEAD < ZSLOTS, "flag line");
 
     // ---- shared memory (float2 units) ----
     // pass-A exchange: one padded region per column; the region stride makes the 16 lanes of a half
@@ -149,7 +163,8 @@ struct Split32 {
     static constexpr int RSA = PADN + (COLS == 8 ? 2 : 1);
     // STAGED: the tile as the TMA delivers it, row-major [NR rows][COLS] in NBOX boxes of 256 rows
     static constexpr int NBOX = NR / 256;
-    static_assert(!STAGED || (LA == 10 && IoTraits<IO>::kRowPtr), "staging: 2^15 points, plain contiguous rows");
+    static_assert(!STAGED || (LA == 10 && (IoTraits<IO>::kRowPtr || PRE)), "staging: 2^15 points, plain contiguous rows");
+    static_assert(!PRE || STAGED, "the untwisted rows are fetched as staged tiles");
     static constexpr int XA = STAGED ? NR * COLS : COLS * RSA;
     static constexpr unsigned TILE_BYTES = 8192u * 8u;
     // pass-A second-pass twiddles: [TA][33] (k1-dependent, shared by the columns)
@@ -157,7 +172,8 @@ struct Split32 {
     // pass-B transposition: per warp two halves of 16 rows x 34 (16-byte accesses, conflict-free)
     static constexpr int RSB = 34, HB = 16 * RSB, XB = 2 * HB;
     // rfft: the CTA's slice of T' (src/rfft.rs:172-183), [warp][register][lane]
-    static constexpr int RTW = EPI == SPLIT_TWIST ? B_WARPS * 32 * 32 : 0;
+    // (PRE: the same room holds the input bins a warp untwists next, [warp][k | n - k][16][lane])
+    static constexpr int RTW = (EPI == SPLIT_TWIST || PRE) ? B_WARPS * 32 * 32 : 0;
     static constexpr int OFF_TWA = (XA + 1) & ~1;
     static constexpr int OFF_XB = (OFF_TWA + TWA + 1) & ~1;
     static constexpr int OFF_RTW = OFF_XB + B_WARPS * XB;
@@ -167,8 +183,11 @@ struct Split32 {
 
     static constexpr int A_WARPS = A_THREADS / 32;
     static constexpr bool WARP_FLAGS = KOFFT_SPLIT_WARP_FLAGS != 0;
+    static constexpr bool LAZY_BAR2 = KOFFT_SPLIT_LAZY_BAR2 != 0;
     static KD unsigned goal_a(long i) { return (unsigned)(NT * (WARP_FLAGS ? A_WARPS : 1) * (i / SLOTS + 1)); }
     static KD unsigned goal_b(long i) { return (unsigned)(NTILES * (i / SLOTS + 1)); }
+    static KD unsigned goal_z(long j) { return (unsigned)(NTILES * (j / ZSLOTS + 1)); } // every B warp of the team has written row j
+    static KD unsigned goal_zfree(long j) { return (unsigned)(NT * (j / ZSLOTS)); }     // the tiles of row j - ZSLOTS have landed
 
     // A warps, per tile: wait (whole warp polls: no block barrier involved) until every B warp of the team has consumed
     // transform i - SLOTS, whose slot this tile's stores overwrite; after the stores each warp arrives by itself
@@ -277,6 +296,19 @@ struct Split32 {
                                  long teams, int kb, float2 *__restrict__ slots, float2 *smem, unsigned *cntA,
                                  unsigned *cntB, int tid, const TmaMap *map, unsigned long long *bar)
     {
+        unsigned *cntZ = cntB + SLOTS, *cntZf = cntZ + ZSLOTS;
+        // the tile's row in the tensor map: the caller's row, or (PRE) the team's slot of untwisted rows
+        auto tile_row = [&](long i) { return PRE ? team * ZSLOTS + i % ZSLOTS : team + i * teams; };
+        // PRE: the row exists once every B warp of the team has arrived; their (generic-proxy) stores are then
+        // ordered before the tile copy's (async-proxy) reads
+        auto wait_row = [&](long i) {
+            if constexpr (PRE) {
+                const unsigned want = goal_z(i);
+                while (flag_load(cntZ + i % ZSLOTS) < want) nano_sleep(32);
+                (void)flag_load_acquire(cntZ + i % ZSLOTS);
+                fence_proxy_async_global();
+            }
+        };
         const long n = 1L << L;
         const int col = tid & 7, t0 = tid >> 3;
         const int k1 = ((tid >> 3) & 3) * 8 + (tid >> 5);
@@ -295,7 +327,10 @@ struct Split32 {
             twa[kk * 33 + e] = table[(long)(kk + (c << RA0)) << (LA - 1 - RA0 - tl + 5)];
         }
         named_barrier(1, A_THREADS);
-        if (tid == 0 && cnt > 0) issue_tile(map, stage, bar, team, kb);
+        if (tid == 0 && cnt > 0) {
+            wait_row(0);
+            issue_tile(map, stage, bar, tile_row(0), kb);
+        }
         const float2 *tw1 = twa + k1 * 33;
         float2 *s0 = stage + t0 * COLS + col;        // row t0 (+ q 32 rows)
         float2 *s0x = stage + (t0 ^ 1) * COLS + col; // the neighbour's row, for outputs with bit 3 set
@@ -310,6 +345,7 @@ struct Split32 {
             float2 x[WIDE];
             mbar_wait(bar, phase);
             phase ^= 1;
+            if (PRE && tid == 64) flag_arrive_relaxed(cntZf + i % ZSLOTS); // the row's slot may be rewritten (by this CTA's share)
 #pragma unroll
             for (int q = 0; q < 32; q++) x[q] = io.from_raw(s0[q * 32 * COLS]);
             A0::compute(x, tw0.v);
@@ -319,15 +355,25 @@ struct Split32 {
                 const int c = bitrev(w, 5);
                 (((c >> 3) & 1) ? s0x : s0)[c * 32 * COLS] = x[w];
             }
+            if (LAZY_BAR2 && !WARP_FLAGS && tid == 0) a_wait_slot(cntB, i, seen); // released to the others by the barrier
             named_barrier(1, A_THREADS); // exchange; also: every thread is past the previous tile's stores
             if (!WARP_FLAGS && tid == 32 && i > 0) flag_arrive(cntA + (i - 1) % SLOTS); // (not the polling thread's warp)
 #pragma unroll
             for (int q = 0; q < 32; q++) x[q] = ((q & 1) ? s1o : s1e)[q * COLS];
-            if (!WARP_FLAGS && tid == 0) a_wait_slot(cntB, i, seen); // released to the others by the barrier
-            named_barrier(1, A_THREADS); // the buffer is free: the next tile may land
+            if (LAZY_BAR2) {
+                // only the warp that issues the next tile's copy waits for the others' reads
+                if (tid < 32)
+                    named_barrier(2, A_THREADS);
+                else
+                    named_barrier_arrive(2, A_THREADS);
+            } else {
+                if (!WARP_FLAGS && tid == 0) a_wait_slot(cntB, i, seen); // released to the others by the barrier
+                named_barrier(1, A_THREADS); // the buffer is free: the next tile may land
+            }
             if (tid == 0 && i + 1 < cnt) {
+                wait_row(i + 1);
                 fence_proxy_async();
-                issue_tile(map, stage, bar, team + (i + 1) * teams, kb);
+                issue_tile(map, stage, bar, tile_row(i + 1), kb);
             }
             A1::compute(x, tw1);
             if (WARP_FLAGS) a_wait_slot(cntB, i);
@@ -348,7 +394,8 @@ struct Split32 {
     // ------------------------------------------------------------------------------------------
     template <bool SPECIAL>
     static KD void b_role(const IO &io, const float2 *__restrict__ table, long cnt, long team, long teams, int kb,
-                          const float2 *__restrict__ slots, float2 *smem, unsigned *cntA, unsigned *cntB, int wl)
+                          const float2 *__restrict__ slots, float2 *smem, unsigned *cntA, unsigned *cntB, int wl,
+                          float2 *__restrict__ zs = nullptr)
     {
         const long n = 1L << L;
         const int w = wl >> 5, lane = wl & 31, h = lane >> 4, lp = lane & 15;
@@ -381,19 +428,90 @@ struct Split32 {
             }
             cp_async_commit();
         };
+        // PRE: this warp's share of row j's untwist -- bins k = 512 wt + lane + 32 jj (jj < 16) and their mirrors n - k,
+        // both from the same two inputs; coalesced 256-byte requests.  Bin 0 (X[0], X[n]) and bin n/2 (its own mirror)
+        // belong to the team's first lane.  The input bins arrive by 8-byte asynchronous copies (the rows of n + 1
+        // bins are only 8-byte aligned) issued one transform earlier, so their HBM latency is not waited for.
+        float2 *xr = smem + OFF_RTW + w * (32 * 32) + lane;
+        const int kfirst = wt * 512 + lane;
+        auto fetch_bins = [&](long j) {
+            if constexpr (PRE) {
+                const float2 *X = io.in + (team + j * teams) * (n + 1);
+#pragma unroll
+                for (int jj = 0; jj < 16; jj++) {
+                    const int kk = kfirst + jj * 32;
+                    cp_async8(xr + jj * 32, X + kk);
+                    cp_async8(xr + 512 + jj * 32, X + ((int)n - kk));
+                }
+                cp_async_commit();
+            }
+        };
+        auto untwist_row = [&](long j) { // the bins of row j have landed
+            if constexpr (PRE) {
+                unsigned *cntZ = cntB + SLOTS, *cntZf = cntZ + ZSLOTS;
+                const L2Policy pol = make_l2_policy();
+                float2 *Z = zs + (j % ZSLOTS) * n;
+                if (j >= ZSLOTS) {
+                    const unsigned want = goal_zfree(j);
+                    while (flag_load(cntZf + j % ZSLOTS) < want) nano_sleep(64);
+                }
+#pragma unroll
+                for (int hb = 0; hb < 2; hb++) {
+                    float2 ta[8], tm[8];
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) {
+                        const int kk = kfirst + (hb * 8 + jj) * 32;
+                        ta[jj] = KOFFT_LDG(io.rtw + kk);
+                        tm[jj] = KOFFT_LDG(io.rtw + (kk == 0 ? 0 : (int)n - kk)); // T' has n entries
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) {
+                        const int kk = kfirst + (hb * 8 + jj) * 32;
+                        const float2 a = xr[(hb * 8 + jj) * 32], b = xr[512 + (hb * 8 + jj) * 32];
+                        if (kk != 0) {
+                            stg_hint(Z + kk, io.untwist(a, b, ta[jj]), pol.last);
+                            stg_hint(Z + ((int)n - kk), io.untwist(b, a, tm[jj]), pol.last);
+                        } else {
+                            const float2 xh = KOFFT_LDG(io.in + (team + j * teams) * (n + 1) + n / 2);
+                            stg_hint(Z, io.untwist0(a, b), pol.last);
+                            stg_hint(Z + n / 2, io.untwist(xh, xh, KOFFT_LDG(io.rtw + n / 2)), pol.last);
+                        }
+                    }
+                }
+                warp_sync(); // orders the warp's stores before lane 0's release
+                if (lane == 0) flag_arrive(cntZ + j % ZSLOTS);
+            }
+        };
+        if constexpr (PRE) {
+            for (long j = 0; j < ZAHEAD && j < cnt; j++) {
+                fetch_bins(j);
+                cp_async_wait_all();
+                untwist_row(j);
+            }
+            if (ZAHEAD < cnt) fetch_bins(ZAHEAD);
+        }
         bool fetched = false;
         for (long i = 0; i < cnt; i++) {
             const long row = team + i * teams;
+            if (PRE && i + ZAHEAD < cnt) {
+                cp_async_wait_all();
+                untwist_row(i + ZAHEAD);
+            }
             if (!fetched) {
                 // every lane polls (one broadcast request per iteration): the warp stays converged, which keeps the
                 // shuffles below plain SHFL instructions (behind a one-lane polling loop the compiler guards every
                 // shuffle with a convergence sequence: 2600 extra instructions per tile, profiles/r03a)
                 const unsigned want = goal_a(i);
-                while (KOFFT_SPLIT_ONLY_ROLE != 2 && flag_load(cntA + i % SLOTS) < want) nano_sleep(32);
+                while (KOFFT_SPLIT_ONLY_ROLE != 2 && flag_load(cntA + i % SLOTS) < want) nano_sleep(KOFFT_SPLIT_POLL_NS);
                 (void)flag_load_acquire(cntA + i % SLOTS);
                 fetch(i);
             }
-            cp_async_wait_all();
+            if (PRE && i + ZAHEAD + 1 < cnt) { // behind the tile's copies, so that only those are waited for
+                fetch_bins(i + ZAHEAD + 1);
+                cp_async_wait_but<1>();
+            } else {
+                cp_async_wait_all();
+            }
             warp_sync();
             if (lane == 0) flag_arrive_relaxed(cntB + i % SLOTS); // the warp's reads of the slot are complete
             float2 x[WIDE];
@@ -463,6 +581,7 @@ struct Split32 {
         unsigned *cntA = flags + team * FLAG_STRIDE, *cntB = cntA + SLOTS;
         const long cnt = team < rows ? (rows - team + teams - 1) / teams : 0;
         float2 *slots = scratch + team * SLOTS * n;
+        float2 *zs = PRE ? scratch + teams * SLOTS * n + team * ZSLOTS * n : nullptr; // behind every team's slots
         if (tid < A_THREADS) {
             setmaxnreg_dec<KOFFT_SPLIT_REGS_A>();
             if (KOFFT_SPLIT_ONLY_ROLE == 2) return;
@@ -476,21 +595,21 @@ struct Split32 {
             if (KOFFT_SPLIT_ONLY_ROLE == 1) return;
             const int wl = tid - A_THREADS;
             if (kb == NT - 1 && (wl >> 5) == B_WARPS - 1)
-                b_role<true>(io, table, cnt, team, teams, kb, slots, smem, cntA, cntB, wl);
+                b_role<true>(io, table, cnt, team, teams, kb, slots, smem, cntA, cntB, wl, zs);
             else
-                b_role<false>(io, table, cnt, team, teams, kb, slots, smem, cntA, cntB, wl);
+                b_role<false>(io, table, cnt, team, teams, kb, slots, smem, cntA, cntB, wl, zs);
         }
     }
 };
 
 #ifdef __CUDACC__
-template <int LA, bool EXACT, class IO, int EPI, bool STAGED>
+template <int LA, bool EXACT, class IO, int EPI, bool STAGED, bool PRE = false>
 __global__ void __launch_bounds__(512, 1)
     split32_kernel(const __grid_constant__ IO io, const __grid_constant__ Tw0W tw0, const float2 *__restrict__ table,
                    long rows, float2 *__restrict__ scratch, unsigned *flags, const __grid_constant__ TmaMap map)
 {
     extern __shared__ __align__(128) float2 smem[];
-    Split32<LA, EXACT, IO, EPI, STAGED>::run(io, tw0, table, rows, scratch, smem, flags, &map);
+    Split32<LA, EXACT, IO, EPI, STAGED, PRE>::run(io, tw0, table, rows, scratch, smem, flags, &map);
 }
 #endif
 

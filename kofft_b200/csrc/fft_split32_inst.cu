@@ -40,7 +40,7 @@ cudaError_t encode_rows_map(TmaMap *out, const void *base, unsigned long long to
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int LA, bool EXACT, class IO, int EPI, bool STAGED>
+template <int LA, bool EXACT, class IO, int EPI, bool STAGED, bool PRE = false>
 cudaError_t launch_split_v(const IO &io, const LaunchArgs &a, SplitArgs &g);
 
 // a.staged: the host verified 16-byte alignment of the rows (TMA tile loads)
@@ -54,17 +54,13 @@ cudaError_t launch_split(const IO &io, const LaunchArgs &a, SplitArgs &g)
 }
 
 // one persistent cooperative launch, one 512-thread CTA per SM, teams of NT CTAs
-template <int LA, bool EXACT, class IO, int EPI, bool STAGED>
+template <int LA, bool EXACT, class IO, int EPI, bool STAGED, bool PRE>
 cudaError_t launch_split_v(const IO &io, const LaunchArgs &a, SplitArgs &g)
 {
-    using F = Split32<LA, EXACT, IO, EPI, STAGED>;
-    static_assert(F::SLOTS == kSplitSlots && F::FLAG_STRIDE == kPipeFlagStride, "host-side sizes");
-    auto kern = split32_kernel<LA, EXACT, IO, EPI, STAGED>;
+    using F = Split32<LA, EXACT, IO, EPI, STAGED, PRE>;
+    static_assert(F::SLOTS == kSplitSlots && F::FLAG_STRIDE == kPipeFlagStride && F::ZSLOTS == kSplitZSlots, "host-side sizes");
+    auto kern = split32_kernel<LA, EXACT, IO, EPI, STAGED, PRE>;
     TmaMap map = {};
-    if constexpr (STAGED) {
-        cudaError_t e = encode_rows_map(&map, io.in, (unsigned long long)a.rows << LA, F::COLS);
-        if (e != cudaSuccess) return e;
-    }
     static PerDevice occ_pd;
     int &occ = occ_pd.get();
     if (occ == 0) {
@@ -88,6 +84,13 @@ cudaError_t launch_split_v(const IO &io, const LaunchArgs &a, SplitArgs &g)
     float2 *scratch = g.scratch;
     unsigned *flags = g.flags;
     const float2 *table = a.table;
+    if constexpr (STAGED) {
+        // the tiles come from the caller's rows, or (PRE) from the teams' untwisted rows behind the intermediate
+        const void *base = PRE ? static_cast<const void *>(scratch + (size_t(teams) * F::SLOTS << F::L)) : static_cast<const void *>(io.in);
+        const unsigned long long trows = PRE ? (unsigned long long)(teams * F::ZSLOTS) : (unsigned long long)a.rows;
+        cudaError_t em = encode_rows_map(&map, base, trows << LA, F::COLS);
+        if (em != cudaSuccess) return em;
+    }
     cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(unsigned) * F::FLAG_STRIDE * teams, a.stream);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -141,6 +144,10 @@ cudaError_t launch_kind(const LaunchArgs &a, SplitArgs &g)
     }
     case KIND_IRFFT: {
         IoIrfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n, q.scale};
+        if constexpr (LA == 10) { // the B warps untwist the rows ahead of pass A, which then stages tiles as for C2C
+            if (g.pre_rows && (long(kSplitZSlots) * g.max_teams << LA) < (1L << 31))
+                return launch_split_v<LA, EXACT, IoIrfft<EXACT>, SPLIT_STORE, true, true>(io, a, g);
+        }
         return launch_split<LA, EXACT, IoIrfft<EXACT>, SPLIT_STORE>(io, a, g);
     }
     default:

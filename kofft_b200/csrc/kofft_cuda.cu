@@ -114,6 +114,7 @@ struct kofft_cuda_ctx {
     // (16 = off).  Cooperative launch; when the device cannot make every CTA resident the older paths compute
     // the same bits and coop_fallbacks counts it.
     int split_min_l = 14;
+    bool split_irfft = true; // irfft at 2^15 through the split kernel with the untwist in its B warps (KOFFT_SPLIT_IRFFT=0: older path)
     bool split_all_kinds = false; // default: C2C and rfft, where it measured faster; irfft / SoA rows keep the older paths
     unsigned long long coop_fallbacks = 0;
     int l2_persist_mode = 0; // 0 off, 1 requested (KOFFT_L2_PERSIST=1), 2 active
@@ -288,7 +289,10 @@ int dispatch_impl(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, siz
             ctx->launches += g.launches;
             return KOFFT_OK;
         }
+        // irfft at 2^15 complex points: the split kernel's B warps untwist the rows ahead of pass A (2^13, 2^14 and the
+        // SoA rows keep the older paths, where they measured faster)
         const bool split_kind = kind == KIND_C2C_FWD || kind == KIND_C2C_INV || kind == KIND_RFFT ||
+                                (kind == KIND_IRFFT && L == 15 && ctx->split_irfft) ||
                                 (ctx->split_all_kinds && (kind == KIND_GEN_FWD || kind == KIND_GEN_INV || kind == KIND_IRFFT));
         if (L >= ctx->split_min_l && L >= 13 && L <= 15 && split_kind) {
             SplitArgs g;
@@ -301,7 +305,8 @@ int dispatch_impl(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, siz
             const int nt = 1 << (L - 13); // CTAs per team
             g.max_teams = ctx->num_sms / nt;
             void *scratch = nullptr;
-            rc = ensure_ws(ctx, 4, size_t(kSplitSlots) * g.max_teams * n * sizeof(float2), &scratch);
+            g.pre_rows = kind == KIND_IRFFT && L == 15 && ctx->split_irfft;
+            rc = ensure_ws(ctx, 4, size_t(kSplitSlots + (g.pre_rows ? kSplitZSlots : 0)) * g.max_teams * n * sizeof(float2), &scratch);
             if (rc) return rc;
             if (!ctx->pipe_flags) // sized for the smallest team of any persistent large-N kernel
                 CU(cudaMalloc(&ctx->pipe_flags, sizeof(unsigned) * kPipeFlagStride * (kMaxPipeCtasPerSm * ctx->num_sms)));
@@ -503,6 +508,7 @@ int kofft_cuda_create(kofft_cuda_ctx **out, int device)
         if (atoi(m) == 1) ctx->l2_persist_mode = 1;
     if (const char *m = getenv("KOFFT_SPLIT_MIN_L"))
         if (atoi(m) >= 13 && atoi(m) <= 16) ctx->split_min_l = atoi(m);
+    if (const char *m = getenv("KOFFT_SPLIT_IRFFT")) ctx->split_irfft = atoi(m) != 0;
 
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;

@@ -99,12 +99,17 @@ cudaError_t launch_large_fft(int L, const LaunchArgs &a, LargeArgs &g);
 #define KOFFT_SPLIT_SLOTS 4
 #endif
 constexpr int kSplitSlots = KOFFT_SPLIT_SLOTS; // intermediate transforms per team (Split32::SLOTS)
+#ifndef KOFFT_SPLIT_ZSLOTS
+#define KOFFT_SPLIT_ZSLOTS 4
+#endif
+constexpr int kSplitZSlots = KOFFT_SPLIT_ZSLOTS; // irfft at 2^15: untwisted rows per team (Split32::ZSLOTS)
 struct SplitArgs {
     float2 v0[32] = {};        // pass-0 twiddles: v[(2^t - 1) + c] = T[c << (L-1-t)]  (Tw0W)
     float2 *scratch = nullptr; // max_teams * kSplitSlots * 2^L complex (stays in L2)
     unsigned *flags = nullptr; // max_teams * kPipeFlagStride counters
     int max_teams = 0;
     bool persist_l2 = false;   // mark the intermediate as a persisting-L2 access window for this launch
+    bool pre_rows = false;     // scratch has room for max_teams * kSplitZSlots * 2^L more (irfft at 2^15: untwisted rows)
 };
 cudaError_t launch_split32_fft(int L, const LaunchArgs &a, SplitArgs &g);
 

@@ -134,6 +134,17 @@ inline void named_barrier(int id, int nthreads)
     while (b.generation == gen) yield_to_scheduler();
 }
 
+// bar.arrive id, nthreads: counts without waiting
+inline void named_barrier_arrive(int id, int nthreads)
+{
+    Scheduler *s = g_sched;
+    NamedBar &b = s->blocks[s->threads[s->current].block].named[id & 15];
+    if (++b.arrived == nthreads) {
+        b.arrived = 0;
+        b.generation++;
+    }
+}
+
 inline WarpState &my_warp()
 {
     Scheduler *s = g_sched;

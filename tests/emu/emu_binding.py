@@ -182,7 +182,9 @@ EmuKernels.istft_fused = _istft_fused
 
 def load_kernels() -> EmuKernels:
     if _stale_k():
-        subprocess.run(["g++", "-O1", "-DKOFFT_EMU", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-shared",
+        # KOFFT_EMU_DEFS: build-time knobs of the kernels under test (e.g. "-DKOFFT_SPLIT_LAZY_BAR2=1")
+        subprocess.run(["g++", "-O1", "-DKOFFT_EMU", *os.environ.get("KOFFT_EMU_DEFS", "").split(), "-ffp-contract=off",
+                        "-fno-fast-math", "-std=c++17", "-shared",
                         "-fPIC", "-fvisibility=hidden", "-I", _HERE, "-o", _SOK, _SRCK], check=True)
     lib = C.CDLL(_SOK)
     _bind_istft(lib)

@@ -256,10 +256,10 @@ API int kofft_emuk_large(int kind, int exact, int L, long rows, const void *in, 
 // of a team run as interleaved coroutines so the A-role / B-role dependency flags are live
 static bool g_split_staged = false;
 
-template <int LA, bool EXACT, class IO, int EPI, bool STAGED>
+template <int LA, bool EXACT, class IO, int EPI, bool STAGED, bool PRE = false>
 static int run_split32_v(const IO &io, const float *table, long rows, int grid)
 {
-    using F = Split32<LA, EXACT, IO, EPI, STAGED>;
+    using F = Split32<LA, EXACT, IO, EPI, STAGED, PRE>;
     const long n = 1L << F::L;
     Tw0W tw0;
     memset(&tw0, 0, sizeof tw0);
@@ -272,7 +272,7 @@ static int run_split32_v(const IO &io, const float *table, long rows, int grid)
     long teams = grid / F::NT;
     if (teams < 1) teams = 1;
     if (teams > rows) teams = rows;
-    std::vector<float2> scratch((size_t)teams * F::SLOTS * n);
+    std::vector<float2> scratch((size_t)teams * (F::SLOTS + (PRE ? F::ZSLOTS : 0)) * n);
     std::vector<unsigned> flags((size_t)teams * F::FLAG_STRIDE, 0u);
     const size_t per = ((F::SMEM_BYTES + 255) / 8 + 15) / 16 * 16;
     std::vector<float2> smem(per * F::NT + 32);
@@ -282,9 +282,14 @@ static int run_split32_v(const IO &io, const float *table, long rows, int grid)
     TmaMap map;
     memset(&map, 0, sizeof map);
     if constexpr (STAGED) { // the [rows * 2^LA][32 complex] view of the input, boxes of 256 rows x 8 complex
-        map.base = io.row_ptr(0);
+        if constexpr (PRE) { // the teams' untwisted rows behind the intermediate
+            map.base = scratch.data() + (size_t)teams * F::SLOTS * n;
+            map.dim1 = (unsigned long long)(teams * F::ZSLOTS) << LA;
+        } else {
+            map.base = io.row_ptr(0);
+            map.dim1 = (unsigned long long)rows << LA;
+        }
         map.dim0 = 64;
-        map.dim1 = (unsigned long long)rows << LA;
         map.stride1 = 256;
         map.box0 = 2 * F::COLS;
         map.box1 = 256;
@@ -315,7 +320,13 @@ static int run_split32_kind(int kind, const Args &q, const float *table, long ro
     case 2: { IoGeneric<false> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_split32<LA, EXACT, IoGeneric<false>, SPLIT_STORE>(io, table, rows, grid); }
     case 3: { IoGeneric<true> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_split32<LA, EXACT, IoGeneric<true>, SPLIT_STORE>(io, table, rows, grid); }
     case 6: { IoRfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n}; return run_split32<LA, EXACT, IoRfft<EXACT>, SPLIT_TWIST>(io, table, rows, grid); }
-    case 7: { IoIrfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n, q.scale}; return run_split32<LA, EXACT, IoIrfft<EXACT>, SPLIT_STORE>(io, table, rows, grid); }
+    case 7: {
+        IoIrfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n, q.scale};
+        if constexpr (LA == 10) {
+            if (g_split_staged) return run_split32_v<LA, EXACT, IoIrfft<EXACT>, SPLIT_STORE, true, true>(io, table, rows, grid);
+        }
+        return run_split32<LA, EXACT, IoIrfft<EXACT>, SPLIT_STORE>(io, table, rows, grid);
+    }
     default: return -2;
     }
 }
