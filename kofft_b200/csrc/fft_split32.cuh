@@ -115,6 +115,18 @@ enum SplitEpilogue : int { SPLIT_STORE = 0, SPLIT_TWIST = 1 };
 #ifndef KOFFT_SPLIT_ZSLOTS
 #define KOFFT_SPLIT_ZSLOTS 4
 #endif
+// irfft (PRE) tuning: transforms the untwist runs ahead of pass A; where a warp announces its untwisted bins (its
+// release fence waits for the stores): 0 right behind them, 2 behind the tile's transposition reads, 1 behind the
+// 32-point rows; 1: evict_last on those stores
+#ifndef KOFFT_SPLIT_ZAHEAD
+#define KOFFT_SPLIT_ZAHEAD 3
+#endif
+#ifndef KOFFT_SPLIT_ZDEFER
+#define KOFFT_SPLIT_ZDEFER 0
+#endif
+#ifndef KOFFT_SPLIT_ZHINT
+#define KOFFT_SPLIT_ZHINT 1
+#endif
 #ifndef KOFFT_SPLIT_WARP_FLAGS
 #define KOFFT_SPLIT_WARP_FLAGS 0
 #endif
@@ -153,7 +165,7 @@ struct Split32 {
     static constexpr int FLAG_STRIDE = 32;        // unsigned per team: cntA[SLOTS], cntB[SLOTS] (PRE: + cntZ, cntZf[ZSLOTS])
     // PRE (irfft): the B warps also untwist the rows (src/rfft.rs:485-498) ZAHEAD transforms ahead of pass A, into
     // ZSLOTS L2-resident rows per team that pass A's tile loads read instead of the caller's input
-    static constexpr int ZSLOTS = KOFFT_SPLIT_ZSLOTS, ZAHEAD = 2;
+    static constexpr int ZSLOTS = KOFFT_SPLIT_ZSLOTS, ZAHEAD = KOFFT_SPLIT_ZAHEAD;
     static_assert(2 * SLOTS + (PRE ? 2 * ZSLOTS : 0) <= FLAG_STRIDE && ZAHEAD < ZSLOTS, "flag line");
 
     // ---- shared memory (float2 units) ----
@@ -446,56 +458,74 @@ struct Split32 {
                 cp_async_commit();
             }
         };
-        auto untwist_row = [&](long j) { // the bins of row j have landed
+        // tile_pending: the copies of the current tile were committed after the bins' (they are the newest group)
+        auto untwist_row = [&](long j, bool tile_pending) {
             if constexpr (PRE) {
                 unsigned *cntZ = cntB + SLOTS, *cntZf = cntZ + ZSLOTS;
-                const L2Policy pol = make_l2_policy();
+                L2Policy pol = make_l2_policy();
+                if (!KOFFT_SPLIT_ZHINT) pol.last = 0x1000000000000000ull; // evict_normal
                 float2 *Z = zs + (j % ZSLOTS) * n;
+                // the warp's 32 entries of T' (L2): requested before anything is waited for
+                float2 ta[16], tm[16];
+#pragma unroll
+                for (int jj = 0; jj < 16; jj++) {
+                    const int kk = kfirst + jj * 32;
+                    ta[jj] = KOFFT_LDG(io.rtw + kk);
+                    tm[jj] = KOFFT_LDG(io.rtw + (kk == 0 ? 0 : (int)n - kk)); // T' has n entries
+                }
                 if (j >= ZSLOTS) {
                     const unsigned want = goal_zfree(j);
                     while (flag_load(cntZf + j % ZSLOTS) < want) nano_sleep(64);
                 }
+                if (tile_pending)
+                    cp_async_wait_but<1>();
+                else
+                    cp_async_wait_all();
 #pragma unroll
-                for (int hb = 0; hb < 2; hb++) {
-                    float2 ta[8], tm[8];
-#pragma unroll
-                    for (int jj = 0; jj < 8; jj++) {
-                        const int kk = kfirst + (hb * 8 + jj) * 32;
-                        ta[jj] = KOFFT_LDG(io.rtw + kk);
-                        tm[jj] = KOFFT_LDG(io.rtw + (kk == 0 ? 0 : (int)n - kk)); // T' has n entries
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < 8; jj++) {
-                        const int kk = kfirst + (hb * 8 + jj) * 32;
-                        const float2 a = xr[(hb * 8 + jj) * 32], b = xr[512 + (hb * 8 + jj) * 32];
-                        if (kk != 0) {
-                            stg_hint(Z + kk, io.untwist(a, b, ta[jj]), pol.last);
-                            stg_hint(Z + ((int)n - kk), io.untwist(b, a, tm[jj]), pol.last);
-                        } else {
-                            const float2 xh = KOFFT_LDG(io.in + (team + j * teams) * (n + 1) + n / 2);
-                            stg_hint(Z, io.untwist0(a, b), pol.last);
-                            stg_hint(Z + n / 2, io.untwist(xh, xh, KOFFT_LDG(io.rtw + n / 2)), pol.last);
-                        }
+                for (int jj = 0; jj < 16; jj++) {
+                    const int kk = kfirst + jj * 32;
+                    const float2 a = xr[jj * 32], b = xr[512 + jj * 32];
+                    if (kk != 0) {
+                        stg_hint(Z + kk, io.untwist(a, b, ta[jj]), pol.last);
+                        stg_hint(Z + ((int)n - kk), io.untwist(b, a, tm[jj]), pol.last);
+                    } else {
+                        const float2 xh = KOFFT_LDG(io.in + (team + j * teams) * (n + 1) + n / 2);
+                        stg_hint(Z, io.untwist0(a, b), pol.last);
+                        stg_hint(Z + n / 2, io.untwist(xh, xh, KOFFT_LDG(io.rtw + n / 2)), pol.last);
                     }
                 }
-                warp_sync(); // orders the warp's stores before lane 0's release
-                if (lane == 0) flag_arrive(cntZ + j % ZSLOTS);
+            }
+        };
+        // the release fence of the announcement waits for the warp's stores: `when` picks where in the iteration it sits
+        auto announce_row = [&](long j, int when) {
+            if constexpr (PRE) {
+                if (when == KOFFT_SPLIT_ZDEFER) {
+                    warp_sync(); // orders the warp's stores before lane 0's release
+                    if (lane == 0) flag_arrive(cntB + SLOTS + j % ZSLOTS);
+                }
             }
         };
         if constexpr (PRE) {
             for (long j = 0; j < ZAHEAD && j < cnt; j++) {
                 fetch_bins(j);
-                cp_async_wait_all();
-                untwist_row(j);
+                untwist_row(j, false);
+                announce_row(j, KOFFT_SPLIT_ZDEFER);
             }
             if (ZAHEAD < cnt) fetch_bins(ZAHEAD);
         }
         bool fetched = false;
         for (long i = 0; i < cnt; i++) {
             const long row = team + i * teams;
-            if (PRE && i + ZAHEAD < cnt) {
-                cp_async_wait_all();
-                untwist_row(i + ZAHEAD);
+            const bool ahead = PRE && i + ZAHEAD < cnt;
+            if (ahead) {
+                // the tile's copies first if pass A is already done with it: their latency hides behind the untwist
+                if (!fetched && warp_all(flag_load(cntA + i % SLOTS) >= goal_a(i))) {
+                    (void)flag_load_acquire(cntA + i % SLOTS);
+                    fetch(i);
+                    fetched = true;
+                }
+                untwist_row(i + ZAHEAD, fetched);
+                announce_row(i + ZAHEAD, 0);
             }
             if (!fetched) {
                 // every lane polls (one broadcast request per iteration): the warp stays converged, which keeps the
@@ -522,10 +552,12 @@ struct Split32 {
                 x[2 * q2 + 1] = make_float2(e.z, e.w);
             }
             warp_sync(); // the region is free again
+            if (ahead) announce_row(i + ZAHEAD, 2);
             // The next tile's rows, if its pass A is already complete: their L2 latency hides behind this tile's epilogue.
             // The flag is loaded here and looked at after the register pass, so its own L2 round trip is hidden too.
             const unsigned nxt = i + 1 < cnt ? flag_load(cntA + (i + 1) % SLOTS) : 0u;
             PB::compute(x, twb);
+            if (ahead) announce_row(i + ZAHEAD, 1);
             fetched = false;
             if (i + 1 < cnt) {
                 if (warp_all(nxt >= goal_a(i + 1))) {

@@ -49,6 +49,11 @@ elif which == "split":  # rfft 2^16 through the warp-specialised split kernel (d
     y = torch.empty((4096, 32769), dtype=torch.complex64, device="cuda")
     for _ in range(6):
         fft.rfft_batch(x, out=y)
+elif which == "isplit":  # irfft 2^16 through the split kernel (the B warps untwist ahead of pass A)
+    x = torch.view_as_complex(torch.rand((4096, 32769, 2), generator=g, device="cuda") * 2 - 1).contiguous()
+    y = torch.empty((4096, 65536), device="cuda")
+    for _ in range(6):
+        fft.irfft_batch(x, 65536, out=y)
 elif which == "rfft":  # the persistent pipelined kernel (16 elements per thread)
     fft.ctx.set_split_min_log2n(16)
     x = (torch.rand((4096, 65536), generator=g, device="cuda") * 2 - 1).contiguous()
