@@ -114,6 +114,7 @@ struct kofft_cuda_ctx {
     // (16 = off).  Cooperative launch; when the device cannot make every CTA resident the older paths compute
     // the same bits and coop_fallbacks counts it.
     int split_min_l = 14;
+    unsigned wide_mask = (1u << 13) | (1u << 14); // bit L: dense C2C rows of 2^L points through the wide single-CTA kernel (KOFFT_WIDE_MASK)
     bool split_irfft = true; // irfft at 2^15 through the split kernel with the untwist in its B warps (KOFFT_SPLIT_IRFFT=0: older path)
     bool split_all_kinds = false; // default: C2C and rfft, where it measured faster; irfft / SoA rows keep the older paths
     unsigned long long coop_fallbacks = 0;
@@ -287,6 +288,19 @@ int dispatch_impl(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, siz
             e = launch_huge_fft(L, a, g);
             if (e != cudaSuccess) return fail_cuda(e, "huge-N kernel launch");
             ctx->launches += g.launches;
+            return KOFFT_OK;
+        }
+        if ((kind == KIND_C2C_FWD || kind == KIND_C2C_INV) && (L == 13 || L == 14) && ((ctx->wide_mask >> L) & 1)) {
+            // dense C2C rows: one CTA per transform, 32 elements per thread, two CTAs per SM at 8192 (fft_wide.cuh)
+            float2 v0[32] = {};
+            for (int tl = 0; tl < 5; tl++)
+                for (int c = 0; c < (1 << tl); c++) {
+                    size_t idx = static_cast<size_t>(c) << (L - 1 - tl);
+                    v0[(1 << tl) - 1 + c] = make_float2(t->host[2 * idx], t->host[2 * idx + 1]);
+                }
+            e = launch_wide_fft(L, a, v0);
+            if (e != cudaSuccess) return fail_cuda(e, "wide kernel launch");
+            ctx->launches += 1;
             return KOFFT_OK;
         }
         // irfft at 2^15 complex points: the split kernel's B warps untwist the rows ahead of pass A (2^13, 2^14 and the
@@ -509,6 +523,7 @@ int kofft_cuda_create(kofft_cuda_ctx **out, int device)
     if (const char *m = getenv("KOFFT_SPLIT_MIN_L"))
         if (atoi(m) >= 13 && atoi(m) <= 16) ctx->split_min_l = atoi(m);
     if (const char *m = getenv("KOFFT_SPLIT_IRFFT")) ctx->split_irfft = atoi(m) != 0;
+    if (const char *m = getenv("KOFFT_WIDE_MASK")) ctx->wide_mask = static_cast<unsigned>(strtoul(m, nullptr, 0));
 
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;

@@ -112,6 +112,9 @@ struct SplitArgs {
     bool pre_rows = false;     // scratch has room for max_teams * kSplitZSlots * 2^L more (irfft at 2^15: untwisted rows)
 };
 cudaError_t launch_split32_fft(int L, const LaunchArgs &a, SplitArgs &g);
+// N = 8192 / 16384, dense C2C rows: one CTA per transform with 32 elements per thread (fft_wide.cuh);
+// v0[(2^t - 1) + c] = T[c << (L-1-t)], t < 5
+cudaError_t launch_wide_fft(int L, const LaunchArgs &a, const float2 *v0);
 
 // power-of-two lengths above 2^16 (fft_huge.cu): 256-point column pass + register passes through two scratch buffers
 constexpr int kHugeMaxLog2 = 27;

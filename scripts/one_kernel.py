@@ -49,6 +49,11 @@ elif which == "split":  # rfft 2^16 through the warp-specialised split kernel (d
     y = torch.empty((4096, 32769), dtype=torch.complex64, device="cuda")
     for _ in range(6):
         fft.rfft_batch(x, out=y)
+elif which == "wide":  # C2C 8192 through the wide single-CTA kernel
+    x = torch.view_as_complex(torch.rand((16384, 8192, 2), generator=g, device="cuda") * 2 - 1).contiguous()
+    y = torch.empty_like(x)
+    for _ in range(6):
+        fft.fft_batch(x, out=y)
 elif which == "isplit":  # irfft 2^16 through the split kernel (the B warps untwist ahead of pass A)
     x = torch.view_as_complex(torch.rand((4096, 32769, 2), generator=g, device="cuda") * 2 - 1).contiguous()
     y = torch.empty((4096, 65536), device="cuda")

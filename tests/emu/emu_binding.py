@@ -67,7 +67,7 @@ def _stale_k() -> bool:
     t = os.path.getmtime(_SOK)
     deps = [_SRCK, os.path.join(_HERE, "cuda_emu.h")] + [
         os.path.join(_CSRC, f) for f in ("hostdev.h", "async_copy.cuh", "fft_engine.cuh", "fft_kernels.cuh",
-                                         "fft_large.cuh", "fft_split32.cuh", "fft_f64.cuh", "istft_fused.cuh", "small_kernels.cuh")]
+                                         "fft_large.cuh", "fft_split32.cuh", "fft_wide.cuh", "fft_f64.cuh", "istft_fused.cuh", "small_kernels.cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -118,6 +118,19 @@ def _split32(self, kind, exact, L, rows, table, inp=None, in2=None, out=None, ou
 
 
 EmuKernels.split32 = _split32
+
+
+def _wide(self, inverse, exact, L, rows, table, inp, out, scale=1.0, grid=2, staged=False):
+    """WideCta::run (fft_wide.cuh): N = 2^L in one CTA of N / 32 threads, 32 elements per thread."""
+    f = self.lib.kofft_emuk_wide
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int]
+    rc = f(int(inverse), int(exact), L, rows, inp.ctypes.data, out.ctypes.data, C.c_float(scale), table.ctypes.data, grid,
+           int(staged))
+    assert rc == 0, rc
+
+
+EmuKernels.wide = _wide
 
 
 def _f64(self, n, rows, inp, out, table, inverse=False, grid=2, staged=False):

@@ -10,6 +10,7 @@
 #include "../../kofft_b200/csrc/fft_f64.cuh"
 #include "../../kofft_b200/csrc/fft_large.cuh"
 #include "../../kofft_b200/csrc/fft_split32.cuh"
+#include "../../kofft_b200/csrc/fft_wide.cuh"
 #include "../../kofft_b200/csrc/small_kernels.cuh"
 #include "../../kofft_b200/csrc/istft_fused.cuh"
 
@@ -344,6 +345,60 @@ API int kofft_emuk_split32(int kind, int exact, int L, long rows, const void *in
     case 15: return exact ? run_split32_kind<10, true>(kind, q, table, rows, grid) : run_split32_kind<10, false>(kind, q, table, rows, grid);
     default: return -1;
     }
+}
+
+// ---- the wide single-CTA kernel (fft_wide.cuh): WideCta::run on `grid` CTAs of N / 32 threads
+static bool g_wide_staged = false;
+template <int L, bool EXACT, class IO, bool STAGED>
+static int run_wide_v(const IO &io, const float *table, long rows, int grid)
+{
+    using F = WideCta<L, EXACT, IO, STAGED>;
+    Tw0W tw0;
+    memset(&tw0, 0, sizeof tw0);
+    for (int tl = 0; tl < 5; tl++)
+        for (int c = 0; c < (1 << tl); c++) {
+            long idx = (long)c << (L - 1 - tl);
+            tw0.v[(1 << tl) - 1 + c] = make_float2(table[2 * idx], table[2 * idx + 1]);
+        }
+    std::vector<float2> smem(F::SMEM_BYTES / 8 + 32);
+    float2 *sm = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
+    const float2 *tab = reinterpret_cast<const float2 *>(table);
+    if (grid > rows) grid = (int)rows;
+    if (grid < 1) grid = 1;
+    const size_t keep = cuda_emu::g_stack_bytes;
+    cuda_emu::g_stack_bytes = 64 * 1024;
+    cuda_emu::launch(grid, F::CTA, [&] { F::run(io, tw0, tab, rows, sm); });
+    cuda_emu::g_stack_bytes = keep;
+    return 0;
+}
+
+template <int L, bool EXACT, class IO>
+static int run_wide(const IO &io, const float *table, long rows, int grid)
+{
+    return g_wide_staged ? run_wide_v<L, EXACT, IO, true>(io, table, rows, grid) : run_wide_v<L, EXACT, IO, false>(io, table, rows, grid);
+}
+
+// kind 0 / 1: C2C forward / inverse; L = 13, 14
+API int kofft_emuk_wide(int kind, int exact, int L, long rows, const void *in, void *out, float scale, const float *table, int grid,
+                        int staged)
+{
+    g_wide_staged = staged != 0;
+    const long n = 1L << L;
+#define WIDE_CASE(LL)                                                                                          \
+    case LL:                                                                                                   \
+        if (kind == 0) {                                                                                       \
+            IoC2C<false> io{(const float2 *)in, (float2 *)out, n, scale};                                      \
+            return exact ? run_wide<LL, true>(io, table, rows, grid) : run_wide<LL, false>(io, table, rows, grid); \
+        } else {                                                                                               \
+            IoC2C<true> io{(const float2 *)in, (float2 *)out, n, scale};                                       \
+            return exact ? run_wide<LL, true>(io, table, rows, grid) : run_wide<LL, false>(io, table, rows, grid); \
+        }
+    switch (L) {
+        WIDE_CASE(13)
+        WIDE_CASE(14)
+    default: return -1;
+    }
+#undef WIDE_CASE
 }
 
 // the real fused istft kernel body (istft_fused.cuh)

@@ -299,6 +299,30 @@ def test_f64_rfft_irfft_kernel_body(emuk, oracle, n):
     assert np.array_equal(z, oracle.irfft_batch_f64(ref, n)), n
 
 
+@pytest.mark.parametrize("L,staged", [(13, False), (13, True), (14, False), (14, True)])
+def test_wide_cta_kernel_body(emuk, oracle, L, staged):
+    """WideCta::run (fft_wide.cuh): N = 8192 / 16384 in one CTA with 32 elements per thread (three register passes, two
+    exchanges in one buffer with two paddings); more rows than CTAs so the buffer is reused.  staged: the row lands by
+    TMA bulk copies in the exchange buffer, pass 0 in place (warp-level swap at 8192).  Bit-exact both ways."""
+    import functools
+
+    emuk_wide = functools.partial(emuk.wide, staged=staged)
+    n = 1 << L
+    rng = np.random.default_rng(1700 + L)
+    rows = 5
+    x = uniform_c64(rng, (rows, n))
+    tab = oracle.twiddles(n)
+    y = np.zeros_like(x)
+    emuk_wide(False, True, L, rows, tab, x, y, grid=2)
+    assert np.array_equal(y, oracle.fft_batch(x))
+    y[...] = 0
+    emuk_wide(True, True, L, rows, tab, x, y, scale=float(np.float32(1) / np.float32(n)), grid=2)
+    assert np.array_equal(y, oracle.fft_batch(x, inverse=True))
+    y[...] = 0
+    emuk_wide(False, False, L, rows, tab, x, y, grid=3)
+    assert rel_l2(y, oracle.fft_batch(x)) <= TOL
+
+
 @pytest.mark.parametrize("L,grid,rows,skew,staged", [(15, 8, 11, None, True), (15, 4, 6, (2, 9), True), (15, 8, 9, (1, 4), False),
                                                      (14, 4, 7, None, False), (14, 2, 6, (1, 5), False), (13, 2, 5, None, False)])
 def test_split32_kernel_body(emuk, oracle, L, grid, rows, skew, staged):
