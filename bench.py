@@ -543,7 +543,9 @@ def run_gpu(args) -> None:
         torch.cuda.synchronize()
         msi = e0.elapsed_time(e1) / reps
         extra["irfft_65536x16384"] = {"ms": msi, "hbm_gbs": algo / msi / 1e6, "frac_of_measured_peak": algo / msi / 1e6 / peak,
-                                      "note": "persistent pipelined kernel (fft_large.cuh), untwist fused into the first load"}
+                                      "note": "split kernel (fft_split32.cuh): its B warps untwist the rows three transforms ahead of "
+                                              "pass A into L2-resident rows that pass A stages by tensor-map copies (older "
+                                              "pipelined path: 4.4 ms)"}
         del yi
         for key, min_l, mode_id, note in (
                 ("rfft_65536x16384_pipelined_16_per_thread_path", 16, 2,
@@ -577,7 +579,11 @@ def run_gpu(args) -> None:
             e1.record()
             torch.cuda.synchronize()
             msc = e0.elapsed_time(e1) / reps
-            extra[f"c2c_{cn}x{crows}"] = {"ms": msc, "gflops": 5.0 * cn * math.log2(cn) * crows / msc / 1e6,
+            kernel_of = {8192: "fft_wide_kernel (32 elements per thread, one CTA per transform, two CTAs per SM)",
+                         16384: "fft_wide_kernel (32 elements per thread, one 512-thread CTA per transform)",
+                         32768: "split32_kernel (warp-specialised, teams of 4 CTAs)",
+                         65536: "colpass_kernel + rowpass_kernel", 1 << 20: "colpass_kernel + 2 x huge_pass_kernel"}
+            extra[f"c2c_{cn}x{crows}"] = {"ms": msc, "kernel": kernel_of[cn], "gflops": 5.0 * cn * math.log2(cn) * crows / msc / 1e6,
                                           "hbm_gbs": 16.0 * cn * crows / msc / 1e6,
                                           "frac_of_measured_peak": 16.0 * cn * crows / msc / 1e6 / peak}
             del xc, yc

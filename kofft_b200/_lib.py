@@ -34,6 +34,7 @@ SIGNATURES = {
     "kofft_cuda_set_large_mode": (_i, [_vp, _i]),
     "kofft_cuda_set_split_min_log2n": (_i, [_vp, _i]),
     "kofft_cuda_set_split_all_kinds": (_i, [_vp, _i]),
+    "kofft_cuda_set_wide_mask": (_i, [_vp, C.c_uint]),
     "kofft_cuda_fallback_count": (C.c_ulonglong, [_vp]),
     "kofft_cuda_set_istft_fusion": (_i, [_vp, _i, _i]),
     "kofft_cuda_twiddles_host_f32": (_i, [_sz, _vp]),

@@ -621,6 +621,12 @@ int kofft_cuda_set_split_all_kinds(kofft_cuda_ctx *ctx, int all_kinds)
     ctx->split_all_kinds = all_kinds != 0;
     return KOFFT_OK;
 }
+int kofft_cuda_set_wide_mask(kofft_cuda_ctx *ctx, unsigned mask)
+{
+    if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
+    ctx->wide_mask = mask;
+    return KOFFT_OK;
+}
 unsigned long long kofft_cuda_fallback_count(const kofft_cuda_ctx *ctx) { return ctx->coop_fallbacks; }
 int kofft_cuda_set_cluster_fusion(kofft_cuda_ctx *ctx, int enable)
 {

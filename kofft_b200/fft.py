@@ -135,6 +135,10 @@ class Context:
         """complex cores of 2^min_log2n .. 2^15 points run the warp-specialised split kernel (default 14; 16 = off)"""
         check(_lib.lib().kofft_cuda_set_split_min_log2n(self.handle, int(min_log2n)))
 
+    def set_wide_mask(self, mask: int) -> None:
+        """bit L: dense C2C rows of 2^L points (L = 13, 14) run the wide single-CTA kernel (default both; 0 = off)"""
+        check(_lib.lib().kofft_cuda_set_wide_mask(self.handle, int(mask)))
+
     def set_split_all_kinds(self, all_kinds: bool) -> None:
         """also route irfft and strided / SoA rows through the split kernel (default: C2C and rfft only)"""
         check(_lib.lib().kofft_cuda_set_split_all_kinds(self.handle, int(bool(all_kinds))))

@@ -30,8 +30,10 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_
     python scripts/one_kernel.py stft > $OUT/ncu_stft.log 2>&1; echo "ncu stft exit $?" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:split32 -s 3 -c 1 -o $OUT/prof_rfft_split \
     python scripts/one_kernel.py split > $OUT/ncu_rfft_split.log 2>&1; echo "ncu rfft (split kernel, default) exit $?" | tee -a $OUT/summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:large_pipe -s 2 -c 1 -o $OUT/prof_rfft_pipe \
-    python scripts/one_kernel.py rfft > $OUT/ncu_rfft_pipe.log 2>&1; echo "ncu rfft (pipelined) exit $?" | tee -a $OUT/summary.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:split32 -s 3 -c 1 -o $OUT/prof_irfft_split \
+    python scripts/one_kernel.py isplit > $OUT/ncu_irfft_split.log 2>&1; echo "ncu irfft (split kernel) exit $?" | tee -a $OUT/summary.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_wide -s 3 -c 1 -o $OUT/prof_wide \
+    python scripts/one_kernel.py wide > $OUT/ncu_wide.log 2>&1; echo "ncu c2c 8192 (wide kernel) exit $?" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:istft_fused -s 2 -c 1 -o $OUT/prof_istft \
     python scripts/one_kernel.py istft > $OUT/ncu_istft.log 2>&1; echo "ncu istft exit $?" | tee -a $OUT/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_f64_kernel -s 2 -c 1 -o $OUT/prof_f64 \
@@ -44,10 +46,10 @@ cat $OUT/kernels.jsonl | tee -a $OUT/summary.txt
 echo "== summaries" | tee -a $OUT/summary.txt
 mkdir -p $OUT/profiles
 python scripts/summarize_ncu.py $TAG prof_c2c c2c --headline >> $OUT/summary.txt 2>&1
-for pair in "prof_stft stft" "prof_rfft_split rfft_split" "prof_rfft_pipe rfft_pipe" "prof_istft istft" "prof_f64 f64"; do
+for pair in "prof_stft stft" "prof_rfft_split rfft_split" "prof_irfft_split irfft_split" "prof_wide c2c8192_wide" "prof_istft istft" "prof_f64 f64"; do
     set -- $pair
     [ -f $OUT/$1.ncu-rep ] && python scripts/summarize_ncu.py $TAG $1 $2 >> $OUT/summary.txt 2>&1
 done
 cp profiles/${TAG}_* profiles/headline_kernel_traffic.json $OUT/profiles/ 2>/dev/null
-for r in prof_stft prof_rfft_split prof_rfft_pipe prof_istft prof_f64; do rm -f $OUT/$r.ncu-rep; done
+for r in prof_stft prof_rfft_split prof_irfft_split prof_wide prof_istft prof_f64; do rm -f $OUT/$r.ncu-rep; done
 du -sh $OUT | tee -a $OUT/summary.txt

@@ -722,7 +722,9 @@ def test_split_kernel_on_device(cuda_fft, cuda_fft_fast, oracle, n):
     try:
         C.set_split_min_log2n(13)
         C.set_split_all_kinds(True)
+        C.set_wide_mask(0)  # dense C2C rows of 8192 / 16384 points would otherwise take the wide single-CTA kernel
         cuda_fft_fast.ctx.set_split_min_log2n(13)
+        cuda_fft_fast.ctx.set_wide_mask(0)
         for max_ctas in (0, 4, 24, 140):
             C.set_max_ctas(max_ctas)
             y = torch.empty_like(x)
@@ -759,7 +761,63 @@ def test_split_kernel_on_device(cuda_fft, cuda_fft_fast, oracle, n):
         C.set_max_ctas(0)
         C.set_split_min_log2n(14)
         C.set_split_all_kinds(False)
+        C.set_wide_mask((1 << 13) | (1 << 14))
         cuda_fft_fast.ctx.set_split_min_log2n(14)
+        cuda_fft_fast.ctx.set_wide_mask((1 << 13) | (1 << 14))
+
+
+@pytest.mark.parametrize("n", [8192, 16384])
+def test_wide_kernel_on_device(cuda_fft, cuda_fft_fast, oracle, n):
+    """The wide single-CTA kernel (fft_wide.cuh; default for dense C2C rows of 8192 / 16384 points): more rows than
+    resident CTAs so every CTA reuses its buffer, grids from one CTA to the full device, both directions, the TMA-staged
+    variant (16-byte aligned rows) and the plain-load variant (rows at an odd complex offset); identical to the
+    split / single-CTA kernels on the whole batch and to the oracle on sampled rows; FAST mode inside the tolerance."""
+    import torch
+
+    rows = 700
+    g = torch.Generator(device="cuda").manual_seed(n + 1)
+    flat = (torch.rand((rows * n + 1, 2), generator=g, device="cuda") * 2 - 1).contiguous()
+    x = torch.view_as_complex(flat[: rows * n]).view(rows, n)
+    xo = torch.view_as_complex(flat[1:]).view(rows, n)  # 8-byte aligned only: plain loads
+    C = cuda_fft.ctx
+    try:
+        outs = []
+        for max_ctas in (0, 1, 37):
+            C.set_max_ctas(max_ctas)
+            y = torch.empty_like(x)
+            for _ in range(2):
+                cuda_fft.fft_batch(x, out=y)
+            torch.cuda.synchronize()
+            outs.append(y)
+        C.set_max_ctas(0)
+        yo = torch.empty((rows, n), dtype=torch.complex64, device="cuda")
+        cuda_fft.fft_batch(xo, out=yo)
+        yi = torch.empty_like(x)
+        cuda_fft.fft_batch(x, out=yi, inverse=True)
+        C.set_wide_mask(0)
+        y_other = torch.empty_like(x)
+        cuda_fft.fft_batch(x, out=y_other)
+        yo_other = torch.empty_like(yo)
+        cuda_fft.fft_batch(xo, out=yo_other)
+        yi_other = torch.empty_like(x)
+        cuda_fft.fft_batch(x, out=yi_other, inverse=True)
+        torch.cuda.synchronize()
+        for y in outs:
+            assert torch.equal(torch.view_as_real(y), torch.view_as_real(y_other))
+        assert torch.equal(torch.view_as_real(yo), torch.view_as_real(yo_other))
+        assert torch.equal(torch.view_as_real(yi), torch.view_as_real(yi_other))
+        pick = [0, 1, 147, 148, 295, 296, 297, rows - 1]
+        xs = x[pick].cpu().numpy()
+        ref = oracle.fft_batch(xs, nthreads=8)
+        assert np.array_equal(outs[0][pick].cpu().numpy(), ref)
+        assert np.array_equal(yi[pick].cpu().numpy(), oracle.fft_batch(xs, inverse=True, nthreads=8))
+        assert np.array_equal(yo[pick].cpu().numpy(), oracle.fft_batch(xo[pick].cpu().numpy(), nthreads=8))
+        z = xs.copy()
+        cuda_fft_fast.fft_batch(z)
+        assert rel_l2(z, ref) <= TOL
+    finally:
+        C.set_max_ctas(0)
+        C.set_wide_mask((1 << 13) | (1 << 14))
 
 
 def test_large_pipelined_many_transforms_per_team_on_device(cuda_fft, oracle):
