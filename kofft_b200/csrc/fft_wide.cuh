@@ -36,6 +36,9 @@ struct WideCta {
     static constexpr int TW1 = 32 * 33;                // [k][33]: 31 twiddles per k, rows on different banks
     static constexpr int SMEM_BYTES = (BUF + TW1 + 2) * 8; // + the mbarrier of the staged row
     static constexpr bool SWAP = P1::LJ == 3;
+    // rfft: the Hermitian twist pairs bin K with bin N - K, which another thread holds: one more exchange through the
+    // buffer (first layout), after which every thread twists and stores its own bins (src/rfft.rs:450-463)
+    static constexpr bool TWIST = IO::kEpilogueExchange;
     static constexpr unsigned ROW_BYTES = N * 8u, PIECE = 16384u;
 
     static KD void issue_row(float2 *buf, const float2 *src, unsigned long long *bar)
@@ -123,7 +126,7 @@ struct WideCta {
             for (int u = 0; u < P2::U; u++)
 #pragma unroll
                 for (int q = 0; q < P2::R; q++) x[u * P2::R + q] = buf[pad_b(P2::src_index(t, u, q))];
-            if constexpr (STAGED) {
+            if constexpr (STAGED && !TWIST) {
                 __syncthreads(); // everyone has read: the next row may land while the last pass runs
                 if (t == 0 && row + gridDim.x < rows) {
                     fence_proxy_async();
@@ -131,10 +134,33 @@ struct WideCta {
                 }
             }
             P2::compute(x, tw2);
+            if constexpr (TWIST) {
+                __syncthreads(); // everyone has read its pass-2 inputs
 #pragma unroll
-            for (int u = 0; u < P2::U; u++)
+                for (int u = 0; u < P2::U; u++)
 #pragma unroll
-                for (int w = 0; w < P2::R; w++) io.store(row, P2::dst_index(t, u, w), x[u * P2::R + w]);
+                    for (int w = 0; w < P2::R; w++) buf[pad_a(P2::dst_index(t, u, w))] = x[u * P2::R + w];
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < P2::U; u++)
+#pragma unroll
+                    for (int w = 0; w < P2::R; w++) {
+                        const int K = P2::dst_index(t, u, w);
+                        io.twist_store(row, K, x[u * P2::R + w], buf[pad_a(K == 0 ? 0 : N - K)]);
+                    }
+                if constexpr (STAGED) {
+                    __syncthreads(); // the mirrors have been read: the next row may land
+                    if (t == 0 && row + gridDim.x < rows) {
+                        fence_proxy_async();
+                        issue_row(buf, io.row_ptr(row + gridDim.x), bar);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < P2::U; u++)
+#pragma unroll
+                    for (int w = 0; w < P2::R; w++) io.store(row, P2::dst_index(t, u, w), x[u * P2::R + w]);
+            }
         }
     }
 };

@@ -1,4 +1,4 @@
-// fft_wide_inst.cu -- instantiates the wide single-CTA kernel (fft_wide.cuh), dense C2C rows of N = 8192 / 16384.
+// fft_wide_inst.cu -- instantiates the wide single-CTA kernel (fft_wide.cuh) for complex cores of N = 8192 / 16384.
 #include "fft_wide.cuh"
 #include "launch.h"
 
@@ -35,7 +35,10 @@ cudaError_t launch_wide_v(const IO &io, const LaunchArgs &a, const float2 *v0)
 template <int L, bool EXACT, class IO>
 cudaError_t launch_wide(const IO &io, const LaunchArgs &a, const float2 *v0)
 {
-    return a.staged ? launch_wide_v<L, EXACT, IO, true>(io, a, v0) : launch_wide_v<L, EXACT, IO, false>(io, a, v0);
+    if constexpr (IoTraits<IO>::kRowPtr) {
+        if (a.staged) return launch_wide_v<L, EXACT, IO, true>(io, a, v0);
+    }
+    return launch_wide_v<L, EXACT, IO, false>(io, a, v0);
 }
 
 template <int L, bool EXACT>
@@ -49,6 +52,24 @@ cudaError_t launch_kind(const LaunchArgs &a, const float2 *v0)
     }
     case KIND_C2C_INV: {
         IoC2C<true> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale};
+        return launch_wide<L, EXACT>(io, a, v0);
+    }
+    case KIND_GEN_FWD: {
+        IoGeneric<false> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2,
+                            q.p0, q.p1, q.p2, q.p3, q.scale};
+        return launch_wide<L, EXACT>(io, a, v0);
+    }
+    case KIND_GEN_INV: {
+        IoGeneric<true> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2,
+                           q.p0, q.p1, q.p2, q.p3, q.scale};
+        return launch_wide<L, EXACT>(io, a, v0);
+    }
+    case KIND_RFFT: {
+        IoRfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n};
+        return launch_wide<L, EXACT>(io, a, v0);
+    }
+    case KIND_IRFFT: {
+        IoIrfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n, q.scale};
         return launch_wide<L, EXACT>(io, a, v0);
     }
     default:

@@ -65,6 +65,9 @@ struct Table {
 
 } // namespace
 
+// default of kofft_cuda_set_wide_mask: bit (L - 13) + 2 g, g = 0 dense C2C, 1 rfft, 2 irfft, 3 SoA / strided rows
+constexpr unsigned kWideDefault = 0x17u; // dense C2C at both lengths; rfft and irfft at 2^13 (measured: profiles/r04r)
+
 struct kofft_cuda_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -114,7 +117,7 @@ struct kofft_cuda_ctx {
     // (16 = off).  Cooperative launch; when the device cannot make every CTA resident the older paths compute
     // the same bits and coop_fallbacks counts it.
     int split_min_l = 14;
-    unsigned wide_mask = (1u << 13) | (1u << 14); // bit L: dense C2C rows of 2^L points through the wide single-CTA kernel (KOFFT_WIDE_MASK)
+    unsigned wide_mask = kWideDefault; // which kinds at 2^13 / 2^14 run the wide single-CTA kernel (kofft_cuda_set_wide_mask)
     bool split_irfft = true; // irfft at 2^15 through the split kernel with the untwist in its B warps (KOFFT_SPLIT_IRFFT=0: older path)
     bool split_all_kinds = false; // default: C2C and rfft, where it measured faster; irfft / SoA rows keep the older paths
     unsigned long long coop_fallbacks = 0;
@@ -290,8 +293,15 @@ int dispatch_impl(kofft_cuda_ctx *ctx, int kind, const IoArgs &io, size_t n, siz
             ctx->launches += g.launches;
             return KOFFT_OK;
         }
-        if ((kind == KIND_C2C_FWD || kind == KIND_C2C_INV) && (L == 13 || L == 14) && ((ctx->wide_mask >> L) & 1)) {
-            // dense C2C rows: one CTA per transform, 32 elements per thread, two CTAs per SM at 8192 (fft_wide.cuh)
+        // wide_mask bit (L - 13) + 2 g, g = 0 dense C2C rows, 1 rfft, 2 irfft, 3 SoA / strided rows
+        const int wide_group = (kind == KIND_C2C_FWD || kind == KIND_C2C_INV) ? 0
+                               : kind == KIND_RFFT                             ? 1
+                               : kind == KIND_IRFFT                            ? 2
+                               : (kind == KIND_GEN_FWD || kind == KIND_GEN_INV) ? 3
+                                                                                : -1;
+        const int wide_bit = wide_group < 0 ? -1 : (L - 13) + 2 * wide_group;
+        if ((L == 13 || L == 14) && wide_bit >= 0 && ((ctx->wide_mask >> wide_bit) & 1)) {
+            // one CTA per transform, 32 elements per thread, two CTAs per SM at 8192 (fft_wide.cuh)
             float2 v0[32] = {};
             for (int tl = 0; tl < 5; tl++)
                 for (int c = 0; c < (1 << tl); c++) {
@@ -624,7 +634,7 @@ int kofft_cuda_set_split_all_kinds(kofft_cuda_ctx *ctx, int all_kinds)
 int kofft_cuda_set_wide_mask(kofft_cuda_ctx *ctx, unsigned mask)
 {
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
-    ctx->wide_mask = mask;
+    ctx->wide_mask = (mask & 0x80000000u) ? kWideDefault : mask;
     return KOFFT_OK;
 }
 unsigned long long kofft_cuda_fallback_count(const kofft_cuda_ctx *ctx) { return ctx->coop_fallbacks; }

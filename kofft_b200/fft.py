@@ -135,9 +135,10 @@ class Context:
         """complex cores of 2^min_log2n .. 2^15 points run the warp-specialised split kernel (default 14; 16 = off)"""
         check(_lib.lib().kofft_cuda_set_split_min_log2n(self.handle, int(min_log2n)))
 
-    def set_wide_mask(self, mask: int) -> None:
-        """bit L: dense C2C rows of 2^L points (L = 13, 14) run the wide single-CTA kernel (default both; 0 = off)"""
-        check(_lib.lib().kofft_cuda_set_wide_mask(self.handle, int(mask)))
+    def set_wide_mask(self, mask: int | None) -> None:
+        """bit (L - 13) + 2 g: cores of 2^L points (L = 13, 14) of group g (0 dense C2C, 1 rfft, 2 irfft, 3 SoA / strided)
+        run the wide single-CTA kernel; None = the default, 0 = off"""
+        check(_lib.lib().kofft_cuda_set_wide_mask(self.handle, 0x80000000 if mask is None else int(mask)))
 
     def set_split_all_kinds(self, all_kinds: bool) -> None:
         """also route irfft and strided / SoA rows through the split kernel (default: C2C and rfft only)"""

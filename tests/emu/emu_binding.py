@@ -120,13 +120,15 @@ def _split32(self, kind, exact, L, rows, table, inp=None, in2=None, out=None, ou
 EmuKernels.split32 = _split32
 
 
-def _wide(self, inverse, exact, L, rows, table, inp, out, scale=1.0, grid=2, staged=False):
-    """WideCta::run (fft_wide.cuh): N = 2^L in one CTA of N / 32 threads, 32 elements per thread."""
+def _wide(self, kind, exact, L, rows, table, inp=None, in2=None, out=None, out2=None, aux=None,
+          p=(0, 0, 0, 0), scale=1.0, grid=2, staged=False):
+    """WideCta::run (fft_wide.cuh): a complex core of 2^L points in one CTA of 2^L / 32 threads, 32 elements per thread."""
     f = self.lib.kofft_emuk_wide
     f.restype = C.c_int
-    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int]
-    rc = f(int(inverse), int(exact), L, rows, inp.ctypes.data, out.ctypes.data, C.c_float(scale), table.ctypes.data, grid,
-           int(staged))
+    f.argtypes = ([C.c_int, C.c_int, C.c_int, C.c_long] + [C.c_void_p] * 5 + [C.c_long] * 4
+                  + [C.c_float, C.c_void_p, C.c_int, C.c_int])
+    rc = f(KIND[kind], int(exact), L, rows, self._ptr(inp), self._ptr(in2), self._ptr(out), self._ptr(out2), self._ptr(aux),
+           *[int(v) for v in p], C.c_float(scale), self._ptr(table), grid, int(staged))
     assert rc == 0, rc
 
 

@@ -378,27 +378,32 @@ static int run_wide(const IO &io, const float *table, long rows, int grid)
     return g_wide_staged ? run_wide_v<L, EXACT, IO, true>(io, table, rows, grid) : run_wide_v<L, EXACT, IO, false>(io, table, rows, grid);
 }
 
-// kind 0 / 1: C2C forward / inverse; L = 13, 14
-API int kofft_emuk_wide(int kind, int exact, int L, long rows, const void *in, void *out, float scale, const float *table, int grid,
-                        int staged)
+template <int L, bool EXACT>
+static int run_wide_kind(int kind, const Args &q, const float *table, long rows, int grid)
+{
+    switch (kind) {
+    case 0: { IoC2C<false> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale}; return run_wide<L, EXACT>(io, table, rows, grid); }
+    case 1: { IoC2C<true> io{(const float2 *)q.in, (float2 *)q.out, q.n, q.scale}; return run_wide<L, EXACT>(io, table, rows, grid); }
+    case 2: { IoGeneric<false> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_wide_v<L, EXACT, IoGeneric<false>, false>(io, table, rows, grid); }
+    case 3: { IoGeneric<true> io{(const float *)q.in, (const float *)q.in2, (float *)q.out, (float *)q.out2, q.p0, q.p1, q.p2, q.p3, q.scale}; return run_wide_v<L, EXACT, IoGeneric<true>, false>(io, table, rows, grid); }
+    case 6: { IoRfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n}; return run_wide<L, EXACT>(io, table, rows, grid); }
+    case 7: { IoIrfft<EXACT> io{(const float2 *)q.in, (float2 *)q.out, (const float2 *)q.aux, q.n, q.scale}; return run_wide_v<L, EXACT, IoIrfft<EXACT>, false>(io, table, rows, grid); }
+    default: return -2;
+    }
+}
+
+// same argument list as kofft_emuk_split32; L = 13, 14 is the length of the complex core
+API int kofft_emuk_wide(int kind, int exact, int L, long rows, const void *in, const void *in2, void *out, void *out2,
+                        const void *aux, long p0, long p1, long p2, long p3, float scale, const float *table,
+                        int grid, int staged)
 {
     g_wide_staged = staged != 0;
-    const long n = 1L << L;
-#define WIDE_CASE(LL)                                                                                          \
-    case LL:                                                                                                   \
-        if (kind == 0) {                                                                                       \
-            IoC2C<false> io{(const float2 *)in, (float2 *)out, n, scale};                                      \
-            return exact ? run_wide<LL, true>(io, table, rows, grid) : run_wide<LL, false>(io, table, rows, grid); \
-        } else {                                                                                               \
-            IoC2C<true> io{(const float2 *)in, (float2 *)out, n, scale};                                       \
-            return exact ? run_wide<LL, true>(io, table, rows, grid) : run_wide<LL, false>(io, table, rows, grid); \
-        }
+    Args q{in, in2, out, out2, aux, 1L << L, p0, p1, p2, p3, scale};
     switch (L) {
-        WIDE_CASE(13)
-        WIDE_CASE(14)
+    case 13: return exact ? run_wide_kind<13, true>(kind, q, table, rows, grid) : run_wide_kind<13, false>(kind, q, table, rows, grid);
+    case 14: return exact ? run_wide_kind<14, true>(kind, q, table, rows, grid) : run_wide_kind<14, false>(kind, q, table, rows, grid);
     default: return -1;
     }
-#undef WIDE_CASE
 }
 
 // the real fused istft kernel body (istft_fused.cuh)

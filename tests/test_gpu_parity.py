@@ -761,9 +761,9 @@ def test_split_kernel_on_device(cuda_fft, cuda_fft_fast, oracle, n):
         C.set_max_ctas(0)
         C.set_split_min_log2n(14)
         C.set_split_all_kinds(False)
-        C.set_wide_mask((1 << 13) | (1 << 14))
+        C.set_wide_mask(None)
         cuda_fft_fast.ctx.set_split_min_log2n(14)
-        cuda_fft_fast.ctx.set_wide_mask((1 << 13) | (1 << 14))
+        cuda_fft_fast.ctx.set_wide_mask(None)
 
 
 @pytest.mark.parametrize("n", [8192, 16384])
@@ -815,9 +815,24 @@ def test_wide_kernel_on_device(cuda_fft, cuda_fft_fast, oracle, n):
         z = xs.copy()
         cuda_fft_fast.fft_batch(z)
         assert rel_l2(z, ref) <= TOL
+        # the other kinds through the same kernel (mask 0xff): rfft with the twist behind one more exchange, irfft with
+        # the untwist at the load, SoA rows; identical to the default paths and to the oracle
+        xr = (torch.rand((rows, 2 * n), generator=g, device="cuda") * 2 - 1).contiguous()
+        C.set_wide_mask(0xFF)
+        yr = cuda_fft.rfft_batch(xr)
+        zr = cuda_fft.irfft_batch(yr, 2 * n)
+        re, im = np.ascontiguousarray(xs[3].real), np.ascontiguousarray(xs[3].imag)
+        cuda_fft.fft_split(re, im)
+        C.set_wide_mask(0)
+        yr0 = cuda_fft.rfft_batch(xr)
+        zr0 = cuda_fft.irfft_batch(yr, 2 * n)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.view_as_real(yr), torch.view_as_real(yr0)) and torch.equal(zr, zr0)
+        assert np.array_equal(yr[pick].cpu().numpy(), oracle.rfft_batch(xr[pick].cpu().numpy(), nthreads=8))
+        assert np.array_equal(re, ref[3].real) and np.array_equal(im, ref[3].imag)
     finally:
         C.set_max_ctas(0)
-        C.set_wide_mask((1 << 13) | (1 << 14))
+        C.set_wide_mask(None)
 
 
 def test_large_pipelined_many_transforms_per_team_on_device(cuda_fft, oracle):

@@ -312,15 +312,32 @@ def test_wide_cta_kernel_body(emuk, oracle, L, staged):
     rows = 5
     x = uniform_c64(rng, (rows, n))
     tab = oracle.twiddles(n)
+    inv_n = float(np.float32(1) / np.float32(n))
     y = np.zeros_like(x)
-    emuk_wide(False, True, L, rows, tab, x, y, grid=2)
+    emuk_wide("c2c_fwd", True, L, rows, tab, inp=x, out=y, grid=2)
     assert np.array_equal(y, oracle.fft_batch(x))
     y[...] = 0
-    emuk_wide(True, True, L, rows, tab, x, y, scale=float(np.float32(1) / np.float32(n)), grid=2)
+    emuk_wide("c2c_inv", True, L, rows, tab, inp=x, out=y, scale=inv_n, grid=2)
     assert np.array_equal(y, oracle.fft_batch(x, inverse=True))
     y[...] = 0
-    emuk_wide(False, False, L, rows, tab, x, y, grid=3)
+    emuk_wide("c2c_fwd", False, L, rows, tab, inp=x, out=y, grid=3)
     assert rel_l2(y, oracle.fft_batch(x)) <= TOL
+    # rfft (twist behind one more exchange), irfft (untwist at the load), SoA rows
+    xr = rng.uniform(-1, 1, (rows, 2 * n)).astype(np.float32)
+    rtw = oracle.rfft_twiddles(n)
+    yr = np.zeros((rows, n + 1), np.complex64)
+    emuk_wide("rfft", True, L, rows, tab, inp=xr, out=yr, aux=rtw, grid=2)
+    ref = oracle.rfft_batch(xr)
+    assert np.array_equal(yr, ref)
+    if not staged:
+        zr = np.zeros((rows, 2 * n), np.float32)
+        emuk_wide("irfft", True, L, rows, tab, inp=ref, out=zr, aux=rtw, scale=inv_n, grid=2)
+        assert np.array_equal(zr, oracle.irfft_batch(ref, 2 * n))
+        re, im = np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag)
+        ore, oim = np.zeros_like(re), np.zeros_like(im)
+        emuk_wide("gen_fwd", True, L, rows, tab, inp=re, in2=im, out=ore, out2=oim, p=(1, n, 1, n), grid=2)
+        want = oracle.fft_batch(x)
+        assert np.array_equal(ore, want.real) and np.array_equal(oim, want.imag)
 
 
 @pytest.mark.parametrize("L,grid,rows,skew,staged", [(15, 8, 11, None, True), (15, 4, 6, (2, 9), True), (15, 8, 9, (1, 4), False),
