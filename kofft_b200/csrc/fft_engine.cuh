@@ -163,6 +163,8 @@ struct Pass {
     }
 
     // r layers of radix-2 butterflies.  tw: per-thread twiddles (p >= 1) or Tw0::v (p == 0).
+    // RE_LAST (p >= 1): the caller uses only the real parts of the results: the last layer computes only those.
+    template <bool RE_LAST = false>
     static KHD void compute(float2 *x, const float2 *tw)
     {
 #pragma unroll
@@ -190,6 +192,8 @@ struct Pass {
                         } else {
                             butterfly<EXACT>(a, b, tw[(1 << tl) - 1 + c_low]);
                         }
+                    } else if (RE_LAST && tl == r - 1) {
+                        butterfly_re<EXACT>(a, b, tw[u * (R - 1) + (1 << tl) - 1 + c_low]);
                     } else {
                         butterfly<EXACT>(a, b, tw[u * (R - 1) + (1 << tl) - 1 + c_low]);
                     }

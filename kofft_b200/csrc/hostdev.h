@@ -130,6 +130,24 @@ KHD void butterfly(float2 &u, float2 &v, const float2 w)
     }
 }
 
+// the real parts only (the last stage of an inverse transform whose caller keeps frame.re, src/stft.rs:144): the same
+// individually rounded products and sums as the .x components above; the .y components are left stale
+template <bool EXACT>
+KHD void butterfly_re(float2 &u, float2 &v, const float2 w)
+{
+    if (EXACT) {
+        float2 p = mul2(v, w); // (v.re w.re, v.im w.im)
+        float t = sub_rn(p.x, p.y);
+        float a = add_rn(u.x, t);
+        v.x = sub_rn(u.x, t);
+        u.x = a;
+    } else {
+        float a = fma_rn(-v.y, w.y, fma_rn(v.x, w.x, u.x));
+        v.x = fma_rn(u.x, 2.0f, -a);
+        u.x = a;
+    }
+}
+
 // twiddle == (1, 0) exactly (table entry 0): v*1 is the identity for finite v
 KHD void butterfly_unit(float2 &u, float2 &v)
 {
