@@ -600,6 +600,35 @@ def run_gpu(args) -> None:
                 extra["c2c_1048576x256"]["gpu_ms_per_transform"] = extra["c2c_1048576x256"]["ms"] / 256
             except Exception as e:  # pragma: no cover
                 extra["c2c_1048576x256"]["cpu_error"] = repr(e)
+        if rank == 0:
+            # ONE transform of 2^20 points, the shape of the reference's own published table (C2C 59.3 ms,
+            # real 66.9 ms per transform on its authors' CPU): device-resident row, and host row in / host row out
+            one_c = torch.view_as_complex(torch.rand((1, 1 << 20, 2), generator=g, device=dev) * 2 - 1).contiguous()
+            one_o = torch.empty_like(one_c)
+            one_r = (torch.rand((1, 1 << 20), generator=g, device=dev) * 2 - 1).contiguous()
+            lat = {}
+            for key, fn in (("c2c_device_us", lambda: fft.fft_batch(one_c, out=one_o)), ("rfft_device_us", lambda: fft.rfft_batch(one_r))):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(20):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                lat[key] = e0.elapsed_time(e1) / 20 * 1e3
+            hrow = (np.random.default_rng(21).uniform(-1, 1, (1, 1 << 20)) + 0j).astype(np.complex64)
+            fft.fft_batch(hrow.copy())
+            ts = []
+            for _ in range(5):
+                hh = hrow.copy()
+                t0 = time.perf_counter()
+                fft.fft_batch(hh)
+                ts.append(time.perf_counter() - t0)
+            lat["c2c_host_call_us_median"] = sorted(ts)[len(ts) // 2] * 1e6
+            lat["published_reference_ms"] = {"c2c": 59.3, "real": 66.9, "source": "BASELINE.md (benchmarks/README.md:67-70), other hardware"}
+            extra["single_transform_1048576"] = lat
+            del one_c, one_o, one_r
         torch.cuda.empty_cache()
 
         # ---- STFT / ISTFT (BASELINE configs[3]); N > 1: the 64 channels are sharded over the ranks ----------------

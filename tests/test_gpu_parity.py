@@ -766,6 +766,20 @@ def test_split_kernel_on_device(cuda_fft, cuda_fft_fast, oracle, n):
         cuda_fft_fast.ctx.set_wide_mask(None)
 
 
+@pytest.mark.parametrize("rows", [1, 2, 3, 5, 38, 149])
+def test_irfft_65536_few_rows_per_team(cuda_fft, oracle, rows):
+    """irfft 2^16 through the split kernel (the B warps untwist three transforms ahead of pass A): fewer transforms per
+    team than the look-ahead, teams without work, one more row than teams; bit-identical to the oracle."""
+    import torch
+
+    rng = np.random.default_rng(6500 + rows)
+    spec = (rng.uniform(-1, 1, (rows, 32769)) + 1j * rng.uniform(-1, 1, (rows, 32769))).astype(np.complex64)
+    back = cuda_fft.irfft_batch(torch.from_numpy(spec).cuda(), 65536)
+    torch.cuda.synchronize()
+    assert np.array_equal(back.cpu().numpy(), oracle.irfft_batch(spec, 65536, nthreads=8))
+    assert cuda_fft.ctx.fallback_count == 0
+
+
 @pytest.mark.parametrize("n", [8192, 16384])
 def test_wide_kernel_on_device(cuda_fft, cuda_fft_fast, oracle, n):
     """The wide single-CTA kernel (fft_wide.cuh; default for dense C2C rows of 8192 / 16384 points): more rows than
@@ -1334,6 +1348,7 @@ def test_persistent_kernels_flag_stress(cuda_fft):
             C.set_large_mode(C.LARGE_TWO_KERNEL)
             ref_r = cuda_fft.rfft_batch(xr).clone()
             ref_c = cuda_fft.fft_batch(xc, out=torch.empty_like(xc)).clone()
+            ref_i = cuda_fft.irfft_batch(ref_r, n).clone()  # (split kernel: rows untwisted by the B warps, their own flags)
             torch.cuda.synchronize()
             for split_min, mode in ((14, C.LARGE_AUTO), (16, C.LARGE_PIPELINED)):
                 C.set_split_min_log2n(split_min)
@@ -1348,6 +1363,8 @@ def test_persistent_kernels_flag_stress(cuda_fft):
                         runs += 2
                         assert torch.equal(torch.view_as_real(y), torch.view_as_real(ref_r)), (n, rows, split_min, max_ctas, rep)
                         assert torch.equal(torch.view_as_real(z), torch.view_as_real(ref_c)), (n, rows, split_min, max_ctas, rep)
+                        if rep < 2:
+                            assert torch.equal(cuda_fft.irfft_batch(ref_r, n), ref_i), (n, rows, split_min, max_ctas, rep)
                 C.set_max_ctas(0)
         torch.cuda.synchronize()
         assert C.fallback_count == fb0
