@@ -65,6 +65,52 @@ __global__ void __launch_bounds__(256) blue_post_kernel(const float2 *__restrict
     }
 }
 
+// ---- T = f64: the same three steps on double2 (every product and sum rounded individually) ----
+__global__ void __launch_bounds__(256) blue_pre_kernel_d(const double2 *__restrict__ x, const double2 *__restrict__ chirp,
+                                                         double2 *__restrict__ a, long n, long m, long rows, int inverse)
+{
+    const long total = rows * m;
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        const long r = idx / m, i = idx - r * m;
+        double2 v = make_double2(0.0, 0.0);
+        if (i < n) {
+            v = x[r * n + i];
+            if (inverse) v.y = -v.y;
+            v = cmul<true>(v, chirp[i]);
+        }
+        a[idx] = v;
+    }
+}
+__global__ void __launch_bounds__(256) blue_mid_kernel_d(double2 *__restrict__ a, const double2 *__restrict__ bfft, long m, long rows)
+{
+    const long total = rows * m;
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        double2 v = cmul<true>(a[idx], bfft[idx & (m - 1)]);
+        v.y = -v.y;
+        a[idx] = v;
+    }
+}
+__global__ void __launch_bounds__(256) blue_post_kernel_d(const double2 *__restrict__ a, const double2 *__restrict__ chirp,
+                                                          double2 *__restrict__ out, long n, long m, long rows, double scale_m,
+                                                          int inverse, double scale_n)
+{
+    const long total = rows * n;
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        const long r = idx / n, i = idx - r * n;
+        double2 v = a[r * m + i];
+        v.y = -v.y;
+        v.x = dmul(v.x, scale_m);
+        v.y = dmul(v.y, scale_m);
+        v = cmul<true>(v, chirp[i]);
+        if (inverse) {
+            v.y = -v.y;
+            v.x = dmul(v.x, scale_n);
+            v.y = dmul(v.y, scale_n);
+        }
+        out[idx] = v;
+    }
+}
+
 // ---- the element-wise steps around a non-power-of-two core in rfft / irfft / stft / istft / strided / split ----
 // (the reference reaches Bluestein from all of them because they call fft.fft(): src/rfft.rs:447, 502,
 // src/stft.rs:102, 141, src/fft.rs:797-809, 1191-1197)
@@ -195,6 +241,24 @@ cudaError_t launch_bluestein_step(int step, const BluesteinArgs &b, bool exact, 
         else
             blue_post_kernel<false><<<grid_for(b.rows * b.n, num_sms), 256, 0, s>>>(b.a, b.chirp, b.out, b.n, b.m, b.rows, b.scale_m,
                                                                                    b.inverse, b.scale_n);
+        break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bluestein_step_f64(int step, const BluesteinArgsD &b, int num_sms, cudaStream_t s)
+{
+    if (b.rows == 0) return cudaSuccess;
+    switch (step) {
+    case 0:
+        blue_pre_kernel_d<<<grid_for(b.rows * b.m, num_sms), 256, 0, s>>>(b.x, b.chirp, b.a, b.n, b.m, b.rows, b.inverse);
+        break;
+    case 1:
+        blue_mid_kernel_d<<<grid_for(b.rows * b.m, num_sms), 256, 0, s>>>(b.a, b.bfft, b.m, b.rows);
+        break;
+    default:
+        blue_post_kernel_d<<<grid_for(b.rows * b.n, num_sms), 256, 0, s>>>(b.a, b.chirp, b.out, b.n, b.m, b.rows, b.scale_m, b.inverse,
+                                                                         b.scale_n);
         break;
     }
     return cudaGetLastError();

@@ -87,6 +87,25 @@ void host_bluestein_chirp(size_t n, size_t m, float *chirp, float *b)
     }
 }
 
+// the same for T = f64 (src/fft.rs:411-433): angle = T::pi() * T::from_f32((i*i) as f32) / T::from_f32(n as f32) -- the square
+// passes through f32 before it is widened -- and expi = f64::sin_cos
+void host_bluestein_chirp_f64(size_t n, size_t m, double *chirp, double *b)
+{
+    for (size_t i = 0; i < 2 * m; ++i) b[i] = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        const double angle = 3.14159265358979323846 * static_cast<double>(static_cast<float>(i * i)) /
+                             static_cast<double>(static_cast<float>(n));
+        chirp[2 * i] = cos(-angle);
+        chirp[2 * i + 1] = sin(-angle);
+        b[2 * i] = cos(angle);
+        b[2 * i + 1] = sin(angle);
+    }
+    for (size_t i = 1; i < n; ++i) {
+        b[2 * (m - i)] = b[2 * i];
+        b[2 * (m - i) + 1] = b[2 * i + 1];
+    }
+}
+
 // build_twiddle_table, reference src/rfft.rs:172-183; `current = current.mul(w)` with
 // Complex::mul unfused (src/num.rs:160-165) or fused under +fma (src/num.rs:173-178)
 void host_rfft_twiddles(size_t m, float *out, bool fma_mul)

@@ -82,6 +82,11 @@ struct kofft_cuda_ctx {
         size_t m = 0;
     };
     std::map<size_t, Blue> blue_tables; // key n (non-power-of-two): the planner's bluestein_cache
+    struct BlueD {
+        double2 *chirp = nullptr, *bfft = nullptr;
+        size_t m = 0;
+    };
+    std::map<size_t, BlueD> blue_tables_f64; // FftPlanner<f64>::bluestein_cache
     bool accurate_tables = false; // true: correctly rounded roots of unity instead of the reference's recurrence
     std::map<std::pair<size_t, int>, Table> rfft_tables; // key (m, fma)
     struct TableD {
@@ -562,6 +567,10 @@ void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
     for (int i = 0; i < kofft_cuda_ctx::kNumWs; i++)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     if (ctx->pipe_flags) cudaFree(ctx->pipe_flags);
+    for (auto &kv : ctx->blue_tables_f64) {
+        cudaFree(kv.second.chirp);
+        cudaFree(kv.second.bfft);
+    }
     for (auto &kv : ctx->fft_tables_f64)
         if (kv.second.dev) cudaFree(kv.second.dev);
     for (auto &kv : ctx->rfft_tables_f64)
@@ -1620,12 +1629,13 @@ int kofft_cuda_twiddles_host_f64(size_t n, double *out)
 namespace {
 // shared by the dense, strided and split f64 entry points: length checks, the device-resident
 // FftPlanner<f64> table, pass-0 twiddles, launch.  a: addressing filled in by the caller.
-int f64_check_len(kofft_cuda_ctx *ctx, size_t n)
+int f64_check_len(kofft_cuda_ctx *ctx, size_t n, bool bluestein_ok = false)
 {
     if (n == 0) return KOFFT_ERR_EMPTY_INPUT; // src/fft.rs:1055-1058
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
-    if (!is_pow2(n))
-        return fail_msg(-static_cast<int>(cudaErrorNotSupported), "f64: non-power-of-two lengths (Bluestein) are not built");
+    if (!is_pow2(n) && !bluestein_ok)
+        return fail_msg(-static_cast<int>(cudaErrorNotSupported),
+                        "f64: non-power-of-two lengths are built for fft / ifft only (not strided / split / real)");
     return KOFFT_OK;
 }
 // the single-CTA f64 kernel covers n <= 8192; dense C2C rows above that make several trips through global memory
@@ -1675,14 +1685,75 @@ int f64_dispatch(kofft_cuda_ctx *ctx, LaunchF64Args &a, size_t n, size_t batch, 
 }
 } // namespace
 
+// Non-power-of-two C2C for T = f64 (src/fft.rs:411-433, 1083-1132): as bluestein_c2c, on double2
+static int bluestein_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch, int inverse,
+                             cudaStream_t s)
+{
+    size_t m = 1;
+    while (m < 2 * n - 1) m <<= 1; // (2n - 1).next_power_of_two()
+    if (m > (size_t(1) << kHugeMaxLog2F64))
+        return fail_msg(-static_cast<int>(cudaErrorNotSupported), "f64: non-power-of-two lengths above 2^25 are not supported");
+    if (batch == 0) return KOFFT_OK;
+    auto it = ctx->blue_tables_f64.find(n);
+    if (it == ctx->blue_tables_f64.end()) {
+        kofft_cuda_ctx::BlueD bt;
+        bt.m = m;
+        std::vector<double> chirp(2 * n), b(2 * m);
+        host_bluestein_chirp_f64(n, m, chirp.data(), b.data());
+        CU(cudaMalloc(&bt.chirp, n * sizeof(double2)));
+        CU(cudaMalloc(&bt.bfft, m * sizeof(double2)));
+        CU(cudaMemcpy(bt.chirp, chirp.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(bt.bfft, b.data(), m * sizeof(double2), cudaMemcpyHostToDevice));
+        int rc = kofft_cuda_fft_c2c_f64(ctx, bt.bfft, bt.bfft, m, 1, 0, ctx->stream); // fft(b), the planner's own transform
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+        it = ctx->blue_tables_f64.emplace(n, bt).first;
+    }
+    const kofft_cuda_ctx::BlueD &bt = it->second;
+    size_t chunk = ctx->istft_ws_limit / (m * sizeof(double2));
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    void *ws = nullptr;
+    int rc = ensure_ws(ctx, 2, chunk * m * sizeof(double2), &ws);
+    if (rc) return rc;
+    rc = ws_acquire(ctx, 2, s);
+    if (rc) return rc;
+    for (size_t r0 = 0; r0 < batch; r0 += chunk) {
+        BluesteinArgsD b;
+        b.rows = static_cast<long>(batch - r0 < chunk ? batch - r0 : chunk);
+        b.x = static_cast<const double2 *>(d_in) + r0 * n;
+        b.out = static_cast<double2 *>(d_out) + r0 * n;
+        b.a = static_cast<double2 *>(ws);
+        b.chirp = bt.chirp;
+        b.bfft = bt.bfft;
+        b.n = static_cast<long>(n);
+        b.m = static_cast<long>(m);
+        b.inverse = inverse ? 1 : 0;
+        b.scale_m = 1.0 / static_cast<double>(static_cast<float>(m)); // T::one() / T::from_f32(m as f32), src/fft.rs:1116
+        b.scale_n = 1.0 / static_cast<double>(static_cast<float>(n)); // src/fft.rs:1167
+        (void)cudaGetLastError();
+        for (int step = 0; step < 3; step++) {
+            cudaError_t e = launch_bluestein_step_f64(step, b, ctx->num_sms, s);
+            if (e != cudaSuccess) return fail_cuda(e, "f64 bluestein step launch");
+            ctx->launches++;
+            if (step < 2) {
+                rc = kofft_cuda_fft_c2c_f64(ctx, b.a, b.a, m, static_cast<size_t>(b.rows), 0, s);
+                if (rc) return rc;
+            }
+        }
+    }
+    return ws_release(ctx, 2, s);
+}
+
 int kofft_cuda_fft_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_t batch, int inverse,
                            void *stream)
 {
-    int rc = f64_check_len(ctx, n);
+    int rc = f64_check_len(ctx, n, true);
     if (rc) return rc;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
+    if (!is_pow2(n)) return bluestein_c2c_f64(ctx, d_in, d_out, n, batch, inverse, s);
     if (n == 1) { // identity for fft; ifft: conj, conj, * (1/1) (src/fft.rs:1139-1141 returns early)
         if (d_in != d_out && batch)
             CU(cudaMemcpyAsync(d_out, d_in, batch * sizeof(double2), cudaMemcpyDeviceToDevice, s));

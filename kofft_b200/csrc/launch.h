@@ -154,6 +154,18 @@ struct BluesteinArgs {
     float scale_m = 1.0f, scale_n = 1.0f;
 };
 cudaError_t launch_bluestein_step(int step, const BluesteinArgs &b, bool exact, int num_sms, cudaStream_t s);
+// the same for ScalarFftImpl<f64> (no FAST variant)
+struct BluesteinArgsD {
+    const double2 *x = nullptr;
+    double2 *out = nullptr;
+    double2 *a = nullptr;
+    const double2 *chirp = nullptr;
+    const double2 *bfft = nullptr;
+    long n = 0, m = 0, rows = 0;
+    int inverse = 0;
+    double scale_m = 1.0, scale_n = 1.0;
+};
+cudaError_t launch_bluestein_step_f64(int step, const BluesteinArgsD &b, int num_sms, cudaStream_t s);
 
 // element-wise steps around a non-power-of-two core (bluestein.cu): the reference's gather / scatter, framing,
 // untwist / twist and real * window loops, one kernel each

@@ -208,13 +208,53 @@ static int kd_plan_ensure(kd_plan *p, size_t n)
     return 0;
 }
 
-/* ScalarFftImpl::<f64>::fft, src/fft.rs:1054-1082 + stockham_fft_with_threshold :642-740.  Power-of-two n
- * only (Bluestein for f64 is outside the path this oracle checks: KO_NON_POW2_NO_STD). */
+static int kd_fft(kd_plan *p, c64 *x, size_t n);
+static void kd_plan_free(kd_plan *p);
+
+/* Bluestein for non-power-of-two n with T = f64 (std builds): FftPlanner::get_bluestein src/fft.rs:411-433 and
+ * ScalarFftImpl::fft src/fft.rs:1083-1132.  angle = T::pi() * T::from_f32((i*i) as f32) / T::from_f32(n as f32): the
+ * square goes through f32 (inexact above 2^24) before it is widened; expi = f64::sin_cos -> libm sin / cos. */
+static int kd_bluestein(kd_plan *p, c64 *x, size_t n)
+{
+    size_t m = 1;
+    while (m < 2 * n - 1) m <<= 1; /* (2n-1).next_power_of_two() */
+    c64 *chirp = (c64 *)malloc(n * sizeof(c64));
+    c64 *b = (c64 *)calloc(m, sizeof(c64));
+    c64 *a = (c64 *)calloc(m, sizeof(c64));
+    if (!chirp || !b || !a) { free(chirp); free(b); free(a); return -1; }
+    for (size_t i = 0; i < n; i++) {
+        double angle = 3.14159265358979323846 * (double)(float)(i * i) / (double)(float)n;
+        chirp[i] = z_new(cos(-angle), sin(-angle));
+        b[i] = z_new(cos(angle), sin(angle));
+    }
+    for (size_t i = 1; i < n; i++) b[m - i] = b[i];
+    kd_plan fresh; memset(&fresh, 0, sizeof fresh);
+    int rc = kd_fft(&fresh, b, m);
+    kd_plan_free(&fresh);
+    if (!rc) {
+        for (size_t i = 0; i < n; i++) a[i] = z_mul(x[i], chirp[i]);
+        rc = kd_fft(p, a, m);
+    }
+    if (!rc) {
+        for (size_t i = 0; i < m; i++) { a[i] = z_mul(a[i], b[i]); a[i].im = -a[i].im; }
+        rc = kd_fft(p, a, m);
+    }
+    if (!rc) {
+        double scale = 1.0 / (double)(float)m; /* T::one() / T::from_f32(m as f32) */
+        for (size_t i = 0; i < m; i++) { a[i].im = -a[i].im; a[i].re = a[i].re * scale; a[i].im = a[i].im * scale; }
+        for (size_t i = 0; i < n; i++) x[i] = z_mul(a[i], chirp[i]);
+    }
+    free(chirp); free(b); free(a);
+    return rc;
+}
+
+/* ScalarFftImpl::<f64>::fft, src/fft.rs:1054-1082 + stockham_fft_with_threshold :642-740; Bluestein for the other
+ * lengths (std build, :1083-1132). */
 static int kd_fft(kd_plan *p, c64 *x, size_t n)
 {
     if (n == 0) return KO_EMPTY_INPUT;
     if (n == 1) return KO_OK;
-    if (!is_pow2(n)) return KO_NON_POW2_NO_STD;
+    if (!is_pow2(n)) return kd_bluestein(p, x, n);
     if (n <= 16) {
         switch (n) {
         case 2: kd_fft2(x); break;

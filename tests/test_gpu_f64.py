@@ -89,8 +89,8 @@ def test_f64_tables_and_errors(fft64, oracle):
     fft64.fft(one)
     fft64.ifft(one)
     assert one[0] == 3 - 2j  # n == 1 is a no-op (src/fft.rs:1059-1061, 1139-1141)
-    with pytest.raises(CudaBackendError):  # Bluestein for f64 is not built
-        fft64.fft(np.zeros(12, np.complex128))
+    with pytest.raises(CudaBackendError):  # f64 Bluestein serves fft / ifft, not the split / strided / real entry points
+        fft64.fft_split(np.zeros(12), np.zeros(12))
     with pytest.raises(CudaBackendError):  # f64 split / strided / real stop at 8192 complex points
         fft64.fft_split(np.zeros(16384), np.zeros(16384))
 
@@ -208,3 +208,30 @@ def test_f64_above_8192(fft64, oracle, log2n):
     out = torch.empty_like(d)
     fft64.fft_batch(d, out=out)
     assert np.array_equal(out.cpu().numpy(), oracle.fft_batch_f64(x, nthreads=4))
+
+
+@pytest.mark.parametrize("n", [3, 5, 6, 12, 100, 1000, 4097, 10007, 70001])
+def test_f64_bluestein_bit_exact(fft64, oracle, n):
+    """ScalarFftImpl<f64>::fft for non-power-of-two n (src/fft.rs:411-433, 1083-1132 with T = f64: the chirp angle's i*i
+    passes through f32; transforms of m = next_pow2(2n - 1) points -- 4097 and up take the multi-pass f64 kernels):
+    both directions, host and device paths, bit-identical to the f64 oracle; close to numpy's DFT."""
+    import torch
+
+    rng = np.random.default_rng(6464 + n)
+    rows = 3 if n < 20000 else 1
+    x = uniform_c128(rng, (rows, n))
+    for inverse in (False, True):
+        ref = oracle.fft_batch_f64(x, inverse=inverse, nthreads=4)
+        y = x.copy()
+        fft64.fft_batch(y, inverse=inverse)
+        assert np.array_equal(y, ref), (n, inverse)
+    d = torch.from_numpy(x).cuda()
+    out = torch.empty_like(d)
+    fft64.fft_batch(d, out=out)
+    got = out.cpu().numpy()
+    assert np.array_equal(got, oracle.fft_batch_f64(x, nthreads=4))
+    want = np.fft.fft(x, axis=1)
+    # as in the reference: m <= 16 runs the literal kernels with their f32 constants; above n = 4096 the f32-rounded
+    # square in the chirp angle limits the accuracy
+    tol = 1e-6 if n <= 8 else (1e-9 if n <= 4097 else 1e-2)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < tol

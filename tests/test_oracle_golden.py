@@ -334,3 +334,19 @@ def test_timing_build_of_the_port_is_bit_identical(oracle):
     w = oracle.hann(2048)
     nf = -(-30000 // 512)
     assert np.array_equal(oracle.stft_batch(sig, w, 512, nf), oracle.stft_batch(sig, w, 512, nf, fast=True))
+
+
+@pytest.mark.parametrize("n", [3, 6, 12, 100, 1000])
+def test_f64_bluestein_restatement(oracle, n):
+    """ScalarFftImpl<f64>::fft for non-power-of-two n (src/fft.rs:411-433, 1083-1132, T = f64): a DFT to the accuracy the
+    reference's own constants allow (m <= 16: f32 literals in the small kernels), ifft round trip, linearity."""
+    rng = np.random.default_rng(640 + n)
+    x = (rng.uniform(-1, 1, (2, n)) + 1j * rng.uniform(-1, 1, (2, n))).astype(np.complex128)
+    y = oracle.fft_batch_f64(x)
+    want = np.fft.fft(x, axis=1)
+    tol = 1e-6 if n <= 8 else 1e-11
+    assert np.linalg.norm(y - want) / np.linalg.norm(want) < tol
+    back = oracle.fft_batch_f64(y, inverse=True)
+    assert np.abs(back - x).max() < (1e-6 if n <= 8 else 1e-10)
+    s = oracle.fft_batch_f64((x[0] + x[1])[None, :])[0]
+    assert np.abs(s - (y[0] + y[1])).max() < (1e-6 if n <= 8 else 1e-10)
