@@ -66,6 +66,7 @@ struct Table {
 } // namespace
 
 // default of kofft_cuda_set_wide_mask: bit (L - 13) + 2 g, g = 0 dense C2C, 1 rfft, 2 irfft, 3 SoA / strided rows
+constexpr size_t kSmallHostBytes = 64 * 1024; // host-pointer C2C calls up to this size run in place on mapped host memory
 constexpr unsigned kWideDefault = 0x17u; // dense C2C at both lengths; rfft and irfft at 2^13 (measured: profiles/r04r)
 
 struct kofft_cuda_ctx {
@@ -122,6 +123,8 @@ struct kofft_cuda_ctx {
     // (16 = off).  Cooperative launch; when the device cannot make every CTA resident the older paths compute
     // the same bits and coop_fallbacks counts it.
     int split_min_l = 14;
+    void *small_host = nullptr, *small_dev = nullptr; // pinned, device-mapped staging of the small host-pointer calls
+    bool small_zero_copy = true;                       // KOFFT_SMALL_ZERO_COPY=0: copy-engine round trip instead
     unsigned wide_mask = kWideDefault; // which kinds at 2^13 / 2^14 run the wide single-CTA kernel (kofft_cuda_set_wide_mask)
     bool split_irfft = true; // irfft at 2^15 through the split kernel with the untwist in its B warps (KOFFT_SPLIT_IRFFT=0: older path)
     bool split_all_kinds = false; // default: C2C and rfft, where it measured faster; irfft / SoA rows keep the older paths
@@ -538,6 +541,7 @@ int kofft_cuda_create(kofft_cuda_ctx **out, int device)
     if (const char *m = getenv("KOFFT_SPLIT_MIN_L"))
         if (atoi(m) >= 13 && atoi(m) <= 16) ctx->split_min_l = atoi(m);
     if (const char *m = getenv("KOFFT_SPLIT_IRFFT")) ctx->split_irfft = atoi(m) != 0;
+    if (const char *m = getenv("KOFFT_SMALL_ZERO_COPY")) ctx->small_zero_copy = atoi(m) != 0;
     if (const char *m = getenv("KOFFT_WIDE_MASK")) ctx->wide_mask = static_cast<unsigned>(strtoul(m, nullptr, 0));
 
     ctx->device = device;
@@ -567,6 +571,7 @@ void kofft_cuda_destroy(kofft_cuda_ctx *ctx)
     for (int i = 0; i < kofft_cuda_ctx::kNumWs; i++)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     if (ctx->pipe_flags) cudaFree(ctx->pipe_flags);
+    if (ctx->small_host) cudaFreeHost(ctx->small_host);
     for (auto &kv : ctx->blue_tables_f64) {
         cudaFree(kv.second.chirp);
         cudaFree(kv.second.bfft);
@@ -1378,6 +1383,20 @@ int kofft_cuda_fft_batch_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, si
                              [&](void *di, void *dout, size_t nr, cudaStream_t s) {
                                  return kofft_cuda_fft_c2c_f32(ctx, di, dout, n, nr, inverse, s);
                              });
+    if (bytes <= kSmallHostBytes && ctx->small_zero_copy) {
+        // latency path (BASELINE configs[0]: one 1024-point transform): the kernel works in place on a pinned,
+        // device-mapped staging buffer -- one launch and one synchronisation, no copy engine round trips
+        if (!ctx->small_host) {
+            CU(cudaHostAlloc(&ctx->small_host, kSmallHostBytes, cudaHostAllocMapped));
+            CU(cudaHostGetDevicePointer(&ctx->small_dev, ctx->small_host, 0));
+        }
+        memcpy(ctx->small_host, data, bytes);
+        rc = kofft_cuda_fft_c2c_f32(ctx, ctx->small_dev, ctx->small_dev, n, batch, inverse, ctx->stream);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+        memcpy(data, ctx->small_host, bytes);
+        return KOFFT_OK;
+    }
     void *d = nullptr;
     rc = host_roundtrip_begin(ctx, data, bytes, 0, &d);
     if (rc) return rc;
