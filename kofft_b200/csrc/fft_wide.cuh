@@ -31,14 +31,19 @@ struct WideCta {
     static_assert(P0::U == 1 && P1::U == 1 && P2::LJ == 0, "pass shapes");
     static constexpr int MIN_BLOCKS = L == 13 ? 2 : 1;
     KHD static constexpr int pad_a(int i) { return i + (i >> 5); }
-    KHD static constexpr int pad_b(int i) { return i + (i >> R2); }
-    static constexpr int BUF = N + (N >> R2) + 8;      // float2; pad_b is the larger layout
+    // second exchange: an XOR swizzle instead of padding (pass 1 stores 16 adjacent elements, pass 2 reads elements
+    // 2^R2 apart: both hit 16 distinct 8-byte banks), so the buffer is exactly one row
+    KHD static constexpr int pad_b(int i) { return i ^ ((i >> 4) & ((1 << R2) - 1)); }
+    static constexpr int BUF = N + (N >> 5) + 8;       // float2; pad_a (plain loads) is the larger layout
     static constexpr int TW1 = 32 * 33;                // [k][33]: 31 twiddles per k, rows on different banks
-    static constexpr int SMEM_BYTES = (BUF + TW1 + 2) * 8; // + the mbarrier of the staged row
-    static constexpr bool SWAP = P1::LJ == 3;
-    // rfft: the Hermitian twist pairs bin K with bin N - K, which another thread holds: one more exchange through the
-    // buffer (first layout), after which every thread twists and stores its own bins (src/rfft.rs:450-463)
+    // rfft: the Hermitian twist pairs bin K with bin N - K, which another thread holds.  Every thread holds 16 bins of the
+    // lower half (c < R/2 in K = b + 1024 c) and the 16 mirrors of other threads' lower bins: the upper bins go through a
+    // side buffer of N/2 elements, then each thread twists both bins of its 16 pairs (src/rfft.rs:450-463).  The main buffer
+    // is free as soon as pass 2 has read its inputs, so the next row's copy overlaps the last pass and the epilogue.
     static constexpr bool TWIST = IO::kEpilogueExchange;
+    static constexpr int SIDE = TWIST ? N / 2 : 0;
+    static constexpr int SMEM_BYTES = (BUF + TW1 + SIDE + 2) * 8; // + the mbarrier of the staged row
+    static constexpr bool SWAP = P1::LJ == 3;
     static constexpr unsigned ROW_BYTES = N * 8u, PIECE = 16384u;
 
     static KD void issue_row(float2 *buf, const float2 *src, unsigned long long *bar)
@@ -63,7 +68,8 @@ struct WideCta {
             tw1s[k * 33 + e] = table[(long)(k + (c << 5)) << (L - 6 - tl)];
         }
         const float2 *tw1 = tw1s + (t >> P1::LJ) * 33;
-        unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + BUF + TW1);
+        float2 *side = smem + BUF + TW1;
+        unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + BUF + TW1 + SIDE);
         unsigned phase = 0;
         if constexpr (STAGED) {
             if (t == 0) {
@@ -126,7 +132,7 @@ struct WideCta {
             for (int u = 0; u < P2::U; u++)
 #pragma unroll
                 for (int q = 0; q < P2::R; q++) x[u * P2::R + q] = buf[pad_b(P2::src_index(t, u, q))];
-            if constexpr (STAGED && !TWIST) {
+            if constexpr (STAGED) {
                 __syncthreads(); // everyone has read: the next row may land while the last pass runs
                 if (t == 0 && row + gridDim.x < rows) {
                     fence_proxy_async();
@@ -135,24 +141,33 @@ struct WideCta {
             }
             P2::compute(x, tw2);
             if constexpr (TWIST) {
-                __syncthreads(); // everyone has read its pass-2 inputs
-#pragma unroll
-                for (int u = 0; u < P2::U; u++)
-#pragma unroll
-                    for (int w = 0; w < P2::R; w++) buf[pad_a(P2::dst_index(t, u, w))] = x[u * P2::R + w];
-                __syncthreads();
+                constexpr int HR = P2::R / 2;
 #pragma unroll
                 for (int u = 0; u < P2::U; u++)
 #pragma unroll
                     for (int w = 0; w < P2::R; w++) {
-                        const int K = P2::dst_index(t, u, w);
-                        io.twist_store(row, K, x[u * P2::R + w], buf[pad_a(K == 0 ? 0 : N - K)]);
+                        const int c = bitrev(w, R2);
+                        if (c >= HR) side[(c - HR) * 1024 + P2::bfly(t, u)] = x[u * P2::R + w];
                     }
-                if constexpr (STAGED) {
-                    __syncthreads(); // the mirrors have been read: the next row may land
-                    if (t == 0 && row + gridDim.x < rows) {
-                        fence_proxy_async();
-                        issue_row(buf, io.row_ptr(row + gridDim.x), bar);
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < P2::U; u++) {
+                    const int b = P2::bfly(t, u);
+#pragma unroll
+                    for (int w = 0; w < P2::R; w++) {
+                        const int c = bitrev(w, R2);
+                        if (c >= HR) continue;
+                        const float2 y = x[u * P2::R + w];
+                        const int K = b + 1024 * c;
+                        if (b == 0 && c == 0) { // bins 0 and N from Y[0]; bin N/2 is its own mirror
+                            io.twist_store(row, 0, y, y);
+                            const float2 h = side[0];
+                            io.twist_store(row, N / 2, h, h);
+                        } else {
+                            const float2 ym = b == 0 ? side[(HR - c) * 1024] : side[(HR - 1 - c) * 1024 + (1024 - b)];
+                            io.twist_store(row, K, y, ym);
+                            io.twist_store(row, N - K, ym, y);
+                        }
                     }
                 }
             } else {
