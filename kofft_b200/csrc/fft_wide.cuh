@@ -16,6 +16,9 @@
 
 namespace kofft {
 
+template <class IO> struct IsIrfftIo { static constexpr bool value = false; };
+template <bool E> struct IsIrfftIo<IoIrfft<E>> { static constexpr bool value = true; };
+
 // STAGED: the row arrives by TMA bulk copies in the exchange buffer itself while the previous row's last pass runs; pass 0
 // is then in place in index space (thread t reads and writes positions t + q N/32).  At N = 8192 pass 1 reads 8 adjacent
 // elements per group k, so two k would share banks: output c of thread t is stored in the slot of thread t ^ 8 when c is
@@ -44,6 +47,11 @@ struct WideCta {
     static constexpr int SIDE = TWIST ? N / 2 : 0;
     static constexpr int SMEM_BYTES = (BUF + TW1 + SIDE + 2) * 8; // + the mbarrier of the staged row
     static constexpr bool SWAP = P1::LJ == 3;
+    // irfft: the rows of N + 1 bins are only 8-byte aligned and the untwist (src/rfft.rs:485-498) pairs bin e with bin N - e,
+    // which another thread loads: the raw row is staged in the buffer by 8-byte asynchronous copies (issued, like the bulk
+    // copies of the STAGED variant, as soon as pass 2 has read its inputs), every thread untwists its 32 elements from the
+    // staged bins, and pass 0 then runs in place as in the STAGED variant
+    static constexpr bool UNTW = IsIrfftIo<IO>::value;
     static constexpr unsigned ROW_BYTES = N * 8u, PIECE = 16384u;
 
     static KD void issue_row(float2 *buf, const float2 *src, unsigned long long *bar)
@@ -71,29 +79,52 @@ struct WideCta {
         float2 *side = smem + BUF + TW1;
         unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + BUF + TW1 + SIDE);
         unsigned phase = 0;
-        if constexpr (STAGED) {
+        if constexpr (STAGED && !UNTW) {
             if (t == 0) {
                 mbar_init(bar, 1);
                 fence_mbar_init();
             }
         }
         __syncthreads();
-        if constexpr (STAGED) {
+        if constexpr (STAGED && !UNTW) {
             if (t == 0 && (long)blockIdx.x < rows) issue_row(buf, io.row_ptr(blockIdx.x), bar);
         }
+        auto fetch_bins = [&](long r) {
+            if constexpr (UNTW) {
+                const float2 *X = io.in + r * (N + 1);
+#pragma unroll
+                for (int q = 0; q < 32; q++) cp_async8(buf + t + q * CTA, X + t + q * CTA);
+                if (t == 0) cp_async8(buf + N, X + N);
+                cp_async_commit();
+            }
+        };
+        if (UNTW && (long)blockIdx.x < rows) fetch_bins(blockIdx.x);
         // STAGED, pass 1: element q of group k = t >> LJ sits at k N/32 + j + ((q ^ (k & 1)) << LJ) when SWAP
         const int k1 = t >> P1::LJ, sb = SWAP ? (k1 & 1) : 0;
         const float2 *s1e = buf + (k1 << (L - 5)) + (t & (P1::J - 1)) + (sb << P1::LJ);
         const float2 *s1o = buf + (k1 << (L - 5)) + (t & (P1::J - 1)) - (sb << P1::LJ);
         for (long row = blockIdx.x; row < rows; row += gridDim.x) {
             float2 x[WIDE];
-            if constexpr (STAGED) {
-                mbar_wait(bar, phase);
-                phase ^= 1;
+            if constexpr (STAGED || UNTW) {
+                if constexpr (UNTW) {
+                    cp_async_wait_all();
+                    __syncthreads(); // every thread's bins have landed
 #pragma unroll
-                for (int q = 0; q < 32; q++) x[q] = io.from_raw(buf[t + q * CTA]);
+                    for (int q = 0; q < 32; q++) {
+                        const int e = t + q * CTA;
+                        const float2 a = buf[e], xm = buf[N - e];
+                        const float2 v = e == 0 ? io.untwist0(a, xm) : io.untwist(a, xm, KOFFT_LDG(io.rtw + e));
+                        x[q] = io.from_raw(v);
+                    }
+                    __syncthreads(); // the raw bins are consumed: pass 0 may write
+                } else {
+                    mbar_wait(bar, phase);
+                    phase ^= 1;
+#pragma unroll
+                    for (int q = 0; q < 32; q++) x[q] = io.from_raw(buf[t + q * CTA]);
+                }
                 P0::compute(x, tw0.v);
-                if (SWAP) warp_sync(); // the warp has read its positions: they may be rewritten
+                if (SWAP && !UNTW) warp_sync(); // the warp has read its positions: they may be rewritten
 #pragma unroll
                 for (int w = 0; w < 32; w++) {
                     const int c = bitrev(w, 5);
@@ -132,7 +163,10 @@ struct WideCta {
             for (int u = 0; u < P2::U; u++)
 #pragma unroll
                 for (int q = 0; q < P2::R; q++) x[u * P2::R + q] = buf[pad_b(P2::src_index(t, u, q))];
-            if constexpr (STAGED) {
+            if constexpr (UNTW) {
+                __syncthreads(); // everyone has read: the next row's bins may land while the last pass runs
+                if (row + gridDim.x < rows) fetch_bins(row + gridDim.x);
+            } else if constexpr (STAGED) {
                 __syncthreads(); // everyone has read: the next row may land while the last pass runs
                 if (t == 0 && row + gridDim.x < rows) {
                     fence_proxy_async();
