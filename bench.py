@@ -587,6 +587,23 @@ def run_gpu(args) -> None:
                                           "hbm_gbs": 16.0 * cn * crows / msc / 1e6,
                                           "frac_of_measured_peak": 16.0 * cn * crows / msc / 1e6 / peak}
             del xc, yc
+        # rfft / irfft at 2^14 reals (wide single-CTA kernel: twist through a half-row side buffer, untwist from staged bins)
+        mrn, mrb = 16384, 32768
+        xm = (torch.rand((mrb, mrn), generator=g, device=dev) * 2 - 1).contiguous()
+        ym = torch.empty((mrb, mrn // 2 + 1), dtype=torch.complex64, device=dev)
+        for key, fn in (("rfft_16384x32768", lambda: fft.rfft_batch(xm, out=ym)), ("irfft_16384x32768", lambda: fft.irfft_batch(ym, mrn, out=xm))):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            msm = e0.elapsed_time(e1) / reps
+            algom = (4 * mrn + 8 * (mrn // 2 + 1)) * mrb
+            extra[key] = {"ms": msm, "kernel": "fft_wide_kernel", "hbm_gbs": algom / msm / 1e6, "frac_of_measured_peak": algom / msm / 1e6 / peak}
+        del xm, ym
         if rank == 0:  # the reference's own benchmark size N = 2^20 (benchmarks/README.md:5-7) beside the CPU port
             try:
                 from oracle import kofft_oracle as ko
