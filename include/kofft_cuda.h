@@ -180,9 +180,10 @@ int kofft_cuda_fft_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, int inve
 int kofft_cuda_fft_batch_host_f32(kofft_cuda_ctx *ctx, float *data, size_t n, size_t batch, int inverse);
 /* ---- f64 twin: what `impl FftImpl<f64> for CudaFftImpl64` calls (ScalarFftImpl<f64>, src/fft.rs:914-1051
  * behind the same dispatch :1054-1082 and ifft :1134-1174).  Elements are interleaved doubles = #[repr(C)]
- * Complex<f64>.  fft / ifft (kofft_cuda_fft_c2c_f64 and its host twins): every power of two up to 2^26 and, through
- * the reference's Bluestein path with T = f64 (:411-433, 1083-1132), every other length up to 2^25.  The strided /
- * split / real entry points: powers of two up to 8192 complex points; beyond that: negative (not supported). */
+ * Complex<f64>.  Every entry point takes every power of two up to 2^26 complex points and, through the reference's
+ * Bluestein path with T = f64 (:411-433, 1083-1132), every other length up to 2^25: powers of two up to 8192 in one
+ * fused kernel, the rest through the dense C2C core with the reference's own gather / scatter / twist / untwist loops
+ * around it (src/fft.rs:921-933, 1191-1197; src/rfft.rs:425-508).  Beyond that: negative (not supported). */
 /* FftPlanner::<f64>::get_twiddles(n) (src/fft.rs:391-405 with T = f64): n/2 complex doubles */
 int kofft_cuda_twiddles_host_f64(size_t n, double *out);
 /* batched, device pointers, stream-ordered, in place allowed */

@@ -111,6 +111,77 @@ __global__ void __launch_bounds__(256) blue_post_kernel_d(const double2 *__restr
     }
 }
 
+// f64 gather / scatter (src/fft.rs:1191-1197, 921-933; ifft_split :1414-1425), untwist (src/rfft.rs:485-498), twist (:450-463)
+__global__ void __launch_bounds__(256) gather_kernel_d(const double *__restrict__ re, const double *__restrict__ im, long es, long rs,
+                                                       double2 *__restrict__ a, long n, long rows, int neg_im)
+{
+    const long total = rows * n;
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        const long r = idx / n, i = idx - r * n;
+        const double y = im[r * rs + i * es];
+        a[idx] = make_double2(re[r * rs + i * es], neg_im ? -y : y);
+    }
+}
+__global__ void __launch_bounds__(256) scatter_kernel_d(const double2 *__restrict__ a, double *__restrict__ re, double *__restrict__ im,
+                                                        long es, long rs, long n, long rows, int neg_im, double scale)
+{
+    const long total = rows * n;
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        const long r = idx / n, i = idx - r * n;
+        double2 v = a[idx];
+        if (neg_im) { // *i = -*i; *r *= scale; *i *= scale
+            v.y = -v.y;
+            v.x = dmul(v.x, scale);
+            v.y = dmul(v.y, scale);
+        }
+        re[r * rs + i * es] = v.x;
+        im[r * rs + i * es] = v.y;
+    }
+}
+__global__ void __launch_bounds__(256) untwist_kernel_d(const double2 *__restrict__ x, const double2 *__restrict__ rtw,
+                                                        double2 *__restrict__ y, long m, long rows)
+{
+    const long total = rows * m;
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        const long r = idx / m, k = idx - r * m;
+        const double2 *X = x + r * (m + 1);
+        double2 v;
+        if (k == 0) {
+            const double2 x0 = X[0], xm = X[m];
+            v = make_double2(dmul(dadd(x0.x, xm.x), 0.5), dmul(dsub(x0.x, xm.x), 0.5));
+        } else {
+            const double2 a = X[k], q = X[m - k];
+            const double2 b = make_double2(q.x, -q.y);
+            const double2 sum = add2(a, b), diff = sub2(a, b);
+            const double2 tw = rtw[k];
+            const double2 t = cmul<true>(make_double2(tw.x, -tw.y), diff);
+            v = make_double2(dmul(dsub(sum.x, t.y), 0.5), dmul(dadd(sum.y, t.x), 0.5));
+        }
+        y[idx] = v;
+    }
+}
+__global__ void __launch_bounds__(256) twist_kernel_d(const double2 *__restrict__ y, const double2 *__restrict__ rtw,
+                                                      double2 *__restrict__ out, long m, long rows)
+{
+    const long total = rows * (m + 1);
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        const long r = idx / (m + 1), k = idx - r * (m + 1);
+        const double2 *Y = y + r * m;
+        double2 v;
+        if (k == 0 || k == m) {
+            const double2 a = Y[0];
+            v = make_double2(k == 0 ? dadd(a.x, a.y) : dsub(a.x, a.y), 0.0);
+        } else {
+            const double2 a = Y[k], q = Y[m - k];
+            const double2 b = make_double2(q.x, -q.y);
+            const double2 sum = add2(a, b), diff = sub2(a, b);
+            const double2 t = cmul<true>(rtw[k], diff);
+            v = make_double2(dmul(dadd(sum.x, t.y), 0.5), dmul(dsub(sum.y, t.x), 0.5));
+        }
+        out[idx] = v;
+    }
+}
+
 // ---- the element-wise steps around a non-power-of-two core in rfft / irfft / stft / istft / strided / split ----
 // (the reference reaches Bluestein from all of them because they call fft.fft(): src/rfft.rs:447, 502,
 // src/stft.rs:102, 141, src/fft.rs:797-809, 1191-1197)
@@ -260,6 +331,28 @@ cudaError_t launch_bluestein_step_f64(int step, const BluesteinArgsD &b, int num
         blue_post_kernel_d<<<grid_for(b.rows * b.n, num_sms), 256, 0, s>>>(b.a, b.chirp, b.out, b.n, b.m, b.rows, b.scale_m, b.inverse,
                                                                          b.scale_n);
         break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_elementwise_f64(const ElementwiseArgsD &e, int num_sms, cudaStream_t s)
+{
+    if (e.rows == 0 || e.n == 0) return cudaSuccess;
+    switch (e.op) {
+    case EW_GATHER:
+        gather_kernel_d<<<grid_for(e.rows * e.n, num_sms), 256, 0, s>>>(e.re, e.im, e.es, e.rs, e.a, e.n, e.rows, e.neg_im);
+        break;
+    case EW_SCATTER:
+        scatter_kernel_d<<<grid_for(e.rows * e.n, num_sms), 256, 0, s>>>(e.a, e.out_re, e.out_im, e.es, e.rs, e.n, e.rows, e.neg_im, e.scale);
+        break;
+    case EW_UNTWIST:
+        untwist_kernel_d<<<grid_for(e.rows * e.n, num_sms), 256, 0, s>>>(e.x, e.rtw, e.a, e.n, e.rows);
+        break;
+    case EW_TWIST:
+        twist_kernel_d<<<grid_for(e.rows * (e.n + 1), num_sms), 256, 0, s>>>(e.x, e.rtw, e.a, e.n, e.rows);
+        break;
+    default:
+        return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }

@@ -1653,15 +1653,7 @@ int f64_check_len(kofft_cuda_ctx *ctx, size_t n, bool bluestein_ok = false)
     if (n == 0) return KOFFT_ERR_EMPTY_INPUT; // src/fft.rs:1055-1058
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     if (!is_pow2(n) && !bluestein_ok)
-        return fail_msg(-static_cast<int>(cudaErrorNotSupported),
-                        "f64: non-power-of-two lengths are built for fft / ifft only (not strided / split / real)");
-    return KOFFT_OK;
-}
-// the single-CTA f64 kernel covers n <= 8192; dense C2C rows above that make several trips through global memory
-// (fft_huge.cu), the strided / split / real entry points stop at 8192 (16384 reals)
-int f64_check_small(size_t n)
-{
-    if (n > 8192) return fail_msg(-static_cast<int>(cudaErrorNotSupported), "f64: strided / split / real transforms above 8192 complex points are not supported");
+        return fail_msg(-static_cast<int>(cudaErrorNotSupported), "f64: non-power-of-two length in a power-of-two-only path");
     return KOFFT_OK;
 }
 int f64_dispatch(kofft_cuda_ctx *ctx, LaunchF64Args &a, size_t n, size_t batch, int inverse, cudaStream_t s)
@@ -1829,18 +1821,71 @@ int kofft_cuda_fft_c2c_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, s
     return f64_dispatch(ctx, a, n, batch, inverse, s);
 }
 
+namespace {
+// the single-CTA f64 kernel covers powers of two up to 8192; everything else goes through the dense C2C core
+// (kofft_cuda_fft_c2c_f64: multi-pass kernels / Bluestein) with element-wise kernels around it, as the reference's
+// own gather / fft / scatter (src/fft.rs:1191-1197, 921-933) and rfft_direct / irfft_direct (src/rfft.rs:425-508)
+bool f64_needs_dense_core(size_t n) { return !is_pow2(n) || n > 8192; }
+
+// split_inverse: ifft_split's own conj / fft / conj * (1.0 / n as f64) (src/fft.rs:1414-1425)
+int f64_generic_dense(kofft_cuda_ctx *ctx, const double *in_re, const double *in_im, long in_es, long in_rs, double *out_re,
+                      double *out_im, long out_es, long out_rs, size_t n, size_t batch, int inverse, bool split_inverse,
+                      cudaStream_t s)
+{
+    if (batch == 0) return KOFFT_OK;
+    const size_t chunk = rows_per_trip(ctx, n * sizeof(double2), batch);
+    void *buf = nullptr;
+    int rc = ensure_ws(ctx, 5, chunk * n * sizeof(double2), &buf);
+    if (rc) return rc;
+    rc = ws_acquire(ctx, 5, s);
+    if (rc) return rc;
+    for (size_t r0 = 0; r0 < batch; r0 += chunk) {
+        const size_t nr = batch - r0 < chunk ? batch - r0 : chunk;
+        ElementwiseArgsD e;
+        e.op = EW_GATHER;
+        e.n = static_cast<long>(n);
+        e.rows = static_cast<long>(nr);
+        e.re = in_re + r0 * in_rs;
+        e.im = in_im + r0 * in_rs;
+        e.es = in_es;
+        e.rs = in_rs;
+        e.a = static_cast<double2 *>(buf);
+        e.neg_im = split_inverse ? 1 : 0;
+        (void)cudaGetLastError();
+        cudaError_t ce = launch_elementwise_f64(e, ctx->num_sms, s);
+        if (ce != cudaSuccess) return fail_cuda(ce, "f64 gather launch");
+        ctx->launches++;
+        rc = kofft_cuda_fft_c2c_f64(ctx, buf, buf, n, nr, split_inverse ? 0 : inverse, s);
+        if (rc) return rc;
+        e.op = EW_SCATTER;
+        e.out_re = out_re + r0 * out_rs;
+        e.out_im = out_im + r0 * out_rs;
+        e.es = out_es;
+        e.rs = out_rs;
+        e.scale = 1.0 / static_cast<double>(n);
+        ce = launch_elementwise_f64(e, ctx->num_sms, s);
+        if (ce != cudaSuccess) return fail_cuda(ce, "f64 scatter launch");
+        ctx->launches++;
+    }
+    return ws_release(ctx, 5, s);
+}
+} // namespace
+
 // strided rows of interleaved complex doubles (strides / distances in complex elements), as
 // kofft_cuda_fft_strided_f32: FftImpl<f64>::fft_strided / fft_out_of_place_strided (src/fft.rs:1175-1336)
 int kofft_cuda_fft_strided_f64(kofft_cuda_ctx *ctx, const void *d_in, size_t in_stride, size_t in_dist, void *d_out,
                                size_t out_stride, size_t out_dist, size_t n, size_t batch, int inverse, void *stream)
 {
     if (in_stride == 0 || out_stride == 0) return KOFFT_ERR_INVALID_STRIDE;
-    int rc = f64_check_len(ctx, n);
-    if (rc) return rc;
-    rc = f64_check_small(n);
+    int rc = f64_check_len(ctx, n, true);
     if (rc) return rc;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
+    if (f64_needs_dense_core(n))
+        return f64_generic_dense(ctx, static_cast<const double *>(d_in), static_cast<const double *>(d_in) + 1,
+                                 2 * static_cast<long>(in_stride), 2 * static_cast<long>(in_dist), static_cast<double *>(d_out),
+                                 static_cast<double *>(d_out) + 1, 2 * static_cast<long>(out_stride),
+                                 2 * static_cast<long>(out_dist), n, batch, inverse, false, pick_stream(ctx, stream));
     LaunchF64Args a;
     a.generic = true;
     a.in_re = static_cast<const double *>(d_in);
@@ -1858,12 +1903,13 @@ int kofft_cuda_fft_strided_f64(kofft_cuda_ctx *ctx, const void *d_in, size_t in_
 int kofft_cuda_fft_split_f64(kofft_cuda_ctx *ctx, const double *d_in_re, const double *d_in_im, double *d_out_re,
                              double *d_out_im, size_t n, size_t batch, int inverse, void *stream)
 {
-    int rc = f64_check_len(ctx, n);
-    if (rc) return rc;
-    rc = f64_check_small(n);
+    int rc = f64_check_len(ctx, n, true);
     if (rc) return rc;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
+    if (f64_needs_dense_core(n))
+        return f64_generic_dense(ctx, d_in_re, d_in_im, 1, static_cast<long>(n), d_out_re, d_out_im, 1, static_cast<long>(n), n,
+                                 batch, inverse, inverse != 0, pick_stream(ctx, stream));
     LaunchF64Args a;
     a.generic = true;
     a.in_re = d_in_re;
@@ -1902,12 +1948,51 @@ int real_f64(kofft_cuda_ctx *ctx, const void *d_in, void *d_out, size_t n, size_
     if (n == 0) return KOFFT_ERR_EMPTY_INPUT;        // src/rfft.rs:434-436 / 477-479
     if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE;  // :437-439 / 480-482
     const size_t m = n / 2;
-    int rc = f64_check_len(ctx, m);
-    if (rc) return rc;
-    rc = f64_check_small(m);
+    int rc = f64_check_len(ctx, m, true);
     if (rc) return rc;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));
+    if (f64_needs_dense_core(m)) {
+        if (batch == 0) return KOFFT_OK;
+        cudaStream_t s = pick_stream(ctx, stream);
+        const double2 *rtw = nullptr;
+        rc = get_rfft_table_f64(ctx, m, &rtw);
+        if (rc) return rc;
+        ElementwiseArgsD e;
+        e.n = static_cast<long>(m);
+        e.rtw = rtw;
+        (void)cudaGetLastError();
+        if (which == 2) { // untwist into the output rows, ifft(m) in place, unpack = reinterpretation (src/rfft.rs:485-507)
+            e.op = EW_UNTWIST;
+            e.rows = static_cast<long>(batch);
+            e.x = static_cast<const double2 *>(d_in);
+            e.a = static_cast<double2 *>(d_out);
+            cudaError_t ce = launch_elementwise_f64(e, ctx->num_sms, s);
+            if (ce != cudaSuccess) return fail_cuda(ce, "f64 untwist launch");
+            ctx->launches++;
+            return kofft_cuda_fft_c2c_f64(ctx, d_out, d_out, m, batch, 1, s);
+        }
+        // pack = reinterpretation, fft(m) into a workspace, twist (src/rfft.rs:444-463)
+        const size_t chunk = rows_per_trip(ctx, m * sizeof(double2), batch);
+        void *y = nullptr;
+        rc = ensure_ws(ctx, 5, chunk * m * sizeof(double2), &y);
+        if (rc) return rc;
+        rc = ws_acquire(ctx, 5, s);
+        if (rc) return rc;
+        for (size_t r0 = 0; r0 < batch; r0 += chunk) {
+            const size_t nr = batch - r0 < chunk ? batch - r0 : chunk;
+            rc = kofft_cuda_fft_c2c_f64(ctx, static_cast<const double *>(d_in) + r0 * n, y, m, nr, 0, s);
+            if (rc) return rc;
+            e.op = EW_TWIST;
+            e.rows = static_cast<long>(nr);
+            e.x = static_cast<const double2 *>(y);
+            e.a = static_cast<double2 *>(d_out) + r0 * (m + 1);
+            cudaError_t ce = launch_elementwise_f64(e, ctx->num_sms, s);
+            if (ce != cudaSuccess) return fail_cuda(ce, "f64 twist launch");
+            ctx->launches++;
+        }
+        return ws_release(ctx, 5, s);
+    }
     LaunchF64Args a;
     a.real = which;
     a.in = static_cast<const double2 *>(d_in);
@@ -1934,9 +2019,7 @@ int kofft_cuda_rfft_batch_host_f64(kofft_cuda_ctx *ctx, const double *input, siz
 {
     if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
     if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE;
-    int rc = f64_check_len(ctx, n / 2);
-    if (rc) return rc;
-    rc = f64_check_small(n / 2);
+    int rc = f64_check_len(ctx, n / 2, true);
     if (rc) return rc;
     if (batch == 0) return KOFFT_OK;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
@@ -1958,9 +2041,7 @@ int kofft_cuda_irfft_batch_host_f64(kofft_cuda_ctx *ctx, const double *input, si
 {
     if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
     if (n % 2 != 0) return KOFFT_ERR_INVALID_VALUE;
-    int rc = f64_check_len(ctx, n / 2);
-    if (rc) return rc;
-    rc = f64_check_small(n / 2);
+    int rc = f64_check_len(ctx, n / 2, true);
     if (rc) return rc;
     if (batch == 0) return KOFFT_OK;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
@@ -2005,9 +2086,7 @@ int kofft_cuda_fft_split_host_f64(kofft_cuda_ctx *ctx, double *re, size_t re_len
 {
     if (re_len != im_len) return KOFFT_ERR_MISMATCHED_LENGTHS; // src/fft.rs:1366-1368
     const size_t n = re_len;
-    int rc = f64_check_len(ctx, n);
-    if (rc) return rc;
-    rc = f64_check_small(n);
+    int rc = f64_check_len(ctx, n, true);
     if (rc) return rc;
     if (n == 1) return KOFFT_OK; // identity; ifft_split: (negate, negate, * 1/1)
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
@@ -2032,9 +2111,7 @@ int kofft_cuda_fft_strided_host_f64(kofft_cuda_ctx *ctx, double *input, size_t i
     if (stride == 0) return KOFFT_ERR_INVALID_STRIDE;                           // src/fft.rs:1181-1183
     if (n == 0) return KOFFT_OK;                                                // :1185-1187
     if (input_len < (n - 1) * stride + 1) return KOFFT_ERR_MISMATCHED_LENGTHS; // :1188-1190
-    int rc = f64_check_len(ctx, n);
-    if (rc) return rc;
-    rc = f64_check_small(n);
+    int rc = f64_check_len(ctx, n, true);
     if (rc) return rc;
     if (n == 1) return KOFFT_OK;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
@@ -2058,9 +2135,7 @@ int kofft_cuda_fft_out_of_place_strided_host_f64(kofft_cuda_ctx *ctx, const doub
     if (input_len % in_stride != 0 || output_len % out_stride != 0) return KOFFT_ERR_INVALID_STRIDE; // :1270-1272
     const size_t n = input_len / in_stride;
     if (output_len / out_stride != n) return KOFFT_ERR_MISMATCHED_LENGTHS;    // :1274-1276
-    int rc = f64_check_len(ctx, n);
-    if (rc) return rc;
-    rc = f64_check_small(n);
+    int rc = f64_check_len(ctx, n, true);
     if (rc) return rc;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));

@@ -166,6 +166,21 @@ struct BluesteinArgsD {
     double scale_m = 1.0, scale_n = 1.0;
 };
 cudaError_t launch_bluestein_step_f64(int step, const BluesteinArgsD &b, int num_sms, cudaStream_t s);
+// f64 element-wise steps around a dense C2C core that the single-CTA f64 kernel does not cover (n > 8192 or not a power
+// of two): gather / scatter of strided or split rows, rfft twist, irfft untwist (bluestein.cu)
+struct ElementwiseArgsD {
+    int op = 0;                    // EW_GATHER, EW_SCATTER, EW_UNTWIST, EW_TWIST
+    long n = 0, rows = 0;
+    const double *re = nullptr, *im = nullptr;
+    double *out_re = nullptr, *out_im = nullptr;
+    long es = 0, rs = 0;           // element and row strides in doubles
+    double2 *a = nullptr;          // dense rows (gather / untwist / twist: destination; scatter: source)
+    const double2 *x = nullptr;    // untwist: X [rows][m+1]; twist: Y [rows][m]
+    const double2 *rtw = nullptr;
+    int neg_im = 0;                // gather: negate the imaginary parts; scatter: negate them and ...
+    double scale = 1.0;            // ... multiply both parts by this (ifft_split, src/fft.rs:1417-1425)
+};
+cudaError_t launch_elementwise_f64(const ElementwiseArgsD &e, int num_sms, cudaStream_t s);
 
 // element-wise steps around a non-power-of-two core (bluestein.cu): the reference's gather / scatter, framing,
 // untwist / twist and real * window loops, one kernel each

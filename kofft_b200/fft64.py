@@ -1,7 +1,8 @@
 """f64 twin of the plugin surface: `ScalarFftImpl<f64>` / `FftPlanner<f64>` (src/fft.rs:914-1051 behind
 the generic dispatch :1054-1082 and `ifft` :1134-1174), on the GPU through the C ABI's *_f64 entry points.
 
-Power-of-two lengths 1 .. 8192.  Same conventions as `CudaFftImpl`: numpy complex128 arrays go
+Every length the reference takes: powers of two (single-CTA kernel to 8192, multi-pass kernels to 2^26) and, through
+kofft's Bluestein path, the others.  Same conventions as `CudaFftImpl`: numpy complex128 arrays go
 through the host-pointer calls (in place, synchronous), CUDA torch.complex128 tensors through the
 device-pointer call (stream-ordered).  No CPU fallback."""
 from __future__ import annotations

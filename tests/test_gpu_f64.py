@@ -79,7 +79,7 @@ def test_f64_reference_checks(fft64, oracle):
 
 def test_f64_tables_and_errors(fft64, oracle):
     import kofft_b200
-    from kofft_b200.errors import CudaBackendError, EmptyInput
+    from kofft_b200.errors import EmptyInput
 
     for n in (8, 32, 4096, 8192):
         assert np.array_equal(kofft_b200.FftPlanner64().get_twiddles(n), oracle.twiddles_f64(n))
@@ -89,10 +89,6 @@ def test_f64_tables_and_errors(fft64, oracle):
     fft64.fft(one)
     fft64.ifft(one)
     assert one[0] == 3 - 2j  # n == 1 is a no-op (src/fft.rs:1059-1061, 1139-1141)
-    with pytest.raises(CudaBackendError):  # f64 Bluestein serves fft / ifft, not the split / strided / real entry points
-        fft64.fft_split(np.zeros(12), np.zeros(12))
-    with pytest.raises(CudaBackendError):  # f64 split / strided / real stop at 8192 complex points
-        fft64.fft_split(np.zeros(16384), np.zeros(16384))
 
 
 def test_f64_split_strided_surface(fft64, oracle):
@@ -235,3 +231,33 @@ def test_f64_bluestein_bit_exact(fft64, oracle, n):
     # square in the chirp angle limits the accuracy
     tol = 1e-6 if n <= 8 else (1e-9 if n <= 4097 else 1e-2)
     assert np.linalg.norm(got - want) / np.linalg.norm(want) < tol
+
+
+@pytest.mark.parametrize("n", [12, 1000, 16384, 40000])
+def test_f64_split_strided_real_beyond_the_single_cta_range(fft64, oracle, n):
+    """fft_split / ifft_split, fft_strided and rfft / irfft for f64 lengths the single-CTA kernel does not cover (not a
+    power of two, or above 8192 points): the reference's own gather / fft / scatter and pack / fft / twist around the
+    dense core (src/fft.rs:921-933, 1191-1197, 1414-1425; src/rfft.rs:425-508), bit-identical to the f64 oracle."""
+    rng = np.random.default_rng(6500 + n)
+    x = uniform_c128(rng, (1, n))[0]
+    ref = oracle.fft_f64(x)
+    re, im = np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag)
+    fft64.fft_split(re, im)
+    assert np.array_equal(re, ref.real) and np.array_equal(im, ref.imag)
+    # ifft_split: negate, fft_split, negate, * (1.0 / n as f64)
+    re, im = np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag)
+    fft64.ifft_split(re, im)
+    f = oracle.fft_f64(np.conj(x))
+    scale = 1.0 / float(n)
+    assert np.array_equal(re, f.real * scale) and np.array_equal(im, (-f.imag) * scale)
+    # strided, in place: every 2nd element
+    buf = uniform_c128(rng, (1, 2 * n))[0]
+    want = buf.copy()
+    want[::2] = oracle.fft_f64(buf[::2])
+    fft64.fft_strided(buf, 2, np.zeros(n, np.complex128))
+    assert np.array_equal(buf, want)
+    # real transforms of 2 n samples (complex core of n points)
+    xr = rng.uniform(-1, 1, (2, 2 * n))
+    spec = oracle.rfft_batch_f64(xr)
+    assert np.array_equal(fft64.rfft_batch(xr), spec)
+    assert np.array_equal(fft64.irfft_batch(spec, 2 * n), oracle.irfft_batch_f64(spec, 2 * n))
