@@ -135,6 +135,17 @@ def _wide(self, kind, exact, L, rows, table, inp=None, in2=None, out=None, out2=
 EmuKernels.wide = _wide
 
 
+def _wide_bank_audit(self, L, staged):
+    """worst number of extra lanes per 8-byte bank pair over every half-warp exchange access of WideCta<L>"""
+    f = self.lib.kofft_emuk_wide_bank_audit
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int]
+    return f(L, int(staged))
+
+
+EmuKernels.wide_bank_audit = _wide_bank_audit
+
+
 def _f64(self, n, rows, inp, out, table, inverse=False, grid=2, staged=False):
     """CtaFftD::run<STAGED> (n >= 32) / the literal kernels (n <= 16) for complex128 rows."""
     self.lib.kofft_emuk_set_f64_staged(int(staged))

@@ -406,6 +406,58 @@ API int kofft_emuk_wide(int kind, int exact, int L, long rows, const void *in, c
     }
 }
 
+// ---- bank audit of the wide kernel's shared-memory exchanges: for every access of a half-warp (16 lanes x 8 bytes) the
+// number of lanes that share an 8-byte bank pair with another lane, using the kernel's own index functions
+template <int L>
+static int wide_bank_audit(int staged)
+{
+    using F = WideCta<L, true, IoC2C<false>, false>;
+    using P0 = typename F::P0;
+    using P1 = typename F::P1;
+    using P2 = typename F::P2;
+    int worst = 0;
+    auto audit = [&](auto addr_of_lane) { // addr_of_lane(lane in 0..15) -> float2 index
+        int cnt[16] = {0};
+        for (int l = 0; l < 16; l++) cnt[addr_of_lane(l) & 15]++;
+        for (int b = 0; b < 16; b++)
+            if (cnt[b] - 1 > worst) worst = cnt[b] - 1;
+    };
+    constexpr int CTA = F::CTA;
+    for (int t0 = 0; t0 < CTA; t0 += 16)
+        for (int q = 0; q < 32; q++) {
+            if (staged) {
+                const int c = bitrev(q, 5);
+                audit([&](int l) { const int t = t0 + l; return t + q * CTA; });                                      // pass-0 load
+                audit([&](int l) { const int t = t0 + l; return ((F::SWAP && (c & 1)) ? (t ^ 8) : t) + c * CTA; });  // pass-0 store
+                audit([&](int l) {                                                                                   // pass-1 load
+                    const int t = t0 + l, k1 = t >> P1::LJ, sb = F::SWAP ? (k1 & 1) : 0;
+                    const int base = (k1 << (L - 5)) + (t & (P1::J - 1));
+                    return base + ((q & 1) ? -(sb << P1::LJ) : (sb << P1::LJ)) + (q << P1::LJ);
+                });
+            } else {
+                audit([&](int l) { return F::pad_a(P0::dst_index(t0 + l, 0, q)); });
+                audit([&](int l) { return F::pad_a(P1::src_index(t0 + l, 0, q)); });
+            }
+            audit([&](int l) { return F::pad_b(P1::dst_index(t0 + l, 0, q)); }); // pass-1 store
+        }
+    for (int t0 = 0; t0 < CTA; t0 += 16)
+        for (int u = 0; u < P2::U; u++)
+            for (int q = 0; q < P2::R; q++) {
+                audit([&](int l) { return F::pad_b(P2::src_index(t0 + l, u, q)); }); // pass-2 load
+                const int c = bitrev(q, F::R2), HR = P2::R / 2;                      // rfft side buffer
+                if (c >= HR)
+                    audit([&](int l) { return (c - HR) * 1024 + P2::bfly(t0 + l, u); });
+                else
+                    audit([&](int l) {
+                        const int b = P2::bfly(t0 + l, u);
+                        return b == 0 ? (HR - c) * 1024 : (HR - 1 - c) * 1024 + (1024 - b);
+                    });
+            }
+    return worst;
+}
+
+API int kofft_emuk_wide_bank_audit(int L, int staged) { return L == 13 ? wide_bank_audit<13>(staged) : (L == 14 ? wide_bank_audit<14>(staged) : -1); }
+
 // the real fused istft kernel body (istft_fused.cuh)
 template <int L, bool EXACT>
 static int run_istft(const IstftFusedArgs &a, const float *table, int grid)

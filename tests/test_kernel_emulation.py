@@ -300,6 +300,14 @@ def test_f64_rfft_irfft_kernel_body(emuk, oracle, n):
 
 
 @pytest.mark.parametrize("L,staged", [(13, False), (13, True), (14, False), (14, True)])
+def test_wide_cta_shared_memory_bank_conflicts(emuk, L, staged):
+    """every exchange access of a half-warp of the wide kernel -- padded or in-place (swapped) first layout, XOR-swizzled
+    second layout, the rfft side buffer -- hits 16 distinct 8-byte bank pairs (enumerated with the kernel's own index
+    functions)"""
+    assert emuk.wide_bank_audit(L, staged) == 0
+
+
+@pytest.mark.parametrize("L,staged", [(13, False), (13, True), (14, False), (14, True)])
 def test_wide_cta_kernel_body(emuk, oracle, L, staged):
     """WideCta::run (fft_wide.cuh): N = 8192 / 16384 in one CTA with 32 elements per thread (three register passes, two
     exchanges in one buffer with two paddings); more rows than CTAs so the buffer is reused.  staged: the row lands by
