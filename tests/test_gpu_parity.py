@@ -1442,3 +1442,41 @@ def test_fast_mode_full_size_rfft_and_stft(cuda_fft, cuda_fft_fast, oracle):
     torch.cuda.synchronize()
     per = (of - oe).double().norm(dim=1) / oe.double().norm(dim=1)
     assert float(per.max()) <= TOL, float(per.max())
+
+
+def test_randomised_differential_against_the_oracle(cuda_fft, oracle):
+    """Seeded random walk over the entry points, lengths (every size class: literal kernels, single-CTA engine, wide
+    kernel, split kernel, multi-pass, Bluestein), batch sizes and directions; each call compared bit for bit with the
+    oracle.  The sizes are bounded so the oracle finishes in seconds."""
+    rng = np.random.default_rng(20261018)
+    pow2 = [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072]
+    other = [3, 5, 6, 7, 12, 24, 100, 255, 1000, 1023, 4097, 10000]
+    for it in range(60):
+        kind = rng.choice(["c2c", "ic2c", "rfft", "irfft", "split", "strided"])
+        n = int(rng.choice(pow2 if rng.random() < 0.7 else other))
+        rows = int(rng.integers(1, 6 if n >= 16384 else 40))
+        tag = (it, kind, n, rows)
+        if kind in ("c2c", "ic2c"):
+            x = uniform_c64(rng, (rows, n))
+            y = x.copy()
+            cuda_fft.fft_batch(y, inverse=(kind == "ic2c"))
+            assert np.array_equal(y, oracle.fft_batch(x, inverse=(kind == "ic2c"), nthreads=4)), tag
+        elif kind == "rfft":
+            xr = rng.uniform(-1, 1, (rows, 2 * n)).astype(np.float32)
+            assert np.array_equal(cuda_fft.rfft_batch(xr), oracle.rfft_batch(xr, nthreads=4)), tag
+        elif kind == "irfft":
+            spec = uniform_c64(rng, (rows, n + 1))
+            assert np.array_equal(cuda_fft.irfft_batch(spec, 2 * n), oracle.irfft_batch(spec, 2 * n, nthreads=4)), tag
+        elif kind == "split":
+            x = uniform_c64(rng, (1, n))[0]
+            re, im = np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag)
+            cuda_fft.fft_split(re, im)
+            ref = oracle.fft_batch(x[None, :])[0]
+            assert np.array_equal(re, ref.real) and np.array_equal(im, ref.imag), tag
+        else:
+            stride = int(rng.integers(2, 5))
+            buf = uniform_c64(rng, (1, n * stride))[0]
+            want = buf.copy()
+            want[::stride] = oracle.fft_batch(buf[::stride][None, :])[0]
+            cuda_fft.fft_strided(buf, stride, np.zeros(n, np.complex64))
+            assert np.array_equal(buf, want), tag
