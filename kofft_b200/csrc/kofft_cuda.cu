@@ -1434,6 +1434,21 @@ int stft_launch_frames(kofft_cuda_ctx *ctx, const float *d_signal, size_t len, s
 {
     // exactly kofft_cuda_stft_f32 without the "enough frames for the whole signal" check: a push emits
     // only the frames that are complete
+    if (!is_pow2(win_len) || win_len > 16384) { // framing kernel, then the C2C core (Bluestein / large-N) in place
+        ElementwiseArgs e;
+        e.op = EW_FRAME;
+        e.n = static_cast<long>(win_len);
+        e.rows = static_cast<long>(channels * nframes);
+        e.re = d_signal;
+        e.aux_f = d_window;
+        e.a = static_cast<float2 *>(d_frames);
+        e.len = static_cast<long>(len);
+        e.nframes = static_cast<long>(nframes);
+        e.hop = static_cast<long>(hop);
+        int rc = elementwise(ctx, e, s);
+        if (rc) return rc;
+        return kofft_cuda_fft_c2c_f32(ctx, d_frames, d_frames, win_len, channels * nframes, 0, s);
+    }
     IoArgs io;
     io.in = d_signal;
     io.aux = d_window;
@@ -1466,7 +1481,7 @@ int kofft_cuda_stft_stream_create(kofft_cuda_ctx *ctx, size_t channels, const fl
 {
     if (!ctx || !out || !window) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null argument");
     if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE; // StftStream::new, src/stft.rs:178-180
-    int rc = check_pow2_len(win_len);
+    int rc = check_fft_len(win_len); // any length: the frames go through fft.fft(), Bluestein included (src/stft.rs:201)
     if (rc) return rc;
     if (channels == 0) return fail_msg(KOFFT_ERR_INVALID_VALUE, "channels == 0");
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
@@ -1559,7 +1574,7 @@ int kofft_cuda_istft_stream_create(kofft_cuda_ctx *ctx, size_t channels, const f
 {
     if (!ctx || !out || !window) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null argument");
     if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE; // IstftStream::new, src/stft.rs:434-436
-    int rc = check_pow2_len(win_len);
+    int rc = check_fft_len(win_len);
     if (rc) return rc;
     if (channels == 0) return fail_msg(KOFFT_ERR_INVALID_VALUE, "channels == 0");
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");

@@ -62,13 +62,12 @@ def test_fft_empty_single_nonpow2(cuda_fft):  # src/lib.rs:313-318, 342-349
     d = c32(1, 2, 3)  # non-power-of-two: Bluestein, like the reference's std build (src/fft.rs:1083-1132)
     cuda_fft.fft(d)
     assert np.allclose(d, np.fft.fft([1, 2, 3]), atol=1e-5)
-    # the rfft / stft cores reach Bluestein too (they call fft.fft(): src/rfft.rs:447, src/stft.rs:102); only the
-    # device-resident streams, built on the power-of-two kernels, refuse
+    # the rfft / stft cores reach Bluestein too (they call fft.fft(): src/rfft.rs:447, src/stft.rs:102), the
+    # device-resident streams included; only the fused magnitude kernel is power-of-two only
     assert cuda_fft.rfft_batch(np.ones((1, 24), np.float32)).shape == (1, 13)
     from kofft_b200 import stft as S
 
-    with pytest.raises(k.NonPowerOfTwoNoStd):
-        S.DeviceStftStream(cuda_fft, 1, np.ones(12, np.float32), 4)
+    S.DeviceStftStream(cuda_fft, 1, np.ones(12, np.float32), 4)
 
 
 def test_fft_out_of_place(cuda_fft, oracle):  # src/lib.rs:281-311, 320-329
@@ -1130,6 +1129,7 @@ def test_ndfft_2d_3d(cuda_fft, oracle):
     (1024, 300, [4096, 1, 1023, 7000]),                   # hop does not divide the window
     (512, 512, [512, 1000, 24]),                          # no overlap
     (256, 700, [300, 1000, 5, 2000, 1, 699, 702]),        # hop > window: samples between frames are skipped across pushes
+    (1000, 250, [999, 1, 4000, 137, 2500]),               # non-power-of-two window: frames through Bluestein
 ])
 def test_device_streams_match_offline(cuda_fft, oracle, win_len, hop, chunks):
     """Device twins of StftStream / IstftStream (src/stft.rs:160-206, 407-520; tests/istft_stream.rs):
