@@ -15,9 +15,9 @@
  *    several trips through global memory (fft_huge.cu).  Non-power-of-two lengths n <= 2^26 take the
  *    reference's Bluestein path (src/fft.rs:411-433, 1083-1132: chirp, two transforms of length
  *    next_pow2(2n-1)) with the same tables and arithmetic -- from fft / ifft and, as in the reference's
- *    std build, from the rfft / irfft / stft / istft / split / strided entry points and the device-resident
- *    streams, which all end in fft.fft().  KOFFT_ERR_NON_POWER_OF_TWO_NO_STD is only returned by the fused
- *    magnitude kernel, which is built on the power-of-two kernels.
+ *    std build, from the rfft / irfft / stft / istft / split / strided / magnitude entry points and the
+ *    device-resident streams, which all end in fft.fft().  KOFFT_ERR_NON_POWER_OF_TWO_NO_STD (the no_std build's
+ *    answer) is therefore never returned.
  *  - Host-pointer functions are synchronous and never retain the caller's pointers.
  *    Device-pointer functions are stream-ordered on `stream`, a cudaStream_t passed as
  *    void* with CUDA's own meaning (NULL = the legacy default stream; kofft_cuda_stream()

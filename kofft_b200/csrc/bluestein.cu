@@ -335,6 +335,23 @@ cudaError_t launch_bluestein_step_f64(int step, const BluesteinArgsD &b, int num
     return cudaGetLastError();
 }
 
+// stft_magnitudes on frames of any length (src/visual/spectrogram.rs:60-73): mags[row][i] = |frame[row][i]| for i < n/2,
+// and the running maximum of all of them (NaN never becomes the maximum)
+__global__ void __launch_bounds__(256) mag_kernel(const float2 *__restrict__ frames, float *__restrict__ mags, int *max_bits, long n,
+                                                  long rows)
+{
+    const long half = n >> 1, total = rows * half;
+    float tmax = 0.0f;
+    for (long idx = blockIdx.x * 256L + threadIdx.x; idx < total; idx += gridDim.x * 256L) {
+        const long r = idx / half, i = idx - r * half;
+        const float2 v = frames[r * n + i];
+        const float mag = sqrt_rn(add_rn(mul_rn(v.x, v.x), mul_rn(v.y, v.y)));
+        mags[idx] = mag;
+        if (mag > tmax) tmax = mag;
+    }
+    if (tmax > 0.0f) atomicMax(max_bits, float_bits(tmax));
+}
+
 cudaError_t launch_elementwise_f64(const ElementwiseArgsD &e, int num_sms, cudaStream_t s)
 {
     if (e.rows == 0 || e.n == 0) return cudaSuccess;
@@ -373,6 +390,10 @@ cudaError_t launch_elementwise(const ElementwiseArgs &e, bool exact, int num_sms
         break;
     case EW_TIME:
         time_kernel<<<g, 256, 0, s>>>(e.a, e.aux_f, e.out_re, e.n, e.rows);
+        break;
+    case EW_MAG:
+        if (e.n < 2) return cudaSuccess;
+        mag_kernel<<<g, 256, 0, s>>>(e.x, e.out_re, e.max_bits, e.n, e.rows);
         break;
     case EW_UNTWIST:
         if (exact)

@@ -465,13 +465,6 @@ int check_fft_len(size_t n)
     if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
     return KOFFT_OK;
 }
-// the device-resident streams and the fused magnitude kernel are built on the power-of-two kernels only
-int check_pow2_len(size_t n)
-{
-    if (n == 0) return KOFFT_ERR_EMPTY_INPUT;
-    if (!is_pow2(n)) return KOFFT_ERR_NON_POWER_OF_TWO_NO_STD;
-    return KOFFT_OK;
-}
 int elementwise(kofft_cuda_ctx *ctx, const ElementwiseArgs &e, cudaStream_t s)
 {
     (void)cudaGetLastError();
@@ -1099,10 +1092,31 @@ int kofft_cuda_stft_magnitudes_f32(kofft_cuda_ctx *ctx, const float *d_signal, s
     cudaStream_t s = pick_stream(ctx, stream);
     CU(cudaMemsetAsync(d_max, 0, channels * sizeof(float), s)); // max_mag starts at 0.0 (spectrogram.rs:64)
     if (nframes == 0) return KOFFT_OK;
-    int rc = check_pow2_len(win_len);
+    int rc = check_fft_len(win_len);
     if (rc) return rc;
-    if (win_len < 32)
-        return fail_msg(-static_cast<int>(cudaErrorNotSupported), "fused stft magnitudes need win_len >= 32");
+    if (!is_pow2(win_len) || win_len < 32 || win_len > 16384) {
+        // frames through the general stft path (Bluestein / literal kernels / large-N core), one channel at a time,
+        // then |.| and the running maximum (src/visual/spectrogram.rs:52-76)
+        void *fr = nullptr;
+        rc = ensure_ws(ctx, 7, nframes * win_len * sizeof(float2), &fr);
+        if (rc) return rc;
+        rc = ws_acquire(ctx, 7, s);
+        if (rc) return rc;
+        for (size_t c = 0; c < channels; c++) {
+            rc = kofft_cuda_stft_f32(ctx, d_signal + c * len, len, 1, d_window, win_len, hop, fr, nframes, s);
+            if (rc) return rc;
+            ElementwiseArgs e;
+            e.op = EW_MAG;
+            e.n = static_cast<long>(win_len);
+            e.rows = static_cast<long>(nframes);
+            e.x = static_cast<const float2 *>(fr);
+            e.out_re = d_mags + c * nframes * (win_len / 2);
+            e.max_bits = reinterpret_cast<int *>(d_max + c);
+            rc = elementwise(ctx, e, s);
+            if (rc) return rc;
+        }
+        return ws_release(ctx, 7, s);
+    }
     const long tpc = tpc_of(win_len, IoTraits<IoStftMag>::kMinCta);
     const bool staged = aligned16(d_signal) && len % 4 == 0 && hop % 4 == 0 && nframes % tpc == 0 &&
                         ((tpc - 1) * static_cast<long>(hop) + static_cast<long>(win_len)) * 4 <= tpc * static_cast<long>(win_len) * kStftStageBytesPerPoint;
@@ -1129,7 +1143,7 @@ int kofft_cuda_stft_magnitudes_host_f32(kofft_cuda_ctx *ctx, const float *sample
 {
     if (hop == 0) return KOFFT_ERR_INVALID_HOP_SIZE;
     if (nframes < (len + hop - 1) / hop) return KOFFT_ERR_MISMATCHED_LENGTHS;
-    int rc = nframes ? check_pow2_len(win_len) : KOFFT_OK;
+    int rc = nframes ? check_fft_len(win_len) : KOFFT_OK;
     if (rc) return rc;
     if (!ctx) return fail_msg(KOFFT_ERR_INVALID_VALUE, "null context");
     CU(cudaSetDevice(ctx->device));

@@ -184,7 +184,7 @@ cudaError_t launch_elementwise_f64(const ElementwiseArgsD &e, int num_sms, cudaS
 
 // element-wise steps around a non-power-of-two core (bluestein.cu): the reference's gather / scatter, framing,
 // untwist / twist and real * window loops, one kernel each
-enum ElementwiseOp : int { EW_GATHER = 0, EW_SCATTER = 1, EW_FRAME = 2, EW_TIME = 3, EW_UNTWIST = 4, EW_TWIST = 5 };
+enum ElementwiseOp : int { EW_GATHER = 0, EW_SCATTER = 1, EW_FRAME = 2, EW_TIME = 3, EW_UNTWIST = 4, EW_TWIST = 5, EW_MAG = 6 };
 struct ElementwiseArgs {
     int op = 0;
     long n = 0, rows = 0;          // core length (twist / untwist: m) and rows
@@ -195,6 +195,7 @@ struct ElementwiseArgs {
     const float2 *x = nullptr;     // untwist: X [rows][m+1]; twist: Y [rows][m]
     const float2 *rtw = nullptr;   // T' (src/rfft.rs:172-183)
     const float *aux_f = nullptr;  // frame / time: window
+    int *max_bits = nullptr;       // mag: running maximum of the rows as float bits (x = frames, out_re = magnitudes)
     long len = 0, nframes = 0, hop = 0;
 };
 cudaError_t launch_elementwise(const ElementwiseArgs &e, bool exact, int num_sms, cudaStream_t s);

@@ -964,9 +964,11 @@ def test_host_pipeline_matches_single_shot(cuda_fft, oracle, chunk_bytes):
         ctx.set_host_pipeline(32 << 20)
 
 
-@pytest.mark.parametrize("win_len,hop,length", [(2048, 512, 100_000), (1024, 256, 33_333), (256, 64, 5000), (4096, 4096, 40_000)])
+@pytest.mark.parametrize("win_len,hop,length", [(2048, 512, 100_000), (1024, 256, 33_333), (256, 64, 5000), (4096, 4096, 40_000),
+                                                 (1000, 250, 20_000), (16, 4, 999), (15, 5, 300)])
 def test_stft_magnitudes_fused(cuda_fft, oracle, win_len, hop, length):
-    """stft_magnitudes (src/visual/spectrogram.rs:52-76) with |X| and max fused behind the FFT."""
+    """stft_magnitudes (src/visual/spectrogram.rs:52-76) with |X| and max fused behind the FFT; windows the fused
+    kernel does not cover (not a power of two, below 32 points) take the general stft path and an |.| / max kernel."""
     import torch
 
     from kofft_b200 import spectrogram as SP
