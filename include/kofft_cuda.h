@@ -94,8 +94,8 @@ int kofft_cuda_set_split_min_log2n(kofft_cuda_ctx *ctx, int min_log2n);
  * older paths, kept for parity testing). */
 int kofft_cuda_set_split_all_kinds(kofft_cuda_ctx *ctx, int all_kinds);
 /* Complex cores of 8192 / 16384 points can run the wide single-CTA kernel (fft_wide.cuh: 32 elements per thread, the row
- * lands by TMA bulk copies in the one exchange buffer, two CTAs per SM at 8192; default: dense C2C and rfft at both
- * lengths, irfft at 2^13).  Bit (L - 13) + 2 g of `mask` enables it
+ * lands by TMA bulk copies in the one exchange buffer, two CTAs per SM at 8192; default: dense C2C, rfft and SoA /
+ * strided rows at both lengths, irfft at 2^13).  Bit (L - 13) + 2 g of `mask` enables it
  * for 2^L-point cores of group g: 0 dense C2C rows, 1 rfft, 2 irfft, 3 SoA / strided rows; a mask with bit 31 set
  * restores the default (the kinds where it measured faster).  0 hands everything back to the split / single-CTA kernels.
  * Bit-identical. */

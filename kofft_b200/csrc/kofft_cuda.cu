@@ -67,7 +67,7 @@ struct Table {
 
 // default of kofft_cuda_set_wide_mask: bit (L - 13) + 2 g, g = 0 dense C2C, 1 rfft, 2 irfft, 3 SoA / strided rows
 constexpr size_t kSmallHostBytes = 64 * 1024; // host-pointer C2C calls up to this size run in place on mapped host memory
-constexpr unsigned kWideDefault = 0x1Fu; // dense C2C and rfft at both lengths, irfft at 2^13 (measured: profiles/r04r, r05a)
+constexpr unsigned kWideDefault = 0xDFu; // dense C2C, rfft and SoA / strided rows at both lengths, irfft at 2^13 (measured: profiles/r04r, r05a, r05e)
 
 struct kofft_cuda_ctx {
     int device = 0;
