@@ -422,6 +422,14 @@ struct IoIrfft {
 #ifndef KOFFT_STFT_BLOCKS
 #define KOFFT_STFT_BLOCKS 0
 #endif
+// copies of the row loop body the compiler lays out (build knob for the STFT: with two copies the per-frame output base
+// is rewritten every other frame, so the stores still reading it delay the loop less)
+#ifndef KOFFT_STFT_UNROLL
+#define KOFFT_STFT_UNROLL 3 // measured (profiles/r05g): 1: 3.86 ms, 2: 3.79, 3: 3.73, 4: 4.00, 5: 4.48 (config 4 shape on 16 channels)
+#endif
+template <class IO> struct RowUnroll { static constexpr int value = 1; };
+template <> struct RowUnroll<IoStft> { static constexpr int value = KOFFT_STFT_UNROLL; };
+
 template <class IO>
 struct IoTraits {
     static constexpr bool kRealInput = false;
@@ -619,6 +627,7 @@ struct CtaFft {
             io.group_init(blockIdx.x, gridDim.x, P::TPC);
             if (tid == 0 && (long)blockIdx.x < groups) stage_issue(io, smem_stage, &mbar, rows);
         }
+#pragma unroll(RowUnroll<IO>::value)
         for (long g = blockIdx.x; g < groups; g += gridDim.x) {
             const long row = g * P::TPC + slot;
             const bool active = row < rows;

@@ -14,6 +14,10 @@
 #pragma once
 #include "fft_split32.cuh"
 
+#ifndef KOFFT_WIDE_UNROLL
+#define KOFFT_WIDE_UNROLL 1
+#endif
+
 namespace kofft {
 
 template <class IO> struct IsIrfftIo { static constexpr bool value = false; };
@@ -46,6 +50,7 @@ struct WideCta {
     static constexpr bool TWIST = IO::kEpilogueExchange;
     static constexpr int SIDE = TWIST ? N / 2 : 0;
     static constexpr int SMEM_BYTES = (BUF + TW1 + SIDE + 2) * 8; // + the mbarrier of the staged row
+    static constexpr int ROW_UNROLL = KOFFT_WIDE_UNROLL; // copies of the row loop body
     static constexpr bool SWAP = P1::LJ == 3;
     // irfft: the rows of N + 1 bins are only 8-byte aligned and the untwist (src/rfft.rs:485-498) pairs bin e with bin N - e,
     // which another thread loads: the raw row is staged in the buffer by 8-byte asynchronous copies (issued, like the bulk
@@ -103,6 +108,7 @@ struct WideCta {
         const int k1 = t >> P1::LJ, sb = SWAP ? (k1 & 1) : 0;
         const float2 *s1e = buf + (k1 << (L - 5)) + (t & (P1::J - 1)) + (sb << P1::LJ);
         const float2 *s1o = buf + (k1 << (L - 5)) + (t & (P1::J - 1)) - (sb << P1::LJ);
+#pragma unroll(ROW_UNROLL)
         for (long row = blockIdx.x; row < rows; row += gridDim.x) {
             float2 x[WIDE];
             if constexpr (STAGED || UNTW) {
