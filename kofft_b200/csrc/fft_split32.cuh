@@ -115,6 +115,12 @@ enum SplitEpilogue : int { SPLIT_STORE = 0, SPLIT_TWIST = 1 };
 #ifndef KOFFT_SPLIT_ZSLOTS
 #define KOFFT_SPLIT_ZSLOTS 4
 #endif
+#ifndef KOFFT_SPLIT_UNROLL_A
+#define KOFFT_SPLIT_UNROLL_A 0 // 0: per kind (see UNROLL_A)
+#endif
+#ifndef KOFFT_SPLIT_UNROLL_B
+#define KOFFT_SPLIT_UNROLL_B 1
+#endif
 // irfft (PRE) tuning: transforms the untwist runs ahead of pass A; where a warp announces its untwisted bins (its
 // release fence waits for the stores): 0 right behind them, 2 behind the tile's transposition reads, 1 behind the
 // 32-point rows; 1: evict_last on those stores
@@ -194,6 +200,10 @@ struct Split32 {
     static constexpr bool HINT = IoTraits<IO>::kHint;
 
     static constexpr int A_WARPS = A_THREADS / 32;
+    // copies of the roles' tile loops.  Measured (profiles/r05h, 2^15): two copies of the A warps' loop take C2C from 1.23 to
+    // 1.18 ms, leave rfft where it is and slow the irfft variant down (4.7 ms); copies of the B warps' loop never help
+    static constexpr int UNROLL_A = KOFFT_SPLIT_UNROLL_A > 0 ? KOFFT_SPLIT_UNROLL_A : ((EPI == SPLIT_STORE && !PRE && LA == 10) ? 2 : 1);
+    static constexpr int UNROLL_B = KOFFT_SPLIT_UNROLL_B;
     static constexpr bool WARP_FLAGS = KOFFT_SPLIT_WARP_FLAGS != 0;
     static constexpr bool LAZY_BAR2 = KOFFT_SPLIT_LAZY_BAR2 != 0;
     static KD unsigned goal_a(long i) { return (unsigned)(NT * (WARP_FLAGS ? A_WARPS : 1) * (i / SLOTS + 1)); }
@@ -247,6 +257,7 @@ struct Split32 {
         named_barrier(1, A_THREADS);
         const float2 *tw1 = twa + t * 33;
         const long j0 = (long)kb * COLS + col;
+#pragma unroll(UNROLL_A)
         for (long i = 0; i < cnt; i++) {
             const long row = team + i * teams;
             unsigned seen = 0;
@@ -351,6 +362,7 @@ struct Split32 {
         const float2 *s1o = stage + (k1 * 32 - sbit) * COLS + col; // odd q:  row k1 32 + q - sbit
         const long j0 = (long)kb * COLS + col;
         unsigned phase = 0;
+#pragma unroll(UNROLL_A)
         for (long i = 0; i < cnt; i++) {
             unsigned seen = 0;
             if (!WARP_FLAGS && tid == 0 && i >= SLOTS) seen = flag_load(cntB + i % SLOTS); // consumed before the second barrier
@@ -514,6 +526,7 @@ struct Split32 {
             if (ZAHEAD < cnt) fetch_bins(ZAHEAD);
         }
         bool fetched = false;
+#pragma unroll(UNROLL_B)
         for (long i = 0; i < cnt; i++) {
             const long row = team + i * teams;
             const bool ahead = PRE && i + ZAHEAD < cnt;
