@@ -429,6 +429,10 @@ struct IoIrfft {
 #endif
 template <class IO> struct RowUnroll { static constexpr int value = 1; };
 template <> struct RowUnroll<IoStft> { static constexpr int value = KOFFT_STFT_UNROLL; };
+#ifndef KOFFT_STFT_MAG_UNROLL
+#define KOFFT_STFT_MAG_UNROLL 1
+#endif
+template <> struct RowUnroll<IoStftMag> { static constexpr int value = KOFFT_STFT_MAG_UNROLL; };
 #ifndef KOFFT_C2C_UNROLL
 #define KOFFT_C2C_UNROLL 1
 #endif
